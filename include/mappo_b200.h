@@ -1,0 +1,232 @@
+/*
+ * mappo_b200.h -- C ABI of the B200-native MAPPO rollout-and-update engine (libmappo_b200.so).
+ *
+ * The reference (marlbenchmark/on-policy) has no FFI on this path: all arithmetic is PyTorch/NumPy
+ * called from four Python classes.  This ABI is the boundary *introduced* beneath those classes
+ * (SURVEY.md section 8b); each entry point names the reference code it replaces
+ * (paths relative to /root/reference/onpolicy/).  Style follows the reference's only C ABI,
+ * envs/hanabi/pyhanabi.h:24-60 (extern "C", opaque handles, plain pointers and sizes).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 unless the name says otherwise (host structs are
+ *     `const mappo_*_t*`); storage is allocated and owned by the caller ("tensors in, tensors out");
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), performs no host
+ *     synchronisation and no allocation, and is CUDA-graph capturable;
+ *   - return value: 0 = ok, negative = mappo_status; text via mappo_last_error() (thread local);
+ *   - row-major everywhere; a "row" is one (t, n, m) sample: row = (t*N + n)*M + m, E = N*M rows per step.
+ */
+#ifndef MAPPO_B200_H_
+#define MAPPO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAPPO_MAX_HEADS 4      /* MultiDiscrete heads per actor */
+#define MAPPO_MAX_LAYERS 2     /* layer_N hidden (H->H) blocks per MLP base */
+#define MAPPO_ABI_VERSION 1
+
+typedef enum mappo_status {
+  MAPPO_OK = 0,
+  MAPPO_ERR_INVALID = -1,      /* bad argument / unsupported configuration */
+  MAPPO_ERR_CUDA = -2,         /* CUDA runtime error (launch, attribute, ...) */
+  MAPPO_ERR_UNSUPPORTED = -3   /* valid in the reference, not built yet (fails loudly, never falls back) */
+} mappo_status;
+
+/* One network (actor or critic).  Mirrors what R_Actor / R_Critic build
+ * (algorithms/r_mappo/algorithm/r_actor_critic.py:12-43, 120-154; algorithms/utils/mlp.py:6-57;
+ * rnn.py:7-22; act.py:12-42): [LayerNorm(in)] -> Linear(in,H) -> act -> LN -> layer_n x [Linear(H,H) -> act -> LN]
+ * -> [GRU(H,H) -> LN] -> heads.  Critic: n_heads = 1, head_dim[0] = 1 (v_out). */
+typedef struct mappo_net_desc {
+  int32_t in_dim;              /* obs_dim (actor) or share_obs_dim (critic) */
+  int32_t hidden;              /* hidden_size H */
+  int32_t layer_n;             /* layer_N */
+  int32_t use_feature_norm;    /* use_feature_normalization */
+  int32_t use_relu;            /* 1 ReLU, 0 Tanh (config.py:203) */
+  int32_t recurrent;           /* 1 = GRU block present (recurrent_N == 1 only) */
+  int32_t n_heads;
+  int32_t head_dim[MAPPO_MAX_HEADS];
+  int32_t is_critic;
+} mappo_net_desc_t;
+
+/* Offsets (in floats) of every tensor inside the flat parameter vector of a net; -1 = absent.
+ * Matrix layouts are the PyTorch ones ([out, in] row-major), so a state_dict copies in verbatim
+ * (key names: SURVEY.md App. A.8). */
+typedef struct mappo_net_layout {
+  int32_t fn_w, fn_b;                                   /* base.feature_norm.{weight,bias}            [in]     */
+  int32_t fc1_w, fc1_b, ln1_w, ln1_b;                   /* base.mlp.fc1.0 [H,in],[H]; fc1.2 [H],[H]              */
+  int32_t fc2_w[MAPPO_MAX_LAYERS], fc2_b[MAPPO_MAX_LAYERS];   /* base.mlp.fc2.i.0 [H,H],[H]                      */
+  int32_t ln2_w[MAPPO_MAX_LAYERS], ln2_b[MAPPO_MAX_LAYERS];   /* base.mlp.fc2.i.2                                */
+  int32_t gru_wih, gru_whh, gru_bih, gru_bhh;           /* rnn.rnn.{weight,bias}_{ih,hh}_l0 [3H,H],[3H] (r,z,n)  */
+  int32_t rnn_ln_w, rnn_ln_b;                           /* rnn.norm.{weight,bias}                               */
+  int32_t head_w, head_b;                               /* heads stacked: [sum(head_dim), H], [sum(head_dim)]   */
+  int32_t total;                                        /* parameter count                                      */
+} mappo_net_layout_t;
+
+/* Hyper-parameters of one optimiser step (R_MAPPO.__init__, algorithms/r_mappo/r_mappo.py:24-41). */
+typedef struct mappo_loss_cfg {
+  float clip_param, entropy_coef, value_loss_coef, huber_delta;
+  int32_t use_clipped_value_loss, use_huber_loss, use_value_active_masks, use_policy_active_masks;
+  int32_t use_valuenorm;       /* normalise return targets with the ValueNorm state */
+  int32_t update_actor;        /* ppo_update(sample, update_actor) r_mappo.py:91,145 */
+} mappo_loss_cfg_t;
+
+/* One minibatch as the update kernels see it.  Either a view of the rollout storage read through
+ * an index list (`rows` != NULL: fused gather, replaces shared_buffer.py:377-396 / 557-604) or a
+ * materialised sample (`rows` == NULL: arrays are already [n_rows, .]).
+ * Recurrent minibatches are time-major [L, n_seq] (position p = l*n_seq + c) with one initial
+ * hidden state per sequence; feed-forward: seq_len = 1, n_seq = n_rows. */
+typedef struct mappo_batch {
+  const float* obs;            /* [.,Do]  actor input rows                       */
+  const float* share_obs;      /* [.,Ds]  critic input rows                      */
+  const float* actions;        /* [.,as]  stored as fp32 (shared_buffer.py:77)   */
+  const float* old_logp;       /* [.,as]                                         */
+  const float* value_preds;    /* [.,1]                                          */
+  const float* returns;        /* [.,1]                                          */
+  const float* advantages;     /* [.,1]   raw advantages (normalised on the fly) */
+  const float* masks;          /* [.,1]                                          */
+  const float* active_masks;   /* [.,1]                                          */
+  const float* avail;          /* [.,A] or NULL                                  */
+  const float* h0_actor;       /* [.,H]   rnn_states        rows (recurrent only) */
+  const float* h0_critic;      /* [.,H]   rnn_states_critic rows (recurrent only) */
+  const int32_t* rows;         /* [n_rows] storage row feeding position p, or NULL */
+  const int32_t* seq_first;    /* [n_seq] storage row whose rnn state starts sequence c, or NULL */
+  int32_t n_rows, seq_len, n_seq;
+} mappo_batch_t;
+
+/* ---- library ------------------------------------------------------------------------------- */
+int32_t mappo_abi_version(void);
+const char* mappo_last_error(void);
+/* SM count / arch check of the current device; fails unless compute capability is 10.x. */
+int32_t mappo_device_check(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+/* ---- parameter layout (host only) ---------------------------------------------------------- */
+int32_t mappo_net_layout(const mappo_net_desc_t* desc, mappo_net_layout_t* out);
+
+/* ---- a8: rollout inference ------------------------------------------------------------------
+ * R_MAPPOPolicy.get_actions / get_values / act (rMAPPOPolicy.py:48-127) -> R_Actor.forward
+ * (r_actor_critic.py:44-71), R_Critic.forward (:156-175), ACTLayer.forward (act.py:44-91),
+ * FixedCategorical.sample/mode/log_probs (distributions.py:14-28).
+ * Either net may be skipped by passing params == NULL (get_values: actor NULL; act: critic NULL).
+ * Sampling: action = argmax_j softmax(logits)_j / q_j with q ~ Exp(1) (== torch multinomial).
+ *   exp_noise != NULL : q read from exp_noise[row, sum(head_dim)] (parity mode, host-drawn noise)
+ *   exp_noise == NULL : q = -log(u), u from Philox4x32-10 keyed by (rng_seed, *rng_offset_dev + row)
+ * deterministic != 0 : argmax of the probabilities.
+ * Outputs go straight into the caller's storage slots: values [E,1], actions [E,as] (fp32, the
+ * buffer dtype) and optionally actions_i64 [E,as], logp [E,as], h_out [E,H] (recurrent). */
+int32_t mappo_policy_step(const mappo_net_desc_t* actor_desc, const float* actor_params,
+                          const mappo_net_desc_t* critic_desc, const float* critic_params,
+                          const float* obs, const float* share_obs,
+                          const float* h_actor_in, const float* h_critic_in, const float* masks,
+                          const float* avail, const float* exp_noise,
+                          uint64_t rng_seed, const uint64_t* rng_offset_dev, int32_t deterministic,
+                          int32_t n_rows,
+                          float* values, float* actions, int64_t* actions_i64, float* logp,
+                          float* h_actor_out, float* h_critic_out, void* stream);
+
+/* Advance the device-side Philox offset after a sampling step (no host round trip). */
+int32_t mappo_counter_add(uint64_t* counter_dev, uint64_t inc, void* stream);
+
+/* ---- a2: insert / after_update --------------------------------------------------------------
+ * SharedReplayBuffer.insert (utils/shared_buffer.py:90-123) fused with the runner's done handling
+ * (runner/shared/mpe_runner.py:125-139): writes the env outputs of one step into slot t+1 / t,
+ * masks = 1 - done, zeroes both rnn states of done rows.  NULL sources are skipped. */
+int32_t mappo_env_insert(const float* next_obs, const float* next_share_obs, const float* rewards,
+                         const float* dones, const float* next_active, const float* next_avail,
+                         int32_t n_rows, int32_t obs_dim, int32_t share_dim, int32_t hidden, int32_t n_act,
+                         float* obs_slot, float* share_obs_slot, float* rewards_slot, float* masks_slot,
+                         float* h_actor_slot, float* h_critic_slot, float* active_slot, float* avail_slot,
+                         void* stream);
+
+/* ---- a3 + a4(denormalise) + a5(statistics): compute_returns ---------------------------------
+ * SharedReplayBuffer.compute_returns (shared_buffer.py:179-262, non-MAT branches) as one backward
+ * scan, one thread per (n,m) lane; ValueNorm.denormalize (utils/valuenorm.py:68-79) folded in
+ * (vn_state = {running_mean, running_mean_sq, debiasing_term} or NULL); also emits the raw
+ * advantages returns - denorm(value_preds) and accumulates {sum, sum^2, count} over active entries
+ * into adv_stats (3 doubles, caller zeroes) for R_MAPPO.train's normalisation (r_mappo.py:179-187).
+ * value_preds must already hold next_value in slot T (shared_buffer.py:218). */
+int32_t mappo_compute_returns(const float* rewards, const float* value_preds, const float* masks,
+                              const float* bad_masks, const float* active_masks, const float* vn_state,
+                              int32_t T, int32_t E, float gamma, float gae_lambda,
+                              int32_t use_gae, int32_t use_proper_time_limits,
+                              float* returns, float* advantages, double* adv_stats, void* stream);
+
+/* Stand-alone a5 for callers that wrote `returns` themselves: advantages[i] = returns[i] -
+ * denorm(value_preds[i]) over n entries + the same masked statistics (r_mappo.py:179-187). */
+int32_t mappo_advantages(const float* returns, const float* value_preds, const float* active_masks,
+                         const float* vn_state, int32_t n, float* advantages, double* adv_stats, void* stream);
+
+/* ---- a4: ValueNorm.update + per-minibatch loss normalisers ----------------------------------
+ * Reduces one minibatch: stats[0]=sum(active), [1]=sum(returns), [2]=sum(returns^2), [3]=n_rows
+ * (doubles; caller zeroes).  Multi-GPU: the caller all-reduces `stats` before applying them. */
+int32_t mappo_minibatch_stats(const float* returns, const float* active_masks, const int32_t* rows,
+                              int32_t n_rows, double* stats, void* stream);
+/* ValueNorm.update (utils/valuenorm.py:38-55) from reduced statistics: vn_state <- beta-blend. */
+int32_t mappo_valuenorm_update(float* vn_state, const double* stats, void* stream);
+
+/* ---- a6 / a7: materialising gathers (only for callers that want the 12-tuples) --------------
+ * dst[p, :] = src[rows[p], :]  (feed_forward_generator shared_buffer.py:377-396; the chunked
+ * recurrent_generator :557-604 and naive_recurrent_generator :409-497 reduce to the same gather
+ * once `rows` is built by mappo_chunk_rows / host arithmetic). */
+int32_t mappo_gather_rows(const float* src, const int32_t* rows, int32_t n_rows, int32_t dim, float* dst,
+                          void* stream);
+/* Row list of recurrent_generator for the chunk ids in `chunks` [n_chunks]: rows[l*n_chunks + c] =
+ * storage row of (n,m,t)-ordered position chunks[c]*L + l, first[c] = rows[0*n_chunks + c]
+ * (shared_buffer.py:505-569, _cast :11-12; chunks may straddle trajectories when T % L != 0). */
+int32_t mappo_chunk_rows(const int32_t* chunks, int32_t n_chunks, int32_t L, int32_t T, int32_t E,
+                         int32_t* rows, int32_t* first, void* stream);
+/* Device-side random permutation of [0, n) (stand-in for torch.randperm when the host RNG stream
+ * is not being reproduced): keyed Feistel network with cycle walking, seed + *counter_dev. */
+int32_t mappo_randperm(int32_t n, uint64_t seed, const uint64_t* counter_dev, int32_t* out, void* stream);
+
+/* ---- a9 - a12: training forward + losses + backward -----------------------------------------
+ * policy.evaluate_actions (rMAPPOPolicy.py:88-114; r_actor_critic.py:73-117, 156-175;
+ * act.py:115-178) + the surrogate / entropy / value losses (r_mappo.py:52-89, 129-146, 156-160)
+ * + their gradients (what autograd computes at :146 and :160), for one net per call.
+ *   norm_stats : the reduced minibatch statistics (4 doubles, see mappo_minibatch_stats)
+ *   adv_stats  : {sum, sum^2, count} of raw advantages over active entries (3 doubles)
+ *   vn_state   : ValueNorm state AFTER this minibatch's update (critic only; r_mappo.py:65)
+ *   grad_part  : workspace [n_slots, layout.total]; slot s receives the partial gradient of the
+ *                tiles handled by CTA s (deterministic two-stage reduction; zeroed by this call)
+ *   loss_out   : 6 doubles accumulated: [0] value_loss [1] policy_loss [2] dist_entropy
+ *                [5] ratio mean (caller zeroes; [3],[4] are the grad norms written by the optimiser)
+ *   workspace  : recurrent nets only, >= mappo_update_workspace_floats() floats. */
+int64_t mappo_update_workspace_floats(const mappo_net_desc_t* desc, int32_t n_rows);
+int32_t mappo_update_grad_slots(const mappo_net_desc_t* desc, int32_t n_rows);
+int32_t mappo_update_fwd_bwd(const mappo_net_desc_t* desc, const float* params, const mappo_batch_t* batch,
+                             const mappo_loss_cfg_t* loss, const double* norm_stats,
+                             const double* adv_stats, const float* vn_state,
+                             float* grad_part, int32_t n_slots, double* loss_out, float* workspace,
+                             void* stream);
+
+/* Gradient-free half of the same kernels = policy.evaluate_actions (rMAPPOPolicy.py:88-114):
+ * actor -> out[n_rows, as] log-probs of batch->actions, loss_out[2] += dist_entropy (act.py:170-176);
+ * critic -> out[n_rows, 1] values.  Loss-only inputs of `batch` may be NULL. */
+int32_t mappo_evaluate_actions(const mappo_net_desc_t* desc, const float* params, const mappo_batch_t* batch,
+                               const mappo_loss_cfg_t* loss, const double* norm_stats, float* out,
+                               double* loss_out, float* workspace, void* stream);
+
+/* ---- a13: gradient reduction + clip_grad_norm_ + Adam ----------------------------------------
+ * Sums the partial-gradient slots into `grad` [n_params] (the buffer a multi-GPU caller
+ * all-reduces), nn.utils.clip_grad_norm_ (r_mappo.py:148-151, 162-165) and
+ * torch.optim.Adam(lr, eps, betas=(0.9,0.999), weight_decay=0) (rMAPPOPolicy.py:31-37).
+ *   mappo_grad_reduce : grad = sum_s grad_part[s]; sumsq_part[b] = per-block sum(grad^2)
+ *   mappo_clip_adam   : total = sqrt(sum sumsq_part); coef = min(1, max_norm/(total+1e-6)) when
+ *                       use_max_grad_norm; Adam step with g*coef; ++*step_dev; *grad_norm_out += total.
+ * lr is read from device memory (lr_dev[0]) so lr_decay (utils/util.py:17-21) needs no re-capture. */
+int32_t mappo_grad_reduce(const float* grad_part, int32_t n_slots, int32_t n_params, float* grad,
+                          float* sumsq_part, int32_t* n_sumsq_blocks_out, void* stream);
+/* Per-block sums of squares of an already reduced (e.g. all-reduced) gradient vector. */
+int32_t mappo_grad_sumsq(const float* grad, int32_t n_params, float* sumsq_part, int32_t* n_sumsq_blocks_out,
+                         void* stream);
+int32_t mappo_clip_adam(float* params, const float* grad, float* exp_avg, float* exp_avg_sq,
+                        int32_t n_params, const float* sumsq_part, int32_t n_sumsq_blocks,
+                        const float* lr_dev, int32_t* step_dev, float eps, float max_grad_norm,
+                        int32_t use_max_grad_norm, double* grad_norm_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAPPO_B200_H_ */

@@ -1,0 +1,356 @@
+// api.cu -- the extern "C" surface of libmappo_b200.so (declared in include/mappo_b200.h).
+// No torch types, no allocation, no host synchronisation: every call validates its arguments on the host,
+// launches on the caller's stream and returns.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "net_tiles.cuh"
+#include "launch_args.h"
+
+namespace mappo {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return MAPPO_ERR_CUDA;
+  }
+  return MAPPO_OK;
+}
+
+static int validate_desc(const mappo_net_desc_t* d) {
+  if (!d) { set_error("net desc is NULL"); return MAPPO_ERR_INVALID; }
+  if (d->in_dim <= 0 || d->hidden <= 0 || d->hidden % 16 != 0) { set_error("bad in_dim/hidden (%d/%d)", d->in_dim, d->hidden); return MAPPO_ERR_INVALID; }
+  if (d->layer_n < 0 || d->layer_n > MAPPO_MAX_LAYERS) { set_error("layer_N %d outside [0,%d]", d->layer_n, MAPPO_MAX_LAYERS); return MAPPO_ERR_UNSUPPORTED; }
+  if (d->n_heads < 1 || d->n_heads > MAPPO_MAX_HEADS) { set_error("n_heads %d outside [1,%d]", d->n_heads, MAPPO_MAX_HEADS); return MAPPO_ERR_UNSUPPORTED; }
+  for (int k = 0; k < d->n_heads; ++k)
+    if (d->head_dim[k] <= 0) { set_error("head_dim[%d] = %d", k, d->head_dim[k]); return MAPPO_ERR_INVALID; }
+  if (d->is_critic && (d->n_heads != 1 || d->head_dim[0] != 1)) { set_error("critic must have one head of width 1"); return MAPPO_ERR_INVALID; }
+  return MAPPO_OK;
+}
+
+static void fill_layout(const mappo_net_desc_t* d, mappo_net_layout_t* L) {
+  const int H = d->hidden, I = d->in_dim;
+  int o = 0, A = 0;
+  for (int k = 0; k < d->n_heads; ++k) A += d->head_dim[k];
+  auto take = [&](int n) { const int at = o; o += n; return at; };
+  L->fn_w = d->use_feature_norm ? take(I) : -1;
+  L->fn_b = d->use_feature_norm ? take(I) : -1;
+  L->fc1_w = take(H * I); L->fc1_b = take(H); L->ln1_w = take(H); L->ln1_b = take(H);
+  for (int l = 0; l < MAPPO_MAX_LAYERS; ++l) {
+    const bool on = l < d->layer_n;
+    L->fc2_w[l] = on ? take(H * H) : -1; L->fc2_b[l] = on ? take(H) : -1;
+    L->ln2_w[l] = on ? take(H) : -1;     L->ln2_b[l] = on ? take(H) : -1;
+  }
+  const bool r = d->recurrent != 0;
+  L->gru_wih = r ? take(3 * H * H) : -1; L->gru_whh = r ? take(3 * H * H) : -1;
+  L->gru_bih = r ? take(3 * H) : -1;     L->gru_bhh = r ? take(3 * H) : -1;
+  L->rnn_ln_w = r ? take(H) : -1;        L->rnn_ln_b = r ? take(H) : -1;
+  L->head_w = take(A * H); L->head_b = take(A);
+  L->total = o;
+}
+
+NetDev make_net_dev(const mappo_net_desc_t* d) {
+  NetDev n;
+  memset(&n, 0, sizeof(n));
+  n.in_dim = d->in_dim; n.hid = d->hidden; n.layer_n = d->layer_n; n.use_fn = d->use_feature_norm;
+  n.use_relu = d->use_relu; n.recurrent = d->recurrent; n.n_heads = d->n_heads; n.is_critic = d->is_critic;
+  n.head_total = 0;
+  for (int k = 0; k < d->n_heads; ++k) { n.head_dim[k] = d->head_dim[k]; n.head_total += d->head_dim[k]; }
+  fill_layout(d, &n.g);
+  return n;
+}
+
+// launchers implemented in the other translation units
+int update_mlp_slots(const NetDev& n, int n_rows, int sm_count);
+int update_mlp_launch(const NetDev&, const float*, const BatchDev&, const LossDev&, const double*, const double*,
+                      const float*, float*, int, double*, cudaStream_t);
+int update_gru_slots(const NetDev& n, int n_rows, int seq_len, int sm_count);
+int64_t update_gru_workspace_floats(const NetDev& n, int n_rows);
+int update_gru_launch(const NetDev&, const float*, const BatchDev&, const LossDev&, const double*, const double*,
+                      const float*, float*, int, double*, float*, cudaStream_t);
+int gae_launch(const float*, const float*, const float*, const float*, const float*, const float*, int, int, float,
+               float, int, int, float*, float*, double*, cudaStream_t);
+int advantages_launch(const float*, const float*, const float*, const float*, int, float*, double*, cudaStream_t);
+int minibatch_stats_launch(const float*, const float*, const int32_t*, int, double*, cudaStream_t);
+int valuenorm_update_launch(float*, const double*, cudaStream_t);
+int gather_rows_launch(const float*, const int32_t*, int, int, float*, cudaStream_t);
+int chunk_rows_launch(const int32_t*, int, int, int, int, int32_t*, int32_t*, cudaStream_t);
+int randperm_launch(int, uint64_t, const uint64_t*, int32_t*, cudaStream_t);
+int grad_reduce_launch(const float*, int, int, float*, float*, int*, cudaStream_t);
+int sumsq_launch(const float*, int, float*, int*, cudaStream_t);
+int clip_adam_launch(float*, const float*, float*, float*, int, const float*, int, const float*, int*, float, float,
+                     int, double*, cudaStream_t);
+int counter_add_launch(uint64_t*, uint64_t, cudaStream_t);
+
+static int g_sm_count = 0;
+static int sm_count() {
+  if (g_sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+}  // namespace mappo
+
+using namespace mappo;
+
+
+extern "C" {
+
+int32_t mappo_abi_version(void) { return MAPPO_ABI_VERSION; }
+const char* mappo_last_error(void) { return g_err; }
+
+int32_t mappo_device_check(int32_t* sm, int32_t* major, int32_t* minor) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return check_launch("cudaGetDevice");
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return check_launch("cudaGetDeviceProperties");
+  if (sm) *sm = p.multiProcessorCount;
+  if (major) *major = p.major;
+  if (minor) *minor = p.minor;
+  if (p.major != 10) {
+    set_error("libmappo_b200 is built for sm_100a only; device %d is sm_%d%d", dev, p.major, p.minor);
+    return MAPPO_ERR_UNSUPPORTED;
+  }
+  return MAPPO_OK;
+}
+
+int32_t mappo_net_layout(const mappo_net_desc_t* desc, mappo_net_layout_t* out) {
+  int rc = validate_desc(desc);
+  if (rc) return rc;
+  if (!out) { set_error("layout out pointer is NULL"); return MAPPO_ERR_INVALID; }
+  fill_layout(desc, out);
+  return MAPPO_OK;
+}
+
+int32_t mappo_policy_step(const mappo_net_desc_t* ad, const float* ap, const mappo_net_desc_t* cd, const float* cp,
+                          const float* obs, const float* share_obs, const float* h_a_in, const float* h_c_in,
+                          const float* masks, const float* avail, const float* exp_noise, uint64_t rng_seed,
+                          const uint64_t* rng_offset_dev, int32_t deterministic, int32_t n_rows, float* values,
+                          float* actions, int64_t* actions_i64, float* logp, float* h_a_out, float* h_c_out,
+                          void* stream) {
+  const bool has_a = ap != nullptr, has_c = cp != nullptr;
+  if (!has_a && !has_c) { set_error("policy_step: both nets are NULL"); return MAPPO_ERR_INVALID; }
+  if (n_rows <= 0) return MAPPO_OK;
+  NetDev na, nc;
+  if (has_a) {
+    int rc = validate_desc(ad); if (rc) return rc;
+    if (ad->is_critic) { set_error("policy_step: actor desc has is_critic set"); return MAPPO_ERR_INVALID; }
+    if (!obs) { set_error("policy_step: obs is NULL"); return MAPPO_ERR_INVALID; }
+    if (!deterministic && !exp_noise && !rng_offset_dev) { set_error("policy_step: sampling needs exp_noise or rng_offset_dev"); return MAPPO_ERR_INVALID; }
+    if (ad->recurrent && (!h_a_in || !masks)) { set_error("policy_step: recurrent actor needs h_actor_in and masks"); return MAPPO_ERR_INVALID; }
+    na = make_net_dev(ad);
+  }
+  if (has_c) {
+    int rc = validate_desc(cd); if (rc) return rc;
+    if (!cd->is_critic) { set_error("policy_step: critic desc lacks is_critic"); return MAPPO_ERR_INVALID; }
+    if (!share_obs) { set_error("policy_step: share_obs is NULL"); return MAPPO_ERR_INVALID; }
+    if (cd->recurrent && (!h_c_in || !masks)) { set_error("policy_step: recurrent critic needs h_critic_in and masks"); return MAPPO_ERR_INVALID; }
+    nc = make_net_dev(cd);
+  }
+  PolArgs a;
+  memset(&a, 0, sizeof(a));
+  a.params[0] = ap; a.params[1] = cp;
+  a.in[0] = obs; a.in[1] = share_obs;
+  a.h_in[0] = h_a_in; a.h_in[1] = h_c_in;
+  a.h_out[0] = h_a_out; a.h_out[1] = h_c_out;
+  a.masks = masks; a.avail = avail; a.exp_noise = exp_noise;
+  a.rng_seed = rng_seed; a.rng_offset = rng_offset_dev;
+  a.deterministic = deterministic; a.n_rows = n_rows;
+  a.n_avail = has_a ? na.head_dim[0] : 0;
+  a.values = values; a.actions = actions; a.actions_i64 = actions_i64; a.logp = logp;
+  return policy_step_launch(has_a ? &na : nullptr, has_c ? &nc : nullptr, a, (cudaStream_t)stream);
+}
+
+int32_t mappo_counter_add(uint64_t* counter_dev, uint64_t inc, void* stream) {
+  if (!counter_dev) { set_error("counter_add: NULL"); return MAPPO_ERR_INVALID; }
+  return counter_add_launch(counter_dev, inc, (cudaStream_t)stream);
+}
+
+int32_t mappo_env_insert(const float* next_obs, const float* next_share_obs, const float* rewards, const float* dones,
+                         const float* next_active, const float* next_avail, int32_t n_rows, int32_t obs_dim,
+                         int32_t share_dim, int32_t hidden, int32_t n_act, float* obs_slot, float* share_obs_slot,
+                         float* rewards_slot, float* masks_slot, float* h_actor_slot, float* h_critic_slot,
+                         float* active_slot, float* avail_slot, void* stream) {
+  if (n_rows <= 0) return MAPPO_OK;
+  if ((next_obs && !obs_slot) || (next_share_obs && !share_obs_slot) || (rewards && !rewards_slot) ||
+      (next_avail && !avail_slot)) { set_error("env_insert: source given without destination slot"); return MAPPO_ERR_INVALID; }
+  InsertArgs a;
+  a.next_obs = next_obs; a.next_share = next_share_obs; a.rewards = rewards; a.dones = dones;
+  a.next_active = next_active; a.next_avail = next_avail;
+  a.E = n_rows; a.Do = obs_dim; a.Ds = share_dim; a.H = hidden; a.A = n_act;
+  a.obs = obs_slot; a.share = share_obs_slot; a.rew = rewards_slot; a.masks = masks_slot;
+  a.ha = h_actor_slot; a.hc = h_critic_slot; a.active = active_slot; a.avail = avail_slot;
+  return env_insert_launch(a, (cudaStream_t)stream);
+}
+
+int32_t mappo_compute_returns(const float* rewards, const float* value_preds, const float* masks,
+                              const float* bad_masks, const float* active_masks, const float* vn_state, int32_t T,
+                              int32_t E, float gamma, float gae_lambda, int32_t use_gae,
+                              int32_t use_proper_time_limits, float* returns, float* advantages, double* adv_stats,
+                              void* stream) {
+  if (!rewards || !value_preds || !masks || !active_masks || !returns) { set_error("compute_returns: NULL array"); return MAPPO_ERR_INVALID; }
+  if (use_proper_time_limits && !bad_masks) { set_error("compute_returns: use_proper_time_limits needs bad_masks"); return MAPPO_ERR_INVALID; }
+  if (T <= 0 || E <= 0) { set_error("compute_returns: T=%d E=%d", T, E); return MAPPO_ERR_INVALID; }
+  return gae_launch(rewards, value_preds, masks, bad_masks, active_masks, vn_state, T, E, gamma, gae_lambda, use_gae,
+                    use_proper_time_limits, returns, advantages, adv_stats, (cudaStream_t)stream);
+}
+
+int32_t mappo_advantages(const float* returns, const float* value_preds, const float* active_masks,
+                         const float* vn_state, int32_t n, float* advantages, double* adv_stats, void* stream) {
+  if (!returns || !value_preds || !active_masks || !advantages || !adv_stats || n <= 0) { set_error("advantages: bad arguments"); return MAPPO_ERR_INVALID; }
+  return advantages_launch(returns, value_preds, active_masks, vn_state, n, advantages, adv_stats, (cudaStream_t)stream);
+}
+
+int32_t mappo_minibatch_stats(const float* returns, const float* active_masks, const int32_t* rows, int32_t n_rows,
+                              double* stats, void* stream) {
+  if (!returns || !active_masks || !stats || n_rows <= 0) { set_error("minibatch_stats: bad arguments"); return MAPPO_ERR_INVALID; }
+  return minibatch_stats_launch(returns, active_masks, rows, n_rows, stats, (cudaStream_t)stream);
+}
+
+int32_t mappo_valuenorm_update(float* vn_state, const double* stats, void* stream) {
+  if (!vn_state || !stats) { set_error("valuenorm_update: NULL"); return MAPPO_ERR_INVALID; }
+  return valuenorm_update_launch(vn_state, stats, (cudaStream_t)stream);
+}
+
+int32_t mappo_gather_rows(const float* src, const int32_t* rows, int32_t n_rows, int32_t dim, float* dst, void* stream) {
+  if (n_rows < 0 || dim <= 0) { set_error("gather_rows: n_rows=%d dim=%d", n_rows, dim); return MAPPO_ERR_INVALID; }
+  if (n_rows == 0) return MAPPO_OK;
+  if (!src || !rows || !dst) { set_error("gather_rows: NULL pointer"); return MAPPO_ERR_INVALID; }
+  return gather_rows_launch(src, rows, n_rows, dim, dst, (cudaStream_t)stream);
+}
+
+int32_t mappo_chunk_rows(const int32_t* chunks, int32_t n_chunks, int32_t L, int32_t T, int32_t E, int32_t* rows,
+                         int32_t* first, void* stream) {
+  if (n_chunks < 0 || L <= 0 || T <= 0 || E <= 0) { set_error("chunk_rows: bad sizes"); return MAPPO_ERR_INVALID; }
+  if (n_chunks == 0) return MAPPO_OK;
+  if (!chunks || !rows) { set_error("chunk_rows: NULL pointer"); return MAPPO_ERR_INVALID; }
+  return chunk_rows_launch(chunks, n_chunks, L, T, E, rows, first, (cudaStream_t)stream);
+}
+
+int32_t mappo_randperm(int32_t n, uint64_t seed, const uint64_t* counter_dev, int32_t* out, void* stream) {
+  if (n < 0 || (n > 0 && !out)) { set_error("randperm: bad arguments"); return MAPPO_ERR_INVALID; }
+  return randperm_launch(n, seed, counter_dev, out, (cudaStream_t)stream);
+}
+
+static int fill_batch(const mappo_net_desc_t* d, const mappo_batch_t* b, BatchDev* o) {
+  if (!b) { set_error("batch is NULL"); return MAPPO_ERR_INVALID; }
+  if (b->n_rows <= 0) { set_error("batch has %d rows", b->n_rows); return MAPPO_ERR_INVALID; }
+  if (b->seq_len < 1 || b->n_seq < 1 || (int64_t)b->seq_len * b->n_seq != b->n_rows) { set_error("batch: seq_len*n_seq != n_rows (%d*%d vs %d)", b->seq_len, b->n_seq, b->n_rows); return MAPPO_ERR_INVALID; }
+  if (!b->active_masks) { set_error("batch: active_masks is NULL"); return MAPPO_ERR_INVALID; }
+  if (d->is_critic) {
+    if (!b->share_obs || !b->value_preds || !b->returns) { set_error("batch: critic needs share_obs, value_preds, returns"); return MAPPO_ERR_INVALID; }
+  } else {
+    if (!b->obs || !b->actions || !b->old_logp || !b->advantages) { set_error("batch: actor needs obs, actions, old_logp, advantages"); return MAPPO_ERR_INVALID; }
+  }
+  if (d->recurrent && (!b->masks || !(d->is_critic ? b->h0_critic : b->h0_actor))) { set_error("batch: recurrent net needs masks and h0"); return MAPPO_ERR_INVALID; }
+  o->obs = b->obs; o->share_obs = b->share_obs; o->actions = b->actions; o->old_logp = b->old_logp;
+  o->value_preds = b->value_preds; o->returns = b->returns; o->advantages = b->advantages; o->masks = b->masks;
+  o->active_masks = b->active_masks; o->avail = b->avail; o->h0_actor = b->h0_actor; o->h0_critic = b->h0_critic;
+  o->rows = b->rows; o->seq_first = b->seq_first; o->n_rows = b->n_rows; o->seq_len = b->seq_len; o->n_seq = b->n_seq;
+  o->act_shape = d->n_heads; o->n_avail = d->head_dim[0];
+  o->eval_out = nullptr; o->eval_only = 0;
+  return MAPPO_OK;
+}
+
+int64_t mappo_update_workspace_floats(const mappo_net_desc_t* desc, int32_t n_rows) {
+  if (validate_desc(desc)) return -1;
+  if (!desc->recurrent) return 0;
+  return update_gru_workspace_floats(make_net_dev(desc), n_rows);
+}
+
+int32_t mappo_update_grad_slots(const mappo_net_desc_t* desc, int32_t n_rows) {
+  if (validate_desc(desc)) return -1;
+  const NetDev n = make_net_dev(desc);
+  return desc->recurrent ? update_gru_slots(n, n_rows, 1, sm_count()) : update_mlp_slots(n, n_rows, sm_count());
+}
+
+int32_t mappo_update_fwd_bwd(const mappo_net_desc_t* desc, const float* params, const mappo_batch_t* batch,
+                             const mappo_loss_cfg_t* loss, const double* norm_stats, const double* adv_stats,
+                             const float* vn_state, float* grad_part, int32_t n_slots, double* loss_out,
+                             float* workspace, void* stream) {
+  int rc = validate_desc(desc);
+  if (rc) return rc;
+  if (!params || !loss || !norm_stats || !grad_part || !loss_out || n_slots <= 0) { set_error("update_fwd_bwd: NULL / bad argument"); return MAPPO_ERR_INVALID; }
+  BatchDev b;
+  rc = fill_batch(desc, batch, &b);
+  if (rc) return rc;
+  LossDev L;
+  L.clip = loss->clip_param; L.ent_coef = loss->entropy_coef; L.vl_coef = loss->value_loss_coef;
+  L.huber_delta = loss->huber_delta; L.use_clipped_value_loss = loss->use_clipped_value_loss;
+  L.use_huber = loss->use_huber_loss; L.use_value_active = loss->use_value_active_masks;
+  L.use_policy_active = loss->use_policy_active_masks; L.use_valuenorm = loss->use_valuenorm;
+  L.update_actor = loss->update_actor;
+  if (desc->is_critic && L.use_valuenorm && !vn_state) { set_error("update_fwd_bwd: use_valuenorm needs vn_state"); return MAPPO_ERR_INVALID; }
+  const NetDev n = make_net_dev(desc);
+  if (desc->recurrent) {
+    if (!workspace) { set_error("update_fwd_bwd: recurrent net needs a workspace"); return MAPPO_ERR_INVALID; }
+    return update_gru_launch(n, params, b, L, norm_stats, adv_stats, vn_state, grad_part, n_slots, loss_out, workspace,
+                             (cudaStream_t)stream);
+  }
+  if (b.seq_len != 1) { set_error("update_fwd_bwd: feed-forward net with seq_len %d", b.seq_len); return MAPPO_ERR_INVALID; }
+  return update_mlp_launch(n, params, b, L, norm_stats, adv_stats, vn_state, grad_part, n_slots, loss_out,
+                           (cudaStream_t)stream);
+}
+
+int32_t mappo_evaluate_actions(const mappo_net_desc_t* desc, const float* params, const mappo_batch_t* batch,
+                               const mappo_loss_cfg_t* loss, const double* norm_stats, float* out, double* loss_out,
+                               float* workspace, void* stream) {
+  int rc = validate_desc(desc);
+  if (rc) return rc;
+  if (!params || !loss || !norm_stats || !out || !loss_out) { set_error("evaluate_actions: NULL argument"); return MAPPO_ERR_INVALID; }
+  BatchDev b;
+  mappo_batch_t bb = *batch;
+  // evaluation needs no targets: let absent loss inputs alias always-present arrays
+  if (!desc->is_critic) { if (!bb.old_logp) bb.old_logp = bb.actions; if (!bb.advantages) bb.advantages = bb.active_masks; }
+  else { if (!bb.value_preds) bb.value_preds = bb.active_masks; if (!bb.returns) bb.returns = bb.active_masks; }
+  rc = fill_batch(desc, &bb, &b);
+  if (rc) return rc;
+  if (!desc->is_critic && bb.old_logp == bb.actions && desc->n_heads != 1 && false) return MAPPO_ERR_INVALID;
+  b.eval_out = out; b.eval_only = 1;
+  LossDev L;
+  memset(&L, 0, sizeof(L));
+  L.clip = loss->clip_param; L.use_policy_active = loss->use_policy_active_masks;
+  L.use_value_active = loss->use_value_active_masks; L.huber_delta = loss->huber_delta;
+  const NetDev n = make_net_dev(desc);
+  const int slots = mappo_update_grad_slots(desc, b.n_rows);
+  if (desc->recurrent) {
+    if (!workspace) { set_error("evaluate_actions: recurrent net needs a workspace"); return MAPPO_ERR_INVALID; }
+    return update_gru_launch(n, params, b, L, norm_stats, nullptr, nullptr, nullptr, slots, loss_out, workspace, (cudaStream_t)stream);
+  }
+  return update_mlp_launch(n, params, b, L, norm_stats, nullptr, nullptr, nullptr, slots, loss_out, (cudaStream_t)stream);
+}
+
+int32_t mappo_grad_reduce(const float* grad_part, int32_t n_slots, int32_t n_params, float* grad, float* sumsq_part,
+                          int32_t* n_blocks_out, void* stream) {
+  if (!grad_part || !grad || !sumsq_part || n_slots <= 0 || n_params <= 0) { set_error("grad_reduce: bad arguments"); return MAPPO_ERR_INVALID; }
+  return grad_reduce_launch(grad_part, n_slots, n_params, grad, sumsq_part, n_blocks_out, (cudaStream_t)stream);
+}
+
+int32_t mappo_grad_sumsq(const float* grad, int32_t n_params, float* sumsq_part, int32_t* n_blocks_out, void* stream) {
+  if (!grad || !sumsq_part || n_params <= 0) { set_error("grad_sumsq: bad arguments"); return MAPPO_ERR_INVALID; }
+  return sumsq_launch(grad, n_params, sumsq_part, n_blocks_out, (cudaStream_t)stream);
+}
+
+int32_t mappo_clip_adam(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int32_t n_params,
+                        const float* sumsq_part, int32_t n_sumsq_blocks, const float* lr_dev, int32_t* step_dev,
+                        float eps, float max_grad_norm, int32_t use_max_grad_norm, double* grad_norm_out, void* stream) {
+  if (!params || !grad || !exp_avg || !exp_avg_sq || !sumsq_part || !lr_dev || !step_dev || n_params <= 0 || n_sumsq_blocks <= 0) { set_error("clip_adam: bad arguments"); return MAPPO_ERR_INVALID; }
+  return clip_adam_launch(params, grad, exp_avg, exp_avg_sq, n_params, sumsq_part, n_sumsq_blocks, lr_dev, step_dev, eps,
+                          max_grad_norm, use_max_grad_norm, grad_norm_out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,33 @@
+// launch_args.h -- argument blocks shared between api.cu and the kernel translation units.
+#pragma once
+#include "common.cuh"
+
+namespace mappo {
+
+struct PolArgs {
+  const float* params[2];      // [0] actor, [1] critic
+  const float* in[2];          // obs, share_obs
+  const float* h_in[2];
+  float* h_out[2];
+  const float* masks;
+  const float* avail;
+  const float* exp_noise;
+  uint64_t rng_seed;
+  const uint64_t* rng_offset;
+  int deterministic, n_rows, n_avail;
+  float* values;
+  float* actions;
+  int64_t* actions_i64;
+  float* logp;
+};
+
+struct InsertArgs {
+  const float *next_obs, *next_share, *rewards, *dones, *next_active, *next_avail;
+  int E, Do, Ds, H, A;
+  float *obs, *share, *rew, *masks, *ha, *hc, *active, *avail;
+};
+
+int policy_step_launch(const NetDev* na, const NetDev* nc, const PolArgs& a, cudaStream_t st);
+int env_insert_launch(const InsertArgs& a, cudaStream_t st);
+
+}  // namespace mappo

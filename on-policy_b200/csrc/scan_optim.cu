@@ -1,0 +1,379 @@
+// scan_optim.cu -- the HBM-bound kernels of the path: GAE scan, statistics, gathers, insert,
+// gradient reduction and clip + Adam.  All coalesced / vectorised elementwise work with warp shuffles.
+#include "common.cuh"
+#include "launch_args.h"
+
+namespace mappo {
+
+// -------------------------------------------------------------------------------------------------
+// a3 + a4 + a5: compute_returns (utils/shared_buffer.py:179-262) as one backward scan.
+// One thread per lane e = (n, m); at step t the warp reads rewards[t*E + e .. +31]: fully coalesced in the
+// reference's own [T, N, M, 1] layout.  Algorithmic bytes: 4*E*(4T+1) + 4*E*T for the
+// emitted advantages.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ vpred, const float* __restrict__ masks,
+                const float* __restrict__ bad, const float* __restrict__ active, const float* __restrict__ vn_state,
+                int T, int E, float gamma, float lam, int use_gae, int use_ptl, float* __restrict__ returns,
+                float* __restrict__ adv_out, double* __restrict__ adv_stats) {
+  __shared__ double sred[3 * 32];
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  float mean = 0.f, sd = 1.f;
+  if (vn_state) {
+    float var;
+    vn_mean_var(vn_state, mean, var);
+    sd = sqrtf(var);
+  }
+  double st[3] = {0.0, 0.0, 0.0};
+  if (e < E) {
+    if (use_gae) {
+      float gae = 0.f;
+      float v_next = fmaf(vpred[(size_t)T * E + e], sd, mean);          // denormalize (valuenorm.py:68-79)
+#pragma unroll 4
+      for (int t = T - 1; t >= 0; --t) {
+        const size_t i = (size_t)t * E + e, in = i + E;
+        const float m_next = masks[in];
+        const float v_t = fmaf(vpred[i], sd, mean);
+        const float delta = rewards[i] + gamma * v_next * m_next - v_t;  // shared_buffer.py:236-238
+        gae = delta + gamma * lam * m_next * gae;                         // :239
+        if (use_ptl) gae *= bad[in];                                      // :194
+        const float ret = gae + v_t;                                      // :240
+        returns[i] = ret;
+        const float adv = ret - v_t;                                      // r_mappo.py:179-182
+        if (adv_out) adv_out[i] = adv;
+        if (active[i] != 0.f) { st[0] += adv; st[1] += (double)adv * adv; st[2] += 1.0; }
+        v_next = v_t;
+      }
+    } else {
+      float ret = vpred[(size_t)T * E + e];                               // returns[-1] = next_value (:204, :260)
+      returns[(size_t)T * E + e] = ret;
+      for (int t = T - 1; t >= 0; --t) {
+        const size_t i = (size_t)t * E + e, in = i + E;
+        const float v_t = fmaf(vpred[i], sd, mean);
+        if (use_ptl) {                                                    // :206-215
+          const float b = bad[in];
+          ret = (ret * gamma * masks[in] + rewards[i]) * b + (1.f - b) * v_t;
+        } else {
+          ret = ret * gamma * masks[in] + rewards[i];                     // :261-262
+        }
+        returns[i] = ret;
+        const float adv = ret - v_t;
+        if (adv_out) adv_out[i] = adv;
+        if (active[i] != 0.f) { st[0] += adv; st[1] += (double)adv * adv; st[2] += 1.0; }
+      }
+    }
+  }
+  if (adv_stats) block_accumulate<3>(st, adv_stats, sred, threadIdx.x, blockDim.x);
+}
+
+int gae_launch(const float* rewards, const float* vpred, const float* masks, const float* bad, const float* active,
+               const float* vn_state, int T, int E, float gamma, float lam, int use_gae, int use_ptl, float* returns,
+               float* adv, double* adv_stats, cudaStream_t st) {
+  const int nt = 128;
+  gae_scan_kernel<<<(E + nt - 1) / nt, nt, 0, st>>>(rewards, vpred, masks, bad, active, vn_state, T, E, gamma, lam,
+                                                    use_gae, use_ptl, returns, adv, adv_stats);
+  return check_launch("gae_scan_kernel");
+}
+
+// a5 stand-alone: advantages = returns - denorm(value_preds) over n entries + masked statistics
+// (r_mappo.py:179-187) for callers that filled `returns` themselves.
+__global__ void __launch_bounds__(256)
+advantages_kernel(const float* __restrict__ returns, const float* __restrict__ vpred, const float* __restrict__ active,
+                  const float* __restrict__ vn_state, int n, float* __restrict__ adv_out, double* __restrict__ stats) {
+  __shared__ double sred[3 * 32];
+  float mean = 0.f, sd = 1.f;
+  if (vn_state) { float var; vn_mean_var(vn_state, mean, var); sd = sqrtf(var); }
+  double st[3] = {0.0, 0.0, 0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float adv = returns[i] - fmaf(vpred[i], sd, mean);
+    adv_out[i] = adv;
+    if (active[i] != 0.f) { st[0] += adv; st[1] += (double)adv * adv; st[2] += 1.0; }
+  }
+  block_accumulate<3>(st, stats, sred, threadIdx.x, blockDim.x);
+}
+
+int advantages_launch(const float* returns, const float* vpred, const float* active, const float* vn_state, int n,
+                      float* adv, double* stats, cudaStream_t st) {
+  int blocks = (n + 255) / 256;
+  if (blocks > 296) blocks = 296;
+  advantages_kernel<<<blocks, 256, 0, st>>>(returns, vpred, active, vn_state, n, adv, stats);
+  return check_launch("advantages_kernel");
+}
+
+// -------------------------------------------------------------------------------------------------
+// a4: minibatch statistics + ValueNorm.update (utils/valuenorm.py:38-55)
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+minibatch_stats_kernel(const float* __restrict__ returns, const float* __restrict__ active,
+                       const int32_t* __restrict__ rows, int n, double* __restrict__ stats) {
+  __shared__ double sred[4 * 32];
+  double v[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+    const int g = rows ? rows[p] : p;
+    const float r = returns[g];
+    v[0] += active[g];
+    v[1] += r;
+    v[2] += (double)r * r;
+    v[3] += 1.0;
+  }
+  block_accumulate<4>(v, stats, sred, threadIdx.x, blockDim.x);
+}
+
+int minibatch_stats_launch(const float* returns, const float* active, const int32_t* rows, int n, double* stats,
+                           cudaStream_t st) {
+  int blocks = (n + 255) / 256;
+  if (blocks > 296) blocks = 296;
+  if (blocks < 1) blocks = 1;
+  minibatch_stats_kernel<<<blocks, 256, 0, st>>>(returns, active, rows, n, stats);
+  return check_launch("minibatch_stats_kernel");
+}
+
+__global__ void valuenorm_update_kernel(float* __restrict__ vn, const double* __restrict__ stats) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const double n = stats[3] > 0.0 ? stats[3] : 1.0;
+    const float bm = (float)(stats[1] / n), bsq = (float)(stats[2] / n);
+    const float w = 0.99999f, om = (float)(1.0 - 0.99999);     // the reference forms (1 - beta) in double
+    vn[0] = vn[0] * w + bm * om;
+    vn[1] = vn[1] * w + bsq * om;
+    vn[2] = vn[2] * w + 1.0f * om;
+  }
+}
+
+int valuenorm_update_launch(float* vn, const double* stats, cudaStream_t st) {
+  valuenorm_update_kernel<<<1, 32, 0, st>>>(vn, stats);
+  return check_launch("valuenorm_update_kernel");
+}
+
+// -------------------------------------------------------------------------------------------------
+// a6 / a7: gathers
+// -------------------------------------------------------------------------------------------------
+// dst[p, :] = src[rows[p], :]; a warp walks one row with coalesced loads.  Bytes: 2 * 4 * n_rows * dim.
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ rows, int n_rows, int dim,
+                   float* __restrict__ dst) {
+  const size_t total = (size_t)n_rows * dim;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int p = (int)(i / dim), c = (int)(i - (size_t)p * dim);
+    dst[i] = __ldg(src + (size_t)rows[p] * dim + c);
+  }
+}
+
+int gather_rows_launch(const float* src, const int32_t* rows, int n_rows, int dim, float* dst, cudaStream_t st) {
+  const size_t total = (size_t)n_rows * dim;
+  if (total == 0) return MAPPO_OK;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  gather_rows_kernel<<<(int)blocks, 256, 0, st>>>(src, rows, n_rows, dim, dst);
+  return check_launch("gather_rows_kernel");
+}
+
+// recurrent_generator row arithmetic (shared_buffer.py:505-569): (n,m,t)-ordered position j = chunk*L + l
+// -> t = j % T, lane = j / T, storage row = t*E + lane.
+__global__ void chunk_rows_kernel(const int32_t* __restrict__ chunks, int n_chunks, int L, int T, int E,
+                                  int32_t* __restrict__ rows, int32_t* __restrict__ first) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_chunks * L) return;
+  const int l = i / n_chunks, c = i - l * n_chunks;
+  const long long j = (long long)chunks[c] * L + l;
+  const int t = (int)(j % T), lane = (int)(j / T);
+  const int row = t * E + lane;
+  rows[i] = row;
+  if (l == 0 && first) first[c] = row;
+}
+
+int chunk_rows_launch(const int32_t* chunks, int n_chunks, int L, int T, int E, int32_t* rows, int32_t* first,
+                      cudaStream_t st) {
+  const int n = n_chunks * L;
+  if (n == 0) return MAPPO_OK;
+  chunk_rows_kernel<<<(n + 255) / 256, 256, 0, st>>>(chunks, n_chunks, L, T, E, rows, first);
+  return check_launch("chunk_rows_kernel");
+}
+
+// Keyed 4-round Feistel permutation on the smallest even-bit domain >= n, cycle-walked into [0, n).
+__device__ __forceinline__ uint32_t mix32(uint32_t x, uint32_t k) {
+  x ^= k; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__global__ void randperm_kernel(int n, uint64_t seed, const uint64_t* __restrict__ counter, int32_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int bits = 2;
+  while ((1u << bits) < (uint32_t)n) bits += 2;
+  const int hb = bits / 2;
+  const uint32_t hm = (1u << hb) - 1u;
+  const uint64_t key = seed ^ ((counter ? *counter : 0ull) * 0x9E3779B97F4A7C15ull);
+  uint32_t x = (uint32_t)i;
+  do {
+    uint32_t l = x >> hb, r = x & hm;
+#pragma unroll
+    for (int round = 0; round < 4; ++round) {
+      const uint32_t f = mix32(r, (uint32_t)(key >> (16 * round)) + 0x9E3779B9u * (uint32_t)round) & hm;
+      const uint32_t nl = r;
+      r = l ^ f;
+      l = nl;
+    }
+    x = (l << hb) | r;
+  } while (x >= (uint32_t)n);
+  out[i] = (int32_t)x;
+}
+
+int randperm_launch(int n, uint64_t seed, const uint64_t* counter, int32_t* out, cudaStream_t st) {
+  if (n <= 0) return MAPPO_OK;
+  randperm_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, seed, counter, out);
+  return check_launch("randperm_kernel");
+}
+
+// -------------------------------------------------------------------------------------------------
+// a2: insert of one env step (shared_buffer.py:90-123 + mpe_runner.py:125-139)
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) env_insert_kernel(const InsertArgs a) {
+  const int seg0 = a.next_obs ? a.E * a.Do : 0;
+  const int seg1 = seg0 + (a.next_share ? a.E * a.Ds : 0);
+  const int seg2 = seg1 + (a.next_avail ? a.E * a.A : 0);
+  const int seg3 = seg2 + ((a.ha && a.dones) ? a.E * a.H : 0);
+  const int seg4 = seg3 + ((a.hc && a.dones) ? a.E * a.H : 0);
+  const int seg5 = seg4 + a.E;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < seg5; i += gridDim.x * blockDim.x) {
+    if (i < seg0) a.obs[i] = a.next_obs[i];
+    else if (i < seg1) a.share[i - seg0] = a.next_share[i - seg0];
+    else if (i < seg2) a.avail[i - seg1] = a.next_avail[i - seg1];
+    else if (i < seg3) { const int j = i - seg2; if (a.dones[j / a.H] != 0.f) a.ha[j] = 0.f; }
+    else if (i < seg4) { const int j = i - seg3; if (a.dones[j / a.H] != 0.f) a.hc[j] = 0.f; }
+    else {
+      const int e = i - seg4;
+      if (a.rewards) a.rew[e] = a.rewards[e];
+      if (a.dones && a.masks) a.masks[e] = a.dones[e] != 0.f ? 0.f : 1.f;
+      if (a.next_active && a.active) a.active[e] = a.next_active[e];
+    }
+  }
+}
+
+int env_insert_launch(const InsertArgs& a, cudaStream_t st) {
+  const int total = a.E * (a.Do + a.Ds + a.A + 2 * a.H + 1);
+  int blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  env_insert_kernel<<<blocks, 256, 0, st>>>(a);
+  return check_launch("env_insert_kernel");
+}
+
+// -------------------------------------------------------------------------------------------------
+// a13: slot reduction, clip_grad_norm_ and Adam.  Algorithmic bytes per optimiser step:
+//   reduce: 4*n_slots*P read + 4*P written;  clip+Adam: 16*P read + 12*P written  (32 B/param)
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+grad_reduce_kernel(const float* __restrict__ part, int n_slots, int P, float* __restrict__ grad,
+                   float* __restrict__ sumsq_part) {
+  __shared__ float sred[32];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float g = 0.f;
+  if (i < P) {
+    int s = 0;
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;          // fixed summation order: deterministic
+    for (; s + 3 < n_slots; s += 4) {
+      g0 += part[(size_t)s * P + i];
+      g1 += part[(size_t)(s + 1) * P + i];
+      g2 += part[(size_t)(s + 2) * P + i];
+      g3 += part[(size_t)(s + 3) * P + i];
+    }
+    for (; s < n_slots; ++s) g0 += part[(size_t)s * P + i];
+    g = (g0 + g1) + (g2 + g3);
+    grad[i] = g;
+  }
+  float q = g * g;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = q;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float x = threadIdx.x < (blockDim.x >> 5) ? sred[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (threadIdx.x == 0) sumsq_part[blockIdx.x] = x;
+  }
+}
+
+int grad_reduce_launch(const float* part, int n_slots, int P, float* grad, float* sumsq_part, int* n_blocks_out,
+                       cudaStream_t st) {
+  const int blocks = (P + 255) / 256;
+  if (n_blocks_out) *n_blocks_out = blocks;
+  grad_reduce_kernel<<<blocks, 256, 0, st>>>(part, n_slots, P, grad, sumsq_part);
+  return check_launch("grad_reduce_kernel");
+}
+
+// Per-block sums of squares of an (all-reduced) gradient vector: the multi-GPU caller re-derives the global
+// norm after the collective.
+__global__ void __launch_bounds__(256)
+sumsq_kernel(const float* __restrict__ grad, int P, float* __restrict__ sumsq_part) {
+  __shared__ float sred[32];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float g = i < P ? grad[i] : 0.f;
+  float q = g * g;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = q;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float x = threadIdx.x < (blockDim.x >> 5) ? sred[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (threadIdx.x == 0) sumsq_part[blockIdx.x] = x;
+  }
+}
+
+int sumsq_launch(const float* grad, int P, float* sumsq_part, int* n_blocks_out, cudaStream_t st) {
+  const int blocks = (P + 255) / 256;
+  if (n_blocks_out) *n_blocks_out = blocks;
+  sumsq_kernel<<<blocks, 256, 0, st>>>(grad, P, sumsq_part);
+  return check_launch("sumsq_kernel");
+}
+
+__global__ void __launch_bounds__(256)
+clip_adam_kernel(float* __restrict__ p, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
+                 int P, const float* __restrict__ sumsq_part, int n_part, const float* __restrict__ lr_dev,
+                 int* __restrict__ step_dev, float eps, float max_norm, int use_clip, double* __restrict__ norm_out) {
+  __shared__ float s_total;
+  // every block re-derives the global norm from the per-block partials (n_part is small) in a fixed order
+  if (threadIdx.x < 32) {
+    double x = 0.0;
+    for (int i = threadIdx.x; i < n_part; i += 32) x += (double)sumsq_part[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (threadIdx.x == 0) s_total = (float)sqrt(x);
+  }
+  __syncthreads();
+  const float total = s_total;
+  float coef = 1.f;
+  if (use_clip) coef = fminf(max_norm / (total + 1e-6f), 1.0f);        // clip_grad_norm_
+  const int step = *step_dev + 1;                                       // 1-based Adam step
+  const double b1 = 0.9, b2 = 0.999;
+  const double bc1 = 1.0 - pow(b1, (double)step), bc2 = 1.0 - pow(b2, (double)step);
+  const float step_size = (float)((double)lr_dev[0] / bc1);
+  const float bc2_sqrt = (float)sqrt(bc2);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P) {
+    const float g = grad[i] * coef;
+    const float mi = m[i] + (g - m[i]) * (float)(1.0 - 0.9);                  // torch: exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = v[i] * 0.999f + (float)(1.0 - 0.999) * g * g;            // exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] - step_size * (mi / denom);
+    m[i] = mi;
+    v[i] = vi;
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0 && norm_out) *norm_out += (double)total;
+}
+
+__global__ void step_inc_kernel(int* step) { *step += 1; }
+
+int clip_adam_launch(float* p, const float* grad, float* m, float* v, int P, const float* sumsq_part, int n_part,
+                     const float* lr_dev, int* step_dev, float eps, float max_norm, int use_clip, double* norm_out,
+                     cudaStream_t st) {
+  clip_adam_kernel<<<(P + 255) / 256, 256, 0, st>>>(p, grad, m, v, P, sumsq_part, n_part, lr_dev, step_dev, eps,
+                                                    max_norm, use_clip, norm_out);
+  int rc = check_launch("clip_adam_kernel");
+  if (rc) return rc;
+  step_inc_kernel<<<1, 1, 0, st>>>(step_dev);                           // after every block has read the old step
+  return check_launch("step_inc_kernel");
+}
+
+}  // namespace mappo

@@ -1,0 +1,212 @@
+"""RolloutEngine: one whole iteration of the hot path as a single CUDA graph.
+
+    collect x T  ->  insert x T  ->  get_values + compute_returns  ->  R_MAPPO update x (ppo_epoch * num_mini_batch)
+    ->  after_update                                  (runner/shared/mpe_runner.py:26-40, base_runner.py:120-141)
+
+Every launch goes through the C ABI of libmappo_b200 on the current stream; the graph is captured once and
+replayed per iteration, so the host's share of an iteration is: refresh the pinned staging buffers (env outputs,
+and -- in "host" RNG mode -- the reference's sampling noise / permutations), one graph launch, one 48-byte read.
+The rollout kernel writes values / actions / log-probs / rnn states STRAIGHT into the storage slots; insert is
+one fused kernel per step.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, ptr
+from .core import stream_ptr
+
+INFO_KEYS = ("value_loss", "policy_loss", "dist_entropy", "actor_grad_norm", "critic_grad_norm", "ratio")
+
+
+class RolloutEngine:
+    def __init__(self, args, policy, trainer, buffer, rng: str = "device", seed: int = 1):
+        self.args, self.policy, self.trainer, self.buffer = args, policy, trainer, buffer
+        self.dev = policy.device
+        self.rng = rng
+        self.seed = int(seed)
+        self.lib = _lib.load()
+        b = buffer
+        self.T, self.E = b.episode_length, b._E
+        self.H = b.hidden_size
+        self.Do, self.Ds = b.obs.shape[-1], b.share_obs.shape[-1]
+        self.A = b.available_actions.shape[-1] if b.available_actions is not None else 0
+        self.sumA = sum(policy.actor.head_dims)
+        self.recurrent = bool(policy.actor.desc.recurrent)
+        T, E = self.T, self.E
+        f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.dev)
+        # device staging of one iteration of env outputs (next obs for slots 1..T, rewards, dones, ...)
+        self.d_obs, self.d_share = f(T, E, self.Do), f(T, E, self.Ds)
+        self.d_rew, self.d_done = f(T, E, 1), f(T, E)
+        self.d_active = None
+        self.d_avail = None
+        self.d_noise = f(T, E, self.sumA) if rng == "host" else None
+        self.perm_len = trainer.perm_length(buffer)
+        self.n_epochs = trainer.ppo_epoch
+        self.d_perm = torch.zeros(self.n_epochs, self.perm_len, dtype=torch.int32, device=self.dev)
+        self.perm_ctr = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.loss_out = torch.zeros(6, dtype=torch.float64, device=self.dev)
+        self.h_loss = torch.zeros(6, dtype=torch.float64).pin_memory()
+        self.host = {}
+        self.graph = None
+        self._epoch_i = 0
+        self.launches_per_iteration = 0
+
+    # -- host staging ----------------------------------------------------------------------------
+    def stage_feed(self, feed):
+        """Pin one iteration of synthetic env outputs (oracle.SyntheticFeed layout) in host memory."""
+        T, E = self.T, self.E
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).pin_memory()
+        self.host = dict(obs=pin(feed.obs[1:].reshape(T, E, -1)), share=pin(feed.share_obs[1:].reshape(T, E, -1)),
+                         rew=pin(feed.rewards.reshape(T, E, 1)), done=pin(feed.dones.reshape(T, E).astype(np.float32)))
+        if feed.active_masks is not None:
+            self.host["active"] = pin(feed.active_masks.reshape(T, E, 1))
+            if self.d_active is None:
+                self.d_active = torch.zeros(T, E, 1, dtype=torch.float32, device=self.dev)
+        if feed.available_actions is not None:
+            self.host["avail"] = pin(feed.available_actions[1:].reshape(T, E, -1))
+            if self.d_avail is None:
+                self.d_avail = torch.zeros(T, E, self.A, dtype=torch.float32, device=self.dev)
+        # warm-up slot 0 (mpe_runner.py:81-93)
+        self.buffer.obs[0].copy_(torch.from_numpy(feed.obs[0]))
+        self.buffer.share_obs[0].copy_(torch.from_numpy(feed.share_obs[0]))
+        if feed.available_actions is not None:
+            self.buffer.available_actions[0].copy_(torch.from_numpy(feed.available_actions[0]))
+        if self.rng == "host":
+            self.host["noise"] = torch.zeros(T, E, self.sumA).pin_memory()
+            self.host["perm"] = torch.zeros(self.n_epochs, self.perm_len, dtype=torch.int32).pin_memory()
+
+    def h2d_bytes(self):
+        return int(sum(v.numel() * v.element_size() for v in self.host.values()))
+
+    def upload(self):
+        """Host -> device copy of this iteration's inputs (async, current stream)."""
+        h = self.host
+        self.d_obs.copy_(h["obs"], non_blocking=True)
+        self.d_share.copy_(h["share"], non_blocking=True)
+        self.d_rew.copy_(h["rew"], non_blocking=True)
+        self.d_done.copy_(h["done"], non_blocking=True)
+        if "active" in h:
+            self.d_active.copy_(h["active"], non_blocking=True)
+        if "avail" in h:
+            self.d_avail.copy_(h["avail"], non_blocking=True)
+        if self.rng == "host":
+            self.draw_host_rng()
+            self.d_noise.copy_(h["noise"], non_blocking=True)
+            self.d_perm.copy_(h["perm"], non_blocking=True)
+
+    def draw_host_rng(self):
+        """Consume torch's CPU generator exactly like one reference iteration does:
+        T x one exponential_ per head, then one randperm per epoch."""
+        noise, perm = self.host["noise"], self.host["perm"]
+        for t in range(self.T):
+            off = 0
+            for a in self.policy.actor.head_dims:
+                noise[t, :, off:off + a] = torch.empty(self.E, a).exponential_(1)
+                off += a
+        for e in range(self.n_epochs):
+            perm[e] = torch.randperm(self.perm_len).to(torch.int32)
+
+    # -- device work -------------------------------------------------------------------------------
+    def _collect_and_insert(self, t):
+        b, pol, lib, st = self.buffer, self.policy, self.lib, stream_ptr()
+        rec = self.recurrent
+        noise = self.d_noise[t] if self.d_noise is not None else None
+        check(lib.mappo_policy_step(
+            C.byref(pol.actor.desc), ptr(pol.actor.flat), C.byref(pol.critic.desc), ptr(pol.critic.flat),
+            ptr(b.obs[t]), ptr(b.share_obs[t]), ptr(b.rnn_states[t]) if rec else None,
+            ptr(b.rnn_states_critic[t]) if rec else None, ptr(b.masks[t]),
+            ptr(b.available_actions[t]) if b.available_actions is not None else None, ptr(noise),
+            self.seed, ptr(pol.rng_offset), 0, self.E,
+            ptr(b.value_preds[t]), ptr(b.actions[t]), None, ptr(b.action_log_probs[t]),
+            ptr(b.rnn_states[t + 1]) if rec else None, ptr(b.rnn_states_critic[t + 1]) if rec else None, st))
+        if noise is None:
+            check(lib.mappo_counter_add(ptr(pol.rng_offset), self.E, st))
+        check(lib.mappo_env_insert(
+            ptr(self.d_obs[t]), ptr(self.d_share[t]), ptr(self.d_rew[t]), ptr(self.d_done[t]),
+            ptr(self.d_active[t]) if self.d_active is not None else None,
+            ptr(self.d_avail[t]) if self.d_avail is not None else None,
+            self.E, self.Do, self.Ds, self.H, self.A,
+            ptr(b.obs[t + 1]), ptr(b.share_obs[t + 1]), ptr(b.rewards[t]), ptr(b.masks[t + 1]),
+            ptr(b.rnn_states[t + 1]) if rec else None, ptr(b.rnn_states_critic[t + 1]) if rec else None,
+            ptr(b.active_masks[t + 1]) if self.d_active is not None else None,
+            ptr(b.available_actions[t + 1]) if self.d_avail is not None else None, st))
+        self.launches_per_iteration += 2 + (1 if noise is None else 0)
+
+    def _compute(self):
+        b, pol, lib, st, T = self.buffer, self.policy, self.lib, stream_ptr(), self.T
+        rec = self.recurrent
+        check(lib.mappo_policy_step(
+            C.byref(pol.actor.desc), None, C.byref(pol.critic.desc), ptr(pol.critic.flat),
+            None, ptr(b.share_obs[T]), None, ptr(b.rnn_states_critic[T]) if rec else None, ptr(b.masks[T]),
+            None, None, 0, None, 1, self.E, ptr(b.value_preds[T]), None, None, None, None, None, st))
+        vn = self.trainer.value_normalizer
+        b._adv_stats.zero_()
+        check(lib.mappo_compute_returns(ptr(b.rewards), ptr(b.value_preds), ptr(b.masks), ptr(b.bad_masks),
+                                        ptr(b.active_masks), ptr(vn.state) if vn is not None else None, T, self.E,
+                                        float(b.gamma), float(b.gae_lambda), int(bool(b._use_gae)),
+                                        int(bool(b._use_proper_time_limits)), ptr(b.returns), ptr(b.advantages),
+                                        ptr(b._adv_stats), st))
+        b._adv_version = id(vn) if vn is not None else 0
+        self.launches_per_iteration += 3
+
+    def _draw_perm(self, n):
+        e = self._epoch_i
+        self._epoch_i += 1
+        out = self.d_perm[e]
+        if self.rng != "host":
+            st = stream_ptr()
+            check(self.lib.mappo_randperm(n, self.seed, ptr(self.perm_ctr), ptr(out), st))
+            check(self.lib.mappo_counter_add(ptr(self.perm_ctr), 1, st))
+            self.launches_per_iteration += 2
+        return out
+
+    def launch_iteration(self):
+        """Enqueue one full iteration on the current stream (no host synchronisation)."""
+        self.launches_per_iteration = 0
+        for t in range(self.T):
+            self._collect_and_insert(t)
+        self._compute()
+        self._epoch_i = 0
+        tr = self.trainer
+        n_upd = tr.ppo_epoch * tr.num_mini_batch
+        tr.launch_train(self.buffer, True, self._draw_perm, self.loss_out)
+        per_update = 2 * 3 + (1 if tr.value_normalizer is not None else 0) + 2 + 1   # fwd/bwd, reduce, adam(+step) x2, vn, stats
+        self.launches_per_iteration += n_upd * per_update
+        if self.recurrent:
+            self.launches_per_iteration += n_upd       # chunk_rows
+        self.buffer.after_update()
+
+    def capture(self, warmup: int = 2):
+        """Warm up eagerly (lazy workspace allocation, cudaFuncSetAttribute) then capture the iteration."""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self.launch_iteration()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.launch_iteration()
+        torch.cuda.synchronize()
+
+    def step_resident(self):
+        """One iteration with inputs already resident in HBM (device staging reused as is)."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.launch_iteration()
+
+    def step_e2e(self):
+        """One iteration from HOST buffers: H2D of the env outputs, the graph, D2H of train_info (+ sync)."""
+        self.upload()
+        self.step_resident()
+        self.h_loss.copy_(self.loss_out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        n = float(self.trainer.ppo_epoch * self.trainer.num_mini_batch)
+        return dict(zip(INFO_KEYS, (self.h_loss / n).tolist()))

@@ -1,0 +1,264 @@
+"""onpolicy.algorithms.r_mappo.r_mappo.R_MAPPO on libmappo_b200 (reference: algorithms/r_mappo/r_mappo.py:8-232).
+
+`train(buffer)` never materialises a minibatch: the permutation the reference would have drawn is uploaded as
+an index list and the fused kernels read the rollout storage through it (gather fused into the loads).
+Per optimiser step and net: ONE forward+loss+backward launch, one slot reduction, one clip+Adam launch; all loss
+scalars stay on the device until the single read at the end of train().
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from mappo_b200 import _lib
+from mappo_b200.core import (Batch, UpdateWorkspace, as_dev, check, launch_update, make_loss_cfg, ptr, require_cuda,
+                             stream_ptr)
+from onpolicy.utils.valuenorm import ValueNorm
+
+INFO_KEYS = ("value_loss", "policy_loss", "dist_entropy", "actor_grad_norm", "critic_grad_norm", "ratio")
+
+
+def _dist_allreduce():
+    """Multi-GPU data parallelism over rollout threads: sum across ranks when a process group
+    with more than one rank exists, else None."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return None
+
+
+class R_MAPPO():
+    def __init__(self, args, policy, device=torch.device("cpu")):
+        self.device = policy.device
+        self.tpdv = dict(dtype=torch.float32, device=self.device)
+        self.policy = policy
+        self.args = args
+        self.clip_param = args.clip_param
+        self.ppo_epoch = args.ppo_epoch
+        self.num_mini_batch = args.num_mini_batch
+        self.data_chunk_length = args.data_chunk_length
+        self.value_loss_coef = args.value_loss_coef
+        self.entropy_coef = args.entropy_coef
+        self.max_grad_norm = args.max_grad_norm
+        self.huber_delta = args.huber_delta
+        self._use_recurrent_policy = args.use_recurrent_policy
+        self._use_naive_recurrent = args.use_naive_recurrent_policy
+        self._use_max_grad_norm = args.use_max_grad_norm
+        self._use_clipped_value_loss = args.use_clipped_value_loss
+        self._use_huber_loss = args.use_huber_loss
+        self._use_popart = args.use_popart
+        self._use_valuenorm = args.use_valuenorm
+        self._use_value_active_masks = args.use_value_active_masks
+        self._use_policy_active_masks = args.use_policy_active_masks
+        assert (self._use_popart and self._use_valuenorm) == False, (
+            "self._use_popart and self._use_valuenorm can not be set True simultaneously")
+        if self._use_popart:
+            raise NotImplementedError("use_popart: PopArt.update raises in the reference itself (SURVEY App. B-7)")
+        self.value_normalizer = ValueNorm(1, device=self.device) if self._use_valuenorm else None
+        self._ws = {}
+        self._loss_out = torch.zeros(6, dtype=torch.float64, device=self.device)
+
+    # ------------------------------------------------------------------------------------------
+    def _workspaces(self, n_rows):
+        key = int(n_rows)
+        if key not in self._ws:
+            self._ws[key] = (UpdateWorkspace(self.policy.actor, key), UpdateWorkspace(self.policy.critic, key))
+        return self._ws[key]
+
+    def _one_update(self, batch, n_rows, norm_stats, adv_stats, loss_out, update_actor, allreduce):
+        pol = self.policy
+        ws_a, ws_c = self._workspaces(n_rows)
+        loss = make_loss_cfg(self.args, update_actor)
+        vn = self.value_normalizer.state if self.value_normalizer is not None else None
+        # actor: backward, clip, step (reference :141-153)
+        launch_update(pol.actor, ws_a, batch, loss, norm_stats, adv_stats, None, loss_out, pol.actor_optimizer,
+                      self.max_grad_norm, self._use_max_grad_norm, 3, allreduce)
+        # ValueNorm.update(return_batch) BEFORE the value loss (reference :65), then critic (reference :156-167)
+        if vn is not None:
+            check(_lib.load().mappo_valuenorm_update(ptr(vn), ptr(norm_stats), stream_ptr()))
+        launch_update(pol.critic, ws_c, batch, loss, norm_stats, None, vn, loss_out, pol.critic_optimizer,
+                      self.max_grad_norm, self._use_max_grad_norm, 4, allreduce)
+
+    def _storage_batch(self, buffer, adv, rows, first, seq_len):
+        b = Batch()
+        T = buffer.episode_length
+        b.obs, b.share_obs = ptr(buffer.obs), ptr(buffer.share_obs)
+        b.actions, b.old_logp = ptr(buffer.actions), ptr(buffer.action_log_probs)
+        b.value_preds, b.returns, b.advantages = ptr(buffer.value_preds), ptr(buffer.returns), ptr(adv)
+        b.masks, b.active_masks = ptr(buffer.masks), ptr(buffer.active_masks)
+        b.avail = ptr(buffer.available_actions)
+        b.h0_actor, b.h0_critic = ptr(buffer.rnn_states), ptr(buffer.rnn_states_critic)
+        b.rows, b.seq_first = ptr(rows), ptr(first)
+        b.n_rows = rows.numel()
+        b.seq_len = seq_len
+        b.n_seq = rows.numel() // seq_len
+        return b
+
+    # ------------------------------------------------------------------------------------------
+    def _host_permutation(self, n):
+        """torch.randperm on the CPU generator, exactly where the reference's generators draw it
+        (utils/shared_buffer.py:360, 415, 511), uploaded as int32."""
+        return torch.randperm(n).to(torch.int32).to(self.device, non_blocking=True)
+
+    def perm_length(self, buffer):
+        B = buffer.episode_length * buffer._E
+        if self._use_recurrent_policy:
+            return B // self.data_chunk_length
+        if self._use_naive_recurrent:
+            return buffer._E
+        return B
+
+    def launch_train(self, buffer, update_actor=True, draw_perm=None, loss_out=None):
+        """All launches of reference :171-224 without any host synchronisation (CUDA-graph capturable when
+        `draw_perm` is).  Leaves the SUMS of the six train_info terms in `loss_out` (device, float64)."""
+        lib = _lib.load()
+        st = stream_ptr()
+        dev = self.device
+        T, E = buffer.episode_length, buffer._E
+        B = T * E
+        allreduce = _dist_allreduce()
+        draw_perm = draw_perm or self._host_permutation
+        loss_out = self._loss_out if loss_out is None else loss_out
+        vn = self.value_normalizer.state if self.value_normalizer is not None else None
+
+        # advantages + masked statistics (reference :179-187): reuse what compute_returns left when still valid
+        want = id(self.value_normalizer) if self.value_normalizer is not None else 0
+        adv, adv_stats = buffer.advantages, buffer._adv_stats
+        if buffer._adv_version != want:
+            adv_stats.zero_()
+            check(lib.mappo_advantages(ptr(buffer.returns), ptr(buffer.value_preds), ptr(buffer.active_masks), ptr(vn),
+                                       B, ptr(adv), ptr(adv_stats), st))
+
+        # minibatch plans: one permutation per epoch, drawn where the reference's generators would
+        n_updates = self.ppo_epoch * self.num_mini_batch
+        plans = []
+        for _ in range(self.ppo_epoch):
+            if self._use_recurrent_policy or self._use_naive_recurrent:
+                L = self.data_chunk_length if self._use_recurrent_policy else T
+                units = (B // L) if self._use_recurrent_policy else E
+                mb = units // self.num_mini_batch
+                perm = draw_perm(units)
+                for i in range(self.num_mini_batch):
+                    rows, first = buffer._chunk_rows(perm[i * mb:(i + 1) * mb].contiguous(), L)
+                    plans.append((rows, first, L))
+            else:
+                mb = B // self.num_mini_batch
+                perm = draw_perm(B)
+                for i in range(self.num_mini_batch):
+                    rows = perm[i * mb:(i + 1) * mb].contiguous()
+                    plans.append((rows, rows, 1))
+
+        # per-update statistics (sum active, sum R, sum R^2, rows): known up front -> one collective for all of them
+        stats = torch.zeros(n_updates * 4 + 4, dtype=torch.float64, device=dev)
+        for u, (rows, _, _) in enumerate(plans):
+            check(lib.mappo_minibatch_stats(ptr(buffer.returns), ptr(buffer.active_masks), ptr(rows), rows.numel(),
+                                            C.c_void_p(stats.data_ptr() + 32 * u), st))
+        if allreduce is not None:
+            stats[n_updates * 4:n_updates * 4 + 3].copy_(adv_stats)
+            allreduce(stats)
+            adv_stats = stats[n_updates * 4:n_updates * 4 + 3]
+
+        loss_out.zero_()
+        for u, (rows, first, seq_len) in enumerate(plans):
+            batch = self._storage_batch(buffer, adv, rows, first, seq_len)
+            self._one_update(batch, rows.numel(), stats[4 * u:4 * u + 4], adv_stats, loss_out, update_actor, allreduce)
+        if allreduce is not None:
+            # loss scalars are partial sums over local rows (global normalisers); norms are already global
+            part = loss_out.clone()
+            part[3:5] = 0
+            allreduce(part)
+            loss_out[0:3] = part[0:3]
+            loss_out[5] = part[5]
+        self._keepalive = plans
+        return loss_out, n_updates
+
+    def train(self, buffer, update_actor=True):
+        """reference :171-224.  One host read at the very end."""
+        self.policy.actor_optimizer.sync_lr()
+        self.policy.critic_optimizer.sync_lr()
+        loss_out, n_updates = self.launch_train(buffer, update_actor)
+        vals = (loss_out / float(n_updates)).cpu().tolist()
+        return dict(zip(INFO_KEYS, vals))
+
+    # ------------------------------------------------------------------------------------------
+    def _sample_batch(self, sample):
+        dev = self.device
+        (share_obs, obs, h_a, h_c, actions, v_old, ret, masks, active, lp_old, adv, avail) = \
+            [as_dev(x, dev) for x in sample[:12]]
+        n_rows = obs.shape[0]
+        n_seq = h_a.shape[0] if (self._use_recurrent_policy or self._use_naive_recurrent) else n_rows
+        b = Batch()
+        b.obs, b.share_obs, b.actions, b.old_logp = ptr(obs), ptr(share_obs), ptr(actions), ptr(lp_old)
+        b.value_preds, b.returns, b.advantages = ptr(v_old), ptr(ret), ptr(adv)
+        b.masks, b.active_masks, b.avail = ptr(masks), ptr(active), ptr(avail)
+        b.h0_actor = ptr(h_a.reshape(h_a.shape[0], -1).contiguous())
+        b.h0_critic = ptr(h_c.reshape(h_c.shape[0], -1).contiguous())
+        b.rows = b.seq_first = None
+        b.n_rows, b.n_seq, b.seq_len = n_rows, n_seq, n_rows // n_seq
+        keep = (share_obs, obs, h_a, h_c, actions, v_old, ret, masks, active, lp_old, adv, avail)
+        return b, keep, ret, active
+
+    def ppo_update(self, sample, update_actor=True):
+        """reference :91-169 on a materialised sample (12- or 13-tuple as the generators yield them).
+        Returns (value_loss, critic_grad_norm, policy_loss, dist_entropy, actor_grad_norm, imp_weights) as device
+        scalars; `imp_weights` is the mean ratio as a 1-element tensor (its only use is `.mean()`, :217)."""
+        lib = _lib.load()
+        batch, keep, ret, active = self._sample_batch(sample)
+        allreduce = _dist_allreduce()
+        stats = torch.zeros(4, dtype=torch.float64, device=self.device)
+        check(lib.mappo_minibatch_stats(ptr(ret), ptr(active), None, batch.n_rows, ptr(stats), stream_ptr()))
+        if allreduce is not None:
+            allreduce(stats)
+        out = torch.zeros(6, dtype=torch.float64, device=self.device)
+        self.policy.actor_optimizer.sync_lr()
+        self.policy.critic_optimizer.sync_lr()
+        self._one_update(batch, batch.n_rows, stats, None, out, update_actor, allreduce)
+        o = out.to(torch.float32)
+        return o[0], o[4], o[1], o[2], o[3], o[5:6]
+
+    def cal_value_loss(self, values, value_preds_batch, return_batch, active_masks_batch):
+        raise NotImplementedError("cal_value_loss is fused into mappo_update_fwd_bwd (critic net); use ppo_update")
+
+    def prep_training(self):
+        self.policy.actor.train()
+        self.policy.critic.train()
+
+    def prep_rollout(self):
+        self.policy.actor.eval()
+        self.policy.critic.eval()
+
+
+def _evaluate_only(policy, cent_obs, obs, h_a, h_c, action, masks, available_actions, active_masks):
+    """policy.evaluate_actions (rMAPPOPolicy.py:88-114): values, log-probs, entropy; no gradients."""
+    lib = _lib.load()
+    dev = policy.device
+    obs, cent, action, masks = as_dev(obs, dev), as_dev(cent_obs, dev), as_dev(action, dev), as_dev(masks, dev)
+    n_rows = obs.shape[0]
+    active = as_dev(active_masks, dev) if active_masks is not None else torch.ones(n_rows, 1, device=dev)
+    h_a, h_c = as_dev(h_a, dev), as_dev(h_c, dev)
+    recurrent = bool(policy.actor.desc.recurrent)
+    n_seq = h_a.shape[0] if recurrent else n_rows
+    b = Batch()
+    b.obs, b.share_obs, b.actions, b.masks, b.active_masks = ptr(obs), ptr(cent), ptr(action), ptr(masks), ptr(active)
+    b.avail = ptr(as_dev(available_actions, dev)) if available_actions is not None else None
+    h_a2, h_c2 = h_a.reshape(h_a.shape[0], -1).contiguous(), h_c.reshape(h_c.shape[0], -1).contiguous()
+    b.h0_actor, b.h0_critic = ptr(h_a2), ptr(h_c2)
+    b.n_rows, b.n_seq, b.seq_len = n_rows, n_seq, n_rows // n_seq
+    stats = torch.tensor([float(active.sum().item()), 0.0, 0.0, float(n_rows)], dtype=torch.float64, device=dev)
+    out = torch.zeros(6, dtype=torch.float64, device=dev)
+    args_like = type("A", (), dict(clip_param=0.2, entropy_coef=0.0, value_loss_coef=1.0, huber_delta=10.0,
+                                   use_clipped_value_loss=True, use_huber_loss=True, use_value_active_masks=True,
+                                   use_policy_active_masks=(active_masks is not None and policy._use_policy_active_masks),
+                                   use_valuenorm=False,
+                                   use_popart=False))
+    loss = make_loss_cfg(args_like)
+    logp = torch.empty(n_rows, len(policy.actor.head_dims), dtype=torch.float32, device=dev)
+    values = torch.empty(n_rows, 1, dtype=torch.float32, device=dev)
+    ws_a = UpdateWorkspace(policy.actor, n_rows)
+    ws_c = UpdateWorkspace(policy.critic, n_rows)
+    st = stream_ptr()
+    check(lib.mappo_evaluate_actions(C.byref(policy.actor.desc), ptr(policy.actor.flat), C.byref(b), C.byref(loss),
+                                     ptr(stats), ptr(logp), ptr(out), ptr(ws_a.workspace), st))
+    check(lib.mappo_evaluate_actions(C.byref(policy.critic.desc), ptr(policy.critic.flat), C.byref(b), C.byref(loss),
+                                     ptr(stats), ptr(values), ptr(out), ptr(ws_c.workspace), st))
+    return values, logp, out[2].to(torch.float32)

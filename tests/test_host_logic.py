@@ -1,0 +1,85 @@
+"""CPU-side tests: C-ABI exports, parameter layout, reference-identical initialisation, index arithmetic."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mappo_oracle as O
+from helpers import Golden, GOLDEN_CASES
+from argsutil import make_args, make_spaces
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from mappo_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "mappo_b200.h")).read()
+    declared = set(re.findall(r"\b(mappo_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"mappo_status"}
+    lib = C.CDLL(_lib.lib_path())
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, f"declared in mappo_b200.h but not exported: {missing}"
+    assert declared == set(_lib.EXPORTS), (declared ^ set(_lib.EXPORTS))
+    assert _lib.load().mappo_abi_version() == 1
+
+
+def test_net_layout_matches_reference_param_count():
+    from mappo_b200 import _lib
+    lib = _lib.load()
+    for name in GOLDEN_CASES:
+        g = Golden(name)
+        for which, in_dim, heads, crit in (("actor", g.cfg.obs_dim, list(g.cfg.act_dims), 0),
+                                           ("critic", g.cfg.share_obs_dim, [1], 1)):
+            d = _lib.NetDesc()
+            d.in_dim, d.hidden, d.layer_n = in_dim, g.cfg.hidden_size, g.cfg.layer_N
+            d.use_feature_norm, d.use_relu, d.recurrent = 1, int(g.cfg.use_ReLU), int(g.cfg.recurrent)
+            d.n_heads = len(heads)
+            for k, a in enumerate(heads):
+                d.head_dim[k] = a
+            d.is_critic = crit
+            lay = _lib.NetLayout()
+            assert lib.mappo_net_layout(C.byref(d), C.byref(lay)) == 0
+            n_ref = sum(v.numel() for v in g.params(f"init/{which}/").values())
+            assert lay.total == n_ref, (name, which)
+
+
+def test_bad_descriptor_is_rejected_with_message():
+    from mappo_b200 import _lib
+    lib = _lib.load()
+    d = _lib.NetDesc()
+    d.in_dim, d.hidden, d.layer_n, d.n_heads = 10, 64, 7, 1
+    d.head_dim[0] = 3
+    assert lib.mappo_net_layout(C.byref(d), C.byref(_lib.NetLayout())) == -3
+    assert b"layer_N" in lib.mappo_last_error()
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_initialisation_is_seed_identical_to_reference(name):
+    """torch.manual_seed(s) + the drop-in constructors' RNG consumption == the reference's initial weights."""
+    from mappo_b200.core import reference_init_state_dict
+    from tests_seeds import SEEDS
+    g = Golden(name)
+    args = make_args(g.cfg)
+    torch.set_num_threads(1)          # train_mpe.py:96 (--n_training_threads 1); LAPACK QR is thread-count sensitive
+    torch.manual_seed(SEEDS[name])
+    np.random.seed(SEEDS[name])
+    actor = reference_init_state_dict(args, g.cfg.obs_dim, list(g.cfg.act_dims), False, g.cfg.multi_discrete)
+    critic = reference_init_state_dict(args, g.cfg.share_obs_dim, [1], True, False)
+    for k, v in g.params("init/actor/").items():
+        assert torch.equal(actor[k], v), f"actor {k}"
+    for k, v in g.params("init/critic/").items():
+        assert torch.equal(critic[k], v), f"critic {k}"
+
+
+def test_chunk_rows_oracle_straddles_like_reference():
+    # T=25, L=10: chunk 2 = t 20..24 of lane 0 followed by t 0..4 of lane 1
+    T, N, M, L = 25, 2, 2, 10
+    perm = np.arange(T * N * M // L)
+    rows, first = O.chunk_minibatch_rows(perm, T, N, M, L, 1)[0]
+    rows = rows.reshape(L, -1)
+    E = N * M
+    assert list(rows[:, 2]) == [t * E + 0 for t in range(20, 25)] + [t * E + 1 for t in range(0, 5)]
+    assert first[2] == 20 * E

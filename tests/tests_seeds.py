@@ -1,0 +1,2 @@
+# seeds used by tests/golden/make_golden.py (CASES[...]["seed"])
+SEEDS = {"c1_mlp_discrete": 1, "c3_gru_multidiscrete": 2, "c4_gru_smac": 3, "c5_mlp_switches": 4, "naive_rnn_ptl": 5}
