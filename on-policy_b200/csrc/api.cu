@@ -73,7 +73,8 @@ NetDev make_net_dev(const mappo_net_desc_t* d) {
 // launchers implemented in the other translation units
 int update_mlp_slots(const NetDev& n, int n_rows, int sm_count);
 int update_mlp_launch(const NetDev&, const float*, const BatchDev&, const LossDev&, const double*, const double*,
-                      const float*, float*, int, double*, cudaStream_t);
+                      const float*, float*, int, double*, cudaStream_t, float* feat_out = nullptr,
+                      const float* dfeat_in = nullptr);
 int update_gru_slots(const NetDev& n, int n_rows, int seq_len, int sm_count);
 int64_t update_gru_workspace_floats(const NetDev& n, int n_rows);
 int update_gru_launch(const NetDev&, const float*, const BatchDev&, const LossDev&, const double*, const double*,

@@ -139,7 +139,7 @@ __device__ __forceinline__ float act_bwd(float a, int act) {
 template <int TR, int NJ>
 __device__ __forceinline__ void tile_mm(const float* __restrict__ inT, int K, const float* __restrict__ W, int sn,
                                         int sk, int N, const float* __restrict__ bias, int act,
-                                        float* __restrict__ outT, int tid) {
+                                        float* __restrict__ outT, int tid, bool accumulate = false) {
   constexpr int LD = Tile<TR>::LD;
   const int tx = tid & 15, r0 = (tid >> 4) * 4;
   float acc[4][NJ];
@@ -169,6 +169,10 @@ __device__ __forceinline__ void tile_mm(const float* __restrict__ inT, int K, co
     const int n = tx + 16 * j;
     if (n < N) {
       const float b = bias ? bias[n] : 0.f;
+      if (accumulate) {
+        const float4 e = *reinterpret_cast<const float4*>(outT + n * LD + r0);
+        acc[0][j] += e.x; acc[1][j] += e.y; acc[2][j] += e.z; acc[3][j] += e.w;
+      }
       float4 o;
       o.x = act_fwd(acc[0][j] + b, act);
       o.y = act_fwd(acc[1][j] + b, act);

@@ -139,4 +139,125 @@ __device__ __forceinline__ void head_lse(const float* __restrict__ lgT, int off,
   lse = mx + logf(se);
 }
 
+// ---------------------------------------------------------------------------------------------
+// loss math of one row (r_mappo.py:52-89, 129-146; act.py:147-176), shared by the MLP and GRU kernels
+// ---------------------------------------------------------------------------------------------
+struct LossConsts {
+  double sum_active, n_rows_d;
+  float adv_mean, adv_inv, vmean, vrs;
+};
+
+__device__ __forceinline__ LossConsts make_loss_consts(const NetDev& n, const LossDev& L,
+                                                       const double* __restrict__ norm_stats,
+                                                       const double* __restrict__ adv_stats,
+                                                       const float* __restrict__ vn_state) {
+  LossConsts c;
+  c.sum_active = norm_stats[0];
+  c.n_rows_d = norm_stats[3];
+  c.adv_mean = 0.f;
+  c.adv_inv = 1.f;
+  if (adv_stats) {                               // r_mappo.py:183-187: stats over active entries, applied to all
+    const double cnt = adv_stats[2] > 0.0 ? adv_stats[2] : 1.0;
+    const double m = adv_stats[0] / cnt;
+    double var = adv_stats[1] / cnt - m * m;
+    if (var < 0.0) var = 0.0;
+    c.adv_mean = (float)m;
+    c.adv_inv = (float)(1.0 / (sqrt(var) + 1e-5));
+  }
+  float vmean = 0.f, vvar = 1.f;
+  if (n.is_critic && L.use_valuenorm && vn_state) vn_mean_var(vn_state, vmean, vvar);
+  c.vmean = vmean;
+  c.vrs = 1.0f / sqrtf(vvar);
+  return c;
+}
+
+// Row r of the logits tile lgT (storage row gr, minibatch position p): accumulates the loss terms into acc
+// (critic: [0] value_loss; actor: [0] policy_loss, [1] entropy, [2] sum of ratios) and overwrites the logits /
+// value with d(loss)/d(logit | value).
+template <int LD>
+__device__ __forceinline__ void row_loss(const NetDev& n, const BatchDev& b, const LossDev& L, const LossConsts& c,
+                                         float* __restrict__ lgT, int r, int gr, int p, double (&acc)[3]) {
+  const int Atot = n.head_total;
+  if (gr < 0) {
+    for (int j = 0; j < Atot; ++j) lgT[j * LD + r] = 0.f;
+    return;
+  }
+  if (n.is_critic) {
+    const float act = b.active_masks[gr];
+    const float w = L.use_value_active ? (float)((double)act / c.sum_active) : (float)(1.0 / c.n_rows_d);
+    const float v = lgT[r], vo = b.value_preds[gr];
+    const float ret = b.returns[gr];
+    const float target = L.use_valuenorm ? (ret - c.vmean) * c.vrs : ret;       // valuenorm.py:57-66
+    const float d = v - vo;
+    const float vclip = vo + fminf(fmaxf(d, -L.clip), L.clip);                  // r_mappo.py:62-63
+    const float eo = target - v, ec = target - vclip;
+    float lo, lcl, go, gc;                                                      // loss and d loss / d e
+    if (L.use_huber) {                                                          // utils/util.py:23-26
+      const float dl = L.huber_delta;
+      lo = fabsf(eo) <= dl ? 0.5f * eo * eo : dl * (fabsf(eo) - 0.5f * dl);
+      lcl = fabsf(ec) <= dl ? 0.5f * ec * ec : dl * (fabsf(ec) - 0.5f * dl);
+      go = fabsf(eo) <= dl ? eo : copysignf(dl, eo);
+      gc = fabsf(ec) <= dl ? ec : copysignf(dl, ec);
+    } else {                                                                    // utils/util.py:28-29
+      lo = 0.5f * eo * eo; lcl = 0.5f * ec * ec; go = eo; gc = ec;
+    }
+    float l = lo, dv = -go;
+    if (L.use_clipped_value_loss) {               // torch.max: gradient to the larger, 1/2 - 1/2 on ties
+      const float inclip = (d >= -L.clip && d <= L.clip) ? 1.f : 0.f;
+      const float dvc = -gc * inclip;
+      if (lcl > lo) { l = lcl; dv = dvc; }
+      else if (lcl == lo) { dv = 0.5f * (dv + dvc); }
+    }
+    acc[0] += (double)(l * w);
+    if (b.eval_out) b.eval_out[p] = v;
+    lgT[r] = dv * w * L.vl_coef;
+    return;
+  }
+  const float act = b.active_masks[gr];
+  const float w = L.use_policy_active ? (float)((double)act / c.sum_active) : (float)(1.0 / c.n_rows_d);
+  const float adv = (b.advantages[gr] - c.adv_mean) * c.adv_inv;
+  const float* av = (b.avail && n.n_heads == 1) ? b.avail + (size_t)gr * b.n_avail : nullptr;
+  const float inv_heads = 1.0f / (float)n.n_heads;
+  int off = 0;
+  for (int k = 0; k < n.n_heads; ++k) {
+    const int A = n.head_dim[k];
+    float lse;
+    head_lse<LD>(lgT, off, A, r, av, lse);
+    const int a = (int)b.actions[(size_t)gr * b.act_shape + k];
+    float ent = 0.f, lp_a = 0.f;
+    for (int j = 0; j < A; ++j) {
+      float lgt = lgT[(off + j) * LD + r];
+      if (av && av[j] == 0.f) lgt = -1e10f;
+      const float lp = lgt - lse;
+      const float pj = expf(lp);
+      ent = fmaf(-pj, lp, ent);
+      if (j == a) lp_a = lp;
+    }
+    if (b.eval_out) b.eval_out[(size_t)p * b.act_shape + k] = lp_a;
+    const float ratio = expf(lp_a - b.old_logp[(size_t)gr * b.act_shape + k]);        // r_mappo.py:129
+    const float s1 = ratio * adv;
+    const float s2 = fminf(fmaxf(ratio, 1.f - L.clip), 1.f + L.clip) * adv;
+    const float mn = fminf(s1, s2);
+    // d min(s1, s2) / d ratio with torch.min / clamp tie semantics
+    const bool inr = ratio >= 1.f - L.clip && ratio <= 1.f + L.clip;
+    const float dm = inr ? adv : (s1 < s2 ? adv : (s1 == s2 ? 0.5f * adv : 0.f));
+    const float dlp = -w * dm * ratio;
+    const float dH = -L.ent_coef * w * inv_heads;
+    acc[0] += (double)(-mn * w);
+    acc[1] += (double)(ent * w * inv_heads);
+    acc[2] += (double)ratio;
+    for (int j = 0; j < A; ++j) {
+      float lgt = lgT[(off + j) * LD + r];
+      const bool masked = av && av[j] == 0.f;
+      if (masked) lgt = -1e10f;
+      const float lp = lgt - lse;
+      const float pj = expf(lp);
+      float dl = dlp * ((j == a ? 1.f : 0.f) - pj) + dH * (-pj * (lp + ent));
+      if (masked || !L.update_actor) dl = 0.f;
+      lgT[(off + j) * LD + r] = dl;
+    }
+    off += A;
+  }
+}
+
 }  // namespace mappo

@@ -36,8 +36,8 @@ __host__ __device__ inline PolSmem make_pol_smem(const NetDev& n, const SmemW& s
   u.s0 = o; o += hT;
   u.s1 = o; o += hT;
   u.h = o; o += n.recurrent ? hT : 0;
-  u.gi = o; o += n.recurrent ? 3 * hT : 0;
-  u.gh = o; o += n.recurrent ? 3 * hT : 0;
+  u.gi = o; o += n.recurrent ? 3 * hT : 0;      // r, z pre-activations (input + hidden parts summed), n input part
+  u.gh = o; o += n.recurrent ? hT : 0;          // n hidden part (multiplied by r before the tanh)
   const int lg = ((n.head_total + 3) & ~3) * LD;     // logits share the gi area when recurrent
   if (!n.recurrent) { u.gi = o; o += lg; }
   u.stats = o; o += 2 * (kMaxLayers + 3) * kPolTR;
@@ -91,20 +91,23 @@ policy_step_kernel(const NetDev na, const NetDev nc, const PolArgs a, int first_
     }
     __syncthreads();
 #pragma unroll 1
-    for (int gate = 0; gate < 3; ++gate) {
+    for (int gate = 0; gate < 3; ++gate)
       tile_mm<TR, NJH>(feat, H, sW + s.wih + gate * H * s.ldh, s.ldh, 1, H, sW + s.bih + gate * H, ACT_NONE,
                        gi + gate * H * LD, tid);
+    // each thread re-reads exactly the outputs it wrote, so no barrier is needed before accumulating
+#pragma unroll 1
+    for (int gate = 0; gate < 2; ++gate)
       tile_mm<TR, NJH>(hT, H, sW + s.whh + gate * H * s.ldh, s.ldh, 1, H, sW + s.bhh + gate * H, ACT_NONE,
-                       gh + gate * H * LD, tid);
-    }
+                       gi + gate * H * LD, tid, true);
+    tile_mm<TR, NJH>(hT, H, sW + s.whh + 2 * H * s.ldh, s.ldh, 1, H, sW + s.bhh + 2 * H, ACT_NONE, gh, tid);
     __syncthreads();
     float* hn = smem + u.s0;                   // new hidden state (pre-LN)
     for (int i = tid; i < TR * H; i += NT) {
       const int c = i / TR, r = i - c * TR;
       const int o = c * LD + r;
-      const float rg = sigmoidf_(gi[o] + gh[o]);
-      const float zg = sigmoidf_(gi[H * LD + o] + gh[H * LD + o]);
-      const float ng = tanhf(gi[2 * H * LD + o] + rg * gh[2 * H * LD + o]);
+      const float rg = sigmoidf_(gi[o]);
+      const float zg = sigmoidf_(gi[H * LD + o]);
+      const float ng = tanhf(gi[2 * H * LD + o] + rg * gh[o]);
       hn[o] = (1.f - zg) * ng + zg * hT[o];
     }
     __syncthreads();

@@ -240,7 +240,8 @@ def _evaluate_only(policy, cent_obs, obs, h_a, h_c, action, masks, available_act
     n_seq = h_a.shape[0] if recurrent else n_rows
     b = Batch()
     b.obs, b.share_obs, b.actions, b.masks, b.active_masks = ptr(obs), ptr(cent), ptr(action), ptr(masks), ptr(active)
-    b.avail = ptr(as_dev(available_actions, dev)) if available_actions is not None else None
+    avail_d = as_dev(available_actions, dev) if available_actions is not None else None     # keep alive
+    b.avail = ptr(avail_d)
     h_a2, h_c2 = h_a.reshape(h_a.shape[0], -1).contiguous(), h_c.reshape(h_c.shape[0], -1).contiguous()
     b.h0_actor, b.h0_critic = ptr(h_a2), ptr(h_c2)
     b.n_rows, b.n_seq, b.seq_len = n_rows, n_seq, n_rows // n_seq

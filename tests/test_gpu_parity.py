@@ -109,7 +109,7 @@ def test_rollout_and_returns_match_reference(name):
     assert_close(adv, g.get("it0/advantages"), 1e-3, 2e-4, "advantages")
 
 
-@pytest.mark.parametrize("name", MLP_CASES)
+@pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_first_update_gradients_match_reference(name, monkeypatch):
     g = Golden(name)
     cfg = g.cfg
@@ -123,7 +123,7 @@ def test_first_update_gradients_match_reference(name, monkeypatch):
     # parameters stay put and the gradient buffers hold the first update's (clipped) gradients
     perms = g.get("it0/perms")
     monkeypatch.setattr(torch, "randperm", FakeRandperm([perms[0]]))
-    if cfg.num_mini_batch == 1:
+    if cfg.num_mini_batch == 1 and not cfg.recurrent:
         trainer.train(buf)
         grads_a = {k: v.cpu().numpy() for k, v in policy.actor.named_grads().items()}
         grads_c = {k: v.cpu().numpy() for k, v in policy.critic.named_grads().items()}
@@ -133,7 +133,13 @@ def test_first_update_gradients_match_reference(name, monkeypatch):
         mean = st[0] / st[2]
         std = np.sqrt(max(st[1] / st[2] - mean * mean, 0.0))
         adv = (buf.advantages - float(mean)) / (float(std) + 1e-5)
-        sample = next(buf.feed_forward_generator(adv, cfg.num_mini_batch))
+        if cfg.use_recurrent_policy:
+            gen = buf.recurrent_generator(adv, cfg.num_mini_batch, cfg.data_chunk_length)
+        elif cfg.use_naive_recurrent_policy:
+            gen = buf.naive_recurrent_generator(adv, cfg.num_mini_batch)
+        else:
+            gen = buf.feed_forward_generator(adv, cfg.num_mini_batch)
+        sample = next(gen)
         trainer.ppo_update(sample)
         grads_a = {k: v.cpu().numpy() for k, v in policy.actor.named_grads().items()}
         grads_c = {k: v.cpu().numpy() for k, v in policy.critic.named_grads().items()}
@@ -147,7 +153,7 @@ def test_first_update_gradients_match_reference(name, monkeypatch):
         assert_close(v * coef_c, g.get(f"it0/first_update/critic/{k}"), 2e-3, 2e-6, f"critic grad {k}")
 
 
-@pytest.mark.parametrize("name", MLP_CASES)
+@pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_full_iterations_match_reference(name, monkeypatch):
     g = Golden(name)
     cfg = g.cfg
@@ -321,3 +327,51 @@ def test_evaluate_actions_matches_oracle(name):
     assert_close(logp.cpu().numpy(), lp_ref.numpy(), 1e-4, 1e-5, "log-probs")
     assert_close(values.cpu().numpy(), v_ref.numpy(), 1e-4, 1e-5, "values")
     assert_close(float(ent), float(ent_ref), 1e-4, 1e-6, "entropy")
+
+
+def test_graft_smoke_runs():
+    import __graft_entry__ as ge
+    ge.smoke()
+
+
+def test_engine_graph_replay_matches_eager_train():
+    """The captured CUDA graph of one iteration reproduces the eager drop-in classes (same noise / permutations)."""
+    from mappo_b200.engine import RolloutEngine
+    g = Golden("c1_mlp_discrete")
+    cfg = g.cfg
+    feed = g.feed(0)
+    # eager, through the public classes
+    args, policy, trainer, buf = build(cfg, g)
+    warm(buf, feed)
+    collect_and_returns(cfg, policy, trainer, buf, feed, g.get("it0/noise"))
+    import torch as _t
+    real = _t.randperm
+    _t.randperm = FakeRandperm(g.get("it0/perms"))
+    try:
+        info_eager = trainer.train(buf)
+    finally:
+        _t.randperm = real
+    # graph, through the engine (host RNG mode so the very same noise / permutations are staged)
+    args2, policy2, trainer2, buf2 = build(cfg, g)
+    eng = RolloutEngine(args2, policy2, trainer2, buf2, rng="host", seed=1)
+    eng.stage_feed(feed)
+    eng.draw_host_rng = lambda: None
+    eng.host["noise"].copy_(_t.from_numpy(g.get("it0/noise")))
+    eng.host["perm"].copy_(_t.from_numpy(g.get("it0/perms").astype(np.int32)))
+    eng.upload()
+    _t.cuda.synchronize()
+    # capture WITHOUT warm-up iterations mutating the weights: snapshot, capture, restore, replay once
+    snap = [policy2.actor.flat.clone(), policy2.critic.flat.clone(), trainer2.value_normalizer.state.clone()]
+    eng.capture(warmup=1)
+    policy2.actor.flat.copy_(snap[0]); policy2.critic.flat.copy_(snap[1]); trainer2.value_normalizer.state.copy_(snap[2])
+    for opt in (policy2.actor_optimizer, policy2.critic_optimizer):
+        opt.exp_avg.zero_(); opt.exp_avg_sq.zero_(); opt.step_dev.zero_()
+    for a in (buf2.rnn_states, buf2.rnn_states_critic):
+        a.zero_()
+    buf2.masks.fill_(1.0); buf2.active_masks.fill_(1.0)
+    warm(buf2, feed)
+    info_graph = eng.step_e2e()
+    for k in INFO_KEYS:
+        assert_close(info_graph[k], info_eager[k], 1e-5, 1e-7, f"graph vs eager train_info[{k}]")
+    assert_close(policy2.actor.flat.cpu().numpy(), policy.actor.flat.cpu().numpy(), 1e-5, 1e-7, "actor weights")
+    assert_close(policy2.critic.flat.cpu().numpy(), policy.critic.flat.cpu().numpy(), 1e-5, 1e-7, "critic weights")
