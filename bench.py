@@ -67,18 +67,30 @@ def cpu_iteration_rate(cfg, iters, warmup, threads):
     return cfg.n_rollout_threads * cfg.episode_length * len(times) / tot, tot / len(times)
 
 
+def best_cpu_threads(cfg):
+    """The port (like the reference) is many tiny torch ops: more intra-op threads is not faster.  Probe a few
+    counts with two iterations each and keep the fastest ("all the host threads it can USE")."""
+    cores = os.cpu_count() or 1
+    best, best_rate = 1, 0.0
+    for th in sorted({1, min(4, cores), min(8, cores), min(16, cores)}):
+        rate, _ = cpu_iteration_rate(cfg, 2, 1, th)
+        if rate > best_rate:
+            best, best_rate = th, rate
+    return best
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cfg = c2_config()
-    cores = os.cpu_count() or 1
+    cores = best_cpu_threads(cfg)
     rate, per = cpu_iteration_rate(cfg, a.steps, a.warmup, cores)
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_dict(cfg, 1),
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{a.steps} full iterations of c2 (3200 env steps each) on {cores} torch threads; "
+                             "sample": f"{a.steps} full iterations of c2 (3200 env steps each) on {cores} torch threads (fastest of 1/4/8/16 on a {os.cpu_count()}-core host); "
                                        "oracle/mappo_oracle.py = CPU restatement of the reference (Python reference "
                                        "cannot travel to the GPU box)"},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -169,14 +181,16 @@ def run_gpu(a):
     eng.stage_feed(feed)
     eng.upload()
     torch.cuda.synchronize()
-    graph_ok = True
+    graph_ok = not a.eager
     try:
+        if a.eager:
+            raise RuntimeError("--eager")
         eng.capture(warmup=2)
     except Exception as e:                                 # e.g. a collective that refuses capture: run eagerly
         graph_ok = False
         eng.graph = None
         torch.cuda.synchronize()
-        if rank == 0:
+        if rank == 0 and not a.eager:
             print(f"[bench] CUDA graph capture unavailable ({type(e).__name__}: {e}); running eager", file=sys.stderr)
 
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)       # > 126 MB L2
@@ -234,7 +248,7 @@ def run_gpu(a):
         peak_tf = float(peaks.get("bf16_tflops", 1590.0))
         fa, fc = update_flops(cfg)
         ach = (fa + fc) / 2 / (kt["avg_ms"] * 1e-3) / 1e12
-        cores = os.cpu_count() or 1
+        cores = best_cpu_threads(cfg) if world == 1 and a.cpu_iters > 0 else 1
         cpu_rate, cpu_per = cpu_iteration_rate(cfg, a.cpu_iters, 2, cores) if world == 1 and a.cpu_iters > 0 else (None, None)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
                 "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -254,7 +268,8 @@ def run_gpu(a):
         if cpu_rate is not None:
             line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{a.cpu_iters} full c2 iterations (3200 env steps each) of "
-                                              f"oracle/mappo_oracle.py on {cores} torch threads, {cpu_per*1e3:.0f} ms each"}
+                                              f"oracle/mappo_oracle.py on {cores} torch threads (fastest of 1/4/8/16; host has {os.cpu_count()} cores), "
+                                              f"{cpu_per*1e3:.0f} ms each"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -297,6 +312,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--eager", action="store_true", help="no CUDA graph (for per-kernel profiling under ncu)")
     ap.add_argument("--cpu-iters", type=int, default=30, help="oracle iterations for cpu_baseline (rank 0, N=1)")
     a = ap.parse_args()
     if a.impl == "reference":

@@ -71,7 +71,11 @@ typedef struct mappo_loss_cfg {
   int32_t use_clipped_value_loss, use_huber_loss, use_value_active_masks, use_policy_active_masks;
   int32_t use_valuenorm;       /* normalise return targets with the ValueNorm state */
   int32_t update_actor;        /* ppo_update(sample, update_actor) r_mappo.py:91,145 */
+  int32_t gemm_mode;           /* MAPPO_GEMM_FP32 (exact fp32 FFMA tiles) or MAPPO_GEMM_TF32 (tcgen05 tensor cores) */
 } mappo_loss_cfg_t;
+
+#define MAPPO_GEMM_FP32 0
+#define MAPPO_GEMM_TF32 1
 
 /* One minibatch as the update kernels see it.  Either a view of the rollout storage read through
  * an index list (`rows` != NULL: fused gather, replaces shared_buffer.py:377-396 / 557-604) or a
@@ -192,9 +196,12 @@ int32_t mappo_randperm(int32_t n, uint64_t seed, const uint64_t* counter_dev, in
  *                tiles handled by CTA s (deterministic two-stage reduction; zeroed by this call)
  *   loss_out   : 6 doubles accumulated: [0] value_loss [1] policy_loss [2] dist_entropy
  *                [5] ratio mean (caller zeroes; [3],[4] are the grad norms written by the optimiser)
- *   workspace  : recurrent nets only, >= mappo_update_workspace_floats() floats. */
-int64_t mappo_update_workspace_floats(const mappo_net_desc_t* desc, int32_t n_rows);
-int32_t mappo_update_grad_slots(const mappo_net_desc_t* desc, int32_t n_rows);
+ *   workspace  : >= mappo_update_workspace_floats() floats, 16-byte aligned (recurrent nets: activations between
+ *                the four launches; MAPPO_GEMM_TF32: the folded tf32 weight image fetched by TMA). */
+int64_t mappo_update_workspace_floats(const mappo_net_desc_t* desc, int32_t n_rows, int32_t gemm_mode);
+int32_t mappo_update_grad_slots(const mappo_net_desc_t* desc, int32_t n_rows, int32_t gemm_mode);
+/* 1 if the tcgen05 (MAPPO_GEMM_TF32) kernels cover this net, else 0 (callers then use MAPPO_GEMM_FP32). */
+int32_t mappo_tf32_supported(const mappo_net_desc_t* desc);
 int32_t mappo_update_fwd_bwd(const mappo_net_desc_t* desc, const float* params, const mappo_batch_t* batch,
                              const mappo_loss_cfg_t* loss, const double* norm_stats,
                              const double* adv_stats, const float* vn_state,

@@ -75,6 +75,11 @@ int update_mlp_slots(const NetDev& n, int n_rows, int sm_count);
 int update_mlp_launch(const NetDev&, const float*, const BatchDev&, const LossDev&, const double*, const double*,
                       const float*, float*, int, double*, cudaStream_t, float* feat_out = nullptr,
                       const float* dfeat_in = nullptr);
+bool update_mlp_tc_supported(const NetDev& n);
+int64_t update_mlp_tc_workspace_floats(const NetDev& n);
+int update_mlp_tc_slots(const NetDev& n, int n_rows, int sm_count);
+int update_mlp_tc_launch(const NetDev&, const float*, const BatchDev&, const LossDev&, const double*, const double*,
+                         const float*, float*, int, double*, float*, cudaStream_t);
 int update_gru_slots(const NetDev& n, int n_rows, int seq_len, int sm_count);
 int64_t update_gru_workspace_floats(const NetDev& n, int n_rows);
 int update_gru_launch(const NetDev&, const float*, const BatchDev&, const LossDev&, const double*, const double*,
@@ -267,16 +272,24 @@ static int fill_batch(const mappo_net_desc_t* d, const mappo_batch_t* b, BatchDe
   return MAPPO_OK;
 }
 
-int64_t mappo_update_workspace_floats(const mappo_net_desc_t* desc, int32_t n_rows) {
-  if (validate_desc(desc)) return -1;
-  if (!desc->recurrent) return 0;
-  return update_gru_workspace_floats(make_net_dev(desc), n_rows);
+int32_t mappo_tf32_supported(const mappo_net_desc_t* desc) {
+  if (validate_desc(desc)) return 0;
+  return update_mlp_tc_supported(make_net_dev(desc)) ? 1 : 0;
 }
 
-int32_t mappo_update_grad_slots(const mappo_net_desc_t* desc, int32_t n_rows) {
+int64_t mappo_update_workspace_floats(const mappo_net_desc_t* desc, int32_t n_rows, int32_t gemm_mode) {
   if (validate_desc(desc)) return -1;
   const NetDev n = make_net_dev(desc);
-  return desc->recurrent ? update_gru_slots(n, n_rows, 1, sm_count()) : update_mlp_slots(n, n_rows, sm_count());
+  if (desc->recurrent) return update_gru_workspace_floats(n, n_rows);
+  return (gemm_mode == MAPPO_GEMM_TF32 && update_mlp_tc_supported(n)) ? update_mlp_tc_workspace_floats(n) : 0;
+}
+
+int32_t mappo_update_grad_slots(const mappo_net_desc_t* desc, int32_t n_rows, int32_t gemm_mode) {
+  if (validate_desc(desc)) return -1;
+  const NetDev n = make_net_dev(desc);
+  if (desc->recurrent) return update_gru_slots(n, n_rows, 1, sm_count());
+  if (gemm_mode == MAPPO_GEMM_TF32 && update_mlp_tc_supported(n)) return update_mlp_tc_slots(n, n_rows, sm_count());
+  return update_mlp_slots(n, n_rows, sm_count());
 }
 
 int32_t mappo_update_fwd_bwd(const mappo_net_desc_t* desc, const float* params, const mappo_batch_t* batch,
@@ -303,6 +316,11 @@ int32_t mappo_update_fwd_bwd(const mappo_net_desc_t* desc, const float* params, 
                              (cudaStream_t)stream);
   }
   if (b.seq_len != 1) { set_error("update_fwd_bwd: feed-forward net with seq_len %d", b.seq_len); return MAPPO_ERR_INVALID; }
+  if (loss->gemm_mode == MAPPO_GEMM_TF32) {
+    if (!update_mlp_tc_supported(n)) { set_error("update_fwd_bwd: MAPPO_GEMM_TF32 is not built for this net (hidden 64, layer_N 1, in_dim <= 63, MLP only)"); return MAPPO_ERR_UNSUPPORTED; }
+    return update_mlp_tc_launch(n, params, b, L, norm_stats, adv_stats, vn_state, grad_part, n_slots, loss_out, workspace,
+                                (cudaStream_t)stream);
+  }
   return update_mlp_launch(n, params, b, L, norm_stats, adv_stats, vn_state, grad_part, n_slots, loss_out,
                            (cudaStream_t)stream);
 }
@@ -327,7 +345,7 @@ int32_t mappo_evaluate_actions(const mappo_net_desc_t* desc, const float* params
   L.clip = loss->clip_param; L.use_policy_active = loss->use_policy_active_masks;
   L.use_value_active = loss->use_value_active_masks; L.huber_delta = loss->huber_delta;
   const NetDev n = make_net_dev(desc);
-  const int slots = mappo_update_grad_slots(desc, b.n_rows);
+  const int slots = mappo_update_grad_slots(desc, b.n_rows, MAPPO_GEMM_FP32);
   if (desc->recurrent) {
     if (!workspace) { set_error("evaluate_actions: recurrent net needs a workspace"); return MAPPO_ERR_INVALID; }
     return update_gru_launch(n, params, b, L, norm_stats, nullptr, nullptr, nullptr, slots, loss_out, workspace, (cudaStream_t)stream);

@@ -72,15 +72,24 @@ __host__ __device__ inline SmemW make_smem_w(const NetDev& n, bool with_gru) {
 // ---------------------------------------------------------------------------------------------
 // weight image: global flat params -> shared memory
 // ---------------------------------------------------------------------------------------------
+// Weights go global -> shared with cp.async (LDGSTS): no register staging, every copy of a thread in flight at
+// once, so the whole image costs one L2/HBM latency instead of one per element.  Call cp_async_wait_all() (done at
+// the end of load_weights / load_gru_w) and then a block barrier before the first use.
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
 __device__ __forceinline__ void copy_vec(float* dst, const float* __restrict__ src, int n, int tid, int nt) {
-  for (int i = tid; i < n; i += nt) dst[i] = __ldg(src + i);
+  for (int i = tid; i < n; i += nt) cp_async4(dst + i, src + i);
 }
 __device__ __forceinline__ void copy_mat(float* dst, int ldd, const float* __restrict__ src, int rows, int cols,
                                          int tid, int nt) {
   const int n = rows * cols;
   for (int i = tid; i < n; i += nt) {
     const int r = i / cols, c = i - r * cols;
-    dst[r * ldd + c] = __ldg(src + i);
+    cp_async4(dst + r * ldd + c, src + i);
   }
 }
 
@@ -111,6 +120,7 @@ __device__ inline void load_weights(float* sW, const SmemW& s, const NetDev& n, 
   }
   copy_mat(sW + s.head_w, s.ldh, p + n.g.head_w, n.head_total, H, tid, nt);
   copy_vec(sW + s.head_b, p + n.g.head_b, n.head_total, tid, nt);
+  cp_async_wait_all();
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -57,6 +57,7 @@ __device__ inline void load_gru_w(float* sW, const GruW& s, const NetDev& n, con
     copy_mat(sW + s.head_w, s.ldh, p + n.g.head_w, n.head_total, H, tid, nt);
     copy_vec(sW + s.head_b, p + n.g.head_b, n.head_total, tid, nt);
   }
+  cp_async_wait_all();
 }
 
 // workspace [p][H] <-> transposed tile

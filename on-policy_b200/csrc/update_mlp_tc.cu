@@ -1,0 +1,655 @@
+// update_mlp_tc.cu -- the fused MLP training step on Blackwell tensor cores (tcgen05.mma kind::tf32, fp32
+// accumulators in TMEM, weights delivered by one TMA bulk copy).  Same contract as update_mlp_kernel (update_mlp.cu):
+// index-driven gather -> forward -> losses -> backward -> per-CTA gradient slot, one launch per net per step.
+//
+// Tile = 128 rows = UMMA M = the 128 TMEM lanes: thread r of the CTA owns row r end to end.  After each MMA the
+// thread pulls ITS row of the accumulator out of TMEM (tcgen05.ld 32x32b) and does bias/activation/LayerNorm in
+// registers -- no cross-thread reductions, no barriers inside a layer.
+//
+// Operand layout ("chunked", no swizzle): an R x F operand is stored as [F/4][R][4] floats, i.e. the 16-byte unit
+// of 4 consecutive features of row r sits at ((f/4)*R + r)*16.  The same bytes serve
+//   * as a K-major operand  (K = features):  SBO = 128 B (next 8 rows),  LBO = R*16 B (next 4 features)
+//   * as an MN-major operand (K = rows):     SBO = R*16 B (next 4 features), LBO = 128 B (next 8 rows)
+// so the forward (Y = X W^T), input-gradient (dX = dY W) and weight-gradient (dW = dY^T X) GEMMs all read the tiles
+// the epilogue threads wrote once, and W is stored once for both the forward and the dX GEMM.
+//
+// LayerNorm affine parameters and biases are folded into the GEMMs: the tiles hold xhat (pre-affine) plus a
+// constant-1 feature, the weight image holds W' = W diag(gamma) and b' = b + W beta in the column of the 1-feature.
+// dW' accumulates in TMEM across the tiles of a CTA; at the end dW = dW' diag(gamma), db = dW'[:, one],
+// dgamma = colsum(dW' .* W), dbeta = W^T db'  (chain rule of the folding), written to the CTA's gradient slot.
+#include "net_tiles.cuh"
+
+namespace mappo {
+
+constexpr int kTM = 128;                 // rows per tile, threads per CTA
+constexpr int kHF = 72;                  // hidden features incl. the constant-1 feature, padded to a multiple of 8
+constexpr int kHC = kHF / 4;             // 18 chunks
+constexpr int kOne = 64;                 // index of the constant-1 feature in hidden tiles
+
+// ------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {     // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {       // same warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], tf32 inputs, fp32 accumulate; issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 16 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+                 "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+// shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
+}
+// instruction descriptor: D fp32, A/B tf32 (cute::UMMA::InstrDescriptor bit layout)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// folded weight image (global), built once per optimiser step by pack_tc_kernel
+// ------------------------------------------------------------------------------------------------------------
+struct TcImage {
+  int inF;      // input features incl. constant-1, padded to a multiple of 8
+  int NH;       // head outputs padded to a multiple of 16
+  int w1, w2, wh, total;   // float offsets: [inF/4][64][4], [18][64][4], [18][NH][4]
+};
+__host__ __device__ inline TcImage make_tc_image(const NetDev& n) {
+  TcImage m;
+  m.inF = (n.in_dim + 1 + 7) & ~7;
+  m.NH = (n.head_total + 15) & ~15;
+  m.w1 = 0;
+  m.w2 = m.w1 + m.inF * 64;
+  m.wh = m.w2 + kHF * 64;
+  m.total = m.wh + kHF * m.NH;
+  return m;
+}
+
+__global__ void __launch_bounds__(256) pack_tc_kernel(const NetDev n, const float* __restrict__ p, float* __restrict__ img) {
+  const TcImage m = make_tc_image(n);
+  const int H = 64;
+  for (int i = threadIdx.x; i < m.total; i += blockDim.x) {
+    float v = 0.f;
+    if (i < m.w2) {                                       // fc1: [inF/4][64][4]
+      const int kc = i / 256, o = (i >> 2) & 63, k = kc * 4 + (i & 3);
+      const float* W = p + n.g.fc1_w + o * n.in_dim;
+      if (k < n.in_dim) v = W[k] * (n.use_fn ? p[n.g.fn_w + k] : 1.f);
+      else if (k == n.in_dim) {
+        v = p[n.g.fc1_b + o];
+        if (n.use_fn) for (int j = 0; j < n.in_dim; ++j) v = fmaf(W[j], p[n.g.fn_b + j], v);
+      }
+    } else if (i < m.wh) {                                // fc2: [18][64][4], input LN = ln1
+      const int t = i - m.w2, kc = t / 256, o = (t >> 2) & 63, k = kc * 4 + (t & 3);
+      const float* W = p + n.g.fc2_w[0] + o * H;
+      if (k < H) v = W[k] * p[n.g.ln1_w + k];
+      else if (k == kOne) {
+        v = p[n.g.fc2_b[0] + o];
+        for (int j = 0; j < H; ++j) v = fmaf(W[j], p[n.g.ln1_b + j], v);
+      }
+    } else {                                              // heads: [18][NH][4], input LN = ln2[0]
+      const int t = i - m.wh, kc = t / (4 * m.NH), a = (t >> 2) % m.NH, k = kc * 4 + (t & 3);
+      if (a < n.head_total) {
+        const float* W = p + n.g.head_w + a * H;
+        if (k < H) v = W[k] * p[n.g.ln2_w[0] + k];
+        else if (k == kOne) {
+          v = p[n.g.head_b + a];
+          for (int j = 0; j < H; ++j) v = fmaf(W[j], p[n.g.ln2_b[0] + j], v);
+        }
+      }
+    }
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    img[i] = __uint_as_float(u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------------------
+struct TcSmem { int img, x0, x1, x2, g, dl, lg, dbh, misc, total; };   // float offsets
+__host__ __device__ inline TcSmem make_tc_smem(const TcImage& m) {
+  TcSmem s;
+  int o = 0;
+  s.img = o; o += m.total;
+  s.x0 = o; o += m.inF * kTM;
+  s.x1 = o; o += kHF * kTM;
+  s.x2 = o; o += kHF * kTM;
+  s.g = o; o += 64 * kTM;
+  s.dl = o; o += m.NH * kTM;
+  s.lg = o; o += 32 * (kTM + 4);           // logits scratch for row_loss, transposed [j][132]
+  s.dbh = o; o += 32;
+  s.misc = o; o += 16;                     // mbarriers (2 x 8 B) + tmem base
+  s.total = o;
+  return s;
+}
+
+// row-wise LayerNorm statistics of 64 register values (two-pass like torch)
+__device__ __forceinline__ void ln_stats64(const float* a, float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 64; ++i) s += a[i];
+  mean = s * (1.f / 64.f);
+  float v = 0.f;
+#pragma unroll
+  for (int i = 0; i < 64; ++i) { const float d = a[i] - mean; v = fmaf(d, d, v); }
+  rstd = 1.0f / sqrtf(v * (1.f / 64.f) + kLnEps);
+}
+
+__global__ void __launch_bounds__(kTM, 1)
+update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const float* __restrict__ image, const BatchDev b,
+                     const LossDev L, const double* __restrict__ norm_stats, const double* __restrict__ adv_stats,
+                     const float* __restrict__ vn_state, float* __restrict__ grad_part, double* __restrict__ loss_out,
+                     int n_tiles, uint32_t tmem_cols) {
+  extern __shared__ __align__(1024) float smem[];
+  __shared__ double sred[2 * 32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const TcImage im = make_tc_image(n);
+  const TcSmem sm = make_tc_smem(im);
+  float* sImg = smem + sm.img;
+  float* X0 = smem + sm.x0;
+  float* X1 = smem + sm.x1;
+  float* X2 = smem + sm.x2;
+  float* G = smem + sm.g;
+  float* DL = smem + sm.dl;
+  float* lgT = smem + sm.lg;
+  float* dbh = smem + sm.dbh;
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + sm.misc);
+  uint64_t* bar_m = bar_w + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 2);
+  const int in = n.in_dim, inF = im.inF, NH = im.NH, Atot = n.head_total;
+  const int act = n.use_relu ? ACT_RELU : ACT_TANH;
+  constexpr int LGLD = kTM + 4;
+
+  // ---- one-time setup: barriers, TMEM, weight image by TMA, constant parts of the tiles ----
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_m, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+  for (int i = tid; i < 32; i += kTM) dbh[i] = 0.f;
+  // constant-1 feature + zero padding of the hidden tiles (chunks 16, 17) and of the unused logit columns
+  for (int t = 0; t < 2; ++t) {
+    float* X = t ? X2 : X1;
+    reinterpret_cast<float4*>(X)[(16 * kTM + tid)] = make_float4(1.f, 0.f, 0.f, 0.f);
+    reinterpret_cast<float4*>(X)[(17 * kTM + tid)] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (tid == 0) {
+    mbar_expect_tx(bar_w, (uint32_t)(im.total * sizeof(float)));
+    tma_bulk_g2s(sImg, image, (uint32_t)(im.total * sizeof(float)), bar_w);
+  }
+  // TMEM columns
+  const uint32_t cD = 0, cDh = 64, cG2 = 96, cG1 = 168, cGh = 240;
+  const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+
+  const LossConsts lc = make_loss_consts(n, L, norm_stats, adv_stats, vn_state);
+  double acc[3] = {0.0, 0.0, 0.0};
+  uint32_t phase = 0;
+  bool first_tile = true;
+  const uint32_t aX0 = smem_u32(X0), aX1 = smem_u32(X1), aX2 = smem_u32(X2), aG = smem_u32(G), aDL = smem_u32(DL);
+  const uint32_t aW1 = smem_u32(sImg + im.w1), aW2 = smem_u32(sImg + im.w2), aWh = smem_u32(sImg + im.wh);
+  const uint32_t ROWB = kTM * 16;                      // bytes between feature chunks of a 128-row tile
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int p = tile * kTM + tid;
+    const int gr = p < b.n_rows ? (b.rows ? b.rows[p] : p) : -1;
+
+    // ---- S1: gather my row, feature LayerNorm in registers, write the xhat0 tile ----
+    {
+      float x[64];
+      const float* src = (n.is_critic ? b.share_obs : b.obs) + (size_t)(gr < 0 ? 0 : gr) * in;
+#pragma unroll
+      for (int k = 0; k < 64; ++k) x[k] = (k < in && gr >= 0) ? __ldg(src + k) : 0.f;
+      if (n.use_fn && gr >= 0) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 64; ++k) s += x[k];                 // padding is zero
+        const float mean = s / (float)in;
+        float v = 0.f;
+#pragma unroll
+        for (int k = 0; k < 64; ++k) { const float d = x[k] - mean; v += (k < in) ? d * d : 0.f; }
+        const float rs = 1.0f / sqrtf(v / (float)in + kLnEps);
+#pragma unroll
+        for (int k = 0; k < 64; ++k) x[k] = (k < in) ? (x[k] - mean) * rs : 0.f;
+      }
+#pragma unroll
+      for (int kc = 0; kc < 18; ++kc) {
+        if (kc * 4 < inF) {
+          float4 q;
+          float* qq = reinterpret_cast<float*>(&q);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = kc * 4 + j;
+            const float v = x[k & 63];
+            qq[j] = (k == in) ? 1.f : ((k < in) ? to_tf32(v) : 0.f);
+          }
+          reinterpret_cast<float4*>(X0)[kc * kTM + tid] = q;
+        }
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      if (first_tile) mbar_wait(bar_w, 0);                      // weight image has landed
+      const uint32_t id = make_idesc(128, 64, 0, 0);
+      for (int s = 0; s < inF / 8; ++s)
+        umma_tf32(tmem + cD, make_desc(aX0 + s * 2 * ROWB, ROWB, 128), make_desc(aW1 + s * 2 * 1024, 1024, 128), id,
+                  s > 0);
+      umma_commit(bar_m);
+    }
+    // ---- S3: fc1 epilogue ----
+    float mu1, rs1, mu2, rs2;
+    {
+      float a[64];
+      mbar_wait(bar_m, phase); phase ^= 1;
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld16(tmem + lane_base + cD + c * 16, a + c * 16);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 64; ++i) a[i] = act_fwd(a[i], act);
+      ln_stats64(a, mu1, rs1);
+#pragma unroll
+      for (int kc = 0; kc < 16; ++kc)
+        reinterpret_cast<float4*>(X1)[kc * kTM + tid] =
+            make_float4(to_tf32((a[4 * kc] - mu1) * rs1), to_tf32((a[4 * kc + 1] - mu1) * rs1),
+                        to_tf32((a[4 * kc + 2] - mu1) * rs1), to_tf32((a[4 * kc + 3] - mu1) * rs1));
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t id = make_idesc(128, 64, 0, 0);
+      for (int s = 0; s < kHF / 8; ++s)
+        umma_tf32(tmem + cD, make_desc(aX1 + s * 2 * ROWB, ROWB, 128), make_desc(aW2 + s * 2 * 1024, 1024, 128), id,
+                  s > 0);
+      umma_commit(bar_m);
+    }
+    // ---- S5: fc2 epilogue ----
+    {
+      float a[64];
+      mbar_wait(bar_m, phase); phase ^= 1;
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld16(tmem + lane_base + cD + c * 16, a + c * 16);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 64; ++i) a[i] = act_fwd(a[i], act);
+      ln_stats64(a, mu2, rs2);
+#pragma unroll
+      for (int kc = 0; kc < 16; ++kc)
+        reinterpret_cast<float4*>(X2)[kc * kTM + tid] =
+            make_float4(to_tf32((a[4 * kc] - mu2) * rs2), to_tf32((a[4 * kc + 1] - mu2) * rs2),
+                        to_tf32((a[4 * kc + 2] - mu2) * rs2), to_tf32((a[4 * kc + 3] - mu2) * rs2));
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t id = make_idesc(128, NH, 0, 0);
+      for (int s = 0; s < kHF / 8; ++s)
+        umma_tf32(tmem + cDh, make_desc(aX2 + s * 2 * ROWB, ROWB, 128),
+                  make_desc(aWh + s * 2 * NH * 16, NH * 16, 128), id, s > 0);
+      umma_commit(bar_m);
+    }
+    // ---- S7: heads, loss, d(loss)/d(logits) ----
+    {
+      float lg[32];
+      mbar_wait(bar_m, phase); phase ^= 1;
+      tc_fence_after();
+      tmem_ld16(tmem + lane_base + cDh, lg);
+      if (NH > 16) tmem_ld16(tmem + lane_base + cDh + 16, lg + 16);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j < Atot) lgT[j * LGLD + tid] = lg[j];
+      row_loss<LGLD>(n, b, L, lc, lgT, tid, gr, p, acc);          // thread-local: only column `tid` is touched
+      if (!b.eval_only) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) lg[j] = j < Atot ? lgT[j * LGLD + tid] : 0.f;
+#pragma unroll
+        for (int kc = 0; kc < 8; ++kc)
+          if (kc * 4 < NH)
+            reinterpret_cast<float4*>(DL)[kc * kTM + tid] =
+                make_float4(to_tf32(lg[4 * kc]), to_tf32(lg[4 * kc + 1]), to_tf32(lg[4 * kc + 2]), to_tf32(lg[4 * kc + 3]));
+        // head bias gradient: sum over the rows of this warp, one shared atomic per warp and output
+        for (int j = 0; j < Atot; ++j) {
+          float v = lg[j];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == 0) atomicAdd(dbh + j, v);
+        }
+      }
+    }
+    if (b.eval_only) { tc_fence_before(); __syncthreads(); continue; }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      // Gh[k][a] += xhat2^T dL   (M = 64 features, N = NH, K = 128 rows), both operands MN-major
+      const uint32_t idg = make_idesc(64, NH, 1, 1);
+      for (int s = 0; s < kTM / 8; ++s)
+        umma_tf32(tmem + cGh, make_desc(aX2 + s * 128, 128, ROWB), make_desc(aDL + s * 128, 128, ROWB), idg,
+                  (!first_tile) || s > 0);
+      // dxhat2 = dL Wh'       (M = 128 rows, N = 64 features, K = NH): A K-major, B = image MN-major
+      const uint32_t idx = make_idesc(128, 64, 0, 1);
+      for (int s = 0; s < NH / 8; ++s)
+        umma_tf32(tmem + cD, make_desc(aDL + s * 2 * ROWB, ROWB, 128), make_desc(aWh + s * 128, 128, NH * 16), idx,
+                  s > 0);
+      umma_commit(bar_m);
+    }
+    // ---- S9: LayerNorm-2 + activation backward -> dZ2 ----
+    {
+      float d[64];
+      mbar_wait(bar_m, phase); phase ^= 1;
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld16(tmem + lane_base + cD + c * 16, d + c * 16);
+      tmem_ld_wait();
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int kc = 0; kc < 16; ++kc) {
+        const float4 xh = reinterpret_cast<const float4*>(X2)[kc * kTM + tid];
+        s1 += (d[4 * kc] + d[4 * kc + 1]) + (d[4 * kc + 2] + d[4 * kc + 3]);
+        s2 = fmaf(d[4 * kc], xh.x, fmaf(d[4 * kc + 1], xh.y, fmaf(d[4 * kc + 2], xh.z, fmaf(d[4 * kc + 3], xh.w, s2))));
+      }
+      s1 *= (1.f / 64.f); s2 *= (1.f / 64.f);
+      const float inv = 1.0f / rs2;
+#pragma unroll
+      for (int kc = 0; kc < 16; ++kc) {
+        const float4 xh = reinterpret_cast<const float4*>(X2)[kc * kTM + tid];
+        const float xs[4] = {xh.x, xh.y, xh.z, xh.w};
+        float o4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float dA = rs2 * (d[4 * kc + j] - s1 - xs[j] * s2);
+          o4[j] = to_tf32(dA * act_bwd(fmaf(xs[j], inv, mu2), act));
+        }
+        reinterpret_cast<float4*>(G)[kc * kTM + tid] = make_float4(o4[0], o4[1], o4[2], o4[3]);
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      // G2[o][k] += dZ2^T xhat1aug   (M = 64, N = 72, K = 128 rows)
+      const uint32_t idg = make_idesc(64, kHF, 1, 1);
+      for (int s = 0; s < kTM / 8; ++s)
+        umma_tf32(tmem + cG2, make_desc(aG + s * 128, 128, ROWB), make_desc(aX1 + s * 128, 128, ROWB), idg,
+                  (!first_tile) || s > 0);
+      // dxhat1 = dZ2 W2'             (M = 128, N = 64, K = 64)
+      const uint32_t idx = make_idesc(128, 64, 0, 1);
+      for (int s = 0; s < 8; ++s)
+        umma_tf32(tmem + cD, make_desc(aG + s * 2 * ROWB, ROWB, 128), make_desc(aW2 + s * 128, 128, 1024), idx, s > 0);
+      umma_commit(bar_m);
+    }
+    // ---- S11: LayerNorm-1 + activation backward -> dZ1 ----
+    {
+      float d[64];
+      mbar_wait(bar_m, phase); phase ^= 1;
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld16(tmem + lane_base + cD + c * 16, d + c * 16);
+      tmem_ld_wait();
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int kc = 0; kc < 16; ++kc) {
+        const float4 xh = reinterpret_cast<const float4*>(X1)[kc * kTM + tid];
+        s1 += (d[4 * kc] + d[4 * kc + 1]) + (d[4 * kc + 2] + d[4 * kc + 3]);
+        s2 = fmaf(d[4 * kc], xh.x, fmaf(d[4 * kc + 1], xh.y, fmaf(d[4 * kc + 2], xh.z, fmaf(d[4 * kc + 3], xh.w, s2))));
+      }
+      s1 *= (1.f / 64.f); s2 *= (1.f / 64.f);
+      const float inv = 1.0f / rs1;
+#pragma unroll
+      for (int kc = 0; kc < 16; ++kc) {
+        const float4 xh = reinterpret_cast<const float4*>(X1)[kc * kTM + tid];
+        const float xs[4] = {xh.x, xh.y, xh.z, xh.w};
+        float o4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float dA = rs1 * (d[4 * kc + j] - s1 - xs[j] * s2);
+          o4[j] = to_tf32(dA * act_bwd(fmaf(xs[j], inv, mu1), act));
+        }
+        reinterpret_cast<float4*>(G)[kc * kTM + tid] = make_float4(o4[0], o4[1], o4[2], o4[3]);
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      // G1[o][k] += dZ1^T xhat0aug   (M = 64, N = inF, K = 128 rows)
+      const uint32_t idg = make_idesc(64, inF, 1, 1);
+      for (int s = 0; s < kTM / 8; ++s)
+        umma_tf32(tmem + cG1, make_desc(aG + s * 128, 128, ROWB), make_desc(aX0 + s * 128, 128, ROWB), idg,
+                  (!first_tile) || s > 0);
+      umma_commit(bar_m);
+    }
+    mbar_wait(bar_m, phase); phase ^= 1;        // tiles X0 / G are rewritten by the next iteration
+    tc_fence_after();
+    first_tile = false;
+  }
+
+  // ---- unfold the folded gradients into this CTA's slot ----
+  if (!b.eval_only) {
+    float* g = grad_part + (size_t)blockIdx.x * n.g.total;
+    const bool has_tile = !first_tile;
+    const int o = warp * 16 + lane;                       // accumulator row of this thread in the M = 64 layout
+    const bool own = lane < 16;
+    float* S = X1;                                        // scratch [64][65] x 2 (tiles are free now)
+    float* T2 = X1 + 64 * 65;
+    // ---------------- fc2 / ln1 ----------------
+    {
+      float v[72];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld16(tmem + lane_base + cG2 + c * 16, v + c * 16);
+      tmem_ld8(tmem + lane_base + cG2 + 64, v + 64);
+      tmem_ld_wait();
+      __syncthreads();
+      if (own) {
+        const float* W = params + n.g.fc2_w[0] + o * 64;
+        const float dbp = has_tile ? v[kOne] : 0.f;
+        g[n.g.fc2_b[0] + o] = dbp;
+#pragma unroll
+        for (int k = 0; k < 64; ++k) {
+          const float dw = has_tile ? v[k] : 0.f;
+          const float w = W[k];
+          g[n.g.fc2_w[0] + o * 64 + k] = dw * params[n.g.ln1_w + k];
+          S[o * 65 + k] = dw * w;
+          T2[o * 65 + k] = dbp * w;
+        }
+      }
+      __syncthreads();
+      if (tid < 64) {
+        float sg = 0.f, sb = 0.f;
+        for (int r = 0; r < 64; ++r) { sg += S[r * 65 + tid]; sb += T2[r * 65 + tid]; }
+        g[n.g.ln1_w + tid] = sg;
+        g[n.g.ln1_b + tid] = sb;
+      }
+      __syncthreads();
+    }
+    // ---------------- fc1 / feature norm ----------------
+    {
+      float v[72];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld16(tmem + lane_base + cG1 + c * 16, v + c * 16);
+      tmem_ld8(tmem + lane_base + cG1 + 64, v + 64);
+      tmem_ld_wait();
+      if (own) {
+        const float* W = params + n.g.fc1_w + o * in;
+        float dbp = 0.f;
+#pragma unroll
+        for (int k = 0; k < 72; ++k) if (k == in) dbp = has_tile ? v[k] : 0.f;
+        g[n.g.fc1_b + o] = dbp;
+#pragma unroll
+        for (int k = 0; k < 64; ++k) {
+          if (k < in) {
+            const float dw = has_tile ? v[k] : 0.f;
+            const float w = W[k];
+            g[n.g.fc1_w + o * in + k] = dw * (n.use_fn ? params[n.g.fn_w + k] : 1.f);
+            S[o * 65 + k] = dw * w;
+            T2[o * 65 + k] = dbp * w;
+          }
+        }
+      }
+      __syncthreads();
+      if (n.use_fn && tid < in) {
+        float sg = 0.f, sb = 0.f;
+        for (int r = 0; r < 64; ++r) { sg += S[r * 65 + tid]; sb += T2[r * 65 + tid]; }
+        g[n.g.fn_w + tid] = sg;
+        g[n.g.fn_b + tid] = sb;
+      }
+      __syncthreads();
+    }
+    // ---------------- heads / ln2 : thread = feature k ----------------
+    {
+      float v[32];
+      tmem_ld16(tmem + lane_base + cGh, v);
+      if (NH > 16) tmem_ld16(tmem + lane_base + cGh + 16, v + 16);
+      tmem_ld_wait();
+      if (own) {
+        const int k = o;
+        float sg = 0.f, sb = 0.f;
+        const float gam = params[n.g.ln2_w[0] + k];
+#pragma unroll
+        for (int a = 0; a < 32; ++a) {
+          if (a < Atot) {
+            const float dw = has_tile ? v[a] : 0.f;
+            const float w = params[n.g.head_w + a * 64 + k];
+            g[n.g.head_w + a * 64 + k] = dw * gam;
+            sg = fmaf(dw, w, sg);
+            sb = fmaf(dbh[a], w, sb);
+          }
+        }
+        g[n.g.ln2_w[0] + k] = sg;
+        g[n.g.ln2_b[0] + k] = sb;
+      }
+      if (tid < Atot) g[n.g.head_b + tid] = dbh[tid];
+    }
+  }
+
+  // ---- loss scalars + teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (n.is_critic) {
+    double one[1] = {acc[0]};
+    block_accumulate<1>(one, loss_out + 0, sred, tid, kTM);
+  } else {
+    double two[2] = {acc[0], acc[1]};
+    block_accumulate<2>(two, loss_out + 1, sred, tid, kTM);
+    double rt[1] = {acc[2] / (lc.n_rows_d * (double)b.act_shape)};
+    block_accumulate<1>(rt, loss_out + 5, sred, tid, kTM);
+  }
+  if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+bool update_mlp_tc_supported(const NetDev& n) {
+  return n.hid == 64 && n.layer_n == 1 && n.in_dim <= 63 && n.head_total <= 32 && !n.recurrent;
+}
+
+int64_t update_mlp_tc_workspace_floats(const NetDev& n) { return make_tc_image(n).total; }
+
+int update_mlp_tc_slots(const NetDev&, int n_rows, int sm_count) {
+  const int n_tiles = (n_rows + kTM - 1) / kTM;
+  return n_tiles < sm_count ? n_tiles : sm_count;
+}
+
+int update_mlp_tc_launch(const NetDev& n, const float* params, const BatchDev& b, const LossDev& L,
+                         const double* norm_stats, const double* adv_stats, const float* vn_state, float* grad_part,
+                         int n_slots, double* loss_out, float* image, cudaStream_t st) {
+  if (!update_mlp_tc_supported(n)) { set_error("update_mlp_tc: configuration not built for the tcgen05 path"); return MAPPO_ERR_UNSUPPORTED; }
+  if (!image) { set_error("update_mlp_tc: weight-image workspace is NULL"); return MAPPO_ERR_INVALID; }
+  if ((reinterpret_cast<uintptr_t>(image) & 15) != 0) { set_error("update_mlp_tc: workspace must be 16-byte aligned"); return MAPPO_ERR_INVALID; }
+  const TcImage im = make_tc_image(n);
+  const TcSmem sm = make_tc_smem(im);
+  const size_t bytes = (size_t)sm.total * sizeof(float) + 1024;
+  if (bytes > 227 * 1024) { set_error("update_mlp_tc: %zu B shared memory > 227 KB", bytes); return MAPPO_ERR_UNSUPPORTED; }
+  pack_tc_kernel<<<1, 256, 0, st>>>(n, params, image);
+  int rc = check_launch("pack_tc_kernel");
+  if (rc) return rc;
+  static thread_local size_t configured = 0;
+  if (bytes > configured) {
+    if (cudaFuncSetAttribute(update_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+      return check_launch("update_mlp_tc: cudaFuncSetAttribute");
+    configured = bytes;
+  }
+  const int n_tiles = (b.n_rows + kTM - 1) / kTM;
+  const uint32_t cols = im.NH > 16 ? 512u : 256u;
+  update_mlp_tc_kernel<<<n_slots, kTM, bytes, st>>>(n, params, image, b, L, norm_stats, adv_stats, vn_state, grad_part,
+                                                    loss_out, n_tiles, cols);
+  return check_launch("update_mlp_tc_kernel");
+}
+
+}  // namespace mappo

@@ -8,6 +8,7 @@ import os
 
 MAX_HEADS = 4
 MAX_LAYERS = 2
+GEMM_FP32, GEMM_TF32 = 0, 1
 _LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lib", "libmappo_b200.so")
 
 
@@ -32,7 +33,7 @@ class LossCfg(C.Structure):
                 ("huber_delta", C.c_float),
                 ("use_clipped_value_loss", C.c_int32), ("use_huber_loss", C.c_int32),
                 ("use_value_active_masks", C.c_int32), ("use_policy_active_masks", C.c_int32),
-                ("use_valuenorm", C.c_int32), ("update_actor", C.c_int32)]
+                ("use_valuenorm", C.c_int32), ("update_actor", C.c_int32), ("gemm_mode", C.c_int32)]
 
 
 _P = C.c_void_p
@@ -62,8 +63,9 @@ _SIGS = {
     "mappo_gather_rows": (_i32, [_P, _P, _i32, _i32, _P, _P]),
     "mappo_chunk_rows": (_i32, [_P, _i32, _i32, _i32, _i32, _P, _P, _P]),
     "mappo_randperm": (_i32, [_i32, _u64, _P, _P, _P]),
-    "mappo_update_workspace_floats": (_i64, [C.POINTER(NetDesc), _i32]),
-    "mappo_update_grad_slots": (_i32, [C.POINTER(NetDesc), _i32]),
+    "mappo_update_workspace_floats": (_i64, [C.POINTER(NetDesc), _i32, _i32]),
+    "mappo_update_grad_slots": (_i32, [C.POINTER(NetDesc), _i32, _i32]),
+    "mappo_tf32_supported": (_i32, [C.POINTER(NetDesc)]),
     "mappo_update_fwd_bwd": (_i32, [C.POINTER(NetDesc), _P, C.POINTER(Batch), C.POINTER(LossCfg), _P, _P, _P, _P,
                                     _i32, _P, _P, _P]),
     "mappo_grad_reduce": (_i32, [_P, _i32, _i32, _P, _P, C.POINTER(_i32), _P]),

@@ -355,15 +355,16 @@ class FusedAdam:
 class UpdateWorkspace:
     """Per-net scratch for mappo_update_fwd_bwd (gradient slots, recurrent activations)."""
 
-    def __init__(self, net: DeviceNet, max_rows: int):
+    def __init__(self, net: DeviceNet, max_rows: int, gemm_mode: int = 0):
         lib = _lib.load()
         self.net = net
         self.max_rows = int(max_rows)
-        self.n_slots = int(lib.mappo_update_grad_slots(C.byref(net.desc), self.max_rows))
+        self.gemm_mode = int(gemm_mode) if lib.mappo_tf32_supported(C.byref(net.desc)) else _lib.GEMM_FP32
+        self.n_slots = int(lib.mappo_update_grad_slots(C.byref(net.desc), self.max_rows, self.gemm_mode))
         if self.n_slots <= 0:
             raise RuntimeError("mappo_update_grad_slots failed: " + lib.mappo_last_error().decode())
         self.grad_part = torch.empty(self.n_slots * net.n_params, dtype=torch.float32, device=net.device)
-        wf = int(lib.mappo_update_workspace_floats(C.byref(net.desc), self.max_rows))
+        wf = int(lib.mappo_update_workspace_floats(C.byref(net.desc), self.max_rows, self.gemm_mode))
         if wf < 0:
             raise RuntimeError("mappo_update_workspace_floats failed: " + lib.mappo_last_error().decode())
         self.workspace = torch.empty(max(wf, 1), dtype=torch.float32, device=net.device)
@@ -379,6 +380,7 @@ def make_loss_cfg(args, update_actor=True) -> LossCfg:
     c.use_policy_active_masks = int(bool(args.use_policy_active_masks))
     c.use_valuenorm = int(bool(args.use_valuenorm or args.use_popart))
     c.update_actor = int(bool(update_actor))
+    c.gemm_mode = _lib.GEMM_FP32
     return c
 
 
@@ -389,7 +391,8 @@ def launch_update(net: DeviceNet, ws: UpdateWorkspace, batch: Batch, loss: LossC
     lib = _lib.load()
     st = stream_ptr()
     n_rows = int(batch.n_rows)
-    n_slots = min(ws.n_slots, int(lib.mappo_update_grad_slots(C.byref(net.desc), n_rows)))
+    n_slots = min(ws.n_slots, int(lib.mappo_update_grad_slots(C.byref(net.desc), n_rows, ws.gemm_mode)))
+    loss.gemm_mode = ws.gemm_mode
     check(lib.mappo_update_fwd_bwd(C.byref(net.desc), ptr(net.flat), C.byref(batch), C.byref(loss), ptr(norm_stats),
                                    None if adv_stats is None else ptr(adv_stats),
                                    None if vn_state is None else ptr(vn_state), ptr(ws.grad_part), n_slots,

@@ -55,6 +55,9 @@ class R_MAPPO():
         if self._use_popart:
             raise NotImplementedError("use_popart: PopArt.update raises in the reference itself (SURVEY App. B-7)")
         self.value_normalizer = ValueNorm(1, device=self.device) if self._use_valuenorm else None
+        # GEMM engine of the update kernels: "tf32" = tcgen05 tensor cores (fp32 accumulate), "fp32" = exact FFMA tiles
+        import os
+        self.gemm_mode = {"fp32": _lib.GEMM_FP32, "tf32": _lib.GEMM_TF32}[os.environ.get("MAPPO_B200_GEMM", "fp32")]
         self._ws = {}
         self._loss_out = torch.zeros(6, dtype=torch.float64, device=self.device)
 
@@ -62,7 +65,8 @@ class R_MAPPO():
     def _workspaces(self, n_rows):
         key = int(n_rows)
         if key not in self._ws:
-            self._ws[key] = (UpdateWorkspace(self.policy.actor, key), UpdateWorkspace(self.policy.critic, key))
+            self._ws[key] = (UpdateWorkspace(self.policy.actor, key, self.gemm_mode),
+                             UpdateWorkspace(self.policy.critic, key, self.gemm_mode))
         return self._ws[key]
 
     def _one_update(self, batch, n_rows, norm_stats, adv_stats, loss_out, update_actor, allreduce):

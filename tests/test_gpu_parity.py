@@ -47,12 +47,12 @@ def collect_and_returns(cfg, policy, trainer, buf, feed, noise):
                                         buf.rnn_states[t].reshape(E, 1, H), buf.rnn_states_critic[t].reshape(E, 1, H),
                                         buf.masks[t].reshape(E, 1), avail, False, True, True,
                                         exp_noise=None if noise is None else noise[t])
-        d = torch.from_numpy(feed.dones[t]).cuda()
+        d = torch.from_numpy(feed.dones[t]).to(buf.device)
         ha = ha.reshape(N, M, 1, H).clone()
         hc = hc.reshape(N, M, 1, H).clone()
         ha[d] = 0.0
         hc[d] = 0.0
-        masks = torch.ones(N, M, 1, device="cuda")
+        masks = torch.ones(N, M, 1, device=buf.device)
         masks[d] = 0.0
         buf.insert(feed.share_obs[t + 1], feed.obs[t + 1], ha, hc, a.reshape(N, M, -1).float(), lp.reshape(N, M, -1),
                    v.reshape(N, M, 1), feed.rewards[t], masks,

@@ -1,0 +1,92 @@
+"""The tcgen05 (kind::tf32, fp32 accumulate in TMEM) build of the fused MLP update against the reference's outputs.
+
+TF32 keeps 10 mantissa bits of the GEMM inputs (round-to-nearest when the operand tiles are written); accumulation,
+LayerNorm, activations, losses, the gradient reduction and Adam stay fp32.  Stated tolerances:
+  first-update gradients   |err| <= 2e-2 * |ref| + 2e-2 * max|ref of that tensor|   (tf32 rounding of a 64..9600-term dot)
+  losses / ratio / entropy  rtol 2e-3
+  weights after a full 10-epoch train()   rtol 2e-2, atol 2e-4
+The exact-fp32 build (MAPPO_B200_GEMM=fp32, tests/test_gpu_parity.py) keeps the tight tolerances.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import Golden, INFO_KEYS, assert_close
+import test_gpu_parity as TP
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _tf32(monkeypatch):
+    monkeypatch.setenv("MAPPO_B200_GEMM", "tf32")
+
+
+def _grad_check(got, want, what):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    scale = np.abs(want).max() + 1e-12
+    err = np.abs(got - want)
+    tol = 2e-2 * np.abs(want) + 2e-2 * scale
+    assert np.all(err <= tol), f"{what}: max err {err.max():.3e} (scale {scale:.3e}, rel-to-scale {err.max()/scale:.3e})"
+    return err.max() / scale
+
+
+def test_tf32_path_is_active():
+    g = Golden("c1_mlp_discrete")
+    args, policy, trainer, buf = TP.build(g.cfg, g)
+    from mappo_b200 import _lib
+    assert trainer.gemm_mode == _lib.GEMM_TF32
+    ws_a, ws_c = trainer._workspaces(600)
+    assert ws_a.gemm_mode == _lib.GEMM_TF32 and ws_c.gemm_mode == _lib.GEMM_TF32
+    assert ws_a.workspace.numel() > 1000          # folded tf32 weight image for the TMA bulk copy
+
+
+def test_tf32_first_update_gradients(monkeypatch):
+    g = Golden("c1_mlp_discrete")
+    cfg = g.cfg
+    from oracle import mappo_oracle as O
+    one = O.PathConfig(**{**cfg.to_dict(), "ppo_epoch": 1, "act_dims": tuple(cfg.act_dims)})
+    args, policy, trainer, buf = TP.build(one, g)
+    feed = g.feed(0)
+    TP.warm(buf, feed)
+    TP.collect_and_returns(cfg, policy, trainer, buf, feed, g.get("it0/noise"))
+    monkeypatch.setattr(torch, "randperm", TP.FakeRandperm([g.get("it0/perms")[0]]))
+    info = trainer.train(buf)
+    norms = g.get("it0/first_update/norms")
+    worst = 0.0
+    for net, name, nrm in ((policy.actor, "actor", norms[0]), (policy.critic, "critic", norms[1])):
+        coef = min(1.0, cfg.max_grad_norm / (nrm + 1e-6))
+        for k, v in net.named_grads().items():
+            worst = max(worst, _grad_check(v.cpu().numpy() * coef, g.get(f"it0/first_update/{name}/{k}"), f"{name} {k}"))
+    losses = g.get("it0/first_update/losses")          # value_loss, policy_loss, dist_entropy, ratio
+    assert_close(info["value_loss"], losses[0], 2e-3, 1e-6, "value_loss")
+    assert_close(info["dist_entropy"], losses[2], 2e-3, 1e-6, "dist_entropy")
+    assert_close(info["ratio"], losses[3], 2e-3, 1e-6, "ratio")
+    assert_close([info["actor_grad_norm"], info["critic_grad_norm"]], norms, 1e-2, 1e-6, "grad norms")
+    print(f"\n[tf32] worst gradient error relative to tensor scale: {worst:.3e}")
+
+
+def test_tf32_full_iterations(monkeypatch):
+    g = Golden("c1_mlp_discrete")
+    cfg = g.cfg
+    args, policy, trainer, buf = TP.build(cfg, g)
+    for it in range(g.iters):
+        feed = g.feed(it)
+        if it == 0:
+            TP.warm(buf, feed)
+        TP.collect_and_returns(cfg, policy, trainer, buf, feed, g.get(f"it{it}/noise"))
+        monkeypatch.setattr(torch, "randperm", TP.FakeRandperm(g.get(f"it{it}/perms")))
+        info = trainer.train(buf)
+        buf.after_update()
+        want = dict(zip(INFO_KEYS, g.get(f"it{it}/train_info")))
+        for k in INFO_KEYS:
+            assert_close(info[k], want[k], 2e-2, 2e-4, f"it{it} train_info[{k}]")
+        worst = 0.0
+        for net, name in ((policy.actor, "actor"), (policy.critic, "critic")):
+            for k, v in net.state_dict().items():
+                ref = g.get(f"it{it}/{name}/{k}")
+                assert_close(v.cpu().numpy(), ref, 2e-2, 2e-4, f"{name} {k} after it{it}")
+                worst = max(worst, float(np.abs(v.cpu().numpy() - ref).max()))
+        print(f"\n[tf32] it{it}: worst absolute weight deviation from the reference {worst:.3e}")
+        if it == 0:
+            break          # iteration 2 samples actions from tf32-trained weights: integer actions may differ
