@@ -149,6 +149,9 @@ def update_flops(cfg):
 
 
 def run_gpu(a):
+    if os.environ.get("BENCH_WATCHDOG"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["BENCH_WATCHDOG"]), exit=True)
     import torch
     import torch.distributed as dist
     from oracle import mappo_oracle as O            # synthetic feed generator + (rank 0) cpu_baseline only
@@ -172,6 +175,7 @@ def run_gpu(a):
     cfg = c2_config()
     args = make_args(cfg)
     obs_s, share_s, act_s = make_spaces(cfg)
+    os.environ["MAPPO_B200_GEMM"] = a.gemm               # update-kernel GEMM engine: tcgen05 tf32 or exact fp32 FFMA
     torch.manual_seed(1)                                   # identical replicas on every rank
     policy = R_MAPPOPolicy(args, obs_s, share_s, act_s, device=dev)
     trainer = R_MAPPO(args, policy, device=dev)
@@ -193,6 +197,11 @@ def run_gpu(a):
         if rank == 0 and not a.eager:
             print(f"[bench] CUDA graph capture unavailable ({type(e).__name__}: {e}); running eager", file=sys.stderr)
 
+    if world > 1:                                          # every rank must run the same mode
+        ok = torch.tensor([1 if graph_ok else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            graph_ok, eng.graph = False, None
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)       # > 126 MB L2
 
     def barrier():
@@ -252,13 +261,17 @@ def run_gpu(a):
         cpu_rate, cpu_per = cpu_iteration_rate(cfg, a.cpu_iters, 2, cores) if world == 1 and a.cpu_iters > 0 else (None, None)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
                 "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic", "config": {**workload_dict(cfg, world), "cuda_graph": graph_ok,
+                "dtype": "tf32 tensor-core GEMMs (fp32 accumulate / fp32 elsewhere)" if a.gemm == "tf32" else "f32",
+                "data": "synthetic", "config": {**workload_dict(cfg, world), "cuda_graph": graph_ok, "gemm": a.gemm,
                                                                 "rng": "device (Philox sampling, Feistel permutations)"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": eng.h2d_bytes(), "d2h_bytes_per_step": 48,
                         "ms_per_step": e2e_ms_max / a.steps},
                 "gpu_launches": launches,
                 "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                             "traffic": None, "kernel": "update_mlp_kernel (fused fwd+loss+bwd, fp32 SIMT)",
+                             "traffic": None,
+                             "kernel": ("update_mlp_tc_kernel (fused fwd+loss+bwd, tcgen05 kind::tf32 + TMEM; launch incl. "
+                                        "its 1-CTA weight-pack kernel)") if a.gemm == "tf32" else
+                                       "update_mlp_kernel (fused fwd+loss+bwd, fp32 FFMA tiles)",
                              "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1590",
                              "avg_launch_ms": kt["avg_ms"], "launches_timed": kt["n"],
                              "algorithmic_gflop_per_launch": (fa + fc) / 2 / 1e9,
@@ -312,6 +325,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--gemm", default=os.environ.get("MAPPO_B200_GEMM", "tf32"), choices=["tf32", "fp32"],
+                    help="GEMM engine of the update kernels (tf32 = tcgen05 tensor cores)")
     ap.add_argument("--eager", action="store_true", help="no CUDA graph (for per-kernel profiling under ncu)")
     ap.add_argument("--cpu-iters", type=int, default=30, help="oracle iterations for cpu_baseline (rank 0, N=1)")
     a = ap.parse_args()

@@ -136,13 +136,14 @@ int32_t mappo_counter_add(uint64_t* counter_dev, uint64_t inc, void* stream);
 /* ---- a2: insert / after_update --------------------------------------------------------------
  * SharedReplayBuffer.insert (utils/shared_buffer.py:90-123) fused with the runner's done handling
  * (runner/shared/mpe_runner.py:125-139): writes the env outputs of one step into slot t+1 / t,
- * masks = 1 - done, zeroes both rnn states of done rows.  NULL sources are skipped. */
+ * masks = 1 - done, zeroes both rnn states of done rows.  NULL sources are skipped.  rng_counter_dev (optional):
+ * *rng_counter_dev += rng_inc, i.e. the Philox offset consumed by the preceding mappo_policy_step. */
 int32_t mappo_env_insert(const float* next_obs, const float* next_share_obs, const float* rewards,
                          const float* dones, const float* next_active, const float* next_avail,
                          int32_t n_rows, int32_t obs_dim, int32_t share_dim, int32_t hidden, int32_t n_act,
                          float* obs_slot, float* share_obs_slot, float* rewards_slot, float* masks_slot,
                          float* h_actor_slot, float* h_critic_slot, float* active_slot, float* avail_slot,
-                         void* stream);
+                         uint64_t* rng_counter_dev, uint64_t rng_inc, void* stream);
 
 /* ---- a3 + a4(denormalise) + a5(statistics): compute_returns ---------------------------------
  * SharedReplayBuffer.compute_returns (shared_buffer.py:179-262, non-MAT branches) as one backward
@@ -221,7 +222,8 @@ int32_t mappo_evaluate_actions(const mappo_net_desc_t* desc, const float* params
  * torch.optim.Adam(lr, eps, betas=(0.9,0.999), weight_decay=0) (rMAPPOPolicy.py:31-37).
  *   mappo_grad_reduce : grad = sum_s grad_part[s]; sumsq_part[b] = per-block sum(grad^2)
  *   mappo_clip_adam   : total = sqrt(sum sumsq_part); coef = min(1, max_norm/(total+1e-6)) when
- *                       use_max_grad_norm; Adam step with g*coef; ++*step_dev; *grad_norm_out += total.
+ *                       use_max_grad_norm; Adam step with g*coef; ++step_dev[0]; *grad_norm_out += total.
+ *                       step_dev points to TWO ints: {Adam step count, scratch ticket (keep 0)}.
  * lr is read from device memory (lr_dev[0]) so lr_decay (utils/util.py:17-21) needs no re-capture. */
 int32_t mappo_grad_reduce(const float* grad_part, int32_t n_slots, int32_t n_params, float* grad,
                           float* sumsq_part, int32_t* n_sumsq_blocks_out, void* stream);

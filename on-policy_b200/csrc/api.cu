@@ -190,7 +190,8 @@ int32_t mappo_env_insert(const float* next_obs, const float* next_share_obs, con
                          const float* next_active, const float* next_avail, int32_t n_rows, int32_t obs_dim,
                          int32_t share_dim, int32_t hidden, int32_t n_act, float* obs_slot, float* share_obs_slot,
                          float* rewards_slot, float* masks_slot, float* h_actor_slot, float* h_critic_slot,
-                         float* active_slot, float* avail_slot, void* stream) {
+                         float* active_slot, float* avail_slot, uint64_t* rng_counter_dev, uint64_t rng_inc,
+                         void* stream) {
   if (n_rows <= 0) return MAPPO_OK;
   if ((next_obs && !obs_slot) || (next_share_obs && !share_obs_slot) || (rewards && !rewards_slot) ||
       (next_avail && !avail_slot)) { set_error("env_insert: source given without destination slot"); return MAPPO_ERR_INVALID; }
@@ -200,6 +201,7 @@ int32_t mappo_env_insert(const float* next_obs, const float* next_share_obs, con
   a.E = n_rows; a.Do = obs_dim; a.Ds = share_dim; a.H = hidden; a.A = n_act;
   a.obs = obs_slot; a.share = share_obs_slot; a.rew = rewards_slot; a.masks = masks_slot;
   a.ha = h_actor_slot; a.hc = h_critic_slot; a.active = active_slot; a.avail = avail_slot;
+  a.rng_counter = rng_counter_dev; a.rng_inc = rng_inc;
   return env_insert_launch(a, (cudaStream_t)stream);
 }
 

@@ -25,6 +25,8 @@ struct InsertArgs {
   const float *next_obs, *next_share, *rewards, *dones, *next_active, *next_avail;
   int E, Do, Ds, H, A;
   float *obs, *share, *rew, *masks, *ha, *hc, *active, *avail;
+  uint64_t* rng_counter;
+  uint64_t rng_inc;
 };
 
 int policy_step_launch(const NetDev* na, const NetDev* nc, const PolArgs& a, cudaStream_t st);

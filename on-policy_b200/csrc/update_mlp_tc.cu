@@ -6,12 +6,13 @@
 // thread pulls ITS row of the accumulator out of TMEM (tcgen05.ld 32x32b) and does bias/activation/LayerNorm in
 // registers -- no cross-thread reductions, no barriers inside a layer.
 //
-// Operand layout ("chunked", no swizzle): an R x F operand is stored as [F/4][R][4] floats, i.e. the 16-byte unit
-// of 4 consecutive features of row r sits at ((f/4)*R + r)*16.  The same bytes serve
-//   * as a K-major operand  (K = features):  SBO = 128 B (next 8 rows),  LBO = R*16 B (next 4 features)
-//   * as an MN-major operand (K = rows):     SBO = R*16 B (next 4 features), LBO = 128 B (next 8 rows)
-// so the forward (Y = X W^T), input-gradient (dX = dY W) and weight-gradient (dW = dY^T X) GEMMs all read the tiles
-// the epilogue threads wrote once, and W is stored once for both the forward and the dX GEMM.
+// Operand layout: every operand is K-major, no swizzle ("interleaved" canonical layout): an R x K operand is stored
+// as [K/4][R(+pad)][4] floats, i.e. the 16-byte unit of 4 consecutive K-elements of row r sits at
+// ((k/4)*S + r)*16 with S >= R; descriptor SBO = 128 B (next 8 rows), LBO = S*16 B (next 4 K-elements).
+// (MN-major tf32 operands in this layout produce no output on sm_100a -- tests/cuda/tc_probe.cu -- so the
+// weight-gradient GEMMs dW = dY^T X, whose contraction runs over the ROWS, read explicitly transposed tiles:
+// thread r scatters its row as column r of a [rows/4][features + 1][4] tile; the odd feature stride S = F + 1
+// makes those 4-byte stores bank-conflict free.)  The dX GEMMs read a transposed weight image built once per step.
 //
 // LayerNorm affine parameters and biases are folded into the GEMMs: the tiles hold xhat (pre-affine) plus a
 // constant-1 feature, the weight image holds W' = W diag(gamma) and b' = b + W beta in the column of the 1-feature.
@@ -112,7 +113,9 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_
 struct TcImage {
   int inF;      // input features incl. constant-1, padded to a multiple of 8
   int NH;       // head outputs padded to a multiple of 16
-  int w1, w2, wh, total;   // float offsets: [inF/4][64][4], [18][64][4], [18][NH][4]
+  // float offsets.  forward (K = in-features):  w1 [inF/4][64][4], w2 [18][64][4], wh [18][NH][4]
+  //                 dX      (K = out-features): w2t [16][64][4] (rows = in-feature k), wht [NH/4][64][4]
+  int w1, w2, wh, w2t, wht, total;
 };
 __host__ __device__ inline TcImage make_tc_image(const NetDev& n) {
   TcImage m;
@@ -121,14 +124,16 @@ __host__ __device__ inline TcImage make_tc_image(const NetDev& n) {
   m.w1 = 0;
   m.w2 = m.w1 + m.inF * 64;
   m.wh = m.w2 + kHF * 64;
-  m.total = m.wh + kHF * m.NH;
+  m.w2t = m.wh + kHF * m.NH;
+  m.wht = m.w2t + 64 * 64;
+  m.total = m.wht + m.NH * 64;
   return m;
 }
 
 __global__ void __launch_bounds__(256) pack_tc_kernel(const NetDev n, const float* __restrict__ p, float* __restrict__ img) {
   const TcImage m = make_tc_image(n);
   const int H = 64;
-  for (int i = threadIdx.x; i < m.total; i += blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m.total; i += gridDim.x * blockDim.x) {
     float v = 0.f;
     if (i < m.w2) {                                       // fc1: [inF/4][64][4]
       const int kc = i / 256, o = (i >> 2) & 63, k = kc * 4 + (i & 3);
@@ -146,7 +151,7 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const NetDev n, const floa
         v = p[n.g.fc2_b[0] + o];
         for (int j = 0; j < H; ++j) v = fmaf(W[j], p[n.g.ln1_b + j], v);
       }
-    } else {                                              // heads: [18][NH][4], input LN = ln2[0]
+    } else if (i < m.w2t) {                               // heads: [18][NH][4], input LN = ln2[0]
       const int t = i - m.wh, kc = t / (4 * m.NH), a = (t >> 2) % m.NH, k = kc * 4 + (t & 3);
       if (a < n.head_total) {
         const float* W = p + n.g.head_w + a * H;
@@ -156,6 +161,12 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const NetDev n, const floa
           for (int j = 0; j < H; ++j) v = fmaf(W[j], p[n.g.ln2_b[0] + j], v);
         }
       }
+    } else if (i < m.wht) {                               // fc2 transposed: element (row k, K-index o) = W2'[o][k]
+      const int t = i - m.w2t, oc = t / 256, k = (t >> 2) & 63, o = oc * 4 + (t & 3);
+      v = p[n.g.fc2_w[0] + o * H + k] * p[n.g.ln1_w + k];
+    } else {                                              // heads transposed: (row k, K-index a) = Wh'[a][k]
+      const int t = i - m.wht, ac = t / 256, k = (t >> 2) & 63, a = ac * 4 + (t & 3);
+      if (a < n.head_total) v = p[n.g.head_w + a * H + k] * p[n.g.ln2_w[0] + k];
     }
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
@@ -166,17 +177,17 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const NetDev n, const floa
 // ------------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------------
-struct TcSmem { int img, x0, x1, x2, g, dl, lg, dbh, misc, total; };   // float offsets
+constexpr int kS65 = 65, kS73 = 73;       // padded row strides of the transposed tiles (odd -> conflict-free scatter)
+struct TcSmem { int img, p, x1t, x2t, ta, lg, dbh, misc, total; };   // float offsets
 __host__ __device__ inline TcSmem make_tc_smem(const TcImage& m) {
   TcSmem s;
   int o = 0;
   s.img = o; o += m.total;
-  s.x0 = o; o += m.inF * kTM;
-  s.x1 = o; o += kHF * kTM;
-  s.x2 = o; o += kHF * kTM;
-  s.g = o; o += 64 * kTM;
-  s.dl = o; o += m.NH * kTM;
-  s.lg = o; o += 32 * (kTM + 4);           // logits scratch for row_loss, transposed [j][132]
+  s.p = o; o += 32 * kS73 * 4;             // staging: K-major [<=18][128][4] tiles, or xhat0^T [32][inF+1][4]
+  s.x1t = o; o += 32 * kS73 * 4;           // xhat1^T (+ constant-1 row 64, zero rows 65..71)
+  s.x2t = o; o += 32 * kS65 * 4;           // xhat2^T
+  s.ta = o; o += 32 * kS65 * 4;            // dL^T / dZ2^T / dZ1^T
+  s.lg = o; o += m.NH * (kTM + 4);         // logits scratch for row_loss, transposed [j][132]
   s.dbh = o; o += 32;
   s.misc = o; o += 16;                     // mbarriers (2 x 8 B) + tmem base
   s.total = o;
@@ -195,6 +206,40 @@ __device__ __forceinline__ void ln_stats64(const float* a, float& mean, float& r
   rstd = 1.0f / sqrtf(v * (1.f / 64.f) + kLnEps);
 }
 
+// thread `tid` = row r: write 64 values as row r of a K-major staging tile [16 (+2 aug)][128][4] ...
+__device__ __forceinline__ void put_kmajor64(float* P, int tid, const float* v, bool aug) {
+#pragma unroll
+  for (int kc = 0; kc < 16; ++kc)
+    reinterpret_cast<float4*>(P)[kc * kTM + tid] = make_float4(v[4 * kc], v[4 * kc + 1], v[4 * kc + 2], v[4 * kc + 3]);
+  if (aug) {
+    reinterpret_cast<float4*>(P)[16 * kTM + tid] = make_float4(1.f, 0.f, 0.f, 0.f);
+    reinterpret_cast<float4*>(P)[17 * kTM + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+// ... and as column r of a transposed tile [32][S][4] (element (feature f, row r) at ((r/4)*S + f)*4 + r%4)
+__device__ __forceinline__ void put_transposed64(float* T, int S, int tid, const float* v) {
+  float* base = T + (tid >> 2) * S * 4 + (tid & 3);
+#pragma unroll
+  for (int f = 0; f < 64; ++f) base[f * 4] = v[f];
+}
+
+// LayerNorm + activation backward for one row: d = dL/dxhat (64 regs) -> dZ in place.  xhat is re-read from the
+// transposed tile (conflict-free 4-byte loads).
+__device__ __forceinline__ void ln_act_bwd64(float* d, const float* XT, int S, int tid, float mu, float rs, int act) {
+  const float* base = XT + (tid >> 2) * S * 4 + (tid & 3);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int f = 0; f < 64; ++f) { s1 += d[f]; s2 = fmaf(d[f], base[f * 4], s2); }
+  s1 *= (1.f / 64.f); s2 *= (1.f / 64.f);
+  const float inv = 1.0f / rs;
+#pragma unroll
+  for (int f = 0; f < 64; ++f) {
+    const float xh = base[f * 4];
+    const float dA = rs * (d[f] - s1 - xh * s2);
+    d[f] = to_tf32(dA * act_bwd(fmaf(xh, inv, mu), act));
+  }
+}
+
 __global__ void __launch_bounds__(kTM, 1)
 update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const float* __restrict__ image, const BatchDev b,
                      const LossDev L, const double* __restrict__ norm_stats, const double* __restrict__ adv_stats,
@@ -206,21 +251,21 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
   const TcImage im = make_tc_image(n);
   const TcSmem sm = make_tc_smem(im);
   float* sImg = smem + sm.img;
-  float* X0 = smem + sm.x0;
-  float* X1 = smem + sm.x1;
-  float* X2 = smem + sm.x2;
-  float* G = smem + sm.g;
-  float* DL = smem + sm.dl;
+  float* P = smem + sm.p;
+  float* X1T = smem + sm.x1t;
+  float* X2T = smem + sm.x2t;
+  float* TA = smem + sm.ta;
   float* lgT = smem + sm.lg;
   float* dbh = smem + sm.dbh;
   uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + sm.misc);
   uint64_t* bar_m = bar_w + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 2);
   const int in = n.in_dim, inF = im.inF, NH = im.NH, Atot = n.head_total;
+  const int S0 = inF + 1, SH = NH + 1;
   const int act = n.use_relu ? ACT_RELU : ACT_TANH;
   constexpr int LGLD = kTM + 4;
 
-  // ---- one-time setup: barriers, TMEM, weight image by TMA, constant parts of the tiles ----
+  // ---- one-time setup: barriers, TMEM, weight image by TMA, constant rows of the transposed tiles ----
   if (tid == 0) {
     mbar_init(bar_w, 1);
     mbar_init(bar_m, 1);
@@ -228,11 +273,10 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
   }
   if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
   for (int i = tid; i < 32; i += kTM) dbh[i] = 0.f;
-  // constant-1 feature + zero padding of the hidden tiles (chunks 16, 17) and of the unused logit columns
-  for (int t = 0; t < 2; ++t) {
-    float* X = t ? X2 : X1;
-    reinterpret_cast<float4*>(X)[(16 * kTM + tid)] = make_float4(1.f, 0.f, 0.f, 0.f);
-    reinterpret_cast<float4*>(X)[(17 * kTM + tid)] = make_float4(0.f, 0.f, 0.f, 0.f);
+  {
+    float* base = X1T + (tid >> 2) * kS73 * 4 + (tid & 3);          // constant-1 feature (row 64) and zero rows 65..71
+#pragma unroll
+    for (int f = 64; f < 72; ++f) base[f * 4] = (f == kOne) ? 1.f : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -242,7 +286,7 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
     mbar_expect_tx(bar_w, (uint32_t)(im.total * sizeof(float)));
     tma_bulk_g2s(sImg, image, (uint32_t)(im.total * sizeof(float)), bar_w);
   }
-  // TMEM columns
+  // TMEM columns: D fwd/bwd accumulator, Dh logits, G2 / G1 / Gh persistent weight-gradient accumulators
   const uint32_t cD = 0, cDh = 64, cG2 = 96, cG1 = 168, cGh = 240;
   const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
 
@@ -250,44 +294,42 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
   double acc[3] = {0.0, 0.0, 0.0};
   uint32_t phase = 0;
   bool first_tile = true;
-  const uint32_t aX0 = smem_u32(X0), aX1 = smem_u32(X1), aX2 = smem_u32(X2), aG = smem_u32(G), aDL = smem_u32(DL);
+  const uint32_t aP = smem_u32(P), aX1T = smem_u32(X1T), aX2T = smem_u32(X2T), aTA = smem_u32(TA);
   const uint32_t aW1 = smem_u32(sImg + im.w1), aW2 = smem_u32(sImg + im.w2), aWh = smem_u32(sImg + im.wh);
-  const uint32_t ROWB = kTM * 16;                      // bytes between feature chunks of a 128-row tile
+  const uint32_t aW2T = smem_u32(sImg + im.w2t), aWhT = smem_u32(sImg + im.wht);
+  constexpr uint32_t ROWB = kTM * 16;                  // chunk stride of a 128-row K-major staging tile
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int p = tile * kTM + tid;
     const int gr = p < b.n_rows ? (b.rows ? b.rows[p] : p) : -1;
+    const float* src = (n.is_critic ? b.share_obs : b.obs) + (size_t)(gr < 0 ? 0 : gr) * in;
+    float mu0 = 0.f, rs0 = 1.f;
 
-    // ---- S1: gather my row, feature LayerNorm in registers, write the xhat0 tile ----
+    // ---- S1: gather my row, feature LayerNorm in registers, stage xhat0 (K-major, + constant-1 feature) ----
     {
       float x[64];
-      const float* src = (n.is_critic ? b.share_obs : b.obs) + (size_t)(gr < 0 ? 0 : gr) * in;
 #pragma unroll
       for (int k = 0; k < 64; ++k) x[k] = (k < in && gr >= 0) ? __ldg(src + k) : 0.f;
       if (n.use_fn && gr >= 0) {
         float s = 0.f;
 #pragma unroll
         for (int k = 0; k < 64; ++k) s += x[k];                 // padding is zero
-        const float mean = s / (float)in;
+        mu0 = s / (float)in;
         float v = 0.f;
 #pragma unroll
-        for (int k = 0; k < 64; ++k) { const float d = x[k] - mean; v += (k < in) ? d * d : 0.f; }
-        const float rs = 1.0f / sqrtf(v / (float)in + kLnEps);
-#pragma unroll
-        for (int k = 0; k < 64; ++k) x[k] = (k < in) ? (x[k] - mean) * rs : 0.f;
+        for (int k = 0; k < 64; ++k) { const float d = x[k] - mu0; v += (k < in) ? d * d : 0.f; }
+        rs0 = 1.0f / sqrtf(v / (float)in + kLnEps);
       }
 #pragma unroll
       for (int kc = 0; kc < 18; ++kc) {
         if (kc * 4 < inF) {
-          float4 q;
-          float* qq = reinterpret_cast<float*>(&q);
+          float q[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int k = kc * 4 + j;
-            const float v = x[k & 63];
-            qq[j] = (k == in) ? 1.f : ((k < in) ? to_tf32(v) : 0.f);
+            q[j] = (k == in) ? 1.f : ((k < in) ? to_tf32((x[k & 63] - mu0) * rs0) : 0.f);
           }
-          reinterpret_cast<float4*>(X0)[kc * kTM + tid] = q;
+          reinterpret_cast<float4*>(P)[kc * kTM + tid] = make_float4(q[0], q[1], q[2], q[3]);
         }
       }
     }
@@ -299,11 +341,10 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
       if (first_tile) mbar_wait(bar_w, 0);                      // weight image has landed
       const uint32_t id = make_idesc(128, 64, 0, 0);
       for (int s = 0; s < inF / 8; ++s)
-        umma_tf32(tmem + cD, make_desc(aX0 + s * 2 * ROWB, ROWB, 128), make_desc(aW1 + s * 2 * 1024, 1024, 128), id,
-                  s > 0);
+        umma_tf32(tmem + cD, make_desc(aP + s * 2 * ROWB, ROWB, 128), make_desc(aW1 + s * 2 * 1024, 1024, 128), id, s > 0);
       umma_commit(bar_m);
     }
-    // ---- S3: fc1 epilogue ----
+    // ---- S3: fc1 epilogue: activation, LayerNorm -> xhat1 (K-major staging + transposed copy) ----
     float mu1, rs1, mu2, rs2;
     {
       float a[64];
@@ -316,10 +357,9 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
       for (int i = 0; i < 64; ++i) a[i] = act_fwd(a[i], act);
       ln_stats64(a, mu1, rs1);
 #pragma unroll
-      for (int kc = 0; kc < 16; ++kc)
-        reinterpret_cast<float4*>(X1)[kc * kTM + tid] =
-            make_float4(to_tf32((a[4 * kc] - mu1) * rs1), to_tf32((a[4 * kc + 1] - mu1) * rs1),
-                        to_tf32((a[4 * kc + 2] - mu1) * rs1), to_tf32((a[4 * kc + 3] - mu1) * rs1));
+      for (int i = 0; i < 64; ++i) a[i] = to_tf32((a[i] - mu1) * rs1);
+      put_kmajor64(P, tid, a, true);
+      put_transposed64(X1T, kS73, tid, a);
     }
     fence_async_smem();
     tc_fence_before();
@@ -328,8 +368,7 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
       tc_fence_after();
       const uint32_t id = make_idesc(128, 64, 0, 0);
       for (int s = 0; s < kHF / 8; ++s)
-        umma_tf32(tmem + cD, make_desc(aX1 + s * 2 * ROWB, ROWB, 128), make_desc(aW2 + s * 2 * 1024, 1024, 128), id,
-                  s > 0);
+        umma_tf32(tmem + cD, make_desc(aP + s * 2 * ROWB, ROWB, 128), make_desc(aW2 + s * 2 * 1024, 1024, 128), id, s > 0);
       umma_commit(bar_m);
     }
     // ---- S5: fc2 epilogue ----
@@ -344,10 +383,9 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
       for (int i = 0; i < 64; ++i) a[i] = act_fwd(a[i], act);
       ln_stats64(a, mu2, rs2);
 #pragma unroll
-      for (int kc = 0; kc < 16; ++kc)
-        reinterpret_cast<float4*>(X2)[kc * kTM + tid] =
-            make_float4(to_tf32((a[4 * kc] - mu2) * rs2), to_tf32((a[4 * kc + 1] - mu2) * rs2),
-                        to_tf32((a[4 * kc + 2] - mu2) * rs2), to_tf32((a[4 * kc + 3] - mu2) * rs2));
+      for (int i = 0; i < 64; ++i) a[i] = to_tf32((a[i] - mu2) * rs2);
+      put_kmajor64(P, tid, a, true);
+      put_transposed64(X2T, kS65, tid, a);
     }
     fence_async_smem();
     tc_fence_before();
@@ -356,8 +394,8 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
       tc_fence_after();
       const uint32_t id = make_idesc(128, NH, 0, 0);
       for (int s = 0; s < kHF / 8; ++s)
-        umma_tf32(tmem + cDh, make_desc(aX2 + s * 2 * ROWB, ROWB, 128),
-                  make_desc(aWh + s * 2 * NH * 16, NH * 16, 128), id, s > 0);
+        umma_tf32(tmem + cDh, make_desc(aP + s * 2 * ROWB, ROWB, 128), make_desc(aWh + s * 2 * NH * 16, NH * 16, 128), id,
+                  s > 0);
       umma_commit(bar_m);
     }
     // ---- S7: heads, loss, d(loss)/d(logits) ----
@@ -373,12 +411,14 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
       row_loss<LGLD>(n, b, L, lc, lgT, tid, gr, p, acc);          // thread-local: only column `tid` is touched
       if (!b.eval_only) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) lg[j] = j < Atot ? lgT[j * LGLD + tid] : 0.f;
+        for (int j = 0; j < 32; ++j) lg[j] = j < Atot ? to_tf32(lgT[j * LGLD + tid]) : 0.f;
 #pragma unroll
         for (int kc = 0; kc < 8; ++kc)
           if (kc * 4 < NH)
-            reinterpret_cast<float4*>(DL)[kc * kTM + tid] =
-                make_float4(to_tf32(lg[4 * kc]), to_tf32(lg[4 * kc + 1]), to_tf32(lg[4 * kc + 2]), to_tf32(lg[4 * kc + 3]));
+            reinterpret_cast<float4*>(P)[kc * kTM + tid] = make_float4(lg[4 * kc], lg[4 * kc + 1], lg[4 * kc + 2], lg[4 * kc + 3]);
+        float* tb = TA + (tid >> 2) * SH * 4 + (tid & 3);         // dL^T: [32][NH + 1][4]
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (j < NH) tb[j * 4] = lg[j];
         // head bias gradient: sum over the rows of this warp, one shared atomic per warp and output
         for (int j = 0; j < Atot; ++j) {
           float v = lg[j];
@@ -394,19 +434,18 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      // Gh[k][a] += xhat2^T dL   (M = 64 features, N = NH, K = 128 rows), both operands MN-major
-      const uint32_t idg = make_idesc(64, NH, 1, 1);
+      // Gh[k][a] += xhat2^T dL   (M = 64 features, N = NH, K = 128 rows): transposed tiles, K-major
+      const uint32_t idg = make_idesc(64, NH, 0, 0);
       for (int s = 0; s < kTM / 8; ++s)
-        umma_tf32(tmem + cGh, make_desc(aX2 + s * 128, 128, ROWB), make_desc(aDL + s * 128, 128, ROWB), idg,
-                  (!first_tile) || s > 0);
-      // dxhat2 = dL Wh'       (M = 128 rows, N = 64 features, K = NH): A K-major, B = image MN-major
-      const uint32_t idx = make_idesc(128, 64, 0, 1);
+        umma_tf32(tmem + cGh, make_desc(aX2T + s * 2 * kS65 * 16, kS65 * 16, 128),
+                  make_desc(aTA + s * 2 * SH * 16, SH * 16, 128), idg, (!first_tile) || s > 0);
+      // dxhat2 = dL Wh'       (M = 128 rows, N = 64 features, K = NH)
+      const uint32_t idx = make_idesc(128, 64, 0, 0);
       for (int s = 0; s < NH / 8; ++s)
-        umma_tf32(tmem + cD, make_desc(aDL + s * 2 * ROWB, ROWB, 128), make_desc(aWh + s * 128, 128, NH * 16), idx,
-                  s > 0);
+        umma_tf32(tmem + cD, make_desc(aP + s * 2 * ROWB, ROWB, 128), make_desc(aWhT + s * 2 * 1024, 1024, 128), idx, s > 0);
       umma_commit(bar_m);
     }
-    // ---- S9: LayerNorm-2 + activation backward -> dZ2 ----
+    // ---- S9: LayerNorm-2 + activation backward -> dZ2 (K-major staging + transposed) ----
     {
       float d[64];
       mbar_wait(bar_m, phase); phase ^= 1;
@@ -414,27 +453,9 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld16(tmem + lane_base + cD + c * 16, d + c * 16);
       tmem_ld_wait();
-      float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-      for (int kc = 0; kc < 16; ++kc) {
-        const float4 xh = reinterpret_cast<const float4*>(X2)[kc * kTM + tid];
-        s1 += (d[4 * kc] + d[4 * kc + 1]) + (d[4 * kc + 2] + d[4 * kc + 3]);
-        s2 = fmaf(d[4 * kc], xh.x, fmaf(d[4 * kc + 1], xh.y, fmaf(d[4 * kc + 2], xh.z, fmaf(d[4 * kc + 3], xh.w, s2))));
-      }
-      s1 *= (1.f / 64.f); s2 *= (1.f / 64.f);
-      const float inv = 1.0f / rs2;
-#pragma unroll
-      for (int kc = 0; kc < 16; ++kc) {
-        const float4 xh = reinterpret_cast<const float4*>(X2)[kc * kTM + tid];
-        const float xs[4] = {xh.x, xh.y, xh.z, xh.w};
-        float o4[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float dA = rs2 * (d[4 * kc + j] - s1 - xs[j] * s2);
-          o4[j] = to_tf32(dA * act_bwd(fmaf(xs[j], inv, mu2), act));
-        }
-        reinterpret_cast<float4*>(G)[kc * kTM + tid] = make_float4(o4[0], o4[1], o4[2], o4[3]);
-      }
+      ln_act_bwd64(d, X2T, kS65, tid, mu2, rs2, act);
+      put_kmajor64(P, tid, d, false);
+      put_transposed64(TA, kS65, tid, d);
     }
     fence_async_smem();
     tc_fence_before();
@@ -442,17 +463,17 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
     if (tid == 0) {
       tc_fence_after();
       // G2[o][k] += dZ2^T xhat1aug   (M = 64, N = 72, K = 128 rows)
-      const uint32_t idg = make_idesc(64, kHF, 1, 1);
+      const uint32_t idg = make_idesc(64, kHF, 0, 0);
       for (int s = 0; s < kTM / 8; ++s)
-        umma_tf32(tmem + cG2, make_desc(aG + s * 128, 128, ROWB), make_desc(aX1 + s * 128, 128, ROWB), idg,
-                  (!first_tile) || s > 0);
+        umma_tf32(tmem + cG2, make_desc(aTA + s * 2 * kS65 * 16, kS65 * 16, 128),
+                  make_desc(aX1T + s * 2 * kS73 * 16, kS73 * 16, 128), idg, (!first_tile) || s > 0);
       // dxhat1 = dZ2 W2'             (M = 128, N = 64, K = 64)
-      const uint32_t idx = make_idesc(128, 64, 0, 1);
+      const uint32_t idx = make_idesc(128, 64, 0, 0);
       for (int s = 0; s < 8; ++s)
-        umma_tf32(tmem + cD, make_desc(aG + s * 2 * ROWB, ROWB, 128), make_desc(aW2 + s * 128, 128, 1024), idx, s > 0);
+        umma_tf32(tmem + cD, make_desc(aP + s * 2 * ROWB, ROWB, 128), make_desc(aW2T + s * 2 * 1024, 1024, 128), idx, s > 0);
       umma_commit(bar_m);
     }
-    // ---- S11: LayerNorm-1 + activation backward -> dZ1 ----
+    // ---- S11: LayerNorm-1 + activation backward -> dZ1^T; xhat0^T re-staged from the (L2-resident) input row ----
     {
       float d[64];
       mbar_wait(bar_m, phase); phase ^= 1;
@@ -460,26 +481,17 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld16(tmem + lane_base + cD + c * 16, d + c * 16);
       tmem_ld_wait();
-      float s1 = 0.f, s2 = 0.f;
+      ln_act_bwd64(d, X1T, kS73, tid, mu1, rs1, act);
+      put_transposed64(TA, kS65, tid, d);
+      float* pb = P + (tid >> 2) * S0 * 4 + (tid & 3);            // xhat0aug^T: [32][inF + 1][4]
 #pragma unroll
-      for (int kc = 0; kc < 16; ++kc) {
-        const float4 xh = reinterpret_cast<const float4*>(X1)[kc * kTM + tid];
-        s1 += (d[4 * kc] + d[4 * kc + 1]) + (d[4 * kc + 2] + d[4 * kc + 3]);
-        s2 = fmaf(d[4 * kc], xh.x, fmaf(d[4 * kc + 1], xh.y, fmaf(d[4 * kc + 2], xh.z, fmaf(d[4 * kc + 3], xh.w, s2))));
-      }
-      s1 *= (1.f / 64.f); s2 *= (1.f / 64.f);
-      const float inv = 1.0f / rs1;
-#pragma unroll
-      for (int kc = 0; kc < 16; ++kc) {
-        const float4 xh = reinterpret_cast<const float4*>(X1)[kc * kTM + tid];
-        const float xs[4] = {xh.x, xh.y, xh.z, xh.w};
-        float o4[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float dA = rs1 * (d[4 * kc + j] - s1 - xs[j] * s2);
-          o4[j] = to_tf32(dA * act_bwd(fmaf(xs[j], inv, mu1), act));
+      for (int k = 0; k < 72; ++k) {
+        if (k < inF) {
+          float v = 0.f;
+          if (k < in) v = gr >= 0 ? to_tf32((__ldg(src + k) - mu0) * rs0) : 0.f;
+          else if (k == in) v = 1.f;
+          pb[k * 4] = v;
         }
-        reinterpret_cast<float4*>(G)[kc * kTM + tid] = make_float4(o4[0], o4[1], o4[2], o4[3]);
       }
     }
     fence_async_smem();
@@ -488,25 +500,24 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
     if (tid == 0) {
       tc_fence_after();
       // G1[o][k] += dZ1^T xhat0aug   (M = 64, N = inF, K = 128 rows)
-      const uint32_t idg = make_idesc(64, inF, 1, 1);
+      const uint32_t idg = make_idesc(64, inF, 0, 0);
       for (int s = 0; s < kTM / 8; ++s)
-        umma_tf32(tmem + cG1, make_desc(aG + s * 128, 128, ROWB), make_desc(aX0 + s * 128, 128, ROWB), idg,
-                  (!first_tile) || s > 0);
+        umma_tf32(tmem + cG1, make_desc(aTA + s * 2 * kS65 * 16, kS65 * 16, 128), make_desc(aP + s * 2 * S0 * 16, S0 * 16, 128),
+                  idg, (!first_tile) || s > 0);
       umma_commit(bar_m);
     }
-    mbar_wait(bar_m, phase); phase ^= 1;        // tiles X0 / G are rewritten by the next iteration
+    mbar_wait(bar_m, phase); phase ^= 1;        // P / TA are rewritten by the next iteration
     tc_fence_after();
     first_tile = false;
   }
-
   // ---- unfold the folded gradients into this CTA's slot ----
   if (!b.eval_only) {
     float* g = grad_part + (size_t)blockIdx.x * n.g.total;
     const bool has_tile = !first_tile;
     const int o = warp * 16 + lane;                       // accumulator row of this thread in the M = 64 layout
     const bool own = lane < 16;
-    float* S = X1;                                        // scratch [64][65] x 2 (tiles are free now)
-    float* T2 = X1 + 64 * 65;
+    float* S = X1T;                                       // scratch [64][65] x 2 (tiles are free now)
+    float* T2 = X1T + 64 * 65;
     // ---------------- fc2 / ln1 ----------------
     {
       float v[72];
@@ -636,7 +647,7 @@ int update_mlp_tc_launch(const NetDev& n, const float* params, const BatchDev& b
   const TcSmem sm = make_tc_smem(im);
   const size_t bytes = (size_t)sm.total * sizeof(float) + 1024;
   if (bytes > 227 * 1024) { set_error("update_mlp_tc: %zu B shared memory > 227 KB", bytes); return MAPPO_ERR_UNSUPPORTED; }
-  pack_tc_kernel<<<1, 256, 0, st>>>(n, params, image);
+  pack_tc_kernel<<<(im.total + 255) / 256, 256, 0, st>>>(n, params, image);      // one element per thread
   int rc = check_launch("pack_tc_kernel");
   if (rc) return rc;
   static thread_local size_t configured = 0;

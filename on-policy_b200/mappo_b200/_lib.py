@@ -54,7 +54,7 @@ _SIGS = {
     "mappo_policy_step": (_i32, [C.POINTER(NetDesc), _P, C.POINTER(NetDesc), _P] + [_P] * 7 +
                           [_u64, _P, _i32, _i32] + [_P] * 6 + [_P]),
     "mappo_counter_add": (_i32, [_P, _u64, _P]),
-    "mappo_env_insert": (_i32, [_P] * 6 + [_i32] * 5 + [_P] * 8 + [_P]),
+    "mappo_env_insert": (_i32, [_P] * 6 + [_i32] * 5 + [_P] * 8 + [_P, _u64] + [_P]),
     "mappo_compute_returns": (_i32, [_P] * 6 + [_i32, _i32, _f32, _f32, _i32, _i32] + [_P] * 3 + [_P]),
     "mappo_advantages": (_i32, [_P, _P, _P, _P, _i32, _P, _P, _P]),
     "mappo_evaluate_actions": (_i32, [C.POINTER(NetDesc), _P, C.POINTER(Batch), C.POINTER(LossCfg), _P, _P, _P, _P, _P]),

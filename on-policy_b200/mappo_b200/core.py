@@ -300,15 +300,13 @@ class FusedAdam:
         self.net = net
         self.exp_avg = torch.zeros_like(net.flat)
         self.exp_avg_sq = torch.zeros_like(net.flat)
-        self.step_dev = torch.zeros(1, dtype=torch.int32, device=net.device)
+        self.step_dev = torch.zeros(2, dtype=torch.int32, device=net.device)      # {step, ticket}
         self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=net.device)
         self._lr_pinned = torch.empty(1, dtype=torch.float32).pin_memory()
         self.param_groups = [dict(lr=float(lr), eps=float(eps), betas=(0.9, 0.999), weight_decay=0.0,
                                   params=net.parameters())]
         self._lr_on_dev = float(lr)
-        n_blocks = (net.n_params + 255) // 256
-        self.sumsq_part = torch.zeros(n_blocks, dtype=torch.float32, device=net.device)
-        self.n_sumsq_blocks = n_blocks
+        self.sumsq_part = torch.zeros((net.n_params + 31) // 32, dtype=torch.float32, device=net.device)
 
     def sync_lr(self):
         """lr_decay writes param_groups[0]['lr'] (utils/util.py:17-21); mirror it to the device scalar."""
@@ -321,15 +319,17 @@ class FusedAdam:
     def zero_grad(self):
         self.net.grad.zero_()
 
-    def apply(self, max_grad_norm, use_max_grad_norm, grad_norm_out, sumsq_ready=False):
-        """clip_grad_norm_ + Adam on net.grad.  `grad_norm_out`: device double* accumulating the pre-clip norm."""
+    def apply(self, max_grad_norm, use_max_grad_norm, grad_norm_out, n_sumsq_blocks=0):
+        """clip_grad_norm_ + Adam on net.grad.  `grad_norm_out`: device double* accumulating the pre-clip norm.
+        n_sumsq_blocks > 0: `sumsq_part` already holds that many partial sums of squares (from mappo_grad_reduce)."""
         lib = _lib.load()
         st = stream_ptr()
-        if not sumsq_ready:
+        if n_sumsq_blocks <= 0:
             nb = C.c_int32(0)
             check(lib.mappo_grad_sumsq(ptr(self.net.grad), self.net.n_params, ptr(self.sumsq_part), C.byref(nb), st))
+            n_sumsq_blocks = nb.value
         check(lib.mappo_clip_adam(ptr(self.net.flat), ptr(self.net.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
-                                  self.net.n_params, ptr(self.sumsq_part), self.n_sumsq_blocks, ptr(self.lr_dev),
+                                  self.net.n_params, ptr(self.sumsq_part), int(n_sumsq_blocks), ptr(self.lr_dev),
                                   ptr(self.step_dev), float(self.param_groups[0]["eps"]), float(max_grad_norm),
                                   int(bool(use_max_grad_norm)), grad_norm_out, st))
 
@@ -338,11 +338,12 @@ class FusedAdam:
         self.apply(0.0, False, None)
 
     def state_dict(self):
-        return dict(step=int(self.step_dev.item()), exp_avg=self.exp_avg.clone(), exp_avg_sq=self.exp_avg_sq.clone(),
+        return dict(step=int(self.step_dev[0].item()), exp_avg=self.exp_avg.clone(), exp_avg_sq=self.exp_avg_sq.clone(),
                     lr=self.param_groups[0]["lr"])
 
     def load_state_dict(self, sd):
-        self.step_dev.fill_(int(sd["step"]))
+        self.step_dev.zero_()
+        self.step_dev[0] = int(sd["step"])
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
         self.param_groups[0]["lr"] = sd["lr"]
@@ -400,9 +401,9 @@ def launch_update(net: DeviceNet, ws: UpdateWorkspace, batch: Batch, loss: LossC
     nb = C.c_int32(0)
     check(lib.mappo_grad_reduce(ptr(ws.grad_part), n_slots, net.n_params, ptr(net.grad), ptr(opt.sumsq_part),
                                 C.byref(nb), st))
-    sumsq_ready = True
+    n_blocks = nb.value
     if allreduce is not None:
         allreduce(net.grad)
-        sumsq_ready = False
+        n_blocks = 0                      # the norm must be re-derived from the all-reduced gradient
     gn_ptr = C.c_void_p(loss_out.data_ptr() + 8 * grad_norm_slot)
-    opt.apply(max_grad_norm, use_max_grad_norm, gn_ptr, sumsq_ready=sumsq_ready)
+    opt.apply(max_grad_norm, use_max_grad_norm, gn_ptr, n_sumsq_blocks=n_blocks)

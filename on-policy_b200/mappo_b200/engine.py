@@ -20,6 +20,40 @@ from . import _lib
 from ._lib import check, ptr
 from .core import stream_ptr
 
+class SegmentedGraph:
+    """A CUDA graph cut at every collective: [graph][all_reduce][graph][all_reduce]...[graph].
+
+    NCCL calls made through torch.distributed are kept OUT of stream capture (their watchdog / event bookkeeping is
+    not capture-safe in every build); the kernels between two collectives are still one graph launch each.  All
+    segments share one memory pool, so tensors allocated while capturing stay valid across segments."""
+
+    def __init__(self):
+        self.items, self.pool, self.cur = [], torch.cuda.graph_pool_handle(), None
+
+    def begin(self):
+        self.cur = torch.cuda.CUDAGraph()
+        self.cur.capture_begin(pool=self.pool)
+
+    def end(self):
+        self.cur.capture_end()
+        self.items.append(("graph", self.cur))
+        self.cur = None
+
+    def collective(self, t):
+        """Called in place of dist.all_reduce while capturing."""
+        self.end()
+        self.items.append(("allreduce", t))
+        self.begin()
+
+    def replay(self):
+        import torch.distributed as dist
+        for kind, x in self.items:
+            if kind == "graph":
+                x.replay()
+            else:
+                dist.all_reduce(x, op=dist.ReduceOp.SUM)
+
+
 INFO_KEYS = ("value_loss", "policy_loss", "dist_entropy", "actor_grad_norm", "critic_grad_norm", "ratio")
 
 
@@ -53,6 +87,7 @@ class RolloutEngine:
         self.h_loss = torch.zeros(6, dtype=torch.float64).pin_memory()
         self.host = {}
         self.graph = None
+        self._allreduce = "auto"        # "auto": torch.distributed when a multi-rank group exists
         self._epoch_i = 0
         self.launches_per_iteration = 0
 
@@ -124,8 +159,6 @@ class RolloutEngine:
             self.seed, ptr(pol.rng_offset), 0, self.E,
             ptr(b.value_preds[t]), ptr(b.actions[t]), None, ptr(b.action_log_probs[t]),
             ptr(b.rnn_states[t + 1]) if rec else None, ptr(b.rnn_states_critic[t + 1]) if rec else None, st))
-        if noise is None:
-            check(lib.mappo_counter_add(ptr(pol.rng_offset), self.E, st))
         check(lib.mappo_env_insert(
             ptr(self.d_obs[t]), ptr(self.d_share[t]), ptr(self.d_rew[t]), ptr(self.d_done[t]),
             ptr(self.d_active[t]) if self.d_active is not None else None,
@@ -134,8 +167,9 @@ class RolloutEngine:
             ptr(b.obs[t + 1]), ptr(b.share_obs[t + 1]), ptr(b.rewards[t]), ptr(b.masks[t + 1]),
             ptr(b.rnn_states[t + 1]) if rec else None, ptr(b.rnn_states_critic[t + 1]) if rec else None,
             ptr(b.active_masks[t + 1]) if self.d_active is not None else None,
-            ptr(b.available_actions[t + 1]) if self.d_avail is not None else None, st))
-        self.launches_per_iteration += 2 + (1 if noise is None else 0)
+            ptr(b.available_actions[t + 1]) if self.d_avail is not None else None,
+            ptr(pol.rng_offset) if noise is None else None, self.E, st))
+        self.launches_per_iteration += 2
 
     def _compute(self):
         b, pol, lib, st, T = self.buffer, self.policy, self.lib, stream_ptr(), self.T
@@ -159,10 +193,10 @@ class RolloutEngine:
         self._epoch_i += 1
         out = self.d_perm[e]
         if self.rng != "host":
-            st = stream_ptr()
-            check(self.lib.mappo_randperm(n, self.seed, ptr(self.perm_ctr), ptr(out), st))
-            check(self.lib.mappo_counter_add(ptr(self.perm_ctr), 1, st))
-            self.launches_per_iteration += 2
+            # one counter bump per iteration (launch_iteration); epochs are told apart by the seed
+            seed = (self.seed + 0x9E3779B97F4A7C15 * (e + 1)) & 0xFFFFFFFFFFFFFFFF
+            check(self.lib.mappo_randperm(n, seed, ptr(self.perm_ctr), ptr(out), stream_ptr()))
+            self.launches_per_iteration += 1
         return out
 
     def launch_iteration(self):
@@ -174,8 +208,13 @@ class RolloutEngine:
         self._epoch_i = 0
         tr = self.trainer
         n_upd = tr.ppo_epoch * tr.num_mini_batch
-        tr.launch_train(self.buffer, True, self._draw_perm, self.loss_out)
-        per_update = 2 * 3 + (1 if tr.value_normalizer is not None else 0) + 2 + 1   # fwd/bwd, reduce, adam(+step) x2, vn, stats
+        tr.launch_train(self.buffer, True, self._draw_perm, self.loss_out, allreduce=self._allreduce)
+        if self.rng != "host":
+            check(self.lib.mappo_counter_add(ptr(self.perm_ctr), 1, stream_ptr()))
+            self.launches_per_iteration += 1
+        # per update: stats + 2 x (fwd/bwd [+ weight pack in tf32 mode], slot reduce, clip+Adam) + ValueNorm update
+        tf32 = 1 if getattr(tr, "gemm_mode", 0) == 1 else 0
+        per_update = 1 + 2 * (3 + tf32) + (1 if tr.value_normalizer is not None else 0)
         self.launches_per_iteration += n_upd * per_update
         if self.recurrent:
             self.launches_per_iteration += n_upd       # chunk_rows
@@ -190,9 +229,23 @@ class RolloutEngine:
                 self.launch_iteration()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.launch_iteration()
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            seg = SegmentedGraph()
+            self._allreduce = seg.collective
+            try:
+                with torch.cuda.stream(s):
+                    seg.begin()
+                    self.launch_iteration()
+                    seg.end()
+            finally:
+                self._allreduce = "auto"
+            torch.cuda.current_stream().wait_stream(s)
+            self.graph = seg
+        else:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.launch_iteration()
         torch.cuda.synchronize()
 
     def step_resident(self):

@@ -112,7 +112,7 @@ class R_MAPPO():
             return buffer._E
         return B
 
-    def launch_train(self, buffer, update_actor=True, draw_perm=None, loss_out=None):
+    def launch_train(self, buffer, update_actor=True, draw_perm=None, loss_out=None, allreduce="auto"):
         """All launches of reference :171-224 without any host synchronisation (CUDA-graph capturable when
         `draw_perm` is).  Leaves the SUMS of the six train_info terms in `loss_out` (device, float64)."""
         lib = _lib.load()
@@ -120,7 +120,8 @@ class R_MAPPO():
         dev = self.device
         T, E = buffer.episode_length, buffer._E
         B = T * E
-        allreduce = _dist_allreduce()
+        if allreduce == "auto":
+            allreduce = _dist_allreduce()
         draw_perm = draw_perm or self._host_permutation
         loss_out = self._loss_out if loss_out is None else loss_out
         vn = self.value_normalizer.state if self.value_normalizer is not None else None

@@ -298,7 +298,7 @@ def test_clip_adam_matches_torch_adam():
         norm_out.zero_()
         mine.apply(10.0, True, norm_out.data_ptr())
         assert_close(norm_out.item(), float(total), 1e-5, 1e-7, "grad norm")
-        assert_close(net.flat.cpu().numpy(), ref.detach().numpy(), 1e-5, 1e-7, f"params after step {step}")
+        assert_close(net.flat.cpu().numpy(), ref.detach().numpy(), 1e-4, 5e-7, f"params after step {step}")
 
 
 @pytest.mark.parametrize("name", MLP_CASES)
