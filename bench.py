@@ -238,6 +238,17 @@ def run_gpu(a):
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
 
+    breakdown = eng.phase_breakdown() if world == 1 else None
+    if breakdown is not None and a.gemm == "tf32":
+        import ctypes as C
+        from mappo_b200 import _lib
+        t = (C.c_int64 * 16)()
+        torch.cuda.synchronize()
+        _lib.load().mappo_debug_tc_timing(t)
+        names = ["setup", "S1", "fc1_mma", "S3", "fc2_mma", "S5", "head_mma", "S7_loss", "dx2_Gh_mma", "S9", "dx1_G2_mma",
+                 "S11", "G1_mma", "unfold", "tail"]
+        breakdown["tc_tile_cycles_warm"] = {nm: int(t[i + 1] - t[i]) for i, nm in enumerate(names)}
+        breakdown["tc_tile_cycles_warm"]["total"] = int(t[15] - t[0])
     # ---- the dominant kernel, timed live with CUDA events on its own stream (eager pass, one train()) ----
     kt = time_update_kernel(eng, cfg, flush)
 
@@ -276,7 +287,7 @@ def run_gpu(a):
                              "avg_launch_ms": kt["avg_ms"], "launches_timed": kt["n"],
                              "algorithmic_gflop_per_launch": (fa + fc) / 2 / 1e9,
                              "kernel_share_of_step": kt["avg_ms"] * 2 * cfg.ppo_epoch / (ms_max / a.steps)},
-                "clocks": clocks, "wall_s_timed_region": t_wall,
+                "clocks": clocks, "wall_s_timed_region": t_wall, "phase_breakdown_ms": breakdown,
                 "train_info_last": info}
         if cpu_rate is not None:
             line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port",

@@ -128,7 +128,13 @@ int32_t mappo_policy_step(const mappo_net_desc_t* actor_desc, const float* actor
                           uint64_t rng_seed, const uint64_t* rng_offset_dev, int32_t deterministic,
                           int32_t n_rows,
                           float* values, float* actions, int64_t* actions_i64, float* logp,
-                          float* h_actor_out, float* h_critic_out, void* stream);
+                          float* h_actor_out, float* h_critic_out,
+                          const float* actor_image, const float* critic_image, void* stream);
+/* Optional: the rollout weights do not change during the T collect steps of an iteration.  Packing them once into
+ * the kernel's shared-memory layout lets every policy_step CTA fetch them with one TMA bulk copy
+ * (cp.async.bulk + mbarrier) -- pass the images to mappo_policy_step (NULL = load from the flat parameters). */
+int32_t mappo_rollout_image_floats(const mappo_net_desc_t* desc);
+int32_t mappo_pack_rollout_weights(const mappo_net_desc_t* desc, const float* params, float* image, void* stream);
 
 /* Advance the device-side Philox offset after a sampling step (no host round trip). */
 int32_t mappo_counter_add(uint64_t* counter_dev, uint64_t inc, void* stream);
@@ -203,6 +209,8 @@ int64_t mappo_update_workspace_floats(const mappo_net_desc_t* desc, int32_t n_ro
 int32_t mappo_update_grad_slots(const mappo_net_desc_t* desc, int32_t n_rows, int32_t gemm_mode);
 /* 1 if the tcgen05 (MAPPO_GEMM_TF32) kernels cover this net, else 0 (callers then use MAPPO_GEMM_FP32). */
 int32_t mappo_tf32_supported(const mappo_net_desc_t* desc);
+/* Diagnostic: clock64() phase stamps of CTA 0 of the last tcgen05 update launch (16 values, host pointer; syncs). */
+int32_t mappo_debug_tc_timing(int64_t* out16);
 int32_t mappo_update_fwd_bwd(const mappo_net_desc_t* desc, const float* params, const mappo_batch_t* batch,
                              const mappo_loss_cfg_t* loss, const double* norm_stats,
                              const double* adv_stats, const float* vn_state,
@@ -225,6 +233,15 @@ int32_t mappo_evaluate_actions(const mappo_net_desc_t* desc, const float* params
  *                       use_max_grad_norm; Adam step with g*coef; ++step_dev[0]; *grad_norm_out += total.
  *                       step_dev points to TWO ints: {Adam step count, scratch ticket (keep 0)}.
  * lr is read from device memory (lr_dev[0]) so lr_decay (utils/util.py:17-21) needs no re-capture. */
+/* Floats per gradient slot (`grad_part` holds n_slots of them): n_params for the fp32 build; the tcgen05 build
+ * parks its still-folded TMEM accumulators (dW', db' columns) instead. */
+int32_t mappo_update_slot_floats(const mappo_net_desc_t* desc, int32_t gemm_mode);
+/* Slot reduction for either build: sums the slots into the flat gradient `grad` [n_params] (tcgen05 build: sums the raw
+ * accumulators into the workspace, then unfolds the LayerNorm/bias folding once) and leaves *n_blocks_out partial sums
+ * of squares in sumsq_part for mappo_clip_adam. */
+int32_t mappo_update_finish(const mappo_net_desc_t* desc, const float* params, const float* grad_part, int32_t n_slots,
+                            int32_t gemm_mode, float* grad, float* sumsq_part, int32_t* n_blocks_out, float* workspace,
+                            void* stream);
 int32_t mappo_grad_reduce(const float* grad_part, int32_t n_slots, int32_t n_params, float* grad,
                           float* sumsq_part, int32_t* n_sumsq_blocks_out, void* stream);
 /* Per-block sums of squares of an already reduced (e.g. all-reduced) gradient vector. */

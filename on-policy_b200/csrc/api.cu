@@ -76,6 +76,9 @@ int update_mlp_launch(const NetDev&, const float*, const BatchDev&, const LossDe
                       const float*, float*, int, double*, cudaStream_t, float* feat_out = nullptr,
                       const float* dfeat_in = nullptr);
 bool update_mlp_tc_supported(const NetDev& n);
+int debug_tc_timing(long long* out16);
+int update_mlp_tc_slot_floats(const NetDev& n);
+int update_mlp_tc_unfold_launch(const NetDev&, const float*, const float*, float*, float*, cudaStream_t);
 int64_t update_mlp_tc_workspace_floats(const NetDev& n);
 int update_mlp_tc_slots(const NetDev& n, int n_rows, int sm_count);
 int update_mlp_tc_launch(const NetDev&, const float*, const BatchDev&, const LossDev&, const double*, const double*,
@@ -97,6 +100,8 @@ int sumsq_launch(const float*, int, float*, int*, cudaStream_t);
 int clip_adam_launch(float*, const float*, float*, float*, int, const float*, int, const float*, int*, float, float,
                      int, double*, cudaStream_t);
 int counter_add_launch(uint64_t*, uint64_t, cudaStream_t);
+int pack_rollout_launch(const NetDev&, const float*, float*, cudaStream_t);
+int rollout_image_floats(const NetDev&);
 
 static int g_sm_count = 0;
 static int sm_count() {
@@ -147,7 +152,7 @@ int32_t mappo_policy_step(const mappo_net_desc_t* ad, const float* ap, const map
                           const float* masks, const float* avail, const float* exp_noise, uint64_t rng_seed,
                           const uint64_t* rng_offset_dev, int32_t deterministic, int32_t n_rows, float* values,
                           float* actions, int64_t* actions_i64, float* logp, float* h_a_out, float* h_c_out,
-                          void* stream) {
+                          const float* actor_image, const float* critic_image, void* stream) {
   const bool has_a = ap != nullptr, has_c = cp != nullptr;
   if (!has_a && !has_c) { set_error("policy_step: both nets are NULL"); return MAPPO_ERR_INVALID; }
   if (n_rows <= 0) return MAPPO_OK;
@@ -170,6 +175,7 @@ int32_t mappo_policy_step(const mappo_net_desc_t* ad, const float* ap, const map
   PolArgs a;
   memset(&a, 0, sizeof(a));
   a.params[0] = ap; a.params[1] = cp;
+  a.image[0] = actor_image; a.image[1] = critic_image;
   a.in[0] = obs; a.in[1] = share_obs;
   a.h_in[0] = h_a_in; a.h_in[1] = h_c_in;
   a.h_out[0] = h_a_out; a.h_out[1] = h_c_out;
@@ -179,6 +185,18 @@ int32_t mappo_policy_step(const mappo_net_desc_t* ad, const float* ap, const map
   a.n_avail = has_a ? na.head_dim[0] : 0;
   a.values = values; a.actions = actions; a.actions_i64 = actions_i64; a.logp = logp;
   return policy_step_launch(has_a ? &na : nullptr, has_c ? &nc : nullptr, a, (cudaStream_t)stream);
+}
+
+int32_t mappo_rollout_image_floats(const mappo_net_desc_t* desc) {
+  if (validate_desc(desc)) return -1;
+  return rollout_image_floats(make_net_dev(desc));
+}
+
+int32_t mappo_pack_rollout_weights(const mappo_net_desc_t* desc, const float* params, float* image, void* stream) {
+  int rc = validate_desc(desc);
+  if (rc) return rc;
+  if (!params || !image || (reinterpret_cast<uintptr_t>(image) & 15)) { set_error("pack_rollout_weights: NULL or unaligned image"); return MAPPO_ERR_INVALID; }
+  return pack_rollout_launch(make_net_dev(desc), params, image, (cudaStream_t)stream);
 }
 
 int32_t mappo_counter_add(uint64_t* counter_dev, uint64_t inc, void* stream) {
@@ -274,6 +292,8 @@ static int fill_batch(const mappo_net_desc_t* d, const mappo_batch_t* b, BatchDe
   return MAPPO_OK;
 }
 
+int32_t mappo_debug_tc_timing(int64_t* out16) { return debug_tc_timing(reinterpret_cast<long long*>(out16)); }
+
 int32_t mappo_tf32_supported(const mappo_net_desc_t* desc) {
   if (validate_desc(desc)) return 0;
   return update_mlp_tc_supported(make_net_dev(desc)) ? 1 : 0;
@@ -283,7 +303,34 @@ int64_t mappo_update_workspace_floats(const mappo_net_desc_t* desc, int32_t n_ro
   if (validate_desc(desc)) return -1;
   const NetDev n = make_net_dev(desc);
   if (desc->recurrent) return update_gru_workspace_floats(n, n_rows);
-  return (gemm_mode == MAPPO_GEMM_TF32 && update_mlp_tc_supported(n)) ? update_mlp_tc_workspace_floats(n) : 0;
+  // tf32: [folded weight image][slot-summed raw accumulators]
+  return (gemm_mode == MAPPO_GEMM_TF32 && update_mlp_tc_supported(n))
+             ? update_mlp_tc_workspace_floats(n) + update_mlp_tc_slot_floats(n) : 0;
+}
+
+int32_t mappo_update_slot_floats(const mappo_net_desc_t* desc, int32_t gemm_mode) {
+  if (validate_desc(desc)) return -1;
+  const NetDev n = make_net_dev(desc);
+  if (!desc->recurrent && gemm_mode == MAPPO_GEMM_TF32 && update_mlp_tc_supported(n)) return update_mlp_tc_slot_floats(n);
+  return n.g.total;
+}
+
+int32_t mappo_update_finish(const mappo_net_desc_t* desc, const float* params, const float* grad_part, int32_t n_slots,
+                            int32_t gemm_mode, float* grad, float* sumsq_part, int32_t* n_blocks_out, float* workspace,
+                            void* stream) {
+  int rc = validate_desc(desc);
+  if (rc) return rc;
+  if (!params || !grad_part || !grad || !sumsq_part || n_slots <= 0) { set_error("update_finish: bad arguments"); return MAPPO_ERR_INVALID; }
+  const NetDev n = make_net_dev(desc);
+  if (!desc->recurrent && gemm_mode == MAPPO_GEMM_TF32 && update_mlp_tc_supported(n)) {
+    if (!workspace) { set_error("update_finish: tf32 mode needs the workspace"); return MAPPO_ERR_INVALID; }
+    float* raw_sum = workspace + update_mlp_tc_workspace_floats(n);
+    rc = grad_reduce_launch(grad_part, n_slots, update_mlp_tc_slot_floats(n), raw_sum, nullptr, nullptr, (cudaStream_t)stream);
+    if (rc) return rc;
+    if (n_blocks_out) *n_blocks_out = 1;
+    return update_mlp_tc_unfold_launch(n, params, raw_sum, grad, sumsq_part, (cudaStream_t)stream);
+  }
+  return grad_reduce_launch(grad_part, n_slots, n.g.total, grad, sumsq_part, n_blocks_out, (cudaStream_t)stream);
 }
 
 int32_t mappo_update_grad_slots(const mappo_net_desc_t* desc, int32_t n_rows, int32_t gemm_mode) {

@@ -193,6 +193,78 @@ __device__ __forceinline__ void tile_mm(const float* __restrict__ inT, int K, co
   }
 }
 
+// Fused layer: Y = LayerNorm(act(X W^T + b)) * gamma + beta for N == 16*NJ output features, the LayerNorm statistics
+// taken with warp shuffles across the 16 threads that share a row (no shared-memory pass, no extra barriers).
+// Optionally also leaves act(.) in AT and (mean, rstd) per row for a later backward pass.
+template <int TR, int NJ>
+__device__ __forceinline__ void tile_mm_ln(const float* __restrict__ inT, int K, const float* __restrict__ W, int ldw,
+                                           const float* __restrict__ bias, int act, const float* __restrict__ gamma,
+                                           const float* __restrict__ beta, float* __restrict__ AT,
+                                           float* __restrict__ YT, float* __restrict__ mean, float* __restrict__ rstd,
+                                           int tid) {
+  constexpr int LD = Tile<TR>::LD;
+  constexpr float invN = 1.0f / (16.f * NJ);
+  const int tx = tid & 15, r0 = (tid >> 4) * 4;
+  float acc[4][NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) acc[0][j] = acc[1][j] = acc[2][j] = acc[3][j] = 0.f;
+  const float* ap = inT + r0;
+  const float* wp = W + tx * ldw;
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    const float4 a = *reinterpret_cast<const float4*>(ap + k * LD);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const float w = wp[16 * j * ldw + k];
+      acc[0][j] = fmaf(a.x, w, acc[0][j]);
+      acc[1][j] = fmaf(a.y, w, acc[1][j]);
+      acc[2][j] = fmaf(a.z, w, acc[2][j]);
+      acc[3][j] = fmaf(a.w, w, acc[3][j]);
+    }
+  }
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const float b = bias[tx + 16 * j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { acc[i][j] = act_fwd(acc[i][j] + b, act); s[i] += acc[i][j]; }
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+  float m[4], v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) m[i] = s[i] * invN;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float d = acc[i][j] - m[i]; v[i] = fmaf(d, d, v[i]); }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  float rs[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) rs[i] = 1.0f / sqrtf(v[i] * invN + kLnEps);
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int n = tx + 16 * j;
+    const float g = gamma[n], be = beta[n];
+    if (AT) *reinterpret_cast<float4*>(AT + n * LD + r0) = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
+    float4 y;
+    y.x = fmaf((acc[0][j] - m[0]) * rs[0], g, be);
+    y.y = fmaf((acc[1][j] - m[1]) * rs[1], g, be);
+    y.z = fmaf((acc[2][j] - m[2]) * rs[2], g, be);
+    y.w = fmaf((acc[3][j] - m[3]) * rs[3], g, be);
+    *reinterpret_cast<float4*>(YT + n * LD + r0) = y;
+  }
+  if (tx == 0 && mean) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { mean[r0 + i] = m[i]; rstd[r0 + i] = rs[i]; }
+  }
+}
+
 // Weight gradient: g[o*ldg + k] += sum_r dYT[o][r] * XT[k][r],  o < No (No <= NTY*NI), k < Nk (Nk <= 16*NJ).
 // g is the CTA-private slot in global memory (plain read-modify-write, same thread every tile).
 template <int TR, int NI, int NJ>

@@ -6,6 +6,7 @@ namespace mappo {
 
 struct PolArgs {
   const float* params[2];      // [0] actor, [1] critic
+  const float* image[2];       // optional pre-packed shared-memory weight images (mappo_pack_rollout_weights)
   const float* in[2];          // obs, share_obs
   const float* h_in[2];
   float* h_out[2];

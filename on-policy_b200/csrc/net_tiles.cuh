@@ -43,6 +43,7 @@ template <int TR> struct BaseTiles {
   float* mean[kMaxLayers + 2];      // [TR]      index 0 = feature norm, 1.. = layer LNs
   float* rstd[kMaxLayers + 2];
   float* red;                       // [8*TR]
+  bool keep_act;                    // training: keep act(.) tiles A[l] for the backward pass
 };
 
 // base.feature_norm + base.mlp (mlp.py:26-30, 52-57) on the tile already loaded in t.x0 (raw input).
@@ -62,14 +63,15 @@ __device__ __forceinline__ void base_forward(const NetDev& n, const SmemW& s, co
     }
     __syncthreads();
   }
-  tile_mm<TR, NJH>(t.x0, n.in_dim, sW + s.fc1_w, s.ld1, 1, H, sW + s.fc1_b, act, t.A[0], tid);
+  // Linear + act + LayerNorm fused per layer (row statistics by warp shuffles); A / mean / rstd are kept for backward
+  // when the caller's tiles do not alias (training), and are simply scratch for the rollout.
+  tile_mm_ln<TR, NJH>(t.x0, n.in_dim, sW + s.fc1_w, s.ld1, sW + s.fc1_b, act, sW + s.ln1_w, sW + s.ln1_b,
+                      t.keep_act ? t.A[0] : nullptr, t.Y[0], t.mean[1], t.rstd[1], tid);
   __syncthreads();
-  tile_layernorm<TR>(t.A[0], H, sW + s.ln1_w, sW + s.ln1_b, t.Y[0], t.mean[1], t.rstd[1], t.red, tid);
   for (int l = 0; l < n.layer_n; ++l) {
-    tile_mm<TR, NJH>(t.Y[l], H, sW + s.fc2_w[l], s.ldh, 1, H, sW + s.fc2_b[l], act, t.A[l + 1], tid);
+    tile_mm_ln<TR, NJH>(t.Y[l], H, sW + s.fc2_w[l], s.ldh, sW + s.fc2_b[l], act, sW + s.ln2_w[l], sW + s.ln2_b[l],
+                        t.keep_act ? t.A[l + 1] : nullptr, t.Y[l + 1], t.mean[l + 2], t.rstd[l + 2], tid);
     __syncthreads();
-    tile_layernorm<TR>(t.A[l + 1], H, sW + s.ln2_w[l], sW + s.ln2_b[l], t.Y[l + 1], t.mean[l + 2], t.rstd[l + 2],
-                       t.red, tid);
   }
 }
 
@@ -171,22 +173,57 @@ __device__ __forceinline__ LossConsts make_loss_consts(const NetDev& n, const Lo
   return c;
 }
 
+// The per-row scalars the loss needs, loadable EARLY (right after the row id is known) so their global-memory latency
+// hides behind the forward pass instead of sitting between the logits and the gradient.
+struct RowIn {
+  float active, v_old, ret, adv;
+  float action[kMaxHeads], old_logp[kMaxHeads];
+};
+// load that the compiler may not sink towards its first use (so it is issued where it is written)
+__device__ __forceinline__ float ldg_pinned(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ RowIn load_row_in(const NetDev& n, const BatchDev& b, int gr) {
+  RowIn q;
+  q.active = q.v_old = q.ret = q.adv = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMaxHeads; ++k) q.action[k] = q.old_logp[k] = 0.f;
+  if (gr < 0) return q;
+  q.active = ldg_pinned(b.active_masks + gr);
+  if (n.is_critic) {
+    q.v_old = ldg_pinned(b.value_preds + gr);
+    q.ret = ldg_pinned(b.returns + gr);
+  } else {
+    q.adv = ldg_pinned(b.advantages + gr);
+#pragma unroll
+    for (int k = 0; k < kMaxHeads; ++k)
+      if (k < n.n_heads) {
+        q.action[k] = ldg_pinned(b.actions + (size_t)gr * b.act_shape + k);
+        q.old_logp[k] = ldg_pinned(b.old_logp + (size_t)gr * b.act_shape + k);
+      }
+  }
+  return q;
+}
+
 // Row r of the logits tile lgT (storage row gr, minibatch position p): accumulates the loss terms into acc
 // (critic: [0] value_loss; actor: [0] policy_loss, [1] entropy, [2] sum of ratios) and overwrites the logits /
 // value with d(loss)/d(logit | value).
 template <int LD>
-__device__ __forceinline__ void row_loss(const NetDev& n, const BatchDev& b, const LossDev& L, const LossConsts& c,
-                                         float* __restrict__ lgT, int r, int gr, int p, double (&acc)[3]) {
+__device__ __forceinline__ void row_loss_pre(const NetDev& n, const BatchDev& b, const LossDev& L, const LossConsts& c,
+                                             float* __restrict__ lgT, int r, int gr, int p, const RowIn& q,
+                                             double (&acc)[3]) {
   const int Atot = n.head_total;
   if (gr < 0) {
     for (int j = 0; j < Atot; ++j) lgT[j * LD + r] = 0.f;
     return;
   }
   if (n.is_critic) {
-    const float act = b.active_masks[gr];
+    const float act = q.active;
     const float w = L.use_value_active ? (float)((double)act / c.sum_active) : (float)(1.0 / c.n_rows_d);
-    const float v = lgT[r], vo = b.value_preds[gr];
-    const float ret = b.returns[gr];
+    const float v = lgT[r], vo = q.v_old;
+    const float ret = q.ret;
     const float target = L.use_valuenorm ? (ret - c.vmean) * c.vrs : ret;       // valuenorm.py:57-66
     const float d = v - vo;
     const float vclip = vo + fminf(fmaxf(d, -L.clip), L.clip);                  // r_mappo.py:62-63
@@ -213,9 +250,9 @@ __device__ __forceinline__ void row_loss(const NetDev& n, const BatchDev& b, con
     lgT[r] = dv * w * L.vl_coef;
     return;
   }
-  const float act = b.active_masks[gr];
+  const float act = q.active;
   const float w = L.use_policy_active ? (float)((double)act / c.sum_active) : (float)(1.0 / c.n_rows_d);
-  const float adv = (b.advantages[gr] - c.adv_mean) * c.adv_inv;
+  const float adv = (q.adv - c.adv_mean) * c.adv_inv;
   const float* av = (b.avail && n.n_heads == 1) ? b.avail + (size_t)gr * b.n_avail : nullptr;
   const float inv_heads = 1.0f / (float)n.n_heads;
   int off = 0;
@@ -223,7 +260,7 @@ __device__ __forceinline__ void row_loss(const NetDev& n, const BatchDev& b, con
     const int A = n.head_dim[k];
     float lse;
     head_lse<LD>(lgT, off, A, r, av, lse);
-    const int a = (int)b.actions[(size_t)gr * b.act_shape + k];
+    const int a = (int)q.action[k];
     float ent = 0.f, lp_a = 0.f;
     for (int j = 0; j < A; ++j) {
       float lgt = lgT[(off + j) * LD + r];
@@ -234,7 +271,7 @@ __device__ __forceinline__ void row_loss(const NetDev& n, const BatchDev& b, con
       if (j == a) lp_a = lp;
     }
     if (b.eval_out) b.eval_out[(size_t)p * b.act_shape + k] = lp_a;
-    const float ratio = expf(lp_a - b.old_logp[(size_t)gr * b.act_shape + k]);        // r_mappo.py:129
+    const float ratio = expf(lp_a - q.old_logp[k]);                                    // r_mappo.py:129
     const float s1 = ratio * adv;
     const float s2 = fminf(fmaxf(ratio, 1.f - L.clip), 1.f + L.clip) * adv;
     const float mn = fminf(s1, s2);
@@ -258,6 +295,14 @@ __device__ __forceinline__ void row_loss(const NetDev& n, const BatchDev& b, con
     }
     off += A;
   }
+}
+
+
+template <int LD>
+__device__ __forceinline__ void row_loss(const NetDev& n, const BatchDev& b, const LossDev& L, const LossConsts& c,
+                                         float* __restrict__ lgT, int r, int gr, int p, double (&acc)[3]) {
+  const RowIn q = load_row_in(n, b, gr);
+  row_loss_pre<LD>(n, b, L, c, lgT, r, gr, p, q, acc);
 }
 
 }  // namespace mappo

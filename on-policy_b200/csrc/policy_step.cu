@@ -23,6 +23,48 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 
+// ---- packed weight image: the shared-memory weight layout (odd leading dimensions), pre-built in global memory so a
+//      CTA fetches it with ONE TMA bulk copy instead of ~70 address-computing cp.async per thread ----
+__device__ __forceinline__ int simt_image_offset(const NetDev& n, const SmemW& s, int i) {
+  const int H = n.hid, I = n.in_dim;
+  auto mat = [&](int base, int rows_cols, int img, int ld, int cols) { const int t = i - base; const int r = t / cols; return img + r * ld + (t - r * cols); };
+  (void)mat;
+  const mappo_net_layout_t& g = n.g;
+  if (n.use_fn) {
+    if (i >= g.fn_w && i < g.fn_w + I) return s.fn_w + (i - g.fn_w);
+    if (i >= g.fn_b && i < g.fn_b + I) return s.fn_b + (i - g.fn_b);
+  }
+  if (i >= g.fc1_w && i < g.fc1_w + H * I) { const int t = i - g.fc1_w, r = t / I; return s.fc1_w + r * s.ld1 + (t - r * I); }
+  if (i >= g.fc1_b && i < g.fc1_b + H) return s.fc1_b + (i - g.fc1_b);
+  if (i >= g.ln1_w && i < g.ln1_w + H) return s.ln1_w + (i - g.ln1_w);
+  if (i >= g.ln1_b && i < g.ln1_b + H) return s.ln1_b + (i - g.ln1_b);
+  for (int l = 0; l < n.layer_n; ++l) {
+    if (i >= g.fc2_w[l] && i < g.fc2_w[l] + H * H) { const int t = i - g.fc2_w[l], r = t / H; return s.fc2_w[l] + r * s.ldh + (t - r * H); }
+    if (i >= g.fc2_b[l] && i < g.fc2_b[l] + H) return s.fc2_b[l] + (i - g.fc2_b[l]);
+    if (i >= g.ln2_w[l] && i < g.ln2_w[l] + H) return s.ln2_w[l] + (i - g.ln2_w[l]);
+    if (i >= g.ln2_b[l] && i < g.ln2_b[l] + H) return s.ln2_b[l] + (i - g.ln2_b[l]);
+  }
+  if (n.recurrent) {
+    if (i >= g.gru_wih && i < g.gru_wih + 3 * H * H) { const int t = i - g.gru_wih, r = t / H; return s.wih + r * s.ldh + (t - r * H); }
+    if (i >= g.gru_whh && i < g.gru_whh + 3 * H * H) { const int t = i - g.gru_whh, r = t / H; return s.whh + r * s.ldh + (t - r * H); }
+    if (i >= g.gru_bih && i < g.gru_bih + 3 * H) return s.bih + (i - g.gru_bih);
+    if (i >= g.gru_bhh && i < g.gru_bhh + 3 * H) return s.bhh + (i - g.gru_bhh);
+    if (i >= g.rnn_ln_w && i < g.rnn_ln_w + H) return s.rln_w + (i - g.rnn_ln_w);
+    if (i >= g.rnn_ln_b && i < g.rnn_ln_b + H) return s.rln_b + (i - g.rnn_ln_b);
+  }
+  if (i >= g.head_w && i < g.head_w + n.head_total * H) { const int t = i - g.head_w, r = t / H; return s.head_w + r * s.ldh + (t - r * H); }
+  if (i >= g.head_b && i < g.head_b + n.head_total) return s.head_b + (i - g.head_b);
+  return -1;
+}
+
+__global__ void __launch_bounds__(256) pack_rollout_kernel(const NetDev n, const float* __restrict__ p, float* __restrict__ img) {
+  const SmemW s = make_smem_w(n, true);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n.g.total; i += gridDim.x * blockDim.x) {
+    const int o = simt_image_offset(n, s, i);
+    if (o >= 0) img[o] = p[i];
+  }
+}
+
 struct PolSmem { int w, x0, xh0, s0, s1, h, gi, gh, stats, red, rowid, total; };
 
 __host__ __device__ inline PolSmem make_pol_smem(const NetDev& n, const SmemW& s) {
@@ -65,19 +107,41 @@ policy_step_kernel(const NetDev na, const NetDev nc, const PolArgs a, int first_
   BaseTiles<TR> t;
   t.xh0 = smem + u.xh0;
   t.x0 = smem + u.x0;
-  for (int l = 0; l <= kMaxLayers; ++l) { t.A[l] = smem + u.s0; t.Y[l] = smem + u.s1; }
+  // fused layers read Y[l-1] and write Y[l]: ping-pong between the two scratch tiles
+  for (int l = 0; l <= kMaxLayers; ++l) { t.A[l] = nullptr; t.Y[l] = smem + ((l & 1) ? u.s0 : u.s1); }
+  t.keep_act = false;
   for (int l = 0; l < kMaxLayers + 2; ++l) { t.mean[l] = smem + u.stats + 2 * l * TR; t.rstd[l] = t.mean[l] + TR; }
   t.red = smem + u.red;
   int* rowid = reinterpret_cast<int*>(smem + u.rowid);
   const int H = n.hid;
 
-  load_weights(sW, s, n, a.params[which], true, tid, NT);
+  __shared__ uint64_t wbar;
+  const float* image = a.image[which];
+  if (image) {                                        // one TMA bulk copy of the pre-packed image (UBLKCP)
+    if (tid == 0) {
+      const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&wbar);
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(s.total * 4)) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"((uint32_t)__cvta_generic_to_shared(sW)), "l"(image), "r"((uint32_t)(s.total * 4)), "r"(bar) : "memory");
+    }
+  } else {
+    load_weights(sW, s, n, a.params[which], true, tid, NT);
+  }
   const int row0 = blockIdx.x * TR;
   if (tid < TR) rowid[tid] = row0 + tid < a.n_rows ? row0 + tid : -1;
   __syncthreads();
   load_rows_T<TR>(a.in[which], n.in_dim, rowid, t.x0, tid);
+  if (image) {                                        // every thread waits for the image (barrier init is ordered by the
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&wbar);   // __syncthreads() above)
+    uint32_t ok = 0;
+    while (!ok)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(bar), "r"(0u) : "memory");
+  }
   base_forward<TR, NJH>(n, s, sW, t, tid);
-  const float* feat = t.Y[n.layer_n];          // = s1
+  const float* feat = t.Y[n.layer_n];
 
   if (n.recurrent) {
     // h <- h * mask (rnn.py:27), one GRU step (torch gate order r,z,n), LN (rnn.py:79)
@@ -101,7 +165,7 @@ policy_step_kernel(const NetDev na, const NetDev nc, const PolArgs a, int first_
                        gi + gate * H * LD, tid, true);
     tile_mm<TR, NJH>(hT, H, sW + s.whh + 2 * H * s.ldh, s.ldh, 1, H, sW + s.bhh + 2 * H, ACT_NONE, gh, tid);
     __syncthreads();
-    float* hn = smem + u.s0;                   // new hidden state (pre-LN)
+    float* hn = (feat == smem + u.s0) ? smem + u.s1 : smem + u.s0;      // new hidden state (pre-LN): the free tile
     for (int i = tid; i < TR * H; i += NT) {
       const int c = i / TR, r = i - c * TR;
       const int o = c * LD + r;
@@ -116,9 +180,10 @@ policy_step_kernel(const NetDev na, const NetDev nc, const PolArgs a, int first_
       const int g = rowid[r];
       if (g >= 0 && a.h_out[which]) a.h_out[which][(size_t)g * H + c] = hn[c * LD + r];
     }
-    tile_layernorm<TR>(hn, H, sW + s.rln_w, sW + s.rln_b, smem + u.s1, t.mean[kMaxLayers + 1] + 2 * TR,
+    float* ln_out = (hn == smem + u.s0) ? smem + u.s1 : smem + u.s0;    // old feat tile: gates are done with it
+    tile_layernorm<TR>(hn, H, sW + s.rln_w, sW + s.rln_b, ln_out, t.mean[kMaxLayers + 1] + 2 * TR,
                        t.rstd[kMaxLayers + 1] + 2 * TR, t.red, tid);
-    feat = smem + u.s1;
+    feat = ln_out;
   }
 
   float* lgT = smem + u.gi;
@@ -198,6 +263,12 @@ int policy_step_launch(const NetDev* na, const NetDev* nc, const PolArgs& a, cud
   kern<<<grid, 4 * kPolTR, bytes, st>>>(na ? *na : ref, nc ? *nc : ref, a, na ? 0 : 1);
   return check_launch("policy_step_kernel");
 }
+
+int pack_rollout_launch(const NetDev& n, const float* params, float* image, cudaStream_t st) {
+  pack_rollout_kernel<<<(n.g.total + 255) / 256, 256, 0, st>>>(n, params, image);
+  return check_launch("pack_rollout_kernel");
+}
+int rollout_image_floats(const NetDev& n) { return make_smem_w(n, true).total; }
 
 int counter_add_launch(uint64_t* c, uint64_t inc, cudaStream_t st) {
   counter_add_kernel<<<1, 1, 0, st>>>(c, inc);

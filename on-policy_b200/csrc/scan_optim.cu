@@ -293,7 +293,7 @@ grad_reduce_kernel(const float* __restrict__ part, int n_slots, int P, float* __
     float q = g * g;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    if (pi == 0) sumsq_part[blockIdx.x] = q;
+    if (pi == 0 && sumsq_part) sumsq_part[blockIdx.x] = q;
   }
 }
 

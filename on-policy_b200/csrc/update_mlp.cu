@@ -61,6 +61,7 @@ update_mlp_kernel(const NetDev n, const float* __restrict__ params, const BatchD
   for (int l = 0; l <= kMaxLayers; ++l) { t.A[l] = smem + u.A[l]; t.Y[l] = smem + u.Y[l]; }
   for (int l = 0; l < kMaxLayers + 2; ++l) { t.mean[l] = smem + u.stats + 2 * l * TR; t.rstd[l] = t.mean[l] + TR; }
   t.red = smem + u.red;
+  t.keep_act = true;
   float* gA = smem + u.gA;
   float* gB = smem + u.gB;
   float* lgT = smem + u.lg;

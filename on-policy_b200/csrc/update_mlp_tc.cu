@@ -88,7 +88,21 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
                : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
                : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+  const uint32_t* u = reinterpret_cast<const uint32_t*>(v);
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// tanh on the SFU (MUFU.TANH): max relative error 2^-11, the same class as the tf32 rounding of the GEMM inputs.
+__device__ __forceinline__ float act_fwd_tc(float z, int act) {
+  if (act == ACT_RELU) return fmaxf(z, 0.f);
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(z));
+  return y;
+}
 
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t u;
@@ -128,6 +142,91 @@ __host__ __device__ inline TcImage make_tc_image(const NetDev& n) {
   m.wht = m.w2t + 64 * 64;
   m.total = m.wht + m.NH * 64;
   return m;
+}
+
+// Raw per-CTA gradient slot of the tcgen05 kernel: the folded accumulators exactly as they sit in TMEM.
+//   g2 [64][72] = dW2'  (column 64 = db2'),  g1 [64][inF] = dW1' (column in = db1'),  gh [64][NH] = dWh'^T (row = feature),
+//   dbh [NH].  mappo_update_finish sums the slots and unfolds ONCE (tc_unfold_kernel) instead of once per CTA.
+struct TcRaw { int g2, g1, gh, dbh, total; };
+__host__ __device__ inline TcRaw make_tc_raw(const TcImage& m) {
+  TcRaw r;
+  r.g2 = 0;
+  r.g1 = r.g2 + 64 * kHF;
+  r.gh = r.g1 + 64 * m.inF;
+  r.dbh = r.gh + 64 * m.NH;
+  r.total = (r.dbh + m.NH + 3) & ~3;
+  return r;
+}
+
+// dW = dW' diag(gamma_in), db = dW'[:, one], dgamma_in = colsum(dW' .* W), dbeta_in = W^T db'   (chain rule of the
+// folding), for the three layers, from the slot-summed raw accumulators.  One CTA; also emits sum(g^2).
+__global__ void __launch_bounds__(512)
+tc_unfold_kernel(const NetDev n, const float* __restrict__ p, const float* __restrict__ raw, float* __restrict__ g,
+                 float* __restrict__ sumsq_part) {
+  __shared__ float part_g[8][64], part_b[8][64], sred[16];
+  const TcImage m = make_tc_image(n);
+  const TcRaw R = make_tc_raw(m);
+  const int tid = threadIdx.x, k = tid & 63, pp = tid >> 6;
+  const int in = n.in_dim, Atot = n.head_total;
+  float sq = 0.f;
+  auto put = [&](int off, float v) { g[off] = v; sq = fmaf(v, v, sq); };
+#pragma unroll 1
+  for (int sec = 0; sec < 2; ++sec) {
+    const int K = sec == 0 ? 64 : in, ld = sec == 0 ? kHF : m.inF, one = sec == 0 ? kOne : in;
+    const float* G = raw + (sec == 0 ? R.g2 : R.g1);
+    const int w_off = sec == 0 ? n.g.fc2_w[0] : n.g.fc1_w, b_off = sec == 0 ? n.g.fc2_b[0] : n.g.fc1_b;
+    const bool fold = sec == 0 ? true : (n.use_fn != 0);
+    const int gam_off = sec == 0 ? n.g.ln1_w : n.g.fn_w, bet_off = sec == 0 ? n.g.ln1_b : n.g.fn_b;
+    for (int idx = tid; idx < 64 * K; idx += 512) {
+      const int o = idx / K, kk = idx - o * K;
+      put(w_off + idx, G[o * ld + kk] * (fold ? p[gam_off + kk] : 1.f));
+    }
+    if (tid < 64) put(b_off + tid, G[tid * ld + one]);
+    float sg = 0.f, sb = 0.f;
+    if (fold && k < K)
+      for (int o = pp; o < 64; o += 8) {
+        const float w = p[w_off + o * K + k];
+        sg = fmaf(G[o * ld + k], w, sg);
+        sb = fmaf(G[o * ld + one], w, sb);
+      }
+    __syncthreads();
+    part_g[pp][k] = sg; part_b[pp][k] = sb;
+    __syncthreads();
+    if (fold && tid < K) {
+      float a = 0.f, c = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { a += part_g[q][tid]; c += part_b[q][tid]; }
+      put(gam_off + tid, a);
+      put(bet_off + tid, c);
+    }
+  }
+  // heads: raw gh[k][a]
+  for (int idx = tid; idx < Atot * 64; idx += 512) {
+    const int a = idx >> 6, kk = idx & 63;
+    put(n.g.head_w + idx, raw[R.gh + kk * m.NH + a] * p[n.g.ln2_w[0] + kk]);
+  }
+  if (tid < Atot) put(n.g.head_b + tid, raw[R.dbh + tid]);
+  if (tid < 64) {
+    float a = 0.f, c = 0.f;
+    for (int q = 0; q < Atot; ++q) {
+      const float w = p[n.g.head_w + q * 64 + tid];
+      a = fmaf(raw[R.gh + tid * m.NH + q], w, a);
+      c = fmaf(raw[R.dbh + q], w, c);
+    }
+    put(n.g.ln2_w[0] + tid, a);
+    put(n.g.ln2_b[0] + tid, c);
+  }
+  // sum of squares of everything written
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  __syncthreads();
+  if ((tid & 31) == 0) sred[tid >> 5] = sq;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+    for (int q = 0; q < 16; ++q) t += sred[q];
+    sumsq_part[0] = t;
+  }
 }
 
 __global__ void __launch_bounds__(256) pack_tc_kernel(const NetDev n, const float* __restrict__ p, float* __restrict__ img) {
@@ -193,6 +292,13 @@ __host__ __device__ inline TcSmem make_tc_smem(const TcImage& m) {
   s.total = o;
   return s;
 }
+
+// phase timestamps of CTA 0 / thread 0 (clock64), read back by mappo_debug_tc_timing(): where does a tile's
+// latency go?  [0] start, [1] setup done, [2] S1 staged, [3] fc1 ready, [4] S3 done, [5] fc2 ready, [6] S5 done,
+// [7] head ready, [8] S7 done, [9] dx2 ready, [10] S9 done, [11] dx1 ready, [12] S11 done, [13] G1 done,
+// [14] unfold done, [15] end
+__device__ long long g_tc_timing[16];
+#define TC_STAMP(i) do { if (blockIdx.x == 0 && tid == 0) g_tc_timing[i] = clock64(); } while (0)
 
 // row-wise LayerNorm statistics of 64 register values (two-pass like torch)
 __device__ __forceinline__ void ln_stats64(const float* a, float& mean, float& rstd) {
@@ -265,6 +371,7 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
   const int act = n.use_relu ? ACT_RELU : ACT_TANH;
   constexpr int LGLD = kTM + 4;
 
+  TC_STAMP(0);
   // ---- one-time setup: barriers, TMEM, weight image by TMA, constant rows of the transposed tiles ----
   if (tid == 0) {
     mbar_init(bar_w, 1);
@@ -287,7 +394,7 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
     tma_bulk_g2s(sImg, image, (uint32_t)(im.total * sizeof(float)), bar_w);
   }
   // TMEM columns: D fwd/bwd accumulator, Dh logits, G2 / G1 / Gh persistent weight-gradient accumulators
-  const uint32_t cD = 0, cDh = 64, cG2 = 96, cG1 = 168, cGh = 240;
+  const uint32_t cD = 0, cDh = 64, cG2 = 96, cG1 = 168, cGh = 240, cX0 = 272;     // cX0: parked xhat0aug (72 cols)
   const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
 
   const LossConsts lc = make_loss_consts(n, L, norm_stats, adv_stats, vn_state);
@@ -299,17 +406,45 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
   const uint32_t aW2T = smem_u32(sImg + im.w2t), aWhT = smem_u32(sImg + im.wht);
   constexpr uint32_t ROWB = kTM * 16;                  // chunk stride of a 128-row K-major staging tile
 
+  TC_STAMP(1);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int p = tile * kTM + tid;
     const int gr = p < b.n_rows ? (b.rows ? b.rows[p] : p) : -1;
     const float* src = (n.is_critic ? b.share_obs : b.obs) + (size_t)(gr < 0 ? 0 : gr) * in;
     float mu0 = 0.f, rs0 = 1.f;
+    const RowIn rin = load_row_in(n, b, gr);      // loss inputs: in flight during the whole forward pass
 
-    // ---- S1: gather my row, feature LayerNorm in registers, stage xhat0 (K-major, + constant-1 feature) ----
+    // ---- S1: coalesced cooperative gather (a warp reads whole rows) -> shared staging -> my row in registers,
+    //      feature LayerNorm, stage xhat0 (K-major in TA, + constant-1 feature), park it in TMEM ----
     {
+      int* rowid_s = reinterpret_cast<int*>(lgT);                 // lgT is free until S7
+      float* Rs = P;                                              // raw rows [128][RS], RS odd -> conflict-free row reads
+      const int RS = in | 1;
+      rowid_s[tid] = gr;
+      __syncthreads();
+      const float* base = n.is_critic ? b.share_obs : b.obs;
+      // two batches of 16 rows x 2 loads: 32 independent coalesced loads in flight per thread, then the stores
+#pragma unroll 1
+      for (int hb = 0; hb < 2; ++hb) {
+        float v0[16], v1[16];
+#pragma unroll
+        for (int rr = 0; rr < 16; ++rr) {
+          const int g0 = rowid_s[warp * 32 + hb * 16 + rr];
+          const float* rp = base + (size_t)(g0 < 0 ? 0 : g0) * in;
+          v0[rr] = (lane < in && g0 >= 0) ? __ldg(rp + lane) : 0.f;
+          v1[rr] = (lane + 32 < in && g0 >= 0) ? __ldg(rp + lane + 32) : 0.f;
+        }
+#pragma unroll
+        for (int rr = 0; rr < 16; ++rr) {
+          const int r = warp * 32 + hb * 16 + rr;
+          if (lane < in) Rs[r * RS + lane] = v0[rr];
+          if (lane + 32 < in) Rs[r * RS + lane + 32] = v1[rr];
+        }
+      }
+      __syncthreads();
       float x[64];
 #pragma unroll
-      for (int k = 0; k < 64; ++k) x[k] = (k < in && gr >= 0) ? __ldg(src + k) : 0.f;
+      for (int k = 0; k < 64; ++k) x[k] = k < in ? Rs[tid * RS + k] : 0.f;
       if (n.use_fn && gr >= 0) {
         float s = 0.f;
 #pragma unroll
@@ -321,18 +456,22 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
         rs0 = 1.0f / sqrtf(v / (float)in + kLnEps);
       }
 #pragma unroll
-      for (int kc = 0; kc < 18; ++kc) {
-        if (kc * 4 < inF) {
-          float q[4];
+      for (int c8 = 0; c8 < 9; ++c8) {
+        if (c8 * 8 < inF) {
+          float q[8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int k = kc * 4 + j;
+          for (int j = 0; j < 8; ++j) {
+            const int k = c8 * 8 + j;
             q[j] = (k == in) ? 1.f : ((k < in) ? to_tf32((x[k & 63] - mu0) * rs0) : 0.f);
           }
-          reinterpret_cast<float4*>(P)[kc * kTM + tid] = make_float4(q[0], q[1], q[2], q[3]);
+          reinterpret_cast<float4*>(TA)[(2 * c8) * kTM + tid] = make_float4(q[0], q[1], q[2], q[3]);
+          reinterpret_cast<float4*>(TA)[(2 * c8 + 1) * kTM + tid] = make_float4(q[4], q[5], q[6], q[7]);
+          tmem_st8(tmem + lane_base + cX0 + c8 * 8, q);        // parked for the fc1 weight gradient (S11)
         }
       }
+      tmem_st_wait();
     }
+    TC_STAMP(2);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -341,26 +480,27 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
       if (first_tile) mbar_wait(bar_w, 0);                      // weight image has landed
       const uint32_t id = make_idesc(128, 64, 0, 0);
       for (int s = 0; s < inF / 8; ++s)
-        umma_tf32(tmem + cD, make_desc(aP + s * 2 * ROWB, ROWB, 128), make_desc(aW1 + s * 2 * 1024, 1024, 128), id, s > 0);
+        umma_tf32(tmem + cD, make_desc(aTA + s * 2 * ROWB, ROWB, 128), make_desc(aW1 + s * 2 * 1024, 1024, 128), id, s > 0);
       umma_commit(bar_m);
     }
     // ---- S3: fc1 epilogue: activation, LayerNorm -> xhat1 (K-major staging + transposed copy) ----
     float mu1, rs1, mu2, rs2;
     {
       float a[64];
-      mbar_wait(bar_m, phase); phase ^= 1;
+      mbar_wait(bar_m, phase); phase ^= 1; TC_STAMP(3);
       tc_fence_after();
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld16(tmem + lane_base + cD + c * 16, a + c * 16);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 64; ++i) a[i] = act_fwd(a[i], act);
+      for (int i = 0; i < 64; ++i) a[i] = act_fwd_tc(a[i], act);
       ln_stats64(a, mu1, rs1);
 #pragma unroll
       for (int i = 0; i < 64; ++i) a[i] = to_tf32((a[i] - mu1) * rs1);
       put_kmajor64(P, tid, a, true);
       put_transposed64(X1T, kS73, tid, a);
     }
+    TC_STAMP(4);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -374,19 +514,20 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
     // ---- S5: fc2 epilogue ----
     {
       float a[64];
-      mbar_wait(bar_m, phase); phase ^= 1;
+      mbar_wait(bar_m, phase); phase ^= 1; TC_STAMP(5);
       tc_fence_after();
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld16(tmem + lane_base + cD + c * 16, a + c * 16);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 64; ++i) a[i] = act_fwd(a[i], act);
+      for (int i = 0; i < 64; ++i) a[i] = act_fwd_tc(a[i], act);
       ln_stats64(a, mu2, rs2);
 #pragma unroll
       for (int i = 0; i < 64; ++i) a[i] = to_tf32((a[i] - mu2) * rs2);
       put_kmajor64(P, tid, a, true);
       put_transposed64(X2T, kS65, tid, a);
     }
+    TC_STAMP(6);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -401,14 +542,14 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
     // ---- S7: heads, loss, d(loss)/d(logits) ----
     {
       float lg[32];
-      mbar_wait(bar_m, phase); phase ^= 1;
+      mbar_wait(bar_m, phase); phase ^= 1; TC_STAMP(7);
       tc_fence_after();
       tmem_ld16(tmem + lane_base + cDh, lg);
       if (NH > 16) tmem_ld16(tmem + lane_base + cDh + 16, lg + 16);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) if (j < Atot) lgT[j * LGLD + tid] = lg[j];
-      row_loss<LGLD>(n, b, L, lc, lgT, tid, gr, p, acc);          // thread-local: only column `tid` is touched
+      row_loss_pre<LGLD>(n, b, L, lc, lgT, tid, gr, p, rin, acc);  // thread-local: only column `tid` is touched
       if (!b.eval_only) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) lg[j] = j < Atot ? to_tf32(lgT[j * LGLD + tid]) : 0.f;
@@ -429,6 +570,7 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
       }
     }
     if (b.eval_only) { tc_fence_before(); __syncthreads(); continue; }
+    TC_STAMP(8);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -448,7 +590,7 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
     // ---- S9: LayerNorm-2 + activation backward -> dZ2 (K-major staging + transposed) ----
     {
       float d[64];
-      mbar_wait(bar_m, phase); phase ^= 1;
+      mbar_wait(bar_m, phase); phase ^= 1; TC_STAMP(9);
       tc_fence_after();
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld16(tmem + lane_base + cD + c * 16, d + c * 16);
@@ -457,6 +599,7 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
       put_kmajor64(P, tid, d, false);
       put_transposed64(TA, kS65, tid, d);
     }
+    TC_STAMP(10);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -473,10 +616,10 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
         umma_tf32(tmem + cD, make_desc(aP + s * 2 * ROWB, ROWB, 128), make_desc(aW2T + s * 2 * 1024, 1024, 128), idx, s > 0);
       umma_commit(bar_m);
     }
-    // ---- S11: LayerNorm-1 + activation backward -> dZ1^T; xhat0^T re-staged from the (L2-resident) input row ----
+    // ---- S11: LayerNorm-1 + activation backward -> dZ1^T; xhat0^T re-staged from its TMEM parking columns ----
     {
       float d[64];
-      mbar_wait(bar_m, phase); phase ^= 1;
+      mbar_wait(bar_m, phase); phase ^= 1; TC_STAMP(11);
       tc_fence_after();
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld16(tmem + lane_base + cD + c * 16, d + c * 16);
@@ -485,15 +628,17 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
       put_transposed64(TA, kS65, tid, d);
       float* pb = P + (tid >> 2) * S0 * 4 + (tid & 3);            // xhat0aug^T: [32][inF + 1][4]
 #pragma unroll
-      for (int k = 0; k < 72; ++k) {
-        if (k < inF) {
-          float v = 0.f;
-          if (k < in) v = gr >= 0 ? to_tf32((__ldg(src + k) - mu0) * rs0) : 0.f;
-          else if (k == in) v = 1.f;
-          pb[k * 4] = v;
+      for (int c8 = 0; c8 < 9; ++c8) {
+        if (c8 * 8 < inF) {
+          float q[8];
+          tmem_ld8(tmem + lane_base + cX0 + c8 * 8, q);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pb[(c8 * 8 + j) * 4] = q[j];
         }
       }
     }
+    TC_STAMP(12);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -506,108 +651,56 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
                   idg, (!first_tile) || s > 0);
       umma_commit(bar_m);
     }
-    mbar_wait(bar_m, phase); phase ^= 1;        // P / TA are rewritten by the next iteration
+    mbar_wait(bar_m, phase); phase ^= 1; TC_STAMP(13);        // P / TA are rewritten by the next iteration
     tc_fence_after();
     first_tile = false;
   }
-  // ---- unfold the folded gradients into this CTA's slot ----
+  // ---- dump the raw (still folded) accumulators into this CTA's slot; they are summed over slots and unfolded once
+  //      by mappo_update_finish (tc_unfold_kernel) ----
   if (!b.eval_only) {
-    float* g = grad_part + (size_t)blockIdx.x * n.g.total;
+    const TcRaw R = make_tc_raw(im);
+    float* g = grad_part + (size_t)blockIdx.x * R.total;
     const bool has_tile = !first_tile;
     const int o = warp * 16 + lane;                       // accumulator row of this thread in the M = 64 layout
     const bool own = lane < 16;
-    float* S = X1T;                                       // scratch [64][65] x 2 (tiles are free now)
-    float* T2 = X1T + 64 * 65;
-    // ---------------- fc2 / ln1 ----------------
     {
       float v[72];
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld16(tmem + lane_base + cG2 + c * 16, v + c * 16);
       tmem_ld8(tmem + lane_base + cG2 + 64, v + 64);
       tmem_ld_wait();
-      __syncthreads();
       if (own) {
-        const float* W = params + n.g.fc2_w[0] + o * 64;
-        const float dbp = has_tile ? v[kOne] : 0.f;
-        g[n.g.fc2_b[0] + o] = dbp;
 #pragma unroll
-        for (int k = 0; k < 64; ++k) {
-          const float dw = has_tile ? v[k] : 0.f;
-          const float w = W[k];
-          g[n.g.fc2_w[0] + o * 64 + k] = dw * params[n.g.ln1_w + k];
-          S[o * 65 + k] = dw * w;
-          T2[o * 65 + k] = dbp * w;
-        }
+        for (int q = 0; q < 18; ++q)
+          reinterpret_cast<float4*>(g + R.g2 + o * kHF)[q] =
+              has_tile ? make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      __syncthreads();
-      if (tid < 64) {
-        float sg = 0.f, sb = 0.f;
-        for (int r = 0; r < 64; ++r) { sg += S[r * 65 + tid]; sb += T2[r * 65 + tid]; }
-        g[n.g.ln1_w + tid] = sg;
-        g[n.g.ln1_b + tid] = sb;
-      }
-      __syncthreads();
-    }
-    // ---------------- fc1 / feature norm ----------------
-    {
-      float v[72];
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld16(tmem + lane_base + cG1 + c * 16, v + c * 16);
       tmem_ld8(tmem + lane_base + cG1 + 64, v + 64);
       tmem_ld_wait();
       if (own) {
-        const float* W = params + n.g.fc1_w + o * in;
-        float dbp = 0.f;
 #pragma unroll
-        for (int k = 0; k < 72; ++k) if (k == in) dbp = has_tile ? v[k] : 0.f;
-        g[n.g.fc1_b + o] = dbp;
-#pragma unroll
-        for (int k = 0; k < 64; ++k) {
-          if (k < in) {
-            const float dw = has_tile ? v[k] : 0.f;
-            const float w = W[k];
-            g[n.g.fc1_w + o * in + k] = dw * (n.use_fn ? params[n.g.fn_w + k] : 1.f);
-            S[o * 65 + k] = dw * w;
-            T2[o * 65 + k] = dbp * w;
-          }
-        }
+        for (int q = 0; q < 18; ++q)
+          if (q * 4 < inF)
+            reinterpret_cast<float4*>(g + R.g1 + o * inF)[q] =
+                has_tile ? make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      __syncthreads();
-      if (n.use_fn && tid < in) {
-        float sg = 0.f, sb = 0.f;
-        for (int r = 0; r < 64; ++r) { sg += S[r * 65 + tid]; sb += T2[r * 65 + tid]; }
-        g[n.g.fn_w + tid] = sg;
-        g[n.g.fn_b + tid] = sb;
-      }
-      __syncthreads();
-    }
-    // ---------------- heads / ln2 : thread = feature k ----------------
-    {
-      float v[32];
       tmem_ld16(tmem + lane_base + cGh, v);
       if (NH > 16) tmem_ld16(tmem + lane_base + cGh + 16, v + 16);
       tmem_ld_wait();
       if (own) {
-        const int k = o;
-        float sg = 0.f, sb = 0.f;
-        const float gam = params[n.g.ln2_w[0] + k];
 #pragma unroll
-        for (int a = 0; a < 32; ++a) {
-          if (a < Atot) {
-            const float dw = has_tile ? v[a] : 0.f;
-            const float w = params[n.g.head_w + a * 64 + k];
-            g[n.g.head_w + a * 64 + k] = dw * gam;
-            sg = fmaf(dw, w, sg);
-            sb = fmaf(dbh[a], w, sb);
-          }
-        }
-        g[n.g.ln2_w[0] + k] = sg;
-        g[n.g.ln2_b[0] + k] = sb;
+        for (int q = 0; q < 8; ++q)
+          if (q * 4 < NH)
+            reinterpret_cast<float4*>(g + R.gh + o * NH)[q] =
+                has_tile ? make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      if (tid < Atot) g[n.g.head_b + tid] = dbh[tid];
     }
+    if (tid < NH) g[R.dbh + tid] = dbh[tid];
   }
 
+  TC_STAMP(14);
   // ---- loss scalars + teardown ----
   tc_fence_before();
   __syncthreads();
@@ -621,16 +714,30 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
     block_accumulate<1>(rt, loss_out + 5, sred, tid, kTM);
   }
   if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+  TC_STAMP(15);
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
+int debug_tc_timing(long long* out16) {
+  return cudaMemcpyFromSymbol(out16, g_tc_timing, sizeof(long long) * 16) == cudaSuccess ? 0 : MAPPO_ERR_CUDA;
+}
+
 bool update_mlp_tc_supported(const NetDev& n) {
   return n.hid == 64 && n.layer_n == 1 && n.in_dim <= 63 && n.head_total <= 32 && !n.recurrent;
 }
 
 int64_t update_mlp_tc_workspace_floats(const NetDev& n) { return make_tc_image(n).total; }
+
+int update_mlp_tc_slot_floats(const NetDev& n) { return make_tc_raw(make_tc_image(n)).total; }
+
+// sum of the raw slots is in `raw_sum` -> flat gradient + sum(g^2) (one partial)
+int update_mlp_tc_unfold_launch(const NetDev& n, const float* params, const float* raw_sum, float* grad,
+                                float* sumsq_part, cudaStream_t st) {
+  tc_unfold_kernel<<<1, 512, 0, st>>>(n, params, raw_sum, grad, sumsq_part);
+  return check_launch("tc_unfold_kernel");
+}
 
 int update_mlp_tc_slots(const NetDev&, int n_rows, int sm_count) {
   const int n_tiles = (n_rows + kTM - 1) / kTM;
@@ -657,7 +764,7 @@ int update_mlp_tc_launch(const NetDev& n, const float* params, const BatchDev& b
     configured = bytes;
   }
   const int n_tiles = (b.n_rows + kTM - 1) / kTM;
-  const uint32_t cols = im.NH > 16 ? 512u : 256u;
+  const uint32_t cols = 512u;          // accumulators [0,272) + parked xhat0 [272,344): one CTA per SM owns all of TMEM
   update_mlp_tc_kernel<<<n_slots, kTM, bytes, st>>>(n, params, image, b, L, norm_stats, adv_stats, vn_state, grad_part,
                                                     loss_out, n_tiles, cols);
   return check_launch("update_mlp_tc_kernel");

@@ -52,7 +52,9 @@ _SIGS = {
     "mappo_device_check": (_i32, [C.POINTER(_i32)] * 3),
     "mappo_net_layout": (_i32, [C.POINTER(NetDesc), C.POINTER(NetLayout)]),
     "mappo_policy_step": (_i32, [C.POINTER(NetDesc), _P, C.POINTER(NetDesc), _P] + [_P] * 7 +
-                          [_u64, _P, _i32, _i32] + [_P] * 6 + [_P]),
+                          [_u64, _P, _i32, _i32] + [_P] * 6 + [_P, _P] + [_P]),
+    "mappo_rollout_image_floats": (_i32, [C.POINTER(NetDesc)]),
+    "mappo_pack_rollout_weights": (_i32, [C.POINTER(NetDesc), _P, _P, _P]),
     "mappo_counter_add": (_i32, [_P, _u64, _P]),
     "mappo_env_insert": (_i32, [_P] * 6 + [_i32] * 5 + [_P] * 8 + [_P, _u64] + [_P]),
     "mappo_compute_returns": (_i32, [_P] * 6 + [_i32, _i32, _f32, _f32, _i32, _i32] + [_P] * 3 + [_P]),
@@ -66,8 +68,11 @@ _SIGS = {
     "mappo_update_workspace_floats": (_i64, [C.POINTER(NetDesc), _i32, _i32]),
     "mappo_update_grad_slots": (_i32, [C.POINTER(NetDesc), _i32, _i32]),
     "mappo_tf32_supported": (_i32, [C.POINTER(NetDesc)]),
+    "mappo_debug_tc_timing": (_i32, [C.POINTER(_i64)]),
     "mappo_update_fwd_bwd": (_i32, [C.POINTER(NetDesc), _P, C.POINTER(Batch), C.POINTER(LossCfg), _P, _P, _P, _P,
                                     _i32, _P, _P, _P]),
+    "mappo_update_slot_floats": (_i32, [C.POINTER(NetDesc), _i32]),
+    "mappo_update_finish": (_i32, [C.POINTER(NetDesc), _P, _P, _i32, _i32, _P, _P, C.POINTER(_i32), _P, _P]),
     "mappo_grad_reduce": (_i32, [_P, _i32, _i32, _P, _P, C.POINTER(_i32), _P]),
     "mappo_grad_sumsq": (_i32, [_P, _i32, _P, C.POINTER(_i32), _P]),
     "mappo_clip_adam": (_i32, [_P, _P, _P, _P, _i32, _P, _i32, _P, _P, _f32, _f32, _i32, _P, _P]),

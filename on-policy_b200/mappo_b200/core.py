@@ -364,7 +364,8 @@ class UpdateWorkspace:
         self.n_slots = int(lib.mappo_update_grad_slots(C.byref(net.desc), self.max_rows, self.gemm_mode))
         if self.n_slots <= 0:
             raise RuntimeError("mappo_update_grad_slots failed: " + lib.mappo_last_error().decode())
-        self.grad_part = torch.empty(self.n_slots * net.n_params, dtype=torch.float32, device=net.device)
+        self.slot_floats = int(lib.mappo_update_slot_floats(C.byref(net.desc), self.gemm_mode))
+        self.grad_part = torch.empty(self.n_slots * self.slot_floats, dtype=torch.float32, device=net.device)
         wf = int(lib.mappo_update_workspace_floats(C.byref(net.desc), self.max_rows, self.gemm_mode))
         if wf < 0:
             raise RuntimeError("mappo_update_workspace_floats failed: " + lib.mappo_last_error().decode())
@@ -399,8 +400,8 @@ def launch_update(net: DeviceNet, ws: UpdateWorkspace, batch: Batch, loss: LossC
                                    None if vn_state is None else ptr(vn_state), ptr(ws.grad_part), n_slots,
                                    ptr(loss_out), ptr(ws.workspace), st))
     nb = C.c_int32(0)
-    check(lib.mappo_grad_reduce(ptr(ws.grad_part), n_slots, net.n_params, ptr(net.grad), ptr(opt.sumsq_part),
-                                C.byref(nb), st))
+    check(lib.mappo_update_finish(C.byref(net.desc), ptr(net.flat), ptr(ws.grad_part), n_slots, ws.gemm_mode,
+                                  ptr(net.grad), ptr(opt.sumsq_part), C.byref(nb), ptr(ws.workspace), st))
     n_blocks = nb.value
     if allreduce is not None:
         allreduce(net.grad)

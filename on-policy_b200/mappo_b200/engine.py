@@ -85,6 +85,11 @@ class RolloutEngine:
         self.perm_ctr = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self.loss_out = torch.zeros(6, dtype=torch.float64, device=self.dev)
         self.h_loss = torch.zeros(6, dtype=torch.float64).pin_memory()
+        # rollout weight images (shared-memory layout), re-packed once per iteration, fetched by TMA in policy_step
+        self.img_actor = torch.zeros(int(self.lib.mappo_rollout_image_floats(C.byref(policy.actor.desc))),
+                                     dtype=torch.float32, device=self.dev)
+        self.img_critic = torch.zeros(int(self.lib.mappo_rollout_image_floats(C.byref(policy.critic.desc))),
+                                      dtype=torch.float32, device=self.dev)
         self.host = {}
         self.graph = None
         self._allreduce = "auto"        # "auto": torch.distributed when a multi-rank group exists
@@ -158,7 +163,8 @@ class RolloutEngine:
             ptr(b.available_actions[t]) if b.available_actions is not None else None, ptr(noise),
             self.seed, ptr(pol.rng_offset), 0, self.E,
             ptr(b.value_preds[t]), ptr(b.actions[t]), None, ptr(b.action_log_probs[t]),
-            ptr(b.rnn_states[t + 1]) if rec else None, ptr(b.rnn_states_critic[t + 1]) if rec else None, st))
+            ptr(b.rnn_states[t + 1]) if rec else None, ptr(b.rnn_states_critic[t + 1]) if rec else None,
+            ptr(self.img_actor), ptr(self.img_critic), st))
         check(lib.mappo_env_insert(
             ptr(self.d_obs[t]), ptr(self.d_share[t]), ptr(self.d_rew[t]), ptr(self.d_done[t]),
             ptr(self.d_active[t]) if self.d_active is not None else None,
@@ -177,7 +183,8 @@ class RolloutEngine:
         check(lib.mappo_policy_step(
             C.byref(pol.actor.desc), None, C.byref(pol.critic.desc), ptr(pol.critic.flat),
             None, ptr(b.share_obs[T]), None, ptr(b.rnn_states_critic[T]) if rec else None, ptr(b.masks[T]),
-            None, None, 0, None, 1, self.E, ptr(b.value_preds[T]), None, None, None, None, None, st))
+            None, None, 0, None, 1, self.E, ptr(b.value_preds[T]), None, None, None, None, None,
+            None, ptr(self.img_critic), st))
         vn = self.trainer.value_normalizer
         b._adv_stats.zero_()
         check(lib.mappo_compute_returns(ptr(b.rewards), ptr(b.value_preds), ptr(b.masks), ptr(b.bad_masks),
@@ -201,7 +208,10 @@ class RolloutEngine:
 
     def launch_iteration(self):
         """Enqueue one full iteration on the current stream (no host synchronisation)."""
-        self.launches_per_iteration = 0
+        self.launches_per_iteration = 2
+        pol = self.policy
+        check(self.lib.mappo_pack_rollout_weights(C.byref(pol.actor.desc), ptr(pol.actor.flat), ptr(self.img_actor), stream_ptr()))
+        check(self.lib.mappo_pack_rollout_weights(C.byref(pol.critic.desc), ptr(pol.critic.flat), ptr(self.img_critic), stream_ptr()))
         for t in range(self.T):
             self._collect_and_insert(t)
         self._compute()
@@ -214,11 +224,48 @@ class RolloutEngine:
             self.launches_per_iteration += 1
         # per update: stats + 2 x (fwd/bwd [+ weight pack in tf32 mode], slot reduce, clip+Adam) + ValueNorm update
         tf32 = 1 if getattr(tr, "gemm_mode", 0) == 1 else 0
-        per_update = 1 + 2 * (3 + tf32) + (1 if tr.value_normalizer is not None else 0)
+        per_update = 1 + 2 * (3 + 2 * tf32) + (1 if tr.value_normalizer is not None else 0)     # tf32: + pack, + unfold
         self.launches_per_iteration += n_upd * per_update
         if self.recurrent:
             self.launches_per_iteration += n_upd       # chunk_rows
         self.buffer.after_update()
+
+    def phase_breakdown(self, reps: int = 20):
+        """Device time of the three phases of an iteration, each captured as its own CUDA graph and replayed `reps`
+        times (single process only; diagnostic for bench.py)."""
+        def timed(fn):
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                fn()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            torch.cuda.synchronize()
+            g.replay()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                g.replay()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+
+        def collect():
+            pol = self.policy
+            check(self.lib.mappo_pack_rollout_weights(C.byref(pol.actor.desc), ptr(pol.actor.flat), ptr(self.img_actor), stream_ptr()))
+            check(self.lib.mappo_pack_rollout_weights(C.byref(pol.critic.desc), ptr(pol.critic.flat), ptr(self.img_critic), stream_ptr()))
+            for t in range(self.T):
+                self._collect_and_insert(t)
+
+        def train():
+            self._epoch_i = 0
+            self.trainer.launch_train(self.buffer, True, self._draw_perm, self.loss_out, allreduce=None)
+
+        return {"collect_insert_ms": timed(collect), "values_gae_ms": timed(self._compute), "train_ms": timed(train),
+                "after_update_ms": timed(self.buffer.after_update)}
 
     def capture(self, warmup: int = 2):
         """Warm up eagerly (lazy workspace allocation, cudaFuncSetAttribute) then capture the iteration."""

@@ -95,7 +95,7 @@ class R_MAPPOPolicy:
             C.byref(self.critic.desc), ptr(self.critic.flat) if want_critic else None,
             ptr(obs), ptr(cent), ptr(h_a_d), ptr(h_c_d), ptr(masks_d), ptr(avail_d), ptr(exp_noise),
             self.rng_seed, ptr(self.rng_offset), int(bool(deterministic)), n_rows,
-            ptr(values), ptr(actions_f), ptr(actions), ptr(logp), ptr(h_a_out), ptr(h_c_out), stream_ptr()))
+            ptr(values), ptr(actions_f), ptr(actions), ptr(logp), ptr(h_a_out), ptr(h_c_out), None, None, stream_ptr()))
         if want_actor and exp_noise is None and not deterministic:
             check(lib.mappo_counter_add(ptr(self.rng_offset), n_rows, stream_ptr()))
         if not self._recurrent:                      # MLP policies hand the states back untouched (r_actor_critic.py:66-71)

@@ -6,6 +6,7 @@ Per optimiser step and net: ONE forward+loss+backward launch, one slot reduction
 scalars stay on the device until the single read at the end of train().
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -56,8 +57,11 @@ class R_MAPPO():
             raise NotImplementedError("use_popart: PopArt.update raises in the reference itself (SURVEY App. B-7)")
         self.value_normalizer = ValueNorm(1, device=self.device) if self._use_valuenorm else None
         # GEMM engine of the update kernels: "tf32" = tcgen05 tensor cores (fp32 accumulate), "fp32" = exact FFMA tiles
-        import os
         self.gemm_mode = {"fp32": _lib.GEMM_FP32, "tf32": _lib.GEMM_TF32}[os.environ.get("MAPPO_B200_GEMM", "fp32")]
+        # actor and critic are independent nets: their update chains run on two streams (fork / join with events,
+        # captured as parallel branches of the CUDA graph).  Off when a process group is active (one collective order).
+        self.overlap_nets = os.environ.get("MAPPO_B200_OVERLAP", "1") == "1"
+        self._side = None
         self._ws = {}
         self._loss_out = torch.zeros(6, dtype=torch.float64, device=self.device)
 
@@ -72,16 +76,32 @@ class R_MAPPO():
     def _one_update(self, batch, n_rows, norm_stats, adv_stats, loss_out, update_actor, allreduce):
         pol = self.policy
         ws_a, ws_c = self._workspaces(n_rows)
-        loss = make_loss_cfg(self.args, update_actor)
+        loss_a = make_loss_cfg(self.args, update_actor)
+        loss_c = make_loss_cfg(self.args, update_actor)
         vn = self.value_normalizer.state if self.value_normalizer is not None else None
-        # actor: backward, clip, step (reference :141-153)
-        launch_update(pol.actor, ws_a, batch, loss, norm_stats, adv_stats, None, loss_out, pol.actor_optimizer,
-                      self.max_grad_norm, self._use_max_grad_norm, 3, allreduce)
-        # ValueNorm.update(return_batch) BEFORE the value loss (reference :65), then critic (reference :156-167)
-        if vn is not None:
-            check(_lib.load().mappo_valuenorm_update(ptr(vn), ptr(norm_stats), stream_ptr()))
-        launch_update(pol.critic, ws_c, batch, loss, norm_stats, None, vn, loss_out, pol.critic_optimizer,
-                      self.max_grad_norm, self._use_max_grad_norm, 4, allreduce)
+
+        def actor_chain():          # backward, clip, step (reference :141-153)
+            launch_update(pol.actor, ws_a, batch, loss_a, norm_stats, adv_stats, None, loss_out, pol.actor_optimizer,
+                          self.max_grad_norm, self._use_max_grad_norm, 3, allreduce)
+
+        def critic_chain():         # ValueNorm.update(return_batch) BEFORE the value loss (reference :65), then :156-167
+            if vn is not None:
+                check(_lib.load().mappo_valuenorm_update(ptr(vn), ptr(norm_stats), stream_ptr()))
+            launch_update(pol.critic, ws_c, batch, loss_c, norm_stats, None, vn, loss_out, pol.critic_optimizer,
+                          self.max_grad_norm, self._use_max_grad_norm, 4, allreduce)
+
+        if self.overlap_nets and allreduce is None:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            main = torch.cuda.current_stream()
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                critic_chain()
+            actor_chain()
+            main.wait_stream(self._side)
+        else:
+            actor_chain()
+            critic_chain()
 
     def _storage_batch(self, buffer, adv, rows, first, seq_len):
         b = Batch()

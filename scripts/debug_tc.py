@@ -34,3 +34,14 @@ for key in res["fp32"][1]:
     scale = np.abs(b).max() + 1e-30
     print(f"{key[0]:6s} {key[1]:34s} shape {str(b.shape):10s} scale {scale:.3e} maxerr/scale {np.abs(a-b).max()/scale:.3e}  "
           f"corr {np.corrcoef(a.ravel(), b.ravel())[0,1] if a.size > 1 else float('nan'):.5f}")
+
+# ---- phase timing of the last tcgen05 launch (critic of the last update) ----
+import ctypes as C
+lib = _lib.load()
+buf16 = (C.c_int64 * 16)()
+torch.cuda.synchronize()
+lib.mappo_debug_tc_timing(buf16)
+t = list(buf16)
+names = ["setup", "S1 gather+LN0", "fc1 mma", "S3 epi", "fc2 mma", "S5 epi", "head mma", "S7 loss", "dx2+Gh mma", "S9 bwd",
+         "dx1+G2 mma", "S11 bwd", "G1 mma", "unfold", "tail"]
+print("TC kernel phase cycles (CTA 0):", {n: t[i + 1] - t[i] for i, n in enumerate(names)}, "total", t[15] - t[0])

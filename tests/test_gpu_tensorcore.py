@@ -4,7 +4,8 @@ TF32 keeps 10 mantissa bits of the GEMM inputs (round-to-nearest when the operan
 LayerNorm, activations, losses, the gradient reduction and Adam stay fp32.  Stated tolerances:
   first-update gradients   |err| <= 2e-2 * |ref| + 2e-2 * max|ref of that tensor|   (tf32 rounding of a 64..9600-term dot)
   losses / ratio / entropy  rtol 2e-3
-  weights after a full 10-epoch train()   rtol 2e-2, atol 2e-4
+  weights after a full 10-epoch train()   rtol 2e-2, atol 2e-3 (~3 Adam steps of lr 7e-4: Adam normalises the
+                                            gradient, so tf32 noise on near-zero gradients moves a weight by O(lr))
 The exact-fp32 build (MAPPO_B200_GEMM=fp32, tests/test_gpu_parity.py) keeps the tight tolerances.
 """
 import numpy as np
@@ -85,7 +86,7 @@ def test_tf32_full_iterations(monkeypatch):
         for net, name in ((policy.actor, "actor"), (policy.critic, "critic")):
             for k, v in net.state_dict().items():
                 ref = g.get(f"it{it}/{name}/{k}")
-                assert_close(v.cpu().numpy(), ref, 2e-2, 2e-4, f"{name} {k} after it{it}")
+                assert_close(v.cpu().numpy(), ref, 2e-2, 2e-3, f"{name} {k} after it{it}")
                 worst = max(worst, float(np.abs(v.cpu().numpy() - ref).max()))
         print(f"\n[tf32] it{it}: worst absolute weight deviation from the reference {worst:.3e}")
         if it == 0:
