@@ -370,6 +370,7 @@ class UpdateWorkspace:
         if wf < 0:
             raise RuntimeError("mappo_update_workspace_floats failed: " + lib.mappo_last_error().decode())
         self.workspace = torch.empty(max(wf, 1), dtype=torch.float32, device=net.device)
+        self.sumsq_part = torch.zeros((net.n_params + 31) // 32, dtype=torch.float32, device=net.device)
 
 
 def make_loss_cfg(args, update_actor=True) -> LossCfg:
@@ -386,10 +387,10 @@ def make_loss_cfg(args, update_actor=True) -> LossCfg:
     return c
 
 
-def launch_update(net: DeviceNet, ws: UpdateWorkspace, batch: Batch, loss: LossCfg, norm_stats, adv_stats, vn_state,
-                  loss_out, opt: FusedAdam, max_grad_norm, use_max_grad_norm, grad_norm_slot: int,
-                  allreduce=None):
-    """forward+loss+backward -> slot reduction -> [all-reduce] -> clip + Adam for one net."""
+def launch_grads(net: DeviceNet, ws: UpdateWorkspace, batch: Batch, loss: LossCfg, norm_stats, adv_stats, vn_state,
+                 loss_out):
+    """forward + loss + backward -> slot reduction: leaves the (local) flat gradient in net.grad.
+    Returns the number of sum-of-squares partials left in the optimiser's scratch (valid until an all-reduce)."""
     lib = _lib.load()
     st = stream_ptr()
     n_rows = int(batch.n_rows)
@@ -401,10 +402,25 @@ def launch_update(net: DeviceNet, ws: UpdateWorkspace, batch: Batch, loss: LossC
                                    ptr(loss_out), ptr(ws.workspace), st))
     nb = C.c_int32(0)
     check(lib.mappo_update_finish(C.byref(net.desc), ptr(net.flat), ptr(ws.grad_part), n_slots, ws.gemm_mode,
-                                  ptr(net.grad), ptr(opt.sumsq_part), C.byref(nb), ptr(ws.workspace), st))
-    n_blocks = nb.value
+                                  ptr(net.grad), ptr(ws.sumsq_part), C.byref(nb), ptr(ws.workspace), st))
+    return nb.value
+
+
+def launch_step(net: DeviceNet, ws: UpdateWorkspace, loss_out, opt: FusedAdam, max_grad_norm, use_max_grad_norm,
+                grad_norm_slot: int, n_sumsq_blocks: int):
+    """clip_grad_norm_ + Adam on net.grad (n_sumsq_blocks == 0: re-derive the norm, e.g. after an all-reduce)."""
+    gn_ptr = C.c_void_p(loss_out.data_ptr() + 8 * grad_norm_slot)
+    if n_sumsq_blocks > 0:
+        opt.sumsq_part = ws.sumsq_part
+    opt.apply(max_grad_norm, use_max_grad_norm, gn_ptr, n_sumsq_blocks=n_sumsq_blocks)
+
+
+def launch_update(net: DeviceNet, ws: UpdateWorkspace, batch: Batch, loss: LossCfg, norm_stats, adv_stats, vn_state,
+                  loss_out, opt: FusedAdam, max_grad_norm, use_max_grad_norm, grad_norm_slot: int,
+                  allreduce=None):
+    """forward+loss+backward -> slot reduction -> [all-reduce] -> clip + Adam for one net."""
+    nb = launch_grads(net, ws, batch, loss, norm_stats, adv_stats, vn_state, loss_out)
     if allreduce is not None:
         allreduce(net.grad)
-        n_blocks = 0                      # the norm must be re-derived from the all-reduced gradient
-    gn_ptr = C.c_void_p(loss_out.data_ptr() + 8 * grad_norm_slot)
-    opt.apply(max_grad_norm, use_max_grad_norm, gn_ptr, n_sumsq_blocks=n_blocks)
+        nb = 0                            # the norm must be re-derived from the all-reduced gradient
+    launch_step(net, ws, loss_out, opt, max_grad_norm, use_max_grad_norm, grad_norm_slot, nb)

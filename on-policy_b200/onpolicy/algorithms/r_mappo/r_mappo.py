@@ -12,8 +12,8 @@ import numpy as np
 import torch
 
 from mappo_b200 import _lib
-from mappo_b200.core import (Batch, UpdateWorkspace, as_dev, check, launch_update, make_loss_cfg, ptr, require_cuda,
-                             stream_ptr)
+from mappo_b200.core import (Batch, UpdateWorkspace, as_dev, check, launch_grads, launch_step, launch_update,
+                             make_loss_cfg, ptr, require_cuda, stream_ptr)
 from onpolicy.utils.valuenorm import ValueNorm
 
 INFO_KEYS = ("value_loss", "policy_loss", "dist_entropy", "actor_grad_norm", "critic_grad_norm", "ratio")
@@ -62,6 +62,12 @@ class R_MAPPO():
         # captured as parallel branches of the CUDA graph).  Off when a process group is active (one collective order).
         self.overlap_nets = os.environ.get("MAPPO_B200_OVERLAP", "1") == "1"
         self._side = None
+        # joint gradient vector [actor | critic]: what a multi-GPU run all-reduces in one collective per optimiser step
+        na, nc = policy.actor.n_params, policy.critic.n_params
+        pad = (-na) % 4
+        self._joint_grad = torch.zeros(na + pad + nc, dtype=torch.float32, device=self.device)
+        policy.actor.grad = self._joint_grad[:na]
+        policy.critic.grad = self._joint_grad[na + pad:]
         self._ws = {}
         self._loss_out = torch.zeros(6, dtype=torch.float64, device=self.device)
 
@@ -99,6 +105,16 @@ class R_MAPPO():
                 critic_chain()
             actor_chain()
             main.wait_stream(self._side)
+        elif allreduce is not None:
+            # data parallel: both nets' local gradients first, ONE collective on the joint gradient vector, then both
+            # optimiser steps (actor and critic are independent, so this is the reference's order up to commuting)
+            nb_a = launch_grads(pol.actor, ws_a, batch, loss_a, norm_stats, adv_stats, None, loss_out)
+            if vn is not None:
+                check(_lib.load().mappo_valuenorm_update(ptr(vn), ptr(norm_stats), stream_ptr()))
+            nb_c = launch_grads(pol.critic, ws_c, batch, loss_c, norm_stats, None, vn, loss_out)
+            allreduce(self._joint_grad)
+            launch_step(pol.actor, ws_a, loss_out, pol.actor_optimizer, self.max_grad_norm, self._use_max_grad_norm, 3, 0)
+            launch_step(pol.critic, ws_c, loss_out, pol.critic_optimizer, self.max_grad_norm, self._use_max_grad_norm, 4, 0)
         else:
             actor_chain()
             critic_chain()
