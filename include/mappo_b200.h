@@ -224,6 +224,19 @@ int32_t mappo_evaluate_actions(const mappo_net_desc_t* desc, const float* params
                                const mappo_loss_cfg_t* loss, const double* norm_stats, float* out,
                                double* loss_out, float* workspace, void* stream);
 
+/* ---- C1: the multi-GPU exchange (none in the reference: single process) ---------------------------------------
+ * One-shot all-reduce over peer-mapped memory (NVLink 5 / NVSwitch) as ONE kernel per rank -- no host involvement, so
+ * the whole multi-GPU iteration stays a single CUDA graph.  peer_bufs[p] / peer_signals[p] (HOST arrays of `world`
+ * device pointers, world <= 8): rank p's symmetric buffer and its signal pad uint32[world] (zero-initialised), both
+ * mapped into this process.  out[i] = sum_p peer_bufs[p][offset_bytes + i] in rank order (bit-identical on every
+ * rank).  round_dev: device uint32[2] = {completed rounds, scratch}, zero-initialised, private to this rank; every
+ * rank must issue the same sequence of calls.  A region of the symmetric buffer may be rewritten once a LATER call has
+ * completed locally (each call is a full barrier): alternate two regions for back-to-back reductions. */
+int32_t mappo_p2p_allreduce_f32(const void* const* peer_bufs, void* const* peer_signals, int32_t world, int32_t rank,
+                                int64_t offset_bytes, int32_t n, float* out, uint32_t* round_dev, void* stream);
+int32_t mappo_p2p_allreduce_f64(const void* const* peer_bufs, void* const* peer_signals, int32_t world, int32_t rank,
+                                int64_t offset_bytes, int32_t n, double* out, uint32_t* round_dev, void* stream);
+
 /* ---- a13: gradient reduction + clip_grad_norm_ + Adam ----------------------------------------
  * Sums the partial-gradient slots into `grad` [n_params] (the buffer a multi-GPU caller
  * all-reduces), nn.utils.clip_grad_norm_ (r_mappo.py:148-151, 162-165) and

@@ -1,0 +1,114 @@
+// p2p_allreduce.cu -- one-shot all-reduce over NVLink / NVSwitch peer memory, as ONE graph-capturable kernel.
+//
+// Every rank owns a "symmetric" buffer (same layout on every GPU, peer-mapped into every process, e.g. through
+// torch.distributed._symmetric_memory) and a tiny signal pad uint32[world].  One launch per rank:
+//   1. arrive : rank r stores the round number into slot r of EVERY peer's signal pad (st.release.sys)
+//   2. wait   : spin until all world slots of my own pad have reached the round (ld.acquire.sys)
+//   3. reduce : out[i] = sum_{p = 0..world-1} peer_p[offset + i], read straight through NVLink (L1-bypassing loads);
+//               fixed order, so every rank ends up with bit-identical sums and the replicas never drift
+//   4. the last CTA publishes the completed round in device memory (read by the next launch; nothing on the host).
+// Reuse rule: a region may be rewritten as soon as a LATER round on any region has completed locally (each round is
+// a full barrier) -- the gradient all-reduce therefore alternates between two halves of the buffer.
+// The reference has no collective (single process); this is the multi-GPU exchange of SURVEY section 8e, C1.
+#include "common.cuh"
+
+namespace mappo {
+
+constexpr int kMaxPeers = 8;
+struct P2PArgs {
+  const void* buf[kMaxPeers];
+  uint32_t* sig[kMaxPeers];
+  int world, rank;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+template <typename T> __device__ __forceinline__ T ld_peer(const T* p);
+template <> __device__ __forceinline__ float ld_peer<float>(const float* p) {
+  float v;
+  asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+template <> __device__ __forceinline__ double ld_peer<double>(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ld_peer4(const float* p) {
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+p2p_allreduce_kernel(const P2PArgs a, long long offset_bytes, int n, T* __restrict__ out, uint32_t* __restrict__ round_dev) {
+  __shared__ uint32_t s_round;
+  if (threadIdx.x == 0) s_round = round_dev[0] + 1;
+  __syncthreads();
+  const uint32_t round = s_round;
+  if (blockIdx.x == 0 && threadIdx.x < a.world) {
+    __threadfence_system();                           // my earlier writes to the symmetric buffer are visible to peers
+    st_release_sys(a.sig[threadIdx.x] + a.rank, round);
+  }
+  if (threadIdx.x < a.world) {
+    const uint32_t* mine = a.sig[a.rank] + threadIdx.x;
+    while ((int)(ld_acquire_sys(mine) - round) < 0) { }
+  }
+  __syncthreads();
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  if (sizeof(T) == 4 && (n & 3) == 0 && (offset_bytes & 15) == 0) {
+    for (int i = tid; i < n / 4; i += nt) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+      for (int p = 0; p < a.world; ++p) {
+        const float4 v = ld_peer4(reinterpret_cast<const float*>(static_cast<const char*>(a.buf[p]) + offset_bytes) + 4 * i);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+      reinterpret_cast<float4*>(out)[i] = s;
+    }
+  } else {
+    for (int i = tid; i < n; i += nt) {
+      T s = (T)0;
+#pragma unroll 1
+      for (int p = 0; p < a.world; ++p)
+        s += ld_peer<T>(reinterpret_cast<const T*>(static_cast<const char*>(a.buf[p]) + offset_bytes) + i);
+      out[i] = s;
+    }
+  }
+  // completion: the last CTA to finish publishes the round (round_dev[1] is its ticket counter)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const uint32_t t = atomicAdd(round_dev + 1, 1u);
+    if (t == gridDim.x - 1) { round_dev[0] = round; round_dev[1] = 0; }
+  }
+}
+
+template <typename T>
+static int launch_p2p(const void* const* bufs, void* const* sigs, int world, int rank, long long offset_bytes, int n, T* out,
+                      uint32_t* round_dev, cudaStream_t st) {
+  if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) { set_error("p2p_allreduce: world %d / rank %d", world, rank); return MAPPO_ERR_INVALID; }
+  if (!bufs || !sigs || !out || !round_dev || n <= 0) { set_error("p2p_allreduce: NULL / empty"); return MAPPO_ERR_INVALID; }
+  P2PArgs a;
+  for (int p = 0; p < kMaxPeers; ++p) { a.buf[p] = p < world ? bufs[p] : nullptr; a.sig[p] = p < world ? static_cast<uint32_t*>(sigs[p]) : nullptr; }
+  a.world = world; a.rank = rank;
+  int blocks = (n / 4 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 64) blocks = 64;
+  p2p_allreduce_kernel<T><<<blocks, 256, 0, st>>>(a, offset_bytes, n, out, round_dev);
+  return check_launch("p2p_allreduce_kernel");
+}
+
+int p2p_allreduce_f32_launch(const void* const* bufs, void* const* sigs, int world, int rank, long long off, int n, float* out,
+                             uint32_t* round_dev, cudaStream_t st) { return launch_p2p<float>(bufs, sigs, world, rank, off, n, out, round_dev, st); }
+int p2p_allreduce_f64_launch(const void* const* bufs, void* const* sigs, int world, int rank, long long off, int n, double* out,
+                             uint32_t* round_dev, cudaStream_t st) { return launch_p2p<double>(bufs, sigs, world, rank, off, n, out, round_dev, st); }
+
+}  // namespace mappo

@@ -388,7 +388,7 @@ def make_loss_cfg(args, update_actor=True) -> LossCfg:
 
 
 def launch_grads(net: DeviceNet, ws: UpdateWorkspace, batch: Batch, loss: LossCfg, norm_stats, adv_stats, vn_state,
-                 loss_out):
+                 loss_out, grad_out=None):
     """forward + loss + backward -> slot reduction: leaves the (local) flat gradient in net.grad.
     Returns the number of sum-of-squares partials left in the optimiser's scratch (valid until an all-reduce)."""
     lib = _lib.load()
@@ -402,7 +402,8 @@ def launch_grads(net: DeviceNet, ws: UpdateWorkspace, batch: Batch, loss: LossCf
                                    ptr(loss_out), ptr(ws.workspace), st))
     nb = C.c_int32(0)
     check(lib.mappo_update_finish(C.byref(net.desc), ptr(net.flat), ptr(ws.grad_part), n_slots, ws.gemm_mode,
-                                  ptr(net.grad), ptr(ws.sumsq_part), C.byref(nb), ptr(ws.workspace), st))
+                                  ptr(net.grad if grad_out is None else grad_out), ptr(ws.sumsq_part), C.byref(nb),
+                                  ptr(ws.workspace), st))
     return nb.value
 
 

@@ -38,3 +38,68 @@ def unpack_stats(flat: torch.Tensor, n_updates: int):
 def loss_weight(active_local_sum: float, rows_local: int, active_global_sum: float, rows_global: int, use_active: bool):
     """Factor turning a rank-local masked mean into its share of the global masked mean."""
     return (active_local_sum / active_global_sum) if use_active else (rows_local / rows_global)
+
+
+class P2PReducer:
+    """All-reduce through libmappo_b200's one-shot peer-memory kernel (mappo_p2p_allreduce_*): buffers come from
+    torch.distributed._symmetric_memory (plumbing: allocation + exchange of the peer mappings), the reduction itself is
+    our kernel -- no NCCL call, no host work per collective, so a multi-GPU iteration stays ONE CUDA graph.
+
+    Layout of the symmetric buffer (floats): [grad half 0][grad half 1][stats (fp64)][loss (fp64)]."""
+
+    def __init__(self, device, n_grad: int, n_stats: int):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self.lib, self.C = _lib.load(), C
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        if self.world > 8:
+            raise RuntimeError("P2PReducer: one NVSwitch box (<= 8 ranks)")
+        pad = lambda n: (n + 3) & ~3
+        self.n_grad = pad(n_grad)
+        self.n_stats = n_stats
+        self.off_grad = [0, self.n_grad]
+        self.off_stats = 2 * self.n_grad
+        self.off_loss = self.off_stats + pad(2 * n_stats)
+        total = self.off_loss + 16
+        self.sym = symm_mem.empty(total, dtype=torch.float32, device=device)
+        self.sig = symm_mem.empty(64, dtype=torch.int32, device=device)
+        self.sym.zero_()
+        self.sig.zero_()
+        torch.cuda.synchronize()
+        h_buf = symm_mem.rendezvous(self.sym, dist.group.WORLD)
+        h_sig = symm_mem.rendezvous(self.sig, dist.group.WORLD)
+        self.bufs = (C.c_void_p * self.world)(*[int(p) for p in h_buf.buffer_ptrs])
+        self.sigs = (C.c_void_p * self.world)(*[int(p) for p in h_sig.buffer_ptrs])
+        self._keep = (h_buf, h_sig)
+        self.round = torch.zeros(2, dtype=torch.int32, device=device)
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def grad_half(self, parity: int) -> torch.Tensor:
+        o = self.off_grad[parity & 1]
+        return self.sym[o:o + self.n_grad]
+
+    def _stream(self):
+        return self.C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def allreduce_grad(self, parity: int, out: torch.Tensor):
+        """out[:] = sum over ranks of grad_half(parity)  (out is an ordinary local tensor)."""
+        rc = self.lib.mappo_p2p_allreduce_f32(self.bufs, self.sigs, self.world, self.rank, 4 * self.off_grad[parity & 1],
+                                              out.numel(), out.data_ptr(), self.round.data_ptr(), self._stream())
+        _check(self.lib, rc)
+
+    def allreduce_f64_(self, t: torch.Tensor, region: str):
+        """In-place sum over ranks of a small fp64 tensor through the 'stats' or 'loss' region."""
+        off = self.off_stats if region == "stats" else self.off_loss
+        n = t.numel()
+        self.sym[off:off + 2 * n].view(torch.float64).copy_(t.reshape(-1))
+        rc = self.lib.mappo_p2p_allreduce_f64(self.bufs, self.sigs, self.world, self.rank, 4 * off, n, t.data_ptr(),
+                                              self.round.data_ptr(), self._stream())
+        _check(self.lib, rc)
+        return t
+
+
+def _check(lib, rc):
+    if rc != 0:
+        raise RuntimeError(f"libmappo_b200: status {rc}: {lib.mappo_last_error().decode()}")

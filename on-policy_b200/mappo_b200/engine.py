@@ -277,7 +277,8 @@ class RolloutEngine:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if multi and getattr(self.trainer, "_p2p", None) is None:
             seg = SegmentedGraph()
             self._allreduce = seg.collective
             try:

@@ -68,6 +68,8 @@ class R_MAPPO():
         self._joint_grad = torch.zeros(na + pad + nc, dtype=torch.float32, device=self.device)
         policy.actor.grad = self._joint_grad[:na]
         policy.critic.grad = self._joint_grad[na + pad:]
+        self._crit_off = na + pad
+        self._p2p, self._p2p_tried, self._parity = None, False, 0
         self._ws = {}
         self._loss_out = torch.zeros(6, dtype=torch.float64, device=self.device)
 
@@ -108,11 +110,20 @@ class R_MAPPO():
         elif allreduce is not None:
             # data parallel: both nets' local gradients first, ONE collective on the joint gradient vector, then both
             # optimiser steps (actor and critic are independent, so this is the reference's order up to commuting)
-            nb_a = launch_grads(pol.actor, ws_a, batch, loss_a, norm_stats, adv_stats, None, loss_out)
+            p2p = self._p2p
+            ga = gc = None
+            if p2p is not None:           # write the local gradients straight into the peer-visible half
+                half = p2p.grad_half(self._parity)
+                ga, gc = half[:pol.actor.n_params], half[self._crit_off:self._crit_off + pol.critic.n_params]
+            launch_grads(pol.actor, ws_a, batch, loss_a, norm_stats, adv_stats, None, loss_out, grad_out=ga)
             if vn is not None:
                 check(_lib.load().mappo_valuenorm_update(ptr(vn), ptr(norm_stats), stream_ptr()))
-            nb_c = launch_grads(pol.critic, ws_c, batch, loss_c, norm_stats, None, vn, loss_out)
-            allreduce(self._joint_grad)
+            launch_grads(pol.critic, ws_c, batch, loss_c, norm_stats, None, vn, loss_out, grad_out=gc)
+            if p2p is not None:
+                p2p.allreduce_grad(self._parity, self._joint_grad)
+                self._parity ^= 1
+            else:
+                allreduce(self._joint_grad)
             launch_step(pol.actor, ws_a, loss_out, pol.actor_optimizer, self.max_grad_norm, self._use_max_grad_norm, 3, 0)
             launch_step(pol.critic, ws_c, loss_out, pol.critic_optimizer, self.max_grad_norm, self._use_max_grad_norm, 4, 0)
         else:
@@ -135,6 +146,22 @@ class R_MAPPO():
         return b
 
     # ------------------------------------------------------------------------------------------
+    def _ensure_p2p(self, n_stats):
+        """Peer-memory all-reduce (our kernel over NVLink) when the process group allows it; NCCL through
+        torch.distributed otherwise (MAPPO_B200_P2P=0 forces NCCL)."""
+        if self._p2p_tried:
+            return
+        self._p2p_tried = True
+        if os.environ.get("MAPPO_B200_P2P", "1") != "1":
+            return
+        try:
+            from mappo_b200.dist import P2PReducer
+            self._p2p = P2PReducer(self.device, self._joint_grad.numel(), n_stats)
+        except Exception as e:                       # no symmetric memory on this system: stay on NCCL
+            import sys
+            print(f"[mappo_b200] peer-memory all-reduce unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
+            self._p2p = None
+
     def _host_permutation(self, n):
         """torch.randperm on the CPU generator, exactly where the reference's generators draw it
         (utils/shared_buffer.py:360, 415, 511), uploaded as int32."""
@@ -158,6 +185,9 @@ class R_MAPPO():
         B = T * E
         if allreduce == "auto":
             allreduce = _dist_allreduce()
+            if allreduce is not None:
+                self._ensure_p2p(n_stats=self.ppo_epoch * self.num_mini_batch * 4 + 4)
+        p2p = self._p2p if allreduce is not None else None
         draw_perm = draw_perm or self._host_permutation
         loss_out = self._loss_out if loss_out is None else loss_out
         vn = self.value_normalizer.state if self.value_normalizer is not None else None
@@ -196,7 +226,10 @@ class R_MAPPO():
                                             C.c_void_p(stats.data_ptr() + 32 * u), st))
         if allreduce is not None:
             stats[n_updates * 4:n_updates * 4 + 3].copy_(adv_stats)
-            allreduce(stats)
+            if p2p is not None:
+                p2p.allreduce_f64_(stats, "stats")
+            else:
+                allreduce(stats)
             adv_stats = stats[n_updates * 4:n_updates * 4 + 3]
 
         loss_out.zero_()
@@ -207,7 +240,10 @@ class R_MAPPO():
             # loss scalars are partial sums over local rows (global normalisers); norms are already global
             part = loss_out.clone()
             part[3:5] = 0
-            allreduce(part)
+            if p2p is not None:
+                p2p.allreduce_f64_(part, "loss")
+            else:
+                allreduce(part)
             loss_out[0:3] = part[0:3]
             loss_out[5] = part[5]
         self._keepalive = plans
