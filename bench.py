@@ -274,6 +274,10 @@ def run_gpu(a):
                 "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "tf32 tensor-core GEMMs (fp32 accumulate / fp32 elsewhere)" if a.gemm == "tf32" else "f32",
                 "data": "synthetic", "config": {**workload_dict(cfg, world), "cuda_graph": graph_ok, "gemm": a.gemm,
+                                                "collective": ("none (1 GPU)" if world == 1 else
+                                                               "one-shot peer-memory all-reduce kernel over NVLink, in-graph"
+                                                               if getattr(trainer, "_p2p", None) is not None else
+                                                               "NCCL all-reduce via torch.distributed between graph segments"),
                                                                 "rng": "device (Philox sampling, Feistel permutations)"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": eng.h2d_bytes(), "d2h_bytes_per_step": 48,
                         "ms_per_step": e2e_ms_max / a.steps},

@@ -115,17 +115,43 @@ class R_MAPPO():
             if p2p is not None:           # write the local gradients straight into the peer-visible half
                 half = p2p.grad_half(self._parity)
                 ga, gc = half[:pol.actor.n_params], half[self._crit_off:self._crit_off + pol.critic.n_params]
+            two_streams = self.overlap_nets and p2p is not None      # our collective is an ordinary kernel on `main`
+            main = torch.cuda.current_stream()
+            if two_streams and self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+
+            def critic_grads():
+                if vn is not None:
+                    check(_lib.load().mappo_valuenorm_update(ptr(vn), ptr(norm_stats), stream_ptr()))
+                launch_grads(pol.critic, ws_c, batch, loss_c, norm_stats, None, vn, loss_out, grad_out=gc)
+
+            def critic_step():
+                launch_step(pol.critic, ws_c, loss_out, pol.critic_optimizer, self.max_grad_norm,
+                            self._use_max_grad_norm, 4, 0)
+
+            if two_streams:
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    critic_grads()
             launch_grads(pol.actor, ws_a, batch, loss_a, norm_stats, adv_stats, None, loss_out, grad_out=ga)
-            if vn is not None:
-                check(_lib.load().mappo_valuenorm_update(ptr(vn), ptr(norm_stats), stream_ptr()))
-            launch_grads(pol.critic, ws_c, batch, loss_c, norm_stats, None, vn, loss_out, grad_out=gc)
+            if two_streams:
+                main.wait_stream(self._side)
+            else:
+                critic_grads()
             if p2p is not None:
                 p2p.allreduce_grad(self._parity, self._joint_grad)
                 self._parity ^= 1
             else:
                 allreduce(self._joint_grad)
+            if two_streams:
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    critic_step()
             launch_step(pol.actor, ws_a, loss_out, pol.actor_optimizer, self.max_grad_norm, self._use_max_grad_norm, 3, 0)
-            launch_step(pol.critic, ws_c, loss_out, pol.critic_optimizer, self.max_grad_norm, self._use_max_grad_norm, 4, 0)
+            if two_streams:
+                main.wait_stream(self._side)
+            else:
+                critic_step()
         else:
             actor_chain()
             critic_chain()
