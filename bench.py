@@ -267,6 +267,10 @@ def run_gpu(a):
             peaks = json.load(open(pk))
         peak_tf = float(peaks.get("bf16_tflops", 1590.0))
         fa, fc = update_flops(cfg)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("update_mlp_tc_kernel" if a.gemm == "tf32" else "update_mlp_kernel")
         ach = (fa + fc) / 2 / (kt["avg_ms"] * 1e-3) / 1e12
         cores = best_cpu_threads(cfg) if world == 1 and a.cpu_iters > 0 else 1
         cpu_rate, cpu_per = cpu_iteration_rate(cfg, a.cpu_iters, 2, cores) if world == 1 and a.cpu_iters > 0 else (None, None)
@@ -283,7 +287,7 @@ def run_gpu(a):
                         "ms_per_step": e2e_ms_max / a.steps},
                 "gpu_launches": launches,
                 "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                             "traffic": None,
+                             "traffic": traffic, "traffic_unit": "bytes/launch (ncu --set full, profiles/)",
                              "kernel": ("update_mlp_tc_kernel (fused fwd+loss+bwd, tcgen05 kind::tf32 + TMEM; launch incl. "
                                         "its 1-CTA weight-pack kernel)") if a.gemm == "tf32" else
                                        "update_mlp_kernel (fused fwd+loss+bwd, fp32 FFMA tiles)",
@@ -343,7 +347,7 @@ def main():
     ap.add_argument("--gemm", default=os.environ.get("MAPPO_B200_GEMM", "tf32"), choices=["tf32", "fp32"],
                     help="GEMM engine of the update kernels (tf32 = tcgen05 tensor cores)")
     ap.add_argument("--eager", action="store_true", help="no CUDA graph (for per-kernel profiling under ncu)")
-    ap.add_argument("--cpu-iters", type=int, default=30, help="oracle iterations for cpu_baseline (rank 0, N=1)")
+    ap.add_argument("--cpu-iters", type=int, default=100, help="oracle iterations for cpu_baseline (rank 0, N=1)")
     a = ap.parse_args()
     if a.impl == "reference":
         if a.steps > 60:

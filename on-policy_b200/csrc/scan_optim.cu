@@ -336,24 +336,29 @@ __global__ void __launch_bounds__(256)
 clip_adam_kernel(float* __restrict__ p, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
                  int P, const float* __restrict__ sumsq_part, int n_part, const float* __restrict__ lr_dev,
                  int* __restrict__ step_dev, float eps, float max_norm, int use_clip, double* __restrict__ norm_out) {
-  __shared__ float s_total;
-  // every block re-derives the global norm from the per-block partials (n_part is small) in a fixed order
+  __shared__ float s_total, s_coef, s_step_size, s_bc2_sqrt;
+  __shared__ int s_step;
+  // every block re-derives the global norm from the per-block partials (n_part is small) in a fixed order; the
+  // scalar prologue (norm, clip coefficient, Adam bias corrections in fp64) runs in ONE warp and is broadcast
   if (threadIdx.x < 32) {
     double x = 0.0;
     for (int i = threadIdx.x; i < n_part; i += 32) x += (double)sumsq_part[i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-    if (threadIdx.x == 0) s_total = (float)sqrt(x);
+    if (threadIdx.x == 0) {
+      const float tot = (float)sqrt(x);
+      const int st = *step_dev + 1;                                      // 1-based Adam step
+      const double bc1 = 1.0 - pow(0.9, (double)st), bc2 = 1.0 - pow(0.999, (double)st);
+      s_total = tot;
+      s_coef = use_clip ? fminf(max_norm / (tot + 1e-6f), 1.0f) : 1.f;   // clip_grad_norm_
+      s_step_size = (float)((double)lr_dev[0] / bc1);
+      s_bc2_sqrt = (float)sqrt(bc2);
+      s_step = st;
+    }
   }
   __syncthreads();
-  const float total = s_total;
-  float coef = 1.f;
-  if (use_clip) coef = fminf(max_norm / (total + 1e-6f), 1.0f);        // clip_grad_norm_
-  const int step = *step_dev + 1;                                       // 1-based Adam step
-  const double b1 = 0.9, b2 = 0.999;
-  const double bc1 = 1.0 - pow(b1, (double)step), bc2 = 1.0 - pow(b2, (double)step);
-  const float step_size = (float)((double)lr_dev[0] / bc1);
-  const float bc2_sqrt = (float)sqrt(bc2);
+  const float total = s_total, coef = s_coef, step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+  const int step = s_step;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < P) {
     const float g = grad[i] * coef;
