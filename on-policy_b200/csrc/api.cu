@@ -338,7 +338,7 @@ int32_t mappo_update_finish(const mappo_net_desc_t* desc, const float* params, c
     float* raw_sum = workspace + update_mlp_tc_workspace_floats(n);
     rc = grad_reduce_launch(grad_part, n_slots, update_mlp_tc_slot_floats(n), raw_sum, nullptr, nullptr, (cudaStream_t)stream);
     if (rc) return rc;
-    if (n_blocks_out) *n_blocks_out = 1;
+    if (n_blocks_out) *n_blocks_out = 12;
     return update_mlp_tc_unfold_launch(n, params, raw_sum, grad, sumsq_part, (cudaStream_t)stream);
   }
   return grad_reduce_launch(grad_part, n_slots, n.g.total, grad, sumsq_part, n_blocks_out, (cudaStream_t)stream);

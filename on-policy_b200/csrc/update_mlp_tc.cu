@@ -159,64 +159,71 @@ __host__ __device__ inline TcRaw make_tc_raw(const TcImage& m) {
 }
 
 // dW = dW' diag(gamma_in), db = dW'[:, one], dgamma_in = colsum(dW' .* W), dbeta_in = W^T db'   (chain rule of the
-// folding), for the three layers, from the slot-summed raw accumulators.  One CTA; also emits sum(g^2).
-__global__ void __launch_bounds__(512)
+// folding) from the slot-summed raw accumulators.  Grid: blockIdx.y = layer (0 fc2, 1 fc1, 2 heads), blockIdx.x = block
+// of 16 input features; 256 threads = 16 features x 16 groups of 4 output rows.  Every CTA also emits its sum(g^2).
+__global__ void __launch_bounds__(256)
 tc_unfold_kernel(const NetDev n, const float* __restrict__ p, const float* __restrict__ raw, float* __restrict__ g,
                  float* __restrict__ sumsq_part) {
-  __shared__ float part_g[8][64], part_b[8][64], sred[16];
+  __shared__ float part_g[16][17], part_b[16][17], sred[8];
   const TcImage m = make_tc_image(n);
   const TcRaw R = make_tc_raw(m);
-  const int tid = threadIdx.x, k = tid & 63, pp = tid >> 6;
+  const int tid = threadIdx.x, kx = tid & 15, og = tid >> 4;
+  const int sec = blockIdx.y, k = blockIdx.x * 16 + kx;
   const int in = n.in_dim, Atot = n.head_total;
   float sq = 0.f;
   auto put = [&](int off, float v) { g[off] = v; sq = fmaf(v, v, sq); };
-#pragma unroll 1
-  for (int sec = 0; sec < 2; ++sec) {
+  if (sec < 2) {
     const int K = sec == 0 ? 64 : in, ld = sec == 0 ? kHF : m.inF, one = sec == 0 ? kOne : in;
     const float* G = raw + (sec == 0 ? R.g2 : R.g1);
     const int w_off = sec == 0 ? n.g.fc2_w[0] : n.g.fc1_w, b_off = sec == 0 ? n.g.fc2_b[0] : n.g.fc1_b;
     const bool fold = sec == 0 ? true : (n.use_fn != 0);
     const int gam_off = sec == 0 ? n.g.ln1_w : n.g.fn_w, bet_off = sec == 0 ? n.g.ln1_b : n.g.fn_b;
-    for (int idx = tid; idx < 64 * K; idx += 512) {
-      const int o = idx / K, kk = idx - o * K;
-      put(w_off + idx, G[o * ld + kk] * (fold ? p[gam_off + kk] : 1.f));
-    }
-    if (tid < 64) put(b_off + tid, G[tid * ld + one]);
     float sg = 0.f, sb = 0.f;
-    if (fold && k < K)
-      for (int o = pp; o < 64; o += 8) {
-        const float w = p[w_off + o * K + k];
-        sg = fmaf(G[o * ld + k], w, sg);
+    if (k < K) {
+      const float gam = fold ? p[gam_off + k] : 1.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int o = og * 4 + j;
+        const float dw = G[o * ld + k], w = p[w_off + o * K + k];
+        put(w_off + o * K + k, dw * gam);
+        sg = fmaf(dw, w, sg);
         sb = fmaf(G[o * ld + one], w, sb);
       }
+    }
+    if (blockIdx.x == 0 && tid < 64) put(b_off + tid, G[tid * ld + one]);
+    part_g[og][kx] = sg; part_b[og][kx] = sb;
     __syncthreads();
-    part_g[pp][k] = sg; part_b[pp][k] = sb;
-    __syncthreads();
-    if (fold && tid < K) {
+    if (fold && og == 0 && k < K) {
       float a = 0.f, c = 0.f;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) { a += part_g[q][tid]; c += part_b[q][tid]; }
-      put(gam_off + tid, a);
-      put(bet_off + tid, c);
+      for (int q = 0; q < 16; ++q) { a += part_g[q][kx]; c += part_b[q][kx]; }
+      put(gam_off + k, a);
+      put(bet_off + k, c);
+    }
+  } else {                                              // heads: raw gh[feature][a]; this CTA owns 16 features
+    const int kk = blockIdx.x * 16 + kx;                // < 64 (grid.x == 4 for this layer, extra blocks exit below)
+    if (kk < 64) {
+      const float gam = p[n.g.ln2_w[0] + kk];
+      float sg = 0.f, sb = 0.f;
+      for (int a = og; a < Atot; a += 16) {
+        const float dw = raw[R.gh + kk * m.NH + a], w = p[n.g.head_w + a * 64 + kk];
+        put(n.g.head_w + a * 64 + kk, dw * gam);
+        sg = fmaf(dw, w, sg);
+        sb = fmaf(raw[R.dbh + a], w, sb);
+      }
+      part_g[og][kx] = sg; part_b[og][kx] = sb;
+    } else { part_g[og][kx] = 0.f; part_b[og][kx] = 0.f; }
+    if (blockIdx.x == 0 && tid < Atot) put(n.g.head_b + tid, raw[R.dbh + tid]);
+    __syncthreads();
+    if (og == 0 && kk < 64) {
+      float a = 0.f, c = 0.f;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) { a += part_g[q][kx]; c += part_b[q][kx]; }
+      put(n.g.ln2_w[0] + kk, a);
+      put(n.g.ln2_b[0] + kk, c);
     }
   }
-  // heads: raw gh[k][a]
-  for (int idx = tid; idx < Atot * 64; idx += 512) {
-    const int a = idx >> 6, kk = idx & 63;
-    put(n.g.head_w + idx, raw[R.gh + kk * m.NH + a] * p[n.g.ln2_w[0] + kk]);
-  }
-  if (tid < Atot) put(n.g.head_b + tid, raw[R.dbh + tid]);
-  if (tid < 64) {
-    float a = 0.f, c = 0.f;
-    for (int q = 0; q < Atot; ++q) {
-      const float w = p[n.g.head_w + q * 64 + tid];
-      a = fmaf(raw[R.gh + tid * m.NH + q], w, a);
-      c = fmaf(raw[R.dbh + q], w, c);
-    }
-    put(n.g.ln2_w[0] + tid, a);
-    put(n.g.ln2_b[0] + tid, c);
-  }
-  // sum of squares of everything written
+  // sum of squares of everything this CTA wrote
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
   __syncthreads();
@@ -224,8 +231,9 @@ tc_unfold_kernel(const NetDev n, const float* __restrict__ p, const float* __res
   __syncthreads();
   if (tid == 0) {
     float t = 0.f;
-    for (int q = 0; q < 16; ++q) t += sred[q];
-    sumsq_part[0] = t;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += sred[q];
+    sumsq_part[blockIdx.y * gridDim.x + blockIdx.x] = t;
   }
 }
 
@@ -735,7 +743,7 @@ int update_mlp_tc_slot_floats(const NetDev& n) { return make_tc_raw(make_tc_imag
 // sum of the raw slots is in `raw_sum` -> flat gradient + sum(g^2) (one partial)
 int update_mlp_tc_unfold_launch(const NetDev& n, const float* params, const float* raw_sum, float* grad,
                                 float* sumsq_part, cudaStream_t st) {
-  tc_unfold_kernel<<<1, 512, 0, st>>>(n, params, raw_sum, grad, sumsq_part);
+  tc_unfold_kernel<<<dim3(4, 3), 256, 0, st>>>(n, params, raw_sum, grad, sumsq_part);       // 12 partial sums of squares
   return check_launch("tc_unfold_kernel");
 }
 

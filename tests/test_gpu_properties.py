@@ -1,0 +1,103 @@
+"""Size-independent properties at the FULL BASELINE c2 size (128 threads x 3 agents x 25 steps = 9600 rows) and the
+reference's edge cases (ragged tiles, empty inputs, unsupported configurations fail loudly)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mappo_oracle as O
+import test_gpu_parity as TP
+
+pytestmark = pytest.mark.gpu
+
+
+def c2():
+    return O.PathConfig(episode_length=25, n_rollout_threads=128, num_agents=3, obs_dim=18, share_obs_dim=54,
+                        act_dims=(5,), use_ReLU=False, ppo_epoch=1, num_mini_batch=1, lr=7e-4, critic_lr=7e-4)
+
+
+def test_gae_reduces_to_suffix_sums_at_full_size():
+    """gamma = lambda = 1, masks = 1, values = 0, no normaliser: returns[t] = sum_{s >= t} r[s]."""
+    cfg = O.PathConfig(**{**c2().to_dict(), "gamma": 1.0, "gae_lambda": 1.0, "use_valuenorm": False, "act_dims": (5,)})
+    args, policy, trainer, buf = TP.build(cfg)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    buf.rewards.copy_(torch.randn(buf.rewards.shape, device="cuda", generator=g))
+    buf.value_preds.zero_()
+    buf.compute_returns(torch.zeros(128, 3, 1), None)
+    want = torch.flip(torch.cumsum(torch.flip(buf.rewards.double(), [0]), 0), [0])
+    assert torch.allclose(buf.returns[:-1].double(), want, rtol=1e-5, atol=1e-5)
+    assert int(buf._adv_stats[2].item()) == 9600
+
+
+def test_gather_round_trip_with_device_permutation():
+    """gather(perm) followed by gather(inverse perm) is the identity; the device permutation is a bijection."""
+    from mappo_b200 import _lib
+    lib = _lib.load()
+    n, dim = 9600, 54
+    x = torch.randn(n, dim, device="cuda")
+    perm = torch.empty(n, dtype=torch.int32, device="cuda")
+    ctr = torch.zeros(1, dtype=torch.int64, device="cuda")
+    _lib.check(lib.mappo_randperm(n, 77, ctr.data_ptr(), perm.data_ptr(), None))
+    inv = torch.empty_like(perm)
+    inv[perm.long()] = torch.arange(n, dtype=torch.int32, device="cuda")
+    y, z = torch.empty_like(x), torch.empty_like(x)
+    _lib.check(lib.mappo_gather_rows(x.data_ptr(), perm.data_ptr(), n, dim, y.data_ptr(), None))
+    _lib.check(lib.mappo_gather_rows(y.data_ptr(), inv.data_ptr(), n, dim, z.data_ptr(), None))
+    assert torch.equal(x, z)
+    assert torch.equal(torch.sort(perm).values, torch.arange(n, dtype=torch.int32, device="cuda"))
+
+
+@pytest.mark.parametrize("gemm", ["fp32", "tf32"])
+def test_first_epoch_identities_at_full_size(gemm, monkeypatch):
+    """On the first optimiser step the new policy equals the sampling policy: ratio == 1 exactly (fp32) and the
+    surrogate loss equals -mean(normalised advantages) = 0; gradients are permutation invariant."""
+    monkeypatch.setenv("MAPPO_B200_GEMM", gemm)
+    cfg = c2()
+    infos, grads = [], []
+    for seed in (0, 1):                                  # two different permutations of the same rollout
+        torch.manual_seed(1)
+        args, policy, trainer, buf = TP.build(cfg)
+        feed = O.make_feed(cfg, seed=3)
+        TP.warm(buf, feed)
+        torch.manual_seed(5)
+        TP.collect_and_returns(cfg, policy, trainer, buf, feed, None)
+        torch.manual_seed(100 + seed)
+        infos.append(trainer.train(buf))
+        grads.append((policy.actor.grad.clone(), policy.critic.grad.clone()))
+    tol = 1e-6 if gemm == "fp32" else 2e-3
+    assert abs(infos[0]["ratio"] - 1.0) < tol
+    assert abs(infos[0]["policy_loss"]) < 1e-4
+    for (a0, c0), (a1, c1) in [grads]:
+        sa, sc = a0.abs().max().item(), c0.abs().max().item()
+        assert (a0 - a1).abs().max().item() <= 2e-4 * sa + 1e-9, "actor gradient depends on the minibatch order"
+        assert (c0 - c1).abs().max().item() <= 2e-4 * sc + 1e-9, "critic gradient depends on the minibatch order"
+
+
+def test_adam_leaves_parameters_alone_for_zero_gradients():
+    from mappo_b200.core import FusedAdam
+    args, policy, trainer, buf = TP.build(c2())
+    net = policy.actor
+    before = net.flat.clone()
+    opt = FusedAdam(net, lr=7e-4, eps=1e-5)
+    net.grad.zero_()
+    norm = torch.zeros(1, dtype=torch.float64, device="cuda")
+    opt.apply(10.0, True, norm.data_ptr())
+    assert torch.equal(before, net.flat) and norm.item() == 0.0
+    assert int(opt.step_dev[0].item()) == 1 and int(opt.step_dev[1].item()) == 0
+
+
+def test_unsupported_configurations_fail_loudly():
+    from mappo_b200 import _lib
+    lib = _lib.load()
+    big = O.PathConfig(hidden_size=512, layer_N=2, obs_dim=658, share_obs_dim=783, act_dims=(20,), n_rollout_threads=4,
+                       episode_length=4, num_agents=2)           # config c5: not built yet
+    args, policy, trainer, buf = TP.build(big)
+    with pytest.raises(RuntimeError, match="hidden_size 512"):
+        policy.get_values(torch.zeros(8, 783), torch.zeros(8, 1, 512), torch.ones(8, 1))
+    d = _lib.NetDesc()
+    d.in_dim, d.hidden, d.layer_n, d.n_heads = 10, 64, 1, 9
+    assert lib.mappo_net_layout(C.byref(d), C.byref(_lib.NetLayout())) == -3
+    # empty inputs are accepted where the reference would simply loop zero times
+    assert lib.mappo_gather_rows(None, None, 0, 4, None, None) == 0
+    assert lib.mappo_randperm(0, 1, None, None, None) == 0
