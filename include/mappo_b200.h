@@ -133,6 +133,20 @@ int32_t mappo_policy_step(const mappo_net_desc_t* actor_desc, const float* actor
 /* Optional: the rollout weights do not change during the T collect steps of an iteration.  Packing them once into
  * the kernel's shared-memory layout lets every policy_step CTA fetch them with one TMA bulk copy
  * (cp.async.bulk + mbarrier) -- pass the images to mappo_policy_step (NULL = load from the flat parameters). */
+/* The whole collect phase of one iteration as ONE launch, for the device-resident pipeline where the env outputs of
+ * the iteration are already staged in HBM (synthetic / on-device environments): T x (policy_step + env_insert) + the
+ * bootstrap get_values of Runner.compute (runner/shared/mpe_runner.py:26-40, base_runner.py:120-134).  Rows never
+ * interact, so each CTA keeps its 32 rows, the weights and the recurrent state on chip and walks t = 0..T.
+ * Storage pointers address slot 0 (slots are E*dim floats apart); f_* are the staged env outputs, index t = what the env
+ * returned after step t (written to slot t+1; rewards to slot t).  Sampling as in mappo_policy_step (per-step noise
+ * [T, E, sum A] or Philox; the device offset advances by T*E). */
+int32_t mappo_rollout_persistent(const mappo_net_desc_t* actor_desc, const float* actor_params, const float* actor_image,
+                                 const mappo_net_desc_t* critic_desc, const float* critic_params, const float* critic_image,
+                                 float* obs, float* share_obs, float* h_actor, float* h_critic, float* masks, float* avail,
+                                 float* value_preds, float* actions, float* logp, float* rewards, float* active_masks,
+                                 const float* f_obs, const float* f_share, const float* f_rew, const float* f_done,
+                                 const float* f_active, const float* f_avail, const float* exp_noise, uint64_t rng_seed,
+                                 uint64_t* rng_offset_dev, int32_t T, int32_t E, void* stream);
 int32_t mappo_rollout_image_floats(const mappo_net_desc_t* desc);
 int32_t mappo_pack_rollout_weights(const mappo_net_desc_t* desc, const float* params, float* image, void* stream);
 
@@ -174,6 +188,12 @@ int32_t mappo_advantages(const float* returns, const float* value_preds, const f
  * (doubles; caller zeroes).  Multi-GPU: the caller all-reduces `stats` before applying them. */
 int32_t mappo_minibatch_stats(const float* returns, const float* active_masks, const int32_t* rows,
                               int32_t n_rows, double* stats, void* stream);
+/* Kernels this library has launched (or recorded into a CUDA graph capture) since it was loaded. */
+int64_t mappo_debug_launch_count(void);
+/* The same for every minibatch of a train() call in one launch: rows of update u start at rows + u*rows_stride, its
+ * statistics land in stats[4u .. 4u+3]. */
+int32_t mappo_minibatch_stats_batch(const float* returns, const float* active_masks, const int32_t* rows,
+                                    int64_t rows_stride, int32_t n_rows, int32_t n_batches, double* stats, void* stream);
 /* ValueNorm.update (utils/valuenorm.py:38-55) from reduced statistics: vn_state <- beta-blend. */
 int32_t mappo_valuenorm_update(float* vn_state, const double* stats, void* stream);
 
@@ -191,6 +211,9 @@ int32_t mappo_chunk_rows(const int32_t* chunks, int32_t n_chunks, int32_t L, int
 /* Device-side random permutation of [0, n) (stand-in for torch.randperm when the host RNG stream
  * is not being reproduced): keyed Feistel network with cycle walking, seed + *counter_dev. */
 int32_t mappo_randperm(int32_t n, uint64_t seed, const uint64_t* counter_dev, int32_t* out, void* stream);
+/* n_perms independent permutations (one per ppo epoch) in one launch: out[e*n .. (e+1)*n). */
+int32_t mappo_randperm_batch(int32_t n, int32_t n_perms, uint64_t seed, const uint64_t* counter_dev, int32_t* out,
+                             void* stream);
 
 /* ---- a9 - a12: training forward + losses + backward -----------------------------------------
  * policy.evaluate_actions (rMAPPOPolicy.py:88-114; r_actor_critic.py:73-117, 156-175;

@@ -1,6 +1,7 @@
 // api.cu -- the extern "C" surface of libmappo_b200.so (declared in include/mappo_b200.h).
 // No torch types, no allocation, no host synchronisation: every call validates its arguments on the host,
 // launches on the caller's stream and returns.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -18,12 +19,16 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static std::atomic<long long> g_launches{0};
+
+// every kernel launch of the library reports here under its kernel name ("x: attribute" strings are not launches)
 int check_launch(const char* what) {
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: %s", what, cudaGetErrorString(e));
     return MAPPO_ERR_CUDA;
   }
+  if (!strchr(what, ':')) g_launches.fetch_add(1, std::memory_order_relaxed);
   return MAPPO_OK;
 }
 
@@ -94,7 +99,8 @@ int minibatch_stats_launch(const float*, const float*, const int32_t*, int, doub
 int valuenorm_update_launch(float*, const double*, cudaStream_t);
 int gather_rows_launch(const float*, const int32_t*, int, int, float*, cudaStream_t);
 int chunk_rows_launch(const int32_t*, int, int, int, int, int32_t*, int32_t*, cudaStream_t);
-int randperm_launch(int, uint64_t, const uint64_t*, int32_t*, cudaStream_t);
+int randperm_launch(int, uint64_t, const uint64_t*, int32_t*, cudaStream_t, int n_perms = 1);
+int minibatch_stats_batch_launch(const float*, const float*, const int32_t*, long long, int, int, double*, cudaStream_t);
 int grad_reduce_launch(const float*, int, int, float*, float*, int*, cudaStream_t);
 int sumsq_launch(const float*, int, float*, int*, cudaStream_t);
 int clip_adam_launch(float*, const float*, float*, float*, int, const float*, int, const float*, int*, float, float,
@@ -189,6 +195,35 @@ int32_t mappo_policy_step(const mappo_net_desc_t* ad, const float* ap, const map
   return policy_step_launch(has_a ? &na : nullptr, has_c ? &nc : nullptr, a, (cudaStream_t)stream);
 }
 
+int32_t mappo_rollout_persistent(const mappo_net_desc_t* ad, const float* ap, const float* a_img,
+                                 const mappo_net_desc_t* cd, const float* cp, const float* c_img,
+                                 float* obs, float* share_obs, float* h_actor, float* h_critic, float* masks, float* avail,
+                                 float* value_preds, float* actions, float* logp, float* rewards, float* active_masks,
+                                 const float* f_obs, const float* f_share, const float* f_rew, const float* f_done,
+                                 const float* f_active, const float* f_avail, const float* exp_noise, uint64_t rng_seed,
+                                 uint64_t* rng_offset_dev, int32_t T, int32_t E, void* stream) {
+  int rc = validate_desc(ad); if (rc) return rc;
+  rc = validate_desc(cd); if (rc) return rc;
+  if (ad->is_critic || !cd->is_critic) { set_error("rollout_persistent: actor/critic descriptors swapped"); return MAPPO_ERR_INVALID; }
+  if (!ap || !cp || !obs || !share_obs || !masks || !value_preds || !actions || !logp || !rewards || !f_obs || !f_share ||
+      !f_rew || !f_done || T <= 0 || E <= 0) { set_error("rollout_persistent: NULL / bad argument"); return MAPPO_ERR_INVALID; }
+  if ((ad->recurrent && !h_actor) || (cd->recurrent && !h_critic)) { set_error("rollout_persistent: recurrent net without state storage"); return MAPPO_ERR_INVALID; }
+  if (!exp_noise && !rng_offset_dev) { set_error("rollout_persistent: sampling needs exp_noise or rng_offset_dev"); return MAPPO_ERR_INVALID; }
+  if ((avail != nullptr) != (f_avail != nullptr)) { set_error("rollout_persistent: avail storage and staged avail must come together"); return MAPPO_ERR_INVALID; }
+  if (f_active && !active_masks) { set_error("rollout_persistent: staged active masks without storage"); return MAPPO_ERR_INVALID; }
+  RolloutArgs a;
+  a.params[0] = ap; a.params[1] = cp; a.image[0] = a_img; a.image[1] = c_img;
+  a.obs = obs; a.share_obs = share_obs; a.h_actor = h_actor; a.h_critic = h_critic; a.masks = masks; a.avail = avail;
+  a.value_preds = value_preds; a.actions = actions; a.logp = logp; a.rewards = rewards; a.active = active_masks;
+  a.f_obs = f_obs; a.f_share = f_share; a.f_rew = f_rew; a.f_done = f_done; a.f_active = f_active; a.f_avail = f_avail;
+  a.exp_noise = exp_noise; a.rng_seed = rng_seed; a.rng_offset = rng_offset_dev; a.T = T; a.E = E;
+  a.n_avail = ad->head_dim[0];
+  rc = rollout_persistent_launch(make_net_dev(ad), make_net_dev(cd), a, (cudaStream_t)stream);
+  if (rc) return rc;
+  if (!exp_noise) return counter_add_launch(rng_offset_dev, (uint64_t)T * (uint64_t)E, (cudaStream_t)stream);
+  return MAPPO_OK;
+}
+
 int32_t mappo_rollout_image_floats(const mappo_net_desc_t* desc) {
   if (validate_desc(desc)) return -1;
   return rollout_image_floats(make_net_dev(desc));
@@ -256,6 +291,19 @@ int32_t mappo_minibatch_stats(const float* returns, const float* active_masks, c
                               double* stats, void* stream) {
   if (!returns || !active_masks || !stats || n_rows <= 0) { set_error("minibatch_stats: bad arguments"); return MAPPO_ERR_INVALID; }
   return minibatch_stats_launch(returns, active_masks, rows, n_rows, stats, (cudaStream_t)stream);
+}
+
+int64_t mappo_debug_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
+
+int32_t mappo_minibatch_stats_batch(const float* returns, const float* active_masks, const int32_t* rows,
+                                    int64_t rows_stride, int32_t n_rows, int32_t n_batches, double* stats, void* stream) {
+  if (!returns || !active_masks || !rows || !stats || n_rows <= 0 || n_batches <= 0) { set_error("minibatch_stats_batch: bad arguments"); return MAPPO_ERR_INVALID; }
+  return minibatch_stats_batch_launch(returns, active_masks, rows, rows_stride, n_rows, n_batches, stats, (cudaStream_t)stream);
+}
+
+int32_t mappo_randperm_batch(int32_t n, int32_t n_perms, uint64_t seed, const uint64_t* counter_dev, int32_t* out, void* stream) {
+  if (n < 0 || n_perms < 0 || (n > 0 && n_perms > 0 && !out)) { set_error("randperm_batch: bad arguments"); return MAPPO_ERR_INVALID; }
+  return randperm_launch(n, seed, counter_dev, out, (cudaStream_t)stream, n_perms);
 }
 
 int32_t mappo_valuenorm_update(float* vn_state, const double* stats, void* stream) {

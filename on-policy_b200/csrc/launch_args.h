@@ -30,6 +30,17 @@ struct InsertArgs {
   uint64_t rng_inc;
 };
 
+struct RolloutArgs {
+  const float* params[2];
+  const float* image[2];
+  float *obs, *share_obs, *h_actor, *h_critic, *masks, *avail, *value_preds, *actions, *logp, *rewards, *active;
+  const float *f_obs, *f_share, *f_rew, *f_done, *f_active, *f_avail;
+  const float* exp_noise;
+  uint64_t rng_seed;
+  uint64_t* rng_offset;
+  int T, E, n_avail;
+};
+int rollout_persistent_launch(const NetDev& na, const NetDev& nc, const RolloutArgs& a, cudaStream_t st);
 int policy_step_launch(const NetDev* na, const NetDev* nc, const PolArgs& a, cudaStream_t st);
 int env_insert_launch(const InsertArgs& a, cudaStream_t st);
 

@@ -146,6 +146,7 @@ __device__ __forceinline__ void head_lse(const float* __restrict__ lgT, int off,
 // ---------------------------------------------------------------------------------------------
 struct LossConsts {
   double sum_active, n_rows_d;
+  double inv_sum_active, inv_n_rows;      // reciprocals formed once per kernel (a row then needs one DMUL, not a DDIV)
   float adv_mean, adv_inv, vmean, vrs;
 };
 
@@ -156,6 +157,8 @@ __device__ __forceinline__ LossConsts make_loss_consts(const NetDev& n, const Lo
   LossConsts c;
   c.sum_active = norm_stats[0];
   c.n_rows_d = norm_stats[3];
+  c.inv_sum_active = 1.0 / c.sum_active;
+  c.inv_n_rows = 1.0 / c.n_rows_d;
   c.adv_mean = 0.f;
   c.adv_inv = 1.f;
   if (adv_stats) {                               // r_mappo.py:183-187: stats over active entries, applied to all
@@ -221,7 +224,7 @@ __device__ __forceinline__ void row_loss_pre(const NetDev& n, const BatchDev& b,
   }
   if (n.is_critic) {
     const float act = q.active;
-    const float w = L.use_value_active ? (float)((double)act / c.sum_active) : (float)(1.0 / c.n_rows_d);
+    const float w = L.use_value_active ? (float)((double)act * c.inv_sum_active) : (float)c.inv_n_rows;
     const float v = lgT[r], vo = q.v_old;
     const float ret = q.ret;
     const float target = L.use_valuenorm ? (ret - c.vmean) * c.vrs : ret;       // valuenorm.py:57-66
@@ -251,7 +254,7 @@ __device__ __forceinline__ void row_loss_pre(const NetDev& n, const BatchDev& b,
     return;
   }
   const float act = q.active;
-  const float w = L.use_policy_active ? (float)((double)act / c.sum_active) : (float)(1.0 / c.n_rows_d);
+  const float w = L.use_policy_active ? (float)((double)act * c.inv_sum_active) : (float)c.inv_n_rows;
   const float adv = (q.adv - c.adv_mean) * c.adv_inv;
   const float* av = (b.avail && n.n_heads == 1) ? b.avail + (size_t)gr * b.n_avail : nullptr;
   const float inv_heads = 1.0f / (float)n.n_heads;

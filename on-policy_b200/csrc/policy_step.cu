@@ -91,57 +91,71 @@ __host__ __device__ inline PolSmem make_pol_smem(const NetDev& n, const SmemW& s
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// Per-step operands of one net for the rows [row0, row0 + TR) of a step.
+struct PolStep {
+  const float* in;            // [E, in_dim] input rows of this step
+  float* in_copy;             // optional: also store the rows here (persistent rollout: the insert of slot t)
+  const float* h_in;          // [E, H] recurrent state of this step, or NULL to use the state carried in shared memory
+  const float* masks;         // [E] or NULL (persistent rollout passes mask_from_done)
+  const float* done_prev;     // [E] done flags of the previous env step: mask = 1 - done (persistent rollout)
+  float* masks_copy;          // optional: store the masks of this step (insert)
+  float* h_out;               // [E, H] new state (slot t+1), optional
+  const float* done_now;      // [E] done flags of THIS env step: zero the new state of done rows (mpe_runner.py:128-131)
+  const float* avail;         // [E, A] or NULL
+  float* avail_copy;
+  const float* exp_noise;     // [E, sum A] or NULL
+  uint64_t rng_ctr;           // Philox counter base of this step (device value + step offset)
+  float* values;              // critic out [E]
+  float* actions;             // actor outs
+  int64_t* actions_i64;
+  float* logp;
+  bool forward;               // false: only the copies (last slot of the actor in the persistent rollout)
+};
+
+struct PolCtx {
+  float* sW;
+  BaseTiles<kPolTR> t;
+  SmemW s;
+  PolSmem u;
+  int* rowid;
+  float* smem;
+  float* hcarry;              // [H][LD] recurrent state carried between steps (persistent rollout)
+};
+
 template <int NJH>
-__global__ void __launch_bounds__(4 * kPolTR)
-policy_step_kernel(const NetDev na, const NetDev nc, const PolArgs a, int first_net) {
+__device__ __forceinline__ void pol_step(const NetDev& n, int which, const PolCtx& c, const PolStep& p, int n_rows,
+                                         int row0, int deterministic, uint64_t rng_seed, int n_avail, int tid) {
   constexpr int TR = kPolTR;
   constexpr int LD = Tile<TR>::LD;
   constexpr int NT = Tile<TR>::NT;
-  extern __shared__ __align__(16) float smem[];
-  const int tid = threadIdx.x;
-  const int which = first_net + blockIdx.y;           // 0 actor, 1 critic
-  const NetDev& n = which == 0 ? na : nc;
-  const SmemW s = make_smem_w(n, true);
-  const PolSmem u = make_pol_smem(n, s);
-  float* sW = smem + u.w;
-  BaseTiles<TR> t;
-  t.xh0 = smem + u.xh0;
-  t.x0 = smem + u.x0;
-  // fused layers read Y[l-1] and write Y[l]: ping-pong between the two scratch tiles
-  for (int l = 0; l <= kMaxLayers; ++l) { t.A[l] = nullptr; t.Y[l] = smem + ((l & 1) ? u.s0 : u.s1); }
-  t.keep_act = false;
-  for (int l = 0; l < kMaxLayers + 2; ++l) { t.mean[l] = smem + u.stats + 2 * l * TR; t.rstd[l] = t.mean[l] + TR; }
-  t.red = smem + u.red;
-  int* rowid = reinterpret_cast<int*>(smem + u.rowid);
   const int H = n.hid;
-
-  __shared__ uint64_t wbar;
-  const float* image = a.image[which];
-  if (image) {                                        // one TMA bulk copy of the pre-packed image (UBLKCP)
-    if (tid == 0) {
-      const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&wbar);
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(s.total * 4)) : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"((uint32_t)__cvta_generic_to_shared(sW)), "l"(image), "r"((uint32_t)(s.total * 4)), "r"(bar) : "memory");
+  const SmemW& s = c.s;
+  const PolSmem& u = c.u;
+  float* smem = c.smem;
+  float* sW = c.sW;
+  const int* rowid = c.rowid;
+  // ---- rows of this step: coalesced (a warp walks a row), optional copy into the storage slot ----
+  {
+    const int warp = tid >> 5, lane = tid & 31, nw = NT >> 5;
+    for (int r = warp; r < TR; r += nw) {
+      const int g = rowid[r];
+      for (int k = lane; k < n.in_dim; k += 32) {
+        const float v = g >= 0 ? p.in[(size_t)g * n.in_dim + k] : 0.f;
+        c.t.x0[k * LD + r] = v;
+        if (p.in_copy && g >= 0) p.in_copy[(size_t)g * n.in_dim + k] = v;
+      }
     }
-  } else {
-    load_weights(sW, s, n, a.params[which], true, tid, NT);
+    if (which == 0 && p.avail_copy && p.avail)
+      for (int i = tid; i < TR * n_avail; i += NT) {
+        const int r = i / n_avail, k = i - r * n_avail, g = rowid[r];
+        if (g >= 0) p.avail_copy[(size_t)g * n_avail + k] = p.avail[(size_t)g * n_avail + k];
+      }
+    if (which == 0 && p.masks_copy && tid < TR && rowid[tid] >= 0)
+      p.masks_copy[rowid[tid]] = p.done_prev ? (p.done_prev[rowid[tid]] != 0.f ? 0.f : 1.f) : p.masks[rowid[tid]];
   }
-  const int row0 = blockIdx.x * TR;
-  if (tid < TR) rowid[tid] = row0 + tid < a.n_rows ? row0 + tid : -1;
-  __syncthreads();
-  load_rows_T<TR>(a.in[which], n.in_dim, rowid, t.x0, tid);
-  if (image) {                                        // every thread waits for the image (barrier init is ordered by the
-    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&wbar);   // __syncthreads() above)
-    uint32_t ok = 0;
-    while (!ok)
-      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                   : "=r"(ok) : "r"(bar), "r"(0u) : "memory");
-  }
-  base_forward<TR, NJH>(n, s, sW, t, tid);
-  const float* feat = t.Y[n.layer_n];
+  if (!p.forward) { __syncthreads(); return; }
+  base_forward<TR, NJH>(n, s, sW, c.t, tid);
+  const float* feat = c.t.Y[n.layer_n];
 
   if (n.recurrent) {
     // h <- h * mask (rnn.py:27), one GRU step (torch gate order r,z,n), LN (rnn.py:79)
@@ -149,9 +163,14 @@ policy_step_kernel(const NetDev na, const NetDev nc, const PolArgs a, int first_
     float* gi = smem + u.gi;
     float* gh = smem + u.gh;
     for (int i = tid; i < TR * H; i += NT) {
-      const int r = i / H, c = i - r * H;
+      const int r = i / H, cc = i - r * H;
       const int g = rowid[r];
-      hT[c * LD + r] = g >= 0 ? a.h_in[which][(size_t)g * H + c] * a.masks[g] : 0.f;
+      float m = 0.f, h = 0.f;
+      if (g >= 0) {
+        m = p.done_prev ? (p.done_prev[g] != 0.f ? 0.f : 1.f) : p.masks[g];
+        h = p.h_in ? p.h_in[(size_t)g * H + cc] : c.hcarry[cc * LD + r];
+      }
+      hT[cc * LD + r] = h * m;
     }
     __syncthreads();
 #pragma unroll 1
@@ -167,8 +186,8 @@ policy_step_kernel(const NetDev na, const NetDev nc, const PolArgs a, int first_
     __syncthreads();
     float* hn = (feat == smem + u.s0) ? smem + u.s1 : smem + u.s0;      // new hidden state (pre-LN): the free tile
     for (int i = tid; i < TR * H; i += NT) {
-      const int c = i / TR, r = i - c * TR;
-      const int o = c * LD + r;
+      const int cc = i / TR, r = i - cc * TR;
+      const int o = cc * LD + r;
       const float rg = sigmoidf_(gi[o]);
       const float zg = sigmoidf_(gi[H * LD + o]);
       const float ng = tanhf(gi[2 * H * LD + o] + rg * gh[o]);
@@ -176,13 +195,16 @@ policy_step_kernel(const NetDev na, const NetDev nc, const PolArgs a, int first_
     }
     __syncthreads();
     for (int i = tid; i < TR * H; i += NT) {
-      const int r = i / H, c = i - r * H;
+      const int r = i / H, cc = i - r * H;
       const int g = rowid[r];
-      if (g >= 0 && a.h_out[which]) a.h_out[which][(size_t)g * H + c] = hn[c * LD + r];
+      float v = hn[cc * LD + r];
+      if (g >= 0 && p.done_now && p.done_now[g] != 0.f) v = 0.f;       // env done: next episode starts from zeros
+      if (g >= 0 && p.h_out) p.h_out[(size_t)g * H + cc] = v;
+      if (c.hcarry) c.hcarry[cc * LD + r] = v;
     }
     float* ln_out = (hn == smem + u.s0) ? smem + u.s1 : smem + u.s0;    // old feat tile: gates are done with it
-    tile_layernorm<TR>(hn, H, sW + s.rln_w, sW + s.rln_b, ln_out, t.mean[kMaxLayers + 1] + 2 * TR,
-                       t.rstd[kMaxLayers + 1] + 2 * TR, t.red, tid);
+    tile_layernorm<TR>(hn, H, sW + s.rln_w, sW + s.rln_b, ln_out, c.t.mean[kMaxLayers + 1] + 2 * TR,
+                       c.t.rstd[kMaxLayers + 1] + 2 * TR, c.t.red, tid);
     feat = ln_out;
   }
 
@@ -194,12 +216,11 @@ policy_step_kernel(const NetDev na, const NetDev nc, const PolArgs a, int first_
   if (tid < TR && rowid[tid] >= 0) {
     const int r = tid, g = rowid[r];
     if (which == 1) {
-      if (a.values) a.values[g] = lgT[r];
+      if (p.values) p.values[g] = lgT[r];
     } else {
-      const float* av = (a.avail && n.n_heads == 1) ? a.avail + (size_t)g * a.n_avail : nullptr;
+      const float* av = (p.avail && n.n_heads == 1) ? p.avail + (size_t)g * n_avail : nullptr;
       const int as = n.n_heads;
-      uint64_t ctr = 0;
-      if (!a.exp_noise && !a.deterministic) ctr = *a.rng_offset + (uint64_t)g;
+      const uint64_t ctr = p.rng_ctr + (uint64_t)g;
       int off = 0;
       for (int k = 0; k < as; ++k) {
         const int A = n.head_dim[k];
@@ -212,29 +233,160 @@ policy_step_kernel(const NetDev na, const NetDev nc, const PolArgs a, int first_
           float lgt = lgT[(off + j) * LD + r];
           if (av && av[j] == 0.f) lgt = -1e10f;
           const float lp = lgt - lse;
-          const float p = expf(lp);
-          float score = p;
-          if (!a.deterministic) {
+          const float pr = expf(lp);
+          float score = pr;
+          if (!deterministic) {
             float q;
-            if (a.exp_noise) {
-              q = a.exp_noise[(size_t)g * Atot + off + j];
+            if (p.exp_noise) {
+              q = p.exp_noise[(size_t)g * Atot + off + j];
             } else {
               if ((j & 3) == 0)
                 rnd = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)(k * 64 + (j >> 2)), 0u),
-                                    make_uint2((uint32_t)a.rng_seed, (uint32_t)(a.rng_seed >> 32)));
+                                    make_uint2((uint32_t)rng_seed, (uint32_t)(rng_seed >> 32)));
               const uint32_t x = (j & 3) == 0 ? rnd.x : ((j & 3) == 1 ? rnd.y : ((j & 3) == 2 ? rnd.z : rnd.w));
               q = -logf(((float)x + 0.5f) * 2.3283064365386963e-10f);
             }
-            score = p / q;                                   // torch multinomial: argmax(p / Exp(1))
+            score = pr / q;                                  // torch multinomial: argmax(p / Exp(1))
           }
           if (score > bestv) { bestv = score; best = j; best_lp = lp; }
         }
-        if (a.actions) a.actions[(size_t)g * as + k] = (float)best;
-        if (a.actions_i64) a.actions_i64[(size_t)g * as + k] = (int64_t)best;
-        if (a.logp) a.logp[(size_t)g * as + k] = best_lp;
+        if (p.actions) p.actions[(size_t)g * as + k] = (float)best;
+        if (p.actions_i64) p.actions_i64[(size_t)g * as + k] = (int64_t)best;
+        if (p.logp) p.logp[(size_t)g * as + k] = best_lp;
         off += A;
       }
     }
+  }
+  __syncthreads();
+}
+
+// shared setup of both kernels: carve shared memory, start the weight fetch, fill rowid; returns the context
+template <int NJH>
+__device__ __forceinline__ PolCtx pol_setup(const NetDev& n, float* smem, const float* params, const float* image,
+                                            int n_rows, uint64_t* wbar, int tid) {
+  constexpr int TR = kPolTR;
+  constexpr int NT = Tile<TR>::NT;
+  PolCtx c;
+  c.s = make_smem_w(n, true);
+  c.u = make_pol_smem(n, c.s);
+  c.smem = smem;
+  c.sW = smem + c.u.w;
+  c.t.xh0 = smem + c.u.xh0;
+  c.t.x0 = smem + c.u.x0;
+  // fused layers read Y[l-1] and write Y[l]: ping-pong between the two scratch tiles
+  for (int l = 0; l <= kMaxLayers; ++l) { c.t.A[l] = nullptr; c.t.Y[l] = smem + ((l & 1) ? c.u.s0 : c.u.s1); }
+  c.t.keep_act = false;
+  for (int l = 0; l < kMaxLayers + 2; ++l) { c.t.mean[l] = smem + c.u.stats + 2 * l * TR; c.t.rstd[l] = c.t.mean[l] + TR; }
+  c.t.red = smem + c.u.red;
+  c.rowid = reinterpret_cast<int*>(smem + c.u.rowid);
+  c.hcarry = nullptr;
+  if (image) {                                        // one TMA bulk copy of the pre-packed image (UBLKCP)
+    if (tid == 0) {
+      const uint32_t bar = (uint32_t)__cvta_generic_to_shared(wbar);
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(c.s.total * 4)) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"((uint32_t)__cvta_generic_to_shared(c.sW)), "l"(image), "r"((uint32_t)(c.s.total * 4)), "r"(bar) : "memory");
+    }
+  } else {
+    load_weights(c.sW, c.s, n, params, true, tid, NT);
+  }
+  const int row0 = blockIdx.x * TR;
+  if (tid < TR) c.rowid[tid] = row0 + tid < n_rows ? row0 + tid : -1;
+  __syncthreads();
+  if (image) {                                        // every thread waits for the image (init ordered by the barrier)
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(wbar);
+    uint32_t ok = 0;
+    while (!ok)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(bar), "r"(0u) : "memory");
+  }
+  return c;
+}
+
+template <int NJH>
+__global__ void __launch_bounds__(4 * kPolTR)
+policy_step_kernel(const NetDev na, const NetDev nc, const PolArgs a, int first_net) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ uint64_t wbar;
+  const int tid = threadIdx.x;
+  const int which = first_net + blockIdx.y;           // 0 actor, 1 critic
+  const NetDev& n = which == 0 ? na : nc;
+  const PolCtx c = pol_setup<NJH>(n, smem, a.params[which], a.image[which], a.n_rows, &wbar, tid);
+  PolStep p;
+  p.in = a.in[which]; p.in_copy = nullptr; p.h_in = a.h_in[which]; p.masks = a.masks; p.done_prev = nullptr;
+  p.masks_copy = nullptr; p.h_out = a.h_out[which]; p.done_now = nullptr; p.avail = a.avail; p.avail_copy = nullptr;
+  p.exp_noise = a.exp_noise;
+  p.rng_ctr = (!a.exp_noise && !a.deterministic && which == 0) ? *a.rng_offset : 0ull;
+  p.values = a.values; p.actions = a.actions; p.actions_i64 = a.actions_i64; p.logp = a.logp; p.forward = true;
+  pol_step<NJH>(n, which, c, p, a.n_rows, blockIdx.x * kPolTR, a.deterministic, a.rng_seed, a.n_avail, tid);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent rollout: the T collect steps + inserts of one iteration as ONE launch.  Rows never interact (an MLP / GRU
+// policy is row-wise, compute_returns works per lane), and in the device-resident pipeline the env outputs of the whole
+// iteration are already staged in HBM -- so a CTA keeps its 32 rows AND the weights in shared memory and walks
+// t = 0..T: read the step's rows (slot 0 of the storage for t = 0, the staged env output afterwards), store them into
+// slot t (= SharedReplayBuffer.insert), forward, sample, write values / actions / log-probs / states; the critic CTA
+// finishes with the bootstrap value of slot T (= Runner.compute's get_values).
+// Replaces T x (mappo_policy_step + mappo_env_insert) + the get_values launch: 2T + 1 launches -> 1.
+// ---------------------------------------------------------------------------------------------------------------
+template <int NJH>
+__global__ void __launch_bounds__(4 * kPolTR)
+rollout_persistent_kernel(const NetDev na, const NetDev nc, const RolloutArgs a) {
+  constexpr int TR = kPolTR;
+  constexpr int LD = Tile<TR>::LD;
+  constexpr int NT = Tile<TR>::NT;
+  extern __shared__ __align__(16) float smem[];
+  __shared__ uint64_t wbar;
+  const int tid = threadIdx.x;
+  const int which = blockIdx.y;
+  const NetDev& n = which == 0 ? na : nc;
+  PolCtx c = pol_setup<NJH>(n, smem, a.params[which], a.image[which], a.E, &wbar, tid);
+  const int H = n.hid, E = a.E, T = a.T;
+  const int Atot = na.head_total;
+  if (n.recurrent) {                                    // carried state lives behind the regular tiles
+    c.hcarry = smem + c.u.total;
+    const float* h0 = which == 0 ? a.h_actor : a.h_critic;
+    for (int i = tid; i < TR * H; i += NT) {
+      const int r = i / H, cc = i - r * H, g = c.rowid[r];
+      c.hcarry[cc * LD + r] = g >= 0 ? h0[(size_t)g * H + cc] : 0.f;
+    }
+  }
+  const uint64_t rng0 = (!a.exp_noise && which == 0) ? *a.rng_offset : 0ull;
+  const int in_dim = n.in_dim;
+  float* store_in = which == 0 ? a.obs : a.share_obs;
+  const float* feed_in = which == 0 ? a.f_obs : a.f_share;
+  float* h_store = which == 0 ? a.h_actor : a.h_critic;
+  __syncthreads();
+#pragma unroll 1
+  for (int t = 0; t <= T; ++t) {
+    PolStep p;
+    p.in = t == 0 ? store_in : feed_in + (size_t)(t - 1) * E * in_dim;
+    p.in_copy = t == 0 ? nullptr : store_in + (size_t)t * E * in_dim;
+    p.h_in = nullptr;                                   // carried in shared memory
+    p.masks = a.masks;                                  // t == 0: slot 0
+    p.done_prev = t == 0 ? nullptr : a.f_done + (size_t)(t - 1) * E;
+    p.masks_copy = t == 0 ? nullptr : a.masks + (size_t)t * E;
+    p.h_out = (n.recurrent && t < T) ? h_store + (size_t)(t + 1) * E * H : nullptr;
+    p.done_now = t < T ? a.f_done + (size_t)t * E : nullptr;
+    p.avail = a.avail ? (t == 0 ? a.avail : a.f_avail + (size_t)(t - 1) * E * a.n_avail) : nullptr;
+    p.avail_copy = (a.avail && t > 0) ? a.avail + (size_t)t * E * a.n_avail : nullptr;
+    p.exp_noise = (a.exp_noise && t < T) ? a.exp_noise + (size_t)t * E * Atot : nullptr;
+    p.rng_ctr = rng0 + (uint64_t)t * (uint64_t)E;
+    p.values = a.value_preds + (size_t)t * E;
+    p.actions = t < T ? a.actions + (size_t)t * E * na.n_heads : nullptr;
+    p.actions_i64 = nullptr;
+    p.logp = t < T ? a.logp + (size_t)t * E * na.n_heads : nullptr;
+    p.forward = (t < T) || which == 1;                  // slot T: only the critic's bootstrap value
+    // rewards / active masks of env step t-1 -> slot t-1 / t (the rest of insert), done by the actor CTAs
+    if (which == 0 && t > 0 && tid < TR && c.rowid[tid] >= 0) {
+      const int g = c.rowid[tid];
+      a.rewards[(size_t)(t - 1) * E + g] = a.f_rew[(size_t)(t - 1) * E + g];
+      if (a.f_active) a.active[(size_t)t * E + g] = a.f_active[(size_t)(t - 1) * E + g];
+    }
+    pol_step<NJH>(n, which, c, p, E, blockIdx.x * TR, 0, a.rng_seed, a.n_avail, tid);
   }
 }
 
@@ -262,6 +414,29 @@ int policy_step_launch(const NetDev* na, const NetDev* nc, const PolArgs& a, cud
   const dim3 grid((a.n_rows + kPolTR - 1) / kPolTR, (na && nc) ? 2 : 1);
   kern<<<grid, 4 * kPolTR, bytes, st>>>(na ? *na : ref, nc ? *nc : ref, a, na ? 0 : 1);
   return check_launch("policy_step_kernel");
+}
+
+int rollout_persistent_launch(const NetDev& na, const NetDev& nc, const RolloutArgs& a, cudaStream_t st) {
+  size_t bytes = 0;
+  for (const NetDev* n : {&na, &nc}) {
+    if (n->hid != 64) { set_error("rollout: hidden_size %d not built in the fused SIMT path (64 only)", n->hid); return MAPPO_ERR_UNSUPPORTED; }
+    if (n->head_total > 32) { set_error("rollout: sum(head_dim) > 32"); return MAPPO_ERR_UNSUPPORTED; }
+    const SmemW s = make_smem_w(*n, true);
+    size_t b = (size_t)make_pol_smem(*n, s).total * sizeof(float);
+    if (n->recurrent) b += (size_t)n->hid * Tile<kPolTR>::LD * sizeof(float);
+    bytes = b > bytes ? b : bytes;
+  }
+  if (bytes > 227 * 1024) { set_error("rollout: %zu B shared memory per CTA > 227 KB", bytes); return MAPPO_ERR_UNSUPPORTED; }
+  auto kern = rollout_persistent_kernel<4>;
+  static thread_local size_t configured = 0;
+  if (bytes > configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+      return check_launch("rollout: cudaFuncSetAttribute");
+    configured = bytes;
+  }
+  const dim3 grid((a.E + kPolTR - 1) / kPolTR, 2);
+  kern<<<grid, 4 * kPolTR, bytes, st>>>(na, nc, a);
+  return check_launch("rollout_persistent_kernel");
 }
 
 int pack_rollout_launch(const NetDev& n, const float* params, float* image, cudaStream_t st) {

@@ -119,6 +119,33 @@ minibatch_stats_kernel(const float* __restrict__ returns, const float* __restric
   block_accumulate<4>(v, stats, sred, threadIdx.x, blockDim.x);
 }
 
+// All minibatches of a train() call at once: blockIdx.y = update index u, rows of update u start at rows + u*stride.
+__global__ void __launch_bounds__(256)
+minibatch_stats_batch_kernel(const float* __restrict__ returns, const float* __restrict__ active,
+                             const int32_t* __restrict__ rows, long long stride, int n, double* __restrict__ stats) {
+  __shared__ double sred[4 * 32];
+  const int32_t* r = rows + (size_t)blockIdx.y * stride;
+  double v[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+    const int g = r[p];
+    const float x = returns[g];
+    v[0] += active[g];
+    v[1] += x;
+    v[2] += (double)x * x;
+    v[3] += 1.0;
+  }
+  block_accumulate<4>(v, stats + 4 * blockIdx.y, sred, threadIdx.x, blockDim.x);
+}
+
+int minibatch_stats_batch_launch(const float* returns, const float* active, const int32_t* rows, long long stride, int n,
+                                 int n_batches, double* stats, cudaStream_t st) {
+  int bx = (n + 255) / 256;
+  if (bx > 32) bx = 32;
+  if (bx < 1) bx = 1;
+  minibatch_stats_batch_kernel<<<dim3(bx, n_batches), 256, 0, st>>>(returns, active, rows, stride, n, stats);
+  return check_launch("minibatch_stats_batch_kernel");
+}
+
 int minibatch_stats_launch(const float* returns, const float* active, const int32_t* rows, int n, double* stats,
                            cudaStream_t st) {
   int blocks = (n + 255) / 256;
@@ -194,9 +221,12 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x, uint32_t k) {
   x ^= k; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
   return x;
 }
+// blockIdx.y = which permutation of a batch (independent keys), out + y*n
 __global__ void randperm_kernel(int n, uint64_t seed, const uint64_t* __restrict__ counter, int32_t* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  seed += 0x9E3779B97F4A7C15ull * (uint64_t)(blockIdx.y + 1) * (uint64_t)(gridDim.y > 1);
+  out += (size_t)blockIdx.y * n;
   int bits = 2;
   while ((1u << bits) < (uint32_t)n) bits += 2;
   const int hb = bits / 2;
@@ -217,9 +247,9 @@ __global__ void randperm_kernel(int n, uint64_t seed, const uint64_t* __restrict
   out[i] = (int32_t)x;
 }
 
-int randperm_launch(int n, uint64_t seed, const uint64_t* counter, int32_t* out, cudaStream_t st) {
-  if (n <= 0) return MAPPO_OK;
-  randperm_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, seed, counter, out);
+int randperm_launch(int n, uint64_t seed, const uint64_t* counter, int32_t* out, cudaStream_t st, int n_perms) {
+  if (n <= 0 || n_perms <= 0) return MAPPO_OK;
+  randperm_kernel<<<dim3((n + 255) / 256, n_perms), 256, 0, st>>>(n, seed, counter, out);
   return check_launch("randperm_kernel");
 }
 

@@ -285,7 +285,8 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const NetDev n, const floa
 // the kernel
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kS65 = 65, kS73 = 73;       // padded row strides of the transposed tiles (odd -> conflict-free scatter)
-struct TcSmem { int img, p, x1t, x2t, ta, lg, dbh, misc, total; };   // float offsets
+constexpr int kTCThreads = 2 * kTM;       // two threads per row: warpgroup g owns hidden columns [32 g, 32 g + 32)
+struct TcSmem { int img, p, x1t, x2t, ta, lg, dbh, xch, misc, total; };   // float offsets
 __host__ __device__ inline TcSmem make_tc_smem(const TcImage& m) {
   TcSmem s;
   int o = 0;
@@ -296,6 +297,7 @@ __host__ __device__ inline TcSmem make_tc_smem(const TcImage& m) {
   s.ta = o; o += 32 * kS65 * 4;            // dL^T / dZ2^T / dZ1^T
   s.lg = o; o += m.NH * (kTM + 4);         // logits scratch for row_loss, transposed [j][132]
   s.dbh = o; o += 32;
+  s.xch = o; o += 2 * 2 * 2 * kTM;         // row-pair exchange: [slot 2][warpgroup 2][128] float2
   s.misc = o; o += 16;                     // mbarriers (2 x 8 B) + tmem base
   s.total = o;
   return s;
@@ -308,53 +310,70 @@ __host__ __device__ inline TcSmem make_tc_smem(const TcImage& m) {
 __device__ long long g_tc_timing[16];
 #define TC_STAMP(i) do { if (blockIdx.x == 0 && tid == 0) g_tc_timing[i] = clock64(); } while (0)
 
-// row-wise LayerNorm statistics of 64 register values (two-pass like torch)
-__device__ __forceinline__ void ln_stats64(const float* a, float& mean, float& rstd) {
+// The two threads of a row live in warps w and w + 4 (same TMEM lane window).  They meet on named barrier 1 + (w & 3)
+// (64 threads) and swap two partial sums through shared memory; both get bit-identical totals (a + b == b + a).
+// Two slots alternate so that a fast pair cannot overwrite values its partner has not read yet.
+struct PairXch {
+  float2* buf;       // [slot][warpgroup][128]
+  int wg, r, bar;
+  int slot;
+  __device__ __forceinline__ float2 sum(float a, float b) {
+    buf[(slot * 2 + wg) * kTM + r] = make_float2(a, b);
+    asm volatile("bar.sync %0, 64;" ::"r"(bar) : "memory");
+    const float2 o = buf[(slot * 2 + (wg ^ 1)) * kTM + r];
+    slot ^= 1;
+    return make_float2(a + o.x, b + o.y);
+  }
+};
+
+// LayerNorm statistics of a 64-wide row held as 2 x 32 register values (two-pass like torch)
+__device__ __forceinline__ void ln_stats_pair(const float* a, PairXch& px, float& mean, float& rstd) {
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < 64; ++i) s += a[i];
-  mean = s * (1.f / 64.f);
+  for (int i = 0; i < 32; ++i) s += a[i];
+  mean = px.sum(s, 0.f).x * (1.f / 64.f);
   float v = 0.f;
 #pragma unroll
-  for (int i = 0; i < 64; ++i) { const float d = a[i] - mean; v = fmaf(d, d, v); }
-  rstd = 1.0f / sqrtf(v * (1.f / 64.f) + kLnEps);
+  for (int i = 0; i < 32; ++i) { const float d = a[i] - mean; v = fmaf(d, d, v); }
+  rstd = 1.0f / sqrtf(px.sum(v, 0.f).x * (1.f / 64.f) + kLnEps);
 }
 
-// thread `tid` = row r: write 64 values as row r of a K-major staging tile [16 (+2 aug)][128][4] ...
-__device__ __forceinline__ void put_kmajor64(float* P, int tid, const float* v, bool aug) {
+// thread (row r, warpgroup g): write its 32 values as chunks [8 g, 8 g + 8) of row r of a K-major staging tile
+// [16 (+2 aug)][128][4] ...
+__device__ __forceinline__ void put_kmajor32(float* P, int r, int wg, const float* v, bool aug) {
 #pragma unroll
-  for (int kc = 0; kc < 16; ++kc)
-    reinterpret_cast<float4*>(P)[kc * kTM + tid] = make_float4(v[4 * kc], v[4 * kc + 1], v[4 * kc + 2], v[4 * kc + 3]);
-  if (aug) {
-    reinterpret_cast<float4*>(P)[16 * kTM + tid] = make_float4(1.f, 0.f, 0.f, 0.f);
-    reinterpret_cast<float4*>(P)[17 * kTM + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+  for (int kc = 0; kc < 8; ++kc)
+    reinterpret_cast<float4*>(P)[(wg * 8 + kc) * kTM + r] = make_float4(v[4 * kc], v[4 * kc + 1], v[4 * kc + 2], v[4 * kc + 3]);
+  if (aug) reinterpret_cast<float4*>(P)[(16 + wg) * kTM + r] = make_float4(wg == 0 ? 1.f : 0.f, 0.f, 0.f, 0.f);
 }
-// ... and as column r of a transposed tile [32][S][4] (element (feature f, row r) at ((r/4)*S + f)*4 + r%4)
-__device__ __forceinline__ void put_transposed64(float* T, int S, int tid, const float* v) {
-  float* base = T + (tid >> 2) * S * 4 + (tid & 3);
+// ... and as features [32 g, 32 g + 32) of column r of a transposed tile [32][S][4] (element (feature f, row r) at
+// ((r/4)*S + f)*4 + r%4)
+__device__ __forceinline__ void put_transposed32(float* T, int S, int r, int wg, const float* v) {
+  float* base = T + ((r >> 2) * S + wg * 32) * 4 + (r & 3);
 #pragma unroll
-  for (int f = 0; f < 64; ++f) base[f * 4] = v[f];
+  for (int f = 0; f < 32; ++f) base[f * 4] = v[f];
 }
 
-// LayerNorm + activation backward for one row: d = dL/dxhat (64 regs) -> dZ in place.  xhat is re-read from the
-// transposed tile (conflict-free 4-byte loads).
-__device__ __forceinline__ void ln_act_bwd64(float* d, const float* XT, int S, int tid, float mu, float rs, int act) {
-  const float* base = XT + (tid >> 2) * S * 4 + (tid & 3);
+// LayerNorm + activation backward for one row: d = dL/dxhat (this thread's 32 columns) -> dZ in place.  xhat is re-read
+// from the transposed tile (conflict-free 4-byte loads).
+__device__ __forceinline__ void ln_act_bwd32(float* d, const float* XT, int S, int r, int wg, PairXch& px, float mu, float rs,
+                                             int act) {
+  const float* base = XT + ((r >> 2) * S + wg * 32) * 4 + (r & 3);
+  float xh[32];
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int f = 0; f < 64; ++f) { s1 += d[f]; s2 = fmaf(d[f], base[f * 4], s2); }
-  s1 *= (1.f / 64.f); s2 *= (1.f / 64.f);
+  for (int f = 0; f < 32; ++f) { xh[f] = base[f * 4]; s1 += d[f]; s2 = fmaf(d[f], xh[f], s2); }
+  const float2 t = px.sum(s1, s2);
+  s1 = t.x * (1.f / 64.f); s2 = t.y * (1.f / 64.f);
   const float inv = 1.0f / rs;
 #pragma unroll
-  for (int f = 0; f < 64; ++f) {
-    const float xh = base[f * 4];
-    const float dA = rs * (d[f] - s1 - xh * s2);
-    d[f] = to_tf32(dA * act_bwd(fmaf(xh, inv, mu), act));
+  for (int f = 0; f < 32; ++f) {
+    const float dA = rs * (d[f] - s1 - xh[f] * s2);
+    d[f] = to_tf32(dA * act_bwd(fmaf(xh[f], inv, mu), act));
   }
 }
 
-__global__ void __launch_bounds__(kTM, 1)
+__global__ void __launch_bounds__(kTCThreads, 1)
 update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const float* __restrict__ image, const BatchDev b,
                      const LossDev L, const double* __restrict__ norm_stats, const double* __restrict__ adv_stats,
                      const float* __restrict__ vn_state, float* __restrict__ grad_part, double* __restrict__ loss_out,
@@ -362,6 +381,7 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
   extern __shared__ __align__(1024) float smem[];
   __shared__ double sred[2 * 32];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r = tid & (kTM - 1), wg = tid >> 7;              // my row of the tile, my half of the hidden columns
   const TcImage im = make_tc_image(n);
   const TcSmem sm = make_tc_smem(im);
   float* sImg = smem + sm.img;
@@ -374,6 +394,7 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
   uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + sm.misc);
   uint64_t* bar_m = bar_w + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 2);
+  PairXch px{reinterpret_cast<float2*>(smem + sm.xch), wg, r, 1 + (warp & 3), 0};
   const int in = n.in_dim, inF = im.inF, NH = im.NH, Atot = n.head_total;
   const int S0 = inF + 1, SH = NH + 1;
   const int act = n.use_relu ? ACT_RELU : ACT_TANH;
@@ -387,9 +408,9 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
-  for (int i = tid; i < 32; i += kTM) dbh[i] = 0.f;
-  {
-    float* base = X1T + (tid >> 2) * kS73 * 4 + (tid & 3);          // constant-1 feature (row 64) and zero rows 65..71
+  for (int i = tid; i < 32; i += kTCThreads) dbh[i] = 0.f;
+  if (wg == 0) {
+    float* base = X1T + (r >> 2) * kS73 * 4 + (r & 3);              // constant-1 feature (row 64) and zero rows 65..71
 #pragma unroll
     for (int f = 64; f < 72; ++f) base[f * 4] = (f == kOne) ? 1.f : 0.f;
   }
@@ -403,7 +424,8 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
   }
   // TMEM columns: D fwd/bwd accumulator, Dh logits, G2 / G1 / Gh persistent weight-gradient accumulators
   const uint32_t cD = 0, cDh = 64, cG2 = 96, cG1 = 168, cGh = 240, cX0 = 272;     // cX0: parked xhat0aug (72 cols)
-  const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+  const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
+  const uint32_t cMy = cD + 32 * wg;                   // my 32 columns of the 64-wide accumulator
 
   const LossConsts lc = make_loss_consts(n, L, norm_stats, adv_stats, vn_state);
   double acc[3] = {0.0, 0.0, 0.0};
@@ -416,11 +438,11 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
 
   TC_STAMP(1);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int p = tile * kTM + tid;
+    const int p = tile * kTM + r;
     const int gr = p < b.n_rows ? (b.rows ? b.rows[p] : p) : -1;
-    const float* src = (n.is_critic ? b.share_obs : b.obs) + (size_t)(gr < 0 ? 0 : gr) * in;
     float mu0 = 0.f, rs0 = 1.f;
-    const RowIn rin = load_row_in(n, b, gr);      // loss inputs: in flight during the whole forward pass
+    const RowIn rin = load_row_in(n, b, wg == 0 ? gr : -1);      // loss inputs (warpgroup 0 owns the loss): in flight
+                                                                 // during the whole forward pass
 
     // ---- S1: coalesced cooperative gather (a warp reads whole rows) -> shared staging -> my row in registers,
     //      feature LayerNorm, stage xhat0 (K-major in TA, + constant-1 feature), park it in TMEM ----
@@ -428,32 +450,31 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
       int* rowid_s = reinterpret_cast<int*>(lgT);                 // lgT is free until S7
       float* Rs = P;                                              // raw rows [128][RS], RS odd -> conflict-free row reads
       const int RS = in | 1;
-      rowid_s[tid] = gr;
+      if (wg == 0) rowid_s[r] = gr;
       __syncthreads();
       const float* base = n.is_critic ? b.share_obs : b.obs;
-      // two batches of 16 rows x 2 loads: 32 independent coalesced loads in flight per thread, then the stores
-#pragma unroll 1
-      for (int hb = 0; hb < 2; ++hb) {
+      // each of the 8 warps gathers 16 rows: 32 independent coalesced loads in flight per thread, then the stores
+      {
         float v0[16], v1[16];
 #pragma unroll
         for (int rr = 0; rr < 16; ++rr) {
-          const int g0 = rowid_s[warp * 32 + hb * 16 + rr];
+          const int g0 = rowid_s[warp * 16 + rr];
           const float* rp = base + (size_t)(g0 < 0 ? 0 : g0) * in;
           v0[rr] = (lane < in && g0 >= 0) ? __ldg(rp + lane) : 0.f;
           v1[rr] = (lane + 32 < in && g0 >= 0) ? __ldg(rp + lane + 32) : 0.f;
         }
 #pragma unroll
         for (int rr = 0; rr < 16; ++rr) {
-          const int r = warp * 32 + hb * 16 + rr;
-          if (lane < in) Rs[r * RS + lane] = v0[rr];
-          if (lane + 32 < in) Rs[r * RS + lane + 32] = v1[rr];
+          const int q = warp * 16 + rr;
+          if (lane < in) Rs[q * RS + lane] = v0[rr];
+          if (lane + 32 < in) Rs[q * RS + lane + 32] = v1[rr];
         }
       }
       __syncthreads();
       float x[64];
 #pragma unroll
-      for (int k = 0; k < 64; ++k) x[k] = k < in ? Rs[tid * RS + k] : 0.f;
-      if (n.use_fn && gr >= 0) {
+      for (int k = 0; k < 64; ++k) x[k] = k < in ? Rs[r * RS + k] : 0.f;
+      if (n.use_fn && gr >= 0) {                                  // both threads of the row: same statistics
         float s = 0.f;
 #pragma unroll
         for (int k = 0; k < 64; ++k) s += x[k];                 // padding is zero
@@ -465,15 +486,15 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
       }
 #pragma unroll
       for (int c8 = 0; c8 < 9; ++c8) {
-        if (c8 * 8 < inF) {
+        if (c8 * 8 < inF && (c8 & 1) == wg) {                     // 8-feature chunks alternate between the two threads
           float q[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int k = c8 * 8 + j;
             q[j] = (k == in) ? 1.f : ((k < in) ? to_tf32((x[k & 63] - mu0) * rs0) : 0.f);
           }
-          reinterpret_cast<float4*>(TA)[(2 * c8) * kTM + tid] = make_float4(q[0], q[1], q[2], q[3]);
-          reinterpret_cast<float4*>(TA)[(2 * c8 + 1) * kTM + tid] = make_float4(q[4], q[5], q[6], q[7]);
+          reinterpret_cast<float4*>(TA)[(2 * c8) * kTM + r] = make_float4(q[0], q[1], q[2], q[3]);
+          reinterpret_cast<float4*>(TA)[(2 * c8 + 1) * kTM + r] = make_float4(q[4], q[5], q[6], q[7]);
           tmem_st8(tmem + lane_base + cX0 + c8 * 8, q);        // parked for the fc1 weight gradient (S11)
         }
       }
@@ -494,19 +515,19 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
     // ---- S3: fc1 epilogue: activation, LayerNorm -> xhat1 (K-major staging + transposed copy) ----
     float mu1, rs1, mu2, rs2;
     {
-      float a[64];
+      float a[32];
       mbar_wait(bar_m, phase); phase ^= 1; TC_STAMP(3);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld16(tmem + lane_base + cD + c * 16, a + c * 16);
+      tmem_ld16(tmem + lane_base + cMy, a);
+      tmem_ld16(tmem + lane_base + cMy + 16, a + 16);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 64; ++i) a[i] = act_fwd_tc(a[i], act);
-      ln_stats64(a, mu1, rs1);
+      for (int i = 0; i < 32; ++i) a[i] = act_fwd_tc(a[i], act);
+      ln_stats_pair(a, px, mu1, rs1);
 #pragma unroll
-      for (int i = 0; i < 64; ++i) a[i] = to_tf32((a[i] - mu1) * rs1);
-      put_kmajor64(P, tid, a, true);
-      put_transposed64(X1T, kS73, tid, a);
+      for (int i = 0; i < 32; ++i) a[i] = to_tf32((a[i] - mu1) * rs1);
+      put_kmajor32(P, r, wg, a, true);
+      put_transposed32(X1T, kS73, r, wg, a);
     }
     TC_STAMP(4);
     fence_async_smem();
@@ -521,19 +542,19 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
     }
     // ---- S5: fc2 epilogue ----
     {
-      float a[64];
+      float a[32];
       mbar_wait(bar_m, phase); phase ^= 1; TC_STAMP(5);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld16(tmem + lane_base + cD + c * 16, a + c * 16);
+      tmem_ld16(tmem + lane_base + cMy, a);
+      tmem_ld16(tmem + lane_base + cMy + 16, a + 16);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 64; ++i) a[i] = act_fwd_tc(a[i], act);
-      ln_stats64(a, mu2, rs2);
+      for (int i = 0; i < 32; ++i) a[i] = act_fwd_tc(a[i], act);
+      ln_stats_pair(a, px, mu2, rs2);
 #pragma unroll
-      for (int i = 0; i < 64; ++i) a[i] = to_tf32((a[i] - mu2) * rs2);
-      put_kmajor64(P, tid, a, true);
-      put_transposed64(X2T, kS65, tid, a);
+      for (int i = 0; i < 32; ++i) a[i] = to_tf32((a[i] - mu2) * rs2);
+      put_kmajor32(P, r, wg, a, true);
+      put_transposed32(X2T, kS65, r, wg, a);
     }
     TC_STAMP(6);
     fence_async_smem();
@@ -547,25 +568,25 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
                   s > 0);
       umma_commit(bar_m);
     }
-    // ---- S7: heads, loss, d(loss)/d(logits) ----
-    {
+    // ---- S7: heads, loss, d(loss)/d(logits): one thread per row (warpgroup 0) ----
+    mbar_wait(bar_m, phase); phase ^= 1; TC_STAMP(7);
+    tc_fence_after();
+    if (wg == 0) {
       float lg[32];
-      mbar_wait(bar_m, phase); phase ^= 1; TC_STAMP(7);
-      tc_fence_after();
       tmem_ld16(tmem + lane_base + cDh, lg);
       if (NH > 16) tmem_ld16(tmem + lane_base + cDh + 16, lg + 16);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) if (j < Atot) lgT[j * LGLD + tid] = lg[j];
-      row_loss_pre<LGLD>(n, b, L, lc, lgT, tid, gr, p, rin, acc);  // thread-local: only column `tid` is touched
+      for (int j = 0; j < 32; ++j) if (j < Atot) lgT[j * LGLD + r] = lg[j];
+      row_loss_pre<LGLD>(n, b, L, lc, lgT, r, gr, p, rin, acc);    // thread-local: only column r is touched
       if (!b.eval_only) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) lg[j] = j < Atot ? to_tf32(lgT[j * LGLD + tid]) : 0.f;
+        for (int j = 0; j < 32; ++j) lg[j] = j < Atot ? to_tf32(lgT[j * LGLD + r]) : 0.f;
 #pragma unroll
         for (int kc = 0; kc < 8; ++kc)
           if (kc * 4 < NH)
-            reinterpret_cast<float4*>(P)[kc * kTM + tid] = make_float4(lg[4 * kc], lg[4 * kc + 1], lg[4 * kc + 2], lg[4 * kc + 3]);
-        float* tb = TA + (tid >> 2) * SH * 4 + (tid & 3);         // dL^T: [32][NH + 1][4]
+            reinterpret_cast<float4*>(P)[kc * kTM + r] = make_float4(lg[4 * kc], lg[4 * kc + 1], lg[4 * kc + 2], lg[4 * kc + 3]);
+        float* tb = TA + (r >> 2) * SH * 4 + (r & 3);             // dL^T: [32][NH + 1][4]
 #pragma unroll
         for (int j = 0; j < 32; ++j) if (j < NH) tb[j * 4] = lg[j];
         // head bias gradient: sum over the rows of this warp, one shared atomic per warp and output
@@ -597,15 +618,15 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
     }
     // ---- S9: LayerNorm-2 + activation backward -> dZ2 (K-major staging + transposed) ----
     {
-      float d[64];
+      float d[32];
       mbar_wait(bar_m, phase); phase ^= 1; TC_STAMP(9);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld16(tmem + lane_base + cD + c * 16, d + c * 16);
+      tmem_ld16(tmem + lane_base + cMy, d);
+      tmem_ld16(tmem + lane_base + cMy + 16, d + 16);
       tmem_ld_wait();
-      ln_act_bwd64(d, X2T, kS65, tid, mu2, rs2, act);
-      put_kmajor64(P, tid, d, false);
-      put_transposed64(TA, kS65, tid, d);
+      ln_act_bwd32(d, X2T, kS65, r, wg, px, mu2, rs2, act);
+      put_kmajor32(P, r, wg, d, false);
+      put_transposed32(TA, kS65, r, wg, d);
     }
     TC_STAMP(10);
     fence_async_smem();
@@ -626,18 +647,18 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
     }
     // ---- S11: LayerNorm-1 + activation backward -> dZ1^T; xhat0^T re-staged from its TMEM parking columns ----
     {
-      float d[64];
+      float d[32];
       mbar_wait(bar_m, phase); phase ^= 1; TC_STAMP(11);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld16(tmem + lane_base + cD + c * 16, d + c * 16);
+      tmem_ld16(tmem + lane_base + cMy, d);
+      tmem_ld16(tmem + lane_base + cMy + 16, d + 16);
       tmem_ld_wait();
-      ln_act_bwd64(d, X1T, kS73, tid, mu1, rs1, act);
-      put_transposed64(TA, kS65, tid, d);
-      float* pb = P + (tid >> 2) * S0 * 4 + (tid & 3);            // xhat0aug^T: [32][inF + 1][4]
+      ln_act_bwd32(d, X1T, kS73, r, wg, px, mu1, rs1, act);
+      put_transposed32(TA, kS65, r, wg, d);
+      float* pb = P + (r >> 2) * S0 * 4 + (r & 3);                // xhat0aug^T: [32][inF + 1][4]
 #pragma unroll
       for (int c8 = 0; c8 < 9; ++c8) {
-        if (c8 * 8 < inF) {
+        if (c8 * 8 < inF && (c8 & 1) == wg) {
           float q[8];
           tmem_ld8(tmem + lane_base + cX0 + c8 * 8, q);
           tmem_ld_wait();
@@ -664,15 +685,15 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
     first_tile = false;
   }
   // ---- dump the raw (still folded) accumulators into this CTA's slot; they are summed over slots and unfolded once
-  //      by mappo_update_finish (tc_unfold_kernel) ----
+  //      by mappo_update_finish (tc_unfold_kernel).  Warpgroup 0 dumps G2, warpgroup 1 dumps G1 and Gh. ----
   if (!b.eval_only) {
     const TcRaw R = make_tc_raw(im);
     float* g = grad_part + (size_t)blockIdx.x * R.total;
     const bool has_tile = !first_tile;
-    const int o = warp * 16 + lane;                       // accumulator row of this thread in the M = 64 layout
+    const int o = (warp & 3) * 16 + lane;                 // accumulator row of this thread in the M = 64 layout
     const bool own = lane < 16;
-    {
-      float v[72];
+    float v[72];
+    if (wg == 0) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld16(tmem + lane_base + cG2 + c * 16, v + c * 16);
       tmem_ld8(tmem + lane_base + cG2 + 64, v + 64);
@@ -683,6 +704,7 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
           reinterpret_cast<float4*>(g + R.g2 + o * kHF)[q] =
               has_tile ? make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+    } else {
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld16(tmem + lane_base + cG1 + c * 16, v + c * 16);
       tmem_ld8(tmem + lane_base + cG1 + 64, v + 64);
@@ -714,12 +736,12 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
   __syncthreads();
   if (n.is_critic) {
     double one[1] = {acc[0]};
-    block_accumulate<1>(one, loss_out + 0, sred, tid, kTM);
+    block_accumulate<1>(one, loss_out + 0, sred, tid, kTCThreads);
   } else {
     double two[2] = {acc[0], acc[1]};
-    block_accumulate<2>(two, loss_out + 1, sred, tid, kTM);
+    block_accumulate<2>(two, loss_out + 1, sred, tid, kTCThreads);
     double rt[1] = {acc[2] / (lc.n_rows_d * (double)b.act_shape)};
-    block_accumulate<1>(rt, loss_out + 5, sred, tid, kTM);
+    block_accumulate<1>(rt, loss_out + 5, sred, tid, kTCThreads);
   }
   if (warp == 0) tmem_dealloc(tmem, tmem_cols);
   TC_STAMP(15);
@@ -773,7 +795,7 @@ int update_mlp_tc_launch(const NetDev& n, const float* params, const BatchDev& b
   }
   const int n_tiles = (b.n_rows + kTM - 1) / kTM;
   const uint32_t cols = 512u;          // accumulators [0,272) + parked xhat0 [272,344): one CTA per SM owns all of TMEM
-  update_mlp_tc_kernel<<<n_slots, kTM, bytes, st>>>(n, params, image, b, L, norm_stats, adv_stats, vn_state, grad_part,
+  update_mlp_tc_kernel<<<n_slots, kTCThreads, bytes, st>>>(n, params, image, b, L, norm_stats, adv_stats, vn_state, grad_part,
                                                     loss_out, n_tiles, cols);
   return check_launch("update_mlp_tc_kernel");
 }

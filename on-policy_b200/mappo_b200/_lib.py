@@ -53,6 +53,8 @@ _SIGS = {
     "mappo_net_layout": (_i32, [C.POINTER(NetDesc), C.POINTER(NetLayout)]),
     "mappo_policy_step": (_i32, [C.POINTER(NetDesc), _P, C.POINTER(NetDesc), _P] + [_P] * 7 +
                           [_u64, _P, _i32, _i32] + [_P] * 6 + [_P, _P] + [_P]),
+    "mappo_rollout_persistent": (_i32, [C.POINTER(NetDesc), _P, _P, C.POINTER(NetDesc), _P, _P] + [_P] * 11 + [_P] * 6 +
+                                 [_P, _u64, _P, _i32, _i32, _P]),
     "mappo_rollout_image_floats": (_i32, [C.POINTER(NetDesc)]),
     "mappo_pack_rollout_weights": (_i32, [C.POINTER(NetDesc), _P, _P, _P]),
     "mappo_counter_add": (_i32, [_P, _u64, _P]),
@@ -63,6 +65,9 @@ _SIGS = {
     "mappo_advantages": (_i32, [_P, _P, _P, _P, _i32, _P, _P, _P]),
     "mappo_evaluate_actions": (_i32, [C.POINTER(NetDesc), _P, C.POINTER(Batch), C.POINTER(LossCfg), _P, _P, _P, _P, _P]),
     "mappo_minibatch_stats": (_i32, [_P, _P, _P, _i32, _P, _P]),
+    "mappo_debug_launch_count": (_i64, []),
+    "mappo_minibatch_stats_batch": (_i32, [_P, _P, _P, _i64, _i32, _i32, _P, _P]),
+    "mappo_randperm_batch": (_i32, [_i32, _i32, _u64, _P, _P, _P]),
     "mappo_valuenorm_update": (_i32, [_P, _P, _P]),
     "mappo_gather_rows": (_i32, [_P, _P, _i32, _i32, _P, _P]),
     "mappo_chunk_rows": (_i32, [_P, _i32, _i32, _i32, _i32, _P, _P, _P]),

@@ -90,6 +90,9 @@ class RolloutEngine:
                                      dtype=torch.float32, device=self.dev)
         self.img_critic = torch.zeros(int(self.lib.mappo_rollout_image_floats(C.byref(policy.critic.desc))),
                                       dtype=torch.float32, device=self.dev)
+        # one persistent launch for the whole collect phase (env outputs are staged on the device anyway)
+        import os
+        self.persistent_rollout = os.environ.get("MAPPO_B200_PERSISTENT_ROLLOUT", "1") == "1"
         self.host = {}
         self.graph = None
         self._allreduce = "auto"        # "auto": torch.distributed when a multi-rank group exists
@@ -175,7 +178,33 @@ class RolloutEngine:
             ptr(b.active_masks[t + 1]) if self.d_active is not None else None,
             ptr(b.available_actions[t + 1]) if self.d_avail is not None else None,
             ptr(pol.rng_offset) if noise is None else None, self.E, st))
-        self.launches_per_iteration += 2
+
+    def _rollout_persistent(self):
+        """All T collect steps + inserts + the bootstrap value as ONE launch (mappo_rollout_persistent)."""
+        b, pol, lib = self.buffer, self.policy, self.lib
+        rec = self.recurrent
+        check(lib.mappo_rollout_persistent(
+            C.byref(pol.actor.desc), ptr(pol.actor.flat), ptr(self.img_actor),
+            C.byref(pol.critic.desc), ptr(pol.critic.flat), ptr(self.img_critic),
+            ptr(b.obs), ptr(b.share_obs), ptr(b.rnn_states) if rec else None, ptr(b.rnn_states_critic) if rec else None,
+            ptr(b.masks), ptr(b.available_actions) if self.d_avail is not None else None,
+            ptr(b.value_preds), ptr(b.actions), ptr(b.action_log_probs), ptr(b.rewards),
+            ptr(b.active_masks) if self.d_active is not None else None,
+            ptr(self.d_obs), ptr(self.d_share), ptr(self.d_rew), ptr(self.d_done),
+            ptr(self.d_active) if self.d_active is not None else None,
+            ptr(self.d_avail) if self.d_avail is not None else None,
+            ptr(self.d_noise), self.seed, ptr(pol.rng_offset), self.T, self.E, stream_ptr()))
+
+    def _returns(self):
+        b, lib, st, T = self.buffer, self.lib, stream_ptr(), self.T
+        vn = self.trainer.value_normalizer
+        b._adv_stats.zero_()
+        check(lib.mappo_compute_returns(ptr(b.rewards), ptr(b.value_preds), ptr(b.masks), ptr(b.bad_masks),
+                                        ptr(b.active_masks), ptr(vn.state) if vn is not None else None, T, self.E,
+                                        float(b.gamma), float(b.gae_lambda), int(bool(b._use_gae)),
+                                        int(bool(b._use_proper_time_limits)), ptr(b.returns), ptr(b.advantages),
+                                        ptr(b._adv_stats), st))
+        b._adv_version = id(vn) if vn is not None else 0
 
     def _compute(self):
         b, pol, lib, st, T = self.buffer, self.policy, self.lib, stream_ptr(), self.T
@@ -193,7 +222,6 @@ class RolloutEngine:
                                         int(bool(b._use_proper_time_limits)), ptr(b.returns), ptr(b.advantages),
                                         ptr(b._adv_stats), st))
         b._adv_version = id(vn) if vn is not None else 0
-        self.launches_per_iteration += 3
 
     def _draw_perm(self, n):
         e = self._epoch_i
@@ -201,34 +229,38 @@ class RolloutEngine:
         out = self.d_perm[e]
         if self.rng != "host":
             # one counter bump per iteration (launch_iteration); epochs are told apart by the seed
-            seed = (self.seed + 0x9E3779B97F4A7C15 * (e + 1)) & 0xFFFFFFFFFFFFFFFF
-            check(self.lib.mappo_randperm(n, seed, ptr(self.perm_ctr), ptr(out), stream_ptr()))
-            self.launches_per_iteration += 1
+            # (mappo_randperm_batch adds the same golden-ratio multiple per permutation)
+            if self.d_perm.shape[0] > 1 and n == self.d_perm.shape[1]:
+                if e == 0:          # every epoch's permutation in one launch
+                    check(self.lib.mappo_randperm_batch(n, self.d_perm.shape[0], self.seed, ptr(self.perm_ctr),
+                                                        ptr(self.d_perm), stream_ptr()))
+            else:
+                seed = (self.seed + 0x9E3779B97F4A7C15 * (e + 1)) & 0xFFFFFFFFFFFFFFFF
+                check(self.lib.mappo_randperm(n, seed, ptr(self.perm_ctr), ptr(out), stream_ptr()))
         return out
 
     def launch_iteration(self):
         """Enqueue one full iteration on the current stream (no host synchronisation)."""
-        self.launches_per_iteration = 2
+        n0 = self.lib.mappo_debug_launch_count()
         pol = self.policy
         check(self.lib.mappo_pack_rollout_weights(C.byref(pol.actor.desc), ptr(pol.actor.flat), ptr(self.img_actor), stream_ptr()))
         check(self.lib.mappo_pack_rollout_weights(C.byref(pol.critic.desc), ptr(pol.critic.flat), ptr(self.img_critic), stream_ptr()))
-        for t in range(self.T):
-            self._collect_and_insert(t)
-        self._compute()
+        if self.persistent_rollout:
+            self._rollout_persistent()
+            self._returns()
+        else:
+            for t in range(self.T):
+                self._collect_and_insert(t)
+            self._compute()
         self._epoch_i = 0
         tr = self.trainer
         n_upd = tr.ppo_epoch * tr.num_mini_batch
         tr.launch_train(self.buffer, True, self._draw_perm, self.loss_out, allreduce=self._allreduce)
         if self.rng != "host":
             check(self.lib.mappo_counter_add(ptr(self.perm_ctr), 1, stream_ptr()))
-            self.launches_per_iteration += 1
-        # per update: stats + 2 x (fwd/bwd [+ weight pack in tf32 mode], slot reduce, clip+Adam) + ValueNorm update
-        tf32 = 1 if getattr(tr, "gemm_mode", 0) == 1 else 0
-        per_update = 1 + 2 * (3 + 2 * tf32) + (1 if tr.value_normalizer is not None else 0)     # tf32: + pack, + unfold
-        self.launches_per_iteration += n_upd * per_update
-        if self.recurrent:
-            self.launches_per_iteration += n_upd       # chunk_rows
         self.buffer.after_update()
+        # kernels of OUR library enqueued by one iteration, counted by the library itself (memsets / torch copies excluded)
+        self.launches_per_iteration = int(self.lib.mappo_debug_launch_count() - n0)
 
     def phase_breakdown(self, reps: int = 20):
         """Device time of the three phases of an iteration, each captured as its own CUDA graph and replayed `reps`
@@ -255,6 +287,11 @@ class RolloutEngine:
 
         def collect():
             pol = self.policy
+            if self.persistent_rollout:
+                check(self.lib.mappo_pack_rollout_weights(C.byref(pol.actor.desc), ptr(pol.actor.flat), ptr(self.img_actor), stream_ptr()))
+                check(self.lib.mappo_pack_rollout_weights(C.byref(pol.critic.desc), ptr(pol.critic.flat), ptr(self.img_critic), stream_ptr()))
+                self._rollout_persistent()
+                return
             check(self.lib.mappo_pack_rollout_weights(C.byref(pol.actor.desc), ptr(pol.actor.flat), ptr(self.img_actor), stream_ptr()))
             check(self.lib.mappo_pack_rollout_weights(C.byref(pol.critic.desc), ptr(pol.critic.flat), ptr(self.img_critic), stream_ptr()))
             for t in range(self.T):
@@ -264,7 +301,8 @@ class RolloutEngine:
             self._epoch_i = 0
             self.trainer.launch_train(self.buffer, True, self._draw_perm, self.loss_out, allreduce=None)
 
-        return {"collect_insert_ms": timed(collect), "values_gae_ms": timed(self._compute), "train_ms": timed(train),
+        return {"collect_insert_ms": timed(collect),
+                "values_gae_ms": timed(self._returns if self.persistent_rollout else self._compute), "train_ms": timed(train),
                 "after_update_ms": timed(self.buffer.after_update)}
 
     def capture(self, warmup: int = 2):

@@ -81,7 +81,7 @@ class R_MAPPO():
                              UpdateWorkspace(self.policy.critic, key, self.gemm_mode))
         return self._ws[key]
 
-    def _one_update(self, batch, n_rows, norm_stats, adv_stats, loss_out, update_actor, allreduce):
+    def _one_update(self, batch, n_rows, norm_stats, adv_stats, loss_out, update_actor, allreduce, only=None):
         pol = self.policy
         ws_a, ws_c = self._workspaces(n_rows)
         loss_a = make_loss_cfg(self.args, update_actor)
@@ -98,7 +98,11 @@ class R_MAPPO():
             launch_update(pol.critic, ws_c, batch, loss_c, norm_stats, None, vn, loss_out, pol.critic_optimizer,
                           self.max_grad_norm, self._use_max_grad_norm, 4, allreduce)
 
-        if self.overlap_nets and allreduce is None:
+        if only == "actor":
+            actor_chain()
+        elif only == "critic":
+            critic_chain()
+        elif self.overlap_nets and allreduce is None:      # a single ppo_update(): fork / join around this update
             if self._side is None:
                 self._side = torch.cuda.Stream(device=self.device)
             main = torch.cuda.current_stream()
@@ -247,9 +251,18 @@ class R_MAPPO():
 
         # per-update statistics (sum active, sum R, sum R^2, rows): known up front -> one collective for all of them
         stats = torch.zeros(n_updates * 4 + 4, dtype=torch.float64, device=dev)
-        for u, (rows, _, _) in enumerate(plans):
-            check(lib.mappo_minibatch_stats(ptr(buffer.returns), ptr(buffer.active_masks), ptr(rows), rows.numel(),
-                                            C.c_void_p(stats.data_ptr() + 32 * u), st))
+        addr = [pl[0].data_ptr() for pl in plans]
+        step = addr[1] - addr[0] if n_updates > 1 else 0
+        n_each = plans[0][0].numel()
+        if (n_updates > 1 and step > 0 and step % 4 == 0 and all(pl[0].numel() == n_each for pl in plans)
+                and all(addr[u] == addr[0] + u * step for u in range(n_updates))):
+            # equally spaced slices of one permutation buffer: every minibatch's statistics in ONE launch
+            check(lib.mappo_minibatch_stats_batch(ptr(buffer.returns), ptr(buffer.active_masks), ptr(plans[0][0]),
+                                                  step // 4, n_each, n_updates, ptr(stats), st))
+        else:
+            for u, (rows, _, _) in enumerate(plans):
+                check(lib.mappo_minibatch_stats(ptr(buffer.returns), ptr(buffer.active_masks), ptr(rows), rows.numel(),
+                                                C.c_void_p(stats.data_ptr() + 32 * u), st))
         if allreduce is not None:
             stats[n_updates * 4:n_updates * 4 + 3].copy_(adv_stats)
             if p2p is not None:
@@ -259,9 +272,27 @@ class R_MAPPO():
             adv_stats = stats[n_updates * 4:n_updates * 4 + 3]
 
         loss_out.zero_()
-        for u, (rows, first, seq_len) in enumerate(plans):
-            batch = self._storage_batch(buffer, adv, rows, first, seq_len)
-            self._one_update(batch, rows.numel(), stats[4 * u:4 * u + 4], adv_stats, loss_out, update_actor, allreduce)
+        batches = [self._storage_batch(buffer, adv, rows, first, seq_len) for rows, first, seq_len in plans]
+
+        def updates(only):
+            for u, (rows, _, _) in enumerate(plans):
+                self._one_update(batches[u], rows.numel(), stats[4 * u:4 * u + 4], adv_stats, loss_out, update_actor,
+                                 allreduce, only)
+
+        if self.overlap_nets and allreduce is None:
+            # actor and critic never read each other's state inside train(): their whole update sequences are two
+            # independent chains (fork once, join once).  Free-running, the two 75-CTA update kernels interleave on
+            # the 148 SMs instead of colliding in lock step (150 CTAs = two waves).
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            main = torch.cuda.current_stream()
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                updates("critic")
+            updates("actor")
+            main.wait_stream(self._side)
+        else:
+            updates(None)
         if allreduce is not None:
             # loss scalars are partial sums over local rows (global normalisers); norms are already global
             part = loss_out.clone()

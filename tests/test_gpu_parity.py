@@ -375,3 +375,48 @@ def test_engine_graph_replay_matches_eager_train():
         assert_close(info_graph[k], info_eager[k], 1e-5, 1e-7, f"graph vs eager train_info[{k}]")
     assert_close(policy2.actor.flat.cpu().numpy(), policy.actor.flat.cpu().numpy(), 1e-5, 1e-7, "actor weights")
     assert_close(policy2.critic.flat.cpu().numpy(), policy.critic.flat.cpu().numpy(), 1e-5, 1e-7, "critic weights")
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("persistent", [True, False])
+def test_engine_rollout_matches_reference(name, persistent, monkeypatch):
+    """The engine's collect phase -- one persistent launch for all T steps (or T x (policy_step + env_insert)) writing
+    straight into the storage slots -- reproduces the reference's rollout: actions bit exact, values / log-probs /
+    recurrent states / masks / returns within the forward tolerance."""
+    from mappo_b200.engine import RolloutEngine
+    monkeypatch.setenv("MAPPO_B200_PERSISTENT_ROLLOUT", "1" if persistent else "0")
+    g = Golden(name)
+    cfg = g.cfg
+    args, policy, trainer, buf = build(cfg, g)
+    feed = g.feed(0)
+    eng = RolloutEngine(args, policy, trainer, buf, rng="host", seed=1)
+    eng.stage_feed(feed)
+    eng.draw_host_rng = lambda: None
+    eng.host["noise"].copy_(torch.from_numpy(g.get("it0/noise")))
+    eng.upload()
+    lib = eng.lib
+    import ctypes as C
+    from mappo_b200._lib import check, ptr
+    from mappo_b200.core import stream_ptr
+    check(lib.mappo_pack_rollout_weights(C.byref(policy.actor.desc), ptr(policy.actor.flat), ptr(eng.img_actor), stream_ptr()))
+    check(lib.mappo_pack_rollout_weights(C.byref(policy.critic.desc), ptr(policy.critic.flat), ptr(eng.img_critic), stream_ptr()))
+    if persistent:
+        eng._rollout_persistent()
+        eng._returns()
+    else:
+        for t in range(cfg.episode_length):
+            eng._collect_and_insert(t)
+        eng._compute()
+    torch.cuda.synchronize()
+    pre = "it0/buf/"
+    np.testing.assert_array_equal(buf.actions.cpu().numpy(), g.get(pre + "actions"))
+    assert_close(buf.action_log_probs.cpu().numpy(), g.get(pre + "action_log_probs"), 1e-4, 1e-5, "logp")
+    assert_close(buf.value_preds.cpu().numpy(), g.get(pre + "value_preds"), 1e-4, 1e-5, "value_preds")
+    assert_close(buf.rnn_states.cpu().numpy()[1:], g.get(pre + "rnn_states")[1:], 1e-4, 1e-5, "rnn_states")
+    assert_close(buf.rnn_states_critic.cpu().numpy()[1:], g.get(pre + "rnn_states_critic")[1:], 1e-4, 1e-5, "rnn_c")
+    np.testing.assert_array_equal(buf.masks.cpu().numpy(), g.get(pre + "masks"))
+    np.testing.assert_array_equal(buf.active_masks.cpu().numpy(), g.get(pre + "active_masks"))
+    assert_close(buf.returns.cpu().numpy()[:-1], g.get(pre + "returns")[:-1], 1e-4, 1e-4, "returns")
+    np.testing.assert_array_equal(buf.obs.cpu().numpy(), feed.obs)
+    np.testing.assert_array_equal(buf.share_obs.cpu().numpy(), feed.share_obs)
+    np.testing.assert_array_equal(buf.rewards.cpu().numpy(), feed.rewards)
