@@ -26,7 +26,7 @@ extern "C" {
 
 #define MAPPO_MAX_HEADS 4      /* MultiDiscrete heads per actor */
 #define MAPPO_MAX_LAYERS 2     /* layer_N hidden (H->H) blocks per MLP base */
-#define MAPPO_ABI_VERSION 1
+#define MAPPO_ABI_VERSION 2
 
 typedef enum mappo_status {
   MAPPO_OK = 0,
@@ -72,6 +72,8 @@ typedef struct mappo_loss_cfg {
   int32_t use_valuenorm;       /* normalise return targets with the ValueNorm state */
   int32_t update_actor;        /* ppo_update(sample, update_actor) r_mappo.py:91,145 */
   int32_t gemm_mode;           /* MAPPO_GEMM_FP32 (exact fp32 FFMA tiles) or MAPPO_GEMM_TF32 (tcgen05 tensor cores) */
+  int32_t weight_image_ready;  /* TF32 only: the workspace already holds the folded weight image of the CURRENT
+                                * parameters (left there by mappo_update_step_fused) -- skip the pack kernel */
 } mappo_loss_cfg_t;
 
 #define MAPPO_GEMM_FP32 0
@@ -234,6 +236,9 @@ int32_t mappo_update_grad_slots(const mappo_net_desc_t* desc, int32_t n_rows, in
 int32_t mappo_tf32_supported(const mappo_net_desc_t* desc);
 /* Diagnostic: clock64() phase stamps of CTA 0 of the last tcgen05 update launch (16 values, host pointer; syncs). */
 int32_t mappo_debug_tc_timing(int64_t* out16);
+/* Accumulated clock64 cycles of the rollout kernels' CTA 0, [8*net + phase] (phase 0 row load, 1 MLP base, 2 GRU cell,
+ * 3 head GEMM, 4 sampling + outputs); `reset` != 0 zeroes the counters after reading. */
+int32_t mappo_debug_pol_timing(int64_t* out16, int32_t reset);
 int32_t mappo_update_fwd_bwd(const mappo_net_desc_t* desc, const float* params, const mappo_batch_t* batch,
                              const mappo_loss_cfg_t* loss, const double* norm_stats,
                              const double* adv_stats, const float* vn_state,
@@ -278,6 +283,16 @@ int32_t mappo_update_slot_floats(const mappo_net_desc_t* desc, int32_t gemm_mode
 int32_t mappo_update_finish(const mappo_net_desc_t* desc, const float* params, const float* grad_part, int32_t n_slots,
                             int32_t gemm_mode, float* grad, float* sumsq_part, int32_t* n_blocks_out, float* workspace,
                             void* stream);
+/* TF32 build, single GPU: everything of ppo_update after the backward pass (r_mappo.py:141-167: clip_grad_norm_,
+ * optimizer.step) in two launches -- slot reduction, then ONE single-CTA kernel that unfolds the folded accumulators into
+ * `grad`, takes the global norm, clips, applies Adam to `params` and leaves the folded weight image of the NEW
+ * parameters in the workspace (next mappo_update_fwd_bwd: loss.weight_image_ready = 1).  vn_state + next_norm_stats
+ * (both nullable): also applies the ValueNorm.update of the NEXT minibatch (its mappo_minibatch_stats) so the critic
+ * chain needs no separate mappo_valuenorm_update launch.  MAPPO_ERR_UNSUPPORTED when mappo_tf32_supported() is 0. */
+int32_t mappo_update_step_fused(const mappo_net_desc_t* desc, float* params, const float* grad_part, int32_t n_slots,
+                                float* grad, float* exp_avg, float* exp_avg_sq, const float* lr_dev, int32_t* step_dev,
+                                float eps, float max_grad_norm, int32_t use_max_grad_norm, double* grad_norm_out,
+                                float* workspace, float* vn_state, const double* next_norm_stats, void* stream);
 int32_t mappo_grad_reduce(const float* grad_part, int32_t n_slots, int32_t n_params, float* grad,
                           float* sumsq_part, int32_t* n_sumsq_blocks_out, void* stream);
 /* Per-block sums of squares of an already reduced (e.g. all-reduced) gradient vector. */

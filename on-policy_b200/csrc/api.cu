@@ -82,12 +82,15 @@ int update_mlp_launch(const NetDev&, const float*, const BatchDev&, const LossDe
                       const float* dfeat_in = nullptr);
 bool update_mlp_tc_supported(const NetDev& n);
 int debug_tc_timing(long long* out16);
+int debug_pol_timing(long long* out16, int reset);
 int update_mlp_tc_slot_floats(const NetDev& n);
 int update_mlp_tc_unfold_launch(const NetDev&, const float*, const float*, float*, float*, cudaStream_t);
 int64_t update_mlp_tc_workspace_floats(const NetDev& n);
 int update_mlp_tc_slots(const NetDev& n, int n_rows, int sm_count);
 int update_mlp_tc_launch(const NetDev&, const float*, const BatchDev&, const LossDev&, const double*, const double*,
-                         const float*, float*, int, double*, float*, cudaStream_t);
+                         const float*, float*, int, double*, float*, bool, cudaStream_t);
+int update_mlp_tc_finish_launch(const NetDev&, float*, const float*, float*, float*, float*, const float*, int*, float, float,
+                                int, double*, float*, float*, const double*, cudaStream_t);
 int update_gru_slots(const NetDev& n, int n_rows, int seq_len, int sm_count);
 int64_t update_gru_workspace_floats(const NetDev& n, int n_rows);
 int update_gru_launch(const NetDev&, const float*, const BatchDev&, const LossDev&, const double*, const double*,
@@ -293,6 +296,11 @@ int32_t mappo_minibatch_stats(const float* returns, const float* active_masks, c
   return minibatch_stats_launch(returns, active_masks, rows, n_rows, stats, (cudaStream_t)stream);
 }
 
+int32_t mappo_debug_pol_timing(int64_t* out16, int32_t reset) {
+  if (!out16) { set_error("debug_pol_timing: NULL"); return MAPPO_ERR_INVALID; }
+  return debug_pol_timing(reinterpret_cast<long long*>(out16), reset);
+}
+
 int64_t mappo_debug_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
 int32_t mappo_minibatch_stats_batch(const float* returns, const float* active_masks, const int32_t* rows,
@@ -392,6 +400,23 @@ int32_t mappo_update_finish(const mappo_net_desc_t* desc, const float* params, c
   return grad_reduce_launch(grad_part, n_slots, n.g.total, grad, sumsq_part, n_blocks_out, (cudaStream_t)stream);
 }
 
+int32_t mappo_update_step_fused(const mappo_net_desc_t* desc, float* params, const float* grad_part, int32_t n_slots,
+                                float* grad, float* exp_avg, float* exp_avg_sq, const float* lr_dev, int32_t* step_dev,
+                                float eps, float max_grad_norm, int32_t use_max_grad_norm, double* grad_norm_out,
+                                float* workspace, float* vn_state, const double* next_norm_stats, void* stream) {
+  int rc = validate_desc(desc);
+  if (rc) return rc;
+  if (!params || !grad_part || !grad || !exp_avg || !exp_avg_sq || !lr_dev || !step_dev || !workspace || n_slots <= 0) { set_error("update_step_fused: bad arguments"); return MAPPO_ERR_INVALID; }
+  const NetDev n = make_net_dev(desc);
+  if (desc->recurrent || !update_mlp_tc_supported(n)) { set_error("update_step_fused: only built for the tcgen05 MLP path (mappo_tf32_supported)"); return MAPPO_ERR_UNSUPPORTED; }
+  float* raw_sum = workspace + update_mlp_tc_workspace_floats(n);
+  rc = grad_reduce_launch(grad_part, n_slots, update_mlp_tc_slot_floats(n), raw_sum, nullptr, nullptr, (cudaStream_t)stream);
+  if (rc) return rc;
+  return update_mlp_tc_finish_launch(n, params, raw_sum, grad, exp_avg, exp_avg_sq, lr_dev, step_dev, eps, max_grad_norm,
+                                     use_max_grad_norm, grad_norm_out, workspace, vn_state, next_norm_stats,
+                                     (cudaStream_t)stream);
+}
+
 int32_t mappo_update_grad_slots(const mappo_net_desc_t* desc, int32_t n_rows, int32_t gemm_mode) {
   if (validate_desc(desc)) return -1;
   const NetDev n = make_net_dev(desc);
@@ -427,7 +452,7 @@ int32_t mappo_update_fwd_bwd(const mappo_net_desc_t* desc, const float* params, 
   if (loss->gemm_mode == MAPPO_GEMM_TF32) {
     if (!update_mlp_tc_supported(n)) { set_error("update_fwd_bwd: MAPPO_GEMM_TF32 is not built for this net (hidden 64, layer_N 1, in_dim <= 63, MLP only)"); return MAPPO_ERR_UNSUPPORTED; }
     return update_mlp_tc_launch(n, params, b, L, norm_stats, adv_stats, vn_state, grad_part, n_slots, loss_out, workspace,
-                                (cudaStream_t)stream);
+                                loss->weight_image_ready != 0, (cudaStream_t)stream);
   }
   return update_mlp_launch(n, params, b, L, norm_stats, adv_stats, vn_state, grad_part, n_slots, loss_out,
                            (cudaStream_t)stream);

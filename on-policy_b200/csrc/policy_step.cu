@@ -122,6 +122,12 @@ struct PolCtx {
   float* hcarry;              // [H][LD] recurrent state carried between steps (persistent rollout)
 };
 
+// accumulated clock64 deltas of CTA x = 0 (thread 0): [8 * net + phase], phases: 0 row load/copy, 1 base forward,
+// 2 recurrent cell, 3 head GEMM, 4 sampling + outputs; read by mappo_debug_pol_timing()
+__device__ long long g_pol_timing[16];
+#define POL_T(i) do { if (blockIdx.x == 0 && tid == 0) { const long long now_ = clock64(); \
+    g_pol_timing[8 * which + (i)] += now_ - t_last; t_last = now_; } } while (0)
+
 template <int NJH>
 __device__ __forceinline__ void pol_step(const NetDev& n, int which, const PolCtx& c, const PolStep& p, int n_rows,
                                          int row0, int deterministic, uint64_t rng_seed, int n_avail, int tid) {
@@ -134,6 +140,7 @@ __device__ __forceinline__ void pol_step(const NetDev& n, int which, const PolCt
   float* smem = c.smem;
   float* sW = c.sW;
   const int* rowid = c.rowid;
+  long long t_last = clock64();
   // ---- rows of this step: coalesced (a warp walks a row), optional copy into the storage slot ----
   {
     const int warp = tid >> 5, lane = tid & 31, nw = NT >> 5;
@@ -154,8 +161,10 @@ __device__ __forceinline__ void pol_step(const NetDev& n, int which, const PolCt
       p.masks_copy[rowid[tid]] = p.done_prev ? (p.done_prev[rowid[tid]] != 0.f ? 0.f : 1.f) : p.masks[rowid[tid]];
   }
   if (!p.forward) { __syncthreads(); return; }
+  POL_T(0);
   base_forward<TR, NJH>(n, s, sW, c.t, tid);
   const float* feat = c.t.Y[n.layer_n];
+  POL_T(1);
 
   if (n.recurrent) {
     // h <- h * mask (rnn.py:27), one GRU step (torch gate order r,z,n), LN (rnn.py:79)
@@ -211,8 +220,10 @@ __device__ __forceinline__ void pol_step(const NetDev& n, int which, const PolCt
   float* lgT = smem + u.gi;
   const int Atot = n.head_total;
   __syncthreads();
+  POL_T(2);
   tile_mm<TR, 2>(feat, H, sW + s.head_w, s.ldh, 1, Atot, sW + s.head_b, ACT_NONE, lgT, tid);
   __syncthreads();
+  POL_T(3);
   if (tid < TR && rowid[tid] >= 0) {
     const int r = tid, g = rowid[r];
     if (which == 1) {
@@ -258,6 +269,7 @@ __device__ __forceinline__ void pol_step(const NetDev& n, int which, const PolCt
     }
   }
   __syncthreads();
+  POL_T(4);
 }
 
 // shared setup of both kernels: carve shared memory, start the weight fetch, fill rowid; returns the context
@@ -388,6 +400,15 @@ rollout_persistent_kernel(const NetDev na, const NetDev nc, const RolloutArgs a)
     }
     pol_step<NJH>(n, which, c, p, E, blockIdx.x * TR, 0, a.rng_seed, a.n_avail, tid);
   }
+}
+
+int debug_pol_timing(long long* out16, int reset) {
+  if (cudaMemcpyFromSymbol(out16, g_pol_timing, sizeof(long long) * 16) != cudaSuccess) return MAPPO_ERR_CUDA;
+  if (reset) {
+    long long z[16] = {0};
+    if (cudaMemcpyToSymbol(g_pol_timing, z, sizeof(z)) != cudaSuccess) return MAPPO_ERR_CUDA;
+  }
+  return MAPPO_OK;
 }
 
 __global__ void counter_add_kernel(uint64_t* c, uint64_t inc) { *c += inc; }

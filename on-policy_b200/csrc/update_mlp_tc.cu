@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const NetDev n, const floa
       if (k < n.in_dim) v = W[k] * (n.use_fn ? p[n.g.fn_w + k] : 1.f);
       else if (k == n.in_dim) {
         v = p[n.g.fc1_b + o];
-        if (n.use_fn) for (int j = 0; j < n.in_dim; ++j) v = fmaf(W[j], p[n.g.fn_b + j], v);
+        if (n.use_fn) for (int j0 = 0; j0 < n.in_dim; ++j0) { const int j = (j0 + o) % n.in_dim; v = fmaf(W[j], p[n.g.fn_b + j], v); }
       }
     } else if (i < m.wh) {                                // fc2: [18][64][4], input LN = ln1
       const int t = i - m.w2, kc = t / 256, o = (t >> 2) & 63, k = kc * 4 + (t & 3);
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const NetDev n, const floa
       if (k < H) v = W[k] * p[n.g.ln1_w + k];
       else if (k == kOne) {
         v = p[n.g.fc2_b[0] + o];
-        for (int j = 0; j < H; ++j) v = fmaf(W[j], p[n.g.ln1_b + j], v);
+        for (int j0 = 0; j0 < H; ++j0) { const int j = (j0 + o) & 63; v = fmaf(W[j], p[n.g.ln1_b + j], v); }
       }
     } else if (i < m.w2t) {                               // heads: [18][NH][4], input LN = ln2[0]
       const int t = i - m.wh, kc = t / (4 * m.NH), a = (t >> 2) % m.NH, k = kc * 4 + (t & 3);
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const NetDev n, const floa
         if (k < H) v = W[k] * p[n.g.ln2_w[0] + k];
         else if (k == kOne) {
           v = p[n.g.head_b + a];
-          for (int j = 0; j < H; ++j) v = fmaf(W[j], p[n.g.ln2_b[0] + j], v);
+          for (int j0 = 0; j0 < H; ++j0) { const int j = (j0 + a) & 63; v = fmaf(W[j], p[n.g.ln2_b[0] + j], v); }
         }
       }
     } else if (i < m.wht) {                               // fc2 transposed: element (row k, K-index o) = W2'[o][k]
@@ -274,6 +274,216 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const NetDev n, const floa
     } else {                                              // heads transposed: (row k, K-index a) = Wh'[a][k]
       const int t = i - m.wht, ac = t / 256, k = (t >> 2) & 63, a = ac * 4 + (t & 3);
       if (a < n.head_total) v = p[n.g.head_w + a * H + k] * p[n.g.ln2_w[0] + k];
+    }
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    img[i] = __uint_as_float(u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Single-GPU optimiser tail of one update as ONE single-CTA kernel (everything after the slot reduction is <= 15 K
+// elements): unfold the summed raw accumulators -> global gradient norm -> clip -> Adam -> the folded weight image of
+// the NEXT update (+ optionally the next minibatch's ValueNorm update).  Replaces tc_unfold + clip_adam + pack_tc
+// (+ valuenorm_update): per update and net the launch chain is  update_mlp_tc -> grad_reduce -> tc_finish.
+// Parameters and gradients live in shared memory between the phases; 1024 threads = 64 input features x 16 groups of
+// 4 output rows (the same partition and summation order as tc_unfold_kernel).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1)
+tc_finish_kernel(const NetDev n, float* __restrict__ p, const float* __restrict__ raw_g, float* __restrict__ g,
+                 float* __restrict__ ea, float* __restrict__ eas, const float* __restrict__ lr_dev,
+                 int* __restrict__ step_dev, float eps, float max_norm, int use_clip, double* __restrict__ norm_out,
+                 float* __restrict__ img, float* __restrict__ vn, const double* __restrict__ next_stats,
+                 int stage_moments) {
+  extern __shared__ __align__(16) float fs[];
+  __shared__ double sredd[32];
+  __shared__ float s_coef, s_step_size, s_bc2_sqrt, s_total;
+  __shared__ int s_step;
+  __shared__ __align__(8) uint64_t bar;
+  const TcImage m = make_tc_image(n);
+  const TcRaw R = make_tc_raw(m);
+  const int P = n.g.total, Pp = (P + 3) & ~3, P4 = P & ~3;
+  float* sp = fs;                      // parameters (old, then new)
+  float* sg = sp + Pp;                 // unfolded gradient
+  float* part_g = sg + Pp;             // [16][64]
+  float* part_b = part_g + 1024;
+  float* raw = part_b + 1024;          // slot-summed raw accumulators
+  float* sm1 = raw + R.total;          // Adam moments (when they fit)
+  float* sm2 = sm1 + Pp;
+  const int tid = threadIdx.x, k = tid & 63, og = tid >> 6;
+  const int in = n.in_dim, Atot = n.head_total, H = 64;
+
+  // ---- every global input arrives by TMA bulk copies issued up front: one round trip instead of one per phase ----
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t bytes = (uint32_t)(R.total * 4 + P4 * 4 * (stage_moments ? 3 : 1));
+    mbar_expect_tx(&bar, bytes);
+    tma_bulk_g2s(raw, raw_g, (uint32_t)(R.total * 4), &bar);
+    tma_bulk_g2s(sp, p, (uint32_t)(P4 * 4), &bar);
+    if (stage_moments) {
+      tma_bulk_g2s(sm1, ea, (uint32_t)(P4 * 4), &bar);
+      tma_bulk_g2s(sm2, eas, (uint32_t)(P4 * 4), &bar);
+    }
+  }
+  if (tid < P - P4) {                                                    // the <= 3 floats past the 16-byte multiple
+    const int i = P4 + tid;
+    sp[i] = p[i];
+    if (stage_moments) { sm1[i] = ea[i]; sm2[i] = eas[i]; }
+  }
+  // scalar work that depends on no gradient: Adam bias corrections (fp64 pow) and the next ValueNorm update
+  if (tid == 992) {
+    const int st = *step_dev + 1;                                        // 1-based Adam step
+    const double bc1 = 1.0 - pow(0.9, (double)st), bc2 = 1.0 - pow(0.999, (double)st);
+    s_step_size = (float)((double)lr_dev[0] / bc1);
+    s_bc2_sqrt = (float)sqrt(bc2);
+    s_step = st;
+  }
+  if (tid == 960 && vn && next_stats) {                                  // utils/valuenorm.py:38-55
+    const double cnt = next_stats[3] > 0.0 ? next_stats[3] : 1.0;
+    const float bm = (float)(next_stats[1] / cnt), bsq = (float)(next_stats[2] / cnt);
+    const float w = 0.99999f, om = (float)(1.0 - 0.99999);
+    vn[0] = vn[0] * w + bm * om;
+    vn[1] = vn[1] * w + bsq * om;
+    vn[2] = vn[2] * w + 1.0f * om;
+  }
+  __syncthreads();                     // barrier init visible; tail elements stored
+  mbar_wait(&bar, 0);
+
+  // ---- unfold: dW = dW' diag(gamma_in), db = dW'[:, one], dgamma_in = colsum(dW' .* W), dbeta_in = W^T db' ----
+#pragma unroll 1
+  for (int sec = 0; sec < 2; ++sec) {
+    const int K = sec == 0 ? 64 : in, ld = sec == 0 ? kHF : m.inF, one = sec == 0 ? kOne : in;
+    const float* G = raw + (sec == 0 ? R.g2 : R.g1);
+    const int w_off = sec == 0 ? n.g.fc2_w[0] : n.g.fc1_w, b_off = sec == 0 ? n.g.fc2_b[0] : n.g.fc1_b;
+    const bool fold = sec == 0 ? true : (n.use_fn != 0);
+    const int gam_off = sec == 0 ? n.g.ln1_w : n.g.fn_w, bet_off = sec == 0 ? n.g.ln1_b : n.g.fn_b;
+    float a = 0.f, c = 0.f;
+    if (k < K) {
+      const float gam = fold ? sp[gam_off + k] : 1.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int o = og * 4 + j;
+        const float dw = G[o * ld + k], w = sp[w_off + o * K + k];
+        sg[w_off + o * K + k] = dw * gam;
+        a = fmaf(dw, w, a);
+        c = fmaf(G[o * ld + one], w, c);
+      }
+    }
+    if (tid < 64) sg[b_off + tid] = G[tid * ld + one];
+    part_g[og * 64 + k] = a; part_b[og * 64 + k] = c;
+    __syncthreads();
+    if (fold && og == 0 && k < K) {
+      float x = 0.f, y = 0.f;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) { x += part_g[q * 64 + k]; y += part_b[q * 64 + k]; }
+      sg[gam_off + k] = x;
+      sg[bet_off + k] = y;
+    }
+    __syncthreads();
+  }
+  {                                                       // heads: raw gh[feature][a]
+    const float gam = sp[n.g.ln2_w[0] + k];
+    float a = 0.f, c = 0.f;
+    for (int h = og; h < Atot; h += 16) {
+      const float dw = raw[R.gh + k * m.NH + h], w = sp[n.g.head_w + h * H + k];
+      sg[n.g.head_w + h * H + k] = dw * gam;
+      a = fmaf(dw, w, a);
+      c = fmaf(raw[R.dbh + h], w, c);
+    }
+    if (tid < Atot) sg[n.g.head_b + tid] = raw[R.dbh + tid];
+    part_g[og * 64 + k] = a; part_b[og * 64 + k] = c;
+    __syncthreads();
+    if (og == 0) {
+      float x = 0.f, y = 0.f;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) { x += part_g[q * 64 + k]; y += part_b[q * 64 + k]; }
+      sg[n.g.ln2_w[0] + k] = x;
+      sg[n.g.ln2_b[0] + k] = y;
+    }
+    __syncthreads();
+  }
+
+  // ---- global norm, clip coefficient (clip_grad_norm_) ----
+  {
+    float q = 0.f;
+    for (int i = tid; i < P; i += 1024) q = fmaf(sg[i], sg[i], q);
+    double x = (double)q;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((tid & 31) == 0) sredd[tid >> 5] = x;
+    __syncthreads();
+    if (tid < 32) {
+      double y = sredd[tid];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) y += __shfl_xor_sync(0xffffffffu, y, o);
+      if (tid == 0) {
+        const float tot = (float)sqrt(y);
+        s_total = tot;
+        s_coef = use_clip ? fminf(max_norm / (tot + 1e-6f), 1.0f) : 1.f;
+      }
+    }
+    __syncthreads();
+  }
+  // ---- Adam (torch single-tensor formula, same expression as clip_adam_kernel) ----
+  {
+    const float coef = s_coef, step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+    for (int i = tid; i < P; i += 1024) {
+      const float gu = sg[i];
+      const float gi = gu * coef;
+      const float mo = stage_moments ? sm1[i] : ea[i], vo = stage_moments ? sm2[i] : eas[i];
+      const float mi = mo + (gi - mo) * (float)(1.0 - 0.9);
+      const float vi = vo * 0.999f + (float)(1.0 - 0.999) * gi * gi;
+      const float denom = sqrtf(vi) / bc2_sqrt + eps;
+      const float pn = sp[i] - step_size * (mi / denom);
+      sp[i] = pn;
+      p[i] = pn;
+      ea[i] = mi;
+      eas[i] = vi;
+      g[i] = gu;                         // the unclipped gradient stays inspectable (named_grads)
+    }
+    if (tid == 0) {
+      step_dev[0] = s_step;
+      if (norm_out) *norm_out += (double)s_total;
+    }
+  }
+  __syncthreads();
+  // ---- folded tf32 weight image of the next update (the formulas of pack_tc_kernel, parameters from shared memory;
+  //      the 64-term bias folds start at a lane-dependent feature so that the 32 rows of a warp hit 32 banks) ----
+  for (int i = tid; i < m.total; i += 1024) {
+    float v = 0.f;
+    if (i < m.w2) {                                       // fc1: [inF/4][64][4]
+      const int kc = i / 256, o = (i >> 2) & 63, kk = kc * 4 + (i & 3);
+      const float* W = sp + n.g.fc1_w + o * in;
+      if (kk < in) v = W[kk] * (n.use_fn ? sp[n.g.fn_w + kk] : 1.f);
+      else if (kk == in) {
+        v = sp[n.g.fc1_b + o];
+        if (n.use_fn) for (int j0 = 0; j0 < in; ++j0) { const int j = (j0 + o) % in; v = fmaf(W[j], sp[n.g.fn_b + j], v); }
+      }
+    } else if (i < m.wh) {                                // fc2: [18][64][4], input LN = ln1
+      const int t = i - m.w2, kc = t / 256, o = (t >> 2) & 63, kk = kc * 4 + (t & 3);
+      const float* W = sp + n.g.fc2_w[0] + o * H;
+      if (kk < H) v = W[kk] * sp[n.g.ln1_w + kk];
+      else if (kk == kOne) {
+        v = sp[n.g.fc2_b[0] + o];
+        for (int j0 = 0; j0 < H; ++j0) { const int j = (j0 + o) & 63; v = fmaf(W[j], sp[n.g.ln1_b + j], v); }
+      }
+    } else if (i < m.w2t) {                               // heads: [18][NH][4], input LN = ln2[0]
+      const int t = i - m.wh, kc = t / (4 * m.NH), a = (t >> 2) % m.NH, kk = kc * 4 + (t & 3);
+      if (a < Atot) {
+        const float* W = sp + n.g.head_w + a * H;
+        if (kk < H) v = W[kk] * sp[n.g.ln2_w[0] + kk];
+        else if (kk == kOne) {
+          v = sp[n.g.head_b + a];
+          for (int j0 = 0; j0 < H; ++j0) { const int j = (j0 + a) & 63; v = fmaf(W[j], sp[n.g.ln2_b[0] + j], v); }
+        }
+      }
+    } else if (i < m.wht) {                               // fc2 transposed: element (row k, K-index o) = W2'[o][k]
+      const int t = i - m.w2t, oc = t / 256, kk = (t >> 2) & 63, o = oc * 4 + (t & 3);
+      v = sp[n.g.fc2_w[0] + o * H + kk] * sp[n.g.ln1_w + kk];
+    } else {                                              // heads transposed: (row k, K-index a) = Wh'[a][k]
+      const int t = i - m.wht, ac = t / 256, kk = (t >> 2) & 63, a = ac * 4 + (t & 3);
+      if (a < Atot) v = sp[n.g.head_w + a * H + kk] * sp[n.g.ln2_w[0] + kk];
     }
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
@@ -776,7 +986,7 @@ int update_mlp_tc_slots(const NetDev&, int n_rows, int sm_count) {
 
 int update_mlp_tc_launch(const NetDev& n, const float* params, const BatchDev& b, const LossDev& L,
                          const double* norm_stats, const double* adv_stats, const float* vn_state, float* grad_part,
-                         int n_slots, double* loss_out, float* image, cudaStream_t st) {
+                         int n_slots, double* loss_out, float* image, bool image_ready, cudaStream_t st) {
   if (!update_mlp_tc_supported(n)) { set_error("update_mlp_tc: configuration not built for the tcgen05 path"); return MAPPO_ERR_UNSUPPORTED; }
   if (!image) { set_error("update_mlp_tc: weight-image workspace is NULL"); return MAPPO_ERR_INVALID; }
   if ((reinterpret_cast<uintptr_t>(image) & 15) != 0) { set_error("update_mlp_tc: workspace must be 16-byte aligned"); return MAPPO_ERR_INVALID; }
@@ -784,9 +994,11 @@ int update_mlp_tc_launch(const NetDev& n, const float* params, const BatchDev& b
   const TcSmem sm = make_tc_smem(im);
   const size_t bytes = (size_t)sm.total * sizeof(float) + 1024;
   if (bytes > 227 * 1024) { set_error("update_mlp_tc: %zu B shared memory > 227 KB", bytes); return MAPPO_ERR_UNSUPPORTED; }
-  pack_tc_kernel<<<(im.total + 255) / 256, 256, 0, st>>>(n, params, image);      // one element per thread
-  int rc = check_launch("pack_tc_kernel");
-  if (rc) return rc;
+  if (!image_ready) {        // the fused optimiser tail of the previous update (tc_finish_kernel) leaves it ready
+    pack_tc_kernel<<<(im.total + 255) / 256, 256, 0, st>>>(n, params, image);      // one element per thread
+    const int rc = check_launch("pack_tc_kernel");
+    if (rc) return rc;
+  }
   static thread_local size_t configured = 0;
   if (bytes > configured) {
     if (cudaFuncSetAttribute(update_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
@@ -798,6 +1010,28 @@ int update_mlp_tc_launch(const NetDev& n, const float* params, const BatchDev& b
   update_mlp_tc_kernel<<<n_slots, kTCThreads, bytes, st>>>(n, params, image, b, L, norm_stats, adv_stats, vn_state, grad_part,
                                                     loss_out, n_tiles, cols);
   return check_launch("update_mlp_tc_kernel");
+}
+
+int update_mlp_tc_finish_launch(const NetDev& n, float* params, const float* raw_sum, float* grad, float* exp_avg,
+                                float* exp_avg_sq, const float* lr_dev, int* step_dev, float eps, float max_norm,
+                                int use_clip, double* norm_out, float* image, float* vn_state, const double* next_stats,
+                                cudaStream_t st) {
+  const int Pp = (n.g.total + 3) & ~3;
+  const int raw_floats = make_tc_raw(make_tc_image(n)).total;
+  size_t bytes = (size_t)(4 * Pp + 2048 + raw_floats) * sizeof(float);
+  int stage_moments = 1;
+  if (bytes > 220 * 1024) { stage_moments = 0; bytes = (size_t)(2 * Pp + 2048 + raw_floats) * sizeof(float); }
+  if (bytes > 220 * 1024) { set_error("update_step_fused: %zu B shared memory", bytes); return MAPPO_ERR_UNSUPPORTED; }
+  if (((uintptr_t)params | (uintptr_t)raw_sum | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) { set_error("update_step_fused: 16-byte alignment required"); return MAPPO_ERR_INVALID; }
+  static thread_local size_t configured = 0;
+  if (bytes > configured) {
+    if (cudaFuncSetAttribute(tc_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+      return check_launch("tc_finish: cudaFuncSetAttribute");
+    configured = bytes;
+  }
+  tc_finish_kernel<<<1, 1024, bytes, st>>>(n, params, raw_sum, grad, exp_avg, exp_avg_sq, lr_dev, step_dev, eps, max_norm,
+                                           use_clip, norm_out, image, vn_state, next_stats, stage_moments);
+  return check_launch("tc_finish_kernel");
 }
 
 }  // namespace mappo

@@ -33,7 +33,8 @@ class LossCfg(C.Structure):
                 ("huber_delta", C.c_float),
                 ("use_clipped_value_loss", C.c_int32), ("use_huber_loss", C.c_int32),
                 ("use_value_active_masks", C.c_int32), ("use_policy_active_masks", C.c_int32),
-                ("use_valuenorm", C.c_int32), ("update_actor", C.c_int32), ("gemm_mode", C.c_int32)]
+                ("use_valuenorm", C.c_int32), ("update_actor", C.c_int32), ("gemm_mode", C.c_int32),
+                ("weight_image_ready", C.c_int32)]
 
 
 _P = C.c_void_p
@@ -66,6 +67,7 @@ _SIGS = {
     "mappo_evaluate_actions": (_i32, [C.POINTER(NetDesc), _P, C.POINTER(Batch), C.POINTER(LossCfg), _P, _P, _P, _P, _P]),
     "mappo_minibatch_stats": (_i32, [_P, _P, _P, _i32, _P, _P]),
     "mappo_debug_launch_count": (_i64, []),
+    "mappo_update_step_fused": (_i32, [_P, _P, _P, _i32, _P, _P, _P, _P, _P, _f32, _f32, _i32, _P, _P, _P, _P, _P]),
     "mappo_minibatch_stats_batch": (_i32, [_P, _P, _P, _i64, _i32, _i32, _P, _P]),
     "mappo_randperm_batch": (_i32, [_i32, _i32, _u64, _P, _P, _P]),
     "mappo_valuenorm_update": (_i32, [_P, _P, _P]),
@@ -76,6 +78,7 @@ _SIGS = {
     "mappo_update_grad_slots": (_i32, [C.POINTER(NetDesc), _i32, _i32]),
     "mappo_tf32_supported": (_i32, [C.POINTER(NetDesc)]),
     "mappo_debug_tc_timing": (_i32, [C.POINTER(_i64)]),
+    "mappo_debug_pol_timing": (_i32, [C.POINTER(_i64), _i32]),
     "mappo_update_fwd_bwd": (_i32, [C.POINTER(NetDesc), _P, C.POINTER(Batch), C.POINTER(LossCfg), _P, _P, _P, _P,
                                     _i32, _P, _P, _P]),
     "mappo_update_slot_floats": (_i32, [C.POINTER(NetDesc), _i32]),
@@ -107,7 +110,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError here = header / library out of sync
         fn.restype = res
         fn.argtypes = args
-    if lib.mappo_abi_version() != 1:
+    if lib.mappo_abi_version() != 2:
         raise RuntimeError("libmappo_b200.so ABI version mismatch")
     _lib = lib
     return lib

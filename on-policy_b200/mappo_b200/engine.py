@@ -301,7 +301,16 @@ class RolloutEngine:
             self._epoch_i = 0
             self.trainer.launch_train(self.buffer, True, self._draw_perm, self.loss_out, allreduce=None)
 
-        return {"collect_insert_ms": timed(collect),
+        # cycle split of one rollout pass inside CTA 0 of each net (clock64 accumulators of the kernel)
+        buf = (C.c_int64 * 16)()
+        torch.cuda.synchronize()
+        self.lib.mappo_debug_pol_timing(buf, 1)
+        collect()
+        torch.cuda.synchronize()
+        self.lib.mappo_debug_pol_timing(buf, 1)
+        names = ["rows", "mlp_base", "gru_cell", "head_gemm", "sample_store"]
+        cyc = {net: {nm: int(buf[8 * k + i]) for i, nm in enumerate(names)} for k, net in enumerate(("actor", "critic"))}
+        return {"rollout_cycles_cta0": cyc, "collect_insert_ms": timed(collect),
                 "values_gae_ms": timed(self._returns if self.persistent_rollout else self._compute), "train_ms": timed(train),
                 "after_update_ms": timed(self.buffer.after_update)}
 
