@@ -272,6 +272,10 @@ __device__ __forceinline__ void pol_step(const NetDev& n, int which, const PolCt
   POL_T(4);
 }
 
+}  // namespace mappo
+#include "rollout_mlp.cuh"
+namespace mappo {
+
 // shared setup of both kernels: carve shared memory, start the weight fetch, fill rowid; returns the context
 template <int NJH>
 __device__ __forceinline__ PolCtx pol_setup(const NetDev& n, float* smem, const float* params, const float* image,
@@ -415,6 +419,27 @@ __global__ void counter_add_kernel(uint64_t* c, uint64_t inc) { *c += inc; }
 
 int policy_step_launch(const NetDev* na, const NetDev* nc, const PolArgs& a, cudaStream_t st) {
   const NetDev& ref = na ? *na : *nc;
+  {   // feed-forward nets with a packed image: the warp-per-two-rows path (rollout_mlp.cuh)
+    bool fast = true;
+    size_t fb = 0;
+    for (int w = 0; w < 2; ++w) {
+      const NetDev* n = w == 0 ? na : nc;
+      if (!n) continue;
+      if (!fast_rollout_supported(*n) || !a.image[w]) fast = false;
+      else { const size_t b = fast_smem_bytes(*n); fb = b > fb ? b : fb; }
+    }
+    if (fast) {
+      static thread_local size_t configured_f = 0;
+      if (fb > configured_f) {
+        if (cudaFuncSetAttribute(policy_step_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fb) != cudaSuccess)
+          return check_launch("policy_step_fast: cudaFuncSetAttribute");
+        configured_f = fb;
+      }
+      const dim3 grid((a.n_rows + kFR - 1) / kFR, (na && nc) ? 2 : 1);
+      policy_step_fast_kernel<<<grid, kFT, fb, st>>>(na ? *na : ref, nc ? *nc : ref, a, na ? 0 : 1);
+      return check_launch("policy_step_fast_kernel");
+    }
+  }
   size_t bytes = 0;
   for (const NetDev* n : {na, nc}) {
     if (!n) continue;
@@ -438,6 +463,17 @@ int policy_step_launch(const NetDev* na, const NetDev* nc, const PolArgs& a, cud
 }
 
 int rollout_persistent_launch(const NetDev& na, const NetDev& nc, const RolloutArgs& a, cudaStream_t st) {
+  if (fast_rollout_supported(na) && fast_rollout_supported(nc) && a.image[0] && a.image[1]) {
+    const size_t ba = fast_smem_bytes(na), bc = fast_smem_bytes(nc), fb = ba > bc ? ba : bc;
+    static thread_local size_t configured_f = 0;
+    if (fb > configured_f) {
+      if (cudaFuncSetAttribute(rollout_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fb) != cudaSuccess)
+        return check_launch("rollout_fast: cudaFuncSetAttribute");
+      configured_f = fb;
+    }
+    rollout_fast_kernel<<<dim3((a.E + kFR - 1) / kFR, 2), kFT, fb, st>>>(na, nc, a);
+    return check_launch("rollout_fast_kernel");
+  }
   size_t bytes = 0;
   for (const NetDev* n : {&na, &nc}) {
     if (n->hid != 64) { set_error("rollout: hidden_size %d not built in the fused SIMT path (64 only)", n->hid); return MAPPO_ERR_UNSUPPORTED; }
@@ -461,10 +497,16 @@ int rollout_persistent_launch(const NetDev& na, const NetDev& nc, const RolloutA
 }
 
 int pack_rollout_launch(const NetDev& n, const float* params, float* image, cudaStream_t st) {
+  if (fast_rollout_supported(n)) {        // feed-forward nets: the [k][tx][4] image of rollout_mlp.cuh
+    pack_fast_kernel<<<(make_fast_img(n).total + 255) / 256, 256, 0, st>>>(n, params, image);
+    return check_launch("pack_fast_kernel");
+  }
   pack_rollout_kernel<<<(n.g.total + 255) / 256, 256, 0, st>>>(n, params, image);
   return check_launch("pack_rollout_kernel");
 }
-int rollout_image_floats(const NetDev& n) { return make_smem_w(n, true).total; }
+int rollout_image_floats(const NetDev& n) {
+  return fast_rollout_supported(n) ? make_fast_img(n).total : make_smem_w(n, true).total;
+}
 
 int counter_add_launch(uint64_t* c, uint64_t inc, cudaStream_t st) {
   counter_add_kernel<<<1, 1, 0, st>>>(c, inc);
