@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "net_tiles.cuh"
 #include "launch_args.h"
@@ -20,6 +21,11 @@ void set_error(const char* fmt, ...) {
 }
 
 static std::atomic<long long> g_launches{0};
+
+int pdl_mode() {
+  static const int mode = [] { const char* e = getenv("MAPPO_B200_PDL"); return e ? atoi(e) : 0; }();
+  return mode;
+}
 
 // every kernel launch of the library reports here under its kernel name ("x: attribute" strings are not launches)
 int check_launch(const char* what) {

@@ -1,38 +1,40 @@
-// rollout_mlp.cuh -- rollout inference of feed-forward (MLP) policies: ONE WARP OWNS TWO ROWS END TO END.
+// rollout_mlp.cuh -- rollout inference of feed-forward (MLP) policies: ONE WARP OWNS ONE ROW END TO END.
 // (included by policy_step.cu only; the GRU policies keep the tile path there.)
 //
-// Rows of a rollout step never interact, and a 64-wide MLP row fits one half-warp: lane tx of the 16 lanes of a row
-// owns hidden columns tx, tx+16, tx+32, tx+48.  Then
-//   * LayerNorm statistics are 16-lane shuffles (the same xor 8,4,2,1 tree as tile_mm_ln: identical rounding),
-//   * a layer's activations travel through a 2-row scratch that only this warp touches: __syncwarp(), never a CTA barrier,
-//   * the weights are packed as [k][tx][4] so one LDS.128 feeds the 4 FMAs of a k (mappo_pack_rollout_weights builds this
-//     image for non-recurrent nets; a CTA fetches it with one TMA bulk copy),
-//   * sampling is parallel over the actions of a head (lane j owns action j) but adds the softmax denominator in the
-//     serial j = 0..A-1 order of the tile path, so log-probs and the argmax(p / Exp(1)) draw stay bit-identical to it.
-// A CTA = 8 warps = 16 rows.  In the persistent rollout each warp walks t = 0..T with the NEXT step's rows already in
-// flight (prefetched into registers), so no global-memory latency sits between two steps.
+// Rows of a rollout step never interact, and a 64-wide MLP row fits one warp: lane l owns hidden columns l and l + 32.
+//   * LayerNorm statistics are warp shuffles,
+//   * a layer's activations travel through a 64-float scratch that only this warp touches: __syncwarp(), never a CTA
+//     barrier; the warp reads them back as broadcast LDS.128 (4 k per load),
+//   * the weights are packed as [k][lane][2] so one conflict-free LDS.64 feeds the lane's 2 FMAs of a k
+//     (mappo_pack_rollout_weights builds this image for non-recurrent nets; a CTA fetches it with one TMA bulk copy),
+//   * every dot product accumulates k = 0, 1, 2, ... sequentially in one register, exactly like tile_mm / tile_mm_ln,
+//   * sampling is parallel over the actions of a head (lane off + j owns action j) but adds the softmax denominator in
+//     the serial j = 0..A-1 order of the tile path, so the argmax(p / Exp(1)) draw sees the same numbers.
+// A CTA = 4 warps = 4 rows, so E rows spread over E/4 CTAs per net (c2: 96 + 96 CTAs on 148 SMs, ~1 warp per scheduler:
+// the per-step latency chain of a row is what is left).  In the persistent rollout each warp walks t = 0..T with the NEXT
+// step's row already in flight (prefetched into registers), so no global-memory latency sits between two steps.
 #pragma once
 #include "net_tiles.cuh"
 #include "launch_args.h"
 
 namespace mappo {
 
-constexpr int kFR = 16;             // rows per CTA
-constexpr int kFT = 256;            // threads per CTA
-constexpr int kFWarpScratch = 320;  // floats per warp: two [64][2] activation buffers + [2][32] logits
+constexpr int kFR = 4;              // rows (= warps) per CTA
+constexpr int kFT = 32 * kFR;       // threads per CTA
+constexpr int kFWarpScratch = 128;  // floats per warp: two 64-float activation buffers
 
 struct FastImg {
-  int fn_w, fn_b, w1, b1, g1, be1;
+  int fn_w, fn_b, w1, b1, g1, be1, K1;       // K1 = in_dim padded to a multiple of 4 (zero rows)
   int w2[kMaxLayers], b2[kMaxLayers], g2[kMaxLayers], be2[kMaxLayers];
   int wh, bh, AP, total;
 };
 __host__ __device__ inline FastImg make_fast_img(const NetDev& n) {
   FastImg f;
   int o = 0;
-  const int inp = (n.in_dim + 3) & ~3;
-  f.fn_w = o; o += n.use_fn ? inp : 0;
-  f.fn_b = o; o += n.use_fn ? inp : 0;
-  f.w1 = o; o += n.in_dim * 64;
+  f.K1 = (n.in_dim + 3) & ~3;
+  f.fn_w = o; o += n.use_fn ? f.K1 : 0;
+  f.fn_b = o; o += n.use_fn ? f.K1 : 0;
+  f.w1 = o; o += f.K1 * 64;
   f.b1 = o; o += 64; f.g1 = o; o += 64; f.be1 = o; o += 64;
   for (int l = 0; l < kMaxLayers; ++l) {
     f.w2[l] = f.b2[l] = f.g2[l] = f.be2[l] = 0;
@@ -54,24 +56,24 @@ __host__ __device__ inline bool fast_rollout_supported(const NetDev& n) {
 __global__ void __launch_bounds__(256) pack_fast_kernel(const NetDev n, const float* __restrict__ p, float* __restrict__ img) {
   const FastImg f = make_fast_img(n);
   const mappo_net_layout_t& g = n.g;
-  const int in = n.in_dim, inp = (in + 3) & ~3;
+  const int in = n.in_dim;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < f.total; i += gridDim.x * blockDim.x) {
     float v = 0.f;
     if (i < f.w1) {                                       // feature-norm affine (only present when use_fn)
       const int t = i - f.fn_w;
-      if (t < inp) { if (t < in) v = p[g.fn_w + t]; }
-      else if (t - inp < in) v = p[g.fn_b + t - inp];
-    } else if (i < f.b1) {                                // fc1 as [k][tx][j]: element = W1[tx + 16 j][k]
-      const int t = i - f.w1, k = t >> 6, tx = (t >> 2) & 15, j = t & 3;
-      v = p[g.fc1_w + (tx + 16 * j) * in + k];
+      if (t < f.K1) { if (t < in) v = p[g.fn_w + t]; }
+      else if (t - f.K1 < in) v = p[g.fn_b + t - f.K1];
+    } else if (i < f.b1) {                                // fc1 as [k][lane][j]: element = W1[lane + 32 j][k]
+      const int t = i - f.w1, k = t >> 6, ln = (t >> 1) & 31, j = t & 1;
+      if (k < in) v = p[g.fc1_w + (ln + 32 * j) * in + k];
     } else if (i < f.g1) v = p[g.fc1_b + i - f.b1];
     else if (i < f.be1) v = p[g.ln1_w + i - f.g1];
     else if (i < f.be1 + 64) v = p[g.ln1_b + i - f.be1];
     else if (i < f.wh) {
       for (int l = 0; l < n.layer_n; ++l) {
         if (i >= f.w2[l] && i < f.b2[l]) {
-          const int t = i - f.w2[l], k = t >> 6, tx = (t >> 2) & 15, j = t & 3;
-          v = p[g.fc2_w[l] + (tx + 16 * j) * 64 + k];
+          const int t = i - f.w2[l], k = t >> 6, ln = (t >> 1) & 31, j = t & 1;
+          v = p[g.fc2_w[l] + (ln + 32 * j) * 64 + k];
         } else if (i >= f.b2[l] && i < f.g2[l]) v = p[g.fc2_b[l] + i - f.b2[l]];
         else if (i >= f.g2[l] && i < f.be2[l]) v = p[g.ln2_w[l] + i - f.g2[l]];
         else if (i >= f.be2[l] && i < f.be2[l] + 64) v = p[g.ln2_b[l] + i - f.be2[l]];
@@ -87,190 +89,161 @@ __global__ void __launch_bounds__(256) pack_fast_kernel(const NetDev n, const fl
   }
 }
 
-__device__ __forceinline__ float sum16(float s) {
+__device__ __forceinline__ float warp_sum(float s) {
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   return s;
 }
 
-// Y = LayerNorm(act(X W^T + b)) * gamma + beta for this lane's row: X [K][2] -> Y [64][2] in the warp's scratch.
-// Same arithmetic, in the same order, as tile_mm_ln (common.cuh).
-__device__ __forceinline__ void fast_layer(const float* __restrict__ X, int K, const float* __restrict__ Wq,
+// Y = LayerNorm(act(X W^T + b)) * gamma + beta for the warp's row: X [K4] -> Y [64] in the warp's scratch.
+// K4 is a multiple of 4 (X and the weight rows are zero-padded).
+__device__ __forceinline__ void fast_layer(const float* __restrict__ X, int K4, const float* __restrict__ Wq,
                                            const float* __restrict__ b, const float* __restrict__ gm,
-                                           const float* __restrict__ be, int act, float* __restrict__ Y, int tx, int rr) {
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  const float4* w4 = reinterpret_cast<const float4*>(Wq) + tx;
-#pragma unroll 8
-  for (int k = 0; k < K; ++k) {
-    const float a = X[k * 2 + rr];
-    const float4 w = w4[k * 16];
-    acc[0] = fmaf(a, w.x, acc[0]);
-    acc[1] = fmaf(a, w.y, acc[1]);
-    acc[2] = fmaf(a, w.z, acc[2]);
-    acc[3] = fmaf(a, w.w, acc[3]);
+                                           const float* __restrict__ be, int act, float* __restrict__ Y, int lane) {
+  float a0 = 0.f, a1 = 0.f;
+  const float2* w2 = reinterpret_cast<const float2*>(Wq) + lane;
+  const float4* x4 = reinterpret_cast<const float4*>(X);
+#pragma unroll 4
+  for (int q = 0; q < (K4 >> 2); ++q) {
+    const float4 x = x4[q];
+    const float2 wa = w2[(4 * q + 0) * 32], wb = w2[(4 * q + 1) * 32], wc = w2[(4 * q + 2) * 32], wd = w2[(4 * q + 3) * 32];
+    a0 = fmaf(x.x, wa.x, a0); a1 = fmaf(x.x, wa.y, a1);
+    a0 = fmaf(x.y, wb.x, a0); a1 = fmaf(x.y, wb.y, a1);
+    a0 = fmaf(x.z, wc.x, a0); a1 = fmaf(x.z, wc.y, a1);
+    a0 = fmaf(x.w, wd.x, a0); a1 = fmaf(x.w, wd.y, a1);
   }
-  float s = 0.f;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) { acc[j] = act_fwd(acc[j] + b[tx + 16 * j], act); s += acc[j]; }
-  const float m = sum16(s) * (1.0f / 64.f);
-  float v = 0.f;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) { const float d = acc[j] - m; v = fmaf(d, d, v); }
-  const float rs = 1.0f / sqrtf(sum16(v) * (1.0f / 64.f) + kLnEps);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int c = tx + 16 * j;
-    Y[c * 2 + rr] = fmaf((acc[j] - m) * rs, gm[c], be[c]);
-  }
+  a0 = act_fwd(a0 + b[lane], act);
+  a1 = act_fwd(a1 + b[lane + 32], act);
+  const float m = warp_sum(a0 + a1) * (1.0f / 64.f);
+  const float d0 = a0 - m, d1 = a1 - m;
+  const float rs = 1.0f / sqrtf(warp_sum(fmaf(d1, d1, d0 * d0)) * (1.0f / 64.f) + kLnEps);
+  Y[lane] = fmaf(d0 * rs, gm[lane], be[lane]);
+  Y[lane + 32] = fmaf(d1 * rs, gm[lane + 32], be[lane + 32]);
   __syncwarp();
 }
 
 struct FastCtx {
   const float* sW;      // weight image in shared memory
   FastImg f;
-  float* bufA;          // this warp's scratch: [64][2]
-  float* bufB;          // [64][2]
-  float* lgs;           // [2][32] logits of the two rows
+  float* bufA;          // this warp's scratch: 64 floats
+  float* bufB;          // 64 floats
 };
 
-// One rollout step of net `which` for the row of this half-warp (storage row g, or -1 past the end).  xin: the lane's
-// input features k = tx + 16 i.  PolStep as in the tile path (policy_step.cu); recurrent fields are unused here.
+// One rollout step of net `which` for the row of this warp (storage row g, or -1 past the end).  xin: the lane's input
+// features k = lane and lane + 32.  PolStep as in the tile path (policy_step.cu); recurrent fields are unused here.
 __device__ __forceinline__ void fast_step(const NetDev& n, int which, const FastCtx& c, const PolStep& p,
-                                          const float (&xin)[4], int g, int tx, int rr, int lane, int n_avail,
-                                          int deterministic, uint64_t rng_seed, long long& t_last, int tid) {
+                                          const float (&xin)[2], int g, int lane, int n_avail, int deterministic,
+                                          uint64_t rng_seed, long long& t_last, int tid) {
   const int in = n.in_dim;
   const FastImg& f = c.f;
   const float* sW = c.sW;
   // ---- the insert of this slot: rows, availability, masks ----
   if (g >= 0) {
     if (p.in_copy) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { const int k = tx + 16 * i; if (k < in) p.in_copy[(size_t)g * in + k] = xin[i]; }
+      if (lane < in) p.in_copy[(size_t)g * in + lane] = xin[0];
+      if (lane + 32 < in) p.in_copy[(size_t)g * in + lane + 32] = xin[1];
     }
     if (which == 0 && p.avail_copy && p.avail)
-      for (int k = tx; k < n_avail; k += 16) p.avail_copy[(size_t)g * n_avail + k] = p.avail[(size_t)g * n_avail + k];
-    if (which == 0 && p.masks_copy && tx == 0)
+      for (int k = lane; k < n_avail; k += 32) p.avail_copy[(size_t)g * n_avail + k] = p.avail[(size_t)g * n_avail + k];
+    if (which == 0 && p.masks_copy && lane == 0)
       p.masks_copy[g] = p.done_prev ? (p.done_prev[g] != 0.f ? 0.f : 1.f) : p.masks[g];
   }
   if (!p.forward) return;
   POL_T(0);
   // ---- feature LayerNorm (mlp.py:47-56) straight from registers ----
   {
-    float y[4];
+    const bool v0 = lane < in, v1 = lane + 32 < in;
+    float y0 = xin[0], y1 = xin[1];
     if (n.use_fn) {
-      float s = 0.f;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) s += (tx + 16 * i < in) ? xin[i] : 0.f;
-      const float m = sum16(s) / (float)in;
-      float v = 0.f;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { const float d = xin[i] - m; if (tx + 16 * i < in) v = fmaf(d, d, v); }
-      const float rs = 1.0f / sqrtf(sum16(v) / (float)in + kLnEps);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int k = tx + 16 * i;
-        y[i] = k < in ? fmaf((xin[i] - m) * rs, sW[f.fn_w + k], sW[f.fn_b + k]) : 0.f;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) y[i] = xin[i];
+      const float m = warp_sum((v0 ? xin[0] : 0.f) + (v1 ? xin[1] : 0.f)) / (float)in;
+      const float d0 = v0 ? xin[0] - m : 0.f, d1 = v1 ? xin[1] - m : 0.f;
+      const float rs = 1.0f / sqrtf(warp_sum(fmaf(d1, d1, d0 * d0)) / (float)in + kLnEps);
+      y0 = v0 ? fmaf(d0 * rs, sW[f.fn_w + lane], sW[f.fn_b + lane]) : 0.f;
+      y1 = v1 ? fmaf(d1 * rs, sW[f.fn_w + lane + 32], sW[f.fn_b + lane + 32]) : 0.f;
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { const int k = tx + 16 * i; if (k < in) c.bufA[k * 2 + rr] = y[i]; }
+    if (lane < f.K1) c.bufA[lane] = v0 ? y0 : 0.f;
+    if (lane + 32 < f.K1) c.bufA[lane + 32] = v1 ? y1 : 0.f;
     __syncwarp();
   }
   const int act = n.use_relu ? ACT_RELU : ACT_TANH;
-  fast_layer(c.bufA, in, sW + f.w1, sW + f.b1, sW + f.g1, sW + f.be1, act, c.bufB, tx, rr);
+  fast_layer(c.bufA, f.K1, sW + f.w1, sW + f.b1, sW + f.g1, sW + f.be1, act, c.bufB, lane);
   float* X = c.bufB;
   float* Y = c.bufA;
   for (int l = 0; l < n.layer_n; ++l) {
-    fast_layer(X, 64, sW + f.w2[l], sW + f.b2[l], sW + f.g2[l], sW + f.be2[l], act, Y, tx, rr);
+    fast_layer(X, 64, sW + f.w2[l], sW + f.b2[l], sW + f.g2[l], sW + f.be2[l], act, Y, lane);
     float* t = X; X = Y; Y = t;
   }
   POL_T(1);
-  // ---- heads: lane tx owns outputs tx and tx + 16 (k-sequential accumulation like tile_mm) ----
+  // ---- heads: lane a owns output a ----
   const int Atot = n.head_total;
-  float lg[2] = {0.f, 0.f};
-#pragma unroll
-  for (int s = 0; s < 2; ++s) {
-    const int a = tx + 16 * s;
-    if (a < Atot) {
-      float acc = 0.f;
-      const float* w = sW + f.wh + a;
-#pragma unroll 8
-      for (int k = 0; k < 64; ++k) acc = fmaf(X[k * 2 + rr], w[k * f.AP], acc);
-      lg[s] = acc + sW[f.bh + a];
+  float lg = 0.f;
+  if (lane < Atot) {
+    float acc = 0.f;
+    const float* w = sW + f.wh + lane;
+    const float4* x4 = reinterpret_cast<const float4*>(X);
+    const int AP = f.AP;
+#pragma unroll 4
+    for (int q = 0; q < 16; ++q) {
+      const float4 x = x4[q];
+      acc = fmaf(x.x, w[(4 * q + 0) * AP], acc);
+      acc = fmaf(x.y, w[(4 * q + 1) * AP], acc);
+      acc = fmaf(x.z, w[(4 * q + 2) * AP], acc);
+      acc = fmaf(x.w, w[(4 * q + 3) * AP], acc);
     }
+    lg = acc + sW[f.bh + lane];
   }
+  __syncwarp();
   POL_T(3);
   if (which == 1) {
-    if (tx == 0 && g >= 0 && p.values) p.values[g] = lg[0];
+    if (lane == 0 && g >= 0 && p.values) p.values[g] = lg;
     POL_T(4);
     return;
   }
-  c.lgs[rr * 32 + tx] = lg[0];
-  c.lgs[rr * 32 + tx + 16] = lg[1];
-  __syncwarp();
   const float* av = (p.avail && n.n_heads == 1 && g >= 0) ? p.avail + (size_t)g * n_avail : nullptr;
   const uint64_t ctr = p.rng_ctr + (uint64_t)(g < 0 ? 0 : g);
-  const int half = lane & 16;
   int off = 0;
   for (int k = 0; k < n.n_heads; ++k) {
     const int A = n.head_dim[k];
-    float l[2], e[2];
-    bool valid[2];
+    const int j = lane - off;
+    const bool valid = j >= 0 && j < A && g >= 0;
+    float l = valid ? lg : -INFINITY;
+    if (valid && av && av[j] == 0.f) l = -1e10f;                          // distributions.py:66-67
+    float mx = l;
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      const int j = tx + 16 * s;
-      valid[s] = j < A && g >= 0;
-      l[s] = valid[s] ? c.lgs[rr * 32 + off + j] : -INFINITY;
-      if (valid[s] && av && av[j] == 0.f) l[s] = -1e10f;                  // distributions.py:66-67
-    }
-    float mx = fmaxf(l[0], l[1]);
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    e[0] = valid[0] ? expf(l[0] - mx) : 0.f;
-    e[1] = valid[1] ? expf(l[1] - mx) : 0.f;
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float e = valid ? expf(l - mx) : 0.f;
     float se = 0.f;
-    for (int j = 0; j < A; ++j) {                                         // serial order: same rounding as head_lse
-      const float e0 = __shfl_sync(0xffffffffu, e[0], half | (j & 15));
-      const float e1 = __shfl_sync(0xffffffffu, e[1], half | (j & 15));
-      se += (j < 16) ? e0 : e1;
-    }
+    for (int jj = 0; jj < A; ++jj) se += __shfl_sync(0xffffffffu, e, off + jj);   // serial order: head_lse's rounding
     const float lse = mx + logf(se);
     float bestv = -INFINITY, best_lp = 0.f;
     int best = 1 << 30;
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      if (valid[s]) {
-        const int j = tx + 16 * s;
-        const float lp = l[s] - lse;
-        const float pr = expf(lp);
-        float score = pr;
-        if (!deterministic) {
-          float q;
-          if (p.exp_noise) {
-            q = p.exp_noise[(size_t)g * Atot + off + j];
-          } else {
-            const uint4 rnd = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)(k * 64 + (j >> 2)), 0u),
-                                            make_uint2((uint32_t)rng_seed, (uint32_t)(rng_seed >> 32)));
-            const uint32_t x = (j & 3) == 0 ? rnd.x : ((j & 3) == 1 ? rnd.y : ((j & 3) == 2 ? rnd.z : rnd.w));
-            q = -logf(((float)x + 0.5f) * 2.3283064365386963e-10f);
-          }
-          score = pr / q;                                                 // torch multinomial: argmax(p / Exp(1))
+    if (valid) {
+      const float lp = l - lse;
+      const float pr = expf(lp);
+      float score = pr;
+      if (!deterministic) {
+        float q;
+        if (p.exp_noise) {
+          q = p.exp_noise[(size_t)g * Atot + off + j];
+        } else {
+          const uint4 rnd = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)(k * 64 + (j >> 2)), 0u),
+                                          make_uint2((uint32_t)rng_seed, (uint32_t)(rng_seed >> 32)));
+          const uint32_t x = (j & 3) == 0 ? rnd.x : ((j & 3) == 1 ? rnd.y : ((j & 3) == 2 ? rnd.z : rnd.w));
+          q = -logf(((float)x + 0.5f) * 2.3283064365386963e-10f);
         }
-        if (score > bestv) { bestv = score; best = j; best_lp = lp; }
+        score = pr / q;                                                   // torch multinomial: argmax(p / Exp(1))
       }
+      bestv = score; best = j; best_lp = lp;
     }
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {                                     // first maximum wins, like the serial scan
+    for (int o = 16; o > 0; o >>= 1) {                                    // first maximum wins, like the serial scan
       const float ov = __shfl_xor_sync(0xffffffffu, bestv, o);
       const int oj = __shfl_xor_sync(0xffffffffu, best, o);
       const float olp = __shfl_xor_sync(0xffffffffu, best_lp, o);
       if (ov > bestv || (ov == bestv && oj < best)) { bestv = ov; best = oj; best_lp = olp; }
     }
     if (best == (1 << 30)) best = 0;
-    if (tx == 0 && g >= 0) {
+    if (lane == 0 && g >= 0) {
       const int as = n.n_heads;
       if (p.actions) p.actions[(size_t)g * as + k] = (float)best;
       if (p.actions_i64) p.actions_i64[(size_t)g * as + k] = (int64_t)best;
@@ -287,7 +260,7 @@ __device__ __forceinline__ FastCtx fast_setup(const NetDev& n, float* smem, cons
   c.f = make_fast_img(n);
   c.sW = smem;
   float* ws = smem + c.f.total + (tid >> 5) * kFWarpScratch;
-  c.bufA = ws; c.bufB = ws + 128; c.lgs = ws + 256;
+  c.bufA = ws; c.bufB = ws + 64;
   if (tid == 0) {
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(wbar);
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
@@ -307,25 +280,22 @@ __device__ __forceinline__ FastCtx fast_setup(const NetDev& n, float* smem, cons
   return c;
 }
 
-__device__ __forceinline__ void load_row_lane(const float* __restrict__ src, int g, int in, int tx, float (&x)[4]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int k = tx + 16 * i;
-    x[i] = (g >= 0 && k < in) ? __ldg(src + (size_t)g * in + k) : 0.f;
-  }
+__device__ __forceinline__ void load_row_lane(const float* __restrict__ src, int g, int in, int lane, float (&x)[2]) {
+  x[0] = (g >= 0 && lane < in) ? __ldg(src + (size_t)g * in + lane) : 0.f;
+  x[1] = (g >= 0 && lane + 32 < in) ? __ldg(src + (size_t)g * in + lane + 32) : 0.f;
 }
 
 __global__ void __launch_bounds__(kFT)
 policy_step_fast_kernel(const NetDev na, const NetDev nc, const PolArgs a, int first_net) {
   extern __shared__ __align__(16) float smem[];
   __shared__ uint64_t wbar;
-  const int tid = threadIdx.x, lane = tid & 31, tx = lane & 15, rr = lane >> 4;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int which = first_net + blockIdx.y;
   const NetDev& n = which == 0 ? na : nc;
-  const int row = blockIdx.x * kFR + (tid >> 5) * 2 + rr;
+  const int row = blockIdx.x * kFR + (tid >> 5);
   const int g = row < a.n_rows ? row : -1;
-  float x[4];
-  load_row_lane(a.in[which], g, n.in_dim, tx, x);                 // in flight while the weights arrive
+  float x[2];
+  load_row_lane(a.in[which], g, n.in_dim, lane, x);                 // in flight while the weights arrive
   const FastCtx c = fast_setup(n, smem, a.image[which], &wbar, tid);
   PolStep p;
   p.in = nullptr; p.in_copy = nullptr; p.h_in = nullptr; p.masks = a.masks; p.done_prev = nullptr;
@@ -334,7 +304,7 @@ policy_step_fast_kernel(const NetDev na, const NetDev nc, const PolArgs a, int f
   p.rng_ctr = (!a.exp_noise && !a.deterministic && which == 0) ? *a.rng_offset : 0ull;
   p.values = a.values; p.actions = a.actions; p.actions_i64 = a.actions_i64; p.logp = a.logp; p.forward = true;
   long long t_last = clock64();
-  fast_step(n, which, c, p, x, g, tx, rr, lane, a.n_avail, a.deterministic, a.rng_seed, t_last, tid);
+  fast_step(n, which, c, p, x, g, lane, a.n_avail, a.deterministic, a.rng_seed, t_last, tid);
 }
 
 // The T collect steps + inserts of one iteration for feed-forward policies (see rollout_persistent_kernel for the
@@ -343,24 +313,24 @@ __global__ void __launch_bounds__(kFT)
 rollout_fast_kernel(const NetDev na, const NetDev nc, const RolloutArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ uint64_t wbar;
-  const int tid = threadIdx.x, lane = tid & 31, tx = lane & 15, rr = lane >> 4;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int which = blockIdx.y;
   const NetDev& n = which == 0 ? na : nc;
   const int E = a.E, T = a.T, in = n.in_dim;
-  const int row = blockIdx.x * kFR + (tid >> 5) * 2 + rr;
+  const int row = blockIdx.x * kFR + (tid >> 5);
   const int g = row < E ? row : -1;
   float* store_in = which == 0 ? a.obs : a.share_obs;
   const float* feed_in = which == 0 ? a.f_obs : a.f_share;
-  float x[4];
-  load_row_lane(store_in, g, in, tx, x);                          // slot 0
+  float x[2];
+  load_row_lane(store_in, g, in, lane, x);                          // slot 0
   const FastCtx c = fast_setup(n, smem, a.image[which], &wbar, tid);
   const int Atot = na.head_total;
   const uint64_t rng0 = (!a.exp_noise && which == 0) ? *a.rng_offset : 0ull;
   long long t_last = clock64();
 #pragma unroll 1
   for (int t = 0; t <= T; ++t) {
-    float xn[4] = {0.f, 0.f, 0.f, 0.f};
-    if (t < T) load_row_lane(feed_in + (size_t)t * E * in, g, in, tx, xn);       // rows of step t + 1
+    float xn[2] = {0.f, 0.f};
+    if (t < T) load_row_lane(feed_in + (size_t)t * E * in, g, in, lane, xn);       // rows of step t + 1
     PolStep p;
     p.in = nullptr;
     p.in_copy = t == 0 ? nullptr : store_in + (size_t)t * E * in;
@@ -378,13 +348,12 @@ rollout_fast_kernel(const NetDev na, const NetDev nc, const RolloutArgs a) {
     p.logp = t < T ? a.logp + (size_t)t * E * na.n_heads : nullptr;
     p.forward = (t < T) || which == 1;                            // slot T: only the critic's bootstrap value
     // rewards / active masks of env step t-1 -> slot t-1 / t (the rest of insert), by the actor's lane 0 of the row
-    if (which == 0 && t > 0 && tx == 0 && g >= 0) {
+    if (which == 0 && t > 0 && lane == 0 && g >= 0) {
       a.rewards[(size_t)(t - 1) * E + g] = a.f_rew[(size_t)(t - 1) * E + g];
       if (a.f_active) a.active[(size_t)t * E + g] = a.f_active[(size_t)(t - 1) * E + g];
     }
-    fast_step(n, which, c, p, x, g, tx, rr, lane, a.n_avail, 0, a.rng_seed, t_last, tid);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) x[i] = xn[i];
+    fast_step(n, which, c, p, x, g, lane, a.n_avail, 0, a.rng_seed, t_last, tid);
+    x[0] = xn[0]; x[1] = xn[1];
   }
 }
 

@@ -165,6 +165,8 @@ __global__ void __launch_bounds__(256)
 tc_unfold_kernel(const NetDev n, const float* __restrict__ p, const float* __restrict__ raw, float* __restrict__ g,
                  float* __restrict__ sumsq_part) {
   __shared__ float part_g[16][17], part_b[16][17], sred[8];
+  pdl_trigger();
+  pdl_wait();
   const TcImage m = make_tc_image(n);
   const TcRaw R = make_tc_raw(m);
   const int tid = threadIdx.x, kx = tid & 15, og = tid >> 4;
@@ -238,6 +240,8 @@ tc_unfold_kernel(const NetDev n, const float* __restrict__ p, const float* __res
 }
 
 __global__ void __launch_bounds__(256) pack_tc_kernel(const NetDev n, const float* __restrict__ p, float* __restrict__ img) {
+  pdl_trigger();
+  pdl_wait();
   const TcImage m = make_tc_image(n);
   const int H = 64;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m.total; i += gridDim.x * blockDim.x) {
@@ -587,7 +591,7 @@ __global__ void __launch_bounds__(kTCThreads, 1)
 update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const float* __restrict__ image, const BatchDev b,
                      const LossDev L, const double* __restrict__ norm_stats, const double* __restrict__ adv_stats,
                      const float* __restrict__ vn_state, float* __restrict__ grad_part, double* __restrict__ loss_out,
-                     int n_tiles, uint32_t tmem_cols) {
+                     int n_tiles, uint32_t tmem_cols, int early_image) {
   extern __shared__ __align__(1024) float smem[];
   __shared__ double sred[2 * 32];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -611,7 +615,10 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
   constexpr int LGLD = kTM + 4;
 
   TC_STAMP(0);
-  // ---- one-time setup: barriers, TMEM, weight image by TMA, constant rows of the transposed tiles ----
+  pdl_trigger();
+  // ---- one-time setup: barriers, TMEM, constant rows of the transposed tiles.  Nothing up to the end of the first
+  //      tile's gather depends on the previous optimiser step: under programmatic dependent launch this part overlaps
+  //      the tail kernels of that step (pdl_wait() sits right before the weight image is fetched). ----
   if (tid == 0) {
     mbar_init(bar_w, 1);
     mbar_init(bar_m, 1);
@@ -628,7 +635,7 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  if (tid == 0) {
+  if (early_image && tid == 0) {           // normal launch: the image is final, fetch it behind the first gather
     mbar_expect_tx(bar_w, (uint32_t)(im.total * sizeof(float)));
     tma_bulk_g2s(sImg, image, (uint32_t)(im.total * sizeof(float)), bar_w);
   }
@@ -637,7 +644,7 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
   const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
   const uint32_t cMy = cD + 32 * wg;                   // my 32 columns of the 64-wide accumulator
 
-  const LossConsts lc = make_loss_consts(n, L, norm_stats, adv_stats, vn_state);
+  LossConsts lc;
   double acc[3] = {0.0, 0.0, 0.0};
   uint32_t phase = 0;
   bool first_tile = true;
@@ -709,6 +716,15 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
         }
       }
       tmem_st_wait();
+    }
+    if (first_tile) {
+      // from here on the kernel reads what the previous step produced: weight image, ValueNorm state
+      pdl_wait();
+      if (!early_image && tid == 0) {
+        mbar_expect_tx(bar_w, (uint32_t)(im.total * sizeof(float)));
+        tma_bulk_g2s(sImg, image, (uint32_t)(im.total * sizeof(float)), bar_w);
+      }
+      lc = make_loss_consts(n, L, norm_stats, adv_stats, vn_state);
     }
     TC_STAMP(2);
     fence_async_smem();
@@ -896,6 +912,8 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
   }
   // ---- dump the raw (still folded) accumulators into this CTA's slot; they are summed over slots and unfolded once
   //      by mappo_update_finish (tc_unfold_kernel).  Warpgroup 0 dumps G2, warpgroup 1 dumps G1 and Gh. ----
+  pdl_wait();                  // (a CTA without tiles has not waited yet; a second wait returns at once)
+  if (first_tile) lc = make_loss_consts(n, L, norm_stats, adv_stats, vn_state);
   if (!b.eval_only) {
     const TcRaw R = make_tc_raw(im);
     float* g = grad_part + (size_t)blockIdx.x * R.total;
@@ -975,7 +993,7 @@ int update_mlp_tc_slot_floats(const NetDev& n) { return make_tc_raw(make_tc_imag
 // sum of the raw slots is in `raw_sum` -> flat gradient + sum(g^2) (one partial)
 int update_mlp_tc_unfold_launch(const NetDev& n, const float* params, const float* raw_sum, float* grad,
                                 float* sumsq_part, cudaStream_t st) {
-  tc_unfold_kernel<<<dim3(4, 3), 256, 0, st>>>(n, params, raw_sum, grad, sumsq_part);       // 12 partial sums of squares
+  launch_chain(tc_unfold_kernel, dim3(4, 3), dim3(256), 0, st, n, params, raw_sum, grad, sumsq_part);       // 12 partial sums of squares
   return check_launch("tc_unfold_kernel");
 }
 
@@ -995,7 +1013,7 @@ int update_mlp_tc_launch(const NetDev& n, const float* params, const BatchDev& b
   const size_t bytes = (size_t)sm.total * sizeof(float) + 1024;
   if (bytes > 227 * 1024) { set_error("update_mlp_tc: %zu B shared memory > 227 KB", bytes); return MAPPO_ERR_UNSUPPORTED; }
   if (!image_ready) {        // the fused optimiser tail of the previous update (tc_finish_kernel) leaves it ready
-    pack_tc_kernel<<<(im.total + 255) / 256, 256, 0, st>>>(n, params, image);      // one element per thread
+    launch_chain(pack_tc_kernel, dim3((im.total + 255) / 256), dim3(256), 0, st, n, params, image);      // one element per thread
     const int rc = check_launch("pack_tc_kernel");
     if (rc) return rc;
   }
@@ -1007,8 +1025,9 @@ int update_mlp_tc_launch(const NetDev& n, const float* params, const BatchDev& b
   }
   const int n_tiles = (b.n_rows + kTM - 1) / kTM;
   const uint32_t cols = 512u;          // accumulators [0,272) + parked xhat0 [272,344): one CTA per SM owns all of TMEM
-  update_mlp_tc_kernel<<<n_slots, kTCThreads, bytes, st>>>(n, params, image, b, L, norm_stats, adv_stats, vn_state, grad_part,
-                                                    loss_out, n_tiles, cols);
+  const bool pdl = pdl_mode() >= 2;
+  launch_chain_if(pdl, update_mlp_tc_kernel, dim3(n_slots), dim3(kTCThreads), bytes, st, n, params, image, b, L, norm_stats,
+                  adv_stats, vn_state, grad_part, loss_out, n_tiles, cols, pdl ? 0 : 1);
   return check_launch("update_mlp_tc_kernel");
 }
 
