@@ -181,7 +181,7 @@ def run_gpu(a):
     trainer = R_MAPPO(args, policy, device=dev)
     buf = SharedReplayBuffer(args, cfg.num_agents, obs_s, share_s, act_s)
     feed = O.make_feed(cfg, seed=100 + rank)               # each rank owns its own 128 rollout threads
-    eng = RolloutEngine(args, policy, trainer, buf, rng="device", seed=1 + rank)
+    eng = RolloutEngine(args, policy, trainer, buf, rng="device", seed=1 + rank, share_obs_from_obs=True)
     eng.stage_feed(feed)
     eng.upload()
     torch.cuda.synchronize()
@@ -246,7 +246,7 @@ def run_gpu(a):
         torch.cuda.synchronize()
         _lib.load().mappo_debug_tc_timing(t)
         names = ["setup", "S1", "fc1_mma", "S3", "fc2_mma", "S5", "head_mma", "S7_loss", "dx2_Gh_mma", "S9", "dx1_G2_mma",
-                 "S11", "G1_mma", "unfold", "tail"]
+                 "S11", "dump_G2", "G1_wait", "tail"]
         breakdown["tc_tile_cycles_warm"] = {nm: int(t[i + 1] - t[i]) for i, nm in enumerate(names)}
         breakdown["tc_tile_cycles_warm"]["total"] = int(t[15] - t[0])
     # ---- the dominant kernel, timed live with CUDA events on its own stream (eager pass, one train()) ----
@@ -282,7 +282,9 @@ def run_gpu(a):
                                                                "one-shot peer-memory all-reduce kernel over NVLink, in-graph"
                                                                if getattr(trainer, "_p2p", None) is not None else
                                                                "NCCL all-reduce via torch.distributed between graph segments"),
-                                                                "rng": "device (Philox sampling, Feistel permutations)"},
+                                                                "rng": "device (Philox sampling, Feistel permutations)",
+                                                "rollout": "persistent kernel, one launch per iteration" if eng.persistent_rollout else "one launch per env step",
+                                                "h2d": "obs, rewards, dones (share_obs = concat of the thread's agents' obs is formed on the device)" if eng.share_from_obs else "obs, share_obs, rewards, dones"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": eng.h2d_bytes(), "d2h_bytes_per_step": 48,
                         "ms_per_step": e2e_ms_max / a.steps},
                 "gpu_launches": launches,
@@ -294,7 +296,10 @@ def run_gpu(a):
                              "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1590",
                              "avg_launch_ms": kt["avg_ms"], "launches_timed": kt["n"],
                              "algorithmic_gflop_per_launch": (fa + fc) / 2 / 1e9,
-                             "kernel_share_of_step": kt["avg_ms"] * 2 * cfg.ppo_epoch / (ms_max / a.steps)},
+                             # the actor and the critic chain run concurrently (two graph branches), each with one
+                             # update kernel per optimiser step: share of the step's critical path = one chain's kernels
+                             "kernel_share_of_step": kt["avg_ms"] * cfg.ppo_epoch * cfg.num_mini_batch / (ms_max / a.steps),
+                             "kernel_time_sum_over_step": kt["avg_ms"] * 2 * cfg.ppo_epoch * cfg.num_mini_batch / (ms_max / a.steps)},
                 "clocks": clocks, "wall_s_timed_region": t_wall, "phase_breakdown_ms": breakdown,
                 "train_info_last": info}
         if cpu_rate is not None:
@@ -324,8 +329,9 @@ def time_update_kernel(eng, cfg, flush):
             return rc
 
     lib = core._lib.load()
-    saved_graph = eng.graph
+    saved_graph, saved_overlap = eng.graph, eng.trainer.overlap_nets
     eng.graph = None
+    eng.trainer.overlap_nets = False          # one launch at a time: the events see this kernel alone on the stream
     try:
         lib.mappo_update_fwd_bwd = Timed()
         flush.zero_()
@@ -333,7 +339,7 @@ def time_update_kernel(eng, cfg, flush):
         torch.cuda.synchronize()
     finally:
         lib.mappo_update_fwd_bwd = orig
-        eng.graph = saved_graph
+        eng.graph, eng.trainer.overlap_nets = saved_graph, saved_overlap
     ms = [s.elapsed_time(e) for s, e in pairs]
     return {"avg_ms": sum(ms) / max(len(ms), 1), "n": len(ms)}
 

@@ -72,8 +72,6 @@ typedef struct mappo_loss_cfg {
   int32_t use_valuenorm;       /* normalise return targets with the ValueNorm state */
   int32_t update_actor;        /* ppo_update(sample, update_actor) r_mappo.py:91,145 */
   int32_t gemm_mode;           /* MAPPO_GEMM_FP32 (exact fp32 FFMA tiles) or MAPPO_GEMM_TF32 (tcgen05 tensor cores) */
-  int32_t weight_image_ready;  /* TF32 only: the workspace already holds the folded weight image of the CURRENT
-                                * parameters (left there by mappo_update_step_fused) -- skip the pack kernel */
 } mappo_loss_cfg_t;
 
 #define MAPPO_GEMM_FP32 0
@@ -141,7 +139,11 @@ int32_t mappo_policy_step(const mappo_net_desc_t* actor_desc, const float* actor
  * interact, so each CTA keeps its 32 rows, the weights and the recurrent state on chip and walks t = 0..T.
  * Storage pointers address slot 0 (slots are E*dim floats apart); f_* are the staged env outputs, index t = what the env
  * returned after step t (written to slot t+1; rewards to slot t).  Sampling as in mappo_policy_step (per-step noise
- * [T, E, sum A] or Philox; the device offset advances by T*E). */
+ * [T, E, sum A] or Philox; the device offset advances by T*E).
+ * f_share may be NULL for feed-forward nets when share_obs is the concatenation of the obs of the agents of a rollout
+ * thread (use_centralized_V in the MPE runner, mpe_runner.py:133-135; requires share_dim = k * obs_dim and rows ordered
+ * thread-major): the critic then reads its rows straight from f_obs and only obs needs staging (4x fewer H2D bytes
+ * for 3 agents); the share_obs storage slots are still written. */
 int32_t mappo_rollout_persistent(const mappo_net_desc_t* actor_desc, const float* actor_params, const float* actor_image,
                                  const mappo_net_desc_t* critic_desc, const float* critic_params, const float* critic_image,
                                  float* obs, float* share_obs, float* h_actor, float* h_critic, float* masks, float* avail,
@@ -283,16 +285,6 @@ int32_t mappo_update_slot_floats(const mappo_net_desc_t* desc, int32_t gemm_mode
 int32_t mappo_update_finish(const mappo_net_desc_t* desc, const float* params, const float* grad_part, int32_t n_slots,
                             int32_t gemm_mode, float* grad, float* sumsq_part, int32_t* n_blocks_out, float* workspace,
                             void* stream);
-/* TF32 build, single GPU: everything of ppo_update after the backward pass (r_mappo.py:141-167: clip_grad_norm_,
- * optimizer.step) in two launches -- slot reduction, then ONE single-CTA kernel that unfolds the folded accumulators into
- * `grad`, takes the global norm, clips, applies Adam to `params` and leaves the folded weight image of the NEW
- * parameters in the workspace (next mappo_update_fwd_bwd: loss.weight_image_ready = 1).  vn_state + next_norm_stats
- * (both nullable): also applies the ValueNorm.update of the NEXT minibatch (its mappo_minibatch_stats) so the critic
- * chain needs no separate mappo_valuenorm_update launch.  MAPPO_ERR_UNSUPPORTED when mappo_tf32_supported() is 0. */
-int32_t mappo_update_step_fused(const mappo_net_desc_t* desc, float* params, const float* grad_part, int32_t n_slots,
-                                float* grad, float* exp_avg, float* exp_avg_sq, const float* lr_dev, int32_t* step_dev,
-                                float eps, float max_grad_norm, int32_t use_max_grad_norm, double* grad_norm_out,
-                                float* workspace, float* vn_state, const double* next_norm_stats, void* stream);
 int32_t mappo_grad_reduce(const float* grad_part, int32_t n_slots, int32_t n_params, float* grad,
                           float* sumsq_part, int32_t* n_sumsq_blocks_out, void* stream);
 /* Per-block sums of squares of an already reduced (e.g. all-reduced) gradient vector. */

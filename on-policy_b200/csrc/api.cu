@@ -22,11 +22,6 @@ void set_error(const char* fmt, ...) {
 
 static std::atomic<long long> g_launches{0};
 
-int pdl_mode() {
-  static const int mode = [] { const char* e = getenv("MAPPO_B200_PDL"); return e ? atoi(e) : 0; }();
-  return mode;
-}
-
 // every kernel launch of the library reports here under its kernel name ("x: attribute" strings are not launches)
 int check_launch(const char* what) {
   const cudaError_t e = cudaGetLastError();
@@ -94,9 +89,7 @@ int update_mlp_tc_unfold_launch(const NetDev&, const float*, const float*, float
 int64_t update_mlp_tc_workspace_floats(const NetDev& n);
 int update_mlp_tc_slots(const NetDev& n, int n_rows, int sm_count);
 int update_mlp_tc_launch(const NetDev&, const float*, const BatchDev&, const LossDev&, const double*, const double*,
-                         const float*, float*, int, double*, float*, bool, cudaStream_t);
-int update_mlp_tc_finish_launch(const NetDev&, float*, const float*, float*, float*, float*, const float*, int*, float, float,
-                                int, double*, float*, float*, const double*, cudaStream_t);
+                         const float*, float*, int, double*, float*, cudaStream_t);
 int update_gru_slots(const NetDev& n, int n_rows, int seq_len, int sm_count);
 int64_t update_gru_workspace_floats(const NetDev& n, int n_rows);
 int update_gru_launch(const NetDev&, const float*, const BatchDev&, const LossDev&, const double*, const double*,
@@ -214,8 +207,13 @@ int32_t mappo_rollout_persistent(const mappo_net_desc_t* ad, const float* ap, co
   int rc = validate_desc(ad); if (rc) return rc;
   rc = validate_desc(cd); if (rc) return rc;
   if (ad->is_critic || !cd->is_critic) { set_error("rollout_persistent: actor/critic descriptors swapped"); return MAPPO_ERR_INVALID; }
-  if (!ap || !cp || !obs || !share_obs || !masks || !value_preds || !actions || !logp || !rewards || !f_obs || !f_share ||
+  if (!ap || !cp || !obs || !share_obs || !masks || !value_preds || !actions || !logp || !rewards || !f_obs ||
       !f_rew || !f_done || T <= 0 || E <= 0) { set_error("rollout_persistent: NULL / bad argument"); return MAPPO_ERR_INVALID; }
+  int share_agents = 0;
+  if (!f_share) {             // centralized V in the MPE runner's sense: share_obs = all agents' obs of the thread
+    if (cd->in_dim % ad->in_dim != 0 || E % (cd->in_dim / ad->in_dim) != 0) { set_error("rollout_persistent: f_share is NULL but share_obs is not a concatenation of obs rows (%d vs %d, E = %d)", cd->in_dim, ad->in_dim, E); return MAPPO_ERR_INVALID; }
+    share_agents = cd->in_dim / ad->in_dim;
+  }
   if ((ad->recurrent && !h_actor) || (cd->recurrent && !h_critic)) { set_error("rollout_persistent: recurrent net without state storage"); return MAPPO_ERR_INVALID; }
   if (!exp_noise && !rng_offset_dev) { set_error("rollout_persistent: sampling needs exp_noise or rng_offset_dev"); return MAPPO_ERR_INVALID; }
   if ((avail != nullptr) != (f_avail != nullptr)) { set_error("rollout_persistent: avail storage and staged avail must come together"); return MAPPO_ERR_INVALID; }
@@ -227,6 +225,7 @@ int32_t mappo_rollout_persistent(const mappo_net_desc_t* ad, const float* ap, co
   a.f_obs = f_obs; a.f_share = f_share; a.f_rew = f_rew; a.f_done = f_done; a.f_active = f_active; a.f_avail = f_avail;
   a.exp_noise = exp_noise; a.rng_seed = rng_seed; a.rng_offset = rng_offset_dev; a.T = T; a.E = E;
   a.n_avail = ad->head_dim[0];
+  a.share_agents = share_agents;
   rc = rollout_persistent_launch(make_net_dev(ad), make_net_dev(cd), a, (cudaStream_t)stream);
   if (rc) return rc;
   if (!exp_noise) return counter_add_launch(rng_offset_dev, (uint64_t)T * (uint64_t)E, (cudaStream_t)stream);
@@ -406,23 +405,6 @@ int32_t mappo_update_finish(const mappo_net_desc_t* desc, const float* params, c
   return grad_reduce_launch(grad_part, n_slots, n.g.total, grad, sumsq_part, n_blocks_out, (cudaStream_t)stream);
 }
 
-int32_t mappo_update_step_fused(const mappo_net_desc_t* desc, float* params, const float* grad_part, int32_t n_slots,
-                                float* grad, float* exp_avg, float* exp_avg_sq, const float* lr_dev, int32_t* step_dev,
-                                float eps, float max_grad_norm, int32_t use_max_grad_norm, double* grad_norm_out,
-                                float* workspace, float* vn_state, const double* next_norm_stats, void* stream) {
-  int rc = validate_desc(desc);
-  if (rc) return rc;
-  if (!params || !grad_part || !grad || !exp_avg || !exp_avg_sq || !lr_dev || !step_dev || !workspace || n_slots <= 0) { set_error("update_step_fused: bad arguments"); return MAPPO_ERR_INVALID; }
-  const NetDev n = make_net_dev(desc);
-  if (desc->recurrent || !update_mlp_tc_supported(n)) { set_error("update_step_fused: only built for the tcgen05 MLP path (mappo_tf32_supported)"); return MAPPO_ERR_UNSUPPORTED; }
-  float* raw_sum = workspace + update_mlp_tc_workspace_floats(n);
-  rc = grad_reduce_launch(grad_part, n_slots, update_mlp_tc_slot_floats(n), raw_sum, nullptr, nullptr, (cudaStream_t)stream);
-  if (rc) return rc;
-  return update_mlp_tc_finish_launch(n, params, raw_sum, grad, exp_avg, exp_avg_sq, lr_dev, step_dev, eps, max_grad_norm,
-                                     use_max_grad_norm, grad_norm_out, workspace, vn_state, next_norm_stats,
-                                     (cudaStream_t)stream);
-}
-
 int32_t mappo_update_grad_slots(const mappo_net_desc_t* desc, int32_t n_rows, int32_t gemm_mode) {
   if (validate_desc(desc)) return -1;
   const NetDev n = make_net_dev(desc);
@@ -458,7 +440,7 @@ int32_t mappo_update_fwd_bwd(const mappo_net_desc_t* desc, const float* params, 
   if (loss->gemm_mode == MAPPO_GEMM_TF32) {
     if (!update_mlp_tc_supported(n)) { set_error("update_fwd_bwd: MAPPO_GEMM_TF32 is not built for this net (hidden 64, layer_N 1, in_dim <= 63, MLP only)"); return MAPPO_ERR_UNSUPPORTED; }
     return update_mlp_tc_launch(n, params, b, L, norm_stats, adv_stats, vn_state, grad_part, n_slots, loss_out, workspace,
-                                loss->weight_image_ready != 0, (cudaStream_t)stream);
+                                (cudaStream_t)stream);
   }
   return update_mlp_launch(n, params, b, L, norm_stats, adv_stats, vn_state, grad_part, n_slots, loss_out,
                            (cudaStream_t)stream);

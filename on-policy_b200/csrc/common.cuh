@@ -454,37 +454,6 @@ __device__ __forceinline__ void vn_mean_var(const float* __restrict__ vn, float&
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 
-// Programmatic dependent launch (PDL), OPT-IN (MAPPO_B200_PDL=1|2; measured on c2 inside the iteration graph it is
-// 10-20% SLOWER than plain kernel->kernel edges): kernels of a dependent chain are launched with
-// cudaLaunchAttributeProgrammaticStreamSerialization, call pdl_trigger() as their first statement (the next kernel of
-// the stream may then be scheduled and run its prologue) and pdl_wait() before the first access to anything a
-// predecessor writes or reads (it returns once ALL prerequisite grids have completed and flushed).  Every kernel of a
-// chain waits before it exits, so completion is transitive.  Both are no-ops in a normally launched kernel.
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-int pdl_mode();                // MAPPO_B200_PDL: 0 off, 1 the small tail kernels of an optimiser step, 2 also the update kernel
-inline bool pdl_enabled() { return pdl_mode() > 0; }
-
-// kernel<<<grid, block, smem, st>>>(args...) with the PDL attribute when enabled
-template <typename... KArgs, typename... Args>
-inline void launch_chain_if(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                            Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
-}
-template <typename... KArgs, typename... Args>
-inline void launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
-  launch_chain_if(pdl_enabled(), kern, grid, block, smem, st, args...);
-}
 NetDev make_net_dev(const mappo_net_desc_t* d);
 
 }  // namespace mappo

@@ -39,6 +39,8 @@ struct RolloutArgs {
   uint64_t rng_seed;
   uint64_t* rng_offset;
   int T, E, n_avail;
+  int share_agents;            // > 0: no staged share_obs -- a critic row is the concatenation of the obs rows of the
+                               // `share_agents` agents of its rollout thread (mpe_runner.py:133-135), read from f_obs
 };
 int rollout_persistent_launch(const NetDev& na, const NetDev& nc, const RolloutArgs& a, cudaStream_t st);
 int policy_step_launch(const NetDev* na, const NetDev* nc, const PolArgs& a, cudaStream_t st);

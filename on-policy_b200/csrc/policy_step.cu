@@ -474,6 +474,7 @@ int rollout_persistent_launch(const NetDev& na, const NetDev& nc, const RolloutA
     rollout_fast_kernel<<<dim3((a.E + kFR - 1) / kFR, 2), kFT, fb, st>>>(na, nc, a);
     return check_launch("rollout_fast_kernel");
   }
+  if (a.share_agents > 0) { set_error("rollout: share_obs derived from obs is only built for the feed-forward path"); return MAPPO_ERR_UNSUPPORTED; }
   size_t bytes = 0;
   for (const NetDev* n : {&na, &nc}) {
     if (n->hid != 64) { set_error("rollout: hidden_size %d not built in the fused SIMT path (64 only)", n->hid); return MAPPO_ERR_UNSUPPORTED; }

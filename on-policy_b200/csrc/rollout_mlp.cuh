@@ -330,14 +330,19 @@ rollout_fast_kernel(const NetDev na, const NetDev nc, const RolloutArgs a) {
 #pragma unroll 1
   for (int t = 0; t <= T; ++t) {
     float xn[2] = {0.f, 0.f};
-    if (t < T) load_row_lane(feed_in + (size_t)t * E * in, g, in, lane, xn);       // rows of step t + 1
+    if (t < T) {                                                  // rows of step t + 1
+      if (which == 1 && a.share_agents > 0)       // centralized V without a staged copy: concat of the thread's agents
+        load_row_lane(a.f_obs + (size_t)t * E * na.in_dim, g < 0 ? -1 : g / a.share_agents, in, lane, xn);
+      else
+        load_row_lane(feed_in + (size_t)t * E * in, g, in, lane, xn);
+    }
     PolStep p;
     p.in = nullptr;
     p.in_copy = t == 0 ? nullptr : store_in + (size_t)t * E * in;
     p.h_in = nullptr; p.h_out = nullptr; p.done_now = nullptr;
     p.masks = a.masks;
-    p.done_prev = t == 0 ? nullptr : a.f_done + (size_t)(t - 1) * E;
-    p.masks_copy = t == 0 ? nullptr : a.masks + (size_t)t * E;
+    p.done_prev = nullptr;
+    p.masks_copy = nullptr;                                       // written below, off the critical path
     p.avail = a.avail ? (t == 0 ? a.avail : a.f_avail + (size_t)(t - 1) * E * a.n_avail) : nullptr;
     p.avail_copy = (a.avail && t > 0) ? a.avail + (size_t)t * E * a.n_avail : nullptr;
     p.exp_noise = (a.exp_noise && t < T) ? a.exp_noise + (size_t)t * E * Atot : nullptr;
@@ -347,12 +352,21 @@ rollout_fast_kernel(const NetDev na, const NetDev nc, const RolloutArgs a) {
     p.actions_i64 = nullptr;
     p.logp = t < T ? a.logp + (size_t)t * E * na.n_heads : nullptr;
     p.forward = (t < T) || which == 1;                            // slot T: only the critic's bootstrap value
-    // rewards / active masks of env step t-1 -> slot t-1 / t (the rest of insert), by the actor's lane 0 of the row
-    if (which == 0 && t > 0 && lane == 0 && g >= 0) {
-      a.rewards[(size_t)(t - 1) * E + g] = a.f_rew[(size_t)(t - 1) * E + g];
-      if (a.f_active) a.active[(size_t)t * E + g] = a.f_active[(size_t)(t - 1) * E + g];
+    // rewards / masks / active masks of env step t-1 -> slot t-1 / t (the rest of insert), by the actor's lane 0 of the
+    // row: the loads are issued here, the dependent stores wait until the step has been computed
+    const bool book = which == 0 && t > 0 && lane == 0 && g >= 0;
+    float b_rew = 0.f, b_done = 0.f, b_act = 0.f;
+    if (book) {
+      b_rew = __ldg(a.f_rew + (size_t)(t - 1) * E + g);
+      b_done = __ldg(a.f_done + (size_t)(t - 1) * E + g);
+      if (a.f_active) b_act = __ldg(a.f_active + (size_t)(t - 1) * E + g);
     }
     fast_step(n, which, c, p, x, g, lane, a.n_avail, 0, a.rng_seed, t_last, tid);
+    if (book) {
+      a.rewards[(size_t)(t - 1) * E + g] = b_rew;
+      a.masks[(size_t)t * E + g] = b_done != 0.f ? 0.f : 1.f;
+      if (a.f_active) a.active[(size_t)t * E + g] = b_act;
+    }
     x[0] = xn[0]; x[1] = xn[1];
   }
 }

@@ -156,8 +156,6 @@ int minibatch_stats_launch(const float* returns, const float* active, const int3
 }
 
 __global__ void valuenorm_update_kernel(float* __restrict__ vn, const double* __restrict__ stats) {
-  pdl_trigger();
-  pdl_wait();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     const double n = stats[3] > 0.0 ? stats[3] : 1.0;
     const float bm = (float)(stats[1] / n), bsq = (float)(stats[2] / n);
@@ -169,7 +167,7 @@ __global__ void valuenorm_update_kernel(float* __restrict__ vn, const double* __
 }
 
 int valuenorm_update_launch(float* vn, const double* stats, cudaStream_t st) {
-  launch_chain(valuenorm_update_kernel, dim3(1), dim3(32), 0, st, vn, stats);
+  valuenorm_update_kernel<<<1, 32, 0, st>>>(vn, stats);
   return check_launch("valuenorm_update_kernel");
 }
 
@@ -302,11 +300,9 @@ __global__ void __launch_bounds__(256)
 grad_reduce_kernel(const float* __restrict__ part, int n_slots, int P, float* __restrict__ grad,
                    float* __restrict__ sumsq_part) {
   __shared__ float sacc[8][33];
-  pdl_trigger();
   const int pi = threadIdx.x & 31, sg = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + pi;
   float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
-  pdl_wait();
   if (i < P) {
     int s = sg;
     for (; s + 24 < n_slots; s += 32) {
@@ -335,7 +331,7 @@ int grad_reduce_launch(const float* part, int n_slots, int P, float* grad, float
                        cudaStream_t st) {
   const int blocks = (P + 31) / 32;
   if (n_blocks_out) *n_blocks_out = blocks;
-  launch_chain(grad_reduce_kernel, dim3(blocks), dim3(256), 0, st, part, n_slots, P, grad, sumsq_part);
+  grad_reduce_kernel<<<blocks, 256, 0, st>>>(part, n_slots, P, grad, sumsq_part);
   return check_launch("grad_reduce_kernel");
 }
 
@@ -372,8 +368,6 @@ clip_adam_kernel(float* __restrict__ p, const float* __restrict__ grad, float* _
                  int* __restrict__ step_dev, float eps, float max_norm, int use_clip, double* __restrict__ norm_out) {
   __shared__ float s_total, s_coef, s_step_size, s_bc2_sqrt;
   __shared__ int s_step;
-  pdl_trigger();
-  pdl_wait();
   // every block re-derives the global norm from the per-block partials (n_part is small) in a fixed order; the
   // scalar prologue (norm, clip coefficient, Adam bias corrections in fp64) runs in ONE warp and is broadcast
   if (threadIdx.x < 32) {
@@ -422,8 +416,8 @@ clip_adam_kernel(float* __restrict__ p, const float* __restrict__ grad, float* _
 int clip_adam_launch(float* p, const float* grad, float* m, float* v, int P, const float* sumsq_part, int n_part,
                      const float* lr_dev, int* step_dev, float eps, float max_norm, int use_clip, double* norm_out,
                      cudaStream_t st) {
-  launch_chain(clip_adam_kernel, dim3((P + 255) / 256), dim3(256), 0, st, p, grad, m, v, P, sumsq_part, n_part, lr_dev,
-               step_dev, eps, max_norm, use_clip, norm_out);
+  clip_adam_kernel<<<(P + 255) / 256, 256, 0, st>>>(p, grad, m, v, P, sumsq_part, n_part, lr_dev, step_dev, eps,
+                                                    max_norm, use_clip, norm_out);
   return check_launch("clip_adam_kernel");
 }
 

@@ -165,8 +165,6 @@ __global__ void __launch_bounds__(256)
 tc_unfold_kernel(const NetDev n, const float* __restrict__ p, const float* __restrict__ raw, float* __restrict__ g,
                  float* __restrict__ sumsq_part) {
   __shared__ float part_g[16][17], part_b[16][17], sred[8];
-  pdl_trigger();
-  pdl_wait();
   const TcImage m = make_tc_image(n);
   const TcRaw R = make_tc_raw(m);
   const int tid = threadIdx.x, kx = tid & 15, og = tid >> 4;
@@ -240,8 +238,6 @@ tc_unfold_kernel(const NetDev n, const float* __restrict__ p, const float* __res
 }
 
 __global__ void __launch_bounds__(256) pack_tc_kernel(const NetDev n, const float* __restrict__ p, float* __restrict__ img) {
-  pdl_trigger();
-  pdl_wait();
   const TcImage m = make_tc_image(n);
   const int H = 64;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m.total; i += gridDim.x * blockDim.x) {
@@ -286,216 +282,6 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const NetDev n, const floa
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Single-GPU optimiser tail of one update as ONE single-CTA kernel (everything after the slot reduction is <= 15 K
-// elements): unfold the summed raw accumulators -> global gradient norm -> clip -> Adam -> the folded weight image of
-// the NEXT update (+ optionally the next minibatch's ValueNorm update).  Replaces tc_unfold + clip_adam + pack_tc
-// (+ valuenorm_update): per update and net the launch chain is  update_mlp_tc -> grad_reduce -> tc_finish.
-// Parameters and gradients live in shared memory between the phases; 1024 threads = 64 input features x 16 groups of
-// 4 output rows (the same partition and summation order as tc_unfold_kernel).
-// ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024, 1)
-tc_finish_kernel(const NetDev n, float* __restrict__ p, const float* __restrict__ raw_g, float* __restrict__ g,
-                 float* __restrict__ ea, float* __restrict__ eas, const float* __restrict__ lr_dev,
-                 int* __restrict__ step_dev, float eps, float max_norm, int use_clip, double* __restrict__ norm_out,
-                 float* __restrict__ img, float* __restrict__ vn, const double* __restrict__ next_stats,
-                 int stage_moments) {
-  extern __shared__ __align__(16) float fs[];
-  __shared__ double sredd[32];
-  __shared__ float s_coef, s_step_size, s_bc2_sqrt, s_total;
-  __shared__ int s_step;
-  __shared__ __align__(8) uint64_t bar;
-  const TcImage m = make_tc_image(n);
-  const TcRaw R = make_tc_raw(m);
-  const int P = n.g.total, Pp = (P + 3) & ~3, P4 = P & ~3;
-  float* sp = fs;                      // parameters (old, then new)
-  float* sg = sp + Pp;                 // unfolded gradient
-  float* part_g = sg + Pp;             // [16][64]
-  float* part_b = part_g + 1024;
-  float* raw = part_b + 1024;          // slot-summed raw accumulators
-  float* sm1 = raw + R.total;          // Adam moments (when they fit)
-  float* sm2 = sm1 + Pp;
-  const int tid = threadIdx.x, k = tid & 63, og = tid >> 6;
-  const int in = n.in_dim, Atot = n.head_total, H = 64;
-
-  // ---- every global input arrives by TMA bulk copies issued up front: one round trip instead of one per phase ----
-  if (tid == 0) {
-    mbar_init(&bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const uint32_t bytes = (uint32_t)(R.total * 4 + P4 * 4 * (stage_moments ? 3 : 1));
-    mbar_expect_tx(&bar, bytes);
-    tma_bulk_g2s(raw, raw_g, (uint32_t)(R.total * 4), &bar);
-    tma_bulk_g2s(sp, p, (uint32_t)(P4 * 4), &bar);
-    if (stage_moments) {
-      tma_bulk_g2s(sm1, ea, (uint32_t)(P4 * 4), &bar);
-      tma_bulk_g2s(sm2, eas, (uint32_t)(P4 * 4), &bar);
-    }
-  }
-  if (tid < P - P4) {                                                    // the <= 3 floats past the 16-byte multiple
-    const int i = P4 + tid;
-    sp[i] = p[i];
-    if (stage_moments) { sm1[i] = ea[i]; sm2[i] = eas[i]; }
-  }
-  // scalar work that depends on no gradient: Adam bias corrections (fp64 pow) and the next ValueNorm update
-  if (tid == 992) {
-    const int st = *step_dev + 1;                                        // 1-based Adam step
-    const double bc1 = 1.0 - pow(0.9, (double)st), bc2 = 1.0 - pow(0.999, (double)st);
-    s_step_size = (float)((double)lr_dev[0] / bc1);
-    s_bc2_sqrt = (float)sqrt(bc2);
-    s_step = st;
-  }
-  if (tid == 960 && vn && next_stats) {                                  // utils/valuenorm.py:38-55
-    const double cnt = next_stats[3] > 0.0 ? next_stats[3] : 1.0;
-    const float bm = (float)(next_stats[1] / cnt), bsq = (float)(next_stats[2] / cnt);
-    const float w = 0.99999f, om = (float)(1.0 - 0.99999);
-    vn[0] = vn[0] * w + bm * om;
-    vn[1] = vn[1] * w + bsq * om;
-    vn[2] = vn[2] * w + 1.0f * om;
-  }
-  __syncthreads();                     // barrier init visible; tail elements stored
-  mbar_wait(&bar, 0);
-
-  // ---- unfold: dW = dW' diag(gamma_in), db = dW'[:, one], dgamma_in = colsum(dW' .* W), dbeta_in = W^T db' ----
-#pragma unroll 1
-  for (int sec = 0; sec < 2; ++sec) {
-    const int K = sec == 0 ? 64 : in, ld = sec == 0 ? kHF : m.inF, one = sec == 0 ? kOne : in;
-    const float* G = raw + (sec == 0 ? R.g2 : R.g1);
-    const int w_off = sec == 0 ? n.g.fc2_w[0] : n.g.fc1_w, b_off = sec == 0 ? n.g.fc2_b[0] : n.g.fc1_b;
-    const bool fold = sec == 0 ? true : (n.use_fn != 0);
-    const int gam_off = sec == 0 ? n.g.ln1_w : n.g.fn_w, bet_off = sec == 0 ? n.g.ln1_b : n.g.fn_b;
-    float a = 0.f, c = 0.f;
-    if (k < K) {
-      const float gam = fold ? sp[gam_off + k] : 1.f;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int o = og * 4 + j;
-        const float dw = G[o * ld + k], w = sp[w_off + o * K + k];
-        sg[w_off + o * K + k] = dw * gam;
-        a = fmaf(dw, w, a);
-        c = fmaf(G[o * ld + one], w, c);
-      }
-    }
-    if (tid < 64) sg[b_off + tid] = G[tid * ld + one];
-    part_g[og * 64 + k] = a; part_b[og * 64 + k] = c;
-    __syncthreads();
-    if (fold && og == 0 && k < K) {
-      float x = 0.f, y = 0.f;
-#pragma unroll
-      for (int q = 0; q < 16; ++q) { x += part_g[q * 64 + k]; y += part_b[q * 64 + k]; }
-      sg[gam_off + k] = x;
-      sg[bet_off + k] = y;
-    }
-    __syncthreads();
-  }
-  {                                                       // heads: raw gh[feature][a]
-    const float gam = sp[n.g.ln2_w[0] + k];
-    float a = 0.f, c = 0.f;
-    for (int h = og; h < Atot; h += 16) {
-      const float dw = raw[R.gh + k * m.NH + h], w = sp[n.g.head_w + h * H + k];
-      sg[n.g.head_w + h * H + k] = dw * gam;
-      a = fmaf(dw, w, a);
-      c = fmaf(raw[R.dbh + h], w, c);
-    }
-    if (tid < Atot) sg[n.g.head_b + tid] = raw[R.dbh + tid];
-    part_g[og * 64 + k] = a; part_b[og * 64 + k] = c;
-    __syncthreads();
-    if (og == 0) {
-      float x = 0.f, y = 0.f;
-#pragma unroll
-      for (int q = 0; q < 16; ++q) { x += part_g[q * 64 + k]; y += part_b[q * 64 + k]; }
-      sg[n.g.ln2_w[0] + k] = x;
-      sg[n.g.ln2_b[0] + k] = y;
-    }
-    __syncthreads();
-  }
-
-  // ---- global norm, clip coefficient (clip_grad_norm_) ----
-  {
-    float q = 0.f;
-    for (int i = tid; i < P; i += 1024) q = fmaf(sg[i], sg[i], q);
-    double x = (double)q;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-    if ((tid & 31) == 0) sredd[tid >> 5] = x;
-    __syncthreads();
-    if (tid < 32) {
-      double y = sredd[tid];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) y += __shfl_xor_sync(0xffffffffu, y, o);
-      if (tid == 0) {
-        const float tot = (float)sqrt(y);
-        s_total = tot;
-        s_coef = use_clip ? fminf(max_norm / (tot + 1e-6f), 1.0f) : 1.f;
-      }
-    }
-    __syncthreads();
-  }
-  // ---- Adam (torch single-tensor formula, same expression as clip_adam_kernel) ----
-  {
-    const float coef = s_coef, step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
-    for (int i = tid; i < P; i += 1024) {
-      const float gu = sg[i];
-      const float gi = gu * coef;
-      const float mo = stage_moments ? sm1[i] : ea[i], vo = stage_moments ? sm2[i] : eas[i];
-      const float mi = mo + (gi - mo) * (float)(1.0 - 0.9);
-      const float vi = vo * 0.999f + (float)(1.0 - 0.999) * gi * gi;
-      const float denom = sqrtf(vi) / bc2_sqrt + eps;
-      const float pn = sp[i] - step_size * (mi / denom);
-      sp[i] = pn;
-      p[i] = pn;
-      ea[i] = mi;
-      eas[i] = vi;
-      g[i] = gu;                         // the unclipped gradient stays inspectable (named_grads)
-    }
-    if (tid == 0) {
-      step_dev[0] = s_step;
-      if (norm_out) *norm_out += (double)s_total;
-    }
-  }
-  __syncthreads();
-  // ---- folded tf32 weight image of the next update (the formulas of pack_tc_kernel, parameters from shared memory;
-  //      the 64-term bias folds start at a lane-dependent feature so that the 32 rows of a warp hit 32 banks) ----
-  for (int i = tid; i < m.total; i += 1024) {
-    float v = 0.f;
-    if (i < m.w2) {                                       // fc1: [inF/4][64][4]
-      const int kc = i / 256, o = (i >> 2) & 63, kk = kc * 4 + (i & 3);
-      const float* W = sp + n.g.fc1_w + o * in;
-      if (kk < in) v = W[kk] * (n.use_fn ? sp[n.g.fn_w + kk] : 1.f);
-      else if (kk == in) {
-        v = sp[n.g.fc1_b + o];
-        if (n.use_fn) for (int j0 = 0; j0 < in; ++j0) { const int j = (j0 + o) % in; v = fmaf(W[j], sp[n.g.fn_b + j], v); }
-      }
-    } else if (i < m.wh) {                                // fc2: [18][64][4], input LN = ln1
-      const int t = i - m.w2, kc = t / 256, o = (t >> 2) & 63, kk = kc * 4 + (t & 3);
-      const float* W = sp + n.g.fc2_w[0] + o * H;
-      if (kk < H) v = W[kk] * sp[n.g.ln1_w + kk];
-      else if (kk == kOne) {
-        v = sp[n.g.fc2_b[0] + o];
-        for (int j0 = 0; j0 < H; ++j0) { const int j = (j0 + o) & 63; v = fmaf(W[j], sp[n.g.ln1_b + j], v); }
-      }
-    } else if (i < m.w2t) {                               // heads: [18][NH][4], input LN = ln2[0]
-      const int t = i - m.wh, kc = t / (4 * m.NH), a = (t >> 2) % m.NH, kk = kc * 4 + (t & 3);
-      if (a < Atot) {
-        const float* W = sp + n.g.head_w + a * H;
-        if (kk < H) v = W[kk] * sp[n.g.ln2_w[0] + kk];
-        else if (kk == kOne) {
-          v = sp[n.g.head_b + a];
-          for (int j0 = 0; j0 < H; ++j0) { const int j = (j0 + a) & 63; v = fmaf(W[j], sp[n.g.ln2_b[0] + j], v); }
-        }
-      }
-    } else if (i < m.wht) {                               // fc2 transposed: element (row k, K-index o) = W2'[o][k]
-      const int t = i - m.w2t, oc = t / 256, kk = (t >> 2) & 63, o = oc * 4 + (t & 3);
-      v = sp[n.g.fc2_w[0] + o * H + kk] * sp[n.g.ln1_w + kk];
-    } else {                                              // heads transposed: (row k, K-index a) = Wh'[a][k]
-      const int t = i - m.wht, ac = t / 256, kk = (t >> 2) & 63, a = ac * 4 + (t & 3);
-      if (a < Atot) v = sp[n.g.head_w + a * H + kk] * sp[n.g.ln2_w[0] + kk];
-    }
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-    img[i] = __uint_as_float(u);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kS65 = 65, kS73 = 73;       // padded row strides of the transposed tiles (odd -> conflict-free scatter)
@@ -519,8 +305,8 @@ __host__ __device__ inline TcSmem make_tc_smem(const TcImage& m) {
 
 // phase timestamps of CTA 0 / thread 0 (clock64), read back by mappo_debug_tc_timing(): where does a tile's
 // latency go?  [0] start, [1] setup done, [2] S1 staged, [3] fc1 ready, [4] S3 done, [5] fc2 ready, [6] S5 done,
-// [7] head ready, [8] S7 done, [9] dx2 ready, [10] S9 done, [11] dx1 ready, [12] S11 done, [13] G1 done,
-// [14] unfold done, [15] end
+// [7] head ready, [8] S7 done, [9] dx2 ready, [10] S9 done, [11] dx1 ready, [12] S11 done, [13] G2 dumped (thread 0
+// is in warpgroup 0, which dumps while the last G1 MMA runs), [14] G1 done, [15] end
 __device__ long long g_tc_timing[16];
 #define TC_STAMP(i) do { if (blockIdx.x == 0 && tid == 0) g_tc_timing[i] = clock64(); } while (0)
 
@@ -591,7 +377,7 @@ __global__ void __launch_bounds__(kTCThreads, 1)
 update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const float* __restrict__ image, const BatchDev b,
                      const LossDev L, const double* __restrict__ norm_stats, const double* __restrict__ adv_stats,
                      const float* __restrict__ vn_state, float* __restrict__ grad_part, double* __restrict__ loss_out,
-                     int n_tiles, uint32_t tmem_cols, int early_image) {
+                     int n_tiles, uint32_t tmem_cols) {
   extern __shared__ __align__(1024) float smem[];
   __shared__ double sred[2 * 32];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -606,8 +392,9 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
   float* lgT = smem + sm.lg;
   float* dbh = smem + sm.dbh;
   uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + sm.misc);
-  uint64_t* bar_m = bar_w + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 2);
+  uint64_t* bar_m = bar_w + 1;               // forward / dX accumulator ready
+  uint64_t* bar_g = bar_w + 2;               // weight-gradient MMAs of the phase done (their operand tiles are free)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 3);
   PairXch px{reinterpret_cast<float2*>(smem + sm.xch), wg, r, 1 + (warp & 3), 0};
   const int in = n.in_dim, inF = im.inF, NH = im.NH, Atot = n.head_total;
   const int S0 = inF + 1, SH = NH + 1;
@@ -615,13 +402,17 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
   constexpr int LGLD = kTM + 4;
 
   TC_STAMP(0);
-  pdl_trigger();
-  // ---- one-time setup: barriers, TMEM, constant rows of the transposed tiles.  Nothing up to the end of the first
-  //      tile's gather depends on the previous optimiser step: under programmatic dependent launch this part overlaps
-  //      the tail kernels of that step (pdl_wait() sits right before the weight image is fetched). ----
+  // row index of my first tile: issued before the setup so that its latency hides behind barrier init / TMEM allocation
+  auto row_of = [&](int tile) {
+    const int q = tile * kTM + r;
+    return (tile < n_tiles && q < b.n_rows) ? (b.rows ? b.rows[q] : q) : -1;
+  };
+  int gr_next = row_of(blockIdx.x);
+  // ---- one-time setup: barriers, TMEM, weight image by TMA, constant rows of the transposed tiles ----
   if (tid == 0) {
     mbar_init(bar_w, 1);
     mbar_init(bar_m, 1);
+    mbar_init(bar_g, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
@@ -631,11 +422,12 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
 #pragma unroll
     for (int f = 64; f < 72; ++f) base[f * 4] = (f == kOne) ? 1.f : 0.f;
   }
+  if (wg == 0) reinterpret_cast<int*>(lgT)[r] = gr_next;          // row ids of the first tile (S1's rowid_s)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  if (early_image && tid == 0) {           // normal launch: the image is final, fetch it behind the first gather
+  if (tid == 0) {                          // the weight image arrives behind the first gather
     mbar_expect_tx(bar_w, (uint32_t)(im.total * sizeof(float)));
     tma_bulk_g2s(sImg, image, (uint32_t)(im.total * sizeof(float)), bar_w);
   }
@@ -644,10 +436,10 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
   const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
   const uint32_t cMy = cD + 32 * wg;                   // my 32 columns of the 64-wide accumulator
 
-  LossConsts lc;
+  const LossConsts lc = make_loss_consts(n, L, norm_stats, adv_stats, vn_state);
   double acc[3] = {0.0, 0.0, 0.0};
-  uint32_t phase = 0;
-  bool first_tile = true;
+  uint32_t phase = 0, phase_g = 0;
+  bool first_tile = true, g1_pending = false;
   const uint32_t aP = smem_u32(P), aX1T = smem_u32(X1T), aX2T = smem_u32(X2T), aTA = smem_u32(TA);
   const uint32_t aW1 = smem_u32(sImg + im.w1), aW2 = smem_u32(sImg + im.w2), aWh = smem_u32(sImg + im.wh);
   const uint32_t aW2T = smem_u32(sImg + im.w2t), aWhT = smem_u32(sImg + im.wht);
@@ -656,7 +448,8 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
   TC_STAMP(1);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int p = tile * kTM + r;
-    const int gr = p < b.n_rows ? (b.rows ? b.rows[p] : p) : -1;
+    const int gr = gr_next;
+    gr_next = row_of(tile + gridDim.x);
     float mu0 = 0.f, rs0 = 1.f;
     const RowIn rin = load_row_in(n, b, wg == 0 ? gr : -1);      // loss inputs (warpgroup 0 owns the loss): in flight
                                                                  // during the whole forward pass
@@ -667,8 +460,10 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
       int* rowid_s = reinterpret_cast<int*>(lgT);                 // lgT is free until S7
       float* Rs = P;                                              // raw rows [128][RS], RS odd -> conflict-free row reads
       const int RS = in | 1;
-      if (wg == 0) rowid_s[r] = gr;
-      __syncthreads();
+      if (!first_tile) {                                          // (first tile: published before the setup barrier)
+        if (wg == 0) rowid_s[r] = gr;
+        __syncthreads();
+      }
       const float* base = n.is_critic ? b.share_obs : b.obs;
       // each of the 8 warps gathers 16 rows: 32 independent coalesced loads in flight per thread, then the stores
       {
@@ -692,14 +487,20 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
 #pragma unroll
       for (int k = 0; k < 64; ++k) x[k] = k < in ? Rs[r * RS + k] : 0.f;
       if (n.use_fn && gr >= 0) {                                  // both threads of the row: same statistics
-        float s = 0.f;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;             // padding is zero; 4 chains instead of one
 #pragma unroll
-        for (int k = 0; k < 64; ++k) s += x[k];                 // padding is zero
-        mu0 = s / (float)in;
-        float v = 0.f;
+        for (int k = 0; k < 64; k += 4) { s0 += x[k]; s1 += x[k + 1]; s2 += x[k + 2]; s3 += x[k + 3]; }
+        mu0 = ((s0 + s1) + (s2 + s3)) / (float)in;
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
 #pragma unroll
-        for (int k = 0; k < 64; ++k) { const float d = x[k] - mu0; v += (k < in) ? d * d : 0.f; }
-        rs0 = 1.0f / sqrtf(v / (float)in + kLnEps);
+        for (int k = 0; k < 64; k += 4) {
+          const float d0 = x[k] - mu0, d1 = x[k + 1] - mu0, d2 = x[k + 2] - mu0, d3 = x[k + 3] - mu0;
+          v0 = (k < in) ? fmaf(d0, d0, v0) : v0;
+          v1 = (k + 1 < in) ? fmaf(d1, d1, v1) : v1;
+          v2 = (k + 2 < in) ? fmaf(d2, d2, v2) : v2;
+          v3 = (k + 3 < in) ? fmaf(d3, d3, v3) : v3;
+        }
+        rs0 = 1.0f / sqrtf(((v0 + v1) + (v2 + v3)) / (float)in + kLnEps);
       }
 #pragma unroll
       for (int c8 = 0; c8 < 9; ++c8) {
@@ -716,15 +517,6 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
         }
       }
       tmem_st_wait();
-    }
-    if (first_tile) {
-      // from here on the kernel reads what the previous step produced: weight image, ValueNorm state
-      pdl_wait();
-      if (!early_image && tid == 0) {
-        mbar_expect_tx(bar_w, (uint32_t)(im.total * sizeof(float)));
-        tma_bulk_g2s(sImg, image, (uint32_t)(im.total * sizeof(float)), bar_w);
-      }
-      lc = make_loss_consts(n, L, norm_stats, adv_stats, vn_state);
     }
     TC_STAMP(2);
     fence_async_smem();
@@ -831,16 +623,18 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      // Gh[k][a] += xhat2^T dL   (M = 64 features, N = NH, K = 128 rows): transposed tiles, K-major
-      const uint32_t idg = make_idesc(64, NH, 0, 0);
-      for (int s = 0; s < kTM / 8; ++s)
-        umma_tf32(tmem + cGh, make_desc(aX2T + s * 2 * kS65 * 16, kS65 * 16, 128),
-                  make_desc(aTA + s * 2 * SH * 16, SH * 16, 128), idg, (!first_tile) || s > 0);
-      // dxhat2 = dL Wh'       (M = 128 rows, N = 64 features, K = NH)
+      // dxhat2 = dL Wh'       (M = 128 rows, N = 64 features, K = NH) first: S9 only needs this one ...
       const uint32_t idx = make_idesc(128, 64, 0, 0);
       for (int s = 0; s < NH / 8; ++s)
         umma_tf32(tmem + cD, make_desc(aP + s * 2 * ROWB, ROWB, 128), make_desc(aWhT + s * 2 * 1024, 1024, 128), idx, s > 0);
       umma_commit(bar_m);
+      // ... Gh[k][a] += xhat2^T dL   (M = 64 features, N = NH, K = 128 rows; transposed tiles, K-major) runs behind the
+      // first half of S9 and only gates the rewrite of TA
+      const uint32_t idg = make_idesc(64, NH, 0, 0);
+      for (int s = 0; s < kTM / 8; ++s)
+        umma_tf32(tmem + cGh, make_desc(aX2T + s * 2 * kS65 * 16, kS65 * 16, 128),
+                  make_desc(aTA + s * 2 * SH * 16, SH * 16, 128), idg, (!first_tile) || s > 0);
+      umma_commit(bar_g);
     }
     // ---- S9: LayerNorm-2 + activation backward -> dZ2 (K-major staging + transposed) ----
     {
@@ -852,6 +646,8 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
       tmem_ld_wait();
       ln_act_bwd32(d, X2T, kS65, r, wg, px, mu2, rs2, act);
       put_kmajor32(P, r, wg, d, false);
+      mbar_wait(bar_g, phase_g); phase_g ^= 1;             // Gh has consumed dL^T (TA)
+      tc_fence_after();
       put_transposed32(TA, kS65, r, wg, d);
     }
     TC_STAMP(10);
@@ -860,16 +656,17 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      // G2[o][k] += dZ2^T xhat1aug   (M = 64, N = 72, K = 128 rows)
-      const uint32_t idg = make_idesc(64, kHF, 0, 0);
-      for (int s = 0; s < kTM / 8; ++s)
-        umma_tf32(tmem + cG2, make_desc(aTA + s * 2 * kS65 * 16, kS65 * 16, 128),
-                  make_desc(aX1T + s * 2 * kS73 * 16, kS73 * 16, 128), idg, (!first_tile) || s > 0);
-      // dxhat1 = dZ2 W2'             (M = 128, N = 64, K = 64)
+      // dxhat1 = dZ2 W2'             (M = 128, N = 64, K = 64) first ...
       const uint32_t idx = make_idesc(128, 64, 0, 0);
       for (int s = 0; s < 8; ++s)
         umma_tf32(tmem + cD, make_desc(aP + s * 2 * ROWB, ROWB, 128), make_desc(aW2T + s * 2 * 1024, 1024, 128), idx, s > 0);
       umma_commit(bar_m);
+      // ... G2[o][k] += dZ2^T xhat1aug   (M = 64, N = 72, K = 128 rows) behind the first half of S11
+      const uint32_t idg = make_idesc(64, kHF, 0, 0);
+      for (int s = 0; s < kTM / 8; ++s)
+        umma_tf32(tmem + cG2, make_desc(aTA + s * 2 * kS65 * 16, kS65 * 16, 128),
+                  make_desc(aX1T + s * 2 * kS73 * 16, kS73 * 16, 128), idg, (!first_tile) || s > 0);
+      umma_commit(bar_g);
     }
     // ---- S11: LayerNorm-1 + activation backward -> dZ1^T; xhat0^T re-staged from its TMEM parking columns ----
     {
@@ -880,6 +677,8 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
       tmem_ld16(tmem + lane_base + cMy + 16, d + 16);
       tmem_ld_wait();
       ln_act_bwd32(d, X1T, kS73, r, wg, px, mu1, rs1, act);
+      mbar_wait(bar_g, phase_g); phase_g ^= 1;             // G2 has consumed dZ2^T (TA)
+      tc_fence_after();
       put_transposed32(TA, kS65, r, wg, d);
       float* pb = P + (r >> 2) * S0 * 4 + (r & 3);                // xhat0aug^T: [32][inF + 1][4]
 #pragma unroll
@@ -906,14 +705,13 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
                   idg, (!first_tile) || s > 0);
       umma_commit(bar_m);
     }
-    mbar_wait(bar_m, phase); phase ^= 1; TC_STAMP(13);        // P / TA are rewritten by the next iteration
-    tc_fence_after();
     first_tile = false;
+    if (wg == 0 && tile + (int)gridDim.x >= n_tiles) { g1_pending = true; break; }   // last tile: G2 can be dumped now
+    mbar_wait(bar_m, phase); phase ^= 1;                      // P / TA are rewritten by the next iteration
+    tc_fence_after();
   }
   // ---- dump the raw (still folded) accumulators into this CTA's slot; they are summed over slots and unfolded once
   //      by mappo_update_finish (tc_unfold_kernel).  Warpgroup 0 dumps G2, warpgroup 1 dumps G1 and Gh. ----
-  pdl_wait();                  // (a CTA without tiles has not waited yet; a second wait returns at once)
-  if (first_tile) lc = make_loss_consts(n, L, norm_stats, adv_stats, vn_state);
   if (!b.eval_only) {
     const TcRaw R = make_tc_raw(im);
     float* g = grad_part + (size_t)blockIdx.x * R.total;
@@ -958,6 +756,8 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
     if (tid < NH) g[R.dbh + tid] = dbh[tid];
   }
 
+  TC_STAMP(13);
+  if (g1_pending) { mbar_wait(bar_m, phase); phase ^= 1; tc_fence_after(); }      // every MMA done before teardown
   TC_STAMP(14);
   // ---- loss scalars + teardown ----
   tc_fence_before();
@@ -993,7 +793,7 @@ int update_mlp_tc_slot_floats(const NetDev& n) { return make_tc_raw(make_tc_imag
 // sum of the raw slots is in `raw_sum` -> flat gradient + sum(g^2) (one partial)
 int update_mlp_tc_unfold_launch(const NetDev& n, const float* params, const float* raw_sum, float* grad,
                                 float* sumsq_part, cudaStream_t st) {
-  launch_chain(tc_unfold_kernel, dim3(4, 3), dim3(256), 0, st, n, params, raw_sum, grad, sumsq_part);       // 12 partial sums of squares
+  tc_unfold_kernel<<<dim3(4, 3), 256, 0, st>>>(n, params, raw_sum, grad, sumsq_part);       // 12 partial sums of squares
   return check_launch("tc_unfold_kernel");
 }
 
@@ -1004,7 +804,7 @@ int update_mlp_tc_slots(const NetDev&, int n_rows, int sm_count) {
 
 int update_mlp_tc_launch(const NetDev& n, const float* params, const BatchDev& b, const LossDev& L,
                          const double* norm_stats, const double* adv_stats, const float* vn_state, float* grad_part,
-                         int n_slots, double* loss_out, float* image, bool image_ready, cudaStream_t st) {
+                         int n_slots, double* loss_out, float* image, cudaStream_t st) {
   if (!update_mlp_tc_supported(n)) { set_error("update_mlp_tc: configuration not built for the tcgen05 path"); return MAPPO_ERR_UNSUPPORTED; }
   if (!image) { set_error("update_mlp_tc: weight-image workspace is NULL"); return MAPPO_ERR_INVALID; }
   if ((reinterpret_cast<uintptr_t>(image) & 15) != 0) { set_error("update_mlp_tc: workspace must be 16-byte aligned"); return MAPPO_ERR_INVALID; }
@@ -1012,11 +812,9 @@ int update_mlp_tc_launch(const NetDev& n, const float* params, const BatchDev& b
   const TcSmem sm = make_tc_smem(im);
   const size_t bytes = (size_t)sm.total * sizeof(float) + 1024;
   if (bytes > 227 * 1024) { set_error("update_mlp_tc: %zu B shared memory > 227 KB", bytes); return MAPPO_ERR_UNSUPPORTED; }
-  if (!image_ready) {        // the fused optimiser tail of the previous update (tc_finish_kernel) leaves it ready
-    launch_chain(pack_tc_kernel, dim3((im.total + 255) / 256), dim3(256), 0, st, n, params, image);      // one element per thread
-    const int rc = check_launch("pack_tc_kernel");
-    if (rc) return rc;
-  }
+  pack_tc_kernel<<<(im.total + 255) / 256, 256, 0, st>>>(n, params, image);      // one element per thread
+  const int rc = check_launch("pack_tc_kernel");
+  if (rc) return rc;
   static thread_local size_t configured = 0;
   if (bytes > configured) {
     if (cudaFuncSetAttribute(update_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
@@ -1025,32 +823,9 @@ int update_mlp_tc_launch(const NetDev& n, const float* params, const BatchDev& b
   }
   const int n_tiles = (b.n_rows + kTM - 1) / kTM;
   const uint32_t cols = 512u;          // accumulators [0,272) + parked xhat0 [272,344): one CTA per SM owns all of TMEM
-  const bool pdl = pdl_mode() >= 2;
-  launch_chain_if(pdl, update_mlp_tc_kernel, dim3(n_slots), dim3(kTCThreads), bytes, st, n, params, image, b, L, norm_stats,
-                  adv_stats, vn_state, grad_part, loss_out, n_tiles, cols, pdl ? 0 : 1);
+  update_mlp_tc_kernel<<<n_slots, kTCThreads, bytes, st>>>(n, params, image, b, L, norm_stats, adv_stats, vn_state, grad_part,
+                                                           loss_out, n_tiles, cols);
   return check_launch("update_mlp_tc_kernel");
-}
-
-int update_mlp_tc_finish_launch(const NetDev& n, float* params, const float* raw_sum, float* grad, float* exp_avg,
-                                float* exp_avg_sq, const float* lr_dev, int* step_dev, float eps, float max_norm,
-                                int use_clip, double* norm_out, float* image, float* vn_state, const double* next_stats,
-                                cudaStream_t st) {
-  const int Pp = (n.g.total + 3) & ~3;
-  const int raw_floats = make_tc_raw(make_tc_image(n)).total;
-  size_t bytes = (size_t)(4 * Pp + 2048 + raw_floats) * sizeof(float);
-  int stage_moments = 1;
-  if (bytes > 220 * 1024) { stage_moments = 0; bytes = (size_t)(2 * Pp + 2048 + raw_floats) * sizeof(float); }
-  if (bytes > 220 * 1024) { set_error("update_step_fused: %zu B shared memory", bytes); return MAPPO_ERR_UNSUPPORTED; }
-  if (((uintptr_t)params | (uintptr_t)raw_sum | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) { set_error("update_step_fused: 16-byte alignment required"); return MAPPO_ERR_INVALID; }
-  static thread_local size_t configured = 0;
-  if (bytes > configured) {
-    if (cudaFuncSetAttribute(tc_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
-      return check_launch("tc_finish: cudaFuncSetAttribute");
-    configured = bytes;
-  }
-  tc_finish_kernel<<<1, 1024, bytes, st>>>(n, params, raw_sum, grad, exp_avg, exp_avg_sq, lr_dev, step_dev, eps, max_norm,
-                                           use_clip, norm_out, image, vn_state, next_stats, stage_moments);
-  return check_launch("tc_finish_kernel");
 }
 
 }  // namespace mappo

@@ -33,8 +33,7 @@ class LossCfg(C.Structure):
                 ("huber_delta", C.c_float),
                 ("use_clipped_value_loss", C.c_int32), ("use_huber_loss", C.c_int32),
                 ("use_value_active_masks", C.c_int32), ("use_policy_active_masks", C.c_int32),
-                ("use_valuenorm", C.c_int32), ("update_actor", C.c_int32), ("gemm_mode", C.c_int32),
-                ("weight_image_ready", C.c_int32)]
+                ("use_valuenorm", C.c_int32), ("update_actor", C.c_int32), ("gemm_mode", C.c_int32)]
 
 
 _P = C.c_void_p
@@ -67,7 +66,6 @@ _SIGS = {
     "mappo_evaluate_actions": (_i32, [C.POINTER(NetDesc), _P, C.POINTER(Batch), C.POINTER(LossCfg), _P, _P, _P, _P, _P]),
     "mappo_minibatch_stats": (_i32, [_P, _P, _P, _i32, _P, _P]),
     "mappo_debug_launch_count": (_i64, []),
-    "mappo_update_step_fused": (_i32, [_P, _P, _P, _i32, _P, _P, _P, _P, _P, _f32, _f32, _i32, _P, _P, _P, _P, _P]),
     "mappo_minibatch_stats_batch": (_i32, [_P, _P, _P, _i64, _i32, _i32, _P, _P]),
     "mappo_randperm_batch": (_i32, [_i32, _i32, _u64, _P, _P, _P]),
     "mappo_valuenorm_update": (_i32, [_P, _P, _P]),

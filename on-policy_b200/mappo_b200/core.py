@@ -418,34 +418,10 @@ def launch_step(net: DeviceNet, ws: UpdateWorkspace, loss_out, opt: FusedAdam, m
 
 def launch_update(net: DeviceNet, ws: UpdateWorkspace, batch: Batch, loss: LossCfg, norm_stats, adv_stats, vn_state,
                   loss_out, opt: FusedAdam, max_grad_norm, use_max_grad_norm, grad_norm_slot: int,
-                  allreduce=None, fused=False, image_ready=False, next_stats=None):
-    """forward+loss+backward -> slot reduction -> [all-reduce] -> clip + Adam for one net.
-
-    fused (tcgen05 build, no collective): the tail is mappo_update_step_fused -- slot reduction + one single-CTA kernel
-    (unfold, norm, clip, Adam, next weight image, optionally the next ValueNorm update from `next_stats`); with
-    `image_ready` the forward skips its weight-pack launch.  Returns True when the workspace holds the weight image of
-    the updated parameters."""
-    if fused and allreduce is None and ws.gemm_mode == _lib.GEMM_TF32:
-        lib = _lib.load()
-        st = stream_ptr()
-        n_slots = min(ws.n_slots, int(lib.mappo_update_grad_slots(C.byref(net.desc), int(batch.n_rows), ws.gemm_mode)))
-        loss.gemm_mode = ws.gemm_mode
-        loss.weight_image_ready = int(bool(image_ready))
-        check(lib.mappo_update_fwd_bwd(C.byref(net.desc), ptr(net.flat), C.byref(batch), C.byref(loss), ptr(norm_stats),
-                                       None if adv_stats is None else ptr(adv_stats),
-                                       None if vn_state is None else ptr(vn_state), ptr(ws.grad_part), n_slots,
-                                       ptr(loss_out), ptr(ws.workspace), st))
-        loss.weight_image_ready = 0
-        check(lib.mappo_update_step_fused(
-            C.byref(net.desc), ptr(net.flat), ptr(ws.grad_part), n_slots, ptr(net.grad), ptr(opt.exp_avg),
-            ptr(opt.exp_avg_sq), ptr(opt.lr_dev), ptr(opt.step_dev), float(opt.param_groups[0]["eps"]),
-            float(max_grad_norm), int(bool(use_max_grad_norm)), C.c_void_p(loss_out.data_ptr() + 8 * grad_norm_slot),
-            ptr(ws.workspace), None if (vn_state is None or next_stats is None) else ptr(vn_state),
-            None if (vn_state is None or next_stats is None) else ptr(next_stats), st))
-        return True
+                  allreduce=None):
+    """forward+loss+backward -> slot reduction -> [all-reduce] -> clip + Adam for one net."""
     nb = launch_grads(net, ws, batch, loss, norm_stats, adv_stats, vn_state, loss_out)
     if allreduce is not None:
         allreduce(net.grad)
         nb = 0                            # the norm must be re-derived from the all-reduced gradient
     launch_step(net, ws, loss_out, opt, max_grad_norm, use_max_grad_norm, grad_norm_slot, nb)
-    return False

@@ -58,7 +58,11 @@ INFO_KEYS = ("value_loss", "policy_loss", "dist_entropy", "actor_grad_norm", "cr
 
 
 class RolloutEngine:
-    def __init__(self, args, policy, trainer, buffer, rng: str = "device", seed: int = 1):
+    def __init__(self, args, policy, trainer, buffer, rng: str = "device", seed: int = 1,
+                 share_obs_from_obs: bool = False):
+        """share_obs_from_obs: the env's share_obs is the concatenation of the obs of the agents of a rollout thread
+        (what the MPE runner builds on the host, mpe_runner.py:133-135): only obs is staged / uploaded and the critic
+        reads its rows from it on the device (feed-forward policies, persistent rollout)."""
         self.args, self.policy, self.trainer, self.buffer = args, policy, trainer, buffer
         self.dev = policy.device
         self.rng = rng
@@ -73,9 +77,20 @@ class RolloutEngine:
         self.recurrent = bool(policy.actor.desc.recurrent)
         T, E = self.T, self.E
         f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.dev)
-        # device staging of one iteration of env outputs (next obs for slots 1..T, rewards, dones, ...)
-        self.d_obs, self.d_share = f(T, E, self.Do), f(T, E, self.Ds)
-        self.d_rew, self.d_done = f(T, E, 1), f(T, E)
+        import os
+        self.persistent_rollout = os.environ.get("MAPPO_B200_PERSISTENT_ROLLOUT", "1") == "1"
+        self.share_from_obs = bool(share_obs_from_obs) and self.persistent_rollout and not self.recurrent \
+            and self.Ds % self.Do == 0 and E % (self.Ds // self.Do) == 0
+        # device staging of one iteration of env outputs (next obs for slots 1..T, rewards, dones, ...): ONE flat buffer
+        # (= one H2D copy per iteration) with views per field
+        n_obs, n_share = T * E * self.Do, (0 if self.share_from_obs else T * E * self.Ds)
+        self.d_stage = f(n_obs + n_share + 2 * T * E)
+        self.h_stage = None
+        o = 0
+        self.d_obs = self.d_stage[o:o + n_obs].view(T, E, self.Do); o += n_obs
+        self.d_share = self.d_stage[o:o + n_share].view(T, E, self.Ds) if n_share else None; o += n_share
+        self.d_rew = self.d_stage[o:o + T * E].view(T, E, 1); o += T * E
+        self.d_done = self.d_stage[o:o + T * E].view(T, E)
         self.d_active = None
         self.d_avail = None
         self.d_noise = f(T, E, self.sumA) if rng == "host" else None
@@ -90,9 +105,6 @@ class RolloutEngine:
                                      dtype=torch.float32, device=self.dev)
         self.img_critic = torch.zeros(int(self.lib.mappo_rollout_image_floats(C.byref(policy.critic.desc))),
                                       dtype=torch.float32, device=self.dev)
-        # one persistent launch for the whole collect phase (env outputs are staged on the device anyway)
-        import os
-        self.persistent_rollout = os.environ.get("MAPPO_B200_PERSISTENT_ROLLOUT", "1") == "1"
         self.host = {}
         self.graph = None
         self._allreduce = "auto"        # "auto": torch.distributed when a multi-rank group exists
@@ -104,8 +116,20 @@ class RolloutEngine:
         """Pin one iteration of synthetic env outputs (oracle.SyntheticFeed layout) in host memory."""
         T, E = self.T, self.E
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).pin_memory()
-        self.host = dict(obs=pin(feed.obs[1:].reshape(T, E, -1)), share=pin(feed.share_obs[1:].reshape(T, E, -1)),
-                         rew=pin(feed.rewards.reshape(T, E, 1)), done=pin(feed.dones.reshape(T, E).astype(np.float32)))
+        if self.share_from_obs:
+            M = self.Ds // self.Do
+            want = np.repeat(feed.obs.reshape(T + 1, E // M, 1, M * self.Do), M, axis=2).reshape(feed.share_obs.shape)
+            if not np.array_equal(want, feed.share_obs):
+                raise ValueError("share_obs_from_obs: the feed's share_obs is not the concatenation of its obs rows")
+        # obs | [share_obs] | rewards | dones in one pinned buffer, mirrored by d_stage
+        if self.h_stage is None:
+            self.h_stage = torch.zeros(self.d_stage.numel(), dtype=torch.float32).pin_memory()
+        parts = [feed.obs[1:]] + ([] if self.share_from_obs else [feed.share_obs[1:]]) + \
+                [feed.rewards, feed.dones.astype(np.float32)]
+        flat = np.concatenate([np.ascontiguousarray(a, dtype=np.float32).reshape(-1) for a in parts])
+        assert flat.size == self.h_stage.numel()
+        self.h_stage.copy_(torch.from_numpy(flat))
+        self.host = dict(stage=self.h_stage)
         if feed.active_masks is not None:
             self.host["active"] = pin(feed.active_masks.reshape(T, E, 1))
             if self.d_active is None:
@@ -129,10 +153,7 @@ class RolloutEngine:
     def upload(self):
         """Host -> device copy of this iteration's inputs (async, current stream)."""
         h = self.host
-        self.d_obs.copy_(h["obs"], non_blocking=True)
-        self.d_share.copy_(h["share"], non_blocking=True)
-        self.d_rew.copy_(h["rew"], non_blocking=True)
-        self.d_done.copy_(h["done"], non_blocking=True)
+        self.d_stage.copy_(h["stage"], non_blocking=True)
         if "active" in h:
             self.d_active.copy_(h["active"], non_blocking=True)
         if "avail" in h:
@@ -190,7 +211,7 @@ class RolloutEngine:
             ptr(b.masks), ptr(b.available_actions) if self.d_avail is not None else None,
             ptr(b.value_preds), ptr(b.actions), ptr(b.action_log_probs), ptr(b.rewards),
             ptr(b.active_masks) if self.d_active is not None else None,
-            ptr(self.d_obs), ptr(self.d_share), ptr(self.d_rew), ptr(self.d_done),
+            ptr(self.d_obs), ptr(self.d_share), ptr(self.d_rew), ptr(self.d_done),          # d_share None: from d_obs
             ptr(self.d_active) if self.d_active is not None else None,
             ptr(self.d_avail) if self.d_avail is not None else None,
             ptr(self.d_noise), self.seed, ptr(pol.rng_offset), self.T, self.E, stream_ptr()))

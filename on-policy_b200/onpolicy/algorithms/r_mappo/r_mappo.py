@@ -61,10 +61,6 @@ class R_MAPPO():
         # actor and critic are independent nets: their update chains run on two streams (fork / join with events,
         # captured as parallel branches of the CUDA graph).  Off when a process group is active (one collective order).
         self.overlap_nets = os.environ.get("MAPPO_B200_OVERLAP", "1") == "1"
-        # tcgen05 build on one GPU: slot reduction + ONE single-CTA kernel for unfold / clip / Adam / next weight image
-        # (mappo_update_step_fused).  Opt-in: measured on c2 it is ~2% slower than the 3 small multi-CTA kernels it
-        # replaces (one SM is issue-bound on ~15 K elements; graph launch gaps are only ~2 us) -- see DESIGN.md.
-        self.fused_step = os.environ.get("MAPPO_B200_FUSED_STEP", "0") == "1"
         self._side = None
         # joint gradient vector [actor | critic]: what a multi-GPU run all-reduces in one collective per optimiser step
         na, nc = policy.actor.n_params, policy.critic.n_params
@@ -85,33 +81,23 @@ class R_MAPPO():
                              UpdateWorkspace(self.policy.critic, key, self.gemm_mode))
         return self._ws[key]
 
-    def _one_update(self, batch, n_rows, norm_stats, adv_stats, loss_out, update_actor, allreduce, only=None,
-                    first=True, next_stats=None):
-        """One optimiser step of both nets.  `first`: first update since the parameters may have changed outside this
-        train() (weight images must be rebuilt); `next_stats`: statistics of the next minibatch of the same train()
-        (lets the fused critic step apply the next ValueNorm update)."""
+    def _one_update(self, batch, n_rows, norm_stats, adv_stats, loss_out, update_actor, allreduce, only=None):
+        """One optimiser step of both nets (`only`: just the "actor" / "critic" chain)."""
         pol = self.policy
         ws_a, ws_c = self._workspaces(n_rows)
-        fused = self.fused_step and allreduce is None
         loss_a = make_loss_cfg(self.args, update_actor)
         loss_c = make_loss_cfg(self.args, update_actor)
         vn = self.value_normalizer.state if self.value_normalizer is not None else None
 
         def actor_chain():          # backward, clip, step (reference :141-153)
-            ws_a.image_ready = launch_update(
-                pol.actor, ws_a, batch, loss_a, norm_stats, adv_stats, None, loss_out, pol.actor_optimizer,
-                self.max_grad_norm, self._use_max_grad_norm, 3, allreduce, fused=fused,
-                image_ready=(not first) and getattr(ws_a, "image_ready", False))
+            launch_update(pol.actor, ws_a, batch, loss_a, norm_stats, adv_stats, None, loss_out, pol.actor_optimizer,
+                          self.max_grad_norm, self._use_max_grad_norm, 3, allreduce)
 
         def critic_chain():         # ValueNorm.update(return_batch) BEFORE the value loss (reference :65), then :156-167
-            chained = fused and (not first) and getattr(ws_c, "vn_applied", False)
-            if vn is not None and not chained:      # otherwise the previous fused step already applied it
+            if vn is not None:
                 check(_lib.load().mappo_valuenorm_update(ptr(vn), ptr(norm_stats), stream_ptr()))
-            ws_c.image_ready = launch_update(
-                pol.critic, ws_c, batch, loss_c, norm_stats, None, vn, loss_out, pol.critic_optimizer,
-                self.max_grad_norm, self._use_max_grad_norm, 4, allreduce, fused=fused,
-                image_ready=(not first) and getattr(ws_c, "image_ready", False), next_stats=next_stats)
-            ws_c.vn_applied = bool(ws_c.image_ready and vn is not None and next_stats is not None)
+            launch_update(pol.critic, ws_c, batch, loss_c, norm_stats, None, vn, loss_out, pol.critic_optimizer,
+                          self.max_grad_norm, self._use_max_grad_norm, 4, allreduce)
 
         if only == "actor":
             actor_chain()
@@ -291,9 +277,8 @@ class R_MAPPO():
 
         def updates(only):
             for u, (rows, _, _) in enumerate(plans):
-                nxt = stats[4 * u + 4:4 * u + 8] if u + 1 < n_updates else None
                 self._one_update(batches[u], rows.numel(), stats[4 * u:4 * u + 4], adv_stats, loss_out, update_actor,
-                                 allreduce, only, first=(u == 0), next_stats=nxt)
+                                 allreduce, only)
 
         if self.overlap_nets and allreduce is None:
             # actor and critic never read each other's state inside train(): their whole update sequences are two

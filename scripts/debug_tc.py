@@ -43,5 +43,5 @@ torch.cuda.synchronize()
 lib.mappo_debug_tc_timing(buf16)
 t = list(buf16)
 names = ["setup", "S1 gather+LN0", "fc1 mma", "S3 epi", "fc2 mma", "S5 epi", "head mma", "S7 loss", "dx2+Gh mma", "S9 bwd",
-         "dx1+G2 mma", "S11 bwd", "G1 mma", "unfold", "tail"]
+         "dx1+G2 mma", "S11 bwd", "dump G2", "G1 wait", "tail"]
 print("TC kernel phase cycles (CTA 0):", {n: t[i + 1] - t[i] for i, n in enumerate(names)}, "total", t[15] - t[0])
