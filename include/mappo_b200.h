@@ -275,6 +275,8 @@ int32_t mappo_p2p_allreduce_f64(const void* const* peer_bufs, void* const* peer_
  *   mappo_clip_adam   : total = sqrt(sum sumsq_part); coef = min(1, max_norm/(total+1e-6)) when
  *                       use_max_grad_norm; Adam step with g*coef; ++step_dev[0]; *grad_norm_out += total.
  *                       step_dev points to TWO ints: {Adam step count, scratch ticket (keep 0)}.
+ *                       beta_pow_dev (nullable): THREE doubles {0.9^t, 0.999^t, t}, a cache of the bias-correction powers
+ *                       the kernel keeps itself (any content is safe: a stale tag just recomputes with pow()).
  * lr is read from device memory (lr_dev[0]) so lr_decay (utils/util.py:17-21) needs no re-capture. */
 /* Floats per gradient slot (`grad_part` holds n_slots of them): n_params for the fp32 build; the tcgen05 build
  * parks its still-folded TMEM accumulators (dW', db' columns) instead. */
@@ -293,7 +295,7 @@ int32_t mappo_grad_sumsq(const float* grad, int32_t n_params, float* sumsq_part,
 int32_t mappo_clip_adam(float* params, const float* grad, float* exp_avg, float* exp_avg_sq,
                         int32_t n_params, const float* sumsq_part, int32_t n_sumsq_blocks,
                         const float* lr_dev, int32_t* step_dev, float eps, float max_grad_norm,
-                        int32_t use_max_grad_norm, double* grad_norm_out, void* stream);
+                        int32_t use_max_grad_norm, double* grad_norm_out, double* beta_pow_dev, void* stream);
 
 #ifdef __cplusplus
 }

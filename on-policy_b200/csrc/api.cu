@@ -106,7 +106,7 @@ int minibatch_stats_batch_launch(const float*, const float*, const int32_t*, lon
 int grad_reduce_launch(const float*, int, int, float*, float*, int*, cudaStream_t);
 int sumsq_launch(const float*, int, float*, int*, cudaStream_t);
 int clip_adam_launch(float*, const float*, float*, float*, int, const float*, int, const float*, int*, float, float,
-                     int, double*, cudaStream_t);
+                     int, double*, double*, cudaStream_t);
 int counter_add_launch(uint64_t*, uint64_t, cudaStream_t);
 int p2p_allreduce_f32_launch(const void* const*, void* const*, int, int, long long, int, float*, uint32_t*, cudaStream_t);
 int p2p_allreduce_f64_launch(const void* const*, void* const*, int, int, long long, int, double*, uint32_t*, cudaStream_t);
@@ -487,10 +487,11 @@ int32_t mappo_grad_sumsq(const float* grad, int32_t n_params, float* sumsq_part,
 
 int32_t mappo_clip_adam(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int32_t n_params,
                         const float* sumsq_part, int32_t n_sumsq_blocks, const float* lr_dev, int32_t* step_dev,
-                        float eps, float max_grad_norm, int32_t use_max_grad_norm, double* grad_norm_out, void* stream) {
+                        float eps, float max_grad_norm, int32_t use_max_grad_norm, double* grad_norm_out,
+                        double* beta_pow_dev, void* stream) {
   if (!params || !grad || !exp_avg || !exp_avg_sq || !sumsq_part || !lr_dev || !step_dev || n_params <= 0 || n_sumsq_blocks <= 0) { set_error("clip_adam: bad arguments"); return MAPPO_ERR_INVALID; }
   return clip_adam_launch(params, grad, exp_avg, exp_avg_sq, n_params, sumsq_part, n_sumsq_blocks, lr_dev, step_dev, eps,
-                          max_grad_norm, use_max_grad_norm, grad_norm_out, (cudaStream_t)stream);
+                          max_grad_norm, use_max_grad_norm, grad_norm_out, beta_pow_dev, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -365,9 +365,11 @@ int sumsq_launch(const float* grad, int P, float* sumsq_part, int* n_blocks_out,
 __global__ void __launch_bounds__(256)
 clip_adam_kernel(float* __restrict__ p, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
                  int P, const float* __restrict__ sumsq_part, int n_part, const float* __restrict__ lr_dev,
-                 int* __restrict__ step_dev, float eps, float max_norm, int use_clip, double* __restrict__ norm_out) {
+                 int* __restrict__ step_dev, float eps, float max_norm, int use_clip, double* __restrict__ norm_out,
+                 double* __restrict__ beta_pow) {
   __shared__ float s_total, s_coef, s_step_size, s_bc2_sqrt;
   __shared__ int s_step;
+  __shared__ double s_p1, s_p2;
   // every block re-derives the global norm from the per-block partials (n_part is small) in a fixed order; the
   // scalar prologue (norm, clip coefficient, Adam bias corrections in fp64) runs in ONE warp and is broadcast
   if (threadIdx.x < 32) {
@@ -378,7 +380,13 @@ clip_adam_kernel(float* __restrict__ p, const float* __restrict__ grad, float* _
     if (threadIdx.x == 0) {
       const float tot = (float)sqrt(x);
       const int st = *step_dev + 1;                                      // 1-based Adam step
-      const double bc1 = 1.0 - pow(0.9, (double)st), bc2 = 1.0 - pow(0.999, (double)st);
+      // beta^t: carried from the previous step when the cache is current ({0.9^t, 0.999^t, t} as doubles; two fp64 pow()
+      // calls cost ~1.5 us of single-thread latency on every launch), recomputed otherwise (first step, reloaded state)
+      double p1, p2;
+      if (beta_pow && beta_pow[2] == (double)(st - 1)) { p1 = beta_pow[0] * 0.9; p2 = beta_pow[1] * 0.999; }
+      else { p1 = pow(0.9, (double)st); p2 = pow(0.999, (double)st); }
+      s_p1 = p1; s_p2 = p2;
+      const double bc1 = 1.0 - p1, bc2 = 1.0 - p2;
       s_total = tot;
       s_coef = use_clip ? fminf(max_norm / (tot + 1e-6f), 1.0f) : 1.f;   // clip_grad_norm_
       s_step_size = (float)((double)lr_dev[0] / bc1);
@@ -408,6 +416,7 @@ clip_adam_kernel(float* __restrict__ p, const float* __restrict__ grad, float* _
     if (ticket == (int)gridDim.x - 1) {
       step_dev[0] = step;
       step_dev[1] = 0;
+      if (beta_pow) { beta_pow[0] = s_p1; beta_pow[1] = s_p2; beta_pow[2] = (double)step; }
       if (norm_out) *norm_out += (double)total;
     }
   }
@@ -415,9 +424,9 @@ clip_adam_kernel(float* __restrict__ p, const float* __restrict__ grad, float* _
 
 int clip_adam_launch(float* p, const float* grad, float* m, float* v, int P, const float* sumsq_part, int n_part,
                      const float* lr_dev, int* step_dev, float eps, float max_norm, int use_clip, double* norm_out,
-                     cudaStream_t st) {
+                     double* beta_pow, cudaStream_t st) {
   clip_adam_kernel<<<(P + 255) / 256, 256, 0, st>>>(p, grad, m, v, P, sumsq_part, n_part, lr_dev, step_dev, eps,
-                                                    max_norm, use_clip, norm_out);
+                                                    max_norm, use_clip, norm_out, beta_pow);
   return check_launch("clip_adam_kernel");
 }
 

@@ -115,6 +115,19 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
 }
+// n MMAs over consecutive K-slices of two operands: the slice-to-slice advance only changes the 14-bit start-address
+// field (bits [0,14), in 16-byte units), so the descriptors are built once and bumped by a constant (shared memory ends
+// below 2^18 bytes: the field cannot overflow into the next one)
+__device__ __forceinline__ void umma_seq(uint32_t d_tmem, uint32_t a_addr, uint32_t a_step, uint32_t a_lbo, uint32_t b_addr,
+                                         uint32_t b_step, uint32_t b_lbo, uint32_t idesc, int n, bool accumulate_first) {
+  uint64_t ad = make_desc(a_addr, a_lbo, 128), bd = make_desc(b_addr, b_lbo, 128);
+  const uint64_t da = a_step >> 4, db = b_step >> 4;
+  for (int s = 0; s < n; ++s) {
+    umma_tf32(d_tmem, ad, bd, idesc, (accumulate_first || s > 0) ? 1u : 0u);
+    ad += da; bd += db;
+  }
+}
+
 // instruction descriptor: D fp32, A/B tf32 (cute::UMMA::InstrDescriptor bit layout)
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
@@ -526,8 +539,7 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
       tc_fence_after();
       if (first_tile) mbar_wait(bar_w, 0);                      // weight image has landed
       const uint32_t id = make_idesc(128, 64, 0, 0);
-      for (int s = 0; s < inF / 8; ++s)
-        umma_tf32(tmem + cD, make_desc(aTA + s * 2 * ROWB, ROWB, 128), make_desc(aW1 + s * 2 * 1024, 1024, 128), id, s > 0);
+      umma_seq(tmem + cD, aTA, 2 * ROWB, ROWB, aW1, 2 * 1024, 1024, id, inF / 8, false);
       umma_commit(bar_m);
     }
     // ---- S3: fc1 epilogue: activation, LayerNorm -> xhat1 (K-major staging + transposed copy) ----
@@ -554,8 +566,7 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
     if (tid == 0) {
       tc_fence_after();
       const uint32_t id = make_idesc(128, 64, 0, 0);
-      for (int s = 0; s < kHF / 8; ++s)
-        umma_tf32(tmem + cD, make_desc(aP + s * 2 * ROWB, ROWB, 128), make_desc(aW2 + s * 2 * 1024, 1024, 128), id, s > 0);
+      umma_seq(tmem + cD, aP, 2 * ROWB, ROWB, aW2, 2 * 1024, 1024, id, kHF / 8, false);
       umma_commit(bar_m);
     }
     // ---- S5: fc2 epilogue ----
@@ -581,9 +592,7 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
     if (tid == 0) {
       tc_fence_after();
       const uint32_t id = make_idesc(128, NH, 0, 0);
-      for (int s = 0; s < kHF / 8; ++s)
-        umma_tf32(tmem + cDh, make_desc(aP + s * 2 * ROWB, ROWB, 128), make_desc(aWh + s * 2 * NH * 16, NH * 16, 128), id,
-                  s > 0);
+      umma_seq(tmem + cDh, aP, 2 * ROWB, ROWB, aWh, 2 * NH * 16, NH * 16, id, kHF / 8, false);
       umma_commit(bar_m);
     }
     // ---- S7: heads, loss, d(loss)/d(logits): one thread per row (warpgroup 0) ----
@@ -625,15 +634,12 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
       tc_fence_after();
       // dxhat2 = dL Wh'       (M = 128 rows, N = 64 features, K = NH) first: S9 only needs this one ...
       const uint32_t idx = make_idesc(128, 64, 0, 0);
-      for (int s = 0; s < NH / 8; ++s)
-        umma_tf32(tmem + cD, make_desc(aP + s * 2 * ROWB, ROWB, 128), make_desc(aWhT + s * 2 * 1024, 1024, 128), idx, s > 0);
+      umma_seq(tmem + cD, aP, 2 * ROWB, ROWB, aWhT, 2 * 1024, 1024, idx, NH / 8, false);
       umma_commit(bar_m);
       // ... Gh[k][a] += xhat2^T dL   (M = 64 features, N = NH, K = 128 rows; transposed tiles, K-major) runs behind the
       // first half of S9 and only gates the rewrite of TA
       const uint32_t idg = make_idesc(64, NH, 0, 0);
-      for (int s = 0; s < kTM / 8; ++s)
-        umma_tf32(tmem + cGh, make_desc(aX2T + s * 2 * kS65 * 16, kS65 * 16, 128),
-                  make_desc(aTA + s * 2 * SH * 16, SH * 16, 128), idg, (!first_tile) || s > 0);
+      umma_seq(tmem + cGh, aX2T, 2 * kS65 * 16, kS65 * 16, aTA, 2 * SH * 16, SH * 16, idg, kTM / 8, !first_tile);
       umma_commit(bar_g);
     }
     // ---- S9: LayerNorm-2 + activation backward -> dZ2 (K-major staging + transposed) ----
@@ -658,14 +664,11 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
       tc_fence_after();
       // dxhat1 = dZ2 W2'             (M = 128, N = 64, K = 64) first ...
       const uint32_t idx = make_idesc(128, 64, 0, 0);
-      for (int s = 0; s < 8; ++s)
-        umma_tf32(tmem + cD, make_desc(aP + s * 2 * ROWB, ROWB, 128), make_desc(aW2T + s * 2 * 1024, 1024, 128), idx, s > 0);
+      umma_seq(tmem + cD, aP, 2 * ROWB, ROWB, aW2T, 2 * 1024, 1024, idx, 8, false);
       umma_commit(bar_m);
       // ... G2[o][k] += dZ2^T xhat1aug   (M = 64, N = 72, K = 128 rows) behind the first half of S11
       const uint32_t idg = make_idesc(64, kHF, 0, 0);
-      for (int s = 0; s < kTM / 8; ++s)
-        umma_tf32(tmem + cG2, make_desc(aTA + s * 2 * kS65 * 16, kS65 * 16, 128),
-                  make_desc(aX1T + s * 2 * kS73 * 16, kS73 * 16, 128), idg, (!first_tile) || s > 0);
+      umma_seq(tmem + cG2, aTA, 2 * kS65 * 16, kS65 * 16, aX1T, 2 * kS73 * 16, kS73 * 16, idg, kTM / 8, !first_tile);
       umma_commit(bar_g);
     }
     // ---- S11: LayerNorm-1 + activation backward -> dZ1^T; xhat0^T re-staged from its TMEM parking columns ----
@@ -700,9 +703,7 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
       tc_fence_after();
       // G1[o][k] += dZ1^T xhat0aug   (M = 64, N = inF, K = 128 rows)
       const uint32_t idg = make_idesc(64, inF, 0, 0);
-      for (int s = 0; s < kTM / 8; ++s)
-        umma_tf32(tmem + cG1, make_desc(aTA + s * 2 * kS65 * 16, kS65 * 16, 128), make_desc(aP + s * 2 * S0 * 16, S0 * 16, 128),
-                  idg, (!first_tile) || s > 0);
+      umma_seq(tmem + cG1, aTA, 2 * kS65 * 16, kS65 * 16, aP, 2 * S0 * 16, S0 * 16, idg, kTM / 8, !first_tile);
       umma_commit(bar_m);
     }
     first_tile = false;

@@ -83,7 +83,7 @@ _SIGS = {
     "mappo_update_finish": (_i32, [C.POINTER(NetDesc), _P, _P, _i32, _i32, _P, _P, C.POINTER(_i32), _P, _P]),
     "mappo_grad_reduce": (_i32, [_P, _i32, _i32, _P, _P, C.POINTER(_i32), _P]),
     "mappo_grad_sumsq": (_i32, [_P, _i32, _P, C.POINTER(_i32), _P]),
-    "mappo_clip_adam": (_i32, [_P, _P, _P, _P, _i32, _P, _i32, _P, _P, _f32, _f32, _i32, _P, _P]),
+    "mappo_clip_adam": (_i32, [_P, _P, _P, _P, _i32, _P, _i32, _P, _P, _f32, _f32, _i32, _P, _P, _P]),
 }
 EXPORTS = tuple(_SIGS)
 

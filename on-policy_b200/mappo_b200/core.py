@@ -301,6 +301,8 @@ class FusedAdam:
         self.exp_avg = torch.zeros_like(net.flat)
         self.exp_avg_sq = torch.zeros_like(net.flat)
         self.step_dev = torch.zeros(2, dtype=torch.int32, device=net.device)      # {step, ticket}
+        # {0.9^t, 0.999^t, t}: bias-correction powers cached by the kernel (tag -1 = empty; self-validating)
+        self.beta_pow = torch.tensor([1.0, 1.0, -1.0], dtype=torch.float64, device=net.device)
         self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=net.device)
         self._lr_pinned = torch.empty(1, dtype=torch.float32).pin_memory()
         self.param_groups = [dict(lr=float(lr), eps=float(eps), betas=(0.9, 0.999), weight_decay=0.0,
@@ -331,7 +333,7 @@ class FusedAdam:
         check(lib.mappo_clip_adam(ptr(self.net.flat), ptr(self.net.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
                                   self.net.n_params, ptr(self.sumsq_part), int(n_sumsq_blocks), ptr(self.lr_dev),
                                   ptr(self.step_dev), float(self.param_groups[0]["eps"]), float(max_grad_norm),
-                                  int(bool(use_max_grad_norm)), grad_norm_out, st))
+                                  int(bool(use_max_grad_norm)), grad_norm_out, ptr(self.beta_pow), st))
 
     def step(self):
         self.sync_lr()
