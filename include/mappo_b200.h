@@ -261,9 +261,12 @@ int32_t mappo_evaluate_actions(const mappo_net_desc_t* desc, const float* params
  * mapped into this process.  out[i] = sum_p peer_bufs[p][offset_bytes + i] in rank order (bit-identical on every
  * rank).  round_dev: device uint32[2] = {completed rounds, scratch}, zero-initialised, private to this rank; every
  * rank must issue the same sequence of calls.  A region of the symmetric buffer may be rewritten once a LATER call has
- * completed locally (each call is a full barrier): alternate two regions for back-to-back reductions. */
+ * completed locally (each call is a full barrier): alternate two regions for back-to-back reductions.
+ * f32 only: sumsq_part (nullable) receives *n_sumsq_blocks_out per-CTA sums of squares of the reduced vector -- exactly
+ * what mappo_clip_adam takes, so no separate mappo_grad_sumsq launch follows the collective. */
 int32_t mappo_p2p_allreduce_f32(const void* const* peer_bufs, void* const* peer_signals, int32_t world, int32_t rank,
-                                int64_t offset_bytes, int32_t n, float* out, uint32_t* round_dev, void* stream);
+                                int64_t offset_bytes, int32_t n, float* out, uint32_t* round_dev, float* sumsq_part,
+                                int32_t* n_sumsq_blocks_out, void* stream);
 int32_t mappo_p2p_allreduce_f64(const void* const* peer_bufs, void* const* peer_signals, int32_t world, int32_t rank,
                                 int64_t offset_bytes, int32_t n, double* out, uint32_t* round_dev, void* stream);
 

@@ -108,7 +108,8 @@ int sumsq_launch(const float*, int, float*, int*, cudaStream_t);
 int clip_adam_launch(float*, const float*, float*, float*, int, const float*, int, const float*, int*, float, float,
                      int, double*, double*, cudaStream_t);
 int counter_add_launch(uint64_t*, uint64_t, cudaStream_t);
-int p2p_allreduce_f32_launch(const void* const*, void* const*, int, int, long long, int, float*, uint32_t*, cudaStream_t);
+int p2p_allreduce_f32_launch(const void* const*, void* const*, int, int, long long, int, float*, uint32_t*, float*, int*,
+                             cudaStream_t);
 int p2p_allreduce_f64_launch(const void* const*, void* const*, int, int, long long, int, double*, uint32_t*, cudaStream_t);
 int pack_rollout_launch(const NetDev&, const float*, float*, cudaStream_t);
 int rollout_image_floats(const NetDev&);
@@ -245,8 +246,10 @@ int32_t mappo_pack_rollout_weights(const mappo_net_desc_t* desc, const float* pa
 }
 
 int32_t mappo_p2p_allreduce_f32(const void* const* peer_bufs, void* const* peer_signals, int32_t world, int32_t rank,
-                                int64_t offset_bytes, int32_t n, float* out, uint32_t* round_dev, void* stream) {
-  return p2p_allreduce_f32_launch(peer_bufs, peer_signals, world, rank, offset_bytes, n, out, round_dev, (cudaStream_t)stream);
+                                int64_t offset_bytes, int32_t n, float* out, uint32_t* round_dev, float* sumsq_part,
+                                int32_t* n_sumsq_blocks_out, void* stream) {
+  return p2p_allreduce_f32_launch(peer_bufs, peer_signals, world, rank, offset_bytes, n, out, round_dev, sumsq_part,
+                                  n_sumsq_blocks_out, (cudaStream_t)stream);
 }
 int32_t mappo_p2p_allreduce_f64(const void* const* peer_bufs, void* const* peer_signals, int32_t world, int32_t rank,
                                 int64_t offset_bytes, int32_t n, double* out, uint32_t* round_dev, void* stream) {

@@ -48,8 +48,11 @@ __device__ __forceinline__ float4 ld_peer4(const float* p) {
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-p2p_allreduce_kernel(const P2PArgs a, long long offset_bytes, int n, T* __restrict__ out, uint32_t* __restrict__ round_dev) {
+p2p_allreduce_kernel(const P2PArgs a, long long offset_bytes, int n, T* __restrict__ out, uint32_t* __restrict__ round_dev,
+                     float* __restrict__ sumsq_part) {
   __shared__ uint32_t s_round;
+  __shared__ float s_sq[8];
+  float sq = 0.f;
   if (threadIdx.x == 0) s_round = round_dev[0] + 1;
   __syncthreads();
   const uint32_t round = s_round;
@@ -65,21 +68,42 @@ p2p_allreduce_kernel(const P2PArgs a, long long offset_bytes, int n, T* __restri
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
   if (sizeof(T) == 4 && (n & 3) == 0 && (offset_bytes & 15) == 0) {
     for (int i = tid; i < n / 4; i += nt) {
+      float4 v[kMaxPeers];
+#pragma unroll
+      for (int p = 0; p < kMaxPeers; ++p)               // every peer's load in flight at once: ONE NVLink round trip
+        if (p < a.world)
+          v[p] = ld_peer4(reinterpret_cast<const float*>(static_cast<const char*>(a.buf[p]) + offset_bytes) + 4 * i);
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-      for (int p = 0; p < a.world; ++p) {
-        const float4 v = ld_peer4(reinterpret_cast<const float*>(static_cast<const char*>(a.buf[p]) + offset_bytes) + 4 * i);
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-      }
+#pragma unroll
+      for (int p = 0; p < kMaxPeers; ++p)               // summed in rank order: bit-identical on every rank
+        if (p < a.world) { s.x += v[p].x; s.y += v[p].y; s.z += v[p].z; s.w += v[p].w; }
       reinterpret_cast<float4*>(out)[i] = s;
+      sq = fmaf(s.x, s.x, fmaf(s.y, s.y, fmaf(s.z, s.z, fmaf(s.w, s.w, sq))));
     }
   } else {
     for (int i = tid; i < n; i += nt) {
+      T v[kMaxPeers];
+#pragma unroll
+      for (int p = 0; p < kMaxPeers; ++p)
+        if (p < a.world) v[p] = ld_peer<T>(reinterpret_cast<const T*>(static_cast<const char*>(a.buf[p]) + offset_bytes) + i);
       T s = (T)0;
-#pragma unroll 1
-      for (int p = 0; p < a.world; ++p)
-        s += ld_peer<T>(reinterpret_cast<const T*>(static_cast<const char*>(a.buf[p]) + offset_bytes) + i);
+#pragma unroll
+      for (int p = 0; p < kMaxPeers; ++p)
+        if (p < a.world) s += v[p];
       out[i] = s;
+      sq = fmaf((float)s, (float)s, sq);
+    }
+  }
+  if (sumsq_part) {                                     // per-CTA sum of squares of the reduced vector (for clip_grad_norm_)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if ((threadIdx.x & 31) == 0) s_sq[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t += s_sq[q];
+      sumsq_part[blockIdx.x] = t;
     }
   }
   // completion: the last CTA to finish publishes the round (round_dev[1] is its ticket counter)
@@ -93,7 +117,7 @@ p2p_allreduce_kernel(const P2PArgs a, long long offset_bytes, int n, T* __restri
 
 template <typename T>
 static int launch_p2p(const void* const* bufs, void* const* sigs, int world, int rank, long long offset_bytes, int n, T* out,
-                      uint32_t* round_dev, cudaStream_t st) {
+                      uint32_t* round_dev, float* sumsq_part, int* n_blocks_out, cudaStream_t st) {
   if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) { set_error("p2p_allreduce: world %d / rank %d", world, rank); return MAPPO_ERR_INVALID; }
   if (!bufs || !sigs || !out || !round_dev || n <= 0) { set_error("p2p_allreduce: NULL / empty"); return MAPPO_ERR_INVALID; }
   P2PArgs a;
@@ -102,13 +126,18 @@ static int launch_p2p(const void* const* bufs, void* const* sigs, int world, int
   int blocks = (n / 4 + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > 64) blocks = 64;
-  p2p_allreduce_kernel<T><<<blocks, 256, 0, st>>>(a, offset_bytes, n, out, round_dev);
+  if (n_blocks_out) *n_blocks_out = blocks;
+  p2p_allreduce_kernel<T><<<blocks, 256, 0, st>>>(a, offset_bytes, n, out, round_dev, sumsq_part);
   return check_launch("p2p_allreduce_kernel");
 }
 
 int p2p_allreduce_f32_launch(const void* const* bufs, void* const* sigs, int world, int rank, long long off, int n, float* out,
-                             uint32_t* round_dev, cudaStream_t st) { return launch_p2p<float>(bufs, sigs, world, rank, off, n, out, round_dev, st); }
+                             uint32_t* round_dev, float* sumsq_part, int* n_blocks_out, cudaStream_t st) {
+  return launch_p2p<float>(bufs, sigs, world, rank, off, n, out, round_dev, sumsq_part, n_blocks_out, st);
+}
 int p2p_allreduce_f64_launch(const void* const* bufs, void* const* sigs, int world, int rank, long long off, int n, double* out,
-                             uint32_t* round_dev, cudaStream_t st) { return launch_p2p<double>(bufs, sigs, world, rank, off, n, out, round_dev, st); }
+                             uint32_t* round_dev, cudaStream_t st) {
+  return launch_p2p<double>(bufs, sigs, world, rank, off, n, out, round_dev, nullptr, nullptr, st);
+}
 
 }  // namespace mappo

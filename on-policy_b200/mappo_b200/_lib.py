@@ -58,7 +58,7 @@ _SIGS = {
     "mappo_rollout_image_floats": (_i32, [C.POINTER(NetDesc)]),
     "mappo_pack_rollout_weights": (_i32, [C.POINTER(NetDesc), _P, _P, _P]),
     "mappo_counter_add": (_i32, [_P, _u64, _P]),
-    "mappo_p2p_allreduce_f32": (_i32, [_P, _P, _i32, _i32, _i64, _i32, _P, _P, _P]),
+    "mappo_p2p_allreduce_f32": (_i32, [_P, _P, _i32, _i32, _i64, _i32, _P, _P, _P, _P, _P]),
     "mappo_p2p_allreduce_f64": (_i32, [_P, _P, _i32, _i32, _i64, _i32, _P, _P, _P]),
     "mappo_env_insert": (_i32, [_P] * 6 + [_i32] * 5 + [_P] * 8 + [_P, _u64] + [_P]),
     "mappo_compute_returns": (_i32, [_P] * 6 + [_i32, _i32, _f32, _f32, _i32, _i32] + [_P] * 3 + [_P]),

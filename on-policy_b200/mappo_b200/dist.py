@@ -83,11 +83,16 @@ class P2PReducer:
     def _stream(self):
         return self.C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
-    def allreduce_grad(self, parity: int, out: torch.Tensor):
-        """out[:] = sum over ranks of grad_half(parity)  (out is an ordinary local tensor)."""
+    def allreduce_grad(self, parity: int, out: torch.Tensor, sumsq_part: torch.Tensor = None) -> int:
+        """out[:] = sum over ranks of grad_half(parity)  (out is an ordinary local tensor).  With `sumsq_part` the
+        kernel also leaves per-CTA sums of squares of the result there; returns how many."""
+        nb = self.C.c_int32(0)
         rc = self.lib.mappo_p2p_allreduce_f32(self.bufs, self.sigs, self.world, self.rank, 4 * self.off_grad[parity & 1],
-                                              out.numel(), out.data_ptr(), self.round.data_ptr(), self._stream())
+                                              out.numel(), out.data_ptr(), self.round.data_ptr(),
+                                              None if sumsq_part is None else sumsq_part.data_ptr(),
+                                              self.C.byref(nb), self._stream())
         _check(self.lib, rc)
+        return nb.value if sumsq_part is not None else 0
 
     def allreduce_f64_(self, t: torch.Tensor, region: str):
         """In-place sum over ranks of a small fp64 tensor through the 'stats' or 'loss' region."""

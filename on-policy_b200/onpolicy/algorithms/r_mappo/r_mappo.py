@@ -70,6 +70,7 @@ class R_MAPPO():
         policy.critic.grad = self._joint_grad[na + pad:]
         self._crit_off = na + pad
         self._p2p, self._p2p_tried, self._parity = None, False, 0
+        self._p2p_nets, self._par = None, [0, 0]
         self._ws = {}
         self._loss_out = torch.zeros(6, dtype=torch.float64, device=self.device)
 
@@ -89,13 +90,30 @@ class R_MAPPO():
         loss_c = make_loss_cfg(self.args, update_actor)
         vn = self.value_normalizer.state if self.value_normalizer is not None else None
 
+        # data parallel with the peer-memory kernel: every net has its OWN reducer (buffer, signal pads, round counter),
+        # so the actor and the critic chain stay independent across ranks too -- one all-reduce per optimiser step of
+        # each optimiser, issued inside that net's chain
+        per_net = allreduce is not None and only is not None and self._p2p_nets is not None
+
+        def p2p_chain(k, net, ws, loss, a_stats, vn_state, opt, slot):
+            r, par = self._p2p_nets[k], self._par[k]
+            launch_grads(net, ws, batch, loss, norm_stats, a_stats, vn_state, loss_out,
+                         grad_out=r.grad_half(par)[:net.n_params])       # local gradient straight into the peer-visible half
+            nb = r.allreduce_grad(par, net.grad, ws.sumsq_part)      # + the partial sums of squares clip_adam needs
+            self._par[k] ^= 1
+            launch_step(net, ws, loss_out, opt, self.max_grad_norm, self._use_max_grad_norm, slot, nb)
+
         def actor_chain():          # backward, clip, step (reference :141-153)
+            if per_net:
+                return p2p_chain(0, pol.actor, ws_a, loss_a, adv_stats, None, pol.actor_optimizer, 3)
             launch_update(pol.actor, ws_a, batch, loss_a, norm_stats, adv_stats, None, loss_out, pol.actor_optimizer,
                           self.max_grad_norm, self._use_max_grad_norm, 3, allreduce)
 
         def critic_chain():         # ValueNorm.update(return_batch) BEFORE the value loss (reference :65), then :156-167
             if vn is not None:
                 check(_lib.load().mappo_valuenorm_update(ptr(vn), ptr(norm_stats), stream_ptr()))
+            if per_net:
+                return p2p_chain(1, pol.critic, ws_c, loss_c, None, vn, pol.critic_optimizer, 4)
             launch_update(pol.critic, ws_c, batch, loss_c, norm_stats, None, vn, loss_out, pol.critic_optimizer,
                           self.max_grad_norm, self._use_max_grad_norm, 4, allreduce)
 
@@ -161,6 +179,13 @@ class R_MAPPO():
             actor_chain()
             critic_chain()
 
+    def _restore_parity(self, k):
+        """The reducers alternate two halves of their buffer (each round is a full barrier).  A captured graph replays a
+        FIXED parity sequence, so an odd number of reductions per train() is padded with one 4-float round."""
+        if self._p2p_nets is not None and self._par[k] & 1:
+            self._p2p_nets[k].allreduce_grad(self._par[k], self._par_scratch)
+            self._par[k] ^= 1
+
     def _storage_batch(self, buffer, adv, rows, first, seq_len):
         b = Batch()
         T = buffer.episode_length
@@ -188,6 +213,11 @@ class R_MAPPO():
         try:
             from mappo_b200.dist import P2PReducer
             self._p2p = P2PReducer(self.device, self._joint_grad.numel(), n_stats)
+            if os.environ.get("MAPPO_B200_P2P_JOINT", "0") != "1":
+                self._p2p_nets = (P2PReducer(self.device, self.policy.actor.n_params, 4),
+                                  P2PReducer(self.device, self.policy.critic.n_params, 4))
+                self._par = [0, 0]
+                self._par_scratch = torch.zeros(4, dtype=torch.float32, device=self.device)
         except Exception as e:                       # no symmetric memory on this system: stay on NCCL
             import sys
             print(f"[mappo_b200] peer-memory all-reduce unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
@@ -280,20 +310,26 @@ class R_MAPPO():
                 self._one_update(batches[u], rows.numel(), stats[4 * u:4 * u + 4], adv_stats, loss_out, update_actor,
                                  allreduce, only)
 
-        if self.overlap_nets and allreduce is None:
+        if self.overlap_nets and (allreduce is None or self._p2p_nets is not None):
             # actor and critic never read each other's state inside train(): their whole update sequences are two
             # independent chains (fork once, join once).  Free-running, the two 75-CTA update kernels interleave on
-            # the 148 SMs instead of colliding in lock step (150 CTAs = two waves).
+            # the 148 SMs instead of colliding in lock step (150 CTAs = two waves).  Multi-GPU: each chain carries its
+            # own peer-memory all-reduce (per-net reducers), so the chains stay independent across ranks as well.
             if self._side is None:
                 self._side = torch.cuda.Stream(device=self.device)
             main = torch.cuda.current_stream()
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
                 updates("critic")
+                self._restore_parity(1)
             updates("actor")
+            self._restore_parity(0)
             main.wait_stream(self._side)
         else:
             updates(None)
+            if p2p is not None and self._parity & 1:          # joint reducer: same fixed-parity rule under graph replay
+                p2p.allreduce_grad(self._parity, self._joint_grad[:4].clone())
+                self._parity ^= 1
         if allreduce is not None:
             # loss scalars are partial sums over local rows (global normalisers); norms are already global
             part = loss_out.clone()
