@@ -370,6 +370,10 @@ clip_adam_kernel(float* __restrict__ p, const float* __restrict__ grad, float* _
   __shared__ float s_total, s_coef, s_step_size, s_bc2_sqrt;
   __shared__ int s_step;
   __shared__ double s_p1, s_p2;
+  // this thread's operands first: their latency overlaps the scalar prologue below instead of following it
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float g_in = 0.f, m_in = 0.f, v_in = 0.f, p_in = 0.f;
+  if (i < P) { g_in = grad[i]; m_in = m[i]; v_in = v[i]; p_in = p[i]; }
   // every block re-derives the global norm from the per-block partials (n_part is small) in a fixed order; the
   // scalar prologue (norm, clip coefficient, Adam bias corrections in fp64) runs in ONE warp and is broadcast
   if (threadIdx.x < 32) {
@@ -397,13 +401,12 @@ clip_adam_kernel(float* __restrict__ p, const float* __restrict__ grad, float* _
   __syncthreads();
   const float total = s_total, coef = s_coef, step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
   const int step = s_step;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < P) {
-    const float g = grad[i] * coef;
-    const float mi = m[i] + (g - m[i]) * (float)(1.0 - 0.9);                  // torch: exp_avg.lerp_(grad, 1 - beta1)
-    const float vi = v[i] * 0.999f + (float)(1.0 - 0.999) * g * g;            // exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
+    const float g = g_in * coef;
+    const float mi = m_in + (g - m_in) * (float)(1.0 - 0.9);                  // torch: exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = v_in * 0.999f + (float)(1.0 - 0.999) * g * g;            // exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = p[i] - step_size * (mi / denom);
+    p[i] = p_in - step_size * (mi / denom);
     m[i] = mi;
     v[i] = vi;
   }

@@ -101,3 +101,30 @@ def test_unsupported_configurations_fail_loudly():
     # empty inputs are accepted where the reference would simply loop zero times
     assert lib.mappo_gather_rows(None, None, 0, 4, None, None) == 0
     assert lib.mappo_randperm(0, 1, None, None, None) == 0
+
+
+def test_share_obs_derived_from_obs_is_identical_at_full_size():
+    """Centralised-V feeds (share_obs = all agents' obs of the rollout thread, mpe_runner.py:133-135): staging only obs
+    and letting the critic read its rows from it gives bit-identical storage, values, actions and returns -- with a
+    quarter of the host->device bytes."""
+    from mappo_b200.engine import RolloutEngine
+    cfg = c2()
+    feed = O.make_feed(cfg, seed=5, kind="mpe")
+    outs = []
+    for share_from_obs in (False, True):
+        torch.manual_seed(1)
+        args, policy, trainer, buf = TP.build(cfg)
+        eng = RolloutEngine(args, policy, trainer, buf, rng="device", seed=3, share_obs_from_obs=share_from_obs)
+        assert eng.share_from_obs == share_from_obs
+        eng.stage_feed(feed)
+        eng.upload()
+        eng.launch_iteration()
+        torch.cuda.synchronize()
+        outs.append((eng.h2d_bytes(), [t.clone() for t in (buf.share_obs, buf.obs, buf.value_preds, buf.actions,
+                                                          buf.action_log_probs, buf.rewards, buf.masks,
+                                                          policy.actor.flat, policy.critic.flat)]))
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert torch.equal(a, b)
+    assert outs[1][0] * 3 < outs[0][0]
+    # (after_update moved the last slot to slot 0)
+    assert torch.equal(outs[1][1][0][0].cpu(), torch.from_numpy(feed.share_obs[-1].reshape(outs[1][1][0][0].shape)))
