@@ -2,9 +2,11 @@
 // accumulators in TMEM, weights delivered by one TMA bulk copy).  Same contract as update_mlp_kernel (update_mlp.cu):
 // index-driven gather -> forward -> losses -> backward -> per-CTA gradient slot, one launch per net per step.
 //
-// Tile = 128 rows = UMMA M = the 128 TMEM lanes: thread r of the CTA owns row r end to end.  After each MMA the
-// thread pulls ITS row of the accumulator out of TMEM (tcgen05.ld 32x32b) and does bias/activation/LayerNorm in
-// registers -- no cross-thread reductions, no barriers inside a layer.
+// Tile = 128 rows = UMMA M = the 128 TMEM lanes, TWO threads per row: warps w and w + 4 address the same 32 TMEM lanes,
+// warpgroup g owns hidden columns [32 g, 32 g + 32).  After each MMA a thread pulls ITS half row of the accumulator out
+// of TMEM (tcgen05.ld 32x32b) and does activation / LayerNorm in registers; the two halves of a row meet on a 64-thread
+// named barrier and swap their partial sums through shared memory (PairXch).  One thread per row was a 16 K-instruction
+// dependent chain on one warp per scheduler; two halve it.
 //
 // Operand layout: every operand is K-major, no swizzle ("interleaved" canonical layout): an R x K operand is stored
 // as [K/4][R(+pad)][4] floats, i.e. the 16-byte unit of 4 consecutive K-elements of row r sits at
