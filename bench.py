@@ -181,9 +181,16 @@ def run_gpu(a):
     trainer = R_MAPPO(args, policy, device=dev)
     buf = SharedReplayBuffer(args, cfg.num_agents, obs_s, share_s, act_s)
     feed = O.make_feed(cfg, seed=100 + rank)               # each rank owns its own 128 rollout threads
-    eng = RolloutEngine(args, policy, trainer, buf, rng="device", seed=1 + rank, share_obs_from_obs=True)
-    eng.stage_feed(feed)
-    eng.upload()
+    if a.env == "device":
+        # closed loop: the simple_spread worlds are stepped on the GPU between policy_step and insert
+        from mappo_b200.mpe_env import DeviceSpreadEnv
+        env = DeviceSpreadEnv(cfg.n_rollout_threads, cfg.num_agents, 3, cfg.episode_length, device=dev, seed=100 + rank)
+        eng = RolloutEngine(args, policy, trainer, buf, rng="device", seed=1 + rank, device_env=env)
+        eng.reset_env()
+    else:
+        eng = RolloutEngine(args, policy, trainer, buf, rng="device", seed=1 + rank, share_obs_from_obs=True)
+        eng.stage_feed(feed)
+        eng.upload()
     torch.cuda.synchronize()
     graph_ok = not a.eager
     try:
@@ -284,6 +291,7 @@ def run_gpu(a):
                                                                "NCCL all-reduce via torch.distributed between graph segments"),
                                                                 "rng": "device (Philox sampling, Feistel permutations)",
                                                 "rollout": "persistent kernel, one launch per iteration" if eng.persistent_rollout else "one launch per env step",
+                                                "env": "device-side simple_spread, closed loop (policy_step -> env step -> insert per step)" if a.env == "device" else "synthetic staged env outputs",
                                                 "h2d": "obs, rewards, dones (share_obs = concat of the thread's agents' obs is formed on the device)" if eng.share_from_obs else "obs, share_obs, rewards, dones"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": eng.h2d_bytes(), "d2h_bytes_per_step": 48,
                         "ms_per_step": e2e_ms_max / a.steps},
@@ -353,6 +361,9 @@ def main():
     ap.add_argument("--gemm", default=os.environ.get("MAPPO_B200_GEMM", "tf32"), choices=["tf32", "fp32"],
                     help="GEMM engine of the update kernels (tf32 = tcgen05 tensor cores)")
     ap.add_argument("--eager", action="store_true", help="no CUDA graph (for per-kernel profiling under ncu)")
+    ap.add_argument("--env", default="staged", choices=["staged", "device"],
+                    help="staged: synthetic env outputs uploaded per iteration (the BASELINE metric: the path only); "
+                         "device: closed loop with the device-side simple_spread environment")
     ap.add_argument("--cpu-iters", type=int, default=100, help="oracle iterations for cpu_baseline (rank 0, N=1)")
     a = ap.parse_args()
     if a.impl == "reference":

@@ -154,6 +154,24 @@ int32_t mappo_rollout_persistent(const mappo_net_desc_t* actor_desc, const float
 int32_t mappo_rollout_image_floats(const mappo_net_desc_t* desc);
 int32_t mappo_pack_rollout_weights(const mappo_net_desc_t* desc, const float* params, float* image, void* stream);
 
+/* ---- f1: device-side environment -------------------------------------------------------------------
+ * One step of n_envs vectorised MPE `simple_spread` worlds (envs/env_wrappers.py:140-154 -> envs/mpe/environment.py:115-146
+ * -> envs/mpe/core.py:207-323 + scenarios/simple_spread.py:32-103): action decoding, action and contact forces, damped
+ * integration, shared reward, observations, done = step >= episode_length, auto-reset (the reset observation replaces the
+ * terminal one).  State (float64, the reference's precision; owned by the caller): agent_pos / agent_vel
+ * [n_envs, num_agents, 2], landmark_pos [n_envs, num_landmarks, 2], step_count [n_envs].
+ * actions [n_envs * num_agents]: integer-valued floats in 0..4 exactly as mappo_policy_step stores them; NULL = reset all
+ * worlds (writes obs only).  reset_states [n_envs, 2 (agents + landmarks)] (nullable): the positions a world restarts
+ * from -- NumPy's global Mersenne stream cannot be reproduced on a device, so parity tests inject the reference's draws;
+ * NULL draws uniform(-1, 1) / 0.8 uniform(-1, 1) from Philox (rng_seed, *rng_counter_dev; the counter advances).
+ * Outputs in the layout mappo_env_insert / mappo_rollout_persistent consume: obs [E, D] (D = 4 + 2 L + 4 (M - 1)),
+ * share_obs [E, M D] (nullable; the thread's obs concatenated, mpe_runner.py:133-135), rewards [E], dones [E] (1.0 / 0.0). */
+int32_t mappo_mpe_spread_step(double* agent_pos, double* agent_vel, double* landmark_pos, int32_t* step_count,
+                              const float* actions, const double* reset_states, uint64_t rng_seed,
+                              uint64_t* rng_counter_dev, int32_t n_envs, int32_t num_agents, int32_t num_landmarks,
+                              int32_t episode_length, float* obs_out, float* share_obs_out, float* rewards_out,
+                              float* dones_out, void* stream);
+
 /* Advance the device-side Philox offset after a sampling step (no host round trip). */
 int32_t mappo_counter_add(uint64_t* counter_dev, uint64_t inc, void* stream);
 

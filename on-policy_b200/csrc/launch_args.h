@@ -42,6 +42,19 @@ struct RolloutArgs {
   int share_agents;            // > 0: no staged share_obs -- a critic row is the concatenation of the obs rows of the
                                // `share_agents` agents of its rollout thread (mpe_runner.py:133-135), read from f_obs
 };
+// f1: vectorised MPE simple_spread worlds (mpe_env.cu)
+struct MpeArgs {
+  double *apos, *avel, *lpos;            // [N][M][2], [N][M][2], [N][L][2]
+  int32_t* step_count;                   // [N]
+  const float* actions;                  // [N*M] integer-valued (Discrete(5)); NULL = reset only
+  const double* reset_states;            // [N][2 (M + L)] or NULL (device RNG)
+  uint64_t rng_seed;
+  const uint64_t* rng_counter;
+  int N, M, L, episode_length;
+  float *obs, *share_obs, *rewards, *dones;   // [N*M][D], [N*M][M*D] (nullable), [N*M], [N*M]
+};
+int mpe_spread_launch(const MpeArgs& a, cudaStream_t st);
+
 int rollout_persistent_launch(const NetDev& na, const NetDev& nc, const RolloutArgs& a, cudaStream_t st);
 int policy_step_launch(const NetDev* na, const NetDev* nc, const PolArgs& a, cudaStream_t st);
 int env_insert_launch(const InsertArgs& a, cudaStream_t st);

@@ -66,6 +66,7 @@ _SIGS = {
     "mappo_evaluate_actions": (_i32, [C.POINTER(NetDesc), _P, C.POINTER(Batch), C.POINTER(LossCfg), _P, _P, _P, _P, _P]),
     "mappo_minibatch_stats": (_i32, [_P, _P, _P, _i32, _P, _P]),
     "mappo_debug_launch_count": (_i64, []),
+    "mappo_mpe_spread_step": (_i32, [_P, _P, _P, _P, _P, _P, _u64, _P, _i32, _i32, _i32, _i32, _P, _P, _P, _P, _P]),
     "mappo_minibatch_stats_batch": (_i32, [_P, _P, _P, _i64, _i32, _i32, _P, _P]),
     "mappo_randperm_batch": (_i32, [_i32, _i32, _u64, _P, _P, _P]),
     "mappo_valuenorm_update": (_i32, [_P, _P, _P]),

@@ -59,10 +59,12 @@ INFO_KEYS = ("value_loss", "policy_loss", "dist_entropy", "actor_grad_norm", "cr
 
 class RolloutEngine:
     def __init__(self, args, policy, trainer, buffer, rng: str = "device", seed: int = 1,
-                 share_obs_from_obs: bool = False):
+                 share_obs_from_obs: bool = False, device_env=None):
         """share_obs_from_obs: the env's share_obs is the concatenation of the obs of the agents of a rollout thread
         (what the MPE runner builds on the host, mpe_runner.py:133-135): only obs is staged / uploaded and the critic
-        reads its rows from it on the device (feed-forward policies, persistent rollout)."""
+        reads its rows from it on the device (feed-forward policies, persistent rollout).
+        device_env: a mappo_b200.mpe_env.DeviceSpreadEnv -- CLOSED LOOP: every collect step is policy_step -> env step ->
+        insert on the device (no staged feed, no upload; the env writes into the staging buffers the insert reads)."""
         self.args, self.policy, self.trainer, self.buffer = args, policy, trainer, buffer
         self.dev = policy.device
         self.rng = rng
@@ -78,7 +80,12 @@ class RolloutEngine:
         T, E = self.T, self.E
         f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.dev)
         import os
-        self.persistent_rollout = os.environ.get("MAPPO_B200_PERSISTENT_ROLLOUT", "1") == "1"
+        self.env = device_env
+        self.env_reset_states = None        # optional [T, N, 2 (M + L)] float64: injected episode starts (parity tests)
+        self.persistent_rollout = os.environ.get("MAPPO_B200_PERSISTENT_ROLLOUT", "1") == "1" and device_env is None
+        if device_env is not None and (device_env.N * device_env.M != E or device_env.obs_dim != self.Do
+                                       or device_env.share_dim != self.Ds):
+            raise ValueError("device_env does not match the rollout storage (rows / obs_dim / share_obs_dim)")
         self.share_from_obs = bool(share_obs_from_obs) and self.persistent_rollout and not self.recurrent \
             and self.Ds % self.Do == 0 and E % (self.Ds // self.Do) == 0
         # device staging of one iteration of env outputs (next obs for slots 1..T, rewards, dones, ...): ONE flat buffer
@@ -150,8 +157,15 @@ class RolloutEngine:
     def h2d_bytes(self):
         return int(sum(v.numel() * v.element_size() for v in self.host.values()))
 
+    def reset_env(self, reset_states=None):
+        """Closed loop: envs.reset() into storage slot 0 (the runner's warmup, mpe_runner.py:81-93)."""
+        self.env.reset(self.buffer.obs[0].view(self.E, self.Do), self.buffer.share_obs[0].view(self.E, self.Ds),
+                       reset_states=reset_states)
+
     def upload(self):
         """Host -> device copy of this iteration's inputs (async, current stream)."""
+        if self.env is not None:
+            return                                             # closed loop: nothing comes from the host
         h = self.host
         self.d_stage.copy_(h["stage"], non_blocking=True)
         if "active" in h:
@@ -189,6 +203,9 @@ class RolloutEngine:
             ptr(b.value_preds[t]), ptr(b.actions[t]), None, ptr(b.action_log_probs[t]),
             ptr(b.rnn_states[t + 1]) if rec else None, ptr(b.rnn_states_critic[t + 1]) if rec else None,
             ptr(self.img_actor), ptr(self.img_critic), st))
+        if self.env is not None:             # closed loop: the env consumes the actions just written to slot t
+            rs = self.env_reset_states[t] if self.env_reset_states is not None else None
+            self.env.step(b.actions[t], self.d_obs[t], self.d_share[t], self.d_rew[t], self.d_done[t], reset_states=rs)
         check(lib.mappo_env_insert(
             ptr(self.d_obs[t]), ptr(self.d_share[t]), ptr(self.d_rew[t]), ptr(self.d_done[t]),
             ptr(self.d_active[t]) if self.d_active is not None else None,

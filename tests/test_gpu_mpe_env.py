@@ -1,0 +1,105 @@
+"""B200: the device environment (mappo_mpe_spread_step, csrc/mpe_env.cu) against the reference-generated fixture and the
+oracle, standalone and in the closed rollout loop of the engine."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mappo_oracle as O
+from oracle.mpe_oracle import SpreadVecEnv
+import test_gpu_parity as TP
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mpe_simple_spread.npz")
+# float64 state, the reference's operation order, no FMA contraction: only exp / log1p of the contact term may differ in the
+# last bits from glibc; observations / rewards are compared after the float32 cast the rollout storage applies.
+RTOL, ATOL = 1e-6, 1e-6
+
+
+def test_device_env_follows_the_reference_trajectories():
+    from mappo_b200.mpe_env import DeviceSpreadEnv
+    g = np.load(GOLD)
+    N, T = g["obs0"].shape[0], g["actions"].shape[0]
+    env = DeviceSpreadEnv(N, 3, 3, int(g["episode_length"]), device="cuda", seed=3)
+    f = lambda *s: torch.zeros(*s, dtype=torch.float32, device="cuda")
+    obs, share, rew, done = f(N * 3, 18), f(N * 3, 54), f(N * 3), f(N * 3)
+    env.reset(obs, share, reset_states=g["resets"][:, 0])
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(obs.cpu().numpy().reshape(N, 3, 18), g["obs0"].astype(np.float32))
+    ep = np.zeros(N, dtype=np.int64)
+    last = g["resets"].shape[1] - 1
+    exact = 0
+    for t in range(T):
+        nxt = g["resets"][np.arange(N), np.minimum(ep + 1, last)]
+        act = torch.from_numpy(g["actions"][t].reshape(-1).astype(np.float32)).cuda()
+        env.step(act, obs, share, rew, done, reset_states=nxt)
+        torch.cuda.synchronize()
+        o = obs.cpu().numpy().reshape(N, 3, 18)
+        np.testing.assert_allclose(o, g["obs"][t].astype(np.float32), rtol=RTOL, atol=ATOL, err_msg=f"obs t={t}")
+        np.testing.assert_allclose(rew.cpu().numpy().reshape(N, 3, 1), g["rewards"][t].astype(np.float32), rtol=RTOL,
+                                   atol=ATOL, err_msg=f"rewards t={t}")
+        np.testing.assert_array_equal(done.cpu().numpy().reshape(N, 3) != 0, g["dones"][t])
+        np.testing.assert_array_equal(share.cpu().numpy().reshape(N, 3, 54),
+                                      np.repeat(o.reshape(N, 1, 54), 3, axis=1))         # mpe_runner.py:133-135
+        exact += int(np.array_equal(o, g["obs"][t].astype(np.float32)))
+        ep += g["dones"][t][:, 0]
+    assert exact >= T - 8            # bit-identical after the fp32 cast except around contacts
+
+
+def test_device_rng_resets_are_inside_the_reference_ranges():
+    from mappo_b200.mpe_env import DeviceSpreadEnv
+    env = DeviceSpreadEnv(512, 3, 3, 25, device="cuda", seed=7)
+    obs = torch.zeros(512 * 3, 18, device="cuda")
+    env.reset(obs)
+    torch.cuda.synchronize()
+    a, l = env.apos.cpu().numpy(), env.lpos.cpu().numpy()
+    assert np.all(np.abs(a) < 1.0) and np.all(np.abs(l) < 0.8) and np.all(env.avel.cpu().numpy() == 0)
+    assert abs(a.mean()) < 0.05 and abs(a.std() - 1 / np.sqrt(3)) < 0.03        # uniform(-1, 1)
+    first = a.copy()
+    env.reset(obs)
+    torch.cuda.synchronize()
+    assert not np.array_equal(first, env.apos.cpu().numpy())                    # the counter advanced
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_closed_loop_iteration_is_consistent_with_the_oracle_env(graph):
+    """Engine in closed loop (policy_step -> device env -> insert, T times, then GAE + train): replaying the actions it
+    stored through the oracle environment from the same episode starts reproduces the stored observations, share_obs,
+    rewards and masks."""
+    from mappo_b200.engine import RolloutEngine
+    from mappo_b200.mpe_env import DeviceSpreadEnv
+    cfg = O.PathConfig(episode_length=25, n_rollout_threads=16, num_agents=3, obs_dim=18, share_obs_dim=54,
+                       act_dims=(5,), use_ReLU=False, ppo_epoch=2, num_mini_batch=1, lr=7e-4, critic_lr=7e-4)
+    torch.manual_seed(1)
+    args, policy, trainer, buf = TP.build(cfg)
+    N, T = cfg.n_rollout_threads, cfg.episode_length
+    env = DeviceSpreadEnv(N, 3, 3, T, device="cuda", seed=5)
+    ref = SpreadVecEnv(N, 3, 3, T, seed=11)
+    starts = ref.draw_reset_states(N)
+    nxt = ref.draw_reset_states(N)
+    eng = RolloutEngine(args, policy, trainer, buf, rng="device", seed=2, device_env=env)
+    rs = torch.from_numpy(np.repeat(nxt[None], T, axis=0)).cuda()               # same restart state whenever an episode ends
+    eng.env_reset_states = rs
+    if graph:
+        eng.reset_env(reset_states=starts)
+        eng.capture(warmup=1)
+    eng.reset_env(reset_states=starts)
+    eng.step_resident()
+    torch.cuda.synchronize()
+    obs0 = ref.reset(starts)
+    # storage after after_update(): slot 0 = last slot; replay from the stored actions
+    acts = buf.actions.cpu().numpy().reshape(T, N, 3).astype(np.int64)
+    want_obs, want_rew, want_done = [], [], []
+    for t in range(T):
+        o, r, d = ref.step(acts[t], nxt)
+        want_obs.append(o); want_rew.append(r); want_done.append(d)
+    got_obs = buf.obs.cpu().numpy()
+    np.testing.assert_allclose(got_obs[1:], np.array(want_obs).astype(np.float32), rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(buf.rewards.cpu().numpy(), np.array(want_rew).astype(np.float32), rtol=RTOL, atol=ATOL)
+    np.testing.assert_array_equal(buf.masks.cpu().numpy()[1:, :, :, 0], 1.0 - np.array(want_done).astype(np.float32))
+    np.testing.assert_array_equal(buf.share_obs.cpu().numpy()[1:],
+                                  np.repeat(got_obs[1:].reshape(T, N, 1, 54), 3, axis=2))
+    assert want_done[-1].all()                                                  # world_length == episode_length
+    assert np.isfinite(policy.actor.flat.cpu().numpy()).all()
+    del obs0
