@@ -290,8 +290,8 @@ def run_gpu(a):
                                                                if getattr(trainer, "_p2p", None) is not None else
                                                                "NCCL all-reduce via torch.distributed between graph segments"),
                                                                 "rng": "device (Philox sampling, Feistel permutations)",
-                                                "rollout": "persistent kernel, one launch per iteration" if eng.persistent_rollout else "one launch per env step",
-                                                "env": "device-side simple_spread, closed loop (policy_step -> env step -> insert per step)" if a.env == "device" else "synthetic staged env outputs",
+                                                "rollout": "persistent kernel, one launch per iteration" if (eng.persistent_rollout or eng.closed_persistent) else "one launch per env step",
+                                                "env": ("device-side simple_spread, closed loop " + ("inside one persistent rollout kernel" if eng.closed_persistent else "(policy_step -> env step -> insert per step)")) if a.env == "device" else "synthetic staged env outputs",
                                                 "h2d": "obs, rewards, dones (share_obs = concat of the thread's agents' obs is formed on the device)" if eng.share_from_obs else "obs, share_obs, rewards, dones"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": eng.h2d_bytes(), "d2h_bytes_per_step": 48,
                         "ms_per_step": e2e_ms_max / a.steps},

@@ -151,6 +151,22 @@ int32_t mappo_rollout_persistent(const mappo_net_desc_t* actor_desc, const float
                                  const float* f_obs, const float* f_share, const float* f_rew, const float* f_done,
                                  const float* f_active, const float* f_avail, const float* exp_noise, uint64_t rng_seed,
                                  uint64_t* rng_offset_dev, int32_t T, int32_t E, void* stream);
+/* The CLOSED rollout loop of one iteration as one launch (feed-forward policies, MPE simple_spread worlds on the device):
+ * T x [mappo_policy_step -> mappo_mpe_spread_step -> mappo_env_insert] + the bootstrap value, i.e. the reference's
+ * `for step in range(episode_length): collect; envs.step; insert` followed by compute()'s get_values
+ * (runner/shared/mpe_runner.py:26-40, base_runner.py:120-134) with the environment inside the kernel -- the observation of
+ * step t + 1 is computed from the action of step t, nothing is staged.  Storage pointers address slot 0 (slot 0 must hold the
+ * current observations, e.g. from mappo_mpe_spread_step(actions = NULL) or the previous iteration's after_update); world state as
+ * in mappo_mpe_spread_step; reset_states [T, n_envs, 2 (agents + landmarks)] (nullable): the state a world restarts from
+ * when its episode ends at step t (NULL: Philox; *env_counter_dev advances by T * n_envs).  Images from
+ * mappo_pack_rollout_weights; sampling as in mappo_rollout_persistent. */
+int32_t mappo_rollout_closed_loop(const mappo_net_desc_t* actor_desc, const float* actor_image,
+                                  const mappo_net_desc_t* critic_desc, const float* critic_image, float* obs, float* share_obs,
+                                  float* masks, float* value_preds, float* actions, float* logp, float* rewards,
+                                  double* agent_pos, double* agent_vel, double* landmark_pos, int32_t* step_count,
+                                  const double* reset_states, uint64_t env_seed, uint64_t* env_counter_dev,
+                                  const float* exp_noise, uint64_t rng_seed, uint64_t* rng_offset_dev, int32_t T, int32_t E,
+                                  int32_t num_agents, int32_t num_landmarks, int32_t episode_length, void* stream);
 int32_t mappo_rollout_image_floats(const mappo_net_desc_t* desc);
 int32_t mappo_pack_rollout_weights(const mappo_net_desc_t* desc, const float* params, float* image, void* stream);
 

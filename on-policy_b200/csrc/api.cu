@@ -233,6 +233,36 @@ int32_t mappo_rollout_persistent(const mappo_net_desc_t* ad, const float* ap, co
   return MAPPO_OK;
 }
 
+int32_t mappo_rollout_closed_loop(const mappo_net_desc_t* ad, const float* a_img, const mappo_net_desc_t* cd, const float* c_img,
+                                  float* obs, float* share_obs, float* masks, float* value_preds, float* actions, float* logp,
+                                  float* rewards, double* agent_pos, double* agent_vel, double* landmark_pos,
+                                  int32_t* step_count, const double* reset_states, uint64_t env_seed,
+                                  uint64_t* env_counter_dev, const float* exp_noise, uint64_t rng_seed,
+                                  uint64_t* rng_offset_dev, int32_t T, int32_t E, int32_t num_agents, int32_t num_landmarks,
+                                  int32_t episode_length, void* stream) {
+  int rc = validate_desc(ad); if (rc) return rc;
+  rc = validate_desc(cd); if (rc) return rc;
+  if (ad->is_critic || !cd->is_critic) { set_error("rollout_closed_loop: actor/critic descriptors swapped"); return MAPPO_ERR_INVALID; }
+  if (!a_img || !c_img || !obs || !share_obs || !masks || !value_preds || !actions || !logp || !rewards || !agent_pos ||
+      !agent_vel || !landmark_pos || !step_count || T <= 0 || E <= 0 || episode_length <= 0) { set_error("rollout_closed_loop: NULL / bad argument"); return MAPPO_ERR_INVALID; }
+  if (!exp_noise && !rng_offset_dev) { set_error("rollout_closed_loop: sampling needs exp_noise or rng_offset_dev"); return MAPPO_ERR_INVALID; }
+  if (!reset_states && !env_counter_dev) { set_error("rollout_closed_loop: resets need reset_states or env_counter_dev"); return MAPPO_ERR_INVALID; }
+  ClosedArgs ca;
+  memset(&ca, 0, sizeof(ca));
+  RolloutArgs& a = ca.r;
+  a.image[0] = a_img; a.image[1] = c_img;
+  a.obs = obs; a.share_obs = share_obs; a.masks = masks; a.value_preds = value_preds; a.actions = actions; a.logp = logp;
+  a.rewards = rewards; a.exp_noise = exp_noise; a.rng_seed = rng_seed; a.rng_offset = rng_offset_dev; a.T = T; a.E = E;
+  ca.apos = agent_pos; ca.avel = agent_vel; ca.lpos = landmark_pos; ca.step_count = step_count; ca.reset_states = reset_states;
+  ca.env_seed = env_seed; ca.env_counter = env_counter_dev; ca.M = num_agents; ca.L = num_landmarks;
+  ca.episode_length = episode_length;
+  rc = rollout_closed_launch(make_net_dev(ad), make_net_dev(cd), ca, (cudaStream_t)stream);
+  if (rc) return rc;
+  if (!exp_noise) { rc = counter_add_launch(rng_offset_dev, (uint64_t)T * (uint64_t)E, (cudaStream_t)stream); if (rc) return rc; }
+  if (!reset_states) return counter_add_launch(env_counter_dev, (uint64_t)T * (uint64_t)(E / num_agents), (cudaStream_t)stream);
+  return MAPPO_OK;
+}
+
 int32_t mappo_rollout_image_floats(const mappo_net_desc_t* desc) {
   if (validate_desc(desc)) return -1;
   return rollout_image_floats(make_net_dev(desc));

@@ -55,6 +55,17 @@ struct MpeArgs {
 };
 int mpe_spread_launch(const MpeArgs& a, cudaStream_t st);
 
+// closed rollout loop with the device-side simple_spread worlds (rollout_closed.cuh)
+struct ClosedArgs {
+  RolloutArgs r;                     // storage pointers, images, sampling noise / RNG, T, E (f_* unused)
+  double *apos, *avel, *lpos;        // world state [N][M][2], [N][M][2], [N][L][2]
+  int32_t* step_count;               // [N]
+  const double* reset_states;        // [T][N][2 (M + L)] episode starts to use when a world ends at step t, or NULL (Philox)
+  uint64_t env_seed;
+  const uint64_t* env_counter;
+  int M, L, episode_length;
+};
+int rollout_closed_launch(const NetDev& na, const NetDev& nc, const ClosedArgs& ca, cudaStream_t st);
 int rollout_persistent_launch(const NetDev& na, const NetDev& nc, const RolloutArgs& a, cudaStream_t st);
 int policy_step_launch(const NetDev* na, const NetDev* nc, const PolArgs& a, cudaStream_t st);
 int env_insert_launch(const InsertArgs& a, cudaStream_t st);

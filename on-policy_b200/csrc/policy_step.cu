@@ -262,6 +262,7 @@ __device__ __forceinline__ void pol_step(const NetDev& n, int which, const PolCt
 
 }  // namespace mappo
 #include "rollout_mlp.cuh"
+#include "rollout_closed.cuh"
 namespace mappo {
 
 // shared setup of both kernels: carve shared memory, start the weight fetch, fill rowid; returns the context
@@ -483,6 +484,24 @@ int rollout_persistent_launch(const NetDev& na, const NetDev& nc, const RolloutA
   const dim3 grid((a.E + kPolTR - 1) / kPolTR, 2);
   kern<<<grid, 4 * kPolTR, bytes, st>>>(na, nc, a);
   return check_launch("rollout_persistent_kernel");
+}
+
+int rollout_closed_launch(const NetDev& na, const NetDev& nc, const ClosedArgs& ca, cudaStream_t st) {
+  const int M = ca.M, L = ca.L;
+  if (!fast_rollout_supported(na) || !fast_rollout_supported(nc) || !ca.r.image[0] || !ca.r.image[1]) { set_error("rollout_closed: needs feed-forward nets (hidden 64, in_dim <= 64) and packed weight images"); return MAPPO_ERR_UNSUPPORTED; }
+  if (M < 1 || M > kMpeMaxAgents || L < 1 || L > kMpeMaxLandmarks || ca.r.E % M != 0) { set_error("rollout_closed: %d agents / %d landmarks / %d rows", M, L, ca.r.E); return MAPPO_ERR_UNSUPPORTED; }
+  if (na.n_heads != 1 || na.head_dim[0] != 5 || na.in_dim != 4 + 2 * L + 4 * (M - 1) || nc.in_dim != M * na.in_dim) { set_error("rollout_closed: policy shapes do not match simple_spread (Discrete(5), obs %d, share_obs %d)", 4 + 2 * L + 4 * (M - 1), M * (4 + 2 * L + 4 * (M - 1))); return MAPPO_ERR_INVALID; }
+  const size_t bytes = closed_smem_bytes(na, nc, M);
+  if (bytes > 227 * 1024) { set_error("rollout_closed: %zu B shared memory", bytes); return MAPPO_ERR_UNSUPPORTED; }
+  static thread_local size_t configured = 0;
+  if (bytes > configured) {
+    if (cudaFuncSetAttribute(rollout_closed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+      return check_launch("rollout_closed: cudaFuncSetAttribute");
+    configured = bytes;
+  }
+  const int N = ca.r.E / M;
+  rollout_closed_kernel<<<(N + kCG - 1) / kCG, 64 * kCG * M, bytes, st>>>(na, nc, ca);
+  return check_launch("rollout_closed_kernel");
 }
 
 int pack_rollout_launch(const NetDev& n, const float* params, float* image, cudaStream_t st) {

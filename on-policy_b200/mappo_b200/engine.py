@@ -82,7 +82,10 @@ class RolloutEngine:
         import os
         self.env = device_env
         self.env_reset_states = None        # optional [T, N, 2 (M + L)] float64: injected episode starts (parity tests)
-        self.persistent_rollout = os.environ.get("MAPPO_B200_PERSISTENT_ROLLOUT", "1") == "1" and device_env is None
+        want_persistent = os.environ.get("MAPPO_B200_PERSISTENT_ROLLOUT", "1") == "1"
+        self.persistent_rollout = want_persistent and device_env is None
+        # closed loop as ONE launch (mappo_rollout_closed_loop): feed-forward policies
+        self.closed_persistent = want_persistent and device_env is not None and not self.recurrent
         if device_env is not None and (device_env.N * device_env.M != E or device_env.obs_dim != self.Do
                                        or device_env.share_dim != self.Ds):
             raise ValueError("device_env does not match the rollout storage (rows / obs_dim / share_obs_dim)")
@@ -233,6 +236,17 @@ class RolloutEngine:
             ptr(self.d_avail) if self.d_avail is not None else None,
             ptr(self.d_noise), self.seed, ptr(pol.rng_offset), self.T, self.E, stream_ptr()))
 
+    def _rollout_closed(self):
+        """Closed loop, all T steps + the bootstrap value as ONE launch (policy -> world step -> insert inside the kernel)."""
+        b, pol, lib, env = self.buffer, self.policy, self.lib, self.env
+        rs = self.env_reset_states
+        check(lib.mappo_rollout_closed_loop(
+            C.byref(pol.actor.desc), ptr(self.img_actor), C.byref(pol.critic.desc), ptr(self.img_critic),
+            ptr(b.obs), ptr(b.share_obs), ptr(b.masks), ptr(b.value_preds), ptr(b.actions), ptr(b.action_log_probs),
+            ptr(b.rewards), ptr(env.apos), ptr(env.avel), ptr(env.lpos), ptr(env.step_count),
+            ptr(rs) if rs is not None else None, env.seed, ptr(env.rng_counter), ptr(self.d_noise), self.seed,
+            ptr(pol.rng_offset), self.T, self.E, env.M, env.L, env.EP, stream_ptr()))
+
     def _returns(self):
         b, lib, st, T = self.buffer, self.lib, stream_ptr(), self.T
         vn = self.trainer.value_normalizer
@@ -286,6 +300,9 @@ class RolloutEngine:
         if self.persistent_rollout:
             self._rollout_persistent()
             self._returns()
+        elif self.closed_persistent:
+            self._rollout_closed()
+            self._returns()
         else:
             for t in range(self.T):
                 self._collect_and_insert(t)
@@ -330,6 +347,11 @@ class RolloutEngine:
                 check(self.lib.mappo_pack_rollout_weights(C.byref(pol.critic.desc), ptr(pol.critic.flat), ptr(self.img_critic), stream_ptr()))
                 self._rollout_persistent()
                 return
+            if self.closed_persistent:
+                check(self.lib.mappo_pack_rollout_weights(C.byref(pol.actor.desc), ptr(pol.actor.flat), ptr(self.img_actor), stream_ptr()))
+                check(self.lib.mappo_pack_rollout_weights(C.byref(pol.critic.desc), ptr(pol.critic.flat), ptr(self.img_critic), stream_ptr()))
+                self._rollout_closed()
+                return
             check(self.lib.mappo_pack_rollout_weights(C.byref(pol.actor.desc), ptr(pol.actor.flat), ptr(self.img_actor), stream_ptr()))
             check(self.lib.mappo_pack_rollout_weights(C.byref(pol.critic.desc), ptr(pol.critic.flat), ptr(self.img_critic), stream_ptr()))
             for t in range(self.T):
@@ -349,7 +371,7 @@ class RolloutEngine:
         names = ["rows", "mlp_base", "gru_cell", "head_gemm", "sample_store"]
         cyc = {net: {nm: int(buf[8 * k + i]) for i, nm in enumerate(names)} for k, net in enumerate(("actor", "critic"))}
         return {"rollout_cycles_cta0": cyc, "collect_insert_ms": timed(collect),
-                "values_gae_ms": timed(self._returns if self.persistent_rollout else self._compute), "train_ms": timed(train),
+                "values_gae_ms": timed(self._returns if (self.persistent_rollout or self.closed_persistent) else self._compute), "train_ms": timed(train),
                 "after_update_ms": timed(self.buffer.after_update)}
 
     def capture(self, warmup: int = 2):

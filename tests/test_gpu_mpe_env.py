@@ -62,14 +62,16 @@ def test_device_rng_resets_are_inside_the_reference_ranges():
     assert not np.array_equal(first, env.apos.cpu().numpy())                    # the counter advanced
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("graph", [False, True])
-def test_closed_loop_iteration_is_consistent_with_the_oracle_env(graph):
+def test_closed_loop_iteration_is_consistent_with_the_oracle_env(graph, fused, monkeypatch):
     """Engine in closed loop (policy_step -> device env -> insert, T times, then GAE + train): replaying the actions it
     stored through the oracle environment from the same episode starts reproduces the stored observations, share_obs,
     rewards and masks."""
     from mappo_b200.engine import RolloutEngine
     from mappo_b200.mpe_env import DeviceSpreadEnv
-    cfg = O.PathConfig(episode_length=25, n_rollout_threads=16, num_agents=3, obs_dim=18, share_obs_dim=54,
+    monkeypatch.setenv("MAPPO_B200_PERSISTENT_ROLLOUT", "1" if fused else "0")
+    cfg = O.PathConfig(episode_length=25, n_rollout_threads=15, num_agents=3, obs_dim=18, share_obs_dim=54,
                        act_dims=(5,), use_ReLU=False, ppo_epoch=2, num_mini_batch=1, lr=7e-4, critic_lr=7e-4)
     torch.manual_seed(1)
     args, policy, trainer, buf = TP.build(cfg)
@@ -79,6 +81,7 @@ def test_closed_loop_iteration_is_consistent_with_the_oracle_env(graph):
     starts = ref.draw_reset_states(N)
     nxt = ref.draw_reset_states(N)
     eng = RolloutEngine(args, policy, trainer, buf, rng="device", seed=2, device_env=env)
+    assert eng.closed_persistent == fused
     rs = torch.from_numpy(np.repeat(nxt[None], T, axis=0)).cuda()               # same restart state whenever an episode ends
     eng.env_reset_states = rs
     if graph:
@@ -103,3 +106,30 @@ def test_closed_loop_iteration_is_consistent_with_the_oracle_env(graph):
     assert want_done[-1].all()                                                  # world_length == episode_length
     assert np.isfinite(policy.actor.flat.cpu().numpy()).all()
     del obs0
+
+
+def test_fused_and_per_step_closed_loops_agree_bit_for_bit(monkeypatch):
+    """mappo_rollout_closed_loop (one launch) and T x [policy_step, mpe_spread_step, env_insert] run the same device
+    functions with the same RNG counters: storage, world state and trained weights must be identical -- also with
+    device-RNG resets (no injected episode starts) across two iterations."""
+    from mappo_b200.engine import RolloutEngine
+    from mappo_b200.mpe_env import DeviceSpreadEnv
+    cfg = O.PathConfig(episode_length=25, n_rollout_threads=33, num_agents=3, obs_dim=18, share_obs_dim=54,
+                       act_dims=(5,), use_ReLU=False, ppo_epoch=2, num_mini_batch=1, lr=7e-4, critic_lr=7e-4)
+    outs = []
+    for fused in (True, False):
+        monkeypatch.setenv("MAPPO_B200_PERSISTENT_ROLLOUT", "1" if fused else "0")
+        torch.manual_seed(1)
+        args, policy, trainer, buf = TP.build(cfg)
+        env = DeviceSpreadEnv(cfg.n_rollout_threads, 3, 3, cfg.episode_length, device="cuda", seed=9)
+        eng = RolloutEngine(args, policy, trainer, buf, rng="device", seed=4, device_env=env)
+        assert eng.closed_persistent == fused
+        eng.reset_env()
+        for _ in range(2):
+            eng.step_resident()
+        torch.cuda.synchronize()
+        outs.append([t.clone() for t in (buf.obs, buf.share_obs, buf.rewards, buf.masks, buf.actions, buf.value_preds,
+                                         buf.action_log_probs, env.apos, env.avel, env.lpos, env.step_count,
+                                         env.rng_counter, policy.rng_offset, policy.actor.flat, policy.critic.flat)])
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
