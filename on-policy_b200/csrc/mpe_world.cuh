@@ -43,8 +43,12 @@ __device__ __forceinline__ double logaddexp0(double y) {
 
 // scenario.reset_world (simple_spread.py:32-45): positions from `s` (agents then landmarks, 2 (M + L) doubles) or, when s is
 // NULL, uniform(-1, 1) / 0.8 uniform(-1, 1) from Philox keyed by (seed, ctr)
-__device__ __forceinline__ void mpe_world_reset(MpeWorld& w, int M, int L, const double* __restrict__ s, uint64_t seed,
+// MT / LT: compile-time agent / landmark counts (0 = use the runtime M / L).  With constants every loop unrolls and the world
+// lives in registers; the arithmetic and its order are the same.
+template <int MT = 0, int LT = 0>
+__device__ __forceinline__ void mpe_world_reset(MpeWorld& w, int Mr, int Lr, const double* __restrict__ s, uint64_t seed,
                                                 uint64_t ctr) {
+  const int M = MT ? MT : Mr, L = LT ? LT : Lr;
   if (s) {
     for (int m = 0; m < M; ++m) { w.ap[m][0] = s[2 * m]; w.ap[m][1] = s[2 * m + 1]; }
     for (int l = 0; l < L; ++l) { w.lp[l][0] = s[2 * (M + l)]; w.lp[l][1] = s[2 * (M + l) + 1]; }
@@ -68,8 +72,11 @@ __device__ __forceinline__ void mpe_world_reset(MpeWorld& w, int M, int L, const
 
 // MultiAgentEnv.step for integer actions act[m] in 0..4 (what the one-hot the runner sends decodes to): returns the shared
 // reward; *done = the episode ended (the caller resets, env_wrappers.py:146-152).
-__device__ __forceinline__ double mpe_world_step(MpeWorld& w, int M, int L, const int* act, int episode_length, bool* done) {
+template <int MT = 0, int LT = 0>
+__device__ __forceinline__ double mpe_world_step(MpeWorld& w, int Mr, int Lr, const int* act, int episode_length, bool* done) {
+  const int M = MT ? MT : Mr, L = LT ? LT : Lr;
   double f[kMpeMaxAgents][2];
+#pragma unroll
   for (int m = 0; m < M; ++m) {          // environment.py:232-246 (_set_action), core.py:229-238 (apply_action_force)
     double u0 = 0.0, u1 = 0.0;
     u0 = d_add(u0, d_sub(act[m] == 1 ? 1.0 : 0.0, act[m] == 2 ? 1.0 : 0.0));
@@ -78,7 +85,9 @@ __device__ __forceinline__ double mpe_world_step(MpeWorld& w, int M, int L, cons
     f[m][0] = d_add(d_mul(1.0, u0), 0.0);
     f[m][1] = d_add(d_mul(1.0, u1), 0.0);
   }
+#pragma unroll
   for (int ia = 0; ia < M; ++ia)         // core.py:241-265, 293-323: contacts between agents (landmarks do not collide)
+#pragma unroll
     for (int ib = ia + 1; ib < M; ++ib) {
       const double dx = d_sub(w.ap[ia][0], w.ap[ib][0]), dy = d_sub(w.ap[ia][1], w.ap[ib][1]);
       const double dist = d_norm2(dx, dy);
@@ -89,7 +98,9 @@ __device__ __forceinline__ double mpe_world_step(MpeWorld& w, int M, int L, cons
       f[ia][0] = d_add(fx, f[ia][0]); f[ia][1] = d_add(fy, f[ia][1]);
       f[ib][0] = d_add(-fx, f[ib][0]); f[ib][1] = d_add(-fy, f[ib][1]);
     }
+#pragma unroll
   for (int m = 0; m < M; ++m)            // core.py:267-281 (integrate_state)
+#pragma unroll
     for (int d = 0; d < 2; ++d) {
       double v = d_mul(w.av[m][d], 1 - kDamping);
       v = d_add(v, d_mul(d_div(f[m][d], 1.0), kDt));
@@ -98,16 +109,20 @@ __device__ __forceinline__ double mpe_world_step(MpeWorld& w, int M, int L, cons
     }
   w.step += 1;
   double reward = 0.0;                   // simple_spread.py:72-85, shared reward = sum over agents (environment.py:139-142)
+#pragma unroll
   for (int m = 0; m < M; ++m) {
     double rew = 0.0;
+#pragma unroll
     for (int l = 0; l < L; ++l) {
       double mn = 0.0;
+#pragma unroll
       for (int q = 0; q < M; ++q) {
         const double d = d_norm2(d_sub(w.ap[q][0], w.lp[l][0]), d_sub(w.ap[q][1], w.lp[l][1]));
         mn = (q == 0 || d < mn) ? d : mn;
       }
       rew = d_sub(rew, mn);
     }
+#pragma unroll
     for (int q = 0; q < M; ++q)          // q == m included: an agent "collides" with itself in the reference
       if (d_norm2(d_sub(w.ap[q][0], w.ap[m][0]), d_sub(w.ap[q][1], w.ap[m][1])) < d_add(kAgentSize, kAgentSize))
         rew = d_sub(rew, 1.0);
@@ -119,7 +134,9 @@ __device__ __forceinline__ double mpe_world_step(MpeWorld& w, int M, int L, cons
 
 // scenario.observation of agent m (simple_spread.py:87-103) as float32 (what the rollout storage keeps):
 // vel, pos, landmarks - pos, other agents - pos, other agents' (silent => zero) communication
-__device__ __forceinline__ void mpe_world_obs(const MpeWorld& w, int M, int L, int m, float* __restrict__ o) {
+template <int MT = 0, int LT = 0>
+__device__ __forceinline__ void mpe_world_obs(const MpeWorld& w, int Mr, int Lr, int m, float* __restrict__ o) {
+  const int M = MT ? MT : Mr, L = LT ? LT : Lr;
   int c = 0;
   o[c++] = (float)w.av[m][0]; o[c++] = (float)w.av[m][1];
   o[c++] = (float)w.ap[m][0]; o[c++] = (float)w.ap[m][1];
@@ -130,18 +147,22 @@ __device__ __forceinline__ void mpe_world_obs(const MpeWorld& w, int M, int L, i
     if (q != m) { o[c++] = 0.f; o[c++] = 0.f; }
 }
 
-__device__ __forceinline__ void mpe_world_load(MpeWorld& w, int M, int L, const double* __restrict__ apos,
+template <int MT = 0, int LT = 0>
+__device__ __forceinline__ void mpe_world_load(MpeWorld& w, int Mr, int Lr, const double* __restrict__ apos,
                                                const double* __restrict__ avel, const double* __restrict__ lpos,
                                                const int32_t* __restrict__ step_count, int e) {
+  const int M = MT ? MT : Mr, L = LT ? LT : Lr;
   for (int m = 0; m < M; ++m)
     for (int d = 0; d < 2; ++d) { w.ap[m][d] = apos[((size_t)e * M + m) * 2 + d]; w.av[m][d] = avel[((size_t)e * M + m) * 2 + d]; }
   for (int l = 0; l < L; ++l)
     for (int d = 0; d < 2; ++d) w.lp[l][d] = lpos[((size_t)e * L + l) * 2 + d];
   w.step = step_count[e];
 }
-__device__ __forceinline__ void mpe_world_store(const MpeWorld& w, int M, int L, double* __restrict__ apos,
+template <int MT = 0, int LT = 0>
+__device__ __forceinline__ void mpe_world_store(const MpeWorld& w, int Mr, int Lr, double* __restrict__ apos,
                                                 double* __restrict__ avel, double* __restrict__ lpos,
                                                 int32_t* __restrict__ step_count, int e) {
+  const int M = MT ? MT : Mr, L = LT ? LT : Lr;
   for (int m = 0; m < M; ++m)
     for (int d = 0; d < 2; ++d) { apos[((size_t)e * M + m) * 2 + d] = w.ap[m][d]; avel[((size_t)e * M + m) * 2 + d] = w.av[m][d]; }
   for (int l = 0; l < L; ++l)

@@ -493,14 +493,16 @@ int rollout_closed_launch(const NetDev& na, const NetDev& nc, const ClosedArgs& 
   if (na.n_heads != 1 || na.head_dim[0] != 5 || na.in_dim != 4 + 2 * L + 4 * (M - 1) || nc.in_dim != M * na.in_dim) { set_error("rollout_closed: policy shapes do not match simple_spread (Discrete(5), obs %d, share_obs %d)", 4 + 2 * L + 4 * (M - 1), M * (4 + 2 * L + 4 * (M - 1))); return MAPPO_ERR_INVALID; }
   const size_t bytes = closed_smem_bytes(na, nc, M);
   if (bytes > 227 * 1024) { set_error("rollout_closed: %zu B shared memory", bytes); return MAPPO_ERR_UNSUPPORTED; }
-  static thread_local size_t configured = 0;
-  if (bytes > configured) {
-    if (cudaFuncSetAttribute(rollout_closed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+  auto kern = (M == 3 && L == 3) ? rollout_closed_kernel<3, 3> : rollout_closed_kernel<0, 0>;   // reference default shape
+  static thread_local size_t configured[2] = {0, 0};
+  size_t& conf = configured[(M == 3 && L == 3) ? 1 : 0];
+  if (bytes > conf) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
       return check_launch("rollout_closed: cudaFuncSetAttribute");
-    configured = bytes;
+    conf = bytes;
   }
   const int N = ca.r.E / M;
-  rollout_closed_kernel<<<(N + kCG - 1) / kCG, 64 * kCG * M, bytes, st>>>(na, nc, ca);
+  kern<<<(N + kCG - 1) / kCG, 64 * kCG * M, bytes, st>>>(na, nc, ca);
   return check_launch("rollout_closed_kernel");
 }
 

@@ -22,13 +22,15 @@ namespace mappo {
 constexpr int kCG = 2;               // worlds per CTA
 
 
-__global__ void __launch_bounds__(64 * kCG * kMpeMaxAgents)
+// MT / LT: compile-time agent / landmark counts (0 = runtime, launch bound for 8 agents)
+template <int MT, int LT>
+__global__ void __launch_bounds__(64 * kCG * (MT ? MT : kMpeMaxAgents))
 rollout_closed_kernel(const NetDev na, const NetDev nc, const ClosedArgs ca) {
   extern __shared__ __align__(16) float smem[];
   __shared__ uint64_t wbar;
   const RolloutArgs& a = ca.r;
   const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
-  const int M = ca.M, L = ca.L, E = a.E, T = a.T, N = E / M;
+  const int M = MT ? MT : ca.M, L = LT ? LT : ca.L, E = a.E, T = a.T, N = E / M;
   const int rows = kCG * M;                                   // actor warps [0, rows), critic warps [rows, 2 rows)
   const int which = wq >= rows ? 1 : 0;
   const int rl = which ? wq - rows : wq, env_local = rl / M, m = rl - env_local * M;
@@ -63,7 +65,7 @@ rollout_closed_kernel(const NetDev na, const NetDev nc, const ClosedArgs ca) {
   // the environment thread of a world: lane 0 of its first actor warp
   const bool env_thread = which == 0 && m == 0 && lane == 0 && env < N;
   MpeWorld w;
-  if (env_thread) mpe_world_load(w, M, L, ca.apos, ca.avel, ca.lpos, ca.step_count, env);
+  if (env_thread) mpe_world_load<MT, LT>(w, M, L, ca.apos, ca.avel, ca.lpos, ca.step_count, env);
   const uint64_t env_ctr0 = (env_thread && !ca.reset_states) ? *ca.env_counter : 0ull;
   __syncthreads();
   {
@@ -98,14 +100,14 @@ rollout_closed_kernel(const NetDev na, const NetDev nc, const ClosedArgs ca) {
       int act[kMpeMaxAgents];
       for (int q = 0; q < M; ++q) act[q] = (int)a.actions[((size_t)t * E + (size_t)env * M + q) * as];
       bool done;
-      const double reward = mpe_world_step(w, M, L, act, ca.episode_length, &done);
+      const double reward = mpe_world_step<MT, LT>(w, M, L, act, ca.episode_length, &done);
       if (done)                                                   // env_wrappers.py:146-152
-        mpe_world_reset(w, M, L, ca.reset_states ? ca.reset_states + ((size_t)t * N + env) * 2 * (M + L) : nullptr,
+        mpe_world_reset<MT, LT>(w, M, L, ca.reset_states ? ca.reset_states + ((size_t)t * N + env) * 2 * (M + L) : nullptr,
                         ca.env_seed, env_ctr0 + (uint64_t)t * N + env);
       for (int q = 0; q < M; ++q) {
         a.rewards[(size_t)t * E + (size_t)env * M + q] = (float)reward;                   // insert: rewards of slot t,
         a.masks[(size_t)(t + 1) * E + (size_t)env * M + q] = done ? 0.f : 1.f;            // masks of slot t + 1
-        mpe_world_obs(w, M, L, q, obs_s + ((size_t)env_local * M + q) * D);
+        mpe_world_obs<MT, LT>(w, M, L, q, obs_s + ((size_t)env_local * M + q) * D);
       }
     }
     __syncthreads();                                              // the next observations are in shared memory
@@ -115,7 +117,7 @@ rollout_closed_kernel(const NetDev na, const NetDev nc, const ClosedArgs ca) {
       x[1] = (g >= 0 && lane + 32 < in) ? src[lane + 32] : 0.f;
     }
   }
-  if (env_thread) mpe_world_store(w, M, L, ca.apos, ca.avel, ca.lpos, ca.step_count, env);
+  if (env_thread) mpe_world_store<MT, LT>(w, M, L, ca.apos, ca.avel, ca.lpos, ca.step_count, env);
 }
 
 inline size_t closed_smem_bytes(const NetDev& na, const NetDev& nc, int M) {
