@@ -88,3 +88,26 @@ def test_separated_mpe_runner_runs(tmp_path):
         assert not torch.equal(a, p.actor.flat)
         assert torch.isfinite(p.actor.flat).all()
     assert (tmp_path / "models" / "actor_agent1.pt").exists() and (tmp_path / "models" / "vnrom_agent0.pt").exists()
+
+
+def test_shared_mpe_runner_drives_the_device_environment(tmp_path):
+    """`DeviceSpreadVecEnv` (device-side simple_spread behind the reference's vec-env interface) is a drop-in for what
+    make_train_env() returns: the unchanged runner loop collects, steps it with one-hot actions, inserts and trains."""
+    from onpolicy.runner.shared.mpe_runner import MPERunner
+    from mappo_b200.mpe_env import DeviceSpreadVecEnv
+    cfg = O.PathConfig(episode_length=10, n_rollout_threads=8, num_agents=3, obs_dim=18, share_obs_dim=54, act_dims=(5,),
+                       ppo_epoch=2, use_ReLU=False)
+    envs = DeviceSpreadVecEnv(8, 3, 3, cfg.episode_length, device="cuda", seed=2)
+    runner = MPERunner(_config(cfg, tmp_path, envs))
+    w0 = runner.policy.actor.flat.clone()
+    runner.run()
+    assert not torch.equal(w0, runner.policy.actor.flat)
+    assert torch.isfinite(runner.policy.actor.flat).all() and torch.isfinite(runner.policy.critic.flat).all()
+    assert runner.buffer.masks[0].sum().item() == 0                        # world_length == episode_length: done at t == T
+    r = runner.buffer.rewards
+    assert torch.isfinite(r).all() and (r < 0).all()                       # distance + self-collision penalties
+    assert torch.equal(r[:, :, 0], r[:, :, 1]) and torch.equal(r[:, :, 0], r[:, :, 2])      # shared reward
+    obs = runner.buffer.obs[1:]                                            # share_obs = the thread's obs concatenated
+    want = obs.reshape(obs.shape[0], obs.shape[1], 1, -1).expand(-1, -1, 3, -1)
+    assert torch.equal(runner.buffer.share_obs[1:], want)
+    runner.writter.close()
