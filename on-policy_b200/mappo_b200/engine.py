@@ -6,8 +6,11 @@
 Every launch goes through the C ABI of libmappo_b200 on the current stream; the graph is captured once and
 replayed per iteration, so the host's share of an iteration is: refresh the pinned staging buffers (env outputs,
 and -- in "host" RNG mode -- the reference's sampling noise / permutations), one graph launch, one 48-byte read.
-The rollout kernel writes values / actions / log-probs / rnn states STRAIGHT into the storage slots; insert is
-one fused kernel per step.
+The rollout kernels write values / actions / log-probs / rnn states STRAIGHT into the storage slots.  Three collect modes:
+  * staged feed, persistent (default): all T steps + inserts + the bootstrap value in ONE launch (mappo_rollout_persistent),
+  * staged feed, per step: T x (mappo_policy_step + mappo_env_insert)  (MAPPO_B200_PERSISTENT_ROLLOUT=0),
+  * closed loop (device_env=DeviceSpreadEnv): the MPE simple_spread worlds are stepped on the device between policy and
+    insert -- inside one persistent kernel (mappo_rollout_closed_loop) or as one extra launch per step.
 """
 from __future__ import annotations
 
