@@ -72,7 +72,7 @@ def best_cpu_threads(cfg):
     counts with two iterations each and keep the fastest ("all the host threads it can USE")."""
     cores = os.cpu_count() or 1
     best, best_rate = 1, 0.0
-    for th in sorted({1, min(4, cores), min(8, cores), min(16, cores)}):
+    for th in sorted({1, min(4, cores), min(8, cores), min(16, cores), min(32, cores)}):
         rate, _ = cpu_iteration_rate(cfg, 2, 1, th)
         if rate > best_rate:
             best, best_rate = th, rate
@@ -90,7 +90,7 @@ def run_reference(a):
             "warmup": a.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_dict(cfg, 1),
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{a.steps} full iterations of c2 (3200 env steps each) on {cores} torch threads (fastest of 1/4/8/16 on a {os.cpu_count()}-core host); "
+                             "sample": f"{a.steps} full iterations of c2 (3200 env steps each) on {cores} torch threads (fastest of 1/4/8/16/32 on a {os.cpu_count()}-core host); "
                                        "oracle/mappo_oracle.py = CPU restatement of the reference (Python reference "
                                        "cannot travel to the GPU box)"},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -313,7 +313,7 @@ def run_gpu(a):
         if cpu_rate is not None:
             line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{a.cpu_iters} full c2 iterations (3200 env steps each) of "
-                                              f"oracle/mappo_oracle.py on {cores} torch threads (fastest of 1/4/8/16; host has {os.cpu_count()} cores), "
+                                              f"oracle/mappo_oracle.py on {cores} torch threads (fastest of 1/4/8/16/32; host has {os.cpu_count()} cores), "
                                               f"{cpu_per*1e3:.0f} ms each"}
         print(json.dumps(line), flush=True)
     if world > 1:
