@@ -454,7 +454,7 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
   const LossConsts lc = make_loss_consts(n, L, norm_stats, adv_stats, vn_state);
   double acc[3] = {0.0, 0.0, 0.0};
   uint32_t phase = 0, phase_g = 0;
-  bool first_tile = true, g1_pending = false;
+  bool first_tile = true, g1_pending = false, ids_published = true;
   const uint32_t aP = smem_u32(P), aX1T = smem_u32(X1T), aX2T = smem_u32(X2T), aTA = smem_u32(TA);
   const uint32_t aW1 = smem_u32(sImg + im.w1), aW2 = smem_u32(sImg + im.w2), aWh = smem_u32(sImg + im.wh);
   const uint32_t aW2T = smem_u32(sImg + im.w2t), aWhT = smem_u32(sImg + im.wht);
@@ -475,10 +475,11 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
       int* rowid_s = reinterpret_cast<int*>(lgT);                 // lgT is free until S7
       float* Rs = P;                                              // raw rows [128][RS], RS odd -> conflict-free row reads
       const int RS = in | 1;
-      if (!first_tile) {                                          // (first tile: published before the setup barrier)
+      if (!ids_published) {                                       // (first pass: published before the setup barrier)
         if (wg == 0) rowid_s[r] = gr;
         __syncthreads();
       }
+      ids_published = false;
       const float* base = n.is_critic ? b.share_obs : b.obs;
       // each of the 8 warps gathers 16 rows: 32 independent coalesced loads in flight per thread, then the stores
       {

@@ -91,3 +91,31 @@ def test_tf32_full_iterations(monkeypatch):
         print(f"\n[tf32] it{it}: worst absolute weight deviation from the reference {worst:.3e}")
         if it == 0:
             break          # iteration 2 samples actions from tf32-trained weights: integer actions may differ
+
+
+def test_tf32_ctas_with_several_tiles_match_the_fp32_build(monkeypatch):
+    """More 128-row tiles than SMs (256 threads x 3 agents x 25 steps = 19200 rows = 150 tiles on 148 CTAs): a CTA then walks
+    several tiles, its weight-gradient accumulators stay in TMEM across them.  First-update gradients and losses of the
+    tcgen05 build against the exact-fp32 build on identical rollouts."""
+    from oracle import mappo_oracle as O
+    cfg = O.PathConfig(episode_length=25, n_rollout_threads=256, num_agents=3, obs_dim=18, share_obs_dim=54,
+                       act_dims=(5,), use_ReLU=False, ppo_epoch=1, num_mini_batch=1, lr=7e-4, critic_lr=7e-4)
+    feed = O.make_feed(cfg, seed=3)
+    noise = np.random.RandomState(5).exponential(size=(cfg.episode_length, cfg.n_rollout_threads * cfg.num_agents, 5)) \
+        .astype(np.float32)
+    perm = np.random.RandomState(6).permutation(cfg.episode_length * cfg.n_rollout_threads * cfg.num_agents)
+    res = {}
+    for mode in ("fp32", "tf32"):
+        monkeypatch.setenv("MAPPO_B200_GEMM", mode)
+        torch.manual_seed(1)
+        args, policy, trainer, buf = TP.build(cfg)
+        TP.warm(buf, feed)
+        TP.collect_and_returns(cfg, policy, trainer, buf, feed, noise)
+        monkeypatch.setattr(torch, "randperm", TP.FakeRandperm([perm]))
+        info = trainer.train(buf)
+        res[mode] = (info, {("a", k): v.cpu().numpy().copy() for k, v in policy.actor.named_grads().items()} |
+                     {("c", k): v.cpu().numpy().copy() for k, v in policy.critic.named_grads().items()})
+    for key, want in res["fp32"][1].items():
+        _grad_check(res["tf32"][1][key], want, f"{key}")
+    for k in ("value_loss", "dist_entropy", "ratio", "actor_grad_norm", "critic_grad_norm"):
+        assert_close(res["tf32"][0][k], res["fp32"][0][k], 1e-2, 1e-6, k)
