@@ -26,6 +26,38 @@ def test_library_exports_every_declared_symbol():
     assert _lib.load().mappo_abi_version() == 2
 
 
+def test_binding_arity_and_scalar_types_match_the_header():
+    """ctypes does not check prototypes: every binding in mappo_b200/_lib.py must take exactly the parameters the header
+    declares, with pointers, 32 / 64-bit integers and floats in the same positions."""
+    from mappo_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "mappo_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    protos = dict(re.findall(r"\b(mappo_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S))
+    kinds = {C.c_int32: "i32", C.c_int64: "i64", C.c_uint64: "i64", C.c_float: "f32", C.c_double: "f64"}
+
+    def header_kind(param):
+        param = " ".join(param.split())
+        if "*" in param:
+            return "ptr"
+        for key, k in (("uint64_t", "i64"), ("int64_t", "i64"), ("int32_t", "i32"), ("float", "f32"), ("double", "f64")):
+            if re.search(r"\b" + key + r"\b", param):
+                return k
+        raise AssertionError(f"unrecognised parameter type: {param!r}")
+
+    def binding_kind(t):
+        if t in kinds:
+            return kinds[t]
+        return "ptr"                                         # c_void_p, POINTER(...), arrays of pointers
+
+    for name, (_, argtypes) in _lib._SIGS.items():
+        assert name in protos, name
+        params = [x for x in protos[name].split(",") if x.strip() and x.strip() != "void"]
+        assert len(params) == len(argtypes), f"{name}: header has {len(params)} parameters, binding {len(argtypes)}"
+        got = [binding_kind(t) for t in argtypes]
+        want = [header_kind(x) for x in params]
+        assert got == want, f"{name}: header {want} vs binding {got}"
+
+
 def test_net_layout_matches_reference_param_count():
     from mappo_b200 import _lib
     lib = _lib.load()
