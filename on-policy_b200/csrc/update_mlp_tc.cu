@@ -18,7 +18,7 @@
 //
 // LayerNorm affine parameters and biases are folded into the GEMMs: the tiles hold xhat (pre-affine) plus a
 // constant-1 feature, the weight image holds W' = W diag(gamma) and b' = b + W beta in the column of the 1-feature.
-// dW' accumulates in TMEM across the tiles of a CTA; at the end dW = dW' diag(gamma), db = dW'[:, one],
+// dW' accumulates in TMEM across the tiles of a CTA; at the end dW = dW' diag(gamma) + db' beta^T, db = dW'[:, one],
 // dgamma = colsum(dW' .* W), dbeta = W^T db'  (chain rule of the folding), written to the CTA's gradient slot.
 #include "net_tiles.cuh"
 
@@ -173,7 +173,7 @@ __host__ __device__ inline TcRaw make_tc_raw(const TcImage& m) {
   return r;
 }
 
-// dW = dW' diag(gamma_in), db = dW'[:, one], dgamma_in = colsum(dW' .* W), dbeta_in = W^T db'   (chain rule of the
+// dW = dW' diag(gamma_in) + db' beta_in^T, db = dW'[:, one], dgamma_in = colsum(dW' .* W), dbeta_in = W^T db'   (chain rule of the
 // folding) from the slot-summed raw accumulators.  Grid: blockIdx.y = layer (0 fc2, 1 fc1, 2 heads), blockIdx.x = block
 // of 16 input features; 256 threads = 16 features x 16 groups of 4 output rows.  Every CTA also emits its sum(g^2).
 __global__ void __launch_bounds__(256)
@@ -195,14 +195,14 @@ tc_unfold_kernel(const NetDev n, const float* __restrict__ p, const float* __res
     const int gam_off = sec == 0 ? n.g.ln1_w : n.g.fn_w, bet_off = sec == 0 ? n.g.ln1_b : n.g.fn_b;
     float sg = 0.f, sb = 0.f;
     if (k < K) {
-      const float gam = fold ? p[gam_off + k] : 1.f;
+      const float gam = fold ? p[gam_off + k] : 1.f, bet = fold ? p[bet_off + k] : 0.f;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int o = og * 4 + j;
-        const float dw = G[o * ld + k], w = p[w_off + o * K + k];
-        put(w_off + o * K + k, dw * gam);
+        const float dw = G[o * ld + k], w = p[w_off + o * K + k], dbo = G[o * ld + one];
+        put(w_off + o * K + k, fmaf(dbo, bet, dw * gam));     // b' = b + W beta depends on W as well
         sg = fmaf(dw, w, sg);
-        sb = fmaf(G[o * ld + one], w, sb);
+        sb = fmaf(dbo, w, sb);
       }
     }
     if (blockIdx.x == 0 && tid < 64) put(b_off + tid, G[tid * ld + one]);
@@ -218,13 +218,13 @@ tc_unfold_kernel(const NetDev n, const float* __restrict__ p, const float* __res
   } else {                                              // heads: raw gh[feature][a]; this CTA owns 16 features
     const int kk = blockIdx.x * 16 + kx;                // < 64 (grid.x == 4 for this layer, extra blocks exit below)
     if (kk < 64) {
-      const float gam = p[n.g.ln2_w[0] + kk];
+      const float gam = p[n.g.ln2_w[0] + kk], bet = p[n.g.ln2_b[0] + kk];
       float sg = 0.f, sb = 0.f;
       for (int a = og; a < Atot; a += 16) {
-        const float dw = raw[R.gh + kk * m.NH + a], w = p[n.g.head_w + a * 64 + kk];
-        put(n.g.head_w + a * 64 + kk, dw * gam);
+        const float dw = raw[R.gh + kk * m.NH + a], w = p[n.g.head_w + a * 64 + kk], dba = raw[R.dbh + a];
+        put(n.g.head_w + a * 64 + kk, fmaf(dba, bet, dw * gam));
         sg = fmaf(dw, w, sg);
-        sb = fmaf(raw[R.dbh + a], w, sb);
+        sb = fmaf(dba, w, sb);
       }
       part_g[og][kx] = sg; part_b[og][kx] = sb;
     } else { part_g[og][kx] = 0.f; part_b[og][kx] = 0.f; }
