@@ -26,7 +26,7 @@ extern "C" {
 
 #define MAPPO_MAX_HEADS 4      /* MultiDiscrete heads per actor */
 #define MAPPO_MAX_LAYERS 2     /* layer_N hidden (H->H) blocks per MLP base */
-#define MAPPO_ABI_VERSION 2
+#define MAPPO_ABI_VERSION 3
 
 typedef enum mappo_status {
   MAPPO_OK = 0,
@@ -169,6 +169,29 @@ int32_t mappo_rollout_closed_loop(const mappo_net_desc_t* actor_desc, const floa
                                   int32_t num_agents, int32_t num_landmarks, int32_t episode_length, void* stream);
 int32_t mappo_rollout_image_floats(const mappo_net_desc_t* desc);
 int32_t mappo_pack_rollout_weights(const mappo_net_desc_t* desc, const float* params, float* image, void* stream);
+
+/* ---- hidden_size >= 128 MLP nets (BASELINE c5: hidden 512, layer_N 2; algorithms/utils/mlp.py:6-57) ---------------------
+ * Weights no longer fit in shared memory: every Linear is its own GEMM (TMA-fed tcgen05 tiles in MAPPO_GEMM_TF32, FFMA tiles
+ * in MAPPO_GEMM_FP32) with LayerNorm / activation / loss fused into the epilogues, activations in a per-net workspace.
+ * mappo_big_net: 1 if `desc` takes that path (MLP, hidden a multiple of 128 up to 1024, sum(head_dim) <= 32).
+ * For such nets the rollout "image" IS the workspace: size from mappo_rollout_workspace_floats(desc, n_rows) (other nets:
+ * = mappo_rollout_image_floats), weights packed by mappo_pack_rollout_weights_ex (gemm_mode decides tf32 rounding), and the
+ * step is mappo_policy_step_ex (= mappo_policy_step + gemm_mode; the persistent / closed-loop kernels do not cover them).
+ * Training uses the same entry points as every net: mappo_update_workspace_floats / mappo_update_fwd_bwd /
+ * mappo_update_finish (one gradient slot: the pipeline leaves the complete flat gradient). */
+int32_t mappo_big_net(const mappo_net_desc_t* desc);
+int64_t mappo_rollout_workspace_floats(const mappo_net_desc_t* desc, int32_t n_rows);
+int32_t mappo_pack_rollout_weights_ex(const mappo_net_desc_t* desc, const float* params, float* image, int32_t gemm_mode,
+                                      void* stream);
+int32_t mappo_policy_step_ex(const mappo_net_desc_t* actor_desc, const float* actor_params,
+                             const mappo_net_desc_t* critic_desc, const float* critic_params,
+                             const float* obs, const float* share_obs,
+                             const float* h_actor_in, const float* h_critic_in, const float* masks,
+                             const float* avail, const float* exp_noise, uint64_t rng_seed,
+                             const uint64_t* rng_offset_dev, int32_t deterministic, int32_t n_rows,
+                             float* values, float* actions, int64_t* actions_i64, float* logp,
+                             float* h_actor_out, float* h_critic_out, const float* actor_image,
+                             const float* critic_image, int32_t gemm_mode, void* stream);
 
 /* ---- f1: device-side environment -------------------------------------------------------------------
  * One step of n_envs vectorised MPE `simple_spread` worlds (envs/env_wrappers.py:140-154 -> envs/mpe/environment.py:115-146

@@ -8,6 +8,7 @@
 #include <cstring>
 #include "net_tiles.cuh"
 #include "launch_args.h"
+#include "big_net.h"
 
 namespace mappo {
 
@@ -113,6 +114,16 @@ int p2p_allreduce_f32_launch(const void* const*, void* const*, int, int, long lo
 int p2p_allreduce_f64_launch(const void* const*, void* const*, int, int, long long, int, double*, uint32_t*, cudaStream_t);
 int pack_rollout_launch(const NetDev&, const float*, float*, cudaStream_t);
 int rollout_image_floats(const NetDev&);
+namespace big {
+int policy_launch(const NetDev& n, float* ws, const float* input, int n_rows, const EpiSample::Args& sample_in, bool tf32, int sm,
+                  cudaStream_t st);
+bool supported(const NetDev& n);
+int64_t workspace_floats(const NetDev& n, int rows, int sm);
+int pack_launch(const NetDev& n, const float* params, float* ws, int rows, bool round_tf32, int sm, cudaStream_t st);
+int update_launch(const NetDev& n, const float* params, const BatchDev& b, const LossDev& L, const double* norm_stats,
+                  const double* adv_stats, const float* vn_state, float* grad, double* loss_out, float* ws, bool tf32, int sm,
+                  cudaStream_t st);
+}  // namespace big
 
 static int g_sm_count = 0;
 static int sm_count() {
@@ -164,6 +175,17 @@ int32_t mappo_policy_step(const mappo_net_desc_t* ad, const float* ap, const map
                           const uint64_t* rng_offset_dev, int32_t deterministic, int32_t n_rows, float* values,
                           float* actions, int64_t* actions_i64, float* logp, float* h_a_out, float* h_c_out,
                           const float* actor_image, const float* critic_image, void* stream) {
+  return mappo_policy_step_ex(ad, ap, cd, cp, obs, share_obs, h_a_in, h_c_in, masks, avail, exp_noise, rng_seed, rng_offset_dev,
+                              deterministic, n_rows, values, actions, actions_i64, logp, h_a_out, h_c_out, actor_image,
+                              critic_image, MAPPO_GEMM_FP32, stream);
+}
+
+int32_t mappo_policy_step_ex(const mappo_net_desc_t* ad, const float* ap, const mappo_net_desc_t* cd, const float* cp,
+                             const float* obs, const float* share_obs, const float* h_a_in, const float* h_c_in,
+                             const float* masks, const float* avail, const float* exp_noise, uint64_t rng_seed,
+                             const uint64_t* rng_offset_dev, int32_t deterministic, int32_t n_rows, float* values,
+                             float* actions, int64_t* actions_i64, float* logp, float* h_a_out, float* h_c_out,
+                             const float* actor_image, const float* critic_image, int32_t gemm_mode, void* stream) {
   const bool has_a = ap != nullptr, has_c = cp != nullptr;
   if (!has_a && !has_c) { set_error("policy_step: both nets are NULL"); return MAPPO_ERR_INVALID; }
   if (n_rows <= 0) return MAPPO_OK;
@@ -182,6 +204,30 @@ int32_t mappo_policy_step(const mappo_net_desc_t* ad, const float* ap, const map
     if (!share_obs) { set_error("policy_step: share_obs is NULL"); return MAPPO_ERR_INVALID; }
     if (cd->recurrent && (!h_c_in || !masks)) { set_error("policy_step: recurrent critic needs h_critic_in and masks"); return MAPPO_ERR_INVALID; }
     nc = make_net_dev(cd);
+  }
+  if ((has_a && big::supported(na)) || (has_c && big::supported(nc))) {
+    // hidden >= 128: layer-by-layer GEMM pipeline; the "image" is the net's workspace with the packed weights in front
+    // (mappo_rollout_workspace_floats / mappo_pack_rollout_weights_ex)
+    const bool tf32 = gemm_mode == MAPPO_GEMM_TF32;
+    if (has_a) {
+      if (!actor_image) { set_error("policy_step: hidden >= 128 actor needs its workspace (actor_image)"); return MAPPO_ERR_INVALID; }
+      big::EpiSample::Args ea;
+      memset(&ea, 0, sizeof(ea));
+      ea.avail = avail; ea.exp_noise = exp_noise; ea.rng_seed = rng_seed; ea.rng_offset = exp_noise || deterministic ? nullptr : rng_offset_dev;
+      ea.deterministic = deterministic; ea.n_avail = na.head_dim[0];
+      ea.actions = actions; ea.actions_i64 = actions_i64; ea.logp = logp;
+      int rc = big::policy_launch(na, const_cast<float*>(actor_image), obs, n_rows, ea, tf32, sm_count(), (cudaStream_t)stream);
+      if (rc) return rc;
+    }
+    if (has_c) {
+      if (!critic_image) { set_error("policy_step: hidden >= 128 critic needs its workspace (critic_image)"); return MAPPO_ERR_INVALID; }
+      big::EpiSample::Args ea;
+      memset(&ea, 0, sizeof(ea));
+      ea.values = values; ea.deterministic = 1;
+      int rc = big::policy_launch(nc, const_cast<float*>(critic_image), share_obs, n_rows, ea, tf32, sm_count(), (cudaStream_t)stream);
+      if (rc) return rc;
+    }
+    return MAPPO_OK;
   }
   PolArgs a;
   memset(&a, 0, sizeof(a));
@@ -268,11 +314,29 @@ int32_t mappo_rollout_image_floats(const mappo_net_desc_t* desc) {
   return rollout_image_floats(make_net_dev(desc));
 }
 
+int32_t mappo_big_net(const mappo_net_desc_t* desc) {
+  if (validate_desc(desc)) return 0;
+  return big::supported(make_net_dev(desc)) ? 1 : 0;
+}
+
+int64_t mappo_rollout_workspace_floats(const mappo_net_desc_t* desc, int32_t n_rows) {
+  if (validate_desc(desc) || n_rows <= 0) return -1;
+  const NetDev n = make_net_dev(desc);
+  return big::supported(n) ? big::workspace_floats(n, n_rows, sm_count()) : (int64_t)rollout_image_floats(n);
+}
+
 int32_t mappo_pack_rollout_weights(const mappo_net_desc_t* desc, const float* params, float* image, void* stream) {
+  return mappo_pack_rollout_weights_ex(desc, params, image, MAPPO_GEMM_FP32, stream);
+}
+
+int32_t mappo_pack_rollout_weights_ex(const mappo_net_desc_t* desc, const float* params, float* image, int32_t gemm_mode,
+                                      void* stream) {
   int rc = validate_desc(desc);
   if (rc) return rc;
   if (!params || !image || (reinterpret_cast<uintptr_t>(image) & 15)) { set_error("pack_rollout_weights: NULL or unaligned image"); return MAPPO_ERR_INVALID; }
-  return pack_rollout_launch(make_net_dev(desc), params, image, (cudaStream_t)stream);
+  const NetDev n = make_net_dev(desc);
+  if (big::supported(n)) return big::pack_launch(n, params, image, 128, gemm_mode == MAPPO_GEMM_TF32, sm_count(), (cudaStream_t)stream);
+  return pack_rollout_launch(n, params, image, (cudaStream_t)stream);
 }
 
 int32_t mappo_p2p_allreduce_f32(const void* const* peer_bufs, void* const* peer_signals, int32_t world, int32_t rank,
@@ -420,13 +484,15 @@ int32_t mappo_debug_tc_timing(int64_t* out16) { return debug_tc_timing(reinterpr
 
 int32_t mappo_tf32_supported(const mappo_net_desc_t* desc) {
   if (validate_desc(desc)) return 0;
-  return update_mlp_tc_supported(make_net_dev(desc)) ? 1 : 0;
+  const NetDev n = make_net_dev(desc);
+  return (update_mlp_tc_supported(n) || big::supported(n)) ? 1 : 0;
 }
 
 int64_t mappo_update_workspace_floats(const mappo_net_desc_t* desc, int32_t n_rows, int32_t gemm_mode) {
   if (validate_desc(desc)) return -1;
   const NetDev n = make_net_dev(desc);
   if (desc->recurrent) return update_gru_workspace_floats(n, n_rows);
+  if (big::supported(n)) return big::workspace_floats(n, n_rows, sm_count());
   // tf32: [folded weight image][slot-summed raw accumulators]
   return (gemm_mode == MAPPO_GEMM_TF32 && update_mlp_tc_supported(n))
              ? update_mlp_tc_workspace_floats(n) + update_mlp_tc_slot_floats(n) : 0;
@@ -461,6 +527,7 @@ int32_t mappo_update_grad_slots(const mappo_net_desc_t* desc, int32_t n_rows, in
   if (validate_desc(desc)) return -1;
   const NetDev n = make_net_dev(desc);
   if (desc->recurrent) return update_gru_slots(n, n_rows, 1, sm_count());
+  if (big::supported(n)) return 1;                     // the GEMM pipeline leaves the complete flat gradient in slot 0
   if (gemm_mode == MAPPO_GEMM_TF32 && update_mlp_tc_supported(n)) return update_mlp_tc_slots(n, n_rows, sm_count());
   return update_mlp_slots(n, n_rows, sm_count());
 }
@@ -489,6 +556,12 @@ int32_t mappo_update_fwd_bwd(const mappo_net_desc_t* desc, const float* params, 
                              (cudaStream_t)stream);
   }
   if (b.seq_len != 1) { set_error("update_fwd_bwd: feed-forward net with seq_len %d", b.seq_len); return MAPPO_ERR_INVALID; }
+  if (big::supported(n)) {
+    if (!workspace) { set_error("update_fwd_bwd: hidden >= 128 net needs its workspace"); return MAPPO_ERR_INVALID; }
+    return big::update_launch(n, params, b, L, norm_stats, adv_stats, vn_state, grad_part, loss_out, workspace,
+                              loss->gemm_mode == MAPPO_GEMM_TF32, sm_count(), (cudaStream_t)stream);
+  }
+  if (n.hid != 64) { set_error("update_fwd_bwd: hidden_size %d is not built (64, or a multiple of 128 up to 1024)", n.hid); return MAPPO_ERR_UNSUPPORTED; }
   if (loss->gemm_mode == MAPPO_GEMM_TF32) {
     if (!update_mlp_tc_supported(n)) { set_error("update_fwd_bwd: MAPPO_GEMM_TF32 is not built for this net (hidden 64, layer_N 1, in_dim <= 63, MLP only)"); return MAPPO_ERR_UNSUPPORTED; }
     return update_mlp_tc_launch(n, params, b, L, norm_stats, adv_stats, vn_state, grad_part, n_slots, loss_out, workspace,
@@ -518,6 +591,11 @@ int32_t mappo_evaluate_actions(const mappo_net_desc_t* desc, const float* params
   L.clip = loss->clip_param; L.use_policy_active = loss->use_policy_active_masks;
   L.use_value_active = loss->use_value_active_masks; L.huber_delta = loss->huber_delta;
   const NetDev n = make_net_dev(desc);
+  if (!desc->recurrent && big::supported(n)) {
+    if (!workspace) { set_error("evaluate_actions: hidden >= 128 net needs its workspace"); return MAPPO_ERR_INVALID; }
+    return big::update_launch(n, params, b, L, norm_stats, nullptr, nullptr, nullptr, loss_out, workspace,
+                              loss->gemm_mode == MAPPO_GEMM_TF32, sm_count(), (cudaStream_t)stream);
+  }
   const int slots = mappo_update_grad_slots(desc, b.n_rows, MAPPO_GEMM_FP32);
   if (desc->recurrent) {
     if (!workspace) { set_error("evaluate_actions: recurrent net needs a workspace"); return MAPPO_ERR_INVALID; }

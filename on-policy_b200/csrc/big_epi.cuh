@@ -84,9 +84,10 @@ struct EpiFwd {
     const float mu = round_op(m, rt);
     const float sigma = round_op(sqrtf(var + kLnEps), rt);
     a.stats_out[grow] = make_float2(mu, 1.0f / sigma);
-    float* e = a.out + (size_t)grow * a.ld_out + a.N;
-    e[0] = mu;
-    e[1] = sigma;
+    float4* e = reinterpret_cast<float4*>(a.out + (size_t)grow * a.ld_out + a.N);      // the kExt extra columns of the row
+    e[0] = make_float4(mu, sigma, 0.f, 0.f);
+#pragma unroll
+    for (int q = 1; q < kExt / 4; ++q) e[q] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 };
 

@@ -1,0 +1,383 @@
+// big_gemm.cu -- the tensor-core kernels of the hidden >= 128 MLP path: TMA-fed, warp-specialised tcgen05 GEMMs.
+//
+//   big_lin_kernel<Epi>   out = epilogue(A[rows, K] . W[N, K]^T)   K-major operands (activations x weights), used for
+//                         forward layers (EpiFwd), the head + losses (EpiHead / EpiSample) and input gradients (EpiBwd)
+//   big_grad_kernel       G[m, q] = sum_rows P[row, m] Q[row, q]   MN-major operands (contraction over the rows of two
+//                         row-major matrices): every weight gradient
+//
+// big_lin_kernel: persistent CTAs (one per SM), 6 warps:
+//   warp 0   TMA producer: A box {32 K x 128 rows} + W box {32 K x BN rows} per stage, SWIZZLE_128B, 3-stage mbarrier ring
+//   warp 1   MMA issuer (one lane): 4 x tcgen05.mma kind::tf32 (M 128, N BN, K 8) per stage into one of TWO TMEM accumulator
+//            stages (2 x BN columns), tcgen05.commit releases the smem stage / publishes the accumulator
+//   warps 2-5  epilogue: thread = row (TMEM lane), 32 columns per step through an Epi functor (big_epi.cuh), results staged
+//            in a 128B-swizzled [128 x 32] tile and written with TMA stores; EpiBwd also TMA-loads the stored activation
+//            tile of the same coordinates into the staging slot first (in-place transform)
+// The two N tiles of a 512-wide row go to the SAME CTA back to back, so the row statistics stay in registers, and the MMA
+// of tile i + 1 overlaps the epilogue of tile i (double-buffered accumulators).
+#include "big_tc.cuh"
+#include "big_epi.cuh"
+#include "big_net.h"
+
+namespace mappo {
+namespace big {
+
+constexpr int kLinThreads = 192;
+constexpr int kNS = 4;                    // staging slots (16 KB each)
+constexpr int kAinDepth = 2;              // activation tiles in flight ahead of the epilogue (EpiBwd)
+constexpr int kABytes = 128 * 128;        // A stage: 128 rows x 32 tf32
+
+struct LinSmem { int stage_bytes, stages_off, slots_off, colvec_off, scratch_off, bars_off, total; };
+__host__ __device__ inline LinSmem make_lin_smem(int BN, int n_stages, int N_cv, bool scratch) {
+  LinSmem s;
+  s.stage_bytes = kABytes + BN * 128;
+  s.stages_off = 0;
+  s.slots_off = n_stages * s.stage_bytes;
+  s.colvec_off = s.slots_off + kNS * 16384;
+  s.scratch_off = s.colvec_off + ((2 * N_cv * 4 + 127) & ~127);
+  s.bars_off = s.scratch_off + (scratch ? 32 * kLgLd * 4 : 0);
+  s.total = s.bars_off + 256;
+  return s;
+}
+
+template <class Epi>
+__global__ void __launch_bounds__(kLinThreads, 1)
+big_lin_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapAin,
+               const typename Epi::Args ea, const LinShape sh) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ double sred[2 * 32];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int BN = sh.BN, NT = sh.N / sh.BN, KB = (sh.K + 31) / 32, NST = sh.n_stages;
+  const LinSmem L = make_lin_smem(BN, NST, sh.N, Epi::kNeedsScratch);
+  float* cv = reinterpret_cast<float*>(smem + L.colvec_off);
+  float* scratch = reinterpret_cast<float*>(smem + L.scratch_off);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars_off);
+  uint64_t* full = bars;                       // [NST]
+  uint64_t* empty = bars + 4;                  // [NST]
+  uint64_t* tfull = bars + 8;                  // [2]
+  uint64_t* tempty = bars + 10;                // [2]
+  uint64_t* ainfull = bars + 12;               // [kNS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  const uint32_t tmem_cols = (2 * BN <= 32) ? 32u : (2 * BN <= 64 ? 64u : (2 * BN <= 128 ? 128u : (2 * BN <= 256 ? 256u : 512u)));
+
+  for (int i = tid; i < 2 * sh.N; i += kLinThreads) cv[i] = ea.colvec[i];
+  if (tid == 0) {
+    for (int i = 0; i < NST; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 128); }
+    for (int i = 0; i < kNS; ++i) mbar_init(ainfull + i, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapB);
+    if (Epi::kStoresOut) tma_prefetch_desc(&mapOut);
+    if (Epi::kHasAin) tma_prefetch_desc(&mapAin);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  typename Epi::Thread th;
+  Epi::init_thread(th);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int rb = blockIdx.x; rb < sh.n_rowblocks; rb += gridDim.x)
+        for (int nt = 0; nt < NT; ++nt)
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(empty + stage, phase ^ 1);
+            uint8_t* sA = smem + L.stages_off + stage * L.stage_bytes;
+            mbar_expect_tx(full + stage, (uint32_t)L.stage_bytes);
+            tma_load_2d(sA, &mapA, kb * 32, rb * 128, full + stage);
+            tma_load_2d(sA + kABytes, &mapB, kb * 32, nt * BN, full + stage);
+            if (++stage == NST) { stage = 0; phase ^= 1; }
+          }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, BN, 0, 0);
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int rb = blockIdx.x; rb < sh.n_rowblocks; rb += gridDim.x)
+        for (int nt = 0; nt < NT; ++nt) {
+          mbar_wait(tempty + as, aphase ^ 1);             // the epilogue has drained this accumulator stage
+          tc_fence_after();
+          const uint32_t d = tmem + (uint32_t)(as * BN);
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(full + stage, phase);
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(smem + L.stages_off + stage * L.stage_bytes), b0 = a0 + kABytes;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_tf32(d, make_desc(a0 + k * 32, 16, 1024, 2), make_desc(b0 + k * 32, 16, 1024, 2), idesc, (kb | k) ? 1u : 0u);
+            umma_commit(empty + stage);                   // frees the smem stage when these MMAs have read it
+            if (++stage == NST) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(tfull + as);                        // accumulator complete
+          as ^= 1;
+          if (as == 0) aphase ^= 1;
+        }
+    }
+  } else {
+    // ===================== epilogue (128 threads) =====================
+    const int et = tid - 64;                              // 0..127
+    const int r = (warp & 3) * 32 + lane;                 // TMEM lane = row of the tile (a warp may only touch lanes 32 (warp % 4)..)
+    const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
+    uint8_t* slots = smem + L.slots_off;
+    const int CPR = sh.N / kChunk;                        // chunks per row block
+    const int my_rbs = (sh.n_rowblocks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const long long total_chunks = (long long)my_rbs * CPR;
+    auto issue_ain = [&](long long g) {                   // thread et == 0 only
+      if (g >= total_chunks) return;
+      const int rbl = (int)(g / CPR), c = (int)(g % CPR);
+      const int slot = (int)(g % kNS);
+      mbar_expect_tx(ainfull + slot, 16384u);
+      tma_load_2d(slots + slot * 16384, &mapAin, c * kChunk, (blockIdx.x + rbl * gridDim.x) * 128, ainfull + slot);
+    };
+    if (Epi::kHasAin && et == 0)
+      for (int i = 0; i < kAinDepth; ++i) issue_ain(i);
+    int as = 0;
+    uint32_t aphase = 0;
+    long long g = 0;                                      // running chunk index of this CTA
+    for (int rb = blockIdx.x; rb < sh.n_rowblocks; rb += gridDim.x) {
+      const int grow = rb * 128 + r;
+      typename Epi::Row row;
+      Epi::begin_row(ea, row, grow);
+      for (int nt = 0; nt < NT; ++nt) {
+        mbar_wait(tfull + as, aphase);
+        tc_fence_after();
+        for (int c = 0; c < BN / kChunk; ++c, ++g) {
+          const int col0 = nt * BN + c * kChunk;
+          float acc[kChunk], ain[kChunk], out[kChunk];
+          tmem_ld32(tmem + lane_base + (uint32_t)(as * BN + c * kChunk), acc);
+          tmem_ld_wait();
+          if (c == BN / kChunk - 1) {                     // last read of this accumulator stage: hand it back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(tempty + as);
+          }
+          const int slot = (int)(g % kNS);
+          uint8_t* sl = slots + slot * 16384;
+          if (Epi::kHasAin) {
+            mbar_wait(ainfull + slot, (uint32_t)((g / kNS) & 1));
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+              const float4 v = *reinterpret_cast<const float4*>(sl + sw128_off(r, ch));
+              ain[4 * ch] = v.x; ain[4 * ch + 1] = v.y; ain[4 * ch + 2] = v.z; ain[4 * ch + 3] = v.w;
+            }
+          } else if (Epi::kStoresOut && sh.store_out) {
+            if (et == 0) tma_store_wait_read<kNS - 1>();  // the store that last used this slot has read it
+            named_bar_sync(1, 128);
+          }
+          Epi::chunk(ea, th, row, acc, ain, out, col0, cv, scratch, r, grow);
+          if (Epi::kStoresOut && sh.store_out) {
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch)
+              *reinterpret_cast<float4*>(sl + sw128_off(r, ch)) = make_float4(out[4 * ch], out[4 * ch + 1], out[4 * ch + 2], out[4 * ch + 3]);
+            fence_async_smem();
+            named_bar_sync(1, 128);
+            if (et == 0) {
+              tma_store_2d(&mapOut, col0, rb * 128, sl);
+              tma_store_commit();
+              if (Epi::kHasAin) {                          // refill: slot of chunk g + depth was last stored by chunk g + depth - kNS
+                tma_store_wait_read<kNS - kAinDepth>();
+                issue_ain(g + kAinDepth);
+              }
+            }
+          } else if (Epi::kHasAin) {
+            named_bar_sync(1, 128);
+            if (et == 0) issue_ain(g + kAinDepth);
+          }
+        }
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+      Epi::end_row(ea, row, grow);
+    }
+    if (et == 0) tma_store_wait_all<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  Epi::finish_thread(ea, th, sred, tid, kLinThreads);
+  if (warp == 1) tmem_dealloc(tmem, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// weight-gradient GEMM: G[m, q] = sum_{row in split} P[row, m] Q[row, q]; one output tile (128 m x up to 288 q) per CTA,
+// the rows of the batch split over `splits` CTAs per tile; partial[split][m][q] written with plain stores.
+// Operands are MN-major tf32: TMA boxes {32 columns x 32 rows} with the 128B-swizzle / 32B-atom mode land as
+// [column group][row][32] and are consumed with UMMA layout type SWIZZLE_128B_BASE32B (SBO = 4 rows, LBO = one group).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kGradKR = 32;               // rows per stage
+constexpr int kGradGroupBytes = kGradKR * 128;
+constexpr int kGradStages = 4;
+constexpr int kGradStageBytes = (4 + 9) * kGradGroupBytes;      // P: 4 groups, Q: up to 9 groups (288 columns)
+
+__global__ void __launch_bounds__(kLinThreads, 1)
+big_grad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapQ, float* __restrict__ partial,
+                const GradShape sh) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t full[kGradStages], empty[kGradStages], done;
+  __shared__ uint32_t tmem_slot;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int unit = blockIdx.x;
+  const int split = unit / (sh.m_tiles * sh.n_tiles), rem = unit % (sh.m_tiles * sh.n_tiles);
+  const int mt = rem / sh.n_tiles, nt = rem % sh.n_tiles;
+  const int q0 = sh.q0[nt], qw = sh.qw[nt], qgroups = qw / 32;
+  const int r0 = split * sh.rows_per_split, r1 = min(sh.rows, r0 + sh.rows_per_split);
+  const int n_kb = r1 > r0 ? (r1 - r0 + kGradKR - 1) / kGradKR : 0;
+  if (tid == 0) {
+    for (int i = 0; i < kGradStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+    mbar_init(&done, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&mapP); tma_prefetch_desc(&mapQ);
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (warp == 0 && lane == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < n_kb; ++kb) {
+      mbar_wait(empty + stage, phase ^ 1);
+      uint8_t* sP = smem + stage * kGradStageBytes;
+      uint8_t* sQ = sP + 4 * kGradGroupBytes;
+      mbar_expect_tx(full + stage, (uint32_t)((4 + qgroups) * kGradGroupBytes));
+      const int row = r0 + kb * kGradKR;
+      // rows beyond r1 belong to the next split: they must not be counted twice -> the row coordinate is clamped by
+      // rows_per_split being a multiple of kGradKR (host), only the LAST split can run past `rows` (TMA zero fill)
+      for (int i = 0; i < 4; ++i) tma_load_2d(sP + i * kGradGroupBytes, &mapP, mt * 128 + i * 32, row, full + stage);
+      for (int i = 0; i < qgroups; ++i) tma_load_2d(sQ + i * kGradGroupBytes, &mapQ, q0 + i * 32, row, full + stage);
+      if (++stage == kGradStages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1 && lane == 0) {
+    const int n1 = qw > 256 ? 256 : qw, n2 = qw - n1;
+    const uint32_t id1 = make_idesc(128, n1, 1, 1), id2 = make_idesc(128, n2 > 0 ? n2 : 32, 1, 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < n_kb; ++kb) {
+      mbar_wait(full + stage, phase);
+      tc_fence_after();
+      const uint32_t p0 = smem_u32(smem + stage * kGradStageBytes), qb = p0 + 4 * kGradGroupBytes;
+#pragma unroll
+      for (int k = 0; k < kGradKR / 8; ++k) {
+        const uint64_t pd = make_desc(p0 + k * 1024, kGradGroupBytes, 512, 1);
+        umma_tf32(tmem, pd, make_desc(qb + k * 1024, kGradGroupBytes, 512, 1), id1, (kb | k) ? 1u : 0u);
+        if (n2 > 0)
+          umma_tf32(tmem + 256, pd, make_desc(qb + 8 * kGradGroupBytes + k * 1024, kGradGroupBytes, 512, 1), id2, (kb | k) ? 1u : 0u);
+      }
+      umma_commit(empty + stage);
+      if (++stage == kGradStages) { stage = 0; phase ^= 1; }
+    }
+    umma_commit(&done);
+  } else if (warp >= 2) {
+    const int r = (warp & 3) * 32 + lane;
+    const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
+    const int m = mt * 128 + r;
+    if (n_kb > 0) { mbar_wait(&done, 0); tc_fence_after(); }
+    float* dst = partial + ((size_t)split * sh.M + (size_t)min(m, sh.M - 1)) * sh.ldq + q0;
+    for (int c = 0; c < qgroups; ++c) {
+      float v[kChunk];
+      if (n_kb > 0) { tmem_ld32(tmem + lane_base + (uint32_t)(c * kChunk), v); tmem_ld_wait(); }
+      else {
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j) v[j] = 0.f;
+      }
+      if (m < sh.M) {
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch)
+          *reinterpret_cast<float4*>(dst + c * kChunk + 4 * ch) = make_float4(v[4 * ch], v[4 * ch + 1], v[4 * ch + 2], v[4 * ch + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side: tensor maps + launches
+// ------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int ensure_encode() {
+  if (g_encode) return MAPPO_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+    set_error("big net path: cuTensorMapEncodeTiled is not available from the driver");
+    return MAPPO_ERR_CUDA;
+  }
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return MAPPO_OK;
+}
+
+// 2-D fp32 map over a row-major matrix [rows][width] with leading dimension ld (floats), box {box_w, box_h}
+int make_map(CUtensorMap* m, const float* base, long long width, long long rows, long long ld, int box_w, int box_h, int swizzle) {
+  int rc = ensure_encode();
+  if (rc) return rc;
+  cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+  cuuint32_t es[2] = {1, 1};
+  const CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, (CUtensorMapSwizzle)swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): base %p width %lld rows %lld ld %lld box %dx%d swizzle %d", (int)r, (const void*)base,
+              width, rows, ld, box_w, box_h, swizzle);
+    return MAPPO_ERR_CUDA;
+  }
+  return MAPPO_OK;
+}
+
+template <class Epi>
+static int lin_launch_t(const LinOperands& o, const typename Epi::Args& ea, LinShape sh, const char* name, cudaStream_t st) {
+  CUtensorMap mA, mB, mO, mI;
+  int rc = make_map(&mA, o.A, sh.K, sh.n_rows, o.lda, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = make_map(&mB, o.W, sh.K, sh.N, o.ldw, 32, sh.BN, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  mO = mA; mI = mA;
+  if (Epi::kStoresOut && sh.store_out) { rc = make_map(&mO, o.out, sh.N, sh.n_rows, o.ldo, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B); if (rc) return rc; }
+  if (Epi::kHasAin) { rc = make_map(&mI, o.ain, sh.N, sh.n_rows, o.ldain, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B); if (rc) return rc; }
+  sh.n_rowblocks = (sh.n_rows + 127) / 128;
+  sh.n_stages = sh.BN >= 256 ? 3 : 4;
+  const LinSmem L = make_lin_smem(sh.BN, sh.n_stages, sh.N, Epi::kNeedsScratch);
+  const size_t bytes = (size_t)L.total + 1024;
+  if (bytes > 227 * 1024) { set_error("%s: %zu B shared memory > 227 KB (N = %d)", name, bytes, sh.N); return MAPPO_ERR_UNSUPPORTED; }
+  if (cudaFuncSetAttribute(big_lin_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+    return check_launch("big_lin_kernel: cudaFuncSetAttribute");
+  const int grid = sh.n_rowblocks < o.sm_count ? sh.n_rowblocks : o.sm_count;
+  big_lin_kernel<Epi><<<grid, kLinThreads, bytes, st>>>(mA, mB, mO, mI, ea, sh);
+  return check_launch(name);
+}
+
+int lin_fwd_launch(const LinOperands& o, const EpiFwd::Args& ea, const LinShape& sh, cudaStream_t st) { return lin_launch_t<EpiFwd>(o, ea, sh, "big_lin_kernel<EpiFwd>", st); }
+int lin_bwd_launch(const LinOperands& o, const EpiBwd::Args& ea, const LinShape& sh, cudaStream_t st) { return lin_launch_t<EpiBwd>(o, ea, sh, "big_lin_kernel<EpiBwd>", st); }
+int lin_head_launch(const LinOperands& o, const EpiHead::Args& ea, const LinShape& sh, cudaStream_t st) { return lin_launch_t<EpiHead>(o, ea, sh, "big_lin_kernel<EpiHead>", st); }
+int lin_sample_launch(const LinOperands& o, const EpiSample::Args& ea, const LinShape& sh, cudaStream_t st) { return lin_launch_t<EpiSample>(o, ea, sh, "big_lin_kernel<EpiSample>", st); }
+
+int grad_gemm_launch(const float* P, int ldp, const float* Q, int ldq_in, float* partial, GradShape sh, cudaStream_t st) {
+  CUtensorMap mP, mQ;
+  int rc = make_map(&mP, P, sh.Pw, sh.rows, ldp, 32, kGradKR, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc) return rc;
+  rc = make_map(&mQ, Q, sh.Qw, sh.rows, ldq_in, 32, kGradKR, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc) return rc;
+  const size_t bytes = (size_t)kGradStages * kGradStageBytes + 1024;
+  if (cudaFuncSetAttribute(big_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+    return check_launch("big_grad_kernel: cudaFuncSetAttribute");
+  big_grad_kernel<<<sh.splits * sh.m_tiles * sh.n_tiles, kLinThreads, bytes, st>>>(mP, mQ, partial, sh);
+  return check_launch("big_grad_kernel");
+}
+
+}  // namespace big
+}  // namespace mappo

@@ -56,6 +56,11 @@ _SIGS = {
     "mappo_rollout_persistent": (_i32, [C.POINTER(NetDesc), _P, _P, C.POINTER(NetDesc), _P, _P] + [_P] * 11 + [_P] * 6 +
                                  [_P, _u64, _P, _i32, _i32, _P]),
     "mappo_rollout_image_floats": (_i32, [C.POINTER(NetDesc)]),
+    "mappo_big_net": (_i32, [C.POINTER(NetDesc)]),
+    "mappo_rollout_workspace_floats": (_i64, [C.POINTER(NetDesc), _i32]),
+    "mappo_pack_rollout_weights_ex": (_i32, [C.POINTER(NetDesc), _P, _P, _i32, _P]),
+    "mappo_policy_step_ex": (_i32, [C.POINTER(NetDesc), _P, C.POINTER(NetDesc), _P] + [_P] * 7 +
+                             [_u64, _P, _i32, _i32] + [_P] * 6 + [_P, _P] + [_i32, _P]),
     "mappo_pack_rollout_weights": (_i32, [C.POINTER(NetDesc), _P, _P, _P]),
     "mappo_counter_add": (_i32, [_P, _u64, _P]),
     "mappo_p2p_allreduce_f32": (_i32, [_P, _P, _i32, _i32, _i64, _i32, _P, _P, _P, _P, _P]),
@@ -111,7 +116,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError here = header / library out of sync
         fn.restype = res
         fn.argtypes = args
-    if lib.mappo_abi_version() != 2:
+    if lib.mappo_abi_version() != 3:
         raise RuntimeError("libmappo_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -86,6 +86,13 @@ class RolloutEngine:
         self.env = device_env
         self.env_reset_states = None        # optional [T, N, 2 (M + L)] float64: injected episode starts (parity tests)
         want_persistent = os.environ.get("MAPPO_B200_PERSISTENT_ROLLOUT", "1") == "1"
+        # hidden >= 128 nets run the layer-by-layer GEMM pipeline per step (the persistent kernels keep weights in shared memory)
+        self.big = bool(self.lib.mappo_big_net(C.byref(policy.actor.desc)))
+        self.gemm = getattr(trainer, "gemm_mode", _lib.GEMM_FP32)
+        if self.big:
+            if device_env is not None:
+                raise NotImplementedError("closed-loop device env with hidden >= 128 nets")
+            want_persistent = False
         self.persistent_rollout = want_persistent and device_env is None
         # closed loop as ONE launch (mappo_rollout_closed_loop): feed-forward policies
         self.closed_persistent = want_persistent and device_env is not None and not self.recurrent
@@ -114,9 +121,10 @@ class RolloutEngine:
         self.loss_out = torch.zeros(6, dtype=torch.float64, device=self.dev)
         self.h_loss = torch.zeros(6, dtype=torch.float64).pin_memory()
         # rollout weight images (shared-memory layout), re-packed once per iteration, fetched by TMA in policy_step
-        self.img_actor = torch.zeros(int(self.lib.mappo_rollout_image_floats(C.byref(policy.actor.desc))),
+        # (hidden >= 128 nets: the image is the workspace of the layer-by-layer GEMM pipeline for E rows)
+        self.img_actor = torch.zeros(int(self.lib.mappo_rollout_workspace_floats(C.byref(policy.actor.desc), self.E)),
                                      dtype=torch.float32, device=self.dev)
-        self.img_critic = torch.zeros(int(self.lib.mappo_rollout_image_floats(C.byref(policy.critic.desc))),
+        self.img_critic = torch.zeros(int(self.lib.mappo_rollout_workspace_floats(C.byref(policy.critic.desc), self.E)),
                                       dtype=torch.float32, device=self.dev)
         self.host = {}
         self.graph = None
@@ -200,7 +208,7 @@ class RolloutEngine:
         b, pol, lib, st = self.buffer, self.policy, self.lib, stream_ptr()
         rec = self.recurrent
         noise = self.d_noise[t] if self.d_noise is not None else None
-        check(lib.mappo_policy_step(
+        check(lib.mappo_policy_step_ex(
             C.byref(pol.actor.desc), ptr(pol.actor.flat), C.byref(pol.critic.desc), ptr(pol.critic.flat),
             ptr(b.obs[t]), ptr(b.share_obs[t]), ptr(b.rnn_states[t]) if rec else None,
             ptr(b.rnn_states_critic[t]) if rec else None, ptr(b.masks[t]),
@@ -208,7 +216,7 @@ class RolloutEngine:
             self.seed, ptr(pol.rng_offset), 0, self.E,
             ptr(b.value_preds[t]), ptr(b.actions[t]), None, ptr(b.action_log_probs[t]),
             ptr(b.rnn_states[t + 1]) if rec else None, ptr(b.rnn_states_critic[t + 1]) if rec else None,
-            ptr(self.img_actor), ptr(self.img_critic), st))
+            ptr(self.img_actor), ptr(self.img_critic), self.gemm, st))
         if self.env is not None:             # closed loop: the env consumes the actions just written to slot t
             rs = self.env_reset_states[t] if self.env_reset_states is not None else None
             self.env.step(b.actions[t], self.d_obs[t], self.d_share[t], self.d_rew[t], self.d_done[t], reset_states=rs)
@@ -264,11 +272,11 @@ class RolloutEngine:
     def _compute(self):
         b, pol, lib, st, T = self.buffer, self.policy, self.lib, stream_ptr(), self.T
         rec = self.recurrent
-        check(lib.mappo_policy_step(
+        check(lib.mappo_policy_step_ex(
             C.byref(pol.actor.desc), None, C.byref(pol.critic.desc), ptr(pol.critic.flat),
             None, ptr(b.share_obs[T]), None, ptr(b.rnn_states_critic[T]) if rec else None, ptr(b.masks[T]),
             None, None, 0, None, 1, self.E, ptr(b.value_preds[T]), None, None, None, None, None,
-            None, ptr(self.img_critic), st))
+            None, ptr(self.img_critic), self.gemm, st))
         vn = self.trainer.value_normalizer
         b._adv_stats.zero_()
         check(lib.mappo_compute_returns(ptr(b.rewards), ptr(b.value_preds), ptr(b.masks), ptr(b.bad_masks),
@@ -298,8 +306,8 @@ class RolloutEngine:
         """Enqueue one full iteration on the current stream (no host synchronisation)."""
         n0 = self.lib.mappo_debug_launch_count()
         pol = self.policy
-        check(self.lib.mappo_pack_rollout_weights(C.byref(pol.actor.desc), ptr(pol.actor.flat), ptr(self.img_actor), stream_ptr()))
-        check(self.lib.mappo_pack_rollout_weights(C.byref(pol.critic.desc), ptr(pol.critic.flat), ptr(self.img_critic), stream_ptr()))
+        check(self.lib.mappo_pack_rollout_weights_ex(C.byref(pol.actor.desc), ptr(pol.actor.flat), ptr(self.img_actor), self.gemm, stream_ptr()))
+        check(self.lib.mappo_pack_rollout_weights_ex(C.byref(pol.critic.desc), ptr(pol.critic.flat), ptr(self.img_critic), self.gemm, stream_ptr()))
         if self.persistent_rollout:
             self._rollout_persistent()
             self._returns()
@@ -346,17 +354,17 @@ class RolloutEngine:
         def collect():
             pol = self.policy
             if self.persistent_rollout:
-                check(self.lib.mappo_pack_rollout_weights(C.byref(pol.actor.desc), ptr(pol.actor.flat), ptr(self.img_actor), stream_ptr()))
-                check(self.lib.mappo_pack_rollout_weights(C.byref(pol.critic.desc), ptr(pol.critic.flat), ptr(self.img_critic), stream_ptr()))
+                check(self.lib.mappo_pack_rollout_weights_ex(C.byref(pol.actor.desc), ptr(pol.actor.flat), ptr(self.img_actor), self.gemm, stream_ptr()))
+                check(self.lib.mappo_pack_rollout_weights_ex(C.byref(pol.critic.desc), ptr(pol.critic.flat), ptr(self.img_critic), self.gemm, stream_ptr()))
                 self._rollout_persistent()
                 return
             if self.closed_persistent:
-                check(self.lib.mappo_pack_rollout_weights(C.byref(pol.actor.desc), ptr(pol.actor.flat), ptr(self.img_actor), stream_ptr()))
-                check(self.lib.mappo_pack_rollout_weights(C.byref(pol.critic.desc), ptr(pol.critic.flat), ptr(self.img_critic), stream_ptr()))
+                check(self.lib.mappo_pack_rollout_weights_ex(C.byref(pol.actor.desc), ptr(pol.actor.flat), ptr(self.img_actor), self.gemm, stream_ptr()))
+                check(self.lib.mappo_pack_rollout_weights_ex(C.byref(pol.critic.desc), ptr(pol.critic.flat), ptr(self.img_critic), self.gemm, stream_ptr()))
                 self._rollout_closed()
                 return
-            check(self.lib.mappo_pack_rollout_weights(C.byref(pol.actor.desc), ptr(pol.actor.flat), ptr(self.img_actor), stream_ptr()))
-            check(self.lib.mappo_pack_rollout_weights(C.byref(pol.critic.desc), ptr(pol.critic.flat), ptr(self.img_critic), stream_ptr()))
+            check(self.lib.mappo_pack_rollout_weights_ex(C.byref(pol.actor.desc), ptr(pol.actor.flat), ptr(self.img_actor), self.gemm, stream_ptr()))
+            check(self.lib.mappo_pack_rollout_weights_ex(C.byref(pol.critic.desc), ptr(pol.critic.flat), ptr(self.img_critic), self.gemm, stream_ptr()))
             for t in range(self.T):
                 self._collect_and_insert(t)
 

@@ -38,7 +38,7 @@ class R_MAPPOPolicy:
         self.rng_mode = os.environ.get("MAPPO_B200_RNG", "host")
         self.rng_seed = int(getattr(args, "seed", 1))
         self.rng_offset = torch.zeros(1, dtype=torch.int64, device=self.device)
-        self._img = None
+        self._img, self._img_key = None, None
 
     def lr_decay(self, episode, episodes):
         """reference :39-46."""
@@ -92,25 +92,30 @@ class R_MAPPOPolicy:
                 if h_c_out is None:
                     h_c_out = torch.empty(n_rows, self._recN, self._H, dtype=torch.float32, device=dev)
         img_a = img_c = None
+        gemm = _lib.GEMM_TF32 if os.environ.get("MAPPO_B200_GEMM", "fp32") == "tf32" else _lib.GEMM_FP32
         if not self._recurrent:
             # feed-forward nets: hand the kernel the packed weight image (one TMA bulk copy per CTA, and the
             # warp-per-two-rows rollout path).  Re-packed per call: the parameters may have been stepped in between.
-            if self._img is None:
-                self._img = [torch.empty(int(lib.mappo_rollout_image_floats(C.byref(n.desc))), dtype=torch.float32,
-                                         device=dev) for n in (self.actor, self.critic)]
+            # hidden >= 128 nets: the "image" is the workspace of the GEMM pipeline (packed weights + activations of n_rows)
+            big = bool(lib.mappo_big_net(C.byref(self.actor.desc)))
+            key = n_rows if big else 0
+            if self._img is None or self._img_key != key:
+                self._img = [torch.empty(int(lib.mappo_rollout_workspace_floats(C.byref(n.desc), max(n_rows, 1))),
+                                         dtype=torch.float32, device=dev) for n in (self.actor, self.critic)]
+                self._img_key = key
             if want_actor:
                 img_a = self._img[0]
-                check(lib.mappo_pack_rollout_weights(C.byref(self.actor.desc), ptr(self.actor.flat), ptr(img_a), stream_ptr()))
+                check(lib.mappo_pack_rollout_weights_ex(C.byref(self.actor.desc), ptr(self.actor.flat), ptr(img_a), gemm, stream_ptr()))
             if want_critic:
                 img_c = self._img[1]
-                check(lib.mappo_pack_rollout_weights(C.byref(self.critic.desc), ptr(self.critic.flat), ptr(img_c), stream_ptr()))
-        check(lib.mappo_policy_step(
+                check(lib.mappo_pack_rollout_weights_ex(C.byref(self.critic.desc), ptr(self.critic.flat), ptr(img_c), gemm, stream_ptr()))
+        check(lib.mappo_policy_step_ex(
             C.byref(self.actor.desc), ptr(self.actor.flat) if want_actor else None,
             C.byref(self.critic.desc), ptr(self.critic.flat) if want_critic else None,
             ptr(obs), ptr(cent), ptr(h_a_d), ptr(h_c_d), ptr(masks_d), ptr(avail_d), ptr(exp_noise),
             self.rng_seed, ptr(self.rng_offset), int(bool(deterministic)), n_rows,
             ptr(values), ptr(actions_f), ptr(actions), ptr(logp), ptr(h_a_out), ptr(h_c_out), ptr(img_a), ptr(img_c),
-            stream_ptr()))
+            gemm, stream_ptr()))
         if want_actor and exp_noise is None and not deterministic:
             check(lib.mappo_counter_add(ptr(self.rng_offset), n_rows, stream_ptr()))
         if not self._recurrent:                      # MLP policies hand the states back untouched (r_actor_critic.py:66-71)

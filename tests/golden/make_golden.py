@@ -83,6 +83,19 @@ CASES = {
                          lr=7e-4, critic_lr=1e-3, use_clipped_value_loss=False, use_huber_loss=False,
                          use_policy_active_masks=False, use_max_grad_norm=False),
         algo="mappo", feed="smac", iters=1, seed=4),
+    # c5 nets at full width (train_hanabi_forward.sh: hidden 512, layer_N 2, obs 658+2, share 783+2, 20 actions, ReLU,
+    # entropy 0.015, critic_lr 1e-3) on a small batch; big tensors are stored subsampled (see `put`), the initial
+    # weights as seed + checksums (the engine's initialiser is seed-identical to the reference's)
+    "c5_h512_hanabi": dict(
+        cfg=O.PathConfig(episode_length=6, n_rollout_threads=12, num_agents=2, obs_dim=660, share_obs_dim=785,
+                         act_dims=(20,), layer_N=2, hidden_size=512, ppo_epoch=2, num_mini_batch=1, entropy_coef=0.015,
+                         lr=7e-4, critic_lr=1e-3),
+        algo="mappo", feed="smac", iters=1, seed=6, compact=True),
+    # c2 of BASELINE.json exactly (the benchmark size, N = 128): one iteration
+    "c2_mlp_n128": dict(
+        cfg=O.PathConfig(episode_length=25, n_rollout_threads=128, num_agents=3, obs_dim=18, share_obs_dim=54,
+                         act_dims=(5,), use_ReLU=False, ppo_epoch=10, lr=7e-4, critic_lr=7e-4),
+        algo="mappo", feed="mpe", iters=1, seed=7, compact=True),
     # non-default return modes: proper time limits + GAE, naive recurrent generator
     "naive_rnn_ptl": dict(
         cfg=O.PathConfig(episode_length=8, n_rollout_threads=4, num_agents=2, obs_dim=10, share_obs_dim=20,
@@ -92,8 +105,21 @@ CASES = {
 }
 
 
+def put(out, key, arr, compact):
+    """Store a tensor; in compact cases a matrix with more than 65536 elements keeps every 16th row + its Frobenius norm."""
+    arr = np.asarray(arr)
+    if compact and arr.ndim == 2 and arr.size > 65536:
+        idx = np.arange(0, arr.shape[0], 16, dtype=np.int32)
+        out[key + "@rows"] = idx
+        out[key + "@norm"] = np.array(np.sqrt((arr.astype(np.float64) ** 2).sum()))
+        out[key] = arr[idx].copy()
+    else:
+        out[key] = arr.copy()
+
+
 def run_case(name, spec):
     cfg, algo, seed = spec["cfg"], spec["algo"], spec["seed"]
+    compact = bool(spec.get("compact", False))
     sys.path.insert(0, REF)
     from onpolicy.utils.shared_buffer import SharedReplayBuffer
     from onpolicy.algorithms.r_mappo.r_mappo import R_MAPPO
@@ -113,10 +139,17 @@ def run_case(name, spec):
     buf = SharedReplayBuffer(args, cfg.num_agents, obs_s, share_s, act_s)
 
     out = {"cfg_json": np.array(repr(cfg.to_dict()))}
-    for k, v in policy.actor.state_dict().items():
-        out[f"init/actor/{k}"] = v.numpy().copy()
-    for k, v in policy.critic.state_dict().items():
-        out[f"init/critic/{k}"] = v.numpy().copy()
+    if compact:
+        out["init_seed"] = np.array(seed)
+        for net, sd in (("actor", policy.actor.state_dict()), ("critic", policy.critic.state_dict())):
+            for k, v in sd.items():
+                a = v.numpy().astype(np.float64)
+                out[f"init_checksum/{net}/{k}"] = np.array([a.sum(), (a * a).sum()])
+    else:
+        for k, v in policy.actor.state_dict().items():
+            out[f"init/actor/{k}"] = v.numpy().copy()
+        for k, v in policy.critic.state_dict().items():
+            out[f"init/critic/{k}"] = v.numpy().copy()
 
     T, N, M = cfg.episode_length, cfg.n_rollout_threads, cfg.num_agents
     E, sumA = N * M, sum(cfg.act_dims)
@@ -200,6 +233,8 @@ def run_case(name, spec):
         out[pre + "noise"], out[pre + "perms"] = noise, perms
         for nm in ("actions", "action_log_probs", "value_preds", "returns", "rnn_states", "rnn_states_critic",
                    "masks", "active_masks"):
+            if compact and nm.startswith("rnn_states") and not cfg.recurrent:
+                continue                                  # all zeros for MLP policies
             out[pre + "buf/" + nm] = getattr(buf, nm).copy()
         out[pre + "advantages"] = adv.astype(np.float32)
 
@@ -211,11 +246,11 @@ def run_case(name, spec):
                                              "critic_grad_norm", "ratio")], dtype=np.float64)
         if it == 0:
             for k, v in first_grads.items():
-                out[f"it0/first_update/{k}"] = v
+                put(out, f"it0/first_update/{k}", v, compact)
         for k, v in policy.actor.state_dict().items():
-            out[pre + f"actor/{k}"] = v.numpy().copy()
+            put(out, pre + f"actor/{k}", v.numpy(), compact)
         for k, v in policy.critic.state_dict().items():
-            out[pre + f"critic/{k}"] = v.numpy().copy()
+            put(out, pre + f"critic/{k}", v.numpy(), compact)
         out[pre + "valuenorm"] = np.array([vn.running_mean.item(), vn.running_mean_sq.item(),
                                            vn.debiasing_term.item()], dtype=np.float32)
     path = os.path.join(HERE, name + ".npz")

@@ -8,7 +8,9 @@ import torch
 from oracle import mappo_oracle as O
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GOLDEN_CASES = ["c1_mlp_discrete", "c3_gru_multidiscrete", "c4_gru_smac", "c5_mlp_switches", "naive_rnn_ptl"]
+GOLDEN_CASES = ["c1_mlp_discrete", "c3_gru_multidiscrete", "c4_gru_smac", "c5_mlp_switches", "naive_rnn_ptl",
+                "c5_h512_hanabi", "c2_mlp_n128"]
+# compact cases (make_golden.py `put`): initial weights = seed + checksums, big matrices = every 16th row + Frobenius norm
 INFO_KEYS = ("value_loss", "policy_loss", "dist_entropy", "actor_grad_norm", "critic_grad_norm", "ratio")
 
 
@@ -21,6 +23,26 @@ class Golden:
         self.cfg = O.PathConfig(**d)
         self.iters = 1 + max(int(k[2:k.index("/")]) for k in self.z.files if k.startswith("it"))
 
+    def init_params(self, which):
+        """Initial state_dict of 'actor' / 'critic': stored in full, or (compact cases) regenerated from the seed with the
+        engine's host-side initialiser, which draws exactly like the reference (test_host_logic.py pins that)."""
+        if not self.has("init_seed"):
+            return self.params(f"init/{which}/")
+        if getattr(self, "_init", None) is None:
+            from mappo_b200.core import reference_init_state_dict
+            from argsutil import make_args
+            cfg, seed = self.cfg, int(self.z["init_seed"])
+            args = make_args(cfg)
+            torch.set_num_threads(1)
+            torch.manual_seed(seed)
+            np.random.seed(seed)
+            actor = reference_init_state_dict(args, cfg.obs_dim, list(cfg.act_dims), False, cfg.multi_discrete)
+            critic = reference_init_state_dict(args, cfg.share_obs_dim, [1], True, False)
+            self._init = dict(actor=actor, critic=critic)
+            self.check_init("actor", actor)
+            self.check_init("critic", critic)
+        return self._init[which]
+
     def params(self, prefix):
         """{state_dict key: tensor} under e.g. 'init/actor/' or 'it0/critic/'."""
         return {k[len(prefix):]: torch.from_numpy(self.z[k].copy()) for k in self.z.files if k.startswith(prefix)}
@@ -32,6 +54,24 @@ class Golden:
 
     def get(self, key):
         return self.z[key]
+
+    def cmp(self, key, value, rtol, atol, what=""):
+        """assert_close against the stored tensor; compact matrices compare the stored rows and the Frobenius norm."""
+        value = np.asarray(value)
+        if key + "@rows" in self.z.files:
+            idx = self.z[key + "@rows"]
+            assert_close(value[idx], self.z[key], rtol, atol, what + " (every 16th row)")
+            norm = float(np.sqrt((value.astype(np.float64) ** 2).sum()))
+            assert_close(norm, float(self.z[key + "@norm"]), rtol, atol, what + " (Frobenius norm)")
+        else:
+            assert_close(value, self.z[key], rtol, atol, what)
+
+    def check_init(self, net_name, state_dict):
+        """compact cases: the nets were initialised from `init_seed`; compare with the reference's checksums."""
+        for k, v in state_dict.items():
+            a = v.detach().cpu().numpy().astype(np.float64)
+            want = self.z[f"init_checksum/{net_name}/{k}"]
+            assert_close(np.array([a.sum(), (a * a).sum()]), want, 1e-5, 1e-6, f"init {net_name} {k}")
 
     def has(self, key):
         return key in self.z.files

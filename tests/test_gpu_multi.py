@@ -37,8 +37,8 @@ def _worker(rank, world, port, out_path):
     obs_s, share_s, act_s = make_spaces(c)
     dev = torch.device("cuda", rank)
     policy = R_MAPPOPolicy(args, obs_s, share_s, act_s, device=dev)
-    policy.actor.load_state_dict(g.params("init/actor/"))
-    policy.critic.load_state_dict(g.params("init/critic/"))
+    policy.actor.load_state_dict(g.init_params("actor"))
+    policy.critic.load_state_dict(g.init_params("critic"))
     trainer = R_MAPPO(args, policy, device=dev)
     buf = SharedReplayBuffer(args, c.num_agents, obs_s, share_s, act_s)
     feed = g.feed(0)

@@ -29,8 +29,16 @@ def build(cfg, g=None):
     args = make_args(cfg)
     obs_s, share_s, act_s = make_spaces(cfg)
     dev = torch.device("cuda:0")
+    seeded = g is not None and g.has("init_seed")
+    if seeded:                     # compact fixtures: the initialiser is seed-identical to the reference's (test_host_logic.py)
+        torch.set_num_threads(1)
+        torch.manual_seed(int(g.get("init_seed")))
+        np.random.seed(int(g.get("init_seed")))
     policy = R_MAPPOPolicy(args, obs_s, share_s, act_s, device=dev)
-    if g is not None:
+    if seeded:
+        g.check_init("actor", policy.actor.state_dict())
+        g.check_init("critic", policy.critic.state_dict())
+    elif g is not None:
         policy.actor.load_state_dict(g.params("init/actor/"))
         policy.critic.load_state_dict(g.params("init/critic/"))
     trainer = R_MAPPO(args, policy, device=dev)
@@ -98,8 +106,9 @@ def test_rollout_and_returns_match_reference(name):
     np.testing.assert_array_equal(buf.actions.cpu().numpy(), g.get(pre + "actions"))        # integer: bit exact
     assert_close(buf.action_log_probs.cpu().numpy(), g.get(pre + "action_log_probs"), 1e-4, 1e-5, "logp")
     assert_close(buf.value_preds.cpu().numpy(), g.get(pre + "value_preds"), 1e-4, 1e-5, "value_preds")
-    assert_close(buf.rnn_states.cpu().numpy()[1:], g.get(pre + "rnn_states")[1:], 1e-4, 1e-5, "rnn_states")
-    assert_close(buf.rnn_states_critic.cpu().numpy()[1:], g.get(pre + "rnn_states_critic")[1:], 1e-4, 1e-5, "rnn_c")
+    if g.has(pre + "rnn_states"):
+        assert_close(buf.rnn_states.cpu().numpy()[1:], g.get(pre + "rnn_states")[1:], 1e-4, 1e-5, "rnn_states")
+        assert_close(buf.rnn_states_critic.cpu().numpy()[1:], g.get(pre + "rnn_states_critic")[1:], 1e-4, 1e-5, "rnn_c")
     assert_close(buf.returns.cpu().numpy()[:-1], g.get(pre + "returns")[:-1], 1e-4, 1e-4, "returns")
     # normalised advantages as R_MAPPO.train forms them
     st = buf._adv_stats.cpu().numpy()
@@ -148,9 +157,9 @@ def test_first_update_gradients_match_reference(name, monkeypatch):
     coef_c = min(1.0, cfg.max_grad_norm / (norms[1] + 1e-6)) if cfg.use_max_grad_norm else 1.0
     # the engine keeps UNCLIPPED gradients in its buffer (clipping is applied inside the Adam kernel)
     for k, v in grads_a.items():
-        assert_close(v * coef_a, g.get(f"it0/first_update/actor/{k}"), 2e-3, 2e-6, f"actor grad {k}")
+        g.cmp(f"it0/first_update/actor/{k}", v * coef_a, 2e-3, 2e-6, f"actor grad {k}")
     for k, v in grads_c.items():
-        assert_close(v * coef_c, g.get(f"it0/first_update/critic/{k}"), 2e-3, 2e-6, f"critic grad {k}")
+        g.cmp(f"it0/first_update/critic/{k}", v * coef_c, 2e-3, 2e-6, f"critic grad {k}")
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
@@ -171,9 +180,9 @@ def test_full_iterations_match_reference(name, monkeypatch):
         for k in INFO_KEYS:
             assert_close(info[k], want[k], 2e-3, 2e-5, f"{name} it{it} train_info[{k}]")
         for k, v in policy.actor.state_dict().items():
-            assert_close(v.cpu().numpy(), g.get(f"it{it}/actor/{k}"), 2e-3, 2e-5, f"actor {k}")
+            g.cmp(f"it{it}/actor/{k}", v.cpu().numpy(), 2e-3, 2e-5, f"actor {k}")
         for k, v in policy.critic.state_dict().items():
-            assert_close(v.cpu().numpy(), g.get(f"it{it}/critic/{k}"), 2e-3, 2e-5, f"critic {k}")
+            g.cmp(f"it{it}/critic/{k}", v.cpu().numpy(), 2e-3, 2e-5, f"critic {k}")
         assert_close(trainer.value_normalizer.state.cpu().numpy(), g.get(f"it{it}/valuenorm"), 1e-4, 1e-8, "valuenorm")
 
 
@@ -320,7 +329,7 @@ def test_evaluate_actions_matches_oracle(name):
         avail[np.arange(n), acts[:, 0].astype(int)] = 1.0
     values, logp, ent = policy.evaluate_actions(cent, obs, h, h, acts, masks, avail, active)
     t = torch.from_numpy
-    pa, pc = g.params("init/actor/"), g.params("init/critic/")
+    pa, pc = g.init_params("actor"), g.init_params("critic")
     lp_ref, ent_ref = O.actor_evaluate(cfg, pa, t(obs), t(h), t(acts), t(masks), None if avail is None else t(avail),
                                        t(active))
     v_ref, _ = O.critic_forward(cfg, pc, t(cent), t(h), t(masks))
@@ -400,6 +409,8 @@ def test_engine_rollout_matches_reference(name, persistent, monkeypatch):
     from mappo_b200.core import stream_ptr
     check(lib.mappo_pack_rollout_weights(C.byref(policy.actor.desc), ptr(policy.actor.flat), ptr(eng.img_actor), stream_ptr()))
     check(lib.mappo_pack_rollout_weights(C.byref(policy.critic.desc), ptr(policy.critic.flat), ptr(eng.img_critic), stream_ptr()))
+    if persistent and eng.big:
+        pytest.skip("hidden >= 128 nets run the per-step GEMM pipeline (no persistent rollout kernel)")
     if persistent:
         eng._rollout_persistent()
         eng._returns()
@@ -412,8 +423,9 @@ def test_engine_rollout_matches_reference(name, persistent, monkeypatch):
     np.testing.assert_array_equal(buf.actions.cpu().numpy(), g.get(pre + "actions"))
     assert_close(buf.action_log_probs.cpu().numpy(), g.get(pre + "action_log_probs"), 1e-4, 1e-5, "logp")
     assert_close(buf.value_preds.cpu().numpy(), g.get(pre + "value_preds"), 1e-4, 1e-5, "value_preds")
-    assert_close(buf.rnn_states.cpu().numpy()[1:], g.get(pre + "rnn_states")[1:], 1e-4, 1e-5, "rnn_states")
-    assert_close(buf.rnn_states_critic.cpu().numpy()[1:], g.get(pre + "rnn_states_critic")[1:], 1e-4, 1e-5, "rnn_c")
+    if g.has(pre + "rnn_states"):
+        assert_close(buf.rnn_states.cpu().numpy()[1:], g.get(pre + "rnn_states")[1:], 1e-4, 1e-5, "rnn_states")
+        assert_close(buf.rnn_states_critic.cpu().numpy()[1:], g.get(pre + "rnn_states_critic")[1:], 1e-4, 1e-5, "rnn_c")
     np.testing.assert_array_equal(buf.masks.cpu().numpy(), g.get(pre + "masks"))
     np.testing.assert_array_equal(buf.active_masks.cpu().numpy(), g.get(pre + "active_masks"))
     assert_close(buf.returns.cpu().numpy()[:-1], g.get(pre + "returns")[:-1], 1e-4, 1e-4, "returns")

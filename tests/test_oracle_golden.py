@@ -10,7 +10,7 @@ from helpers import Golden, GOLDEN_CASES, INFO_KEYS, assert_close
 def test_oracle_reproduces_reference_iterations(name):
     g = Golden(name)
     cfg = g.cfg
-    learner = O.Learner(cfg, g.params("init/actor/"), g.params("init/critic/"))
+    learner = O.Learner(cfg, g.init_params("actor"), g.init_params("critic"))
     store = O.RolloutStore(cfg)
     T, N, M = cfg.episode_length, cfg.n_rollout_threads, cfg.num_agents
     for it in range(g.iters):
@@ -29,14 +29,15 @@ def test_oracle_reproduces_reference_iterations(name):
         assert_close(store.value_preds, g.get(pre + "buf/value_preds"), 1e-5, 1e-6, "value_preds")
         assert_close(store.returns[:-1], g.get(pre + "buf/returns")[:-1], 1e-5, 1e-5, "returns")
         # rnn states / masks: compare pre-after_update slots 1..T (slot 0 was overwritten by after_update)
-        assert_close(store.rnn_states[1:], g.get(pre + "buf/rnn_states")[1:], 1e-5, 1e-6, "rnn_states")
+        if g.has(pre + "buf/rnn_states"):
+            assert_close(store.rnn_states[1:], g.get(pre + "buf/rnn_states")[1:], 1e-5, 1e-6, "rnn_states")
         want = dict(zip(INFO_KEYS, g.get(pre + "train_info")))
         for k in INFO_KEYS:
             assert_close(info[k], want[k], 2e-4, 1e-6, f"train_info[{k}] it{it}")
         for k, v in learner.actor.items():
-            assert_close(v.detach().numpy(), g.get(pre + f"actor/{k}"), 1e-4, 2e-6, f"actor {k}")
+            g.cmp(pre + f"actor/{k}", v.detach().numpy(), 1e-4, 2e-6, f"actor {k}")
         for k, v in learner.critic.items():
-            assert_close(v.detach().numpy(), g.get(pre + f"critic/{k}"), 1e-4, 2e-6, f"critic {k}")
+            g.cmp(pre + f"critic/{k}", v.detach().numpy(), 1e-4, 2e-6, f"critic {k}")
         if learner.vn is not None:
             assert_close(learner.vn.state(), g.get(pre + "valuenorm"), 1e-5, 1e-9, "valuenorm")
 
@@ -47,7 +48,7 @@ def test_oracle_first_update_gradients(name):
     cfg = g.cfg
     feed = g.feed(0)
     store2 = O.RolloutStore(cfg)
-    learner2 = O.Learner(cfg, g.params("init/actor/"), g.params("init/critic/"))
+    learner2 = O.Learner(cfg, g.init_params("actor"), g.init_params("critic"))
     store2.obs[0], store2.share_obs[0] = feed.obs[0], feed.share_obs[0]
     if feed.available_actions is not None:
         store2.available_actions[0] = feed.available_actions[0]
@@ -57,9 +58,9 @@ def test_oracle_first_update_gradients(name):
     sample = next(O.minibatches(store2, adv, g.get("it0/perms")[0]))
     out = learner2.ppo_update(sample, keep_grads=True)
     for k, v in out["actor_grads"].items():
-        assert_close(v.numpy(), g.get(f"it0/first_update/actor/{k}"), 1e-3, 1e-7, f"actor grad {k}")
+        g.cmp(f"it0/first_update/actor/{k}", v.numpy(), 1e-3, 1e-7, f"actor grad {k}")
     for k, v in out["critic_grads"].items():
-        assert_close(v.numpy(), g.get(f"it0/first_update/critic/{k}"), 1e-3, 1e-6, f"critic grad {k}")
+        g.cmp(f"it0/first_update/critic/{k}", v.numpy(), 1e-3, 1e-6, f"critic grad {k}")
     assert_close([out["actor_grad_norm"], out["critic_grad_norm"]], g.get("it0/first_update/norms"), 1e-4, 1e-7)
 
 
