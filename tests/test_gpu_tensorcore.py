@@ -2,10 +2,12 @@
 
 TF32 keeps 10 mantissa bits of the GEMM inputs (round-to-nearest when the operand tiles are written); accumulation,
 LayerNorm, activations, losses, the gradient reduction and Adam stay fp32.  Stated tolerances:
-  first-update gradients   |err| <= 2e-2 * |ref| + 2e-2 * max|ref of that tensor|   (tf32 rounding of a 64..9600-term dot)
-  losses / ratio / entropy  rtol 2e-3
-  weights after a full 10-epoch train()   rtol 2e-2, atol 2e-3 (~3 Adam steps of lr 7e-4: Adam normalises the
-                                            gradient, so tf32 noise on near-zero gradients moves a weight by O(lr))
+  first-update gradients   |err| <= 5e-3 * |ref| + 5e-3 * max|ref of that tensor|   (tf32 rounding of a 64..9600-term dot;
+                           measured worst case 1.5e-3 of the tensor's scale)
+  losses / ratio / entropy  rtol 2e-3 (policy_loss: + 2e-5 absolute, it is a difference of O(1) terms near zero)
+  weights after a full train()   rtol 2e-2, atol 2e-3 (~3 Adam steps of lr 7e-4: Adam normalises the
+                                   gradient, so tf32 noise on near-zero gradients moves a weight by O(lr))
+Cases: c1 (N = 8), c2 at the benchmark size (N = 128) and the c5 widths (hidden 512, layer_N 2: the TMA-fed GEMM pipeline).
 The exact-fp32 build (MAPPO_B200_GEMM=fp32, tests/test_gpu_parity.py) keeps the tight tolerances.
 """
 import numpy as np
@@ -27,7 +29,7 @@ def _grad_check(got, want, what):
     got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
     scale = np.abs(want).max() + 1e-12
     err = np.abs(got - want)
-    tol = 2e-2 * np.abs(want) + 2e-2 * scale
+    tol = 5e-3 * np.abs(want) + 5e-3 * scale
     assert np.all(err <= tol), f"{what}: max err {err.max():.3e} (scale {scale:.3e}, rel-to-scale {err.max()/scale:.3e})"
     return err.max() / scale
 
@@ -42,55 +44,77 @@ def test_tf32_path_is_active():
     assert ws_a.workspace.numel() > 1000          # folded tf32 weight image for the TMA bulk copy
 
 
-def test_tf32_first_update_gradients(monkeypatch):
-    g = Golden("c1_mlp_discrete")
+TF32_CASES = ["c1_mlp_discrete", "c2_mlp_n128", "c5_h512_hanabi"]
+
+
+def _collect_fp32(monkeypatch, cfg, policy, trainer, buf, feed, noise):
+    """Rollout with fp32 forward passes so that the stored trajectory IS the reference's (a hidden >= 128 net would otherwise
+    run its rollout GEMMs in tf32 as well and may flip a near-tie; tests/test_gpu_bignet.py covers that rollout), then
+    back to the tcgen05 build for the update under test."""
+    monkeypatch.setenv("MAPPO_B200_GEMM", "fp32")
+    TP.collect_and_returns(cfg, policy, trainer, buf, feed, noise)
+    monkeypatch.setenv("MAPPO_B200_GEMM", "tf32")
+
+
+def _golden_rows(g, key, value):
+    """(value restricted to the rows a compact fixture stores, stored tensor)."""
+    value = np.asarray(value)
+    if g.has(key + "@rows"):
+        return value[g.get(key + "@rows")], g.get(key)
+    return value, g.get(key)
+
+
+@pytest.mark.parametrize("name", TF32_CASES)
+def test_tf32_first_update_gradients(name, monkeypatch):
+    g = Golden(name)
     cfg = g.cfg
     from oracle import mappo_oracle as O
     one = O.PathConfig(**{**cfg.to_dict(), "ppo_epoch": 1, "act_dims": tuple(cfg.act_dims)})
     args, policy, trainer, buf = TP.build(one, g)
     feed = g.feed(0)
     TP.warm(buf, feed)
-    TP.collect_and_returns(cfg, policy, trainer, buf, feed, g.get("it0/noise"))
+    _collect_fp32(monkeypatch, cfg, policy, trainer, buf, feed, g.get("it0/noise"))
     monkeypatch.setattr(torch, "randperm", TP.FakeRandperm([g.get("it0/perms")[0]]))
     info = trainer.train(buf)
     norms = g.get("it0/first_update/norms")
     worst = 0.0
-    for net, name, nrm in ((policy.actor, "actor", norms[0]), (policy.critic, "critic", norms[1])):
+    for net, nm, nrm in ((policy.actor, "actor", norms[0]), (policy.critic, "critic", norms[1])):
         coef = min(1.0, cfg.max_grad_norm / (nrm + 1e-6))
         for k, v in net.named_grads().items():
-            worst = max(worst, _grad_check(v.cpu().numpy() * coef, g.get(f"it0/first_update/{name}/{k}"), f"{name} {k}"))
+            got, want = _golden_rows(g, f"it0/first_update/{nm}/{k}", v.cpu().numpy() * coef)
+            worst = max(worst, _grad_check(got, want, f"{nm} {k}"))
     losses = g.get("it0/first_update/losses")          # value_loss, policy_loss, dist_entropy, ratio
     assert_close(info["value_loss"], losses[0], 2e-3, 1e-6, "value_loss")
+    assert_close(info["policy_loss"], losses[1], 2e-3, 2e-5, "policy_loss")
     assert_close(info["dist_entropy"], losses[2], 2e-3, 1e-6, "dist_entropy")
     assert_close(info["ratio"], losses[3], 2e-3, 1e-6, "ratio")
-    assert_close([info["actor_grad_norm"], info["critic_grad_norm"]], norms, 1e-2, 1e-6, "grad norms")
-    print(f"\n[tf32] worst gradient error relative to tensor scale: {worst:.3e}")
+    assert_close([info["actor_grad_norm"], info["critic_grad_norm"]], norms, 5e-3, 1e-6, "grad norms")
+    print(f"\n[tf32] {name}: worst gradient error relative to tensor scale: {worst:.3e}")
 
 
-def test_tf32_full_iterations(monkeypatch):
-    g = Golden("c1_mlp_discrete")
+@pytest.mark.parametrize("name", TF32_CASES)
+def test_tf32_full_iterations(name, monkeypatch):
+    g = Golden(name)
     cfg = g.cfg
     args, policy, trainer, buf = TP.build(cfg, g)
-    for it in range(g.iters):
-        feed = g.feed(it)
-        if it == 0:
-            TP.warm(buf, feed)
-        TP.collect_and_returns(cfg, policy, trainer, buf, feed, g.get(f"it{it}/noise"))
-        monkeypatch.setattr(torch, "randperm", TP.FakeRandperm(g.get(f"it{it}/perms")))
-        info = trainer.train(buf)
-        buf.after_update()
-        want = dict(zip(INFO_KEYS, g.get(f"it{it}/train_info")))
-        for k in INFO_KEYS:
-            assert_close(info[k], want[k], 2e-2, 2e-4, f"it{it} train_info[{k}]")
-        worst = 0.0
-        for net, name in ((policy.actor, "actor"), (policy.critic, "critic")):
-            for k, v in net.state_dict().items():
-                ref = g.get(f"it{it}/{name}/{k}")
-                assert_close(v.cpu().numpy(), ref, 2e-2, 2e-3, f"{name} {k} after it{it}")
-                worst = max(worst, float(np.abs(v.cpu().numpy() - ref).max()))
-        print(f"\n[tf32] it{it}: worst absolute weight deviation from the reference {worst:.3e}")
-        if it == 0:
-            break          # iteration 2 samples actions from tf32-trained weights: integer actions may differ
+    feed = g.feed(0)
+    TP.warm(buf, feed)
+    _collect_fp32(monkeypatch, cfg, policy, trainer, buf, feed, g.get("it0/noise"))
+    np.testing.assert_array_equal(buf.actions.cpu().numpy(), g.get("it0/buf/actions"))
+    # (only the first iteration: iteration 2 samples actions from tf32-trained weights)
+    monkeypatch.setattr(torch, "randperm", TP.FakeRandperm(g.get("it0/perms")))
+    info = trainer.train(buf)
+    buf.after_update()
+    want = dict(zip(INFO_KEYS, g.get("it0/train_info")))
+    for k in INFO_KEYS:
+        assert_close(info[k], want[k], 2e-2, 2e-4, f"train_info[{k}]")
+    worst = 0.0
+    for net, nm in ((policy.actor, "actor"), (policy.critic, "critic")):
+        for k, v in net.state_dict().items():
+            got, ref = _golden_rows(g, f"it0/{nm}/{k}", v.cpu().numpy())
+            assert_close(got, ref, 2e-2, 2e-3, f"{nm} {k} after it0")
+            worst = max(worst, float(np.abs(got - ref).max()))
+    print(f"\n[tf32] {name}: worst absolute weight deviation from the reference after one train() {worst:.3e}")
 
 
 def test_tf32_ctas_with_several_tiles_match_the_fp32_build(monkeypatch):
