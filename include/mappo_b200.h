@@ -180,6 +180,11 @@ int32_t mappo_pack_rollout_weights(const mappo_net_desc_t* desc, const float* pa
  * Training uses the same entry points as every net: mappo_update_workspace_floats / mappo_update_fwd_bwd /
  * mappo_update_finish (one gradient slot: the pipeline leaves the complete flat gradient). */
 int32_t mappo_big_net(const mappo_net_desc_t* desc);
+/* Diagnostic: CUDA-event device time (ms) and launch count of each kernel family of the pipeline since the last call --
+ * [0] weight pack, [1] feature norm, [2] forward GEMMs, [3] head + loss, [4] input-gradient GEMMs, [5] weight-gradient
+ * GEMMs, [6] slot reduction + unfold -- accumulated over eager (non-captured) launches while `enable` was set; reading
+ * synchronises on the recorded events.  Host pointers (7 entries each, nullable). */
+int32_t mappo_debug_big_timing(int32_t enable, double* ms_out7, int64_t* launches_out7);
 int64_t mappo_rollout_workspace_floats(const mappo_net_desc_t* desc, int32_t n_rows);
 int32_t mappo_pack_rollout_weights_ex(const mappo_net_desc_t* desc, const float* params, float* image, int32_t gemm_mode,
                                       void* stream);

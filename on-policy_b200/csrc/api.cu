@@ -118,6 +118,7 @@ namespace big {
 int policy_launch(const NetDev& n, float* ws, const float* input, int n_rows, const EpiSample::Args& sample_in, bool tf32, int sm,
                   cudaStream_t st);
 bool supported(const NetDev& n);
+int debug_timing(int enable, double* ms_out, long long* n_out);
 int64_t workspace_floats(const NetDev& n, int rows, int sm);
 int pack_launch(const NetDev& n, const float* params, float* ws, int rows, bool round_tf32, int sm, cudaStream_t st);
 int update_launch(const NetDev& n, const float* params, const BatchDev& b, const LossDev& L, const double* norm_stats,
@@ -312,6 +313,10 @@ int32_t mappo_rollout_closed_loop(const mappo_net_desc_t* ad, const float* a_img
 int32_t mappo_rollout_image_floats(const mappo_net_desc_t* desc) {
   if (validate_desc(desc)) return -1;
   return rollout_image_floats(make_net_dev(desc));
+}
+
+int32_t mappo_debug_big_timing(int32_t enable, double* ms_out7, int64_t* launches_out7) {
+  return big::debug_timing(enable, ms_out7, reinterpret_cast<long long*>(launches_out7));
 }
 
 int32_t mappo_big_net(const mappo_net_desc_t* desc) {

@@ -16,6 +16,7 @@
 //   stats_l, mprime_l  float2 per row;   P ping-pong [rows][H];   Ph [rows][32]
 //   partial [splits][M][ldq], gsum [M][ldq];  fp32 mode: one accumulator scratch [rows][H]
 #include <cstring>
+#include <vector>
 #include "big_net.h"
 
 namespace mappo {
@@ -34,6 +35,41 @@ struct Plan {
 };
 
 static inline size_t align64(size_t x) { return (x + 63) & ~(size_t)63; }
+
+// diagnostic (bench.py's roofline leg, eager passes only -- events are not recorded while a stream is capturing):
+// CUDA-event timing of every launch family of the pipeline
+enum { T_PACK = 0, T_FEATNORM, T_FWD, T_HEAD, T_BWD, T_GRAD, T_FINISH, T_N };
+struct TimedLaunch { cudaEvent_t a, b; int cat; };
+static bool g_timing = false;
+static std::vector<TimedLaunch> g_timed;
+struct Timed {
+  cudaStream_t st; cudaEvent_t a; int cat; bool on;
+  Timed(int c, cudaStream_t s) : st(s), a(nullptr), cat(c), on(false) {
+    if (!g_timing) return;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
+    on = cudaEventCreate(&a) == cudaSuccess && cudaEventRecord(a, s) == cudaSuccess;
+  }
+  ~Timed() {
+    if (!on) return;
+    cudaEvent_t b;
+    if (cudaEventCreate(&b) == cudaSuccess && cudaEventRecord(b, st) == cudaSuccess) g_timed.push_back({a, b, cat});
+  }
+};
+int debug_timing(int enable, double* ms_out, long long* n_out) {
+  for (int i = 0; i < T_N; ++i) { if (ms_out) ms_out[i] = 0.0; if (n_out) n_out[i] = 0; }
+  for (const TimedLaunch& t : g_timed) {
+    cudaEventSynchronize(t.b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, t.a, t.b);
+    if (ms_out) ms_out[t.cat] += ms;
+    if (n_out) n_out[t.cat] += 1;
+    cudaEventDestroy(t.a); cudaEventDestroy(t.b);
+  }
+  g_timed.clear();
+  g_timing = enable != 0;
+  return MAPPO_OK;
+}
 
 bool supported(const NetDev& n) {
   return !n.recurrent && n.hid >= 128 && n.hid <= 1024 && n.hid % 128 == 0 && n.head_total <= 32 && n.in_dim <= 1023;
@@ -307,6 +343,7 @@ int pack_launch(const NetDev& n, const float* params, float* ws, int rows, bool 
   const Plan pl = make_plan(n, rows, sm);
   const PackArgs a = make_pack_args(n, pl, round_tf32);
   const int warps = pl.Lh * pl.H + 32;
+  Timed tm(T_PACK, st);
   big_pack_kernel<<<(warps * 32 + 255) / 256, 256, 0, st>>>(a, params, ws);
   return check_launch("big_pack_kernel");
 }
@@ -314,8 +351,12 @@ int pack_launch(const NetDev& n, const float* params, float* ws, int rows, bool 
 static int run_forward(const NetDev& n, const Plan& pl, float* ws, const float* input, const int32_t* rows, int n_rows, bool tf32,
                        int sm, cudaStream_t st) {
   const int act = n.use_relu ? ACT_RELU : ACT_TANH;
-  big_featnorm_kernel<<<(n_rows * 32 + 255) / 256, 256, 0, st>>>(input, rows, n_rows, n.in_dim, pl.K0p, n.use_fn, tf32 ? 1 : 0, ws + pl.x0);
-  int rc = check_launch("big_featnorm_kernel");
+  int rc;
+  {
+    Timed tm(T_FEATNORM, st);
+    big_featnorm_kernel<<<(n_rows * 32 + 255) / 256, 256, 0, st>>>(input, rows, n_rows, n.in_dim, pl.K0p, n.use_fn, tf32 ? 1 : 0, ws + pl.x0);
+    rc = check_launch("big_featnorm_kernel");
+  }
   if (rc) return rc;
   for (int i = 0; i < pl.Lh; ++i) {
     LinOperands o;
@@ -331,7 +372,10 @@ static int run_forward(const NetDev& n, const Plan& pl, float* ws, const float* 
     LinShape sh;
     memset(&sh, 0, sizeof(sh));
     sh.n_rows = n_rows; sh.K = i == 0 ? pl.K0p : pl.H; sh.N = pl.H; sh.BN = pl.H % 256 == 0 ? 256 : 128; sh.store_out = 1;
-    rc = tf32 ? lin_fwd_launch(o, ea, sh, st) : ref_lin_fwd_launch(o, ea, sh, ws + pl.scratch, st);
+    {
+      Timed tm(T_FWD, st);
+      rc = tf32 ? lin_fwd_launch(o, ea, sh, st) : ref_lin_fwd_launch(o, ea, sh, ws + pl.scratch, st);
+    }
     if (rc) return rc;
   }
   return MAPPO_OK;
@@ -342,8 +386,13 @@ static int run_grad(const Plan& pl, float* ws, const float* P, int ldp, int Pw, 
   if (Qw > 3 * 256 + 288) { set_error("big net: gradient GEMM operand %d columns wide", Qw); return MAPPO_ERR_UNSUPPORTED; }
   const GradShape g = make_grad_shape(rows, M, Pw, Qw, sm);
   if ((size_t)g.splits * M * g.ldq > pl.partial_floats) { set_error("big net: gradient partial buffer too small"); return MAPPO_ERR_INVALID; }
-  int rc = tf32 ? grad_gemm_launch(P, ldp, Q, ldq_in, ws + pl.partial, g, st) : ref_grad_gemm_launch(P, ldp, Q, ldq_in, ws + pl.partial, g, st);
+  int rc;
+  {
+    Timed tm(T_GRAD, st);
+    rc = tf32 ? grad_gemm_launch(P, ldp, Q, ldq_in, ws + pl.partial, g, st) : ref_grad_gemm_launch(P, ldp, Q, ldq_in, ws + pl.partial, g, st);
+  }
   if (rc) return rc;
+  Timed tm(T_FINISH, st);
   return grad_reduce_launch(ws + pl.partial, g.splits, M * g.ldq, ws + pl.gsum, nullptr, nullptr, st);
 }
 
@@ -373,7 +422,10 @@ int update_launch(const NetDev& n, const float* params, const BatchDev& b, const
     LinShape sh;
     memset(&sh, 0, sizeof(sh));
     sh.n_rows = rows; sh.K = pl.H; sh.N = 32; sh.BN = 32; sh.store_out = b.eval_only ? 0 : 1;
-    rc = tf32 ? lin_head_launch(o, ea, sh, st) : ref_lin_head_launch(o, ea, sh, ws + pl.scratch, st);
+    {
+      Timed tm(T_HEAD, st);
+      rc = tf32 ? lin_head_launch(o, ea, sh, st) : ref_lin_head_launch(o, ea, sh, ws + pl.scratch, st);
+    }
     if (rc) return rc;
   }
   if (b.eval_only) return MAPPO_OK;
@@ -382,9 +434,12 @@ int update_launch(const NetDev& n, const float* params, const BatchDev& b, const
   // head weight gradient: G_h[k][j] = sum_rows a_L_ext[row][k] Ph[row][j]
   rc = run_grad(pl, ws, ws + pl.act[Lh], pl.Hx, pl.Hx, pl.Hx, ws + pl.Ph, 32, 32, rows, tf32, sm, st);
   if (rc) return rc;
-  big_unfold_head_kernel<<<(pl.H + 31) / 32, 256, 0, st>>>(ws + pl.gsum, params, grad, pl.H, n.head_total, n.g.head_w, n.g.head_b,
-                                                          pa.gam_off[Lh], pa.bet_off[Lh]);
-  rc = check_launch("big_unfold_head_kernel");
+  {
+    Timed tm(T_FINISH, st);
+    big_unfold_head_kernel<<<(pl.H + 31) / 32, 256, 0, st>>>(ws + pl.gsum, params, grad, pl.H, n.head_total, n.g.head_w, n.g.head_b,
+                                                            pa.gam_off[Lh], pa.bet_off[Lh]);
+    rc = check_launch("big_unfold_head_kernel");
+  }
   if (rc) return rc;
   // walk down: l = Lh .. 1 produces P_l (gradient w.r.t. the pre-activation that made a_l) and the gradient of matrix l - 1
   const float* Pup = ws + pl.Ph;
@@ -406,7 +461,10 @@ int update_launch(const NetDev& n, const float* params, const BatchDev& b, const
     LinShape sh;
     memset(&sh, 0, sizeof(sh));
     sh.n_rows = rows; sh.K = K_up; sh.N = pl.H; sh.BN = pl.H % 256 == 0 ? 256 : 128; sh.store_out = 1;
-    rc = tf32 ? lin_bwd_launch(o, ea, sh, st) : ref_lin_bwd_launch(o, ea, sh, ws + pl.scratch, st);
+    {
+      Timed tm(T_BWD, st);
+      rc = tf32 ? lin_bwd_launch(o, ea, sh, st) : ref_lin_bwd_launch(o, ea, sh, ws + pl.scratch, st);
+    }
     if (rc) return rc;
     // weight gradient of matrix l - 1: G[o][k] = sum_rows P_l[row][o] Q[row][k],  Q = x0 (l == 1) or the extended a_{l-1}
     const int i = l - 1;
@@ -415,9 +473,12 @@ int update_launch(const NetDev& n, const float* params, const BatchDev& b, const
     rc = run_grad(pl, ws, Pl, pl.H, pl.H, pl.H, Q, ldq, ldq, rows, tf32, sm, st);
     if (rc) return rc;
     const int K = i == 0 ? n.in_dim : pl.H;
-    big_unfold_kernel<<<(K + 31) / 32, 256, 0, st>>>(ws + pl.gsum, ldq, params, grad, pl.H, K, i == 0 ? 1 : 0, pa.w_off[i], pa.b_off[i],
-                                                    pa.gam_off[i], pa.bet_off[i]);
-    rc = check_launch("big_unfold_kernel");
+    {
+      Timed tm(T_FINISH, st);
+      big_unfold_kernel<<<(K + 31) / 32, 256, 0, st>>>(ws + pl.gsum, ldq, params, grad, pl.H, K, i == 0 ? 1 : 0, pa.w_off[i], pa.b_off[i],
+                                                      pa.gam_off[i], pa.bet_off[i]);
+      rc = check_launch("big_unfold_kernel");
+    }
     if (rc) return rc;
     Pup = Pl; ld_up = pl.H; K_up = pl.H;
   }

@@ -450,6 +450,17 @@ __device__ __forceinline__ void vn_mean_var(const float* __restrict__ vn, float&
   var = fmaxf(msq - mean * mean, 1e-2f);
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-(function, DEVICE) setting: remember what was configured per device
+// ordinal, so that a process driving several GPUs configures each of them (one static instance per call site)
+struct SmemConfig {
+  size_t bytes[64];
+  size_t& slot() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return bytes[d & 63];
+  }
+};
+
 // error plumbing (api.cu)
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);

@@ -7,6 +7,7 @@
 //   3. reduce : out[i] = sum_{p = 0..world-1} peer_p[offset + i], read straight through NVLink (L1-bypassing loads);
 //               fixed order, so every rank ends up with bit-identical sums and the replicas never drift
 //   4. the last CTA publishes the completed round in device memory (read by the next launch; nothing on the host).
+// round_dev: uint32[4] = {completed round, CTA ticket, error flag (0 = ok, 1 + peer whose arrival timed out), unused}.
 // Reuse rule: a region may be rewritten as soon as a LATER round on any region has completed locally (each round is
 // a full barrier) -- the gradient all-reduce therefore alternates between two halves of the buffer.
 // The reference has no collective (single process); this is the multi-GPU exchange of SURVEY section 8e, C1.
@@ -61,8 +62,13 @@ p2p_allreduce_kernel(const P2PArgs a, long long offset_bytes, int n, T* __restri
     st_release_sys(a.sig[threadIdx.x] + a.rank, round);
   }
   if (threadIdx.x < a.world) {
+    // bounded wait (~4 s at 2 GHz): a dead peer, or two reducers whose kernels cannot be co-resident on some rank (a
+    // serialising tool), raise round_dev[2] instead of hanging the box; the caller reads it with mappo_p2p_error().
     const uint32_t* mine = a.sig[a.rank] + threadIdx.x;
-    while ((int)(ld_acquire_sys(mine) - round) < 0) { }
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(mine) - round) < 0) {
+      if (clock64() - t0 > 8000000000LL) { atomicExch(round_dev + 2, 1u + (uint32_t)threadIdx.x); break; }
+    }
   }
   __syncthreads();
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;

@@ -418,7 +418,8 @@ int policy_step_launch(const NetDev* na, const NetDev* nc, const PolArgs& a, cud
       else { const size_t b = fast_smem_bytes(*n); fb = b > fb ? b : fb; }
     }
     if (fast) {
-      static thread_local size_t configured_f = 0;
+      static thread_local SmemConfig configured_f_dev = {};
+  size_t& configured_f = configured_f_dev.slot();
       if (fb > configured_f) {
         if (cudaFuncSetAttribute(policy_step_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fb) != cudaSuccess)
           return check_launch("policy_step_fast: cudaFuncSetAttribute");
@@ -440,7 +441,8 @@ int policy_step_launch(const NetDev* na, const NetDev* nc, const PolArgs& a, cud
   }
   if (bytes > 227 * 1024) { set_error("policy_step: %zu B shared memory per CTA > 227 KB (in_dim too large)", bytes); return MAPPO_ERR_UNSUPPORTED; }
   auto kern = policy_step_kernel<4>;
-  static thread_local size_t configured = 0;
+  static thread_local SmemConfig configured_dev = {};
+  size_t& configured = configured_dev.slot();
   if (bytes > configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
       return check_launch("policy_step: cudaFuncSetAttribute");
@@ -454,7 +456,8 @@ int policy_step_launch(const NetDev* na, const NetDev* nc, const PolArgs& a, cud
 int rollout_persistent_launch(const NetDev& na, const NetDev& nc, const RolloutArgs& a, cudaStream_t st) {
   if (fast_rollout_supported(na) && fast_rollout_supported(nc) && a.image[0] && a.image[1]) {
     const size_t ba = fast_smem_bytes(na), bc = fast_smem_bytes(nc), fb = ba > bc ? ba : bc;
-    static thread_local size_t configured_f = 0;
+    static thread_local SmemConfig configured_f_dev = {};
+  size_t& configured_f = configured_f_dev.slot();
     if (fb > configured_f) {
       if (cudaFuncSetAttribute(rollout_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fb) != cudaSuccess)
         return check_launch("rollout_fast: cudaFuncSetAttribute");
@@ -475,7 +478,8 @@ int rollout_persistent_launch(const NetDev& na, const NetDev& nc, const RolloutA
   }
   if (bytes > 227 * 1024) { set_error("rollout: %zu B shared memory per CTA > 227 KB", bytes); return MAPPO_ERR_UNSUPPORTED; }
   auto kern = rollout_persistent_kernel<4>;
-  static thread_local size_t configured = 0;
+  static thread_local SmemConfig configured_dev = {};
+  size_t& configured = configured_dev.slot();
   if (bytes > configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
       return check_launch("rollout: cudaFuncSetAttribute");
@@ -494,8 +498,8 @@ int rollout_closed_launch(const NetDev& na, const NetDev& nc, const ClosedArgs& 
   const size_t bytes = closed_smem_bytes(na, nc, M);
   if (bytes > 227 * 1024) { set_error("rollout_closed: %zu B shared memory", bytes); return MAPPO_ERR_UNSUPPORTED; }
   auto kern = (M == 3 && L == 3) ? rollout_closed_kernel<3, 3> : rollout_closed_kernel<0, 0>;   // reference default shape
-  static thread_local size_t configured[2] = {0, 0};
-  size_t& conf = configured[(M == 3 && L == 3) ? 1 : 0];
+  static thread_local SmemConfig configured[2] = {};
+  size_t& conf = configured[(M == 3 && L == 3) ? 1 : 0].slot();
   if (bytes > conf) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
       return check_launch("rollout_closed: cudaFuncSetAttribute");

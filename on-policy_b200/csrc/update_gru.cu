@@ -331,7 +331,8 @@ int update_gru_launch(const NetDev& n, const float* params, const BatchDev& b, c
     const size_t bytes = fwd_smem_bytes(n);
     if (bytes > 227 * 1024) { set_error("gru_seq_fwd: %zu B shared memory > 227 KB", bytes); return MAPPO_ERR_UNSUPPORTED; }
     auto kern = gru_seq_fwd_kernel<4>;
-    static thread_local size_t configured = 0;
+    static thread_local SmemConfig configured_dev = {};
+  size_t& configured = configured_dev.slot();
     if (bytes > configured) {
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
         return check_launch("gru_seq_fwd: cudaFuncSetAttribute");
@@ -347,7 +348,8 @@ int update_gru_launch(const NetDev& n, const float* params, const BatchDev& b, c
     const size_t bytes = bwd_smem_bytes(n);
     if (bytes > 227 * 1024) { set_error("gru_seq_bwd: %zu B shared memory > 227 KB", bytes); return MAPPO_ERR_UNSUPPORTED; }
     auto kern = gru_seq_bwd_kernel<4>;
-    static thread_local size_t configured = 0;
+    static thread_local SmemConfig configured_dev = {};
+  size_t& configured = configured_dev.slot();
     if (bytes > configured) {
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
         return check_launch("gru_seq_bwd: cudaFuncSetAttribute");

@@ -173,7 +173,8 @@ static int launch_upd(const NetDev& n, const float* params, const BatchDev& b, c
     return MAPPO_ERR_UNSUPPORTED;
   }
   auto kern = update_mlp_kernel<kUpdTR, 4, NJIN>;
-  static thread_local size_t configured = 0;
+  static thread_local SmemConfig configured_dev = {};
+  size_t& configured = configured_dev.slot();
   if (bytes > configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
       return check_launch("update_mlp: cudaFuncSetAttribute");

@@ -819,7 +819,8 @@ int update_mlp_tc_launch(const NetDev& n, const float* params, const BatchDev& b
   pack_tc_kernel<<<(im.total + 255) / 256, 256, 0, st>>>(n, params, image);      // one element per thread
   const int rc = check_launch("pack_tc_kernel");
   if (rc) return rc;
-  static thread_local size_t configured = 0;
+  static thread_local SmemConfig configured_dev = {};
+  size_t& configured = configured_dev.slot();
   if (bytes > configured) {
     if (cudaFuncSetAttribute(update_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
       return check_launch("update_mlp_tc: cudaFuncSetAttribute");

@@ -72,9 +72,16 @@ class P2PReducer:
         self.bufs = (C.c_void_p * self.world)(*[int(p) for p in h_buf.buffer_ptrs])
         self.sigs = (C.c_void_p * self.world)(*[int(p) for p in h_sig.buffer_ptrs])
         self._keep = (h_buf, h_sig)
-        self.round = torch.zeros(2, dtype=torch.int32, device=device)
+        self.round = torch.zeros(4, dtype=torch.int32, device=device)      # {round, CTA ticket, error flag, -}
         dist.barrier()
         torch.cuda.synchronize()
+
+    def check_error(self):
+        """Host read of the kernel's error flag (a peer's arrival timed out): synchronises; raises if set."""
+        flag = int(self.round[2].item())
+        if flag:
+            raise RuntimeError(f"peer-memory all-reduce: rank {self.rank} timed out waiting for rank {flag - 1} "
+                               "(dead peer, or the two per-net reducers could not run concurrently on some rank)")
 
     def grad_half(self, parity: int) -> torch.Tensor:
         o = self.off_grad[parity & 1]

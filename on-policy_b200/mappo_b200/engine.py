@@ -160,10 +160,11 @@ class RolloutEngine:
             if self.d_avail is None:
                 self.d_avail = torch.zeros(T, E, self.A, dtype=torch.float32, device=self.dev)
         # warm-up slot 0 (mpe_runner.py:81-93)
-        self.buffer.obs[0].copy_(torch.from_numpy(feed.obs[0]))
-        self.buffer.share_obs[0].copy_(torch.from_numpy(feed.share_obs[0]))
+        b = self.buffer                                  # (separated buffers have no agent axis: reshape, same row order)
+        b.obs[0].copy_(torch.from_numpy(feed.obs[0]).reshape(b.obs[0].shape))
+        b.share_obs[0].copy_(torch.from_numpy(feed.share_obs[0]).reshape(b.share_obs[0].shape))
         if feed.available_actions is not None:
-            self.buffer.available_actions[0].copy_(torch.from_numpy(feed.available_actions[0]))
+            b.available_actions[0].copy_(torch.from_numpy(feed.available_actions[0]).reshape(b.available_actions[0].shape))
         if self.rng == "host":
             self.host["noise"] = torch.zeros(T, E, self.sumA).pin_memory()
             self.host["perm"] = torch.zeros(self.n_epochs, self.perm_len, dtype=torch.int32).pin_memory()

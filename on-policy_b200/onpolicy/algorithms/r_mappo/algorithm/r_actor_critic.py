@@ -18,6 +18,14 @@ class R_Actor(DeviceNet):
         self._keys = self._key_table()
         self.init_like_reference(args)
         self.algo = args.algorithm_name
+        self._use_policy_active_masks = bool(args.use_policy_active_masks)
+
+    def evaluate_actions(self, obs, rnn_states, action, masks, available_actions=None, active_masks=None):
+        """reference :73-117 -> (action_log_probs [rows, as], dist_entropy); gradient free (the separated runner's factor
+        bookkeeping, runner/separated/base_runner.py:145-179, is its only caller outside training)."""
+        from onpolicy.algorithms.r_mappo.r_mappo import _evaluate_actor
+        return _evaluate_actor(self, obs, rnn_states, action, masks, available_actions, active_masks,
+                               self._use_policy_active_masks)
 
 
 class R_Critic(DeviceNet):

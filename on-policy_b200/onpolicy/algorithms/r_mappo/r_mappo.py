@@ -210,18 +210,37 @@ class R_MAPPO():
         self._p2p_tried = True
         if os.environ.get("MAPPO_B200_P2P", "1") != "1":
             return
+        import torch.distributed as dist
+        ok, err = 1, None
         try:
             from mappo_b200.dist import P2PReducer
             self._p2p = P2PReducer(self.device, self._joint_grad.numel(), n_stats)
-            if os.environ.get("MAPPO_B200_P2P_JOINT", "0") != "1":
+            # per-net reducers keep the actor and the critic chain independent across ranks; their two spin-wait kernels must
+            # be able to run CONCURRENTLY on every rank, so a serialising environment uses the single joint collective
+            joint = os.environ.get("MAPPO_B200_P2P_JOINT", "0") == "1" or os.environ.get("CUDA_LAUNCH_BLOCKING", "0") == "1"
+            if not joint:
                 self._p2p_nets = (P2PReducer(self.device, self.policy.actor.n_params, 4),
                                   P2PReducer(self.device, self.policy.critic.n_params, 4))
                 self._par = [0, 0]
                 self._par_scratch = torch.zeros(4, dtype=torch.float32, device=self.device)
-        except Exception as e:                       # no symmetric memory on this system: stay on NCCL
+        except (RuntimeError, ImportError, AttributeError, NotImplementedError) as e:     # no symmetric memory here
+            ok, err = 0, e
+        # every rank must take the same path: agree on the outcome (a rank falling back to NCCL alone would leave its peers
+        # spinning in the peer-memory kernel)
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
             import sys
-            print(f"[mappo_b200] peer-memory all-reduce unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
-            self._p2p = None
+            if dist.get_rank() == 0:
+                print(f"[mappo_b200] peer-memory all-reduce unavailable on some rank ({type(err).__name__ if err else 'peer'}: {err}); "
+                      "using NCCL", file=sys.stderr)
+            self._p2p, self._p2p_nets = None, None
+
+    def check_collectives(self):
+        """Host check (synchronises): no peer-memory all-reduce of this trainer timed out."""
+        for r in [self._p2p] + list(self._p2p_nets or ()):
+            if r is not None:
+                r.check_error()
 
     def _host_permutation(self, n):
         """torch.randperm on the CPU generator, exactly where the reference's generators draw it
@@ -341,6 +360,9 @@ class R_MAPPO():
             loss_out[0:3] = part[0:3]
             loss_out[5] = part[5]
         self._keepalive = plans
+        # the advantages / statistics cached by compute_returns were formed with the ValueNorm state of BEFORE this train():
+        # a second train() on the same buffer must recompute them (reference r_mappo.py:179-187 recomputes every time)
+        buffer._adv_version = -1
         return loss_out, n_updates
 
     def train(self, buffer, update_actor=True):
@@ -388,7 +410,31 @@ class R_MAPPO():
         return o[0], o[4], o[1], o[2], o[3], o[5:6]
 
     def cal_value_loss(self, values, value_preds_batch, return_batch, active_masks_batch):
-        raise NotImplementedError("cal_value_loss is fused into mappo_update_fwd_bwd (critic net); use ppo_update")
+        """reference :52-89: clipped / Huber value loss of `values` against the (ValueNorm-normalised) returns, INCLUDING the
+        `value_normalizer.update(return_batch)` side effect (:65).  Device tensors in, a device scalar out.  The training
+        path does not come through here (the loss is fused into the critic's update kernel, net_tiles.cuh row_loss_pre);
+        this is the reference's public method kept for callers that evaluate the loss on their own tensors -- a handful
+        of elementwise torch ops on the device (no autograd graph: values produced by the engine carry none)."""
+        dev = self.device
+        values, v_old = as_dev(values, dev), as_dev(value_preds_batch, dev)
+        ret, active = as_dev(return_batch, dev), as_dev(active_masks_batch, dev)
+        v_clip = v_old + (values - v_old).clamp(-self.clip_param, self.clip_param)
+        if self._use_valuenorm:
+            self.value_normalizer.update(ret)
+            target = self.value_normalizer.normalize(ret)
+        else:
+            target = ret
+        e_c, e_o = target - v_clip, target - values
+        if self._use_huber_loss:
+            d = self.huber_delta
+            hub = lambda e: torch.where(e.abs() <= d, e * e / 2, d * (e.abs() - d / 2))
+            l_c, l_o = hub(e_c), hub(e_o)
+        else:
+            l_c, l_o = e_c * e_c / 2, e_o * e_o / 2
+        vl = torch.max(l_o, l_c) if self._use_clipped_value_loss else l_o
+        if self._use_value_active_masks:
+            return (vl * active).sum() / active.sum()
+        return vl.mean()
 
     def prep_training(self):
         self.policy.actor.train()
@@ -397,6 +443,37 @@ class R_MAPPO():
     def prep_rollout(self):
         self.policy.actor.eval()
         self.policy.critic.eval()
+
+
+def _evaluate_actor(actor, obs, h_a, action, masks, available_actions, active_masks, use_policy_active_masks=True):
+    """R_Actor.evaluate_actions (r_actor_critic.py:73-117): log-probs [rows, as] and the (masked) mean entropy; no gradients."""
+    lib = _lib.load()
+    dev = actor.device
+    obs, action, masks = as_dev(obs, dev), as_dev(action, dev), as_dev(masks, dev)
+    n_rows = obs.shape[0]
+    active = as_dev(active_masks, dev) if active_masks is not None else torch.ones(n_rows, 1, device=dev)
+    recurrent = bool(actor.desc.recurrent)
+    h_a = as_dev(h_a, dev)
+    n_seq = h_a.shape[0] if recurrent else n_rows
+    b = Batch()
+    b.obs, b.actions, b.masks, b.active_masks = ptr(obs), ptr(action), ptr(masks), ptr(active)
+    avail_d = as_dev(available_actions, dev) if available_actions is not None else None
+    b.avail = ptr(avail_d)
+    h_a2 = h_a.reshape(h_a.shape[0], -1).contiguous()
+    b.h0_actor = ptr(h_a2)
+    b.n_rows, b.n_seq, b.seq_len = n_rows, n_seq, n_rows // n_seq
+    stats = torch.tensor([float(active.sum().item()), 0.0, 0.0, float(n_rows)], dtype=torch.float64, device=dev)
+    out = torch.zeros(6, dtype=torch.float64, device=dev)
+    args_like = type("A", (), dict(clip_param=0.2, entropy_coef=0.0, value_loss_coef=1.0, huber_delta=10.0,
+                                   use_clipped_value_loss=True, use_huber_loss=True, use_value_active_masks=True,
+                                   use_policy_active_masks=(active_masks is not None and use_policy_active_masks),
+                                   use_valuenorm=False, use_popart=False))
+    loss = make_loss_cfg(args_like)
+    logp = torch.empty(n_rows, len(actor.head_dims), dtype=torch.float32, device=dev)
+    ws = UpdateWorkspace(actor, n_rows)
+    check(lib.mappo_evaluate_actions(C.byref(actor.desc), ptr(actor.flat), C.byref(b), C.byref(loss), ptr(stats), ptr(logp),
+                                     ptr(out), ptr(ws.workspace), stream_ptr()))
+    return logp, out[2].to(torch.float32)
 
 
 def _evaluate_only(policy, cent_obs, obs, h_a, h_c, action, masks, available_actions, active_masks):

@@ -1,8 +1,7 @@
 """onpolicy.runner.separated.base_runner.Runner on the B200 engine (reference: runner/separated/base_runner.py:15-215).
 
 One (policy, trainer, buffer) triple per agent; agents are trained sequentially in `torch.randperm(M)` order like the
-reference (:142).  For MAPPO the HAPPO `factor` is carried but unused (r_mappo.py:108-111), so the two extra
-full-buffer actor evaluations the reference performs per agent (:145-179) are skipped: they cannot change the result.
+reference (:142), with the HAPPO `factor` bookkeeping around each train() (`train_agents`).
 """
 import os
 
@@ -13,6 +12,33 @@ from onpolicy.algorithms.r_mappo.algorithm.rMAPPOPolicy import R_MAPPOPolicy as 
 from onpolicy.algorithms.r_mappo.r_mappo import R_MAPPO as TrainAlgo
 from onpolicy.runner.shared.base_runner import make_writer, _t2n
 from onpolicy.utils.separated_buffer import SeparatedReplayBuffer
+
+
+def train_agents(trainers, buffers, episode_length, n_rollout_threads):
+    """The body of Runner.train (reference :135-183, MAPPO branch), also used by the parity tests: agents are trained in
+    `torch.randperm(M)` order (:142); each gets the running HAPPO importance `factor` (update_factor, carried and unused by
+    MAPPO -- r_mappo.py:108-111), which is the product over the agents trained so far of exp(new - old log-prob) of the
+    whole buffer (two gradient-free actor evaluations around each train(), :145-179).  train_infos is APPENDED in training
+    order, exactly like the reference (so `log_train` labels entry i "agent i" whatever agent produced it)."""
+    train_infos = []
+    dev = buffers[0].device
+    factor = torch.ones(episode_length, n_rollout_threads, 1, dtype=torch.float32, device=dev)
+    for agent_id in torch.randperm(len(trainers)):                # same RNG draw as the reference (:142)
+        agent_id = int(agent_id)
+        tr, b = trainers[agent_id], buffers[agent_id]
+        tr.prep_training()
+        b.update_factor(factor)
+        avail = None if b.available_actions is None else b.available_actions[:-1].reshape(-1, b.available_actions.shape[-1])
+        ev = lambda: tr.policy.actor.evaluate_actions(
+            b.obs[:-1].reshape(-1, b.obs.shape[-1]), b.rnn_states[0:1].reshape(-1, *b.rnn_states.shape[2:]),
+            b.actions.reshape(-1, b.actions.shape[-1]), b.masks[:-1].reshape(-1, 1), avail,
+            b.active_masks[:-1].reshape(-1, 1))[0]
+        old_lp = ev()
+        train_infos.append(tr.train(b))
+        new_lp = ev()
+        factor = factor * torch.prod(torch.exp(new_lp - old_lp), dim=-1).reshape(episode_length, n_rollout_threads, 1)
+        b.after_update()
+    return train_infos
 
 
 class Runner(object):
@@ -85,13 +111,7 @@ class Runner(object):
 
     def train(self):
         """reference :135-183 (MAPPO branch)."""
-        train_infos = [None] * self.num_agents
-        for agent_id in torch.randperm(self.num_agents):          # same RNG draw as the reference (:142)
-            agent_id = int(agent_id)
-            self.trainer[agent_id].prep_training()
-            train_infos[agent_id] = self.trainer[agent_id].train(self.buffer[agent_id])
-            self.buffer[agent_id].after_update()
-        return train_infos
+        return train_agents(self.trainer, self.buffer, self.episode_length, self.n_rollout_threads)
 
     def save(self):
         """reference :185-193 (file names actor_agent{i}.pt / critic_agent{i}.pt / vnrom_agent{i}.pt)."""

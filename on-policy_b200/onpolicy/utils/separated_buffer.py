@@ -17,12 +17,9 @@ class SeparatedReplayBuffer(SharedReplayBuffer):
         self.factor = None
 
     def update_factor(self, factor):
-        """reference :62-63 (HAPPO importance factor; carried, unused by MAPPO -- r_mappo.py:108-111)."""
+        """reference :62-63 (HAPPO importance factor; carried, unused by MAPPO -- r_mappo.py:108-111).  Once set, every
+        generator yields it as the 13th tuple element (reference :197-227), gathered with the same rows."""
         self.factor = as_dev(factor, self.device).clone()
-
-    def _with_factor(self, gen, rows_of):
-        for sample, rows in gen:
-            yield sample if self.factor is None else sample + (self.factor.reshape(-1, 1)[rows.long()],)
 
     def recurrent_generator(self, advantages, num_mini_batch, data_chunk_length):
         # The reference stacks chunks on axis 0 here and then flattens them as if time-major

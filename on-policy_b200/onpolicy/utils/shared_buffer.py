@@ -192,6 +192,9 @@ class SharedReplayBuffer(object):
                 out.append(self._gather(a, first).view(first.numel(), self.recurrent_N, self.hidden_size))
             else:
                 out.append(self._gather(a, rows))
+        factor = getattr(self, "factor", None)            # separated buffers: 13th element once update_factor() was called
+        if factor is not None:                            # (reference utils/separated_buffer.py:197-227)
+            out.append(self._gather(factor.reshape(self.episode_length * self._E, -1), rows))
         return tuple(out)
 
     def feed_forward_generator(self, advantages, num_mini_batch=None, mini_batch_size=None):

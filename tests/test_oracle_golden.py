@@ -86,3 +86,66 @@ def _collect_only(cfg, learner, store, feed, noise):
                      available_actions=None if feed.available_actions is None else feed.available_actions[t + 1])
     nv = learner.get_values(cat(store.share_obs[-1]), cat(store.rnn_states_critic[-1]), cat(store.masks[-1]))
     O.compute_returns(store, nv.numpy().reshape(N, M, 1), learner.vn)
+
+
+# --------------------------------------------------------------------------------------------
+# separated policies: one learner + store per agent, trained in the reference's randperm order
+# --------------------------------------------------------------------------------------------
+def load_separated():
+    import ast
+    import os
+    import torch
+    from helpers import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "sep_mlp_2agents.npz"), allow_pickle=False)
+    M = int(z["n_agents"])
+    cfgs = []
+    for i in range(M):
+        d = ast.literal_eval(str(z[f"agent{i}/cfg_json"]))
+        d["act_dims"] = tuple(d["act_dims"])
+        cfgs.append(O.PathConfig(**d))
+    params = lambda pre: {k[len(pre):]: torch.from_numpy(z[k].copy()) for k in z.files if k.startswith(pre)}
+    feed = lambda i: O.SyntheticFeed(*[z[f"agent{i}/feed/{n}"].copy() for n in
+                                       ("obs", "share_obs", "rewards", "dones", "active_masks", "available_actions")])
+    return z, M, cfgs, params, feed
+
+
+def test_oracle_separated_matches_reference():
+    import torch
+    z, M, cfgs, params, feed = load_separated()
+    learners = [O.Learner(cfgs[i], params(f"agent{i}/init/actor/"), params(f"agent{i}/init/critic/")) for i in range(M)]
+    stores = [O.RolloutStore(c) for c in cfgs]
+    feeds = [feed(i) for i in range(M)]
+    for i in range(M):
+        stores[i].obs[0], stores[i].share_obs[0] = feeds[i].obs[0], feeds[i].share_obs[0]
+        stores[i].available_actions[0] = feeds[i].available_actions[0]
+        _collect_only(cfgs[i], learners[i], stores[i], feeds[i], z[f"agent{i}/noise"])
+        sq = lambda a: a.reshape(a.shape[0], a.shape[1], *a.shape[3:])
+        np.testing.assert_array_equal(sq(stores[i].actions), z[f"agent{i}/buf/actions"])
+        assert_close(sq(stores[i].action_log_probs), z[f"agent{i}/buf/action_log_probs"], 1e-5, 1e-6, "logp")
+        assert_close(sq(stores[i].value_preds), z[f"agent{i}/buf/value_preds"], 1e-5, 1e-6, "values")
+        assert_close(sq(stores[i].returns)[:-1], z[f"agent{i}/buf/returns"][:-1], 1e-5, 1e-5, "returns")
+    T, N = cfgs[0].episode_length, cfgs[0].n_rollout_threads
+    factor = np.ones((T, N, 1), np.float32)
+    t = torch.from_numpy
+    for pos, i in enumerate(z["agent_order"]):
+        i = int(i)
+        assert_close(factor, z[f"agent{i}/factor_in"], 1e-4, 1e-6, f"factor handed to agent {i}")
+        s, c = stores[i], cfgs[i]
+        flat = lambda a: t(a[:T].reshape(T * N, -1))
+        ev = lambda: O.actor_evaluate(c, learners[i].actor, flat(s.obs), flat(s.rnn_states).reshape(T * N, 1, -1), flat(s.actions),
+                                      flat(s.masks), flat(s.available_actions), flat(s.active_masks))[0].detach()
+        old = ev()
+        info = learners[i].train(s, list(z[f"agent{i}/perms"]))
+        new = ev()
+        factor = factor * torch.prod(torch.exp(new - old), dim=-1).reshape(T, N, 1).numpy()
+        s.after_update()
+        want = dict(zip(INFO_KEYS, z[f"train_info_pos{pos}"]))
+        for k in INFO_KEYS:
+            assert_close(info[k], want[k], 2e-4, 1e-6, f"train_info[{k}] of the agent trained at position {pos}")
+    assert_close(factor, z["factor_final"], 1e-4, 1e-6, "final factor")
+    for i in range(M):
+        for k, v in learners[i].actor.items():
+            assert_close(v.detach().numpy(), z[f"agent{i}/final/actor/{k}"], 1e-4, 2e-6, f"agent {i} actor {k}")
+        for k, v in learners[i].critic.items():
+            assert_close(v.detach().numpy(), z[f"agent{i}/final/critic/{k}"], 1e-4, 2e-6, f"agent {i} critic {k}")
+        assert_close(learners[i].vn.state(), z[f"agent{i}/valuenorm"], 1e-5, 1e-9, "valuenorm")
