@@ -106,6 +106,7 @@ int randperm_launch(int, uint64_t, const uint64_t*, int32_t*, cudaStream_t, int 
 int minibatch_stats_batch_launch(const float*, const float*, const int32_t*, long long, int, int, double*, cudaStream_t);
 int grad_reduce_launch(const float*, int, int, float*, float*, int*, cudaStream_t);
 int sumsq_launch(const float*, int, float*, int*, cudaStream_t);
+int copy_sumsq_launch(const float*, float*, int, float*, int*, cudaStream_t);
 int clip_adam_launch(float*, const float*, float*, float*, int, const float*, int, const float*, int*, float, float,
                      int, double*, double*, cudaStream_t);
 int counter_add_launch(uint64_t*, uint64_t, cudaStream_t);
@@ -525,6 +526,8 @@ int32_t mappo_update_finish(const mappo_net_desc_t* desc, const float* params, c
     if (n_blocks_out) *n_blocks_out = 12;
     return update_mlp_tc_unfold_launch(n, params, raw_sum, grad, sumsq_part, (cudaStream_t)stream);
   }
+  if (n_slots == 1 && n.g.total >= 65536 && ((reinterpret_cast<uintptr_t>(grad_part) | reinterpret_cast<uintptr_t>(grad)) & 15) == 0)
+    return copy_sumsq_launch(grad_part, grad, n.g.total, sumsq_part, n_blocks_out, (cudaStream_t)stream);
   return grad_reduce_launch(grad_part, n_slots, n.g.total, grad, sumsq_part, n_blocks_out, (cudaStream_t)stream);
 }
 

@@ -362,6 +362,9 @@ int sumsq_launch(const float* grad, int P, float* sumsq_part, int* n_blocks_out,
   return check_launch("sumsq_kernel");
 }
 
+// VEC = 1: one element per thread (the small nets: 6 - 33 K parameters, latency bound).  VEC = 4: four consecutive elements
+// per thread as 128-bit loads / stores (the hidden >= 128 nets: ~0.9 M parameters, 28 B/param of HBM traffic).
+template <int VEC>
 __global__ void __launch_bounds__(256)
 clip_adam_kernel(float* __restrict__ p, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
                  int P, const float* __restrict__ sumsq_part, int n_part, const float* __restrict__ lr_dev,
@@ -371,9 +374,23 @@ clip_adam_kernel(float* __restrict__ p, const float* __restrict__ grad, float* _
   __shared__ int s_step;
   __shared__ double s_p1, s_p2;
   // this thread's operands first: their latency overlaps the scalar prologue below instead of following it
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  float g_in = 0.f, m_in = 0.f, v_in = 0.f, p_in = 0.f;
-  if (i < P) { g_in = grad[i]; m_in = m[i]; v_in = v[i]; p_in = p[i]; }
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  float g_in[VEC], m_in[VEC], v_in[VEC], p_in[VEC];
+  const bool full = i + VEC <= P;
+  if (VEC == 4 && full) {
+    const float4 a = *reinterpret_cast<const float4*>(grad + i), b = *reinterpret_cast<const float4*>(m + i);
+    const float4 c = *reinterpret_cast<const float4*>(v + i), d = *reinterpret_cast<const float4*>(p + i);
+    g_in[0] = a.x; g_in[VEC > 1 ? 1 : 0] = a.y; g_in[VEC > 2 ? 2 : 0] = a.z; g_in[VEC > 3 ? 3 : 0] = a.w;
+    m_in[0] = b.x; m_in[VEC > 1 ? 1 : 0] = b.y; m_in[VEC > 2 ? 2 : 0] = b.z; m_in[VEC > 3 ? 3 : 0] = b.w;
+    v_in[0] = c.x; v_in[VEC > 1 ? 1 : 0] = c.y; v_in[VEC > 2 ? 2 : 0] = c.z; v_in[VEC > 3 ? 3 : 0] = c.w;
+    p_in[0] = d.x; p_in[VEC > 1 ? 1 : 0] = d.y; p_in[VEC > 2 ? 2 : 0] = d.z; p_in[VEC > 3 ? 3 : 0] = d.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const bool ok = i + k < P;
+      g_in[k] = ok ? grad[i + k] : 0.f; m_in[k] = ok ? m[i + k] : 0.f; v_in[k] = ok ? v[i + k] : 0.f; p_in[k] = ok ? p[i + k] : 0.f;
+    }
+  }
   // every block re-derives the global norm from the per-block partials (n_part is small) in a fixed order; the
   // scalar prologue (norm, clip coefficient, Adam bias corrections in fp64) runs in ONE warp and is broadcast
   if (threadIdx.x < 32) {
@@ -401,14 +418,23 @@ clip_adam_kernel(float* __restrict__ p, const float* __restrict__ grad, float* _
   __syncthreads();
   const float total = s_total, coef = s_coef, step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
   const int step = s_step;
-  if (i < P) {
-    const float g = g_in * coef;
-    const float mi = m_in + (g - m_in) * (float)(1.0 - 0.9);                  // torch: exp_avg.lerp_(grad, 1 - beta1)
-    const float vi = v_in * 0.999f + (float)(1.0 - 0.999) * g * g;            // exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = p_in - step_size * (mi / denom);
-    m[i] = mi;
-    v[i] = vi;
+  float po[VEC], mo[VEC], vo[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    const float g = g_in[k] * coef;
+    mo[k] = m_in[k] + (g - m_in[k]) * (float)(1.0 - 0.9);                     // torch: exp_avg.lerp_(grad, 1 - beta1)
+    vo[k] = v_in[k] * 0.999f + (float)(1.0 - 0.999) * g * g;                  // exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
+    const float denom = sqrtf(vo[k]) / bc2_sqrt + eps;
+    po[k] = p_in[k] - step_size * (mo[k] / denom);
+  }
+  if (VEC == 4 && full) {
+    *reinterpret_cast<float4*>(p + i) = make_float4(po[0], po[VEC > 1 ? 1 : 0], po[VEC > 2 ? 2 : 0], po[VEC > 3 ? 3 : 0]);
+    *reinterpret_cast<float4*>(m + i) = make_float4(mo[0], mo[VEC > 1 ? 1 : 0], mo[VEC > 2 ? 2 : 0], mo[VEC > 3 ? 3 : 0]);
+    *reinterpret_cast<float4*>(v + i) = make_float4(vo[0], vo[VEC > 1 ? 1 : 0], vo[VEC > 2 ? 2 : 0], vo[VEC > 3 ? 3 : 0]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k)
+      if (i + k < P) { p[i + k] = po[k]; m[i + k] = mo[k]; v[i + k] = vo[k]; }
   }
   // the last block to finish publishes the new step count (step_dev[1] is its ticket counter): every block has
   // read the old value by then, and no extra launch is needed
@@ -428,9 +454,48 @@ clip_adam_kernel(float* __restrict__ p, const float* __restrict__ grad, float* _
 int clip_adam_launch(float* p, const float* grad, float* m, float* v, int P, const float* sumsq_part, int n_part,
                      const float* lr_dev, int* step_dev, float eps, float max_norm, int use_clip, double* norm_out,
                      double* beta_pow, cudaStream_t st) {
-  clip_adam_kernel<<<(P + 255) / 256, 256, 0, st>>>(p, grad, m, v, P, sumsq_part, n_part, lr_dev, step_dev, eps,
-                                                    max_norm, use_clip, norm_out, beta_pow);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(m) |
+                         reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  if (P >= 65536 && aligned)
+    clip_adam_kernel<4><<<(P + 1023) / 1024, 256, 0, st>>>(p, grad, m, v, P, sumsq_part, n_part, lr_dev, step_dev, eps,
+                                                           max_norm, use_clip, norm_out, beta_pow);
+  else
+    clip_adam_kernel<1><<<(P + 255) / 256, 256, 0, st>>>(p, grad, m, v, P, sumsq_part, n_part, lr_dev, step_dev, eps,
+                                                         max_norm, use_clip, norm_out, beta_pow);
   return check_launch("clip_adam_kernel");
+}
+
+// dst = src with one partial sum of squares per 1024-element block (128-bit accesses): the single-slot case of the
+// gradient reduction for the hidden >= 128 nets (their GEMM pipeline leaves one complete flat gradient)
+__global__ void __launch_bounds__(256)
+copy_sumsq4_kernel(const float* __restrict__ src, float* __restrict__ dst, int P, float* __restrict__ sumsq_part) {
+  __shared__ float sred[8];
+  const int i = (blockIdx.x * 256 + threadIdx.x) * 4;
+  float q = 0.f;
+  if (i + 4 <= P) {
+    const float4 a = *reinterpret_cast<const float4*>(src + i);
+    *reinterpret_cast<float4*>(dst + i) = a;
+    q = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, a.w * a.w)));
+  } else {
+    for (int k = i; k < P; ++k) { const float a = src[k]; dst[k] = a; q = fmaf(a, a, q); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = q;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sred[k];
+    if (sumsq_part) sumsq_part[blockIdx.x] = t;
+  }
+}
+
+int copy_sumsq_launch(const float* src, float* dst, int P, float* sumsq_part, int* n_blocks_out, cudaStream_t st) {
+  const int blocks = (P + 1023) / 1024;
+  if (n_blocks_out) *n_blocks_out = blocks;
+  copy_sumsq4_kernel<<<blocks, 256, 0, st>>>(src, dst, P, sumsq_part);
+  return check_launch("copy_sumsq4_kernel");
 }
 
 }  // namespace mappo

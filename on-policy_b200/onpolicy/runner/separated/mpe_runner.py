@@ -92,4 +92,41 @@ class MPERunner(Runner):
 
     @torch.no_grad()
     def eval(self, total_num_steps):
-        raise NotImplementedError("separated eval: SURVEY section 8f row f2")
+        """reference :178-239: deterministic rollouts on eval_envs with every agent's own policy; logs each agent's
+        eval_average_episode_rewards (per-agent reward column summed over the episode, averaged over the eval threads)."""
+        n, M = self.n_eval_rollout_threads, self.num_agents
+        dev = self.buffer[0].device
+        eval_obs = self.eval_envs.reset()
+        h = [torch.zeros(n, self.recurrent_N, self.hidden_size, device=dev) for _ in range(M)]
+        masks = torch.ones(n, M, 1, device=dev)
+        rewards_log = []
+        for _ in range(self.episode_length):
+            parts = []
+            for agent_id in range(M):
+                self.trainer[agent_id].prep_rollout()
+                mine = np.stack([np.asarray(o[agent_id], dtype=np.float32) for o in eval_obs])
+                a, h[agent_id] = self.trainer[agent_id].policy.act(mine, h[agent_id], masks[:, agent_id], deterministic=True)
+                a_np = _t2n(a)
+                space = self.eval_envs.action_space[agent_id]
+                if space.__class__.__name__ == "MultiDiscrete":
+                    parts.append(np.concatenate([np.eye(space.high[i] + 1)[a_np[:, i]] for i in range(space.shape)], 1))
+                elif space.__class__.__name__ == "Discrete":
+                    parts.append(np.squeeze(np.eye(space.n)[a_np], 1))
+                else:
+                    raise NotImplementedError
+            actions_env = [[parts[m][i] for m in range(M)] for i in range(n)]
+            eval_obs, eval_rewards, eval_dones, _ = self.eval_envs.step(actions_env)
+            rewards_log.append(eval_rewards)
+            done = torch.from_numpy(np.asarray(eval_dones, dtype=bool)).to(dev)
+            masks = torch.ones(n, M, 1, device=dev)
+            masks[done] = 0.0
+            for agent_id in range(M):
+                h[agent_id] = h[agent_id].clone()
+                h[agent_id][done[:, agent_id]] = 0.0
+        rew = np.array(rewards_log)                                   # [T, n, M, 1]
+        infos = []
+        for agent_id in range(M):
+            avg = float(np.mean(np.sum(rew[:, :, agent_id], axis=0)))
+            infos.append({"eval_average_episode_rewards": avg})
+            print("eval average episode rewards of agent%i: " % agent_id + str(avg))
+        self.log_train(infos, total_num_steps)

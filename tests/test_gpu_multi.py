@@ -1,5 +1,7 @@
-"""2-GPU data parallelism over rollout threads reproduces the reference's single-process iteration (golden c1):
-each rank owns half of the threads, normalisers are global, gradients are all-reduced."""
+"""Data parallelism over rollout threads on 2 / 4 / 8 GPUs reproduces the reference's single-process iteration (golden c1):
+each rank owns a slice of the threads, normalisers are global, gradients are all-reduced.  Two passes per
+rank: the eager drop-in classes, and the engine's CUDA graph (one graph per iteration with the per-net peer-memory
+all-reduce kernels inside -- the path bench.py times); every rank's weights must be bit-identical."""
 import os
 import sys
 
@@ -53,24 +55,70 @@ def _worker(rank, world, port, out_path):
         TP.collect_and_returns(c, policy, trainer, buf, sh, noise)
         info = trainer.train(buf)
     torch.cuda.synchronize()
+    trainer.check_collectives()
+
+    # ---- the same iteration as ONE replayed CUDA graph (engine, host RNG mode: the same noise, any permutation) ----
+    from mappo_b200.engine import RolloutEngine
+    policy2 = R_MAPPOPolicy(args, obs_s, share_s, act_s, device=dev)
+    policy2.actor.load_state_dict(g.init_params("actor"))
+    policy2.critic.load_state_dict(g.init_params("critic"))
+    trainer2 = R_MAPPO(args, policy2, device=dev)
+    buf2 = SharedReplayBuffer(args, c.num_agents, obs_s, share_s, act_s)
+    with torch.cuda.device(rank):
+        eng = RolloutEngine(args, policy2, trainer2, buf2, rng="host", seed=1)
+        eng.stage_feed(sh)
+        eng.draw_host_rng = lambda: None
+        eng.host["noise"].copy_(torch.from_numpy(noise))
+        for e in range(eng.n_epochs):
+            eng.host["perm"][e] = torch.randperm(eng.perm_len).to(torch.int32)
+        eng.upload()
+        torch.cuda.synchronize()
+        snap = [policy2.actor.flat.clone(), policy2.critic.flat.clone(), trainer2.value_normalizer.state.clone()]
+        eng.capture(warmup=1)
+        graph_kind = type(eng.graph).__name__
+        policy2.actor.flat.copy_(snap[0]); policy2.critic.flat.copy_(snap[1]); trainer2.value_normalizer.state.copy_(snap[2])
+        for opt in (policy2.actor_optimizer, policy2.critic_optimizer):
+            opt.exp_avg.zero_(); opt.exp_avg_sq.zero_(); opt.step_dev.zero_()
+        for a in (buf2.rnn_states, buf2.rnn_states_critic):
+            a.zero_()
+        buf2.masks.fill_(1.0); buf2.active_masks.fill_(1.0)
+        TP.warm(buf2, sh)
+        info2 = eng.step_e2e()
+    torch.cuda.synchronize()
+    trainer2.check_collectives()
+    # replicas: bit-identical parameters on every rank, in both passes
+    for t in (policy.actor.flat, policy.critic.flat, policy2.actor.flat, policy2.critic.flat):
+        lo_t, hi_t = t.clone(), t.clone()
+        dist.all_reduce(lo_t, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi_t, op=dist.ReduceOp.MAX)
+        assert torch.equal(lo_t, hi_t), "replica parameters differ across ranks"
     if rank == 0:
         np.savez(out_path, actor=policy.actor.flat.cpu().numpy(), critic=policy.critic.flat.cpu().numpy(),
-                 info=np.array([info[k] for k in TP.INFO_KEYS]), vn=trainer.value_normalizer.state.cpu().numpy())
+                 info=np.array([info[k] for k in TP.INFO_KEYS]), vn=trainer.value_normalizer.state.cpu().numpy(),
+                 actor2=policy2.actor.flat.cpu().numpy(), critic2=policy2.critic.flat.cpu().numpy(),
+                 info2=np.array([info2[k] for k in TP.INFO_KEYS]), graph_kind=np.array(graph_kind),
+                 p2p=np.array(int(trainer2._p2p is not None)))
+    dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_rank_sharded_iteration_matches_reference(tmp_path):
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_iteration_matches_reference(world, tmp_path):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     from helpers import Golden, INFO_KEYS, assert_close
     out = str(tmp_path / "r0.npz")
-    mp.spawn(_worker, args=(2, 29600 + os.getpid() % 1000, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, 29600 + os.getpid() % 1000 + world, out), nprocs=world, join=True)
     z = np.load(out)
     g = Golden("c1_mlp_discrete")
     want = np.concatenate([v.numpy().reshape(-1) for v in g.params("it0/actor/").values()])
     # flat layout == state_dict order for this net (feature norm, fc1, ln1, fc2, ln2, head)
-    assert_close(z["actor"], want, 2e-3, 2e-5, "actor weights after 2-rank train")
     wantc = np.concatenate([v.numpy().reshape(-1) for v in g.params("it0/critic/").values()])
-    assert_close(z["critic"], wantc, 2e-3, 2e-5, "critic weights after 2-rank train")
-    assert_close(z["info"], g.get("it0/train_info"), 2e-3, 2e-5, "train_info")
+    for tag, a, c_, info in (("eager", "actor", "critic", "info"), ("graph", "actor2", "critic2", "info2")):
+        assert_close(z[a], want, 2e-3, 2e-5, f"{tag}: actor weights after a {world}-rank train")
+        assert_close(z[c_], wantc, 2e-3, 2e-5, f"{tag}: critic weights after a {world}-rank train")
+        assert_close(z[info], g.get("it0/train_info"), 2e-3, 2e-5, f"{tag}: train_info")
     assert_close(z["vn"], g.get("it0/valuenorm"), 1e-4, 1e-8, "valuenorm")
+    assert_close(z["actor2"], z["actor"], 1e-5, 1e-7, "graph replay vs eager")
+    print(f"\n[multi] world {world}: iteration graph = {z['graph_kind']}, peer-memory all-reduce = {bool(z['p2p'])}")

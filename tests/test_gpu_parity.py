@@ -288,9 +288,10 @@ def test_device_randperm_is_a_permutation():
     assert abs(np.corrcoef(a.cpu().numpy(), np.arange(9600))[0, 1]) < 0.05
 
 
-def test_clip_adam_matches_torch_adam():
+@pytest.mark.parametrize("hidden,share", [(64, 54), (512, 785)])      # 8 K parameters (scalar kernel) / 0.93 M, P % 4 == 3 (128-bit kernel + tail)
+def test_clip_adam_matches_torch_adam(hidden, share):
     from mappo_b200.core import FusedAdam
-    cfg = O.PathConfig()
+    cfg = O.PathConfig(hidden_size=hidden, share_obs_dim=share, layer_N=2 if hidden > 64 else 1)
     args, policy, trainer, buf = build(cfg)
     net = policy.critic
     ref = net.flat.detach().cpu().clone().requires_grad_(True)
