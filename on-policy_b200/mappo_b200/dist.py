@@ -19,6 +19,20 @@ def shard_of_threads(n_rollout_threads_global: int, world_size: int, rank: int):
     return rank * per, (rank + 1) * per
 
 
+def local_rows_of_global(rows_global: torch.Tensor, n_threads_global: int, num_agents: int, lo: int, hi: int) -> torch.Tensor:
+    """The rows of a GLOBAL minibatch (indices into the flattened [T, N_global, M] storage, row = (t N + n) M + m, as drawn by
+    the reference's `torch.randperm(B_global)`, shared_buffer.py:360) that live on the rank owning rollout threads [lo, hi),
+    renumbered for that rank's local [T, hi - lo, M] storage.  Order preserved (minibatch partitioning)."""
+    r = rows_global.to(torch.int64)
+    m = r % num_agents
+    tn = r // num_agents
+    n = tn % n_threads_global
+    t = tn // n_threads_global
+    keep = (n >= lo) & (n < hi)
+    local = (t * (hi - lo) + (n - lo)) * num_agents + m
+    return local[keep].to(torch.int32)
+
+
 def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
     ws, _ = world()
     if ws > 1:

@@ -268,6 +268,10 @@ class R_MAPPO():
             if allreduce is not None:
                 self._ensure_p2p(n_stats=self.ppo_epoch * self.num_mini_batch * 4 + 4)
         p2p = self._p2p if allreduce is not None else None
+        # (with ONE minibatch per epoch -- every BASELINE config -- the update is permutation independent and each rank simply
+        # permutes its own rows; device-drawn permutations (the engine's graph) keep per-rank permutations in every case)
+        global_minibatches = (allreduce is not None and draw_perm is None and self.num_mini_batch > 1
+                              and not (self._use_recurrent_policy or self._use_naive_recurrent))
         draw_perm = draw_perm or self._host_permutation
         loss_out = self._loss_out if loss_out is None else loss_out
         vn = self.value_normalizer.state if self.value_normalizer is not None else None
@@ -292,6 +296,19 @@ class R_MAPPO():
                 for i in range(self.num_mini_batch):
                     rows, first = buffer._chunk_rows(perm[i * mb:(i + 1) * mb].contiguous(), L)
                     plans.append((rows, first, L))
+            elif global_minibatches:
+                # data parallel with several minibatches: the reference's GLOBAL permutation (every rank draws it from the
+                # same CPU generator state), each rank keeps the rows of its own rollout threads
+                import torch.distributed as dist
+                from mappo_b200.dist import local_rows_of_global, shard_of_threads
+                ws, rk = dist.get_world_size(), dist.get_rank()
+                n_loc, M = buffer.n_rollout_threads, buffer.num_agents
+                lo, hi = shard_of_threads(n_loc * ws, ws, rk)
+                perm_g = torch.randperm(B * ws)
+                mbg = (B * ws) // self.num_mini_batch
+                for i in range(self.num_mini_batch):
+                    rows = local_rows_of_global(perm_g[i * mbg:(i + 1) * mbg], n_loc * ws, M, lo, hi).to(dev).contiguous()
+                    plans.append((rows, rows, 1))
             else:
                 mb = B // self.num_mini_batch
                 perm = draw_perm(B)

@@ -91,3 +91,73 @@ def test_shard_of_threads():
         assert False
     except ValueError:
         pass
+
+
+def _worker_mb(rank, world, port, out):
+    """num_mini_batch = 2: every rank draws the reference's GLOBAL permutation (same seed), keeps the rows it owns."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "on-policy_b200"))
+    from mappo_b200 import dist as D
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    cfg, store, adv, pa, pc = _full_problem()
+    T, N, M = cfg.episode_length, cfg.n_rollout_threads, cfg.num_agents
+    lo, hi = D.shard_of_threads(N, world, rank)
+    c, s, a = _shard(cfg, store, adv, lo, hi)
+    torch.manual_seed(123)
+    perm = torch.randperm(T * N * M)                      # identical on every rank
+    mb = T * N * M // 2
+    mine = D.local_rows_of_global(perm[:mb], N, M, lo, hi).numpy().astype(np.int64)       # first minibatch
+    tab, _ = O._flat_tables(s, a)
+    act_rows = tab["active_masks"][mine]
+    local = torch.tensor([[act_rows.sum(), tab["returns"][mine].sum(), (tab["returns"][mine] ** 2).sum(), len(mine)]], dtype=torch.float64)
+    flat = D.pack_stats(local, torch.zeros(3, dtype=torch.float64))
+    D.allreduce_sum_(flat)
+    per_update, _ = D.unpack_stats(flat, 1)
+    learner = O.Learner(c, pa, pc)
+    sample = tuple(None if tab[nm] is None else tab[nm][mine] for nm in O._GEN_FIELDS)
+    g = learner.ppo_update(sample, keep_grads=True)
+    w = D.loss_weight(float(act_rows.sum()), len(mine), float(per_update[0, 0]), int(per_update[0, 3]), True)
+    grads = torch.cat([v.reshape(-1) for v in g["actor_grads"].values()] + [v.reshape(-1) for v in g["critic_grads"].values()]) * w
+    D.allreduce_sum_(grads)
+    if rank == 0:
+        np.save(out, np.concatenate([grads.numpy(), [float(per_update[0, 3])]]))
+    dist.destroy_process_group()
+
+
+def test_global_minibatch_partition_equals_single_process(tmp_path):
+    out = str(tmp_path / "g.npy")
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker_mb, args=(2, port, out), nprocs=2, join=True)
+    got = np.load(out)
+    cfg, store, adv, pa, pc = _full_problem()
+    T, N, M = cfg.episode_length, cfg.n_rollout_threads, cfg.num_agents
+    torch.manual_seed(123)
+    perm = torch.randperm(T * N * M).numpy()
+    learner = O.Learner(cfg, pa, pc)
+    tab, _ = O._flat_tables(store, adv)
+    rows = perm[:T * N * M // 2]                         # the first of two minibatches (shared_buffer.py:358-361)
+    g = learner.ppo_update(tuple(None if tab[nm] is None else tab[nm][rows] for nm in O._GEN_FIELDS), keep_grads=True)
+    want = torch.cat([v.reshape(-1) for v in g["actor_grads"].values()] + [v.reshape(-1) for v in g["critic_grads"].values()]).numpy()
+    assert got[-1] == len(rows)
+    np.testing.assert_allclose(got[:-1], want, rtol=2e-4, atol=1e-7)
+
+
+def test_local_rows_of_global_is_the_ownership_filter():
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "on-policy_b200"))
+    from mappo_b200 import dist as D
+    T, N, M, world = 5, 8, 3, 4
+    g = torch.arange(T * N * M).reshape(T, N, M)
+    perm = torch.randperm(T * N * M)
+    seen = []
+    for rank in range(world):
+        lo, hi = D.shard_of_threads(N, world, rank)
+        loc = D.local_rows_of_global(perm, N, M, lo, hi).long()
+        local_storage = g[:, lo:hi].reshape(-1)                # what the rank's own flattened storage holds (global row ids)
+        picked = local_storage[loc]
+        want = perm[(perm // M % N >= lo) & (perm // M % N < hi)]
+        assert torch.equal(picked, want)                       # the owned rows, in permutation order
+        seen.append(picked)
+    assert torch.equal(torch.sort(torch.cat(seen)).values, torch.arange(T * N * M))
