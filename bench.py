@@ -547,7 +547,11 @@ def run_gpu(a):
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         peaks = json.load(open(pk))
-    tf32_peak = measure_tf32_peak(dev)
+    try:
+        tf32_peak = measure_tf32_peak(dev)
+    except Exception as e:                                 # never lose the headline to a side measurement
+        print(f"[bench] tf32 peak measurement failed ({type(e).__name__}: {e}); using bf16 / 2", file=sys.stderr)
+        tf32_peak = float(peaks.get("bf16_tflops", 1590.0)) / 2
 
     sampler = ClockSampler(local)
     res = run_config(a.config, a, world, rank, dev, dist, sampler)
@@ -572,8 +576,12 @@ def run_gpu(a):
 
     breakdown = None
     if rank == 0 and a.breakdown and res["workload"]["n_policies"] == 1:
-        breakdown = eng0.phase_breakdown()
-        if a.gemm == "tf32" and not eng0.big and not cfg.recurrent:
+        try:
+            breakdown = eng0.phase_breakdown()
+        except Exception as e:
+            print(f"[bench] phase breakdown failed ({type(e).__name__}: {e})", file=sys.stderr)
+            breakdown = {"error": f"{type(e).__name__}: {e}"}
+        if a.gemm == "tf32" and not eng0.big and not cfg.recurrent and "error" not in breakdown:
             import ctypes as C
             from mappo_b200 import _lib
             t = (C.c_int64 * 16)()
@@ -583,7 +591,13 @@ def run_gpu(a):
                      "S11", "dump_G2", "G1_wait", "tail"]
             breakdown["tc_tile_cycles_warm"] = {nm: int(t[i + 1] - t[i]) for i, nm in enumerate(names)}
             breakdown["tc_tile_cycles_warm"]["total"] = int(t[15] - t[0])
-    roof = kernel_roofline(res, a, peaks, tf32_peak) if rank == 0 else None
+    roof = None
+    if rank == 0:
+        try:
+            roof = kernel_roofline(res, a, peaks, tf32_peak)
+        except Exception as e:
+            print(f"[bench] roofline leg failed ({type(e).__name__}: {e})", file=sys.stderr)
+            roof = {"error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         traffic = None
@@ -596,7 +610,10 @@ def run_gpu(a):
         roof["traffic_unit"] = "bytes/launch (ncu --set full, profiles/)"
         cpu = None
         if world == 1 and a.cpu_iters > 0:
-            cpu, _ = cpu_baseline(a.config, min(a.cpu_iters, {"c2": 100, "c3": 10, "c4": 2, "c5": 3}[a.config]))
+            try:
+                cpu, _ = cpu_baseline(a.config, min(a.cpu_iters, {"c2": 100, "c3": 10, "c4": 2, "c5": 3}[a.config]))
+            except Exception as e:
+                print(f"[bench] cpu_baseline leg failed ({type(e).__name__}: {e})", file=sys.stderr)
         line = result_line(a.config, res, a, world, roof, cpu, res["clocks"], extra_cfg)
         line["phase_breakdown_ms"] = breakdown
         line["tf32_peak_tflops_measured"] = tf32_peak
@@ -606,11 +623,14 @@ def run_gpu(a):
             torch.cuda.empty_cache()
             others = {}
             if a.gemm == "tf32" and a.config in ("c2", "c5"):
-                a2 = argparse.Namespace(**{**vars(a), "gemm": "fp32", "steps": max(3, a.steps // 4)})
-                r2 = run_config(a.config, a2, 1, 0, dev, dist, None, light=True)
-                line["value_fp32"] = {"value": r2["value"], "ms_per_step": r2["ms_per_step"], "e2e_value": r2["e2e_value"],
-                                      "gemm": "fp32 (exact FFMA build of the same kernels)"}
-                del r2
+                try:
+                    a2 = argparse.Namespace(**{**vars(a), "gemm": "fp32", "steps": max(3, a.steps // 4)})
+                    r2 = run_config(a.config, a2, 1, 0, dev, dist, None, light=True)
+                    line["value_fp32"] = {"value": r2["value"], "ms_per_step": r2["ms_per_step"], "e2e_value": r2["e2e_value"],
+                                          "gemm": "fp32 (exact FFMA build of the same kernels)"}
+                    del r2
+                except Exception as e:
+                    line["value_fp32"] = {"error": f"{type(e).__name__}: {e}"}
                 torch.cuda.empty_cache()
             for other in (["c3", "c5"] if a.config == "c2" else []):
                 try:

@@ -72,6 +72,9 @@ typedef struct mappo_loss_cfg {
   int32_t use_valuenorm;       /* normalise return targets with the ValueNorm state */
   int32_t update_actor;        /* ppo_update(sample, update_actor) r_mappo.py:91,145 */
   int32_t gemm_mode;           /* MAPPO_GEMM_FP32 (exact fp32 FFMA tiles) or MAPPO_GEMM_TF32 (tcgen05 tensor cores) */
+  int32_t inputs_prepared;     /* hidden >= 128 nets only: the workspace already holds the normalised input rows of THIS batch
+                                  (same rows, same order) from an earlier mappo_update_fwd_bwd on it -- e.g. the later PPO epochs
+                                  of one train() over an unchanged buffer -- so the feature-norm pass is skipped */
 } mappo_loss_cfg_t;
 
 #define MAPPO_GEMM_FP32 0

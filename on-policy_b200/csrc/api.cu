@@ -124,7 +124,7 @@ int64_t workspace_floats(const NetDev& n, int rows, int sm);
 int pack_launch(const NetDev& n, const float* params, float* ws, int rows, bool round_tf32, int sm, cudaStream_t st);
 int update_launch(const NetDev& n, const float* params, const BatchDev& b, const LossDev& L, const double* norm_stats,
                   const double* adv_stats, const float* vn_state, float* grad, double* loss_out, float* ws, bool tf32, int sm,
-                  cudaStream_t st);
+                  cudaStream_t st, bool inputs_prepared = false);
 }  // namespace big
 
 static int g_sm_count = 0;
@@ -567,7 +567,7 @@ int32_t mappo_update_fwd_bwd(const mappo_net_desc_t* desc, const float* params, 
   if (big::supported(n)) {
     if (!workspace) { set_error("update_fwd_bwd: hidden >= 128 net needs its workspace"); return MAPPO_ERR_INVALID; }
     return big::update_launch(n, params, b, L, norm_stats, adv_stats, vn_state, grad_part, loss_out, workspace,
-                              loss->gemm_mode == MAPPO_GEMM_TF32, sm_count(), (cudaStream_t)stream);
+                              loss->gemm_mode == MAPPO_GEMM_TF32, sm_count(), (cudaStream_t)stream, loss->inputs_prepared != 0);
   }
   if (n.hid != 64) { set_error("update_fwd_bwd: hidden_size %d is not built (64, or a multiple of 128 up to 1024)", n.hid); return MAPPO_ERR_UNSUPPORTED; }
   if (loss->gemm_mode == MAPPO_GEMM_TF32) {

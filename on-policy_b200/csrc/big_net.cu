@@ -349,10 +349,10 @@ int pack_launch(const NetDev& n, const float* params, float* ws, int rows, bool 
 }
 
 static int run_forward(const NetDev& n, const Plan& pl, float* ws, const float* input, const int32_t* rows, int n_rows, bool tf32,
-                       int sm, cudaStream_t st) {
+                       int sm, cudaStream_t st, bool inputs_prepared = false) {
   const int act = n.use_relu ? ACT_RELU : ACT_TANH;
-  int rc;
-  {
+  int rc = MAPPO_OK;
+  if (!inputs_prepared) {
     Timed tm(T_FEATNORM, st);
     big_featnorm_kernel<<<(n_rows * 32 + 255) / 256, 256, 0, st>>>(input, rows, n_rows, n.in_dim, pl.K0p, n.use_fn, tf32 ? 1 : 0, ws + pl.x0);
     rc = check_launch("big_featnorm_kernel");
@@ -399,7 +399,7 @@ static int run_grad(const Plan& pl, float* ws, const float* P, int ldp, int Pw, 
 // forward + loss + backward of one net; the complete flat gradient goes to `grad`, loss sums to loss_out
 int update_launch(const NetDev& n, const float* params, const BatchDev& b, const LossDev& L, const double* norm_stats,
                   const double* adv_stats, const float* vn_state, float* grad, double* loss_out, float* ws, bool tf32, int sm,
-                  cudaStream_t st) {
+                  cudaStream_t st, bool inputs_prepared) {
   if (!supported(n)) { set_error("big net path: unsupported configuration (hidden %d, heads %d, in_dim %d)", n.hid, n.head_total, n.in_dim); return MAPPO_ERR_UNSUPPORTED; }
   if (!ws || (reinterpret_cast<uintptr_t>(ws) & 255)) { set_error("big net path: workspace NULL or not 256-byte aligned"); return MAPPO_ERR_INVALID; }
   const int rows = b.n_rows;
@@ -407,7 +407,7 @@ int update_launch(const NetDev& n, const float* params, const BatchDev& b, const
   const int act = n.use_relu ? ACT_RELU : ACT_TANH;
   int rc = pack_launch(n, params, ws, rows, tf32, sm, st);
   if (rc) return rc;
-  rc = run_forward(n, pl, ws, n.is_critic ? b.share_obs : b.obs, b.rows, rows, tf32, sm, st);
+  rc = run_forward(n, pl, ws, n.is_critic ? b.share_obs : b.obs, b.rows, rows, tf32, sm, st, inputs_prepared);
   if (rc) return rc;
   const int Lh = pl.Lh;
   {   // heads + losses

@@ -33,7 +33,8 @@ class LossCfg(C.Structure):
                 ("huber_delta", C.c_float),
                 ("use_clipped_value_loss", C.c_int32), ("use_huber_loss", C.c_int32),
                 ("use_value_active_masks", C.c_int32), ("use_policy_active_masks", C.c_int32),
-                ("use_valuenorm", C.c_int32), ("update_actor", C.c_int32), ("gemm_mode", C.c_int32)]
+                ("use_valuenorm", C.c_int32), ("update_actor", C.c_int32), ("gemm_mode", C.c_int32),
+                ("inputs_prepared", C.c_int32)]
 
 
 _P = C.c_void_p

@@ -82,12 +82,14 @@ class R_MAPPO():
                              UpdateWorkspace(self.policy.critic, key, self.gemm_mode))
         return self._ws[key]
 
-    def _one_update(self, batch, n_rows, norm_stats, adv_stats, loss_out, update_actor, allreduce, only=None):
-        """One optimiser step of both nets (`only`: just the "actor" / "critic" chain)."""
+    def _one_update(self, batch, n_rows, norm_stats, adv_stats, loss_out, update_actor, allreduce, only=None, prepared=False):
+        """One optimiser step of both nets (`only`: just the "actor" / "critic" chain).  `prepared`: the workspaces already
+        hold the normalised input rows of this batch (hidden >= 128 nets, later epochs over the same rows)."""
         pol = self.policy
         ws_a, ws_c = self._workspaces(n_rows)
         loss_a = make_loss_cfg(self.args, update_actor)
         loss_c = make_loss_cfg(self.args, update_actor)
+        loss_a.inputs_prepared = loss_c.inputs_prepared = int(bool(prepared))
         vn = self.value_normalizer.state if self.value_normalizer is not None else None
 
         # data parallel with the peer-memory kernel: every net has its OWN reducer (buffer, signal pads, round counter),
@@ -186,7 +188,7 @@ class R_MAPPO():
             self._p2p_nets[k].allreduce_grad(self._par[k], self._par_scratch)
             self._par[k] ^= 1
 
-    def _storage_batch(self, buffer, adv, rows, first, seq_len):
+    def _storage_batch(self, buffer, adv, rows, first, seq_len, n_rows=None):
         b = Batch()
         T = buffer.episode_length
         b.obs, b.share_obs = ptr(buffer.obs), ptr(buffer.share_obs)
@@ -195,10 +197,10 @@ class R_MAPPO():
         b.masks, b.active_masks = ptr(buffer.masks), ptr(buffer.active_masks)
         b.avail = ptr(buffer.available_actions)
         b.h0_actor, b.h0_critic = ptr(buffer.rnn_states), ptr(buffer.rnn_states_critic)
-        b.rows, b.seq_first = ptr(rows), ptr(first)
-        b.n_rows = rows.numel()
+        b.rows, b.seq_first = ptr(rows), ptr(first)             # None: storage order
+        b.n_rows = rows.numel() if rows is not None else int(n_rows)
         b.seq_len = seq_len
-        b.n_seq = rows.numel() // seq_len
+        b.n_seq = b.n_rows // seq_len
         return b
 
     # ------------------------------------------------------------------------------------------
@@ -339,12 +341,19 @@ class R_MAPPO():
             adv_stats = stats[n_updates * 4:n_updates * 4 + 3]
 
         loss_out.zero_()
-        batches = [self._storage_batch(buffer, adv, rows, first, seq_len) for rows, first, seq_len in plans]
+        # hidden >= 128 nets with ONE minibatch per epoch (every BASELINE config): an epoch is a sum over all rows, so the
+        # rows are processed in storage order (no gather; the permutation is still drawn where the reference draws it) and
+        # the normalised inputs computed by the first epoch are reused by the later ones (the buffer does not change)
+        in_order = (bool(lib.mappo_big_net(C.byref(self.policy.actor.desc))) and self.num_mini_batch == 1 and
+                    not (self._use_recurrent_policy or self._use_naive_recurrent) and
+                    os.environ.get("MAPPO_B200_BIG_IN_ORDER", "1") == "1")
+        batches = [self._storage_batch(buffer, adv, None if in_order else rows, None if in_order else first, seq_len,
+                                       n_rows=rows.numel()) for rows, first, seq_len in plans]
 
         def updates(only):
             for u, (rows, _, _) in enumerate(plans):
                 self._one_update(batches[u], rows.numel(), stats[4 * u:4 * u + 4], adv_stats, loss_out, update_actor,
-                                 allreduce, only)
+                                 allreduce, only, prepared=in_order and u > 0)
 
         if self.overlap_nets and (allreduce is None or self._p2p_nets is not None):
             # actor and critic never read each other's state inside train(): their whole update sequences are two

@@ -90,11 +90,18 @@ def test_adam_leaves_parameters_alone_for_zero_gradients():
 def test_unsupported_configurations_fail_loudly():
     from mappo_b200 import _lib
     lib = _lib.load()
-    big = O.PathConfig(hidden_size=512, layer_N=2, obs_dim=658, share_obs_dim=783, act_dims=(20,), n_rollout_threads=4,
-                       episode_length=4, num_agents=2)           # config c5: not built yet
-    args, policy, trainer, buf = TP.build(big)
-    with pytest.raises(RuntimeError, match="hidden_size 512"):
-        policy.get_values(torch.zeros(8, 783), torch.zeros(8, 1, 512), torch.ones(8, 1))
+    # hidden sizes other than 64 (fused kernels) or a multiple of 128 up to 1024 (GEMM pipeline) are not built; neither is a GRU
+    # policy at hidden 128: both fail with a message instead of falling back
+    odd = O.PathConfig(hidden_size=96, layer_N=1, obs_dim=20, share_obs_dim=40, act_dims=(5,), n_rollout_threads=4,
+                       episode_length=4, num_agents=2)
+    args, policy, trainer, buf = TP.build(odd)
+    with pytest.raises(RuntimeError, match="hidden_size 96"):
+        policy.get_values(torch.zeros(8, 40), torch.zeros(8, 1, 96), torch.ones(8, 1))
+    gru = O.PathConfig(hidden_size=128, layer_N=1, obs_dim=20, share_obs_dim=40, act_dims=(5,), n_rollout_threads=4,
+                       episode_length=4, num_agents=2, use_recurrent_policy=True)
+    args, policy, trainer, buf = TP.build(gru)
+    with pytest.raises(RuntimeError, match="hidden_size 128"):
+        policy.get_values(torch.zeros(8, 40), torch.zeros(8, 1, 128), torch.ones(8, 1))
     d = _lib.NetDesc()
     d.in_dim, d.hidden, d.layer_n, d.n_heads = 10, 64, 1, 9
     assert lib.mappo_net_layout(C.byref(d), C.byref(_lib.NetLayout())) == -3
