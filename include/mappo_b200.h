@@ -188,6 +188,16 @@ int32_t mappo_big_net(const mappo_net_desc_t* desc);
  * GEMMs, [6] slot reduction + unfold -- accumulated over eager (non-captured) launches while `enable` was set; reading
  * synchronises on the recorded events.  Host pointers (7 entries each, nullable). */
 int32_t mappo_debug_big_timing(int32_t enable, double* ms_out7, int64_t* launches_out7);
+/* Kernel-level test entries: the two GEMM kernels of the pipeline in isolation (tests/test_gpu_bignet.py compares them with
+ * torch.matmul).  mappo_debug_big_lin: out[rows, N] (leading dimension N + 32; columns N, N + 1 = row mean / sigma) =
+ * relu(A[rows, K] W[N, K]^T + colvec[N + o]) and stats[rows] = (mean, 1 / sigma), K and N multiples of 32; scratch [rows, N]
+ * (fp32 build only).  mappo_debug_big_grad: gsum[M, Qw] = P[rows, :M]^T Q[rows, :Qw] via partial[splits, M, Qw]
+ * (splits from mappo_debug_big_grad_splits). */
+int32_t mappo_debug_big_lin(const float* A, int32_t lda, const float* W, int32_t ldw, float* out, float* stats, const float* colvec,
+                            float* scratch, int32_t rows, int32_t K, int32_t N, int32_t gemm_mode, void* stream);
+int32_t mappo_debug_big_grad(const float* P, int32_t ldp, int32_t Pw, int32_t M, const float* Q, int32_t ldq, int32_t Qw, int32_t rows,
+                             float* partial, float* gsum, int32_t gemm_mode, void* stream);
+int32_t mappo_debug_big_grad_splits(int32_t rows, int32_t M, int32_t Pw, int32_t Qw);
 int64_t mappo_rollout_workspace_floats(const mappo_net_desc_t* desc, int32_t n_rows);
 int32_t mappo_pack_rollout_weights_ex(const mappo_net_desc_t* desc, const float* params, float* image, int32_t gemm_mode,
                                       void* stream);

@@ -120,6 +120,11 @@ int policy_launch(const NetDev& n, float* ws, const float* input, int n_rows, co
                   cudaStream_t st);
 bool supported(const NetDev& n);
 int debug_timing(int enable, double* ms_out, long long* n_out);
+int debug_lin(const float* A, int lda, const float* W, int ldw, float* out, float* stats, const float* colvec, float* scratch,
+              int rows, int K, int N, bool tf32, int sm, cudaStream_t st);
+int debug_grad(const float* P, int ldp, int Pw, int M, const float* Q, int ldq, int Qw, int rows, float* partial, float* gsum,
+               bool tf32, int sm, cudaStream_t st);
+int debug_grad_splits(int rows, int M, int Pw, int Qw, int sm);
 int64_t workspace_floats(const NetDev& n, int rows, int sm);
 int pack_launch(const NetDev& n, const float* params, float* ws, int rows, bool round_tf32, int sm, cudaStream_t st);
 int update_launch(const NetDev& n, const float* params, const BatchDev& b, const LossDev& L, const double* norm_stats,
@@ -319,6 +324,18 @@ int32_t mappo_rollout_image_floats(const mappo_net_desc_t* desc) {
 int32_t mappo_debug_big_timing(int32_t enable, double* ms_out7, int64_t* launches_out7) {
   return big::debug_timing(enable, ms_out7, reinterpret_cast<long long*>(launches_out7));
 }
+
+int32_t mappo_debug_big_lin(const float* A, int32_t lda, const float* W, int32_t ldw, float* out, float* stats, const float* colvec,
+                            float* scratch, int32_t rows, int32_t K, int32_t N, int32_t gemm_mode, void* stream) {
+  if (!A || !W || !out || !stats || !colvec || rows <= 0 || K <= 0 || K % 32 || N <= 0 || N % 32 || N > 1024) { set_error("debug_big_lin: bad arguments"); return MAPPO_ERR_INVALID; }
+  return big::debug_lin(A, lda, W, ldw, out, stats, colvec, scratch, rows, K, N, gemm_mode == MAPPO_GEMM_TF32, sm_count(), (cudaStream_t)stream);
+}
+int32_t mappo_debug_big_grad(const float* P, int32_t ldp, int32_t Pw, int32_t M, const float* Q, int32_t ldq, int32_t Qw, int32_t rows,
+                             float* partial, float* gsum, int32_t gemm_mode, void* stream) {
+  if (!P || !Q || !partial || !gsum || rows <= 0 || Pw % 32 || Qw % 32 || M <= 0 || M > Pw) { set_error("debug_big_grad: bad arguments"); return MAPPO_ERR_INVALID; }
+  return big::debug_grad(P, ldp, Pw, M, Q, ldq, Qw, rows, partial, gsum, gemm_mode == MAPPO_GEMM_TF32, sm_count(), (cudaStream_t)stream);
+}
+int32_t mappo_debug_big_grad_splits(int32_t rows, int32_t M, int32_t Pw, int32_t Qw) { return big::debug_grad_splits(rows, M, Pw, Qw, sm_count()); }
 
 int32_t mappo_big_net(const mappo_net_desc_t* desc) {
   if (validate_desc(desc)) return 0;

@@ -485,6 +485,31 @@ int update_launch(const NetDev& n, const float* params, const BatchDev& b, const
   return MAPPO_OK;
 }
 
+// ---- kernel-level test entries (tests/test_gpu_bignet.py): the GEMM kernels in isolation against torch.matmul ----
+// out[rows, N] (ld N + 32) = relu(A[rows, K] W[N, K]^T) through big_lin_kernel<EpiFwd> (or the FFMA build), + row stats
+int debug_lin(const float* A, int lda, const float* W, int ldw, float* out, float* stats, const float* colvec, float* scratch,
+              int rows, int K, int N, bool tf32, int sm, cudaStream_t st) {
+  LinOperands o;
+  memset(&o, 0, sizeof(o));
+  o.A = A; o.lda = lda; o.W = W; o.ldw = ldw; o.out = out; o.ldo = N + kExt; o.sm_count = sm;
+  EpiFwd::Args ea;
+  ea.colvec = colvec; ea.stats_in = nullptr; ea.stats_out = reinterpret_cast<float2*>(stats); ea.out = out; ea.ld_out = N + kExt;
+  ea.N = N; ea.n_rows = rows; ea.act = ACT_RELU; ea.round_tf32 = 0;
+  LinShape sh;
+  memset(&sh, 0, sizeof(sh));
+  sh.n_rows = rows; sh.K = K; sh.N = N; sh.BN = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 32); sh.store_out = 1;
+  return tf32 ? lin_fwd_launch(o, ea, sh, st) : ref_lin_fwd_launch(o, ea, sh, scratch, st);
+}
+// gsum[M, Qw] = P[rows, :M]^T Q[rows, :Qw] through big_grad_kernel (or the FFMA build) + the slot reduction
+int debug_grad(const float* P, int ldp, int Pw, int M, const float* Q, int ldq, int Qw, int rows, float* partial, float* gsum,
+               bool tf32, int sm, cudaStream_t st) {
+  const GradShape g = make_grad_shape(rows, M, Pw, Qw, sm);
+  int rc = tf32 ? grad_gemm_launch(P, ldp, Q, ldq, partial, g, st) : ref_grad_gemm_launch(P, ldp, Q, ldq, partial, g, st);
+  if (rc) return rc;
+  return grad_reduce_launch(partial, g.splits, M * g.ldq, gsum, nullptr, nullptr, st);
+}
+int debug_grad_splits(int rows, int M, int Pw, int Qw, int sm) { return make_grad_shape(rows, M, Pw, Qw, sm).splits; }
+
 // rollout inference of one net on n_rows rows: packed weights must already sit at the front of `ws` (pack_launch)
 int policy_launch(const NetDev& n, float* ws, const float* input, int n_rows, const EpiSample::Args& sample_in, bool tf32, int sm,
                   cudaStream_t st) {

@@ -59,6 +59,9 @@ _SIGS = {
     "mappo_rollout_image_floats": (_i32, [C.POINTER(NetDesc)]),
     "mappo_big_net": (_i32, [C.POINTER(NetDesc)]),
     "mappo_debug_big_timing": (_i32, [_i32, _P, _P]),
+    "mappo_debug_big_lin": (_i32, [_P, _i32, _P, _i32, _P, _P, _P, _P, _i32, _i32, _i32, _i32, _P]),
+    "mappo_debug_big_grad": (_i32, [_P, _i32, _i32, _i32, _P, _i32, _i32, _i32, _P, _P, _i32, _P]),
+    "mappo_debug_big_grad_splits": (_i32, [_i32, _i32, _i32, _i32]),
     "mappo_rollout_workspace_floats": (_i64, [C.POINTER(NetDesc), _i32]),
     "mappo_pack_rollout_weights_ex": (_i32, [C.POINTER(NetDesc), _P, _P, _i32, _P]),
     "mappo_policy_step_ex": (_i32, [C.POINTER(NetDesc), _P, C.POINTER(NetDesc), _P] + [_P] * 7 +

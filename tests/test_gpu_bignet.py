@@ -66,6 +66,65 @@ def _sample(cfg, n, seed):
     return (cent, obs, h, h, acts, v_old, ret, masks, active, lp_old, adv, avail)
 
 
+def _tf32_values(shape, rng, scale=1.0):
+    """Random fp32 values exactly representable in tf32 (so a tf32 GEMM with fp32 accumulation is exact up to summation order)."""
+    return (np.round(rng.randn(*shape) * 64 * scale) / 64).astype(np.float32)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+@pytest.mark.parametrize("rows,K,N", [(128, 32, 128), (300, 64, 256), (128, 672, 512), (5000, 512, 512), (1000, 800, 1024), (77, 32, 32)])
+def test_big_lin_kernel_matches_matmul(rows, K, N, mode):
+    """The K-major GEMM kernel (TMA SWIZZLE_128B boxes -> tcgen05.mma kind::tf32 -> TMEM -> epilogue -> TMA store) in isolation."""
+    import ctypes as C
+    from mappo_b200 import _lib
+    from mappo_b200._lib import check, ptr
+    lib = _lib.load()
+    rng = np.random.RandomState(rows + K + N)
+    dev = torch.device("cuda:0")
+    A = torch.from_numpy(_tf32_values((rows, K), rng)).to(dev)
+    W = torch.from_numpy(_tf32_values((N, K), rng, 0.25)).to(dev)
+    bias = torch.from_numpy(rng.randn(N).astype(np.float32)).to(dev)
+    colvec = torch.cat([torch.zeros(N, device=dev), bias]).contiguous()
+    out = torch.full((rows, N + 32), float("nan"), device=dev)
+    stats = torch.zeros(rows, 2, device=dev)
+    scratch = torch.zeros(rows, N, device=dev)
+    check(lib.mappo_debug_big_lin(ptr(A), K, ptr(W), K, ptr(out), ptr(stats), ptr(colvec), ptr(scratch), rows, K, N,
+                                  1 if mode == "tf32" else 0, None))
+    torch.cuda.synchronize()
+    want = torch.relu(A.double() @ W.double().T + bias.double())
+    assert_close(out[:, :N].cpu().numpy(), want.cpu().numpy(), 1e-5, 1e-4, f"relu(A W^T + b) {rows}x{K}x{N}")
+    mu = want.mean(1)
+    sigma = torch.sqrt(want.var(1, unbiased=False) + 1e-5)
+    assert_close(stats[:, 0].cpu().numpy(), mu.cpu().numpy(), 1e-4, 1e-4, "row mean")
+    assert_close(stats[:, 1].cpu().numpy(), (1 / sigma).cpu().numpy(), 1e-3, 1e-5, "row 1/sigma")
+    assert_close(out[:, N].cpu().numpy(), mu.cpu().numpy(), 1e-4, 1e-4, "mean column")
+    assert_close(out[:, N + 1].cpu().numpy(), sigma.cpu().numpy(), 1e-3, 1e-5, "sigma column")
+    assert torch.all(out[:, N + 2:] == 0)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+@pytest.mark.parametrize("rows,Pw,M,Qw", [(128, 128, 128, 32), (300, 512, 512, 544), (5000, 512, 512, 672), (2000, 544, 544, 32),
+                                          (700, 256, 256, 800), (40000, 512, 512, 544)])
+def test_big_grad_kernel_matches_matmul(rows, Pw, M, Qw, mode):
+    """The MN-major GEMM kernel (contraction over the rows of two row-major matrices: TMA 128B-swizzle / 32B-atom boxes ->
+    tcgen05.mma with SWIZZLE_128B_BASE32B descriptors, row-split partials + slot sum) in isolation."""
+    from mappo_b200 import _lib
+    from mappo_b200._lib import check, ptr
+    lib = _lib.load()
+    rng = np.random.RandomState(rows + Pw + Qw)
+    dev = torch.device("cuda:0")
+    P = torch.from_numpy(_tf32_values((rows, Pw), rng, 0.25)).to(dev)
+    Q = torch.from_numpy(_tf32_values((rows, Qw), rng, 0.25)).to(dev)
+    splits = int(lib.mappo_debug_big_grad_splits(rows, M, Pw, Qw))
+    assert splits >= 1
+    partial = torch.full((splits, M, Qw), float("nan"), device=dev)
+    gsum = torch.full((M, Qw), float("nan"), device=dev)
+    check(lib.mappo_debug_big_grad(ptr(P), Pw, Pw, M, ptr(Q), Qw, Qw, rows, ptr(partial), ptr(gsum), 1 if mode == "tf32" else 0, None))
+    torch.cuda.synchronize()
+    want = (P[:, :M].double().T @ Q.double()).cpu().numpy()
+    assert_close(gsum.cpu().numpy(), want, 1e-5, 2e-3 * np.sqrt(rows / 128), f"P^T Q {rows}: {M}x{Qw} ({splits} row splits)")
+
+
 @pytest.mark.parametrize("mode", ["fp32", "tf32"])
 @pytest.mark.parametrize("name,n_rows", [("h64_tanh", 600), ("h128_tanh_multi", 333), ("h512_relu", 300), ("h256_relu_l0", 128),
                                          ("h512_relu", 5000)])
