@@ -72,6 +72,8 @@ typedef struct mappo_loss_cfg {
   int32_t use_valuenorm;       /* normalise return targets with the ValueNorm state */
   int32_t update_actor;        /* ppo_update(sample, update_actor) r_mappo.py:91,145 */
   int32_t gemm_mode;           /* MAPPO_GEMM_FP32 (exact fp32 FFMA tiles) or MAPPO_GEMM_TF32 (tcgen05 tensor cores) */
+  int32_t happo;               /* 1: actor loss of HAPPO (algorithms/happo/happo_trainer.py:129-141): one importance weight per row
+                                  (product over the action heads) times mappo_batch_t.factor inside the clipped surrogate */
   int32_t inputs_prepared;     /* hidden >= 128 nets only: the workspace already holds the normalised input rows of THIS batch
                                   (same rows, same order) from an earlier mappo_update_fwd_bwd on it -- e.g. the later PPO epochs
                                   of one train() over an unchanged buffer -- so the feature-norm pass is skipped */
@@ -100,6 +102,7 @@ typedef struct mappo_batch {
   const float* h0_critic;      /* [.,H]   rnn_states_critic rows (recurrent only) */
   const int32_t* rows;         /* [n_rows] storage row feeding position p, or NULL */
   const int32_t* seq_first;    /* [n_seq] storage row whose rnn state starts sequence c, or NULL */
+  const float* factor;         /* [.,1]   HAPPO importance factor of the row (separated_buffer.py:62-63) or NULL (= 1) */
   int32_t n_rows, seq_len, n_seq;
 } mappo_batch_t;
 

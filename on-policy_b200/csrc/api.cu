@@ -497,6 +497,7 @@ static int fill_batch(const mappo_net_desc_t* d, const mappo_batch_t* b, BatchDe
   o->obs = b->obs; o->share_obs = b->share_obs; o->actions = b->actions; o->old_logp = b->old_logp;
   o->value_preds = b->value_preds; o->returns = b->returns; o->advantages = b->advantages; o->masks = b->masks;
   o->active_masks = b->active_masks; o->avail = b->avail; o->h0_actor = b->h0_actor; o->h0_critic = b->h0_critic;
+  o->factor = b->factor;
   o->rows = b->rows; o->seq_first = b->seq_first; o->n_rows = b->n_rows; o->seq_len = b->seq_len; o->n_seq = b->n_seq;
   o->act_shape = d->n_heads; o->n_avail = d->head_dim[0];
   o->eval_out = nullptr; o->eval_only = 0;
@@ -573,6 +574,7 @@ int32_t mappo_update_fwd_bwd(const mappo_net_desc_t* desc, const float* params, 
   L.use_huber = loss->use_huber_loss; L.use_value_active = loss->use_value_active_masks;
   L.use_policy_active = loss->use_policy_active_masks; L.use_valuenorm = loss->use_valuenorm;
   L.update_actor = loss->update_actor;
+  L.happo = loss->happo;
   if (desc->is_critic && L.use_valuenorm && !vn_state) { set_error("update_fwd_bwd: use_valuenorm needs vn_state"); return MAPPO_ERR_INVALID; }
   const NetDev n = make_net_dev(desc);
   if (desc->recurrent) {

@@ -9,6 +9,7 @@ namespace mappo {
 struct BatchDev {
   const float *obs, *share_obs, *actions, *old_logp, *value_preds, *returns, *advantages, *masks, *active_masks,
       *avail, *h0_actor, *h0_critic;
+  const float* factor;         // [.,1] HAPPO importance factor of the row (separated_buffer.py:62-63), NULL = 1
   const int32_t *rows, *seq_first;
   int n_rows, seq_len, n_seq, act_shape, n_avail;
   // evaluate_actions mode (no gradients): per-position outputs, actor -> log-probs [n_rows, as], critic -> values
@@ -19,6 +20,7 @@ struct BatchDev {
 struct LossDev {
   float clip, ent_coef, vl_coef, huber_delta;
   int use_clipped_value_loss, use_huber, use_value_active, use_policy_active, use_valuenorm, update_actor;
+  int happo;                   // actor loss of algorithms/happo/happo_trainer.py:129-141 (joint ratio x factor)
 };
 
 // gather TR rows of `dim` floats into a transposed tile; rowid < 0 -> zeros
@@ -179,7 +181,7 @@ __device__ __forceinline__ LossConsts make_loss_consts(const NetDev& n, const Lo
 // The per-row scalars the loss needs, loadable EARLY (right after the row id is known) so their global-memory latency
 // hides behind the forward pass instead of sitting between the logits and the gradient.
 struct RowIn {
-  float active, v_old, ret, adv;
+  float active, v_old, ret, adv, factor;
   float action[kMaxHeads], old_logp[kMaxHeads];
 };
 // load that the compiler may not sink towards its first use (so it is issued where it is written)
@@ -191,6 +193,7 @@ __device__ __forceinline__ float ldg_pinned(const float* p) {
 __device__ __forceinline__ RowIn load_row_in(const NetDev& n, const BatchDev& b, int gr) {
   RowIn q;
   q.active = q.v_old = q.ret = q.adv = 0.f;
+  q.factor = 1.f;
 #pragma unroll
   for (int k = 0; k < kMaxHeads; ++k) q.action[k] = q.old_logp[k] = 0.f;
   if (gr < 0) return q;
@@ -200,6 +203,7 @@ __device__ __forceinline__ RowIn load_row_in(const NetDev& n, const BatchDev& b,
     q.ret = ldg_pinned(b.returns + gr);
   } else {
     q.adv = ldg_pinned(b.advantages + gr);
+    if (b.factor) q.factor = ldg_pinned(b.factor + gr);
 #pragma unroll
     for (int k = 0; k < kMaxHeads; ++k)
       if (k < n.n_heads) {
@@ -258,6 +262,60 @@ __device__ __forceinline__ void row_loss_pre(const NetDev& n, const BatchDev& b,
   const float adv = (q.adv - c.adv_mean) * c.adv_inv;
   const float* av = (b.avail && n.n_heads == 1) ? b.avail + (size_t)gr * b.n_avail : nullptr;
   const float inv_heads = 1.0f / (float)n.n_heads;
+  if (L.happo) {
+    // HAPPO (happo_trainer.py:129-141): ONE importance weight per row, R = prod_k exp(logp_k - old_logp_k), and the row's
+    // factor f multiplies min(R adv, clamp(R) adv).  Pass 1: per-head log-sum-exp, entropy, log-prob of the stored action.
+    float lse_k[kMaxHeads], ent_k[kMaxHeads], R = 1.f;
+    int off1 = 0;
+#pragma unroll
+    for (int k = 0; k < kMaxHeads; ++k) {
+      if (k < n.n_heads) {
+        const int A = n.head_dim[k];
+        head_lse<LD>(lgT, off1, A, r, av, lse_k[k]);
+        const int a = (int)q.action[k];
+        float ent = 0.f, lp_a = 0.f;
+        for (int j = 0; j < A; ++j) {
+          float lgt = lgT[(off1 + j) * LD + r];
+          if (av && av[j] == 0.f) lgt = -1e10f;
+          const float lp = lgt - lse_k[k];
+          ent = fmaf(-expf(lp), lp, ent);
+          if (j == a) lp_a = lp;
+        }
+        ent_k[k] = ent;
+        if (b.eval_out) b.eval_out[(size_t)p * b.act_shape + k] = lp_a;
+        R *= expf(lp_a - q.old_logp[k]);
+        acc[1] += (double)(ent * w * inv_heads);
+        off1 += A;
+      }
+    }
+    const float s1 = R * adv, s2 = fminf(fmaxf(R, 1.f - L.clip), 1.f + L.clip) * adv;
+    const float mn = fminf(s1, s2);
+    const bool inr = R >= 1.f - L.clip && R <= 1.f + L.clip;
+    const float dm = inr ? adv : (s1 < s2 ? adv : (s1 == s2 ? 0.5f * adv : 0.f));
+    const float dlp = -w * q.factor * dm * R;               // d loss / d logp_k: the same for every head (dR / dlogp_k = R)
+    const float dH = -L.ent_coef * w * inv_heads;
+    acc[0] += (double)(-q.factor * mn * w);
+    acc[2] += (double)R * (double)n.n_heads;                // reported as imp_weights.mean() over [rows, 1]
+    int off2 = 0;
+#pragma unroll
+    for (int k = 0; k < kMaxHeads; ++k) {
+      if (k < n.n_heads) {
+        const int A = n.head_dim[k], a = (int)q.action[k];
+        for (int j = 0; j < A; ++j) {
+          float lgt = lgT[(off2 + j) * LD + r];
+          const bool masked = av && av[j] == 0.f;
+          if (masked) lgt = -1e10f;
+          const float lp = lgt - lse_k[k];
+          const float pj = expf(lp);
+          float dl = dlp * ((j == a ? 1.f : 0.f) - pj) + dH * (-pj * (lp + ent_k[k]));
+          if (masked || !L.update_actor) dl = 0.f;
+          lgT[(off2 + j) * LD + r] = dl;
+        }
+        off2 += A;
+      }
+    }
+    return;
+  }
   int off = 0;
   for (int k = 0; k < n.n_heads; ++k) {
     const int A = n.head_dim[k];

@@ -34,7 +34,7 @@ class LossCfg(C.Structure):
                 ("use_clipped_value_loss", C.c_int32), ("use_huber_loss", C.c_int32),
                 ("use_value_active_masks", C.c_int32), ("use_policy_active_masks", C.c_int32),
                 ("use_valuenorm", C.c_int32), ("update_actor", C.c_int32), ("gemm_mode", C.c_int32),
-                ("inputs_prepared", C.c_int32)]
+                ("happo", C.c_int32), ("inputs_prepared", C.c_int32)]
 
 
 _P = C.c_void_p
@@ -42,7 +42,7 @@ _P = C.c_void_p
 
 class Batch(C.Structure):
     _fields_ = [(n, _P) for n in ("obs", "share_obs", "actions", "old_logp", "value_preds", "returns", "advantages",
-                                  "masks", "active_masks", "avail", "h0_actor", "h0_critic", "rows", "seq_first")] + \
+                                  "masks", "active_masks", "avail", "h0_actor", "h0_critic", "rows", "seq_first", "factor")] + \
                [("n_rows", C.c_int32), ("seq_len", C.c_int32), ("n_seq", C.c_int32)]
 
 

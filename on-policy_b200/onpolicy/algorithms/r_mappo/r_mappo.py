@@ -56,6 +56,7 @@ class R_MAPPO():
         if self._use_popart:
             raise NotImplementedError("use_popart: PopArt.update raises in the reference itself (SURVEY App. B-7)")
         self.value_normalizer = ValueNorm(1, device=self.device) if self._use_valuenorm else None
+        self._happo = False               # set by onpolicy.algorithms.happo.happo_trainer.HAPPO (same kernels, three switches)
         # GEMM engine of the update kernels: "tf32" = tcgen05 tensor cores (fp32 accumulate), "fp32" = exact FFMA tiles
         self.gemm_mode = {"fp32": _lib.GEMM_FP32, "tf32": _lib.GEMM_TF32}[os.environ.get("MAPPO_B200_GEMM", "fp32")]
         # actor and critic are independent nets: their update chains run on two streams (fork / join with events,
@@ -90,6 +91,7 @@ class R_MAPPO():
         loss_a = make_loss_cfg(self.args, update_actor)
         loss_c = make_loss_cfg(self.args, update_actor)
         loss_a.inputs_prepared = loss_c.inputs_prepared = int(bool(prepared))
+        loss_a.happo = loss_c.happo = int(self._happo)
         vn = self.value_normalizer.state if self.value_normalizer is not None else None
 
         # data parallel with the peer-memory kernel: every net has its OWN reducer (buffer, signal pads, round counter),
@@ -112,7 +114,7 @@ class R_MAPPO():
                           self.max_grad_norm, self._use_max_grad_norm, 3, allreduce)
 
         def critic_chain():         # ValueNorm.update(return_batch) BEFORE the value loss (reference :65), then :156-167
-            if vn is not None:
+            if vn is not None and not self._happo:      # (happo_trainer.py:56-66 never updates its normaliser)
                 check(_lib.load().mappo_valuenorm_update(ptr(vn), ptr(norm_stats), stream_ptr()))
             if per_net:
                 return p2p_chain(1, pol.critic, ws_c, loss_c, None, vn, pol.critic_optimizer, 4)
@@ -146,7 +148,7 @@ class R_MAPPO():
                 self._side = torch.cuda.Stream(device=self.device)
 
             def critic_grads():
-                if vn is not None:
+                if vn is not None and not self._happo:
                     check(_lib.load().mappo_valuenorm_update(ptr(vn), ptr(norm_stats), stream_ptr()))
                 launch_grads(pol.critic, ws_c, batch, loss_c, norm_stats, None, vn, loss_out, grad_out=gc)
 
@@ -197,6 +199,8 @@ class R_MAPPO():
         b.masks, b.active_masks = ptr(buffer.masks), ptr(buffer.active_masks)
         b.avail = ptr(buffer.available_actions)
         b.h0_actor, b.h0_critic = ptr(buffer.rnn_states), ptr(buffer.rnn_states_critic)
+        if self._happo and getattr(buffer, "factor", None) is not None:
+            b.factor = ptr(buffer.factor)                         # [T, N, 1] in storage row order (separated_buffer.py:62-63)
         b.rows, b.seq_first = ptr(rows), ptr(first)             # None: storage order
         b.n_rows = rows.numel() if rows is not None else int(n_rows)
         b.seq_len = seq_len
@@ -281,7 +285,11 @@ class R_MAPPO():
         # advantages + masked statistics (reference :179-187): reuse what compute_returns left when still valid
         want = id(self.value_normalizer) if self.value_normalizer is not None else 0
         adv, adv_stats = buffer.advantages, buffer._adv_stats
-        if buffer._adv_version != want:
+        if self._happo:                  # happo_trainer.py:181-184: value predictions are denormalised only under use_popart
+            adv_stats.zero_()
+            check(lib.mappo_advantages(ptr(buffer.returns), ptr(buffer.value_preds), ptr(buffer.active_masks), None,
+                                       B, ptr(adv), ptr(adv_stats), st))
+        elif buffer._adv_version != want:
             adv_stats.zero_()
             check(lib.mappo_advantages(ptr(buffer.returns), ptr(buffer.value_preds), ptr(buffer.active_masks), ptr(vn),
                                        B, ptr(adv), ptr(adv_stats), st))
@@ -414,7 +422,9 @@ class R_MAPPO():
         b.h0_critic = ptr(h_c.reshape(h_c.shape[0], -1).contiguous())
         b.rows = b.seq_first = None
         b.n_rows, b.n_seq, b.seq_len = n_rows, n_seq, n_rows // n_seq
-        keep = (share_obs, obs, h_a, h_c, actions, v_old, ret, masks, active, lp_old, adv, avail)
+        factor = as_dev(sample[12], dev) if (self._happo and len(sample) > 12) else None      # 13-tuples of separated buffers
+        b.factor = ptr(factor)
+        keep = (share_obs, obs, h_a, h_c, actions, v_old, ret, masks, active, lp_old, adv, avail, factor)
         return b, keep, ret, active
 
     def ppo_update(self, sample, update_actor=True):
@@ -446,7 +456,8 @@ class R_MAPPO():
         ret, active = as_dev(return_batch, dev), as_dev(active_masks_batch, dev)
         v_clip = v_old + (values - v_old).clamp(-self.clip_param, self.clip_param)
         if self._use_valuenorm:
-            self.value_normalizer.update(ret)
+            if not self._happo:
+                self.value_normalizer.update(ret)
             target = self.value_normalizer.normalize(ret)
         else:
             target = ret

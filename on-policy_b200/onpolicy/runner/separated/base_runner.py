@@ -54,8 +54,12 @@ class Runner(object):
                      "eval_interval", "log_interval", "model_dir"):
             setattr(self, name, getattr(a, name))
         self.use_wandb = a.use_wandb
-        if self.algorithm_name in ("happo", "hatrpo"):
-            raise NotImplementedError("HAPPO / HATRPO are outside this round's hot path (SURVEY section 8f row f3)")
+        Policy_, TrainAlgo_ = Policy, TrainAlgo
+        if self.algorithm_name == "happo":                     # reference :69-71
+            from onpolicy.algorithms.happo.happo_trainer import HAPPO as TrainAlgo_
+            from onpolicy.algorithms.happo.policy import HAPPO_Policy as Policy_
+        elif self.algorithm_name == "hatrpo":
+            raise NotImplementedError("HATRPO (trust-region step with conjugate gradients) is outside the hot path (SURVEY 2.1)")
         if self.use_render:
             import imageio  # noqa: F401
             self.run_dir = config["run_dir"]
@@ -76,14 +80,14 @@ class Runner(object):
         for agent_id in range(self.num_agents):
             cent = (self.envs.share_observation_space[agent_id] if self.use_centralized_V
                     else self.envs.observation_space[agent_id])
-            self.policy.append(Policy(a, self.envs.observation_space[agent_id], cent, self.envs.action_space[agent_id],
-                                      device=self.device))
+            self.policy.append(Policy_(a, self.envs.observation_space[agent_id], cent, self.envs.action_space[agent_id],
+                                       device=self.device))
         if self.model_dir is not None:
             self.restore()
         for agent_id in range(self.num_agents):
             cent = (self.envs.share_observation_space[agent_id] if self.use_centralized_V
                     else self.envs.observation_space[agent_id])
-            self.trainer.append(TrainAlgo(a, self.policy[agent_id], device=self.device))
+            self.trainer.append(TrainAlgo_(a, self.policy[agent_id], device=self.device))
             self.buffer.append(SeparatedReplayBuffer(a, self.envs.observation_space[agent_id], cent,
                                                      self.envs.action_space[agent_id],
                                                      device=self.policy[agent_id].device))

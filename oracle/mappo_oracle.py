@@ -14,8 +14,8 @@ which the reference's own arithmetic lives) of the referen
 Every function cites the reference file:line (relative to /root/reference/onpolicy/) it follows.
 Parity pin: the reference holds no tests or golden vectors for this path, so the
 oracle is pinned against outputs of the reference itself, generated in the build container by
-`tests/golden/make_golden.py` (committed together with the fixtures it wrote), and -- when
-/root/reference is present -- live in `tests/test_oracle_vs_reference.py`.
+`tests/golden/make_golden.py` / `make_golden_separated.py` (committed together with the fixtures they wrote;
+`tests/test_oracle_golden.py` checks the oracle against every one of them).
 """
 from __future__ import annotations
 
@@ -295,8 +295,9 @@ def _flat_tables(store: RolloutStore, advantages):
     return tab, B
 
 
-def minibatches(store: RolloutStore, advantages, perm: np.ndarray):
-    """Yield the reference's 12-tuples (order of shared_buffer.py:397-400 / :602-604) for one epoch.
+def minibatches(store: RolloutStore, advantages, perm: np.ndarray, factor=None):
+    """Yield the reference's 12-tuples (order of shared_buffer.py:397-400 / :602-604) for one epoch (13-tuples with the
+    gathered `factor` rows when given, separated_buffer.py:197-227).
     `perm` is the permutation the reference would have drawn with torch.randperm at :360 / :415 / :511."""
     c = store.cfg
     tab, B = _flat_tables(store, advantages)
@@ -317,6 +318,8 @@ def minibatches(store: RolloutStore, advantages, perm: np.ndarray):
                 sample.append(a[first])
             else:
                 sample.append(a[rows])
+        if factor is not None:
+            sample.append(np.asarray(factor).reshape(B, -1)[rows])
         yield tuple(sample)
 
 
@@ -487,8 +490,9 @@ class Learner:
     """Actor + critic parameter sets, two Adam optimisers (rMAPPOPolicy.py:31-37), ValueNorm,
     and the reference update rule (r_mappo.py:52-224)."""
 
-    def __init__(self, cfg: PathConfig, actor: Dict[str, torch.Tensor], critic: Dict[str, torch.Tensor]):
+    def __init__(self, cfg: PathConfig, actor: Dict[str, torch.Tensor], critic: Dict[str, torch.Tensor], happo: bool = False):
         self.cfg = cfg
+        self.happo = happo            # algorithms/happo/happo_trainer.py instead of r_mappo.py (see ppo_update / train)
         self.actor = {k: v.detach().clone().float().requires_grad_(True) for k, v in actor.items()}
         self.critic = {k: v.detach().clone().float().requires_grad_(True) for k, v in critic.items()}
         self.opt_a = torch.optim.Adam(list(self.actor.values()), lr=cfg.lr, eps=cfg.opti_eps, weight_decay=0)
@@ -519,10 +523,17 @@ class Learner:
         values, _ = critic_forward(c, self.critic, share_obs, h_c, masks)
         logp, ent = actor_evaluate(c, self.actor, obs, h_a, actions, masks, avail, active)
 
-        ratio = torch.exp(logp - lp_old)                                          # :129
-        s1 = ratio * adv
-        s2 = torch.clamp(ratio, 1.0 - c.clip_param, 1.0 + c.clip_param) * adv
-        per_row = -torch.sum(torch.min(s1, s2), dim=-1, keepdim=True)
+        if self.happo:                                     # happo_trainer.py:129-141: joint ratio, per-row factor
+            factor = t(sample[12])
+            ratio = torch.prod(torch.exp(logp - lp_old), dim=-1, keepdim=True)
+            s1 = ratio * adv
+            s2 = torch.clamp(ratio, 1.0 - c.clip_param, 1.0 + c.clip_param) * adv
+            per_row = -torch.sum(factor * torch.min(s1, s2), dim=-1, keepdim=True)
+        else:
+            ratio = torch.exp(logp - lp_old)                                      # :129
+            s1 = ratio * adv
+            s2 = torch.clamp(ratio, 1.0 - c.clip_param, 1.0 + c.clip_param) * adv
+            per_row = -torch.sum(torch.min(s1, s2), dim=-1, keepdim=True)
         pol = (per_row * active).sum() / active.sum() if c.use_policy_active_masks else per_row.mean()  # :134-139
 
         self.opt_a.zero_grad()
@@ -535,7 +546,8 @@ class Learner:
 
         v_clip = v_old + (values - v_old).clamp(-c.clip_param, c.clip_param)      # :62-63
         if self.vn is not None:
-            self.vn.update(ret.numpy())                                           # :65
+            if not self.happo:                 # happo_trainer.py:56-66 normalises with the state as is (never updates it)
+                self.vn.update(ret.numpy())                                       # :65
             mean, var = self.vn.mean_var()
             target = (ret - torch.tensor(mean)) / torch.sqrt(torch.tensor(var))    # fp32, valuenorm.py:63-64
         else:
@@ -570,14 +582,17 @@ class Learner:
         return math.sqrt(sum(float(v.grad.norm()) ** 2 for v in ps))            # utils/util.py:9-15
 
     # ---- r_mappo.py:171-224 ----
-    def train(self, store: RolloutStore, perms: Optional[List[np.ndarray]] = None, update_actor=True):
+    def train(self, store: RolloutStore, perms: Optional[List[np.ndarray]] = None, update_actor=True, factor=None):
+        """`factor` [T, N, M, 1]: the separated buffers' importance factor (separated_buffer.py:62-63), yielded as the 13th
+        element of every minibatch (:197-227); MAPPO ignores it (r_mappo.py:108-111), HAPPO multiplies it in."""
         c = self.cfg
-        adv = normalized_advantages(store, self.vn)
+        # happo_trainer.py:181-184 denormalises the value predictions only under use_popart (never with ValueNorm)
+        adv = normalized_advantages(store, None if self.happo else self.vn)
         info = dict(value_loss=0.0, policy_loss=0.0, dist_entropy=0.0, actor_grad_norm=0.0,
                     critic_grad_norm=0.0, ratio=0.0)
         for e in range(c.ppo_epoch):
             perm = perms[e] if perms is not None else torch.randperm(perm_length(c)).numpy()
-            for sample in minibatches(store, adv, perm):
+            for sample in minibatches(store, adv, perm, factor):
                 o = self.ppo_update(sample, update_actor)
                 for k in info:
                     info[k] += o[k]

@@ -9,16 +9,20 @@ import torch
 from oracle import mappo_oracle as O
 from helpers import INFO_KEYS, assert_close
 from argsutil import make_args, make_spaces
-from test_oracle_golden import load_separated
+from test_oracle_golden import load_separated, SEPARATED_CASES
 import test_gpu_parity as TP
 
 pytestmark = pytest.mark.gpu
 
 
 def _build_agents(z, M, cfgs, params):
-    from onpolicy.algorithms.r_mappo.algorithm.rMAPPOPolicy import R_MAPPOPolicy
-    from onpolicy.algorithms.r_mappo.r_mappo import R_MAPPO
     from onpolicy.utils.separated_buffer import SeparatedReplayBuffer
+    if str(z["algo"]) == "happo":                          # what runner/separated/base_runner.py:69-71 selects
+        from onpolicy.algorithms.happo.happo_trainer import HAPPO as R_MAPPO
+        from onpolicy.algorithms.happo.policy import HAPPO_Policy as R_MAPPOPolicy
+    else:
+        from onpolicy.algorithms.r_mappo.algorithm.rMAPPOPolicy import R_MAPPOPolicy
+        from onpolicy.algorithms.r_mappo.r_mappo import R_MAPPO
     dev = torch.device("cuda:0")
     pol, tr, buf = [], [], []
     for i, c in enumerate(cfgs):
@@ -33,9 +37,12 @@ def _build_agents(z, M, cfgs, params):
     return pol, tr, buf
 
 
-def test_separated_iteration_matches_reference(monkeypatch):
+@pytest.mark.parametrize("name", SEPARATED_CASES)
+def test_separated_iteration_matches_reference(name, monkeypatch):
+    """MAPPO: the factor is carried and ignored.  HAPPO (row f3): the factor and the joint (product over heads) importance weight
+    enter the actor loss, ValueNorm is never updated, advantages use the raw value predictions -- all as in the reference."""
     from onpolicy.runner.separated.base_runner import train_agents
-    z, M, cfgs, params, feed = load_separated()
+    z, M, cfgs, params, feed = load_separated(name)
     pol, tr, buf = _build_agents(z, M, cfgs, params)
     T, N = cfgs[0].episode_length, cfgs[0].n_rollout_threads
     feeds = [feed(i) for i in range(M)]
@@ -43,17 +50,20 @@ def test_separated_iteration_matches_reference(monkeypatch):
         b, f = buf[i], feeds[i]
         b.obs[0].copy_(torch.from_numpy(f.obs[0][:, 0]))
         b.share_obs[0].copy_(torch.from_numpy(f.share_obs[0][:, 0]))
-        b.available_actions[0].copy_(torch.from_numpy(f.available_actions[0][:, 0]))
+        if f.available_actions is not None:
+            b.available_actions[0].copy_(torch.from_numpy(f.available_actions[0][:, 0]))
     for t in range(T):
         for i in range(M):                                        # per step, every agent in order (separated mpe_runner.py:100-131)
             b, f = buf[i], feeds[i]
             v, a, lp, ha, hc = pol[i]._step(b.share_obs[t], b.obs[t], b.rnn_states[t], b.rnn_states_critic[t], b.masks[t],
-                                            b.available_actions[t], False, True, True, exp_noise=z[f"agent{i}/noise"][t])
+                                            None if b.available_actions is None else b.available_actions[t], False, True, True,
+                                            exp_noise=z[f"agent{i}/noise"][t])
             d = torch.from_numpy(f.dones[t][:, 0]).to(b.device)
             masks = torch.ones(N, 1, device=b.device)
             masks[d] = 0.0
             b.insert(f.share_obs[t + 1][:, 0], f.obs[t + 1][:, 0], ha, hc, a.float(), lp, v, f.rewards[t][:, 0], masks,
-                     active_masks=f.active_masks[t][:, 0], available_actions=f.available_actions[t + 1][:, 0])
+                     active_masks=f.active_masks[t][:, 0],
+                     available_actions=None if f.available_actions is None else f.available_actions[t + 1][:, 0])
     for i in range(M):
         nv = pol[i].get_values(buf[i].share_obs[-1], buf[i].rnn_states_critic[-1], buf[i].masks[-1])
         buf[i].compute_returns(nv, tr[i].value_normalizer)

@@ -91,12 +91,15 @@ def _collect_only(cfg, learner, store, feed, noise):
 # --------------------------------------------------------------------------------------------
 # separated policies: one learner + store per agent, trained in the reference's randperm order
 # --------------------------------------------------------------------------------------------
-def load_separated():
+SEPARATED_CASES = ["sep_mlp_2agents", "sep_happo_2agents"]
+
+
+def load_separated(name="sep_mlp_2agents"):
     import ast
     import os
     import torch
     from helpers import GOLDEN_DIR
-    z = np.load(os.path.join(GOLDEN_DIR, "sep_mlp_2agents.npz"), allow_pickle=False)
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
     M = int(z["n_agents"])
     cfgs = []
     for i in range(M):
@@ -104,20 +107,23 @@ def load_separated():
         d["act_dims"] = tuple(d["act_dims"])
         cfgs.append(O.PathConfig(**d))
     params = lambda pre: {k[len(pre):]: torch.from_numpy(z[k].copy()) for k in z.files if k.startswith(pre)}
-    feed = lambda i: O.SyntheticFeed(*[z[f"agent{i}/feed/{n}"].copy() for n in
+    feed = lambda i: O.SyntheticFeed(*[z[f"agent{i}/feed/{n}"].copy() if f"agent{i}/feed/{n}" in z.files else None for n in
                                        ("obs", "share_obs", "rewards", "dones", "active_masks", "available_actions")])
     return z, M, cfgs, params, feed
 
 
-def test_oracle_separated_matches_reference():
+@pytest.mark.parametrize("name", SEPARATED_CASES)
+def test_oracle_separated_matches_reference(name):
     import torch
-    z, M, cfgs, params, feed = load_separated()
-    learners = [O.Learner(cfgs[i], params(f"agent{i}/init/actor/"), params(f"agent{i}/init/critic/")) for i in range(M)]
+    z, M, cfgs, params, feed = load_separated(name)
+    happo = str(z["algo"]) == "happo"
+    learners = [O.Learner(cfgs[i], params(f"agent{i}/init/actor/"), params(f"agent{i}/init/critic/"), happo=happo) for i in range(M)]
     stores = [O.RolloutStore(c) for c in cfgs]
     feeds = [feed(i) for i in range(M)]
     for i in range(M):
         stores[i].obs[0], stores[i].share_obs[0] = feeds[i].obs[0], feeds[i].share_obs[0]
-        stores[i].available_actions[0] = feeds[i].available_actions[0]
+        if feeds[i].available_actions is not None:
+            stores[i].available_actions[0] = feeds[i].available_actions[0]
         _collect_only(cfgs[i], learners[i], stores[i], feeds[i], z[f"agent{i}/noise"])
         sq = lambda a: a.reshape(a.shape[0], a.shape[1], *a.shape[3:])
         np.testing.assert_array_equal(sq(stores[i].actions), z[f"agent{i}/buf/actions"])
@@ -133,9 +139,10 @@ def test_oracle_separated_matches_reference():
         s, c = stores[i], cfgs[i]
         flat = lambda a: t(a[:T].reshape(T * N, -1))
         ev = lambda: O.actor_evaluate(c, learners[i].actor, flat(s.obs), flat(s.rnn_states).reshape(T * N, 1, -1), flat(s.actions),
-                                      flat(s.masks), flat(s.available_actions), flat(s.active_masks))[0].detach()
+                                      flat(s.masks), None if s.available_actions is None else flat(s.available_actions),
+                                      flat(s.active_masks))[0].detach()
         old = ev()
-        info = learners[i].train(s, list(z[f"agent{i}/perms"]))
+        info = learners[i].train(s, list(z[f"agent{i}/perms"]), factor=factor.reshape(T, N, 1, 1))
         new = ev()
         factor = factor * torch.prod(torch.exp(new - old), dim=-1).reshape(T, N, 1).numpy()
         s.after_update()
@@ -149,3 +156,5 @@ def test_oracle_separated_matches_reference():
         for k, v in learners[i].critic.items():
             assert_close(v.detach().numpy(), z[f"agent{i}/final/critic/{k}"], 1e-4, 2e-6, f"agent {i} critic {k}")
         assert_close(learners[i].vn.state(), z[f"agent{i}/valuenorm"], 1e-5, 1e-9, "valuenorm")
+    if happo:                          # the reference's HAPPO never updates its ValueNorm (happo_trainer.py:42-84)
+        assert np.all(z["agent0/valuenorm"] == 0)
