@@ -111,3 +111,115 @@ def test_shared_mpe_runner_drives_the_device_environment(tmp_path):
     want = obs.reshape(obs.shape[0], obs.shape[1], 1, -1).expand(-1, -1, 3, -1)
     assert torch.equal(runner.buffer.share_obs[1:], want)
     runner.writter.close()
+
+
+# --------------------------------------------------------------------------------------------
+# SMAC runner: bookkeeping of insert against a NumPy restatement of reference smac_runner.py:133-151
+# --------------------------------------------------------------------------------------------
+class FakeSmacEnv:
+    """SMAC-shaped host vec-env: per-agent deaths, env-level episode ends, available-action masks, bad_transition infos."""
+
+    def __init__(self, cfg, n, seed=0):
+        self.cfg, self.n, self.rng = cfg, n, np.random.RandomState(seed)
+        obs_s, share_s, act_s = make_spaces(cfg)
+        M = cfg.num_agents
+        self.observation_space, self.share_observation_space, self.action_space = [obs_s] * M, [share_s] * M, [act_s] * M
+        self.dead = np.zeros((n, M), bool)
+        self.battles = np.zeros(n)
+        self.log = []
+
+    def _arrays(self):
+        n, M, c = self.n, self.cfg.num_agents, self.cfg
+        avail = (self.rng.rand(n, M, c.act_dims[0]) < 0.7).astype(np.float32)
+        avail[..., 0] = 1.0
+        return (self.rng.randn(n, M, c.obs_dim).astype(np.float32), self.rng.randn(n, M, c.share_obs_dim).astype(np.float32), avail)
+
+    def reset(self):
+        self.dead[:] = False
+        return self._arrays()
+
+    def step(self, actions):
+        a = np.asarray(actions)
+        n, M = self.n, self.cfg.num_agents
+        assert a.shape == (n, M, 1) and (a >= 0).all() and (a < self.cfg.act_dims[0]).all()
+        self.dead |= self.rng.rand(n, M) < 0.15
+        end = self.rng.rand(n) < 0.2
+        dones = self.dead | end[:, None]
+        bad = self.rng.rand(n, M) < 0.1
+        infos = [[{"bad_transition": bool(bad[i, m]), "battles_won": float(self.battles[i]), "battles_game": float(self.battles[i] + 1),
+                   "won": bool(end[i])} for m in range(M)] for i in range(n)]
+        self.battles += end
+        rew = np.repeat(self.rng.randn(n, 1, 1).astype(np.float32), M, 1)
+        obs, share, avail = self._arrays()
+        self.log.append((dones.copy(), bad.copy()))
+        self.dead[end] = False
+        return obs, share, rew, dones, infos, avail
+
+    def close(self):
+        pass
+
+
+def test_smac_runner_bookkeeping_and_training(tmp_path):
+    from onpolicy.runner.shared.smac_runner import SMACRunner
+    cfg = O.PathConfig(episode_length=12, n_rollout_threads=5, num_agents=3, obs_dim=30, share_obs_dim=48, act_dims=(9,), ppo_epoch=2,
+                       use_recurrent_policy=True, data_chunk_length=4, use_value_active_masks=False)
+    envs = FakeSmacEnv(cfg, 5, seed=1)
+    c = _config(cfg, tmp_path, envs, env_name="StarCraft2", map_name="3m", use_eval=True, eval_interval=1, n_eval_rollout_threads=2,
+                eval_episodes=3)
+    ecfg = O.PathConfig(**{**cfg.to_dict(), "n_rollout_threads": 2, "act_dims": (9,)})
+    c["eval_envs"] = FakeSmacEnv(ecfg, 2, seed=9)
+    c["all_args"].num_env_steps = cfg.episode_length * cfg.n_rollout_threads * 2
+    runner = SMACRunner(c)
+    # one rollout by hand: compare the storage with the reference's NumPy bookkeeping (smac_runner.py:133-151)
+    runner.warmup()
+    T, N, M, H = cfg.episode_length, 5, 3, cfg.hidden_size
+    want_masks, want_active, want_bad = np.ones((T + 1, N, M, 1), np.float32), np.ones((T + 1, N, M, 1), np.float32), np.ones((T + 1, N, M, 1), np.float32)
+    for step in range(T):
+        values, actions, lp, h_a, h_c = runner.collect(step)
+        obs, share, rew, dones, infos, avail = envs.step(actions)
+        runner.insert((obs, share, rew, dones, infos, avail, values, actions, lp, h_a, h_c))
+        dones_env = np.all(dones, axis=1)
+        m = np.ones((N, M, 1), np.float32); m[dones_env] = 0.0
+        am = np.ones((N, M, 1), np.float32); am[dones] = 0.0; am[dones_env] = 1.0
+        bm = np.array([[[0.0] if info[a]["bad_transition"] else [1.0] for a in range(M)] for info in infos], np.float32)
+        want_masks[step + 1], want_active[step + 1], want_bad[step + 1] = m, am, bm
+        assert torch.all(runner.buffer.rnn_states[step + 1][torch.from_numpy(dones_env)] == 0)
+        np.testing.assert_array_equal(runner.buffer.available_actions[step + 1].cpu().numpy(), avail)
+        np.testing.assert_array_equal(runner.buffer.share_obs[step + 1].cpu().numpy(), share)
+    np.testing.assert_array_equal(runner.buffer.masks.cpu().numpy(), want_masks)
+    np.testing.assert_array_equal(runner.buffer.active_masks.cpu().numpy(), want_active)
+    np.testing.assert_array_equal(runner.buffer.bad_masks.cpu().numpy(), want_bad)
+    assert 0 < want_active.mean() < 1 and want_masks.min() == 0          # the fake env exercised deaths and episode ends
+    # and the whole loop: trains, logs dead_ratio / win rates, evaluates
+    w0 = runner.policy.actor.flat.clone()
+    runner.run()
+    assert not torch.equal(w0, runner.policy.actor.flat) and torch.isfinite(runner.policy.actor.flat).all()
+    sc = runner.writter.scalars if hasattr(runner.writter, "scalars") else None
+    if sc is not None:
+        assert any(k.startswith("dead_ratio") for k in sc) and any(k.startswith("eval_win_rate") for k in sc)
+        assert any(k.startswith("incre_win_rate") for k in sc) and any(k.startswith("average_step_rewards") for k in sc)
+    runner.writter.close()
+
+
+@pytest.mark.parametrize("separated", [False, True])
+def test_mpe_runners_evaluate(tmp_path, separated, capsys):
+    """use_eval: deterministic rollouts on eval_envs, logged under the reference's keys (shared :141-183, separated :178-239)."""
+    if separated:
+        from onpolicy.runner.separated.mpe_runner import MPERunner
+    else:
+        from onpolicy.runner.shared.mpe_runner import MPERunner
+    cfg = O.PathConfig(episode_length=6, n_rollout_threads=4, num_agents=2, obs_dim=6, share_obs_dim=12, act_dims=(3,), ppo_epoch=1)
+    ecfg = O.PathConfig(**{**cfg.to_dict(), "n_rollout_threads": 3, "act_dims": (3,)})
+    c = _config(cfg, tmp_path, FakeVecEnv(cfg, separated=separated), share_policy=not separated, use_eval=True, eval_interval=1,
+                n_eval_rollout_threads=3)
+    c["eval_envs"] = FakeVecEnv(ecfg, seed=5, separated=separated)
+    c["all_args"].num_env_steps = cfg.episode_length * cfg.n_rollout_threads * 2
+    runner = MPERunner(c)
+    runner.run()
+    out = capsys.readouterr().out
+    assert "eval average episode rewards of agent" in out
+    assert c["eval_envs"].last_actions is not None and c["eval_envs"].last_actions.shape[:2] == (3, 2)
+    sc = getattr(runner.writter, "scalars", None)
+    if sc is not None:
+        assert any("eval_average_episode_rewards" in k for k in sc)
+    runner.writter.close()
