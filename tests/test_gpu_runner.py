@@ -223,3 +223,41 @@ def test_mpe_runners_evaluate(tmp_path, separated, capsys):
     if sc is not None:
         assert any("eval_average_episode_rewards" in k for k in sc)
     runner.writter.close()
+
+
+def test_hanabi_forward_runner_matches_reference(tmp_path):
+    """The turn-based runner against the UNMODIFIED reference runner driven on the same scripted environment
+    (tests/golden/make_golden_hanabi.py): per-player collect on the chosen games, reward attribution to the player's NEXT move,
+    chooseinsert, the one-slot reward shift, compute, train, chooseafter_update -- storage, weights, scores, step counts."""
+    import ast
+    import os
+    from helpers import GOLDEN_DIR, assert_close
+    from fake_hanabi import FakeHanabiVecEnv
+    from onpolicy.runner.shared.hanabi_runner_forward import HanabiRunner
+    z = np.load(os.path.join(GOLDEN_DIR, "hanabi_forward_runner.npz"), allow_pickle=False)
+    S = ast.literal_eval(str(z["spec"]))
+    cfg = O.PathConfig(episode_length=S["episode_length"], n_rollout_threads=S["n"], num_agents=S["players"], obs_dim=S["obs_dim"],
+                       share_obs_dim=S["share_dim"], act_dims=(S["n_moves"],), ppo_epoch=S["ppo_epoch"], lr=7e-4, critic_lr=7e-4)
+    envs = FakeHanabiVecEnv(S["n"], S["players"], S["obs_dim"], S["share_dim"], S["n_moves"], seed=S["env_seed"])
+    c = _config(cfg, tmp_path, envs, env_name="Hanabi", hanabi_name="Hanabi-Scripted", save_interval=1000)
+    c["all_args"].num_env_steps = S["episode_length"] * S["n"] * S["episodes"]
+    runner = HanabiRunner(c)
+    params = lambda pre: {k[len(pre):]: torch.from_numpy(z[k].copy()) for k in z.files if k.startswith(pre)}
+    runner.policy.actor.load_state_dict(params("init/actor/"))
+    runner.policy.critic.load_state_dict(params("init/critic/"))
+    torch.manual_seed(S["run_seed"])
+    runner.run()
+    assert runner.true_total_num_steps == int(z["true_total_num_steps"]) and envs.n_steps == int(z["env_steps"])
+    np.testing.assert_array_equal(np.array(runner.scores, dtype=np.float64), z["scores"])
+    b = runner.buffer
+    for nm in ("actions", "masks", "bad_masks", "active_masks", "available_actions", "rewards", "obs", "share_obs"):
+        np.testing.assert_array_equal(getattr(b, nm).cpu().numpy(), z["buf/" + nm], err_msg=nm)      # data movement: exact
+    assert_close(b.action_log_probs.cpu().numpy(), z["buf/action_log_probs"], 1e-4, 1e-5, "log-probs")
+    assert_close(b.value_preds.cpu().numpy(), z["buf/value_preds"], 1e-4, 1e-5, "value_preds")
+    assert_close(b.returns.cpu().numpy()[:-1], z["buf/returns"][:-1], 1e-4, 1e-4, "returns")
+    for k, v in runner.policy.actor.state_dict().items():
+        assert_close(v.cpu().numpy(), z[f"final/actor/{k}"], 2e-3, 2e-5, f"actor {k}")
+    for k, v in runner.policy.critic.state_dict().items():
+        assert_close(v.cpu().numpy(), z[f"final/critic/{k}"], 2e-3, 2e-5, f"critic {k}")
+    assert_close(runner.trainer.value_normalizer.state.cpu().numpy(), z["valuenorm"], 1e-4, 1e-8, "valuenorm")
+    runner.writter.close()
