@@ -133,3 +133,96 @@ class SpreadVecEnv:
             self._set_states(idx, rs)
         obs = self.observe()
         return obs, rew, np.repeat(done_env[:, None], M, axis=1)
+
+
+class ReferenceVecEnv:
+    """N independent MPE `simple_reference` worlds (2 agents, 3 landmarks, 10 communication symbols), float64, in the reference's
+    order of operations.  Pinned against tests/golden/mpe_simple_reference.npz (make_golden_mpe.py, unmodified reference env).
+
+      * scenario               envs/mpe/scenarios/simple_reference.py:8-97: agents and landmarks do not collide; agent i wants
+                               the OTHER agent at landmark goal[i]; reward_i = -|other.pos - landmark[goal_i].pos|^2, both
+                               agents receive the sum (collaborative); observation = own velocity, landmark positions relative
+                               to the agent, the colour of its goal landmark, the other agent's communication state
+      * action decoding        envs/mpe/environment.py:184-250 with a MultiDiscrete([[0,4],[0,9]]) space: the runner sends the
+                               two heads one-hot, concatenated (mpe_runner.py:112-119); u = 5 (a1 - a2, a3 - a4), c = one-hot
+      * World.step             envs/mpe/core.py:207-226, :229-238, :267-281 (no contact forces), update_agent_state :283-290
+                               (state.c = action.c, no noise)
+      * done / auto-reset      as SpreadVecEnv
+      * reset_world            :35-60: goal landmarks by np.random.choice, then positions -- the DRAWS are an input
+                               (`reset_states` [N, 2 + 2 (2 + 3)]: goal_0, goal_1, agent positions, landmark positions)."""
+    M, L, DIM_C = 2, 3, 10
+    COLORS = np.array([[0.75, 0.25, 0.25], [0.25, 0.75, 0.25], [0.25, 0.25, 0.75]])        # simple_reference.py:46-48
+
+    def __init__(self, n_envs: int, episode_length: int = 25, seed: int = 0):
+        self.N, self.EP = n_envs, episode_length
+        self.rng = np.random.RandomState(seed)
+        self.apos, self.avel = np.zeros((n_envs, 2, 2)), np.zeros((n_envs, 2, 2))
+        self.lpos = np.zeros((n_envs, 3, 2))
+        self.goal = np.zeros((n_envs, 2), dtype=np.int64)
+        self.comm = np.zeros((n_envs, 2, self.DIM_C))
+        self.step_count = np.zeros(n_envs, dtype=np.int64)
+        self.obs_dim = 2 + 2 * self.L + 3 + self.DIM_C           # 21
+
+    def draw_reset_states(self, n: int) -> np.ndarray:
+        out = np.zeros((n, 2 + 2 * (self.M + self.L)))
+        for i in range(n):
+            g = [self.rng.randint(0, self.L), self.rng.randint(0, self.L)]
+            a = [self.rng.uniform(-1, +1, 2) for _ in range(self.M)]
+            l = [0.8 * self.rng.uniform(-1, +1, 2) for _ in range(self.L)]
+            out[i] = np.concatenate([np.array(g, dtype=np.float64)] + a + l)
+        return out
+
+    def _set_states(self, idx, states):
+        s = np.asarray(states, dtype=np.float64).reshape(len(idx), -1)
+        self.goal[idx] = s[:, :2].astype(np.int64)
+        p = s[:, 2:].reshape(len(idx), self.M + self.L, 2)
+        self.apos[idx], self.lpos[idx] = p[:, :self.M], p[:, self.M:]
+        self.avel[idx] = 0.0
+        self.comm[idx] = 0.0
+        self.step_count[idx] = 0
+
+    def reset(self, reset_states: Optional[np.ndarray] = None) -> np.ndarray:
+        if reset_states is None:
+            reset_states = self.draw_reset_states(self.N)
+        self._set_states(np.arange(self.N), reset_states)
+        return self.observe()
+
+    def observe(self) -> np.ndarray:
+        out = np.zeros((self.N, self.M, self.obs_dim))
+        for m in range(self.M):
+            parts = [self.avel[:, m]] + [self.lpos[:, l] - self.apos[:, m] for l in range(self.L)]
+            parts += [self.COLORS[self.goal[:, m]], self.comm[:, 1 - m]]
+            out[:, m] = np.concatenate(parts, axis=1)
+        return out
+
+    def rewards(self) -> np.ndarray:
+        idx = np.arange(self.N)
+        indiv = []
+        for m in range(self.M):
+            d = self.apos[:, 1 - m] - self.lpos[idx, self.goal[:, m]]
+            indiv.append(-np.sum(np.square(d), axis=1))
+        total = indiv[0] + indiv[1]
+        return np.repeat(total[:, None, None], self.M, axis=1)
+
+    def step(self, actions: np.ndarray, reset_states: Optional[np.ndarray] = None):
+        """actions [N, 2, 2] integers (move in 0..4, symbol in 0..9).  Returns obs [N, 2, 21], rewards [N, 2, 1], dones [N, 2]."""
+        N, M = self.N, self.M
+        a = np.asarray(actions).reshape(N, M, 2).astype(np.int64)
+        onehot = np.eye(5)[a[:, :, 0]]
+        u = np.zeros((N, M, 2))
+        u[:, :, 0] += onehot[:, :, 1] - onehot[:, :, 2]
+        u[:, :, 1] += onehot[:, :, 3] - onehot[:, :, 4]
+        u *= SENSITIVITY
+        force = 1.0 * u + 0.0
+        self.avel = self.avel * (1 - DAMPING)
+        self.avel = self.avel + (force / 1.0) * DT
+        self.apos = self.apos + self.avel * DT
+        self.comm = np.eye(self.DIM_C)[a[:, :, 1]] + 0.0
+        self.step_count += 1
+        rew = self.rewards()
+        done_env = self.step_count >= self.EP
+        if np.any(done_env):
+            idx = np.nonzero(done_env)[0]
+            rs = self.draw_reset_states(len(idx)) if reset_states is None else np.asarray(reset_states)[idx]
+            self._set_states(idx, rs)
+        return self.observe(), rew, np.repeat(done_env[:, None], M, axis=1)

@@ -100,5 +100,56 @@ def main():
     print("wrote", out, "episodes per env", ep.tolist(), "reward range", float(rew.min()), float(rew.max()))
 
 
+def main_reference():
+    """simple_reference (c3's environment): MultiDiscrete([[0,4],[0,9]]) actions, goals + communication."""
+    shim_missing_modules()
+    sys.path.insert(0, REF)
+    from onpolicy.envs.mpe.MPE_env import MPEEnv
+
+    N, T, M, L, EP = 6, 64, 2, 3, 25
+    args = Namespace(scenario_name="simple_reference", episode_length=EP, num_agents=M, num_landmarks=L)
+    act_rng = np.random.RandomState(4321)
+    envs = []
+    for i in range(N):
+        env = MPEEnv(args)
+        env.seed(1 + i * 1000)
+        envs.append(env)
+
+    def state_of(env):
+        w = env.world
+        goals = [w.landmarks.index(w.agents[0].goal_b), w.landmarks.index(w.agents[1].goal_b)]
+        return np.concatenate([np.array(goals, dtype=np.float64)] + [a.state.p_pos for a in w.agents] + [l.state.p_pos for l in w.landmarks])
+
+    n_ep = T // EP + 2
+    resets = np.zeros((N, n_ep, 2 + 2 * (M + L)))
+    ep = np.zeros(N, dtype=np.int64)
+    obs0 = np.zeros((N, M, 21))
+    for i, env in enumerate(envs):
+        obs0[i] = np.array(env.reset())
+        resets[i, 0] = state_of(env)
+    actions = np.stack([act_rng.randint(0, 5, size=(T, N, M)), act_rng.randint(0, 10, size=(T, N, M))], axis=-1)
+    obs = np.zeros((T, N, M, 21))
+    rew = np.zeros((T, N, M, 1))
+    done = np.zeros((T, N, M), dtype=bool)
+    for t in range(T):
+        for i, env in enumerate(envs):
+            # mpe_runner.py:112-119: MultiDiscrete actions go in as the heads' one-hots concatenated
+            acts = [np.concatenate([np.eye(5)[actions[t, i, m, 0]], np.eye(10)[actions[t, i, m, 1]]]) for m in range(M)]
+            o, r, d, _ = env.step(acts)
+            if np.all(d):
+                o = env.reset()
+                ep[i] += 1
+                resets[i, ep[i]] = state_of(env)
+            obs[t, i], rew[t, i], done[t, i] = np.array(o), np.array(r), np.array(d)
+    out = os.path.join(HERE, "mpe_simple_reference.npz")
+    np.savez_compressed(out, episode_length=EP, obs0=obs0, resets=resets[:, :int(ep.max()) + 1], actions=actions, obs=obs,
+                        rewards=rew, dones=done)
+    print("wrote", out, "episodes per env", ep.tolist(), "reward range", float(rew.min()), float(rew.max()))
+
+
 if __name__ == "__main__":
-    main()
+    which = sys.argv[1:] or ["spread", "reference"]
+    if "spread" in which:
+        main()
+    if "reference" in which:
+        main_reference()

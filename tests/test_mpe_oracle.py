@@ -61,3 +61,17 @@ def test_reward_counts_the_self_collision_like_the_reference():
     for l in range(3):
         dists += min(np.linalg.norm(env.apos[0, a] - env.lpos[0, l]) for a in range(3))
     assert np.allclose(r[0, :, 0], 3 * (-dists - 1.0))
+
+
+def test_reference_scenario_oracle_is_bit_exact_against_the_reference_environment():
+    """simple_reference (BASELINE c3's environment): MultiDiscrete move + symbol actions, goal colours, the other agent's
+    communication state in the observation, reward = summed squared goal distances; 64 steps x 6 worlds, two auto-resets."""
+    from oracle.mpe_oracle import ReferenceVecEnv
+    g = np.load(os.path.join(os.path.dirname(GOLD), "mpe_simple_reference.npz"))
+    env = ReferenceVecEnv(g["obs0"].shape[0], int(g["episode_length"]))
+    assert np.array_equal(env.reset(g["resets"][:, 0]), g["obs0"])
+    for t, (o, r, d) in enumerate(replay(env, g)):
+        assert np.array_equal(o, g["obs"][t]), t
+        assert np.array_equal(r, g["rewards"][t]), t
+        assert np.array_equal(d, g["dones"][t]), t
+    assert g["dones"].any(axis=(1, 2)).sum() == 2 and g["obs"][..., 11:].sum() > 0        # resets and symbols were exercised
