@@ -232,6 +232,18 @@ int32_t mappo_mpe_spread_step(double* agent_pos, double* agent_vel, double* land
                               int32_t episode_length, float* obs_out, float* share_obs_out, float* rewards_out,
                               float* dones_out, void* stream);
 
+/* The same for MPE `simple_reference` (BASELINE configs[2]'s scenario; scenarios/simple_reference.py:8-97): 2 agents, 3
+ * landmarks, 10 communication symbols, no contacts.  Extra state: goal [n_envs, 2] (the landmark agent m wants the OTHER agent
+ * on), comm [n_envs, 2] (the symbol agent m uttered last step, -1 = silent after a reset).  actions [n_envs * 2, 2]: the
+ * MultiDiscrete([[0,4],[0,9]]) pair (move, symbol) as integer-valued floats, the layout mappo_policy_step stores.
+ * reset_states [n_envs, 12] (nullable): goal_0, goal_1, agent positions, landmark positions.  obs [E, 21] = velocity,
+ * landmarks - pos, goal colour, other agent's symbol one-hot; share_obs [E, 42] (nullable); rewards = r_0 + r_1 for both
+ * agents, r_m = -|pos[1 - m] - landmark[goal_m]|^2. */
+int32_t mappo_mpe_reference_step(double* agent_pos, double* agent_vel, double* landmark_pos, int32_t* goal, int32_t* comm,
+                                 int32_t* step_count, const float* actions, const double* reset_states, uint64_t rng_seed,
+                                 uint64_t* rng_counter_dev, int32_t n_envs, int32_t episode_length, float* obs_out,
+                                 float* share_obs_out, float* rewards_out, float* dones_out, void* stream);
+
 /* Advance the device-side Philox offset after a sampling step (no host round trip). */
 int32_t mappo_counter_add(uint64_t* counter_dev, uint64_t inc, void* stream);
 

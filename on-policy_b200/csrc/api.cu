@@ -392,6 +392,24 @@ int32_t mappo_mpe_spread_step(double* agent_pos, double* agent_vel, double* land
   return MAPPO_OK;
 }
 
+int32_t mappo_mpe_reference_step(double* agent_pos, double* agent_vel, double* landmark_pos, int32_t* goal, int32_t* comm,
+                                 int32_t* step_count, const float* actions, const double* reset_states, uint64_t rng_seed,
+                                 uint64_t* rng_counter_dev, int32_t n_envs, int32_t episode_length, float* obs_out,
+                                 float* share_obs_out, float* rewards_out, float* dones_out, void* stream) {
+  if (!agent_pos || !agent_vel || !landmark_pos || !goal || !comm || !step_count || !obs_out || n_envs <= 0 || episode_length <= 0) { set_error("mpe_reference_step: NULL / bad argument"); return MAPPO_ERR_INVALID; }
+  if (!reset_states && !rng_counter_dev) { set_error("mpe_reference_step: resets need reset_states or rng_counter_dev"); return MAPPO_ERR_INVALID; }
+  if (actions && (!rewards_out || !dones_out)) { set_error("mpe_reference_step: a step needs rewards_out and dones_out"); return MAPPO_ERR_INVALID; }
+  MpeRefArgs a;
+  a.apos = agent_pos; a.avel = agent_vel; a.lpos = landmark_pos; a.goal = goal; a.comm = comm; a.step_count = step_count;
+  a.actions = actions; a.reset_states = reset_states; a.rng_seed = rng_seed; a.rng_counter = rng_counter_dev;
+  a.N = n_envs; a.episode_length = episode_length;
+  a.obs = obs_out; a.share_obs = share_obs_out; a.rewards = rewards_out; a.dones = dones_out;
+  const int rc = mpe_reference_launch(a, (cudaStream_t)stream);
+  if (rc) return rc;
+  if (!reset_states) return counter_add_launch(rng_counter_dev, (uint64_t)n_envs, (cudaStream_t)stream);
+  return MAPPO_OK;
+}
+
 int32_t mappo_counter_add(uint64_t* counter_dev, uint64_t inc, void* stream) {
   if (!counter_dev) { set_error("counter_add: NULL"); return MAPPO_ERR_INVALID; }
   return counter_add_launch(counter_dev, inc, (cudaStream_t)stream);

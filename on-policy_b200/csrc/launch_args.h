@@ -54,6 +54,17 @@ struct MpeArgs {
   float *obs, *share_obs, *rewards, *dones;   // [N*M][D], [N*M][M*D] (nullable), [N*M], [N*M]
 };
 int mpe_spread_launch(const MpeArgs& a, cudaStream_t st);
+struct MpeRefArgs {                      // `simple_reference`: 2 agents, 3 landmarks, 10 symbols
+  double *apos, *avel, *lpos;            // [N][2][2], [N][2][2], [N][3][2]
+  int32_t *goal, *comm, *step_count;     // [N][2] goal landmark, [N][2] last symbol (-1 = silent), [N]
+  const float* actions;                  // [N*2][2] integer-valued (move 0..4, symbol 0..9); NULL = reset only
+  const double* reset_states;            // [N][12]: goal_0, goal_1, agent positions, landmark positions; or NULL (device RNG)
+  uint64_t rng_seed;
+  const uint64_t* rng_counter;
+  int N, episode_length;
+  float *obs, *share_obs, *rewards, *dones;   // [N*2][21], [N*2][42] (nullable), [N*2], [N*2]
+};
+int mpe_reference_launch(const MpeRefArgs& a, cudaStream_t st);
 
 // closed rollout loop with the device-side simple_spread worlds (rollout_closed.cuh)
 struct ClosedArgs {

@@ -79,6 +79,7 @@ _SIGS = {
     "mappo_rollout_closed_loop": (_i32, [C.POINTER(NetDesc), _P, C.POINTER(NetDesc), _P] + [_P] * 7 + [_P] * 4 +
                                   [_P, _u64, _P, _P, _u64, _P, _i32, _i32, _i32, _i32, _i32, _P]),
     "mappo_mpe_spread_step": (_i32, [_P, _P, _P, _P, _P, _P, _u64, _P, _i32, _i32, _i32, _i32, _P, _P, _P, _P, _P]),
+    "mappo_mpe_reference_step": (_i32, [_P, _P, _P, _P, _P, _P, _P, _P, _u64, _P, _i32, _i32, _P, _P, _P, _P, _P]),
     "mappo_minibatch_stats_batch": (_i32, [_P, _P, _P, _i64, _i32, _i32, _P, _P]),
     "mappo_randperm_batch": (_i32, [_i32, _i32, _u64, _P, _P, _P]),
     "mappo_valuenorm_update": (_i32, [_P, _P, _P]),

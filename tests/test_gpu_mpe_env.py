@@ -133,3 +133,47 @@ def test_fused_and_per_step_closed_loops_agree_bit_for_bit(monkeypatch):
                                          env.rng_counter, policy.rng_offset, policy.actor.flat, policy.critic.flat)])
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+
+
+def test_device_reference_scenario_is_bit_exact_against_the_reference_trajectories():
+    """mappo_mpe_reference_step against the trajectories of the unmodified reference `simple_reference` environment
+    (make_golden_mpe.py main_reference): no exp / log in this scenario, so the float64 state is IEEE-exact and the float32
+    outputs must be bit-identical.  Also checks share_obs and the device-RNG reset ranges."""
+    from mappo_b200.mpe_env import DeviceReferenceEnv, DeviceReferenceVecEnv
+    g = np.load(os.path.join(os.path.dirname(GOLD), "mpe_simple_reference.npz"))
+    N, T = g["obs0"].shape[0], g["actions"].shape[0]
+    env = DeviceReferenceEnv(N, int(g["episode_length"]), device="cuda", seed=3)
+    f = lambda *s: torch.zeros(*s, dtype=torch.float32, device="cuda")
+    obs, share, rew, done = f(N * 2, 21), f(N * 2, 42), f(N * 2), f(N * 2)
+    env.reset(obs, share, reset_states=g["resets"][:, 0])
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(obs.cpu().numpy().reshape(N, 2, 21), g["obs0"].astype(np.float32))
+    ep = np.zeros(N, dtype=np.int64)
+    last = g["resets"].shape[1] - 1
+    for t in range(T):
+        nxt = g["resets"][np.arange(N), np.minimum(ep + 1, last)]
+        act = torch.from_numpy(np.ascontiguousarray(g["actions"][t].reshape(-1, 2).astype(np.float32))).cuda()
+        env.step(act, obs, share, rew, done, reset_states=nxt)
+        torch.cuda.synchronize()
+        o = obs.cpu().numpy().reshape(N, 2, 21)
+        np.testing.assert_array_equal(o, g["obs"][t].astype(np.float32), err_msg=f"obs t={t}")
+        np.testing.assert_array_equal(rew.cpu().numpy().reshape(N, 2, 1), g["rewards"][t].astype(np.float32), err_msg=f"rewards t={t}")
+        np.testing.assert_array_equal(done.cpu().numpy().reshape(N, 2) != 0, g["dones"][t])
+        np.testing.assert_array_equal(share.cpu().numpy().reshape(N, 2, 42), np.repeat(o.reshape(N, 1, 42), 2, axis=1))
+        ep += g["dones"][t][:, 0]
+    # device RNG resets + the vec-env adapter with the runner's concatenated one-hot actions
+    venv = DeviceReferenceVecEnv(256, 5, device="cuda", seed=11)
+    o0 = venv.reset()
+    e = venv.env
+    assert np.all(np.abs(e.apos.cpu().numpy()) < 1) and np.all(np.abs(e.lpos.cpu().numpy()) < 0.8)
+    gl = e.goal.cpu().numpy()
+    assert gl.min() == 0 and gl.max() == 2 and set(np.unique(o0[..., 8:11])) == {0.25, 0.75} and o0[..., 11:].sum() == 0
+    rng = np.random.RandomState(0)
+    mv, sy = rng.randint(0, 5, (256, 2)), rng.randint(0, 10, (256, 2))
+    onehot = np.concatenate([np.eye(5)[mv], np.eye(10)[sy]], axis=-1)
+    o1, r1, d1, _ = venv.step(onehot)
+    assert np.array_equal(o1[:, 0, 11:].argmax(-1), sy[:, 1]) and np.array_equal(o1[:, 1, 11:].argmax(-1), sy[:, 0])
+    assert not d1.any() and np.all(r1 <= 0) and np.array_equal(r1[:, 0], r1[:, 1])
+    for _ in range(4):
+        o1, r1, d1, _ = venv.step(onehot)
+    assert d1.all() and o1[..., 11:].sum() == 0 and np.all(o1[..., :2] == 0)          # auto-reset: silent, at rest
