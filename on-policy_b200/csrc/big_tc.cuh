@@ -15,12 +15,21 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ bool mbar_try(uint32_t a, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  return ok != 0;
+}
+// A pipeline bug (wrong byte count, lost arrive) must surface as a launch failure, not as a hung GPU: the wait traps after
+// ~2 s of spinning (no legitimate wait in these kernels is longer than microseconds).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  if (mbar_try(a, parity)) return;
+  const long long t0 = clock64();
+  for (uint32_t it = 1;; ++it) {
+    if (mbar_try(a, parity)) return;
+    if ((it & 0xFFFu) == 0 && clock64() - t0 > 4000000000ll) __trap();
   }
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
