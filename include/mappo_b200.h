@@ -26,7 +26,7 @@ extern "C" {
 
 #define MAPPO_MAX_HEADS 4      /* MultiDiscrete heads per actor */
 #define MAPPO_MAX_LAYERS 2     /* layer_N hidden (H->H) blocks per MLP base */
-#define MAPPO_ABI_VERSION 3
+#define MAPPO_ABI_VERSION 4
 
 typedef enum mappo_status {
   MAPPO_OK = 0,
@@ -77,6 +77,8 @@ typedef struct mappo_loss_cfg {
   int32_t inputs_prepared;     /* hidden >= 128 nets only: the workspace already holds the normalised input rows of THIS batch
                                   (same rows, same order) from an earlier mappo_update_fwd_bwd on it -- e.g. the later PPO epochs
                                   of one train() over an unchanged buffer -- so the feature-norm pass is skipped */
+  int32_t image_ready;         /* MAPPO_GEMM_TF32 hidden-64 nets only: the workspace already holds the folded weight image of the
+                                  CURRENT parameters (left there by mappo_update_tail of the previous optimiser step) */
 } mappo_loss_cfg_t;
 
 #define MAPPO_GEMM_FP32 0
@@ -380,6 +382,16 @@ int32_t mappo_update_slot_floats(const mappo_net_desc_t* desc, int32_t gemm_mode
 int32_t mappo_update_finish(const mappo_net_desc_t* desc, const float* params, const float* grad_part, int32_t n_slots,
                             int32_t gemm_mode, float* grad, float* sumsq_part, int32_t* n_blocks_out, float* workspace,
                             void* stream);
+/* The optimiser tail of one MAPPO_GEMM_TF32 hidden-64 net as ONE launch (one 8-CTA thread-block cluster, stages separated by
+ * cluster barriers): `stages` bit 0 = mappo_update_finish (slot sum + unfold -> grad, 12 partial sums of squares in sumsq_part);
+ * bit 1 = mappo_clip_adam on `grad` (reading n_sumsq_blocks partials; 12 when bit 0 ran in the same launch) followed by the
+ * folded weight image of the NEW parameters into `workspace` -- so the next mappo_update_fwd_bwd may be called with
+ * mappo_loss_cfg_t.image_ready = 1 and launches no pack kernel.  Bit-identical to the separate calls.  A multi-GPU caller
+ * runs stages = 1, its all-reduce of `grad`, then stages = 2.  workspace as for mappo_update_fwd_bwd / mappo_update_finish. */
+int32_t mappo_update_tail(const mappo_net_desc_t* desc, float* params, const float* grad_part, int32_t n_slots, float* grad,
+                          float* exp_avg, float* exp_avg_sq, float* sumsq_part, int32_t n_sumsq_blocks, const float* lr_dev,
+                          int32_t* step_dev, float eps, float max_grad_norm, int32_t use_max_grad_norm, double* grad_norm_out,
+                          double* beta_pow_dev, float* workspace, int32_t stages, void* stream);
 int32_t mappo_grad_reduce(const float* grad_part, int32_t n_slots, int32_t n_params, float* grad,
                           float* sumsq_part, int32_t* n_sumsq_blocks_out, void* stream);
 /* Per-block sums of squares of an already reduced (e.g. all-reduced) gradient vector. */

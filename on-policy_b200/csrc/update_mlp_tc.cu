@@ -176,24 +176,27 @@ __host__ __device__ inline TcRaw make_tc_raw(const TcImage& m) {
 // dW = dW' diag(gamma_in) + db' beta_in^T, db = dW'[:, one], dgamma_in = colsum(dW' .* W), dbeta_in = W^T db'   (chain rule of the
 // folding) from the slot-summed raw accumulators.  Grid: blockIdx.y = layer (0 fc2, 1 fc1, 2 heads), blockIdx.x = block
 // of 16 input features; 256 threads = 16 features x 16 groups of 4 output rows.  Every CTA also emits its sum(g^2).
-__global__ void __launch_bounds__(256)
-tc_unfold_kernel(const NetDev n, const float* __restrict__ p, const float* __restrict__ raw, float* __restrict__ g,
-                 float* __restrict__ sumsq_part) {
-  __shared__ float part_g[16][17], part_b[16][17], sred[8];
+// The body works on one (bx, by) unit with 256 threads `tid`; part_g / part_b / sred are that unit's shared scratch.  `active`
+// == false: the unit only takes part in the barriers (tc_tail_kernel runs four units per CTA, not all of them populated).
+struct UnfoldScratch { float part_g[16][17], part_b[16][17], sred[8]; };
+__device__ __forceinline__ void tc_unfold_unit(const NetDev& n, const float* p, const float* raw, float* g, float* sumsq_part,
+                                               int bx, int by, int grid_x, int tid, bool active, UnfoldScratch& S) {
   const TcImage m = make_tc_image(n);
   const TcRaw R = make_tc_raw(m);
-  const int tid = threadIdx.x, kx = tid & 15, og = tid >> 4;
-  const int sec = blockIdx.y, k = blockIdx.x * 16 + kx;
+  const int kx = tid & 15, og = tid >> 4;
+  const int sec = by, k = bx * 16 + kx;                 // for the heads (sec == 2) k < 64 always (grid_x == 4)
   const int in = n.in_dim, Atot = n.head_total;
   float sq = 0.f;
   auto put = [&](int off, float v) { g[off] = v; sq = fmaf(v, v, sq); };
-  if (sec < 2) {
-    const int K = sec == 0 ? 64 : in, ld = sec == 0 ? kHF : m.inF, one = sec == 0 ? kOne : in;
+  const int K = sec == 0 ? 64 : (sec == 1 ? in : 64);
+  const bool fold = sec == 1 ? (n.use_fn != 0) : true;
+  const int gam_off = sec == 0 ? n.g.ln1_w : (sec == 1 ? n.g.fn_w : n.g.ln2_w[0]);
+  const int bet_off = sec == 0 ? n.g.ln1_b : (sec == 1 ? n.g.fn_b : n.g.ln2_b[0]);
+  float sg = 0.f, sb = 0.f;
+  if (active && sec < 2) {
+    const int ld = sec == 0 ? kHF : m.inF, one = sec == 0 ? kOne : in;
     const float* G = raw + (sec == 0 ? R.g2 : R.g1);
     const int w_off = sec == 0 ? n.g.fc2_w[0] : n.g.fc1_w, b_off = sec == 0 ? n.g.fc2_b[0] : n.g.fc1_b;
-    const bool fold = sec == 0 ? true : (n.use_fn != 0);
-    const int gam_off = sec == 0 ? n.g.ln1_w : n.g.fn_w, bet_off = sec == 0 ? n.g.ln1_b : n.g.fn_b;
-    float sg = 0.f, sb = 0.f;
     if (k < K) {
       const float gam = fold ? p[gam_off + k] : 1.f, bet = fold ? p[bet_off + k] : 0.f;
 #pragma unroll
@@ -205,57 +208,52 @@ tc_unfold_kernel(const NetDev n, const float* __restrict__ p, const float* __res
         sb = fmaf(dbo, w, sb);
       }
     }
-    if (blockIdx.x == 0 && tid < 64) put(b_off + tid, G[tid * ld + one]);
-    part_g[og][kx] = sg; part_b[og][kx] = sb;
-    __syncthreads();
-    if (fold && og == 0 && k < K) {
-      float a = 0.f, c = 0.f;
-#pragma unroll
-      for (int q = 0; q < 16; ++q) { a += part_g[q][kx]; c += part_b[q][kx]; }
-      put(gam_off + k, a);
-      put(bet_off + k, c);
-    }
-  } else {                                              // heads: raw gh[feature][a]; this CTA owns 16 features
-    const int kk = blockIdx.x * 16 + kx;                // < 64 (grid.x == 4 for this layer, extra blocks exit below)
-    if (kk < 64) {
-      const float gam = p[n.g.ln2_w[0] + kk], bet = p[n.g.ln2_b[0] + kk];
-      float sg = 0.f, sb = 0.f;
+    if (bx == 0 && tid < 64) put(b_off + tid, G[tid * ld + one]);
+  } else if (active) {                                  // heads: raw gh[feature][a]; this unit owns 16 features
+    if (k < 64) {
+      const float gam = p[gam_off + k], bet = p[bet_off + k];
       for (int a = og; a < Atot; a += 16) {
-        const float dw = raw[R.gh + kk * m.NH + a], w = p[n.g.head_w + a * 64 + kk], dba = raw[R.dbh + a];
-        put(n.g.head_w + a * 64 + kk, fmaf(dba, bet, dw * gam));
+        const float dw = raw[R.gh + k * m.NH + a], w = p[n.g.head_w + a * 64 + k], dba = raw[R.dbh + a];
+        put(n.g.head_w + a * 64 + k, fmaf(dba, bet, dw * gam));
         sg = fmaf(dw, w, sg);
         sb = fmaf(dba, w, sb);
       }
-      part_g[og][kx] = sg; part_b[og][kx] = sb;
-    } else { part_g[og][kx] = 0.f; part_b[og][kx] = 0.f; }
-    if (blockIdx.x == 0 && tid < Atot) put(n.g.head_b + tid, raw[R.dbh + tid]);
-    __syncthreads();
-    if (og == 0 && kk < 64) {
-      float a = 0.f, c = 0.f;
-#pragma unroll
-      for (int q = 0; q < 16; ++q) { a += part_g[q][kx]; c += part_b[q][kx]; }
-      put(n.g.ln2_w[0] + kk, a);
-      put(n.g.ln2_b[0] + kk, c);
     }
+    if (bx == 0 && tid < Atot) put(n.g.head_b + tid, raw[R.dbh + tid]);
   }
-  // sum of squares of everything this CTA wrote
+  S.part_g[og][kx] = sg; S.part_b[og][kx] = sb;
+  __syncthreads();
+  if (active && fold && og == 0 && k < K) {
+    float a = 0.f, c = 0.f;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { a += S.part_g[q][kx]; c += S.part_b[q][kx]; }
+    put(gam_off + k, a);
+    put(bet_off + k, c);
+  }
+  // sum of squares of everything this unit wrote
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  if ((tid & 31) == 0) S.sred[tid >> 5] = sq;
   __syncthreads();
-  if ((tid & 31) == 0) sred[tid >> 5] = sq;
-  __syncthreads();
-  if (tid == 0) {
+  if (tid == 0 && active) {
     float t = 0.f;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) t += sred[q];
-    sumsq_part[blockIdx.y * gridDim.x + blockIdx.x] = t;
+    for (int q = 0; q < 8; ++q) t += S.sred[q];
+    sumsq_part[by * grid_x + bx] = t;
   }
 }
 
-__global__ void __launch_bounds__(256) pack_tc_kernel(const NetDev n, const float* __restrict__ p, float* __restrict__ img) {
-  const TcImage m = make_tc_image(n);
+__global__ void __launch_bounds__(256)
+tc_unfold_kernel(const NetDev n, const float* __restrict__ p, const float* __restrict__ raw, float* __restrict__ g,
+                 float* __restrict__ sumsq_part) {
+  __shared__ UnfoldScratch S;
+  tc_unfold_unit(n, p, raw, g, sumsq_part, blockIdx.x, blockIdx.y, gridDim.x, threadIdx.x, true, S);
+}
+
+// element i of the folded tf32 weight image
+__device__ __forceinline__ float pack_tc_element(const NetDev& n, const TcImage& m, const float* p, int i) {
   const int H = 64;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m.total; i += gridDim.x * blockDim.x) {
+  {
     float v = 0.f;
     if (i < m.w2) {                                       // fc1: [inF/4][64][4]
       const int kc = i / 256, o = (i >> 2) & 63, k = kc * 4 + (i & 3);
@@ -292,8 +290,12 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const NetDev n, const floa
     }
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-    img[i] = __uint_as_float(u);
+    return __uint_as_float(u);
   }
+}
+__global__ void __launch_bounds__(256) pack_tc_kernel(const NetDev n, const float* __restrict__ p, float* __restrict__ img) {
+  const TcImage m = make_tc_image(n);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m.total; i += gridDim.x * blockDim.x) img[i] = pack_tc_element(n, m, p, i);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -801,6 +803,151 @@ int update_mlp_tc_unfold_launch(const NetDev& n, const float* params, const floa
   return check_launch("tc_unfold_kernel");
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// The whole optimiser tail of one net as ONE launch: slot sum -> unfold (+ sum g^2) -> clip + Adam -> folded image of the NEW
+// weights for the next step's update kernel.  One thread-block cluster of 8 CTAs x 1024 threads; the stages are separated by
+// cluster barriers (release / acquire at cluster scope orders the global-memory hand-offs), so the four launches of the
+// unfused tail (grad_reduce, tc_unfold, clip_adam, next step's pack_tc) and the gaps between them collapse into one.
+// Every stage keeps the arithmetic AND the summation order of the kernel it replaces (grad_reduce_kernel's 8 x 4 partial
+// sums per element, tc_unfold_unit, clip_adam_kernel<1>, pack_tc_element): the result is bit-identical to the unfused
+// path, which tests/test_gpu_tensorcore.py asserts.
+// `stages`: bit 0 = slot sum + unfold (leaves grad + 12 partial sums of squares), bit 1 = clip + Adam + image (reads
+// sumsq_part[0 .. n_part)): a multi-GPU caller runs stage 1, its all-reduce, then stage 2.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kTailCtas = 8, kTailThreads = 1024, kTailUnits = kTailCtas * (kTailThreads / 256), kTailUnroll = 3;
+struct TailArgs {
+  NetDev n;
+  const float* part; int n_slots;      // raw gradient slots [n_slots][R]
+  float* raw_sum;                      // [R]
+  float *p, *grad, *m, *v;             // flat parameters, gradient, Adam moments [P]
+  float* sumsq_part; int n_part;       // partial sums of squares (stage 1 writes 12; stage 2 reads n_part)
+  const float* lr_dev; int* step_dev; float eps, max_norm; int use_clip;
+  double* norm_out; double* beta_pow;
+  float* image;                        // folded tf32 weight image (NULL: not rebuilt)
+  int stages;
+};
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
+__global__ void __cluster_dims__(kTailCtas, 1, 1) __launch_bounds__(kTailThreads, 1) tc_tail_kernel(const TailArgs a) {
+  __shared__ float sacc[kTailThreads / 256][kTailUnroll][8][33];
+  __shared__ UnfoldScratch us[kTailThreads / 256];
+  __shared__ float s_total, s_coef, s_step_size, s_bc2_sqrt;
+  __shared__ int s_step;
+  __shared__ double s_p1, s_p2;
+  const int tid = threadIdx.x, sub = tid >> 8, t = tid & 255;
+  const int cta = (int)cluster_cta_rank();
+  const int unit = cta * (kTailThreads / 256) + sub;              // 0 .. 31
+  const int gtid = cta * kTailThreads + tid, gthreads = kTailCtas * kTailThreads;
+  const TcImage im = make_tc_image(a.n);
+  const int P = a.n.g.total;
+
+  if (a.stages & 1) {
+    // ---- slot sum (grad_reduce_kernel's order: warp sg adds slots sg, sg + 8, ... into 4 accumulators, then the 8 partials in turn)
+    const int R = make_tc_raw(im).total, nvb = (R + 31) / 32;
+    const int pi = t & 31, sg = t >> 5;
+    const int n_it = (nvb + kTailUnits * kTailUnroll - 1) / (kTailUnits * kTailUnroll);
+    for (int it = 0; it < n_it; ++it) {
+#pragma unroll
+      for (int u = 0; u < kTailUnroll; ++u) {
+        const int vb = unit + kTailUnits * (it * kTailUnroll + u), i = vb * 32 + pi;
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+        if (i < R) {
+          int s = sg;
+          for (; s + 24 < a.n_slots; s += 32) {
+            g0 += a.part[(size_t)s * R + i];
+            g1 += a.part[(size_t)(s + 8) * R + i];
+            g2 += a.part[(size_t)(s + 16) * R + i];
+            g3 += a.part[(size_t)(s + 24) * R + i];
+          }
+          for (; s < a.n_slots; s += 8) g0 += a.part[(size_t)s * R + i];
+        }
+        sacc[sub][u][sg][pi] = (g0 + g1) + (g2 + g3);
+      }
+      __syncthreads();
+      if (sg == 0) {
+#pragma unroll
+        for (int u = 0; u < kTailUnroll; ++u) {
+          const int vb = unit + kTailUnits * (it * kTailUnroll + u), i = vb * 32 + pi;
+          float g = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) g += sacc[sub][u][k][pi];
+          if (i < R) a.raw_sum[i] = g;
+        }
+      }
+      __syncthreads();
+    }
+    cluster_sync_all();
+    // ---- unfold: the 12 (bx, by) units of tc_unfold_kernel's grid (4, 3)
+    tc_unfold_unit(a.n, a.p, a.raw_sum, a.grad, a.sumsq_part, unit & 3, unit >> 2, 4, t, unit < 12, us[sub]);
+    cluster_sync_all();
+  }
+  if (a.stages & 2) {
+    // ---- clip_grad_norm_ + Adam (clip_adam_kernel<1>: the scalar prologue in one warp of every CTA, fixed order)
+    const int n_part = (a.stages & 1) ? 12 : a.n_part;
+    if (tid < 32) {
+      double x = 0.0;
+      for (int i = tid; i < n_part; i += 32) x += (double)a.sumsq_part[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      if (tid == 0) {
+        const float tot = (float)sqrt(x);
+        const int st = *a.step_dev + 1;
+        double p1, p2;
+        if (a.beta_pow && a.beta_pow[2] == (double)(st - 1)) { p1 = a.beta_pow[0] * 0.9; p2 = a.beta_pow[1] * 0.999; }
+        else { p1 = pow(0.9, (double)st); p2 = pow(0.999, (double)st); }
+        s_p1 = p1; s_p2 = p2;
+        const double bc1 = 1.0 - p1, bc2 = 1.0 - p2;
+        s_total = tot;
+        s_coef = a.use_clip ? fminf(a.max_norm / (tot + 1e-6f), 1.0f) : 1.f;
+        s_step_size = (float)((double)a.lr_dev[0] / bc1);
+        s_bc2_sqrt = (float)sqrt(bc2);
+        s_step = st;
+      }
+    }
+    __syncthreads();
+    const float coef = s_coef, step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+    for (int i = gtid; i < P; i += gthreads) {
+      const float g = a.grad[i] * coef, m_in = a.m[i], v_in = a.v[i];
+      const float mo = m_in + (g - m_in) * (float)(1.0 - 0.9);
+      const float vo = v_in * 0.999f + (float)(1.0 - 0.999) * g * g;
+      const float denom = sqrtf(vo) / bc2_sqrt + a.eps;
+      a.p[i] = a.p[i] - step_size * (mo / denom);
+      a.m[i] = mo; a.v[i] = vo;
+    }
+    cluster_sync_all();                                   // every CTA has read the old step count / powers; new weights are visible
+    if (gtid == 0) {
+      a.step_dev[0] = s_step;
+      if (a.beta_pow) { a.beta_pow[0] = s_p1; a.beta_pow[1] = s_p2; a.beta_pow[2] = (double)s_step; }
+      if (a.norm_out) *a.norm_out += (double)s_total;
+    }
+    // ---- folded image of the new weights (pack_tc_kernel of the NEXT optimiser step)
+    if (a.image)
+      for (int i = gtid; i < im.total; i += gthreads) a.image[i] = pack_tc_element(a.n, im, a.p, i);
+  }
+}
+
+int update_mlp_tc_tail_launch(const NetDev& n, const float* part, int n_slots, float* raw_sum, float* params, float* grad, float* m,
+                              float* v, float* sumsq_part, int n_part, const float* lr_dev, int* step_dev, float eps, float max_norm,
+                              int use_clip, double* norm_out, double* beta_pow, float* image, int stages, cudaStream_t st) {
+  if (!update_mlp_tc_supported(n)) { set_error("update_tail: the fused optimiser tail is built for the tcgen05 small-net path only"); return MAPPO_ERR_UNSUPPORTED; }
+  if ((stages & 3) == 0 || ((stages & 1) && (!part || n_slots <= 0 || !raw_sum)) || ((stages & 2) && (!m || !v || !lr_dev || !step_dev)) ||
+      ((stages & 3) == 2 && n_part <= 0)) { set_error("update_tail: bad arguments for stages %d", stages); return MAPPO_ERR_INVALID; }
+  TailArgs a;
+  a.n = n; a.part = part; a.n_slots = n_slots; a.raw_sum = raw_sum; a.p = params; a.grad = grad; a.m = m; a.v = v;
+  a.sumsq_part = sumsq_part; a.n_part = n_part; a.lr_dev = lr_dev; a.step_dev = step_dev; a.eps = eps; a.max_norm = max_norm;
+  a.use_clip = use_clip; a.norm_out = norm_out; a.beta_pow = beta_pow; a.image = image; a.stages = stages;
+  tc_tail_kernel<<<kTailCtas, kTailThreads, 0, st>>>(a);
+  return check_launch("tc_tail_kernel");
+}
+
 int update_mlp_tc_slots(const NetDev&, int n_rows, int sm_count) {
   const int n_tiles = (n_rows + kTM - 1) / kTM;
   return n_tiles < sm_count ? n_tiles : sm_count;
@@ -808,7 +955,7 @@ int update_mlp_tc_slots(const NetDev&, int n_rows, int sm_count) {
 
 int update_mlp_tc_launch(const NetDev& n, const float* params, const BatchDev& b, const LossDev& L,
                          const double* norm_stats, const double* adv_stats, const float* vn_state, float* grad_part,
-                         int n_slots, double* loss_out, float* image, cudaStream_t st) {
+                         int n_slots, double* loss_out, float* image, cudaStream_t st, bool image_ready) {
   if (!update_mlp_tc_supported(n)) { set_error("update_mlp_tc: configuration not built for the tcgen05 path"); return MAPPO_ERR_UNSUPPORTED; }
   if (!image) { set_error("update_mlp_tc: weight-image workspace is NULL"); return MAPPO_ERR_INVALID; }
   if ((reinterpret_cast<uintptr_t>(image) & 15) != 0) { set_error("update_mlp_tc: workspace must be 16-byte aligned"); return MAPPO_ERR_INVALID; }
@@ -816,9 +963,11 @@ int update_mlp_tc_launch(const NetDev& n, const float* params, const BatchDev& b
   const TcSmem sm = make_tc_smem(im);
   const size_t bytes = (size_t)sm.total * sizeof(float) + 1024;
   if (bytes > 227 * 1024) { set_error("update_mlp_tc: %zu B shared memory > 227 KB", bytes); return MAPPO_ERR_UNSUPPORTED; }
-  pack_tc_kernel<<<(im.total + 255) / 256, 256, 0, st>>>(n, params, image);      // one element per thread
-  const int rc = check_launch("pack_tc_kernel");
-  if (rc) return rc;
+  if (!image_ready) {                  // (the fused optimiser tail of the previous step leaves the image of the current weights)
+    pack_tc_kernel<<<(im.total + 255) / 256, 256, 0, st>>>(n, params, image);      // one element per thread
+    const int rc = check_launch("pack_tc_kernel");
+    if (rc) return rc;
+  }
   static thread_local SmemConfig configured_dev = {};
   size_t& configured = configured_dev.slot();
   if (bytes > configured) {

@@ -34,7 +34,7 @@ class LossCfg(C.Structure):
                 ("use_clipped_value_loss", C.c_int32), ("use_huber_loss", C.c_int32),
                 ("use_value_active_masks", C.c_int32), ("use_policy_active_masks", C.c_int32),
                 ("use_valuenorm", C.c_int32), ("update_actor", C.c_int32), ("gemm_mode", C.c_int32),
-                ("happo", C.c_int32), ("inputs_prepared", C.c_int32)]
+                ("happo", C.c_int32), ("inputs_prepared", C.c_int32), ("image_ready", C.c_int32)]
 
 
 _P = C.c_void_p
@@ -86,6 +86,7 @@ _SIGS = {
     "mappo_gather_rows": (_i32, [_P, _P, _i32, _i32, _P, _P]),
     "mappo_chunk_rows": (_i32, [_P, _i32, _i32, _i32, _i32, _P, _P, _P]),
     "mappo_randperm": (_i32, [_i32, _u64, _P, _P, _P]),
+    "mappo_update_tail": (_i32, [C.POINTER(NetDesc), _P, _P, _i32, _P, _P, _P, _P, _i32, _P, _P, _f32, _f32, _i32, _P, _P, _P, _i32, _P]),
     "mappo_update_workspace_floats": (_i64, [C.POINTER(NetDesc), _i32, _i32]),
     "mappo_update_grad_slots": (_i32, [C.POINTER(NetDesc), _i32, _i32]),
     "mappo_tf32_supported": (_i32, [C.POINTER(NetDesc)]),
@@ -122,7 +123,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError here = header / library out of sync
         fn.restype = res
         fn.argtypes = args
-    if lib.mappo_abi_version() != 3:
+    if lib.mappo_abi_version() != 4:
         raise RuntimeError("libmappo_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -7,6 +7,7 @@ fallback: without the library (or without a CUDA device) these objects cannot be
 from __future__ import annotations
 
 import ctypes as C
+import os
 import math
 from collections import OrderedDict
 from typing import List, Optional
@@ -373,6 +374,24 @@ class UpdateWorkspace:
             raise RuntimeError("mappo_update_workspace_floats failed: " + lib.mappo_last_error().decode())
         self.workspace = torch.empty(max(wf, 1), dtype=torch.float32, device=net.device)
         self.sumsq_part = torch.zeros((net.n_params + 31) // 32, dtype=torch.float32, device=net.device)
+        # hidden-64 tcgen05 path: the optimiser tail (slot sum, unfold, clip + Adam, next weight image) as one cluster launch
+        # (mappo_update_tail).  image_ready: the workspace holds the image of the CURRENT weights -- callers clear it whenever
+        # the parameters may have changed behind the tail's back (R_MAPPO.train() does at its start).
+        self.fused_tail = (self.gemm_mode == _lib.GEMM_TF32 and not lib.mappo_big_net(C.byref(net.desc))
+                           and os.environ.get("MAPPO_B200_FUSED_TAIL", "0") == "1")
+        self.image_ready = 0
+
+
+def _tail(net, ws, opt, stages, n_part, max_grad_norm, use_max_grad_norm, gn_ptr, grad):
+    lib = _lib.load()
+    n_slots = ws._n_slots_last
+    check(lib.mappo_update_tail(C.byref(net.desc), ptr(net.flat), ptr(ws.grad_part), n_slots, ptr(grad),
+                                None if opt is None else ptr(opt.exp_avg), None if opt is None else ptr(opt.exp_avg_sq),
+                                ptr(ws.sumsq_part), int(n_part), None if opt is None else ptr(opt.lr_dev),
+                                None if opt is None else ptr(opt.step_dev),
+                                0.0 if opt is None else float(opt.param_groups[0]["eps"]), float(max_grad_norm),
+                                int(bool(use_max_grad_norm)), gn_ptr, None if opt is None else ptr(opt.beta_pow),
+                                ptr(ws.workspace), int(stages), stream_ptr()))
 
 
 def make_loss_cfg(args, update_actor=True) -> LossCfg:
@@ -390,7 +409,7 @@ def make_loss_cfg(args, update_actor=True) -> LossCfg:
 
 
 def launch_grads(net: DeviceNet, ws: UpdateWorkspace, batch: Batch, loss: LossCfg, norm_stats, adv_stats, vn_state,
-                 loss_out, grad_out=None):
+                 loss_out, grad_out=None, finish=True):
     """forward + loss + backward -> slot reduction: leaves the (local) flat gradient in net.grad.
     Returns the number of sum-of-squares partials left in the optimiser's scratch (valid until an all-reduce)."""
     lib = _lib.load()
@@ -398,10 +417,18 @@ def launch_grads(net: DeviceNet, ws: UpdateWorkspace, batch: Batch, loss: LossCf
     n_rows = int(batch.n_rows)
     n_slots = min(ws.n_slots, int(lib.mappo_update_grad_slots(C.byref(net.desc), n_rows, ws.gemm_mode)))
     loss.gemm_mode = ws.gemm_mode
+    loss.image_ready = ws.image_ready if ws.fused_tail else 0
+    ws.image_ready = 0                   # whatever follows changes the weights; only a completed fused tail re-arms it
+    ws._n_slots_last = n_slots
     check(lib.mappo_update_fwd_bwd(C.byref(net.desc), ptr(net.flat), C.byref(batch), C.byref(loss), ptr(norm_stats),
                                    None if adv_stats is None else ptr(adv_stats),
                                    None if vn_state is None else ptr(vn_state), ptr(ws.grad_part), n_slots,
                                    ptr(loss_out), ptr(ws.workspace), st))
+    if finish is False:
+        return 0
+    if ws.fused_tail:
+        _tail(net, ws, None, 1, 0, 0.0, False, None, net.grad if grad_out is None else grad_out)
+        return 12
     nb = C.c_int32(0)
     check(lib.mappo_update_finish(C.byref(net.desc), ptr(net.flat), ptr(ws.grad_part), n_slots, ws.gemm_mode,
                                   ptr(net.grad if grad_out is None else grad_out), ptr(ws.sumsq_part), C.byref(nb),
@@ -413,6 +440,10 @@ def launch_step(net: DeviceNet, ws: UpdateWorkspace, loss_out, opt: FusedAdam, m
                 grad_norm_slot: int, n_sumsq_blocks: int):
     """clip_grad_norm_ + Adam on net.grad (n_sumsq_blocks == 0: re-derive the norm, e.g. after an all-reduce)."""
     gn_ptr = C.c_void_p(loss_out.data_ptr() + 8 * grad_norm_slot)
+    if ws.fused_tail and n_sumsq_blocks > 0:          # clip + Adam + the next step's weight image in one launch
+        _tail(net, ws, opt, 2, n_sumsq_blocks, max_grad_norm, use_max_grad_norm, gn_ptr, net.grad)
+        ws.image_ready = 1
+        return
     if n_sumsq_blocks > 0:
         opt.sumsq_part = ws.sumsq_part
     opt.apply(max_grad_norm, use_max_grad_norm, gn_ptr, n_sumsq_blocks=n_sumsq_blocks)
@@ -422,6 +453,12 @@ def launch_update(net: DeviceNet, ws: UpdateWorkspace, batch: Batch, loss: LossC
                   loss_out, opt: FusedAdam, max_grad_norm, use_max_grad_norm, grad_norm_slot: int,
                   allreduce=None):
     """forward+loss+backward -> slot reduction -> [all-reduce] -> clip + Adam for one net."""
+    if ws.fused_tail and allreduce is None:           # the whole tail as one cluster launch
+        launch_grads(net, ws, batch, loss, norm_stats, adv_stats, vn_state, loss_out, finish=False)
+        _tail(net, ws, opt, 3, 0, max_grad_norm, use_max_grad_norm,
+              C.c_void_p(loss_out.data_ptr() + 8 * grad_norm_slot), net.grad)
+        ws.image_ready = 1
+        return
     nb = launch_grads(net, ws, batch, loss, norm_stats, adv_stats, vn_state, loss_out)
     if allreduce is not None:
         allreduce(net.grad)

@@ -83,6 +83,13 @@ class R_MAPPO():
                              UpdateWorkspace(self.policy.critic, key, self.gemm_mode))
         return self._ws[key]
 
+    def _invalidate_images(self):
+        """The weights may have changed since the last fused optimiser tail (checkpoint load, another trainer): the first
+        update of a train() / ppo_update() packs its weight image again."""
+        for pair in self._ws.values():
+            for ws in pair:
+                ws.image_ready = 0
+
     def _one_update(self, batch, n_rows, norm_stats, adv_stats, loss_out, update_actor, allreduce, only=None, prepared=False):
         """One optimiser step of both nets (`only`: just the "actor" / "critic" chain).  `prepared`: the workspaces already
         hold the normalised input rows of this batch (hidden >= 128 nets, later epochs over the same rows)."""
@@ -269,6 +276,7 @@ class R_MAPPO():
         dev = self.device
         T, E = buffer.episode_length, buffer._E
         B = T * E
+        self._invalidate_images()
         if allreduce == "auto":
             allreduce = _dist_allreduce()
             if allreduce is not None:
@@ -433,6 +441,7 @@ class R_MAPPO():
         scalars; `imp_weights` is the mean ratio as a 1-element tensor (its only use is `.mean()`, :217)."""
         lib = _lib.load()
         batch, keep, ret, active = self._sample_batch(sample)
+        self._invalidate_images()
         allreduce = _dist_allreduce()
         stats = torch.zeros(4, dtype=torch.float64, device=self.device)
         check(lib.mappo_minibatch_stats(ptr(ret), ptr(active), None, batch.n_rows, ptr(stats), stream_ptr()))

@@ -143,3 +143,36 @@ def test_tf32_ctas_with_several_tiles_match_the_fp32_build(monkeypatch):
         _grad_check(res["tf32"][1][key], want, f"{key}")
     for k in ("value_loss", "dist_entropy", "ratio", "actor_grad_norm", "critic_grad_norm"):
         assert_close(res["tf32"][0][k], res["fp32"][0][k], 1e-2, 1e-6, k)
+
+
+@pytest.mark.parametrize("name", ["c1_mlp_discrete", "c2_mlp_n128"])
+def test_fused_optimiser_tail_is_bit_identical_to_the_separate_launches(name, monkeypatch):
+    """mappo_update_tail (one 8-CTA cluster launch: slot sum -> unfold -> clip + Adam -> next weight image) against the four
+    launches it replaces, over a full train() (several epochs, so the re-used weight image is exercised): every weight, both
+    Adam moments, the step counts and the train_info sums must be identical to the last bit."""
+    g = Golden(name)
+    cfg = g.cfg
+    res = {}
+    for fused in ("0", "1"):
+        monkeypatch.setenv("MAPPO_B200_FUSED_TAIL", fused)
+        args, policy, trainer, buf = TP.build(cfg, g)
+        feed = g.feed(0)
+        TP.warm(buf, feed)
+        _collect_fp32(monkeypatch, cfg, policy, trainer, buf, feed, g.get("it0/noise"))
+        monkeypatch.setattr(torch, "randperm", TP.FakeRandperm(g.get("it0/perms")))
+        info = trainer.train(buf)
+        ws_a, ws_c = next(iter(trainer._ws.values()))
+        assert ws_a.fused_tail == (fused == "1") and ws_c.fused_tail == (fused == "1")
+        state = {}
+        for nm, net, opt in (("actor", policy.actor, policy.actor_optimizer), ("critic", policy.critic, policy.critic_optimizer)):
+            state[nm + "/flat"] = net.flat.cpu().numpy().copy()
+            state[nm + "/grad"] = net.grad.cpu().numpy().copy()
+            state[nm + "/m"] = opt.exp_avg.cpu().numpy().copy()
+            state[nm + "/v"] = opt.exp_avg_sq.cpu().numpy().copy()
+            state[nm + "/step"] = opt.step_dev.cpu().numpy().copy()
+            state[nm + "/beta_pow"] = opt.beta_pow.cpu().numpy().copy()
+        res[fused] = (info, state)
+    for k, v in res["0"][1].items():
+        np.testing.assert_array_equal(res["1"][1][k], v, err_msg=k)
+    assert res["1"][0] == res["0"][0]
+    assert res["0"][1]["actor/step"][0] == cfg.ppo_epoch * cfg.num_mini_batch
