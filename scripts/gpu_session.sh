@@ -8,7 +8,7 @@ for st in $STAGES; do
   echo "=== stage $st $(date +%T)"
   case $st in
     newtests)
-      timeout 900 python -m pytest tests -m gpu -q -k "c5_h512 or c2_mlp_n128 or bignet or separated or tensorcore or clip_adam" -s 2>&1 | tail -120 > gpurun_out/s_newtests.log
+      timeout 900 python -m pytest tests -m gpu -q -k "c5_h512 or c2_mlp_n128 or bignet or separated or tensorcore or clip_adam or reference_scenario" -s 2>&1 | tail -120 > gpurun_out/s_newtests.log
       tail -40 gpurun_out/s_newtests.log ;;
     c5bench)
       timeout 900 python bench.py --config c5 --steps 3 --no-extras --cpu-iters 0 > gpurun_out/s_c5bench.json 2> gpurun_out/s_c5bench.err
@@ -28,6 +28,11 @@ for st in $STAGES; do
     bench)
       timeout 1200 python bench.py --steps 20 --warmup 5 > gpurun_out/s_bench.json 2> gpurun_out/s_bench.err
       tail -c 2500 gpurun_out/s_bench.json; tail -5 gpurun_out/s_bench.err ;;
+    fusedbench)
+      MAPPO_B200_FUSED_TAIL=1 timeout 600 python bench.py --steps 20 --warmup 5 --no-extras --cpu-iters 0 > gpurun_out/s_bench_fused.json 2> gpurun_out/s_bench_fused.err
+      tail -c 1500 gpurun_out/s_bench_fused.json; tail -3 gpurun_out/s_bench_fused.err
+      MAPPO_B200_FUSED_TAIL=0 timeout 600 python bench.py --steps 20 --warmup 5 --no-extras --cpu-iters 0 > gpurun_out/s_bench_unfused.json 2> gpurun_out/s_bench_unfused.err
+      tail -c 1500 gpurun_out/s_bench_unfused.json; tail -3 gpurun_out/s_bench_unfused.err ;;
     smoke)
       timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 ;;
     sanitizer)
