@@ -387,11 +387,17 @@ int32_t mappo_update_finish(const mappo_net_desc_t* desc, const float* params, c
  * bit 1 = mappo_clip_adam on `grad` (reading n_sumsq_blocks partials; 12 when bit 0 ran in the same launch) followed by the
  * folded weight image of the NEW parameters into `workspace` -- so the next mappo_update_fwd_bwd may be called with
  * mappo_loss_cfg_t.image_ready = 1 and launches no pack kernel.  Bit-identical to the separate calls.  A multi-GPU caller
- * runs stages = 1, its all-reduce of `grad`, then stages = 2.  workspace as for mappo_update_fwd_bwd / mappo_update_finish. */
+ * runs stages = 1, its all-reduce of `grad`, then stages = 2 -- or stages = 7: bit 2 puts the exchange INSIDE the launch
+ * (mappo_p2p_allreduce_f32's protocol, arguments and summation order: the local gradient is written at sym_offset_bytes of this
+ * rank's symmetric buffer, every rank sums all peers' copies into `grad`), so a data-parallel optimiser step is the update kernel
+ * plus this one launch.  peer_* / world / rank / round_dev as in mappo_p2p_allreduce_f32 (ignored unless bit 2 is set).
+ * workspace as for mappo_update_fwd_bwd / mappo_update_finish. */
 int32_t mappo_update_tail(const mappo_net_desc_t* desc, float* params, const float* grad_part, int32_t n_slots, float* grad,
                           float* exp_avg, float* exp_avg_sq, float* sumsq_part, int32_t n_sumsq_blocks, const float* lr_dev,
                           int32_t* step_dev, float eps, float max_grad_norm, int32_t use_max_grad_norm, double* grad_norm_out,
-                          double* beta_pow_dev, float* workspace, int32_t stages, void* stream);
+                          double* beta_pow_dev, float* workspace, int32_t stages, const void* const* peer_bufs,
+                          void* const* peer_signals, int32_t world, int32_t rank, int64_t sym_offset_bytes, uint32_t* round_dev,
+                          void* stream);
 int32_t mappo_grad_reduce(const float* grad_part, int32_t n_slots, int32_t n_params, float* grad,
                           float* sumsq_part, int32_t* n_sumsq_blocks_out, void* stream);
 /* Per-block sums of squares of an already reduced (e.g. all-reduced) gradient vector. */

@@ -92,7 +92,8 @@ int update_mlp_tc_slots(const NetDev& n, int n_rows, int sm_count);
 int update_mlp_tc_launch(const NetDev&, const float*, const BatchDev&, const LossDev&, const double*, const double*,
                          const float*, float*, int, double*, float*, cudaStream_t, bool image_ready);
 int update_mlp_tc_tail_launch(const NetDev&, const float*, int, float*, float*, float*, float*, float*, float*, int, const float*, int*,
-                              float, float, int, double*, double*, float*, int, cudaStream_t);
+                              float, float, int, double*, double*, float*, int, cudaStream_t, const void* const*, void* const*, int, int,
+                              long long, uint32_t*);
 int update_gru_slots(const NetDev& n, int n_rows, int seq_len, int sm_count);
 int64_t update_gru_workspace_floats(const NetDev& n, int n_rows);
 int update_gru_launch(const NetDev&, const float*, const BatchDev&, const LossDev&, const double*, const double*,
@@ -572,7 +573,9 @@ int32_t mappo_update_finish(const mappo_net_desc_t* desc, const float* params, c
 int32_t mappo_update_tail(const mappo_net_desc_t* desc, float* params, const float* grad_part, int32_t n_slots, float* grad,
                           float* exp_avg, float* exp_avg_sq, float* sumsq_part, int32_t n_sumsq_blocks, const float* lr_dev,
                           int32_t* step_dev, float eps, float max_grad_norm, int32_t use_max_grad_norm, double* grad_norm_out,
-                          double* beta_pow_dev, float* workspace, int32_t stages, void* stream) {
+                          double* beta_pow_dev, float* workspace, int32_t stages, const void* const* peer_bufs,
+                          void* const* peer_signals, int32_t world, int32_t rank, int64_t sym_offset_bytes, uint32_t* round_dev,
+                          void* stream) {
   int rc = validate_desc(desc);
   if (rc) return rc;
   if (!params || !grad || !sumsq_part || !workspace) { set_error("update_tail: NULL argument"); return MAPPO_ERR_INVALID; }
@@ -580,7 +583,8 @@ int32_t mappo_update_tail(const mappo_net_desc_t* desc, float* params, const flo
   if (desc->recurrent || !update_mlp_tc_supported(n)) { set_error("update_tail: built for the MAPPO_GEMM_TF32 hidden-64 MLP path only"); return MAPPO_ERR_UNSUPPORTED; }
   return update_mlp_tc_tail_launch(n, grad_part, n_slots, workspace + update_mlp_tc_workspace_floats(n), params, grad, exp_avg, exp_avg_sq,
                                    sumsq_part, n_sumsq_blocks, lr_dev, step_dev, eps, max_grad_norm, use_max_grad_norm, grad_norm_out,
-                                   beta_pow_dev, workspace, stages, (cudaStream_t)stream);
+                                   beta_pow_dev, workspace, stages, (cudaStream_t)stream, peer_bufs, peer_signals, world, rank,
+                                   (long long)sym_offset_bytes, round_dev);
 }
 
 int32_t mappo_update_grad_slots(const mappo_net_desc_t* desc, int32_t n_rows, int32_t gemm_mode) {

@@ -21,6 +21,7 @@
 // dW' accumulates in TMEM across the tiles of a CTA; at the end dW = dW' diag(gamma) + db' beta^T, db = dW'[:, one],
 // dgamma = colsum(dW' .* W), dbeta = W^T db'  (chain rule of the folding), written to the CTA's gradient slot.
 #include "net_tiles.cuh"
+#include "p2p.cuh"
 
 namespace mappo {
 
@@ -812,7 +813,9 @@ int update_mlp_tc_unfold_launch(const NetDev& n, const float* params, const floa
 // sums per element, tc_unfold_unit, clip_adam_kernel<1>, pack_tc_element): the result is bit-identical to the unfused
 // path, which tests/test_gpu_tensorcore.py asserts.
 // `stages`: bit 0 = slot sum + unfold (leaves grad + 12 partial sums of squares), bit 1 = clip + Adam + image (reads
-// sumsq_part[0 .. n_part)): a multi-GPU caller runs stage 1, its all-reduce, then stage 2.
+// sumsq_part[0 .. n_part)), bit 2 = the data-parallel exchange between the two (p2p_allreduce_kernel's protocol and summation
+// order inside this launch: the local gradient goes to this rank's symmetric buffer, signals cross NVLink, every rank sums all
+// peers' copies in rank order) -- a multi-GPU optimiser step is then the update kernel plus THIS launch.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kTailCtas = 8, kTailThreads = 1024, kTailUnits = kTailCtas * (kTailThreads / 256), kTailUnroll = 3;
 struct TailArgs {
@@ -825,6 +828,9 @@ struct TailArgs {
   double* norm_out; double* beta_pow;
   float* image;                        // folded tf32 weight image (NULL: not rebuilt)
   int stages;
+  P2PArgs peers;                       // stage bit 2: symmetric buffers / signal pads of all ranks
+  long long sym_offset_bytes;          // where the local gradient sits inside every rank's symmetric buffer
+  uint32_t* round_dev;                 // {completed round, -, error flag, -} of this reducer
 };
 
 __device__ __forceinline__ void cluster_sync_all() {
@@ -886,12 +892,84 @@ __global__ void __cluster_dims__(kTailCtas, 1, 1) __launch_bounds__(kTailThreads
     }
     cluster_sync_all();
     // ---- unfold: the 12 (bx, by) units of tc_unfold_kernel's grid (4, 3)
-    tc_unfold_unit(a.n, a.p, a.raw_sum, a.grad, a.sumsq_part, unit & 3, unit >> 2, 4, t, unit < 12, us[sub]);
+    float* g_local = (a.stages & 4) ? reinterpret_cast<float*>(const_cast<char*>(static_cast<const char*>(a.peers.buf[a.peers.rank])) + a.sym_offset_bytes)
+                                    : a.grad;
+    tc_unfold_unit(a.n, a.p, a.raw_sum, g_local, a.sumsq_part, unit & 3, unit >> 2, 4, t, unit < 12, us[sub]);
     cluster_sync_all();
+  }
+  int n_part_x = 0;
+  if (a.stages & 4) {
+    // ---- all-reduce over peer memory (p2p_allreduce_kernel<float>: arrive, wait, sum in rank order, per-block sum of squares)
+    __shared__ uint32_t s_round;
+    if (tid == 0) s_round = a.round_dev[0] + 1;
+    __syncthreads();
+    const uint32_t round = s_round;
+    if (cta == 0 && tid < a.peers.world) {
+      __threadfence_system();
+      st_release_sys(a.peers.sig[tid] + a.peers.rank, round);
+    }
+    if (tid < a.peers.world) {
+      const uint32_t* mine = a.peers.sig[a.peers.rank] + tid;
+      const long long t0 = clock64();
+      while ((int)(ld_acquire_sys(mine) - round) < 0) {
+        if (clock64() - t0 > 8000000000LL) { atomicExch(a.round_dev + 2, 1u + (uint32_t)tid); break; }
+      }
+    }
+    __syncthreads();
+    // virtual grid of the stand-alone kernel: `blocks` CTAs of 256 threads, unit u plays CTA u (blocks <= 32 here: P <= 32 K)
+    const int n = P;
+    int blocks = (n / 4 + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > kTailUnits) blocks = kTailUnits;
+    n_part_x = blocks;
+    float sq = 0.f;
+    if (unit < blocks) {
+      const int vt = unit * 256 + t, nt = blocks * 256;
+      if ((n & 3) == 0 && (a.sym_offset_bytes & 15) == 0) {
+        for (int i = vt; i < n / 4; i += nt) {
+          float4 v[kMaxPeers];
+#pragma unroll
+          for (int q = 0; q < kMaxPeers; ++q)
+            if (q < a.peers.world)
+              v[q] = ld_peer4(reinterpret_cast<const float*>(static_cast<const char*>(a.peers.buf[q]) + a.sym_offset_bytes) + 4 * i);
+          float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int q = 0; q < kMaxPeers; ++q)
+            if (q < a.peers.world) { sum.x += v[q].x; sum.y += v[q].y; sum.z += v[q].z; sum.w += v[q].w; }
+          reinterpret_cast<float4*>(a.grad)[i] = sum;
+          sq = fmaf(sum.x, sum.x, fmaf(sum.y, sum.y, fmaf(sum.z, sum.z, fmaf(sum.w, sum.w, sq))));
+        }
+      } else {
+        for (int i = vt; i < n; i += nt) {
+          float v[kMaxPeers];
+#pragma unroll
+          for (int q = 0; q < kMaxPeers; ++q)
+            if (q < a.peers.world) v[q] = ld_peer<float>(reinterpret_cast<const float*>(static_cast<const char*>(a.peers.buf[q]) + a.sym_offset_bytes) + i);
+          float sum = 0.f;
+#pragma unroll
+          for (int q = 0; q < kMaxPeers; ++q)
+            if (q < a.peers.world) sum += v[q];
+          a.grad[i] = sum;
+          sq = fmaf(sum, sum, sq);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if ((tid & 31) == 0) us[sub].sred[t >> 5] = sq;
+    __syncthreads();
+    if (t == 0 && unit < blocks) {
+      float tot = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) tot += us[sub].sred[q];
+      a.sumsq_part[unit] = tot;
+    }
+    cluster_sync_all();
+    if (gtid == 0) a.round_dev[0] = round;              // every CTA of this launch has read the old value
   }
   if (a.stages & 2) {
     // ---- clip_grad_norm_ + Adam (clip_adam_kernel<1>: the scalar prologue in one warp of every CTA, fixed order)
-    const int n_part = (a.stages & 1) ? 12 : a.n_part;
+    const int n_part = (a.stages & 4) ? n_part_x : ((a.stages & 1) ? 12 : a.n_part);
     if (tid < 32) {
       double x = 0.0;
       for (int i = tid; i < n_part; i += 32) x += (double)a.sumsq_part[i];
@@ -936,7 +1014,9 @@ __global__ void __cluster_dims__(kTailCtas, 1, 1) __launch_bounds__(kTailThreads
 
 int update_mlp_tc_tail_launch(const NetDev& n, const float* part, int n_slots, float* raw_sum, float* params, float* grad, float* m,
                               float* v, float* sumsq_part, int n_part, const float* lr_dev, int* step_dev, float eps, float max_norm,
-                              int use_clip, double* norm_out, double* beta_pow, float* image, int stages, cudaStream_t st) {
+                              int use_clip, double* norm_out, double* beta_pow, float* image, int stages, cudaStream_t st,
+                              const void* const* peer_bufs, void* const* peer_signals, int world, int rank, long long sym_offset_bytes,
+                              uint32_t* round_dev) {
   if (!update_mlp_tc_supported(n)) { set_error("update_tail: the fused optimiser tail is built for the tcgen05 small-net path only"); return MAPPO_ERR_UNSUPPORTED; }
   if ((stages & 3) == 0 || ((stages & 1) && (!part || n_slots <= 0 || !raw_sum)) || ((stages & 2) && (!m || !v || !lr_dev || !step_dev)) ||
       ((stages & 3) == 2 && n_part <= 0)) { set_error("update_tail: bad arguments for stages %d", stages); return MAPPO_ERR_INVALID; }
@@ -944,6 +1024,16 @@ int update_mlp_tc_tail_launch(const NetDev& n, const float* part, int n_slots, f
   a.n = n; a.part = part; a.n_slots = n_slots; a.raw_sum = raw_sum; a.p = params; a.grad = grad; a.m = m; a.v = v;
   a.sumsq_part = sumsq_part; a.n_part = n_part; a.lr_dev = lr_dev; a.step_dev = step_dev; a.eps = eps; a.max_norm = max_norm;
   a.use_clip = use_clip; a.norm_out = norm_out; a.beta_pow = beta_pow; a.image = image; a.stages = stages;
+  memset(&a.peers, 0, sizeof(a.peers));
+  a.sym_offset_bytes = sym_offset_bytes; a.round_dev = round_dev;
+  if (stages & 4) {
+    if ((stages & 7) != 7) { set_error("update_tail: the exchange stage runs between stages 1 and 2 of the same launch (stages = 7)"); return MAPPO_ERR_INVALID; }
+    if (!peer_bufs || !peer_signals || !round_dev || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || (sym_offset_bytes & 3)) {
+      set_error("update_tail: bad peer arguments (world %d, rank %d)", world, rank); return MAPPO_ERR_INVALID;
+    }
+    for (int q = 0; q < world; ++q) { a.peers.buf[q] = peer_bufs[q]; a.peers.sig[q] = static_cast<uint32_t*>(peer_signals[q]); }
+    a.peers.world = world; a.peers.rank = rank;
+  }
   tc_tail_kernel<<<kTailCtas, kTailThreads, 0, st>>>(a);
   return check_launch("tc_tail_kernel");
 }

@@ -382,16 +382,19 @@ class UpdateWorkspace:
         self.image_ready = 0
 
 
-def _tail(net, ws, opt, stages, n_part, max_grad_norm, use_max_grad_norm, gn_ptr, grad):
+def _tail(net, ws, opt, stages, n_part, max_grad_norm, use_max_grad_norm, gn_ptr, grad, reducer=None, parity=0):
     lib = _lib.load()
     n_slots = ws._n_slots_last
+    peers = (None, None, 0, 0, 0, None)
+    if reducer is not None:
+        peers = (reducer.bufs, reducer.sigs, reducer.world, reducer.rank, 4 * reducer.off_grad[parity & 1], ptr(reducer.round))
     check(lib.mappo_update_tail(C.byref(net.desc), ptr(net.flat), ptr(ws.grad_part), n_slots, ptr(grad),
                                 None if opt is None else ptr(opt.exp_avg), None if opt is None else ptr(opt.exp_avg_sq),
                                 ptr(ws.sumsq_part), int(n_part), None if opt is None else ptr(opt.lr_dev),
                                 None if opt is None else ptr(opt.step_dev),
                                 0.0 if opt is None else float(opt.param_groups[0]["eps"]), float(max_grad_norm),
                                 int(bool(use_max_grad_norm)), gn_ptr, None if opt is None else ptr(opt.beta_pow),
-                                ptr(ws.workspace), int(stages), stream_ptr()))
+                                ptr(ws.workspace), int(stages), *peers, stream_ptr()))
 
 
 def make_loss_cfg(args, update_actor=True) -> LossCfg:
@@ -447,6 +450,18 @@ def launch_step(net: DeviceNet, ws: UpdateWorkspace, loss_out, opt: FusedAdam, m
     if n_sumsq_blocks > 0:
         opt.sumsq_part = ws.sumsq_part
     opt.apply(max_grad_norm, use_max_grad_norm, gn_ptr, n_sumsq_blocks=n_sumsq_blocks)
+
+
+def launch_update_p2p(net: DeviceNet, ws: UpdateWorkspace, batch: Batch, loss: LossCfg, norm_stats, adv_stats, vn_state,
+                      loss_out, opt: FusedAdam, max_grad_norm, use_max_grad_norm, grad_norm_slot: int, reducer, parity: int):
+    """Data-parallel optimiser step of one hidden-64 tcgen05 net as TWO launches: the update kernel, then the fused tail with
+    the peer-memory exchange inside it (slot sum -> unfold into the symmetric buffer -> signals over NVLink -> sum of all
+    ranks' gradients -> clip + Adam -> next weight image)."""
+    assert ws.fused_tail
+    launch_grads(net, ws, batch, loss, norm_stats, adv_stats, vn_state, loss_out, finish=False)
+    _tail(net, ws, opt, 7, 0, max_grad_norm, use_max_grad_norm, C.c_void_p(loss_out.data_ptr() + 8 * grad_norm_slot),
+          net.grad, reducer, parity)
+    ws.image_ready = 1
 
 
 def launch_update(net: DeviceNet, ws: UpdateWorkspace, batch: Batch, loss: LossCfg, norm_stats, adv_stats, vn_state,

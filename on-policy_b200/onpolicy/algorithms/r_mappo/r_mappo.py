@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from mappo_b200 import _lib
-from mappo_b200.core import (Batch, UpdateWorkspace, as_dev, check, launch_grads, launch_step, launch_update,
+from mappo_b200.core import (Batch, UpdateWorkspace, as_dev, check, launch_grads, launch_step, launch_update, launch_update_p2p,
                              make_loss_cfg, ptr, require_cuda, stream_ptr)
 from onpolicy.utils.valuenorm import ValueNorm
 
@@ -108,6 +108,11 @@ class R_MAPPO():
 
         def p2p_chain(k, net, ws, loss, a_stats, vn_state, opt, slot):
             r, par = self._p2p_nets[k], self._par[k]
+            if ws.fused_tail:             # update kernel + ONE tail launch with the exchange inside
+                launch_update_p2p(net, ws, batch, loss, norm_stats, a_stats, vn_state, loss_out, opt, self.max_grad_norm,
+                                  self._use_max_grad_norm, slot, r, par)
+                self._par[k] ^= 1
+                return
             launch_grads(net, ws, batch, loss, norm_stats, a_stats, vn_state, loss_out,
                          grad_out=r.grad_half(par)[:net.n_params])       # local gradient straight into the peer-visible half
             nb = r.allreduce_grad(par, net.grad, ws.sumsq_part)      # + the partial sums of squares clip_adam needs

@@ -122,3 +122,22 @@ def test_sharded_iteration_matches_reference(world, tmp_path):
     assert_close(z["vn"], g.get("it0/valuenorm"), 1e-4, 1e-8, "valuenorm")
     assert_close(z["actor2"], z["actor"], 1e-5, 1e-7, "graph replay vs eager")
     print(f"\n[multi] world {world}: iteration graph = {z['graph_kind']}, peer-memory all-reduce = {bool(z['p2p'])}")
+
+
+def test_fused_tail_with_the_exchange_inside_is_bit_identical(tmp_path, monkeypatch):
+    """2 ranks, tcgen05 build: the data-parallel optimiser step as update kernel + ONE tail launch (mappo_update_tail stages = 7,
+    peer-memory exchange inside the cluster kernel) against the separate finish / all-reduce / clip_adam launches -- weights
+    and train_info of the eager and the graph pass must be identical to the last bit."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    monkeypatch.setenv("MAPPO_B200_GEMM", "tf32")
+    res = {}
+    for fused in ("0", "1"):
+        monkeypatch.setenv("MAPPO_B200_FUSED_TAIL", fused)
+        out = str(tmp_path / f"f{fused}.npz")
+        mp.spawn(_worker, args=(2, 29700 + os.getpid() % 1000 + int(fused), out), nprocs=2, join=True)
+        res[fused] = np.load(out)
+    for k in ("actor", "critic", "info", "actor2", "critic2", "info2", "vn"):
+        np.testing.assert_array_equal(res["1"][k], res["0"][k], err_msg=k)
+    assert bool(res["1"]["p2p"])
