@@ -61,19 +61,26 @@ struct EpiFwd {
     if (a.stats_in && grow < a.n_rows) { const float2 st = a.stats_in[grow]; w.rs_in = st.y; w.c_in = st.x * st.y; }
     w.sum = 0.f; w.sumsq = 0.f;
   }
-  __device__ static void chunk(const Args& a, Thread& th, Row& w, const float* acc, const float* /*ain*/, float* out, int col0,
-                               const float* cv, float* /*scratch*/, int /*r*/, int /*grow*/) {
-    const float* s = cv + col0;
-    const float* b = cv + a.N + col0;
-    const bool rt = a.round_tf32 != 0;
+  // The activation and the tf32 rounding are compile-time inside the element loop (a run-time `act` makes the compiler evaluate
+  // tanhf for every element and select afterwards: 4x the instructions of the ReLU case).
+  template <int ACT, bool RT>
+  __device__ static __forceinline__ void chunk_t(Row& w, const float* acc, float* out, const float* s, const float* b) {
 #pragma unroll
     for (int j = 0; j < kChunk; ++j) {
       const float t = fmaf(-w.c_in, s[j], b[j]);
-      const float v = round_op(act_apply(fmaf(w.rs_in, acc[j], t), a.act), rt);
+      const float z = fmaf(w.rs_in, acc[j], t);
+      const float v = round_op(ACT == ACT_RELU ? fmaxf(z, 0.f) : tanhf(z), RT);
       w.sum += v;
       w.sumsq = fmaf(v, v, w.sumsq);
       out[j] = v;
     }
+  }
+  __device__ static void chunk(const Args& a, Thread& th, Row& w, const float* acc, const float* /*ain*/, float* out, int col0,
+                               const float* cv, float* /*scratch*/, int /*r*/, int /*grow*/) {
+    const float* s = cv + col0;
+    const float* b = cv + a.N + col0;
+    if (a.act == ACT_RELU) { if (a.round_tf32) chunk_t<ACT_RELU, true>(w, acc, out, s, b); else chunk_t<ACT_RELU, false>(w, acc, out, s, b); }
+    else { if (a.round_tf32) chunk_t<ACT_TANH, true>(w, acc, out, s, b); else chunk_t<ACT_TANH, false>(w, acc, out, s, b); }
   }
   __device__ static void end_row(const Args& a, Row& w, int grow) {
     if (grow >= a.n_rows) return;
@@ -117,21 +124,25 @@ struct EpiBwd {
     }
     w.S1 = 0.f; w.S2 = 0.f;
   }
-  __device__ static void chunk(const Args& a, Thread& th, Row& w, const float* acc, const float* ain, float* out, int col0,
-                               const float* cv, float* /*scratch*/, int /*r*/, int /*grow*/) {
-    const float* s = cv + col0;
-    const float* b = cv + a.N + col0;
-    const bool rt = a.round_tf32 != 0;
+  template <int ACT, bool RT>
+  __device__ static __forceinline__ void chunk_t(Row& w, const float* acc, const float* ain, float* out, const float* s, const float* b) {
 #pragma unroll
     for (int j = 0; j < kChunk; ++j) {
       const float av = ain[j];
       const float xh = (av - w.mu) * w.rs;
       const float dA = acc[j] - fmaf(xh, w.m2, w.m1);
-      const float p = round_op(dA * act_bwd(av, a.act) * w.rs_prev, rt);
+      const float p = round_op(dA * act_bwd(av, ACT) * w.rs_prev, RT);
       w.S1 = fmaf(p, s[j], w.S1);
-      w.S2 = fmaf(p, act_inverse(av, a.act) - b[j], w.S2);
+      w.S2 = fmaf(p, act_inverse(av, ACT) - b[j], w.S2);
       out[j] = p;
     }
+  }
+  __device__ static void chunk(const Args& a, Thread& th, Row& w, const float* acc, const float* ain, float* out, int col0,
+                               const float* cv, float* /*scratch*/, int /*r*/, int /*grow*/) {
+    const float* s = cv + col0;
+    const float* b = cv + a.N + col0;
+    if (a.act == ACT_RELU) { if (a.round_tf32) chunk_t<ACT_RELU, true>(w, acc, ain, out, s, b); else chunk_t<ACT_RELU, false>(w, acc, ain, out, s, b); }
+    else { if (a.round_tf32) chunk_t<ACT_TANH, true>(w, acc, ain, out, s, b); else chunk_t<ACT_TANH, false>(w, acc, ain, out, s, b); }
   }
   __device__ static void end_row(const Args& a, Row& w, int grow) {
     if (grow >= a.n_rows || !a.mprime_out) return;

@@ -46,7 +46,9 @@ big_lin_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                const typename Epi::Args ea, const LinShape sh) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ double sred[2 * 32];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by pointer arithmetic on the shared array (an integer round trip would make every later access a
+  // generic LD / ST instead of LDS / STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int BN = sh.BN, NT = sh.N / sh.BN, KB = (sh.K + 31) / 32, NST = sh.n_stages;
   const LinSmem L = make_lin_smem(BN, NST, sh.N, Epi::kNeedsScratch);
@@ -221,7 +223,7 @@ big_grad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint64_t full[kGradStages], empty[kGradStages], done;
   __shared__ uint32_t tmem_slot;
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int unit = blockIdx.x;
   const int split = unit / (sh.m_tiles * sh.n_tiles), rem = unit % (sh.m_tiles * sh.n_tiles);
