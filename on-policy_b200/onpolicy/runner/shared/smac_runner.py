@@ -157,7 +157,10 @@ class SMACRunner(Runner):
                     if eval_infos[eval_i][0]["won"]:
                         eval_battles_won += 1
             if eval_episode >= self.all_args.eval_episodes:
-                self.log_env({"eval_average_episode_rewards": np.array(eval_episode_rewards)}, total_num_steps)
+                # (two threads finishing in the same step leave a 0-d entry next to [n, M, 1] ones -- the reference's list is
+                #  ragged in exactly the same way, which NumPy >= 1.24 refuses to stack: flatten before averaging)
+                flat = np.concatenate([np.asarray(x, dtype=np.float64).reshape(-1) for x in eval_episode_rewards])
+                self.log_env({"eval_average_episode_rewards": flat}, total_num_steps)
                 eval_win_rate = eval_battles_won / eval_episode
                 print("eval win rate is {}.".format(eval_win_rate))
                 self._log("eval_win_rate", eval_win_rate, total_num_steps)
