@@ -307,7 +307,9 @@ def test_clip_adam_matches_torch_adam(hidden, share):
         net.grad.copy_(gcpu)
         norm_out.zero_()
         mine.apply(10.0, True, norm_out.data_ptr())
-        assert_close(norm_out.item(), float(total), 1e-5, 1e-7, "grad norm")
+        # torch's fp32 CPU norm of 0.93 M elements is itself 1e-5 low against float64; ours is pairwise per 256 + fp64 on top
+        assert_close(norm_out.item(), float(total), 3e-5, 1e-7, "grad norm")
+        assert_close(norm_out.item(), float(gcpu.double().norm()), 2e-6, 1e-7, "grad norm against float64")
         assert_close(net.flat.cpu().numpy(), ref.detach().numpy(), 1e-4, 5e-7, f"params after step {step}")
 
 
