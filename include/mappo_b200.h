@@ -203,6 +203,9 @@ int32_t mappo_debug_big_lin(const float* A, int32_t lda, const float* W, int32_t
 int32_t mappo_debug_big_grad(const float* P, int32_t ldp, int32_t Pw, int32_t M, const float* Q, int32_t ldq, int32_t Qw, int32_t rows,
                              float* partial, float* gsum, int32_t gemm_mode, void* stream);
 int32_t mappo_debug_big_grad_splits(int32_t rows, int32_t M, int32_t Pw, int32_t Qw);
+/* Diagnostic: float offsets of the regions of a hidden >= 128 net's update workspace for n_rows rows (64 values, host pointer;
+ * layout in csrc/big_net.cu debug_plan) -- scripts/diag_big.py checks the stored intermediates against float64 algebra. */
+int32_t mappo_debug_big_plan(const mappo_net_desc_t* desc, int32_t n_rows, int64_t* out64);
 int64_t mappo_rollout_workspace_floats(const mappo_net_desc_t* desc, int32_t n_rows);
 int32_t mappo_pack_rollout_weights_ex(const mappo_net_desc_t* desc, const float* params, float* image, int32_t gemm_mode,
                                       void* stream);

@@ -128,6 +128,7 @@ int debug_lin(const float* A, int lda, const float* W, int ldw, float* out, floa
 int debug_grad(const float* P, int ldp, int Pw, int M, const float* Q, int ldq, int Qw, int rows, float* partial, float* gsum,
                bool tf32, int sm, cudaStream_t st);
 int debug_grad_splits(int rows, int M, int Pw, int Qw, int sm);
+int debug_plan(const NetDev& n, int rows, int sm, long long* out);
 int64_t workspace_floats(const NetDev& n, int rows, int sm);
 int pack_launch(const NetDev& n, const float* params, float* ws, int rows, bool round_tf32, int sm, cudaStream_t st);
 int update_launch(const NetDev& n, const float* params, const BatchDev& b, const LossDev& L, const double* norm_stats,
@@ -339,6 +340,14 @@ int32_t mappo_debug_big_grad(const float* P, int32_t ldp, int32_t Pw, int32_t M,
   return big::debug_grad(P, ldp, Pw, M, Q, ldq, Qw, rows, partial, gsum, gemm_mode == MAPPO_GEMM_TF32, sm_count(), (cudaStream_t)stream);
 }
 int32_t mappo_debug_big_grad_splits(int32_t rows, int32_t M, int32_t Pw, int32_t Qw) { return big::debug_grad_splits(rows, M, Pw, Qw, sm_count()); }
+int32_t mappo_debug_big_plan(const mappo_net_desc_t* desc, int32_t n_rows, int64_t* out64) {
+  int rc = validate_desc(desc);
+  if (rc) return rc;
+  if (!out64) { set_error("debug_big_plan: NULL output"); return MAPPO_ERR_INVALID; }
+  const NetDev n = make_net_dev(desc);
+  if (!big::supported(n)) { set_error("debug_big_plan: not a hidden >= 128 MLP"); return MAPPO_ERR_UNSUPPORTED; }
+  return big::debug_plan(n, n_rows, sm_count(), reinterpret_cast<long long*>(out64));
+}
 
 int32_t mappo_big_net(const mappo_net_desc_t* desc) {
   if (validate_desc(desc)) return 0;

@@ -26,11 +26,13 @@ int grad_reduce_launch(const float*, int, int, float*, float*, int*, cudaStream_
 namespace big {
 
 constexpr int kMaxMat = kMaxLayers + 1;      // hidden matrices: fc1, fc2[0..layer_N)
+constexpr int kUnfY = 16;                    // output-row groups of the unfold grid
 
 struct Plan {
   int H, Hx, Lh, in_dim, K0p, rows, n_heads_pad;
   size_t wf[kMaxMat], wft[kMaxMat], cv[kMaxMat], whf, whft, cvh, pack_total;
   size_t x0, act[kMaxMat + 1], stats[kMaxMat + 1], mprime[kMaxMat + 1], P[2], Ph, partial, gsum, scratch, total;
+  size_t unf_part, unf_ticket;           // big_unfold_kernel: [2][kUnfY][1024] column partials, 64 int tickets (zeroed by the pack kernel)
   size_t partial_floats;
 };
 
@@ -117,6 +119,7 @@ static Plan make_plan(const NetDev& n, int rows, int sm) {
   p.whf = o; o = align64(o + 32 * (size_t)p.H);
   p.whft = o; o = align64(o + 32 * (size_t)p.H);
   p.cvh = o; o = align64(o + 64);
+  p.unf_ticket = o; o = align64(o + 64);
   p.pack_total = o;
   const size_t R = (size_t)((rows + 127) / 128) * 128;
   p.x0 = o; o = align64(o + R * p.K0p);
@@ -139,12 +142,27 @@ static Plan make_plan(const NetDev& n, int rows, int sm) {
   p.partial_floats = pf;
   p.partial = o; o = align64(o + pf);
   p.gsum = o; o = align64(o + gs);
+  p.unf_part = o; o = align64(o + 2 * kUnfY * 1024);
   p.scratch = o; o = align64(o + R * p.H);
   p.total = o;
   return p;
 }
 
 int64_t workspace_floats(const NetDev& n, int rows, int sm) { return (int64_t)make_plan(n, rows, sm).total; }
+
+// diagnostic: float offsets of the workspace regions (scripts/diag_big.py compares the stored intermediates with float64 algebra)
+//   out[0..7] = H, Hx, Lh, K0p, x0, P0, P1, Ph;  out[8] = partial, out[9] = gsum, out[10] = whf, out[11] = whft, out[12] = cvh;
+//   out[16 + 4 l + {0,1,2}] = act[l], stats[l], mprime[l] (l = 1..Lh);  out[40 + 3 i + {0,1,2}] = wf[i], wft[i], cv[i]
+int debug_plan(const NetDev& n, int rows, int sm, long long* out) {
+  const Plan p = make_plan(n, rows, sm);
+  for (int i = 0; i < 64; ++i) out[i] = -1;
+  out[0] = p.H; out[1] = p.Hx; out[2] = p.Lh; out[3] = p.K0p; out[4] = (long long)p.x0; out[5] = (long long)p.P[0]; out[6] = (long long)p.P[1];
+  out[7] = (long long)p.Ph; out[8] = (long long)p.partial; out[9] = (long long)p.gsum; out[10] = (long long)p.whf; out[11] = (long long)p.whft;
+  out[12] = (long long)p.cvh;
+  for (int l = 1; l <= p.Lh; ++l) { out[16 + 4 * l] = (long long)p.act[l]; out[17 + 4 * l] = (long long)p.stats[l]; out[18 + 4 * l] = (long long)p.mprime[l]; }
+  for (int i = 0; i < p.Lh; ++i) { out[40 + 3 * i] = (long long)p.wf[i]; out[41 + 3 * i] = (long long)p.wft[i]; out[42 + 3 * i] = (long long)p.cv[i]; }
+  return MAPPO_OK;
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // small kernels
@@ -153,13 +171,14 @@ struct PackArgs {
   int H, Lh, in_dim, K0p, Atot, round_tf32;
   int w_off[kMaxMat], b_off[kMaxMat], gam_off[kMaxMat + 1], bet_off[kMaxMat + 1];   // flat-parameter offsets (-1 = identity LN)
   int hw_off, hb_off;
-  long long wf[kMaxMat], wft[kMaxMat], cv[kMaxMat], whf, whft, cvh;
+  long long wf[kMaxMat], wft[kMaxMat], cv[kMaxMat], whf, whft, cvh, ticket;
 };
 
 // one warp per output row of each folded matrix: W' = W diag(gamma_in), b' = b + W beta_in, s = rowsum(W')
 __global__ void __launch_bounds__(256) big_pack_kernel(const PackArgs a, const float* __restrict__ p, float* __restrict__ ws) {
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int n_rows_total = a.Lh * a.H + 32;
+  if (blockIdx.x == 0 && threadIdx.x < 64) reinterpret_cast<int*>(ws + a.ticket)[threadIdx.x] = 0;     // big_unfold_kernel's tickets
   if (gw >= n_rows_total) return;
   const bool rt = a.round_tf32 != 0;
   if (gw < a.Lh * a.H) {
@@ -253,38 +272,75 @@ __global__ void __launch_bounds__(256) big_featnorm_kernel(const float* __restri
   }
 }
 
-// hidden matrix i: gsum[o][ldq] -> dW, db, d gamma_in, d beta_in     (chain rule of the folding, header of big_epi.cuh)
-//   first (explicit input): dW' = G[:, :K], db' = G[:, K];  else dW' = G[:, :H] - G[:, H], db' = G[:, H + 1]
-__global__ void __launch_bounds__(256) big_unfold_kernel(const float* __restrict__ gsum, int ldq, const float* __restrict__ p, float* __restrict__ g,
-                                                         int H, int K, int first, int w_off, int b_off, int gam_off, int bet_off) {
+// hidden matrix i: the row-split partials of G[o][ldq] -> dW, db, d gamma_in, d beta_in   (chain rule of the folding, header of
+// big_epi.cuh).   first (explicit input): dW' = G[:, :K], db' = G[:, K];  else dW' = G[:, :H] - G[:, H], db' = G[:, H + 1].
+// Grid (K / 32, kUnfY): a CTA owns 32 input features x H / kUnfY output rows and sums the `splits` partials itself (in split
+// order) -- no separate slot-sum launch, no summed copy of G.  The LayerNorm column sums cross the kUnfY row groups through
+// `part`; the last CTA of a column block to arrive (ticket) adds them in row-group order, so the result is reproducible.
+__global__ void __launch_bounds__(256) big_unfold_kernel(const float* __restrict__ partial, int splits, int ldq, const float* __restrict__ p,
+                                                         float* __restrict__ g, int H, int K, int first, int w_off, int b_off, int gam_off,
+                                                         int bet_off, float* part, int* tickets) {
   __shared__ float pg[8][33], pb[8][33];
+  __shared__ int s_last;
   const int kx = threadIdx.x & 31, og = threadIdx.x >> 5;
-  const int k = blockIdx.x * 32 + kx;
+  const int k = blockIdx.x * 32 + kx, y = blockIdx.y;
+  const int rows_y = H / kUnfY, o0 = y * rows_y;
   const int ucol = first ? -1 : H, bcol = first ? K : H + 1;
+  const size_t slot = (size_t)H * ldq;
   const float gam = (gam_off >= 0 && k < K) ? p[gam_off + k] : 1.f, bet = (bet_off >= 0 && k < K) ? p[bet_off + k] : 0.f;
   float sg = 0.f, sb = 0.f;
-  if (k < K) {
-    for (int o = og; o < H; o += 8) {
-      const float* G = gsum + (size_t)o * ldq;
-      const float dbp = G[bcol];
-      const float dwf = G[k] - (ucol >= 0 ? G[ucol] : 0.f);
+  for (int o = o0 + og; o < o0 + rows_y; o += 8) {
+    const float* G = partial + (size_t)o * ldq;
+    // four independent partial sums over the splits (12 loads in flight), combined in a fixed order
+    float d4[4] = {0.f, 0.f, 0.f, 0.f}, u4[4] = {0.f, 0.f, 0.f, 0.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
+    int s = 0;
+    for (; s + 3 < splits; s += 4) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (k < K) d4[q] += G[(s + q) * slot + k];
+        if (ucol >= 0) u4[q] += G[(s + q) * slot + ucol];
+        b4[q] += G[(s + q) * slot + bcol];
+      }
+    }
+    for (; s < splits; ++s) {
+      if (k < K) d4[0] += G[s * slot + k];
+      if (ucol >= 0) u4[0] += G[s * slot + ucol];
+      b4[0] += G[s * slot + bcol];
+    }
+    const float dbp = (b4[0] + b4[1]) + (b4[2] + b4[3]);
+    const float dwf = ((d4[0] + d4[1]) + (d4[2] + d4[3])) - ((u4[0] + u4[1]) + (u4[2] + u4[3]));
+    if (k < K) {
       const float w = p[w_off + (size_t)o * K + k];
       g[w_off + (size_t)o * K + k] = fmaf(dbp, bet, dwf * gam);
       sg = fmaf(dwf, w, sg);
       sb = fmaf(dbp, w, sb);
     }
+    if (blockIdx.x == 0 && kx == 0) g[b_off + o] = dbp;
   }
+  if (gam_off < 0) return;                                // no LayerNorm in front of this matrix (uniform over the grid)
   pg[og][kx] = sg; pb[og][kx] = sb;
   __syncthreads();
-  if (og == 0 && k < K && gam_off >= 0) {
+  if (og == 0) {
     float a = 0.f, c = 0.f;
 #pragma unroll
     for (int q = 0; q < 8; ++q) { a += pg[q][kx]; c += pb[q][kx]; }
+    part[(size_t)y * 1024 + k] = a;
+    part[(size_t)(kUnfY + y) * 1024 + k] = c;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(tickets + blockIdx.x, 1) == kUnfY - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (og == 0 && k < K) {
+    float a = 0.f, c = 0.f;
+#pragma unroll
+    for (int q = 0; q < kUnfY; ++q) { a += __ldcg(part + (size_t)q * 1024 + k); c += __ldcg(part + (size_t)(kUnfY + q) * 1024 + k); }
     g[gam_off + k] = a;
     g[bet_off + k] = c;
   }
-  if (blockIdx.x == 0)
-    for (int o = threadIdx.x; o < H; o += 256) g[b_off + o] = gsum[(size_t)o * ldq + bcol];
+  if (threadIdx.x == 0) tickets[blockIdx.x] = 0;          // ready for the next launch
 }
 
 // heads: gsum[k][32] (k over the extended activation row) -> dWh, dbh, d gamma_L, d beta_L
@@ -335,7 +391,7 @@ static PackArgs make_pack_args(const NetDev& n, const Plan& pl, bool round_tf32)
     a.bet_off[i] = i == 0 ? (n.use_fn ? n.g.fn_b : -1) : (i == 1 ? n.g.ln1_b : n.g.ln2_b[i - 2]);
   }
   a.hw_off = n.g.head_w; a.hb_off = n.g.head_b;
-  a.whf = (long long)pl.whf; a.whft = (long long)pl.whft; a.cvh = (long long)pl.cvh;
+  a.whf = (long long)pl.whf; a.whft = (long long)pl.whft; a.cvh = (long long)pl.cvh; a.ticket = (long long)pl.unf_ticket;
   return a;
 }
 
@@ -382,7 +438,7 @@ static int run_forward(const NetDev& n, const Plan& pl, float* ws, const float* 
 }
 
 static int run_grad(const Plan& pl, float* ws, const float* P, int ldp, int Pw, int M, const float* Q, int ldq_in, int Qw, int rows, bool tf32,
-                    int sm, cudaStream_t st) {
+                    int sm, cudaStream_t st, int* splits_out = nullptr) {
   if (Qw > 3 * 256 + 288) { set_error("big net: gradient GEMM operand %d columns wide", Qw); return MAPPO_ERR_UNSUPPORTED; }
   const GradShape g = make_grad_shape(rows, M, Pw, Qw, sm);
   if ((size_t)g.splits * M * g.ldq > pl.partial_floats) { set_error("big net: gradient partial buffer too small"); return MAPPO_ERR_INVALID; }
@@ -392,6 +448,7 @@ static int run_grad(const Plan& pl, float* ws, const float* P, int ldp, int Pw, 
     rc = tf32 ? grad_gemm_launch(P, ldp, Q, ldq_in, ws + pl.partial, g, st) : ref_grad_gemm_launch(P, ldp, Q, ldq_in, ws + pl.partial, g, st);
   }
   if (rc) return rc;
+  if (splits_out) { *splits_out = g.splits; return MAPPO_OK; }     // the consumer sums the partials itself
   Timed tm(T_FINISH, st);
   return grad_reduce_launch(ws + pl.partial, g.splits, M * g.ldq, ws + pl.gsum, nullptr, nullptr, st);
 }
@@ -470,13 +527,15 @@ int update_launch(const NetDev& n, const float* params, const BatchDev& b, const
     const int i = l - 1;
     const float* Q = i == 0 ? ws + pl.x0 : ws + pl.act[i];
     const int ldq = i == 0 ? pl.K0p : pl.Hx;
-    rc = run_grad(pl, ws, Pl, pl.H, pl.H, pl.H, Q, ldq, ldq, rows, tf32, sm, st);
+    int splits = 1;
+    rc = run_grad(pl, ws, Pl, pl.H, pl.H, pl.H, Q, ldq, ldq, rows, tf32, sm, st, &splits);
     if (rc) return rc;
     const int K = i == 0 ? n.in_dim : pl.H;
     {
       Timed tm(T_FINISH, st);
-      big_unfold_kernel<<<(K + 31) / 32, 256, 0, st>>>(ws + pl.gsum, ldq, params, grad, pl.H, K, i == 0 ? 1 : 0, pa.w_off[i], pa.b_off[i],
-                                                      pa.gam_off[i], pa.bet_off[i]);
+      big_unfold_kernel<<<dim3((K + 31) / 32, kUnfY), 256, 0, st>>>(ws + pl.partial, splits, ldq, params, grad, pl.H, K, i == 0 ? 1 : 0,
+                                                                   pa.w_off[i], pa.b_off[i], pa.gam_off[i], pa.bet_off[i],
+                                                                   ws + pl.unf_part, reinterpret_cast<int*>(ws + pl.unf_ticket));
       rc = check_launch("big_unfold_kernel");
     }
     if (rc) return rc;

@@ -86,6 +86,7 @@ _SIGS = {
     "mappo_gather_rows": (_i32, [_P, _P, _i32, _i32, _P, _P]),
     "mappo_chunk_rows": (_i32, [_P, _i32, _i32, _i32, _i32, _P, _P, _P]),
     "mappo_randperm": (_i32, [_i32, _u64, _P, _P, _P]),
+    "mappo_debug_big_plan": (_i32, [C.POINTER(NetDesc), _i32, _P]),
     "mappo_update_tail": (_i32, [C.POINTER(NetDesc), _P, _P, _i32, _P, _P, _P, _P, _i32, _P, _P, _f32, _f32, _i32, _P, _P, _P, _i32, _P, _P, _i32, _i32, _i64, _P, _P]),
     "mappo_update_workspace_floats": (_i64, [C.POINTER(NetDesc), _i32, _i32]),
     "mappo_update_grad_slots": (_i32, [C.POINTER(NetDesc), _i32, _i32]),

@@ -87,3 +87,36 @@ def assert_close(a, b, rtol, atol, what=""):
         i = np.unravel_index(np.argmax(err - tol), err.shape)
         raise AssertionError(f"{what}: max violation at {i}: got {a[i]!r} want {b[i]!r} "
                              f"(|err|={err[i]:.3e}, tol={tol[i]:.3e}); max|err|={err.max():.3e}")
+
+
+def grad_agreement(got, want, key, smooth, tf32, report=None):
+    """Agreement of one gradient tensor with the reference, as (ok, relative L2 error).
+
+    Smooth (tanh) nets: every element within a |ref| + b max|ref| (fp32 build a 2e-3, b 1e-4; tcgen05 / tf32 build a = b = 5e-3;
+    LayerNorm affine parameters b x 10-20: in the hidden >= 128 pipeline they are contractions of the folded weight gradients with
+    the weights -- sums of H signed terms that largely cancel -- so they carry the weight gradients' absolute error at a smaller scale).
+
+    ReLU nets: a unit whose pre-activation is within rounding distance of zero is on for one implementation and off for the other (the
+    reference's own CPU and GPU runs differ the same way).  One such flip changes that unit's row of dW by its whole contribution of
+    one sample, i.e. ~1/sqrt(active rows) of the row's scale -- 2-9 % here -- so the element-wise maximum is not a usable metric.
+    Measured on the B200 (scripts/diag_big.py): every stored intermediate of the pipeline agrees with float64 algebra on ITS OWN inputs
+    to 1e-6 (fp32 build) / 3e-4 (tf32), the flips are the entire difference.  Criteria: relative L2 error of the tensor
+    (fp32 1e-2, tf32 4e-2) and at most 5 % of the elements outside the smooth-net tolerance."""
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    scale = np.abs(want).max() + 1e-300
+    err = np.abs(got - want)
+    ln = "feature_norm" in key or ".2." in key or "norm" in key
+    if tf32:
+        tol = 5e-3 * np.abs(want) + (5e-2 if ln else 5e-3) * scale
+    else:
+        tol = 2e-3 * np.abs(want) + (2e-3 if ln else 1e-4) * scale
+    l2 = float(np.linalg.norm(got - want) / (np.linalg.norm(want) + 1e-300))
+    outside = float((err > tol).mean())
+    if smooth:
+        ok = outside == 0.0
+    else:
+        ok = l2 <= (4e-2 if tf32 else 1e-2) and outside <= 0.05
+    if report is not None:
+        report.append(f"{key}: max err / scale {err.max() / scale:.3e}, rel L2 {l2:.3e}, outside element tolerance {100 * outside:.2f} %"
+                      + ("" if ok else "  <-- FAIL"))
+    return ok, l2
