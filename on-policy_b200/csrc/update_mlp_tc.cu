@@ -181,14 +181,15 @@ __host__ __device__ inline TcRaw make_tc_raw(const TcImage& m) {
 // == false: the unit only takes part in the barriers (tc_tail_kernel runs four units per CTA, not all of them populated).
 struct UnfoldScratch { float part_g[16][17], part_b[16][17], sred[8]; };
 __device__ __forceinline__ void tc_unfold_unit(const NetDev& n, const float* p, const float* raw, float* g, float* sumsq_part,
-                                               int bx, int by, int grid_x, int tid, bool active, UnfoldScratch& S) {
+                                               int bx, int by, int grid_x, int tid, bool active, UnfoldScratch& S,
+                                               float* g_mirror = nullptr) {
   const TcImage m = make_tc_image(n);
   const TcRaw R = make_tc_raw(m);
   const int kx = tid & 15, og = tid >> 4;
   const int sec = by, k = bx * 16 + kx;                 // for the heads (sec == 2) k < 64 always (grid_x == 4)
   const int in = n.in_dim, Atot = n.head_total;
   float sq = 0.f;
-  auto put = [&](int off, float v) { g[off] = v; sq = fmaf(v, v, sq); };
+  auto put = [&](int off, float v) { g[off] = v; if (g_mirror) g_mirror[off] = v; sq = fmaf(v, v, sq); };
   const int K = sec == 0 ? 64 : (sec == 1 ? in : 64);
   const bool fold = sec == 1 ? (n.use_fn != 0) : true;
   const int gam_off = sec == 0 ? n.g.ln1_w : (sec == 1 ? n.g.fn_w : n.g.ln2_w[0]);
@@ -805,25 +806,25 @@ int update_mlp_tc_unfold_launch(const NetDev& n, const float* params, const floa
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// The whole optimiser tail of one net as ONE launch: slot sum -> unfold (+ sum g^2) -> clip + Adam -> folded image of the NEW
-// weights for the next step's update kernel.  One thread-block cluster of 8 CTAs x 1024 threads; the stages are separated by
-// cluster barriers (release / acquire at cluster scope orders the global-memory hand-offs), so the four launches of the
-// unfused tail (grad_reduce, tc_unfold, clip_adam, next step's pack_tc) and the gaps between them collapse into one.
-// Every stage keeps the arithmetic AND the summation order of the kernel it replaces (grad_reduce_kernel's 8 x 4 partial
-// sums per element, tc_unfold_unit, clip_adam_kernel<1>, pack_tc_element): the result is bit-identical to the unfused
-// path, which tests/test_gpu_tensorcore.py asserts.
-// `stages`: bit 0 = slot sum + unfold (leaves grad + 12 partial sums of squares), bit 1 = clip + Adam + image (reads
-// sumsq_part[0 .. n_part)), bit 2 = the data-parallel exchange between the two (p2p_allreduce_kernel's protocol and summation
-// order inside this launch: the local gradient goes to this rank's symmetric buffer, signals cross NVLink, every rank sums all
-// peers' copies in rank order) -- a multi-GPU optimiser step is then the update kernel plus THIS launch.
+// The whole optimiser tail of one net as ONE launch: slot sum -> unfold (+ sum g^2) -> [all-reduce over peer memory] ->
+// clip + Adam -> folded image of the NEW weights for the next step's update kernel.
+// One thread-block cluster of 8 CTAs x 1024 threads does the only wide part, the sum of the n_slots raw gradient slots
+// (2.7 MB at c2), and delivers the result straight into the SHARED MEMORY of CTA 0 through distributed shared memory
+// (st.shared::cluster); after one cluster barrier CTA 0 finishes alone out of its own shared memory -- the summed raw
+// accumulators (43 KB), the gradient (42 KB) and the new parameters (42 KB) all fit -- so the unfold, the norm, Adam and the
+// re-pack are separated by __syncthreads only, with no further global-memory hand-off.
+// The arithmetic and every summation order are those of the kernels it replaces (grad_reduce_kernel's 8 x 4 partial sums per
+// element, tc_unfold_unit, clip_adam_kernel<1>, pack_tc_element, p2p_allreduce_kernel).
+// `stages`: bit 0 = slot sum + unfold (leaves grad + 12 partial sums of squares), bit 1 = clip + Adam + image (reading
+// sumsq_part[0 .. n_part) when bit 0 did not run in the same launch), bit 2 = the data-parallel exchange between the two
+// (only with both: 7) -- a multi-GPU optimiser step is then the update kernel plus THIS launch.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kTailCtas = 8, kTailThreads = 1024, kTailUnits = kTailCtas * (kTailThreads / 256), kTailUnroll = 3;
+constexpr int kTailCtas = 8, kTailThreads = 1024, kTailSubs = kTailThreads / 256, kTailUnits = kTailCtas * kTailSubs, kTailUnroll = 3;
 struct TailArgs {
   NetDev n;
   const float* part; int n_slots;      // raw gradient slots [n_slots][R]
-  float* raw_sum;                      // [R]
   float *p, *grad, *m, *v;             // flat parameters, gradient, Adam moments [P]
-  float* sumsq_part; int n_part;       // partial sums of squares (stage 1 writes 12; stage 2 reads n_part)
+  float* sumsq_part; int n_part;       // partial sums of squares (stage 1 alone writes 12; stage 2 alone reads n_part)
   const float* lr_dev; int* step_dev; float eps, max_norm; int use_clip;
   double* norm_out; double* beta_pow;
   float* image;                        // folded tf32 weight image (NULL: not rebuilt)
@@ -832,6 +833,16 @@ struct TailArgs {
   long long sym_offset_bytes;          // where the local gradient sits inside every rank's symmetric buffer
   uint32_t* round_dev;                 // {completed round, -, error flag, -} of this reducer
 };
+struct TailSmem { int raw, grad, par, total; };          // float offsets inside the dynamic shared memory
+__host__ __device__ inline TailSmem make_tail_smem(const NetDev& n) {
+  TailSmem t;
+  const int R = make_tc_raw(make_tc_image(n)).total, P = n.g.total;
+  t.raw = 0;
+  t.grad = (R + 31) & ~31;
+  t.par = t.grad + ((P + 31) & ~31);
+  t.total = t.par + ((P + 31) & ~31);
+  return t;
+}
 
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -841,19 +852,31 @@ __device__ __forceinline__ uint32_t cluster_cta_rank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
+// store into the shared memory of CTA `rank` of this cluster, at the address `local` has in this CTA's own window
+__device__ __forceinline__ void st_cluster_f32(const float* local, uint32_t rank, float v) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"((uint32_t)__cvta_generic_to_shared(local)), "r"(rank));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+}
 
 __global__ void __cluster_dims__(kTailCtas, 1, 1) __launch_bounds__(kTailThreads, 1) tc_tail_kernel(const TailArgs a) {
-  __shared__ float sacc[kTailThreads / 256][kTailUnroll][8][33];
-  __shared__ UnfoldScratch us[kTailThreads / 256];
+  extern __shared__ __align__(16) float tsm[];
+  __shared__ float sacc[kTailSubs][kTailUnroll][8][33];
+  __shared__ UnfoldScratch us[kTailSubs];
+  __shared__ float s_sq[kTailUnits];
   __shared__ float s_total, s_coef, s_step_size, s_bc2_sqrt;
   __shared__ int s_step;
   __shared__ double s_p1, s_p2;
+  __shared__ uint32_t s_round;
   const int tid = threadIdx.x, sub = tid >> 8, t = tid & 255;
   const int cta = (int)cluster_cta_rank();
-  const int unit = cta * (kTailThreads / 256) + sub;              // 0 .. 31
-  const int gtid = cta * kTailThreads + tid, gthreads = kTailCtas * kTailThreads;
+  const int unit = cta * kTailSubs + sub;                        // 0 .. 31
   const TcImage im = make_tc_image(a.n);
+  const TailSmem L = make_tail_smem(a.n);
   const int P = a.n.g.total;
+  float* raw_s = tsm + L.raw;                                    // summed raw accumulators (valid in CTA 0)
+  float* g_s = tsm + L.grad;                                     // the gradient Adam consumes
+  float* p_s = tsm + L.par;                                      // the new parameters (for the re-pack)
 
   if (a.stages & 1) {
     // ---- slot sum (grad_reduce_kernel's order: warp sg adds slots sg, sg + 8, ... into 4 accumulators, then the 8 partials in turn)
@@ -885,30 +908,36 @@ __global__ void __cluster_dims__(kTailCtas, 1, 1) __launch_bounds__(kTailThreads
           float g = 0.f;
 #pragma unroll
           for (int k = 0; k < 8; ++k) g += sacc[sub][u][k][pi];
-          if (i < R) a.raw_sum[i] = g;
+          if (i < R) st_cluster_f32(raw_s + i, 0u, g);           // into CTA 0's shared memory
         }
       }
       __syncthreads();
     }
-    cluster_sync_all();
-    // ---- unfold: the 12 (bx, by) units of tc_unfold_kernel's grid (4, 3)
-    float* g_local = (a.stages & 4) ? reinterpret_cast<float*>(const_cast<char*>(static_cast<const char*>(a.peers.buf[a.peers.rank])) + a.sym_offset_bytes)
-                                    : a.grad;
-    tc_unfold_unit(a.n, a.p, a.raw_sum, g_local, a.sumsq_part, unit & 3, unit >> 2, 4, t, unit < 12, us[sub]);
-    cluster_sync_all();
+    cluster_sync_all();                                          // the DSMEM stores have landed in CTA 0
   }
-  int n_part_x = 0;
+  if (cta != 0) return;                                          // CTA 0 finishes alone (nobody touches the others' memory)
+
+  int n_part = a.n_part;
+  if (a.stages & 1) {
+    // ---- unfold: the 12 (bx, by) units of tc_unfold_kernel's grid (4, 3), four at a time
+    float* g_out = (a.stages & 4) ? reinterpret_cast<float*>(const_cast<char*>(static_cast<const char*>(a.peers.buf[a.peers.rank])) + a.sym_offset_bytes)
+                                  : a.grad;
+    for (int u0 = 0; u0 < 12; u0 += kTailSubs) {
+      const int u = u0 + sub;
+      tc_unfold_unit(a.n, a.p, raw_s, g_out, s_sq, u & 3, u >> 2, 4, t, u < 12, us[sub], g_s);
+      __syncthreads();
+    }
+    n_part = 12;
+    if (!(a.stages & 2) && tid < 12) a.sumsq_part[tid] = s_sq[tid];
+  }
   if (a.stages & 4) {
     // ---- all-reduce over peer memory (p2p_allreduce_kernel<float>: arrive, wait, sum in rank order, per-block sum of squares)
-    __shared__ uint32_t s_round;
     if (tid == 0) s_round = a.round_dev[0] + 1;
     __syncthreads();
     const uint32_t round = s_round;
-    if (cta == 0 && tid < a.peers.world) {
-      __threadfence_system();
-      st_release_sys(a.peers.sig[tid] + a.peers.rank, round);
-    }
     if (tid < a.peers.world) {
+      __threadfence_system();                                     // the unfolded gradient is visible to the peers
+      st_release_sys(a.peers.sig[tid] + a.peers.rank, round);
       const uint32_t* mine = a.peers.sig[a.peers.rank] + tid;
       const long long t0 = clock64();
       while ((int)(ld_acquire_sys(mine) - round) < 0) {
@@ -916,100 +945,107 @@ __global__ void __cluster_dims__(kTailCtas, 1, 1) __launch_bounds__(kTailThreads
       }
     }
     __syncthreads();
-    // virtual grid of the stand-alone kernel: `blocks` CTAs of 256 threads, unit u plays CTA u (blocks <= 32 here: P <= 32 K)
+    // the stand-alone kernel's grid: `blocks` CTAs of 256 threads; sub-block s plays CTAs s, s + 4, ...
     const int n = P;
     int blocks = (n / 4 + 255) / 256;
     if (blocks < 1) blocks = 1;
     if (blocks > kTailUnits) blocks = kTailUnits;
-    n_part_x = blocks;
-    float sq = 0.f;
-    if (unit < blocks) {
-      const int vt = unit * 256 + t, nt = blocks * 256;
-      if ((n & 3) == 0 && (a.sym_offset_bytes & 15) == 0) {
-        for (int i = vt; i < n / 4; i += nt) {
-          float4 v[kMaxPeers];
+    for (int vb0 = 0; vb0 < blocks; vb0 += kTailSubs) {
+      const int vb = vb0 + sub;
+      float sq = 0.f;
+      if (vb < blocks) {
+        const int vt = vb * 256 + t, nt = blocks * 256;
+        if ((n & 3) == 0 && (a.sym_offset_bytes & 15) == 0) {
+          for (int i = vt; i < n / 4; i += nt) {
+            float4 v[kMaxPeers];
 #pragma unroll
-          for (int q = 0; q < kMaxPeers; ++q)
-            if (q < a.peers.world)
-              v[q] = ld_peer4(reinterpret_cast<const float*>(static_cast<const char*>(a.peers.buf[q]) + a.sym_offset_bytes) + 4 * i);
-          float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = 0; q < kMaxPeers; ++q)
+              if (q < a.peers.world)
+                v[q] = ld_peer4(reinterpret_cast<const float*>(static_cast<const char*>(a.peers.buf[q]) + a.sym_offset_bytes) + 4 * i);
+            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int q = 0; q < kMaxPeers; ++q)
-            if (q < a.peers.world) { sum.x += v[q].x; sum.y += v[q].y; sum.z += v[q].z; sum.w += v[q].w; }
-          reinterpret_cast<float4*>(a.grad)[i] = sum;
-          sq = fmaf(sum.x, sum.x, fmaf(sum.y, sum.y, fmaf(sum.z, sum.z, fmaf(sum.w, sum.w, sq))));
-        }
-      } else {
-        for (int i = vt; i < n; i += nt) {
-          float v[kMaxPeers];
+            for (int q = 0; q < kMaxPeers; ++q)
+              if (q < a.peers.world) { sum.x += v[q].x; sum.y += v[q].y; sum.z += v[q].z; sum.w += v[q].w; }
+            reinterpret_cast<float4*>(a.grad)[i] = sum;
+            reinterpret_cast<float4*>(g_s)[i] = sum;
+            sq = fmaf(sum.x, sum.x, fmaf(sum.y, sum.y, fmaf(sum.z, sum.z, fmaf(sum.w, sum.w, sq))));
+          }
+        } else {
+          for (int i = vt; i < n; i += nt) {
+            float v[kMaxPeers];
 #pragma unroll
-          for (int q = 0; q < kMaxPeers; ++q)
-            if (q < a.peers.world) v[q] = ld_peer<float>(reinterpret_cast<const float*>(static_cast<const char*>(a.peers.buf[q]) + a.sym_offset_bytes) + i);
-          float sum = 0.f;
+            for (int q = 0; q < kMaxPeers; ++q)
+              if (q < a.peers.world) v[q] = ld_peer<float>(reinterpret_cast<const float*>(static_cast<const char*>(a.peers.buf[q]) + a.sym_offset_bytes) + i);
+            float sum = 0.f;
 #pragma unroll
-          for (int q = 0; q < kMaxPeers; ++q)
-            if (q < a.peers.world) sum += v[q];
-          a.grad[i] = sum;
-          sq = fmaf(sum, sum, sq);
+            for (int q = 0; q < kMaxPeers; ++q)
+              if (q < a.peers.world) sum += v[q];
+            a.grad[i] = sum;
+            g_s[i] = sum;
+            sq = fmaf(sum, sum, sq);
+          }
         }
       }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    if ((tid & 31) == 0) us[sub].sred[t >> 5] = sq;
-    __syncthreads();
-    if (t == 0 && unit < blocks) {
-      float tot = 0.f;
+      for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      if ((tid & 31) == 0) us[sub].sred[t >> 5] = sq;
+      __syncthreads();
+      if (t == 0 && vb < blocks) {
+        float tot = 0.f;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) tot += us[sub].sred[q];
-      a.sumsq_part[unit] = tot;
-    }
-    cluster_sync_all();
-    if (gtid == 0) a.round_dev[0] = round;              // every CTA of this launch has read the old value
-  }
-  if (a.stages & 2) {
-    // ---- clip_grad_norm_ + Adam (clip_adam_kernel<1>: the scalar prologue in one warp of every CTA, fixed order)
-    const int n_part = (a.stages & 4) ? n_part_x : ((a.stages & 1) ? 12 : a.n_part);
-    if (tid < 32) {
-      double x = 0.0;
-      for (int i = tid; i < n_part; i += 32) x += (double)a.sumsq_part[i];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-      if (tid == 0) {
-        const float tot = (float)sqrt(x);
-        const int st = *a.step_dev + 1;
-        double p1, p2;
-        if (a.beta_pow && a.beta_pow[2] == (double)(st - 1)) { p1 = a.beta_pow[0] * 0.9; p2 = a.beta_pow[1] * 0.999; }
-        else { p1 = pow(0.9, (double)st); p2 = pow(0.999, (double)st); }
-        s_p1 = p1; s_p2 = p2;
-        const double bc1 = 1.0 - p1, bc2 = 1.0 - p2;
-        s_total = tot;
-        s_coef = a.use_clip ? fminf(a.max_norm / (tot + 1e-6f), 1.0f) : 1.f;
-        s_step_size = (float)((double)a.lr_dev[0] / bc1);
-        s_bc2_sqrt = (float)sqrt(bc2);
-        s_step = st;
+        for (int q = 0; q < 8; ++q) tot += us[sub].sred[q];
+        s_sq[vb] = tot;
       }
+      __syncthreads();
     }
-    __syncthreads();
-    const float coef = s_coef, step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
-    for (int i = gtid; i < P; i += gthreads) {
-      const float g = a.grad[i] * coef, m_in = a.m[i], v_in = a.v[i];
-      const float mo = m_in + (g - m_in) * (float)(1.0 - 0.9);
-      const float vo = v_in * 0.999f + (float)(1.0 - 0.999) * g * g;
-      const float denom = sqrtf(vo) / bc2_sqrt + a.eps;
-      a.p[i] = a.p[i] - step_size * (mo / denom);
-      a.m[i] = mo; a.v[i] = vo;
-    }
-    cluster_sync_all();                                   // every CTA has read the old step count / powers; new weights are visible
-    if (gtid == 0) {
-      a.step_dev[0] = s_step;
-      if (a.beta_pow) { a.beta_pow[0] = s_p1; a.beta_pow[1] = s_p2; a.beta_pow[2] = (double)s_step; }
-      if (a.norm_out) *a.norm_out += (double)s_total;
-    }
-    // ---- folded image of the new weights (pack_tc_kernel of the NEXT optimiser step)
-    if (a.image)
-      for (int i = gtid; i < im.total; i += gthreads) a.image[i] = pack_tc_element(a.n, im, a.p, i);
+    n_part = blocks;
+    if (tid == 0) a.round_dev[0] = round;
   }
+  if (!(a.stages & 2)) return;
+
+  // ---- clip_grad_norm_ + Adam (clip_adam_kernel<1>: the scalar prologue in one warp, fixed order)
+  const bool from_global = !(a.stages & 1);                       // stage 2 alone: gradient and partials come from global memory
+  __syncthreads();
+  if (tid < 32) {
+    double x = 0.0;
+    for (int i = tid; i < n_part; i += 32) x += (double)(from_global ? a.sumsq_part[i] : s_sq[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (tid == 0) {
+      const float tot = (float)sqrt(x);
+      const int st = *a.step_dev + 1;
+      double p1, p2;
+      if (a.beta_pow && a.beta_pow[2] == (double)(st - 1)) { p1 = a.beta_pow[0] * 0.9; p2 = a.beta_pow[1] * 0.999; }
+      else { p1 = pow(0.9, (double)st); p2 = pow(0.999, (double)st); }
+      s_p1 = p1; s_p2 = p2;
+      const double bc1 = 1.0 - p1, bc2 = 1.0 - p2;
+      s_total = tot;
+      s_coef = a.use_clip ? fminf(a.max_norm / (tot + 1e-6f), 1.0f) : 1.f;
+      s_step_size = (float)((double)a.lr_dev[0] / bc1);
+      s_bc2_sqrt = (float)sqrt(bc2);
+      s_step = st;
+    }
+  }
+  __syncthreads();
+  const float coef = s_coef, step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+  for (int i = tid; i < P; i += kTailThreads) {
+    const float g = (from_global ? a.grad[i] : g_s[i]) * coef, m_in = a.m[i], v_in = a.v[i];
+    const float mo = m_in + (g - m_in) * (float)(1.0 - 0.9);
+    const float vo = v_in * 0.999f + (float)(1.0 - 0.999) * g * g;
+    const float denom = sqrtf(vo) / bc2_sqrt + a.eps;
+    const float pn = a.p[i] - step_size * (mo / denom);
+    a.p[i] = pn; p_s[i] = pn;
+    a.m[i] = mo; a.v[i] = vo;
+  }
+  if (tid == 0) {
+    a.step_dev[0] = s_step;
+    if (a.beta_pow) { a.beta_pow[0] = s_p1; a.beta_pow[1] = s_p2; a.beta_pow[2] = (double)s_step; }
+    if (a.norm_out) *a.norm_out += (double)s_total;
+  }
+  __syncthreads();
+  // ---- folded image of the new weights (pack_tc_kernel of the NEXT optimiser step), parameters read from shared memory
+  if (a.image)
+    for (int i = tid; i < im.total; i += kTailThreads) a.image[i] = pack_tc_element(a.n, im, p_s, i);
 }
 
 int update_mlp_tc_tail_launch(const NetDev& n, const float* part, int n_slots, float* raw_sum, float* params, float* grad, float* m,
@@ -1018,10 +1054,11 @@ int update_mlp_tc_tail_launch(const NetDev& n, const float* part, int n_slots, f
                               const void* const* peer_bufs, void* const* peer_signals, int world, int rank, long long sym_offset_bytes,
                               uint32_t* round_dev) {
   if (!update_mlp_tc_supported(n)) { set_error("update_tail: the fused optimiser tail is built for the tcgen05 small-net path only"); return MAPPO_ERR_UNSUPPORTED; }
-  if ((stages & 3) == 0 || ((stages & 1) && (!part || n_slots <= 0 || !raw_sum)) || ((stages & 2) && (!m || !v || !lr_dev || !step_dev)) ||
+  if ((stages & 3) == 0 || ((stages & 1) && (!part || n_slots <= 0)) || ((stages & 2) && (!m || !v || !lr_dev || !step_dev)) ||
       ((stages & 3) == 2 && n_part <= 0)) { set_error("update_tail: bad arguments for stages %d", stages); return MAPPO_ERR_INVALID; }
   TailArgs a;
-  a.n = n; a.part = part; a.n_slots = n_slots; a.raw_sum = raw_sum; a.p = params; a.grad = grad; a.m = m; a.v = v;
+  (void)raw_sum;
+  a.n = n; a.part = part; a.n_slots = n_slots; a.p = params; a.grad = grad; a.m = m; a.v = v;
   a.sumsq_part = sumsq_part; a.n_part = n_part; a.lr_dev = lr_dev; a.step_dev = step_dev; a.eps = eps; a.max_norm = max_norm;
   a.use_clip = use_clip; a.norm_out = norm_out; a.beta_pow = beta_pow; a.image = image; a.stages = stages;
   memset(&a.peers, 0, sizeof(a.peers));
@@ -1034,7 +1071,15 @@ int update_mlp_tc_tail_launch(const NetDev& n, const float* part, int n_slots, f
     for (int q = 0; q < world; ++q) { a.peers.buf[q] = peer_bufs[q]; a.peers.sig[q] = static_cast<uint32_t*>(peer_signals[q]); }
     a.peers.world = world; a.peers.rank = rank;
   }
-  tc_tail_kernel<<<kTailCtas, kTailThreads, 0, st>>>(a);
+  const size_t bytes = (size_t)make_tail_smem(n).total * sizeof(float);
+  static thread_local SmemConfig tail_cfg = {};
+  size_t& configured = tail_cfg.slot();
+  if (bytes > configured) {
+    if (cudaFuncSetAttribute(tc_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+      return check_launch("tc_tail_kernel: cudaFuncSetAttribute");
+    configured = bytes;
+  }
+  tc_tail_kernel<<<kTailCtas, kTailThreads, bytes, st>>>(a);
   return check_launch("tc_tail_kernel");
 }
 
