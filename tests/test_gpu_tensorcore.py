@@ -4,11 +4,12 @@ TF32 keeps 10 mantissa bits of the GEMM inputs (round-to-nearest when the operan
 LayerNorm, activations, losses, the gradient reduction and Adam stay fp32.  Stated tolerances:
   first-update gradients   tanh nets: |err| <= 5e-3 * |ref| + 5e-3 * max|ref of that tensor| (tf32 rounding of a 64..9600-term dot;
                            measured worst case 1.7e-3 of the tensor's scale); ReLU nets (c5): relative L2 error of every tensor
-                           <= 4e-2 and <= 5 % of its elements outside that element tolerance -- helpers.grad_agreement says why
+                           <= 5e-2 (measured 1.6e-2) -- helpers.grad_agreement says why the element-wise maximum is not usable
   losses / ratio / entropy  rtol 2e-3 (policy_loss: + 2e-5 absolute, it is a difference of O(1) terms near zero)
-  weights after a full train()   rtol 2e-2, atol 1.2 * (optimiser steps) * lr: Adam normalises the gradient, so a weight whose
-                                   gradient is within tf32 noise of zero moves by up to lr per step in EITHER direction in each
-                                   implementation (worst case 2 lr apart per step; measured 1.0 steps * lr on c5, 0.16 on c2)
+  weights after a full train()   rtol 2e-2, atol 2.1 * (optimiser steps) * lr: Adam normalises the gradient, so a weight whose
+                                   gradient is within tf32 noise of zero moves by lr per step in EITHER direction in each
+                                   implementation -- 2 lr apart per step at worst (measured 1.7 steps * lr on the 72-row c5
+                                   fixture, where most first-layer gradients are noise; 0.16 on c2)
   LayerNorm affine gradients     5e-2 of the tensor's scale (see _grad_check)
 Cases: c1 (N = 8), c2 at the benchmark size (N = 128) and the c5 widths (hidden 512, layer_N 2: the TMA-fed GEMM pipeline).
 The exact-fp32 build (MAPPO_B200_GEMM=fp32, tests/test_gpu_parity.py) keeps the tight tolerances.
@@ -111,7 +112,7 @@ def test_tf32_full_iterations(name, monkeypatch):
     for k in INFO_KEYS:
         assert_close(info[k], want[k], 2e-2, 2e-4, f"train_info[{k}]")
     worst = 0.0
-    atol_w = max(2e-3, 1.2 * cfg.ppo_epoch * cfg.num_mini_batch * max(cfg.lr, cfg.critic_lr))
+    atol_w = max(2e-3, 2.1 * cfg.ppo_epoch * cfg.num_mini_batch * max(cfg.lr, cfg.critic_lr))
     for net, nm in ((policy.actor, "actor"), (policy.critic, "critic")):
         for k, v in net.state_dict().items():
             got, ref = _golden_rows(g, f"it0/{nm}/{k}", v.cpu().numpy())
