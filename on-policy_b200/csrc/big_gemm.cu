@@ -14,6 +14,8 @@
 //            tile of the same coordinates into the staging slot first (in-place transform)
 // The two N tiles of a 512-wide row go to the SAME CTA back to back, so the row statistics stay in registers, and the MMA
 // of tile i + 1 overlaps the epilogue of tile i (double-buffered accumulators).
+#include <cstdlib>
+#include <cstring>
 #include "big_tc.cuh"
 #include "big_epi.cuh"
 #include "big_net.h"
@@ -27,9 +29,10 @@ constexpr int kAinDepth = 2;              // activation tiles in flight ahead of
 constexpr int kABytes = 128 * 128;        // A stage: 128 rows x 32 tf32
 
 struct LinSmem { int stage_bytes, stages_off, slots_off, colvec_off, scratch_off, bars_off, total; };
-__host__ __device__ inline LinSmem make_lin_smem(int BN, int n_stages, int N_cv, bool scratch) {
+// pair: each CTA of a cta_group::2 pair stages its 128 rows of A and HALF of the B tile (BN / 2 rows of W)
+__host__ __device__ inline LinSmem make_lin_smem(int BN, int n_stages, int N_cv, bool scratch, bool pair = false) {
   LinSmem s;
-  s.stage_bytes = kABytes + BN * 128;
+  s.stage_bytes = kABytes + (pair ? BN / 2 : BN) * 128;
   s.stages_off = 0;
   s.slots_off = n_stages * s.stage_bytes;
   s.colvec_off = s.slots_off + kNS * 16384;
@@ -39,7 +42,7 @@ __host__ __device__ inline LinSmem make_lin_smem(int BN, int n_stages, int N_cv,
   return s;
 }
 
-template <class Epi>
+template <class Epi, bool PAIR>
 __global__ void __launch_bounds__(kLinThreads, 1)
 big_lin_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapAin,
@@ -51,7 +54,11 @@ big_lin_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int BN = sh.BN, NT = sh.N / sh.BN, KB = (sh.K + 31) / 32, NST = sh.n_stages;
-  const LinSmem L = make_lin_smem(BN, NST, sh.N, Epi::kNeedsScratch);
+  const LinSmem L = make_lin_smem(BN, NST, sh.N, Epi::kNeedsScratch, PAIR);
+  // PAIR: CTAs 2 p and 2 p + 1 form a cta_group::2 pair on one 256-row block; rank 0 (the leader) issues the MMAs for both
+  const uint32_t rank = PAIR ? cluster_rank() : 0u;
+  const int unit = PAIR ? (int)blockIdx.x >> 1 : (int)blockIdx.x, n_units = PAIR ? (int)gridDim.x >> 1 : (int)gridDim.x;
+  const int n_ublocks = PAIR ? (sh.n_rowblocks + 1) >> 1 : sh.n_rowblocks;        // row blocks of a unit (256 or 128 rows)
   float* cv = reinterpret_cast<float*>(smem + L.colvec_off);
   float* scratch = reinterpret_cast<float*>(smem + L.scratch_off);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars_off);
@@ -66,16 +73,16 @@ big_lin_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   for (int i = tid; i < 2 * sh.N; i += kLinThreads) cv[i] = ea.colvec[i];
   if (tid == 0) {
     for (int i = 0; i < NST; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, PAIR ? 256 : 128); }
     for (int i = 0; i < kNS; ++i) mbar_init(ainfull + i, 1);
     mbar_fence_init();
     tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapB);
     if (Epi::kStoresOut) tma_prefetch_desc(&mapOut);
     if (Epi::kHasAin) tma_prefetch_desc(&mapAin);
   }
-  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == 1) { if (PAIR) tmem_alloc_pair(tmem_slot, tmem_cols); else tmem_alloc(tmem_slot, tmem_cols); }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync(); else __syncthreads();                // (pair: the peer's barriers are initialised before anything signals them)
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   typename Epi::Thread th;
@@ -86,26 +93,36 @@ big_lin_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int rb = blockIdx.x; rb < sh.n_rowblocks; rb += gridDim.x)
+      for (int ub = unit; ub < n_ublocks; ub += n_units) {
+        const int rb = PAIR ? 2 * ub + (int)rank : ub;
         for (int nt = 0; nt < NT; ++nt)
           for (int kb = 0; kb < KB; ++kb) {
             mbar_wait(empty + stage, phase ^ 1);
             uint8_t* sA = smem + L.stages_off + stage * L.stage_bytes;
-            mbar_expect_tx(full + stage, (uint32_t)L.stage_bytes);
-            tma_load_2d(sA, &mapA, kb * 32, rb * 128, full + stage);
-            tma_load_2d(sA + kABytes, &mapB, kb * 32, nt * BN, full + stage);
+            if (PAIR) {
+              // both CTAs' bytes are accounted on the LEADER's barrier (armed by the leader for the whole pair)
+              if (rank == 0) mbar_expect_tx(full + stage, 2u * (uint32_t)L.stage_bytes);
+              const uint32_t lb = leader_addr(full + stage);
+              tma_load_2d_pair(sA, &mapA, kb * 32, rb * 128, lb);
+              tma_load_2d_pair(sA + kABytes, &mapB, kb * 32, nt * BN + (int)rank * (BN / 2), lb);
+            } else {
+              mbar_expect_tx(full + stage, (uint32_t)L.stage_bytes);
+              tma_load_2d(sA, &mapA, kb * 32, rb * 128, full + stage);
+              tma_load_2d(sA + kABytes, &mapB, kb * 32, nt * BN, full + stage);
+            }
             if (++stage == NST) { stage = 0; phase ^= 1; }
           }
+      }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, BN, 0, 0);
+    // ===================== MMA issuer (pair: the leader only) =====================
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc(PAIR ? 256 : 128, BN, 0, 0);
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
-      for (int rb = blockIdx.x; rb < sh.n_rowblocks; rb += gridDim.x)
+      for (int ub = unit; ub < n_ublocks; ub += n_units)
         for (int nt = 0; nt < NT; ++nt) {
-          mbar_wait(tempty + as, aphase ^ 1);             // the epilogue has drained this accumulator stage
+          mbar_wait(tempty + as, aphase ^ 1);             // the epilogue(s) have drained this accumulator stage
           tc_fence_after();
           const uint32_t d = tmem + (uint32_t)(as * BN);
           for (int kb = 0; kb < KB; ++kb) {
@@ -113,12 +130,15 @@ big_lin_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             tc_fence_after();
             const uint32_t a0 = smem_u32(smem + L.stages_off + stage * L.stage_bytes), b0 = a0 + kABytes;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_tf32(d, make_desc(a0 + k * 32, 16, 1024, 2), make_desc(b0 + k * 32, 16, 1024, 2), idesc, (kb | k) ? 1u : 0u);
-            umma_commit(empty + stage);                   // frees the smem stage when these MMAs have read it
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = make_desc(a0 + k * 32, 16, 1024, 2), bd = make_desc(b0 + k * 32, 16, 1024, 2);
+              if (PAIR) umma_tf32_pair(d, ad, bd, idesc, (kb | k) ? 1u : 0u);
+              else umma_tf32(d, ad, bd, idesc, (kb | k) ? 1u : 0u);
+            }
+            if (PAIR) umma_commit_pair(empty + stage); else umma_commit(empty + stage);     // frees the smem stage (in both CTAs)
             if (++stage == NST) { stage = 0; phase ^= 1; }
           }
-          umma_commit(tfull + as);                        // accumulator complete
+          if (PAIR) umma_commit_pair(tfull + as); else umma_commit(tfull + as);             // accumulator complete
           as ^= 1;
           if (as == 0) aphase ^= 1;
         }
@@ -130,21 +150,23 @@ big_lin_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
     uint8_t* slots = smem + L.slots_off;
     const int CPR = sh.N / kChunk;                        // chunks per row block
-    const int my_rbs = (sh.n_rowblocks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int my_rbs = unit < n_ublocks ? (n_ublocks - unit + n_units - 1) / n_units : 0;
     const long long total_chunks = (long long)my_rbs * CPR;
     auto issue_ain = [&](long long g) {                   // thread et == 0 only
       if (g >= total_chunks) return;
       const int rbl = (int)(g / CPR), c = (int)(g % CPR);
       const int slot = (int)(g % kNS);
       mbar_expect_tx(ainfull + slot, 16384u);
-      tma_load_2d(slots + slot * 16384, &mapAin, c * kChunk, (blockIdx.x + rbl * gridDim.x) * 128, ainfull + slot);
+      const int ubl = unit + rbl * n_units;
+      tma_load_2d(slots + slot * 16384, &mapAin, c * kChunk, (PAIR ? 2 * ubl + (int)rank : ubl) * 128, ainfull + slot);
     };
     if (Epi::kHasAin && et == 0)
       for (int i = 0; i < kAinDepth; ++i) issue_ain(i);
     int as = 0;
     uint32_t aphase = 0;
     long long g = 0;                                      // running chunk index of this CTA
-    for (int rb = blockIdx.x; rb < sh.n_rowblocks; rb += gridDim.x) {
+    for (int ub = unit; ub < n_ublocks; ub += n_units) {
+      const int rb = PAIR ? 2 * ub + (int)rank : ub;
       const int grow = rb * 128 + r;
       typename Epi::Row row;
       Epi::begin_row(ea, row, grow);
@@ -158,7 +180,7 @@ big_lin_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           tmem_ld_wait();
           if (c == BN / kChunk - 1) {                     // last read of this accumulator stage: hand it back to the MMA warp
             tc_fence_before();
-            mbar_arrive(tempty + as);
+            if (PAIR) mbar_arrive_leader(tempty + as); else mbar_arrive(tempty + as);
           }
           const int slot = (int)(g % kNS);
           uint8_t* sl = slots + slot * 16384;
@@ -201,9 +223,9 @@ big_lin_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (et == 0) tma_store_wait_all<0>();
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync(); else __syncthreads();                // (pair: nobody leaves while the peer may still signal its barriers / read its tiles)
   Epi::finish_thread(ea, th, sred, tid, kLinThreads);
-  if (warp == 1) tmem_dealloc(tmem, tmem_cols);
+  if (warp == 1) { if (PAIR) tmem_dealloc_pair(tmem, tmem_cols); else tmem_dealloc(tmem, tmem_cols); }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -341,25 +363,52 @@ int make_map(CUtensorMap* m, const float* base, long long width, long long rows,
   return MAPPO_OK;
 }
 
+// pair mode (cta_group::2, 256-row tiles): halves the B-operand traffic per SM, which is what bounds the 128-row kernel
+// (48 KB of operands per 2.1 MFLOP k-step); used for every 256-wide N tile with at least two row blocks (the wave count is the
+// same as with single CTAs).  MAPPO_B200_PAIR=0 forces the single-CTA kernel.
+static bool pair_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MAPPO_B200_PAIR"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
 template <class Epi>
 static int lin_launch_t(const LinOperands& o, const typename Epi::Args& ea, LinShape sh, const char* name, cudaStream_t st) {
+  sh.n_rowblocks = (sh.n_rows + 127) / 128;
+  const bool pair = pair_enabled() && sh.BN == 256 && sh.n_rowblocks >= 2 && o.sm_count >= 2;
   CUtensorMap mA, mB, mO, mI;
   int rc = make_map(&mA, o.A, sh.K, sh.n_rows, o.lda, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  rc = make_map(&mB, o.W, sh.K, sh.N, o.ldw, 32, sh.BN, CU_TENSOR_MAP_SWIZZLE_128B);
+  rc = make_map(&mB, o.W, sh.K, sh.N, o.ldw, 32, pair ? sh.BN / 2 : sh.BN, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   mO = mA; mI = mA;
   if (Epi::kStoresOut && sh.store_out) { rc = make_map(&mO, o.out, sh.N, sh.n_rows, o.ldo, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B); if (rc) return rc; }
   if (Epi::kHasAin) { rc = make_map(&mI, o.ain, sh.N, sh.n_rows, o.ldain, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B); if (rc) return rc; }
-  sh.n_rowblocks = (sh.n_rows + 127) / 128;
-  sh.n_stages = sh.BN >= 256 ? 3 : 4;
-  const LinSmem L = make_lin_smem(sh.BN, sh.n_stages, sh.N, Epi::kNeedsScratch);
+  sh.n_stages = pair ? 4 : (sh.BN >= 256 ? 3 : 4);
+  const LinSmem L = make_lin_smem(sh.BN, sh.n_stages, sh.N, Epi::kNeedsScratch, pair);
   const size_t bytes = (size_t)L.total + 1024;
   if (bytes > 227 * 1024) { set_error("%s: %zu B shared memory > 227 KB (N = %d)", name, bytes, sh.N); return MAPPO_ERR_UNSUPPORTED; }
-  if (cudaFuncSetAttribute(big_lin_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+  if (pair) {
+    if (cudaFuncSetAttribute(big_lin_kernel<Epi, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+      return check_launch("big_lin_kernel: cudaFuncSetAttribute");
+    const int n_ublocks = (sh.n_rowblocks + 1) / 2, max_pairs = o.sm_count / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * (n_ublocks < max_pairs ? n_ublocks : max_pairs));
+    cfg.blockDim = dim3(kLinThreads);
+    cfg.dynamicSmemBytes = bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, big_lin_kernel<Epi, true>, mA, mB, mO, mI, ea, sh) != cudaSuccess) return check_launch(name);
+    return check_launch(name);
+  }
+  if (cudaFuncSetAttribute(big_lin_kernel<Epi, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
     return check_launch("big_lin_kernel: cudaFuncSetAttribute");
   const int grid = sh.n_rowblocks < o.sm_count ? sh.n_rowblocks : o.sm_count;
-  big_lin_kernel<Epi><<<grid, kLinThreads, bytes, st>>>(mA, mB, mO, mI, ea, sh);
+  big_lin_kernel<Epi, false><<<grid, kLinThreads, bytes, st>>>(mA, mB, mO, mI, ea, sh);
   return check_launch(name);
 }
 

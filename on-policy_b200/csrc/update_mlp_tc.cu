@@ -876,7 +876,27 @@ __global__ void __cluster_dims__(kTailCtas, 1, 1) __launch_bounds__(kTailThreads
   const int P = a.n.g.total;
   float* raw_s = tsm + L.raw;                                    // summed raw accumulators (valid in CTA 0)
   float* g_s = tsm + L.grad;                                     // the gradient Adam consumes
-  float* p_s = tsm + L.par;                                      // the new parameters (for the re-pack)
+  float* p_s = tsm + L.par;                                      // parameters: the old ones for the unfold, the new ones for the re-pack
+  constexpr int kPer = 11;                                       // parameters per thread of CTA 0 (P <= 11 K for every net of this path)
+
+  // CTA 0: everything it will need from global memory is requested NOW, in flight underneath the slot sum
+  float pr[kPer], mr[kPer], vr[kPer];
+  int step_old = 0;
+  double bp0 = 1.0, bp1 = 1.0, bp2 = -1.0;
+  float lr = 0.f;
+  if (cta == 0) {
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const int i = tid + j * kTailThreads;
+      pr[j] = i < P ? a.p[i] : 0.f;
+      mr[j] = ((a.stages & 2) && i < P) ? a.m[i] : 0.f;
+      vr[j] = ((a.stages & 2) && i < P) ? a.v[i] : 0.f;
+    }
+    if (tid == 0 && (a.stages & 2)) {
+      step_old = *a.step_dev; lr = a.lr_dev[0];
+      if (a.beta_pow) { bp0 = a.beta_pow[0]; bp1 = a.beta_pow[1]; bp2 = a.beta_pow[2]; }
+    }
+  }
 
   if (a.stages & 1) {
     // ---- slot sum (grad_reduce_kernel's order: warp sg adds slots sg, sg + 8, ... into 4 accumulators, then the 8 partials in turn)
@@ -916,6 +936,12 @@ __global__ void __cluster_dims__(kTailCtas, 1, 1) __launch_bounds__(kTailThreads
     cluster_sync_all();                                          // the DSMEM stores have landed in CTA 0
   }
   if (cta != 0) return;                                          // CTA 0 finishes alone (nobody touches the others' memory)
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    const int i = tid + j * kTailThreads;
+    if (i < P) p_s[i] = pr[j];
+  }
+  __syncthreads();
 
   int n_part = a.n_part;
   if (a.stages & 1) {
@@ -924,7 +950,7 @@ __global__ void __cluster_dims__(kTailCtas, 1, 1) __launch_bounds__(kTailThreads
                                   : a.grad;
     for (int u0 = 0; u0 < 12; u0 += kTailSubs) {
       const int u = u0 + sub;
-      tc_unfold_unit(a.n, a.p, raw_s, g_out, s_sq, u & 3, u >> 2, 4, t, u < 12, us[sub], g_s);
+      tc_unfold_unit(a.n, p_s, raw_s, g_out, s_sq, u & 3, u >> 2, 4, t, u < 12, us[sub], g_s);
       __syncthreads();
     }
     n_part = 12;
@@ -1013,29 +1039,39 @@ __global__ void __cluster_dims__(kTailCtas, 1, 1) __launch_bounds__(kTailThreads
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
     if (tid == 0) {
       const float tot = (float)sqrt(x);
-      const int st = *a.step_dev + 1;
+      const int st = step_old + 1;
       double p1, p2;
-      if (a.beta_pow && a.beta_pow[2] == (double)(st - 1)) { p1 = a.beta_pow[0] * 0.9; p2 = a.beta_pow[1] * 0.999; }
+      if (a.beta_pow && bp2 == (double)(st - 1)) { p1 = bp0 * 0.9; p2 = bp1 * 0.999; }
       else { p1 = pow(0.9, (double)st); p2 = pow(0.999, (double)st); }
       s_p1 = p1; s_p2 = p2;
       const double bc1 = 1.0 - p1, bc2 = 1.0 - p2;
       s_total = tot;
       s_coef = a.use_clip ? fminf(a.max_norm / (tot + 1e-6f), 1.0f) : 1.f;
-      s_step_size = (float)((double)a.lr_dev[0] / bc1);
+      s_step_size = (float)((double)lr / bc1);
       s_bc2_sqrt = (float)sqrt(bc2);
       s_step = st;
     }
   }
   __syncthreads();
   const float coef = s_coef, step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
-  for (int i = tid; i < P; i += kTailThreads) {
-    const float g = (from_global ? a.grad[i] : g_s[i]) * coef, m_in = a.m[i], v_in = a.v[i];
-    const float mo = m_in + (g - m_in) * (float)(1.0 - 0.9);
-    const float vo = v_in * 0.999f + (float)(1.0 - 0.999) * g * g;
-    const float denom = sqrtf(vo) / bc2_sqrt + a.eps;
-    const float pn = a.p[i] - step_size * (mo / denom);
-    a.p[i] = pn; p_s[i] = pn;
-    a.m[i] = mo; a.v[i] = vo;
+  float gr[kPer];
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    const int i = tid + j * kTailThreads;
+    gr[j] = i < P ? (from_global ? a.grad[i] : g_s[i]) : 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    const int i = tid + j * kTailThreads;
+    if (i < P) {
+      const float g = gr[j] * coef, m_in = mr[j], v_in = vr[j];
+      const float mo = m_in + (g - m_in) * (float)(1.0 - 0.9);
+      const float vo = v_in * 0.999f + (float)(1.0 - 0.999) * g * g;
+      const float denom = sqrtf(vo) / bc2_sqrt + a.eps;
+      const float pn = pr[j] - step_size * (mo / denom);
+      a.p[i] = pn; p_s[i] = pn;
+      a.m[i] = mo; a.v[i] = vo;
+    }
   }
   if (tid == 0) {
     a.step_dev[0] = s_step;
@@ -1071,6 +1107,7 @@ int update_mlp_tc_tail_launch(const NetDev& n, const float* part, int n_slots, f
     for (int q = 0; q < world; ++q) { a.peers.buf[q] = peer_bufs[q]; a.peers.sig[q] = static_cast<uint32_t*>(peer_signals[q]); }
     a.peers.world = world; a.peers.rank = rank;
   }
+  if (n.g.total > 11 * kTailThreads) { set_error("update_tail: %d parameters exceed the kernel's register budget", n.g.total); return MAPPO_ERR_UNSUPPORTED; }
   const size_t bytes = (size_t)make_tail_smem(n).total * sizeof(float);
   static thread_local SmemConfig tail_cfg = {};
   size_t& configured = tail_cfg.slot();
