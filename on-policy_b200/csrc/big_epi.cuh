@@ -23,7 +23,8 @@ namespace mappo {
 namespace big {
 
 constexpr int kChunk = 32;            // accumulator columns per epilogue step (= one 128-byte swizzled store tile)
-constexpr int kExt = 32;              // extra columns of a stored activation row: [H] = mu, [H+1] = sigma, rest 0
+constexpr int kExt = 64;              // extra columns of a stored activation row: [H] = mu, [H+1] = sigma, rest 0 (64: the
+                                      // last 256 + 64 column tile of the pair weight-gradient GEMM splits into whole 32-column groups)
 constexpr int kTileRows = 128;
 constexpr int kLgLd = kTileRows + 4;  // leading dimension of the transposed logits scratch lgT[j][kLgLd]
 

@@ -237,7 +237,7 @@ big_lin_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 constexpr int kGradKR = 32;               // rows per stage
 constexpr int kGradGroupBytes = kGradKR * 128;
 constexpr int kGradStages = 4;
-constexpr int kGradStageBytes = (4 + 9) * kGradGroupBytes;      // P: 4 groups, Q: up to 9 groups (288 columns)
+constexpr int kGradStageBytes = (4 + 10) * kGradGroupBytes;     // P: 4 groups, Q: up to 10 groups (320 columns)
 
 __global__ void __launch_bounds__(kLinThreads, 1)
 big_grad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapQ, float* __restrict__ partial,

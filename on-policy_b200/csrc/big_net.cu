@@ -15,6 +15,7 @@
 //   a_l  [rows][H+32]  l = 1..layer_N+1: act(z_l); columns H, H+1 = mu_l, sigma_l (what the weight-gradient GEMM needs)
 //   stats_l, mprime_l  float2 per row;   P ping-pong [rows][H];   Ph [rows][32]
 //   partial [splits][M][ldq], gsum [M][ldq];  fp32 mode: one accumulator scratch [rows][H]
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "big_net.h"
@@ -85,22 +86,30 @@ static int grad_splits(int tiles, int rows, int sm) {
   return s < 1 ? 1 : s;
 }
 
-// tiling of one weight-gradient GEMM G[M][Qw] = P^T Q: 128-row M tiles, Q tiles of 256 columns (a 32-column remainder
-// rides with the last tile), the rows of the batch split so that about one CTA per SM is busy
-static GradShape make_grad_shape(int rows, int M, int Pw, int Qw, int sm) {
+// tiling of one weight-gradient GEMM G[M][Qw] = P^T Q: Q tiles of 256 columns, the last one takes what is left (<= 320), the rows of
+// the batch split so that about one CTA (pair) per SM (pair) is busy.  pair: CTA pairs own 256-column tiles of P (big_grad_pair.cu),
+// possible when P spans whole 256-column tiles and every Q tile is a multiple of 64 columns; otherwise 128-column tiles, one CTA each.
+static bool grad_pair_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MAPPO_B200_PAIR"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+static GradShape make_grad_shape(int rows, int M, int Pw, int Qw, int sm, bool* pair_out = nullptr) {
   GradShape g;
   memset(&g, 0, sizeof(g));
   g.rows = rows; g.M = M; g.Pw = Pw; g.Qw = Qw; g.ldq = Qw;
-  g.m_tiles = (Pw + 127) / 128;
   int nt = 0, q = 0;
   while (q < Qw && nt < 4) {
     int w = Qw - q;
-    if (w > 288) w = 256;
+    if (w > 320) w = 256;
     g.q0[nt] = q; g.qw[nt] = w; q += w; ++nt;
   }
   g.n_tiles = nt;
-  g.splits = grad_splits(g.m_tiles * g.n_tiles, rows, sm);
+  const bool pair = grad_pair_enabled() && Pw % 256 == 0 && Qw % 64 == 0 && sm >= 2;
+  g.m_tiles = pair ? Pw / 256 : (Pw + 127) / 128;
+  g.splits = grad_splits(g.m_tiles * g.n_tiles, rows, pair ? sm / 2 : sm);
   g.rows_per_split = (((rows + g.splits - 1) / g.splits) + 31) & ~31;
+  if (pair_out) *pair_out = pair;
   return g;
 }
 
@@ -108,7 +117,7 @@ static Plan make_plan(const NetDev& n, int rows, int sm) {
   Plan p;
   memset(&p, 0, sizeof(p));
   p.H = n.hid; p.Hx = n.hid + kExt; p.Lh = n.layer_n + 1; p.in_dim = n.in_dim; p.rows = rows;
-  p.K0p = (n.in_dim + 1 + 31) & ~31;
+  p.K0p = (n.in_dim + 1 + 63) & ~63;          // multiple of 64: pair gradient tiles split into whole 32-column groups
   size_t o = 0;
   for (int i = 0; i < p.Lh; ++i) {
     const int Kp = i == 0 ? p.K0p : p.H;
@@ -439,13 +448,15 @@ static int run_forward(const NetDev& n, const Plan& pl, float* ws, const float* 
 
 static int run_grad(const Plan& pl, float* ws, const float* P, int ldp, int Pw, int M, const float* Q, int ldq_in, int Qw, int rows, bool tf32,
                     int sm, cudaStream_t st, int* splits_out = nullptr) {
-  if (Qw > 3 * 256 + 288) { set_error("big net: gradient GEMM operand %d columns wide", Qw); return MAPPO_ERR_UNSUPPORTED; }
-  const GradShape g = make_grad_shape(rows, M, Pw, Qw, sm);
+  if (Qw > 3 * 256 + 320) { set_error("big net: gradient GEMM operand %d columns wide", Qw); return MAPPO_ERR_UNSUPPORTED; }
+  bool pair = false;
+  const GradShape g = make_grad_shape(rows, M, Pw, Qw, sm, &pair);
   if ((size_t)g.splits * M * g.ldq > pl.partial_floats) { set_error("big net: gradient partial buffer too small"); return MAPPO_ERR_INVALID; }
   int rc;
   {
     Timed tm(T_GRAD, st);
-    rc = tf32 ? grad_gemm_launch(P, ldp, Q, ldq_in, ws + pl.partial, g, st) : ref_grad_gemm_launch(P, ldp, Q, ldq_in, ws + pl.partial, g, st);
+    rc = !tf32 ? ref_grad_gemm_launch(P, ldp, Q, ldq_in, ws + pl.partial, g, st)
+               : (pair ? grad_gemm_pair_launch(P, ldp, Q, ldq_in, ws + pl.partial, g, st) : grad_gemm_launch(P, ldp, Q, ldq_in, ws + pl.partial, g, st));
   }
   if (rc) return rc;
   if (splits_out) { *splits_out = g.splits; return MAPPO_OK; }     // the consumer sums the partials itself
@@ -562,8 +573,10 @@ int debug_lin(const float* A, int lda, const float* W, int ldw, float* out, floa
 // gsum[M, Qw] = P[rows, :M]^T Q[rows, :Qw] through big_grad_kernel (or the FFMA build) + the slot reduction
 int debug_grad(const float* P, int ldp, int Pw, int M, const float* Q, int ldq, int Qw, int rows, float* partial, float* gsum,
                bool tf32, int sm, cudaStream_t st) {
-  const GradShape g = make_grad_shape(rows, M, Pw, Qw, sm);
-  int rc = tf32 ? grad_gemm_launch(P, ldp, Q, ldq, partial, g, st) : ref_grad_gemm_launch(P, ldp, Q, ldq, partial, g, st);
+  bool pair = false;
+  const GradShape g = make_grad_shape(rows, M, Pw, Qw, sm, &pair);
+  int rc = !tf32 ? ref_grad_gemm_launch(P, ldp, Q, ldq, partial, g, st)
+                 : (pair ? grad_gemm_pair_launch(P, ldp, Q, ldq, partial, g, st) : grad_gemm_launch(P, ldp, Q, ldq, partial, g, st));
   if (rc) return rc;
   return grad_reduce_launch(partial, g.splits, M * g.ldq, gsum, nullptr, nullptr, st);
 }

@@ -18,7 +18,7 @@ struct GradShape {
   int rows, rows_per_split, splits, m_tiles, n_tiles;
   int M;                                // valid output rows (columns of P)
   int Pw, Qw, ldq;                      // widths of P and Q (multiples of 32); ldq = leading dimension of a partial row
-  int q0[4], qw[4];                     // column range of every Q tile (qw <= 288, multiple of 32)
+  int q0[4], qw[4];                     // column range of every Q tile (qw <= 320, multiple of 32)
 };
 
 // tcgen05 path (big_gemm.cu)
@@ -27,6 +27,7 @@ int lin_bwd_launch(const LinOperands&, const EpiBwd::Args&, const LinShape&, cud
 int lin_head_launch(const LinOperands&, const EpiHead::Args&, const LinShape&, cudaStream_t);
 int lin_sample_launch(const LinOperands&, const EpiSample::Args&, const LinShape&, cudaStream_t);
 int grad_gemm_launch(const float* P, int ldp, const float* Q, int ldq_in, float* partial, GradShape sh, cudaStream_t st);
+int grad_gemm_pair_launch(const float* P, int ldp, const float* Q, int ldq_in, float* partial, GradShape sh, cudaStream_t st);   // big_grad_pair.cu
 
 // exact fp32 path (big_ref.cu): same contracts, FFMA main loops; `scratch` holds one [rows][N] accumulator matrix
 int ref_lin_fwd_launch(const LinOperands&, const EpiFwd::Args&, const LinShape&, float* scratch, cudaStream_t);

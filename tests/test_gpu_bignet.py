@@ -72,7 +72,11 @@ def _tf32_values(shape, rng, scale=1.0):
 
 
 @pytest.mark.parametrize("mode", ["fp32", "tf32"])
-@pytest.mark.parametrize("rows,K,N", [(128, 32, 128), (300, 64, 256), (128, 672, 512), (5000, 512, 512), (1000, 800, 1024), (77, 32, 32)])
+EXT = 64          # csrc/big_epi.cuh kExt: extra columns of a stored activation row (mean, sigma, zeros)
+
+
+@pytest.mark.parametrize("rows,K,N", [(128, 32, 128), (300, 64, 256), (128, 672, 512), (5000, 512, 512), (1000, 800, 1024), (77, 32, 32),
+                                      (40000, 512, 512)])          # 313 row blocks: CTA pairs walking several 256-row blocks
 def test_big_lin_kernel_matches_matmul(rows, K, N, mode):
     """The K-major GEMM kernel (TMA SWIZZLE_128B boxes -> tcgen05.mma kind::tf32 -> TMEM -> epilogue -> TMA store) in isolation."""
     import ctypes as C
@@ -85,7 +89,7 @@ def test_big_lin_kernel_matches_matmul(rows, K, N, mode):
     W = torch.from_numpy(_tf32_values((N, K), rng, 0.25)).to(dev)
     bias = torch.from_numpy(rng.randn(N).astype(np.float32)).to(dev)
     colvec = torch.cat([torch.zeros(N, device=dev), bias]).contiguous()
-    out = torch.full((rows, N + 32), float("nan"), device=dev)
+    out = torch.full((rows, N + EXT), float("nan"), device=dev)
     stats = torch.zeros(rows, 2, device=dev)
     scratch = torch.zeros(rows, N, device=dev)
     check(lib.mappo_debug_big_lin(ptr(A), K, ptr(W), K, ptr(out), ptr(stats), ptr(colvec), ptr(scratch), rows, K, N,
@@ -103,8 +107,11 @@ def test_big_lin_kernel_matches_matmul(rows, K, N, mode):
 
 
 @pytest.mark.parametrize("mode", ["fp32", "tf32"])
-@pytest.mark.parametrize("rows,Pw,M,Qw", [(128, 128, 128, 32), (300, 512, 512, 544), (5000, 512, 512, 672), (2000, 544, 544, 32),
-                                          (700, 256, 256, 800), (40000, 512, 512, 544)])
+@pytest.mark.parametrize("rows,Pw,M,Qw", [(128, 128, 128, 32), (300, 512, 512, 544), (5000, 512, 512, 672), (2000, 576, 576, 32),
+                                          (700, 256, 256, 800), (40000, 512, 512, 544),
+                                          # CTA-pair kernel (P in whole 256-column tiles, Q tiles multiples of 64): 256 + 320, 256 + 256 + 192, one 192
+                                          (300, 512, 512, 576), (5000, 512, 512, 704), (700, 256, 256, 192), (40000, 512, 512, 576),
+                                          (1000, 1024, 1024, 1088)])
 def test_big_grad_kernel_matches_matmul(rows, Pw, M, Qw, mode):
     """The MN-major GEMM kernel (contraction over the rows of two row-major matrices: TMA 128B-swizzle / 32B-atom boxes ->
     tcgen05.mma with SWIZZLE_128B_BASE32B descriptors, row-split partials + slot sum) in isolation."""
