@@ -66,15 +66,15 @@ def _sample(cfg, n, seed):
     return (cent, obs, h, h, acts, v_old, ret, masks, active, lp_old, adv, avail)
 
 
+EXT = 64          # csrc/big_epi.cuh kExt: extra columns of a stored activation row (mean, sigma, zeros)
+
+
 def _tf32_values(shape, rng, scale=1.0):
     """Random fp32 values exactly representable in tf32 (so a tf32 GEMM with fp32 accumulation is exact up to summation order)."""
     return (np.round(rng.randn(*shape) * 64 * scale) / 64).astype(np.float32)
 
 
 @pytest.mark.parametrize("mode", ["fp32", "tf32"])
-EXT = 64          # csrc/big_epi.cuh kExt: extra columns of a stored activation row (mean, sigma, zeros)
-
-
 @pytest.mark.parametrize("rows,K,N", [(128, 32, 128), (300, 64, 256), (128, 672, 512), (5000, 512, 512), (1000, 800, 1024), (77, 32, 32),
                                       (40000, 512, 512)])          # 313 row blocks: CTA pairs walking several 256-row blocks
 def test_big_lin_kernel_matches_matmul(rows, K, N, mode):
