@@ -36,8 +36,19 @@ for st in $STAGES; do
     smoke)
       timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 ;;
     sanitizer)
-      timeout 1500 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_bignet.py -q -k "h128 or h256" -x 2>&1 | tail -40 > gpurun_out/r2_sanitizer_memcheck_big.log
-      tail -15 gpurun_out/r2_sanitizer_memcheck_big.log ;;
+      # compute-sanitizer over the hand-rolled synchronisation: mbarrier / TMA / tcgen05 pipelines, cluster kernels, peer flags
+      timeout 1200 compute-sanitizer --tool memcheck --print-limit 30 python -m pytest -q -x -m gpu \
+          "tests/test_gpu_bignet.py::test_big_lin_kernel_matches_matmul" "tests/test_gpu_bignet.py::test_big_grad_kernel_matches_matmul" \
+          "tests/test_gpu_bignet.py::test_ppo_update_gradients_match_oracle" "tests/test_gpu_tensorcore.py::test_fused_optimiser_tail_matches_the_separate_launches" \
+          "tests/test_gpu_mpe_env.py" -k "not 40000" 2>&1 | tail -25 > gpurun_out/r2_sanitizer_memcheck.log
+      tail -8 gpurun_out/r2_sanitizer_memcheck.log
+      timeout 1200 compute-sanitizer --tool racecheck --print-limit 30 python -m pytest -q -x -m gpu \
+          "tests/test_gpu_tensorcore.py::test_tf32_first_update_gradients" "tests/test_gpu_tensorcore.py::test_fused_optimiser_tail_matches_the_separate_launches" \
+          "tests/test_gpu_bignet.py::test_ppo_update_gradients_match_oracle" -k "c1_mlp or c2_mlp or h128 or h256" 2>&1 | tail -25 > gpurun_out/r2_sanitizer_racecheck.log
+      tail -8 gpurun_out/r2_sanitizer_racecheck.log ;;
+    c4bench)
+      timeout 900 python bench.py --config c4 --steps 3 --no-extras --cpu-iters 0 > gpurun_out/s_c4bench.json 2> gpurun_out/s_c4bench.err
+      tail -c 1500 gpurun_out/s_c4bench.json; tail -3 gpurun_out/s_c4bench.err ;;
   esac
 done
 echo "=== done $(date +%T)"
