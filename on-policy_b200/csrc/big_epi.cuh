@@ -55,6 +55,9 @@ struct EpiFwd {
   };
   struct Row { float rs_in, c_in, sum, sumsq; };
   struct Thread {};
+  // partial row sums handed from one epilogue group to the other when the N tiles of a row are split between them
+  __device__ static void get_part(const Row& w, float* p) { p[0] = w.sum; p[1] = w.sumsq; }
+  __device__ static void add_part(Row& w, const float* p) { w.sum += p[0]; w.sumsq += p[1]; }
   __device__ static void init_thread(Thread&) {}
   __device__ static void finish_thread(const Args&, Thread&, double*, int, int) {}
   __device__ static void begin_row(const Args& a, Row& w, int grow) {
@@ -114,6 +117,8 @@ struct EpiBwd {
   };
   struct Row { float mu, rs, m1, m2, rs_prev, S1, S2; };
   struct Thread {};
+  __device__ static void get_part(const Row& w, float* p) { p[0] = w.S1; p[1] = w.S2; }
+  __device__ static void add_part(Row& w, const float* p) { w.S1 += p[0]; w.S2 += p[1]; }
   __device__ static void init_thread(Thread&) {}
   __device__ static void finish_thread(const Args&, Thread&, double*, int, int) {}
   __device__ static void begin_row(const Args& a, Row& w, int grow) {
@@ -172,6 +177,8 @@ struct EpiHead {
   };
   struct Row { float rs, c, S1, S2; RowIn rin; int gr; };
   struct Thread { double acc[3]; };
+  __device__ static void get_part(const Row&, float*) {}          // (N = 32: one tile per row)
+  __device__ static void add_part(Row&, const float*) {}
   __device__ static void init_thread(Thread& t) { t.acc[0] = t.acc[1] = t.acc[2] = 0.0; }
   // every thread of the CTA calls this once at the end (non-epilogue threads carry zeros); sred: [2 * 32] doubles
   __device__ static void finish_thread(const Args& a, Thread& t, double* sred, int tid, int nthreads) {
@@ -247,6 +254,8 @@ struct EpiSample {
   };
   struct Row { float rs, c; };
   struct Thread {};
+  __device__ static void get_part(const Row&, float*) {}
+  __device__ static void add_part(Row&, const float*) {}
   __device__ static void init_thread(Thread&) {}
   __device__ static void finish_thread(const Args&, Thread&, double*, int, int) {}
   __device__ static void begin_row(const Args& a, Row& w, int grow) {

@@ -28,22 +28,28 @@ constexpr int kNS = 4;                    // staging slots (16 KB each)
 constexpr int kAinDepth = 2;              // activation tiles in flight ahead of the epilogue (EpiBwd)
 constexpr int kABytes = 128 * 128;        // A stage: 128 rows x 32 tf32
 
-struct LinSmem { int stage_bytes, stages_off, slots_off, colvec_off, scratch_off, bars_off, total; };
+struct LinSmem { int stage_bytes, stages_off, slots_off, colvec_off, scratch_off, rowpart_off, bars_off, total; };
+constexpr int kNSPair = 3;                // staging slots of EACH of the two epilogue groups of the pair kernel
 // pair: each CTA of a cta_group::2 pair stages its 128 rows of A and HALF of the B tile (BN / 2 rows of W)
 __host__ __device__ inline LinSmem make_lin_smem(int BN, int n_stages, int N_cv, bool scratch, bool pair = false) {
   LinSmem s;
   s.stage_bytes = kABytes + (pair ? BN / 2 : BN) * 128;
   s.stages_off = 0;
   s.slots_off = n_stages * s.stage_bytes;
-  s.colvec_off = s.slots_off + kNS * 16384;
+  s.colvec_off = s.slots_off + (pair ? 2 * kNSPair : kNS) * 16384;
   s.scratch_off = s.colvec_off + ((2 * N_cv * 4 + 127) & ~127);
-  s.bars_off = s.scratch_off + (scratch ? 32 * kLgLd * 4 : 0);
+  s.rowpart_off = s.scratch_off + (scratch ? 32 * kLgLd * 4 : 0);
+  s.bars_off = s.rowpart_off + (pair ? 3 * 128 * 2 * 4 : 0);
   s.total = s.bars_off + 256;
   return s;
 }
 
+// PAIR: two epilogue groups of four warps (warps 2-5 and 6-9): group q drains accumulator stage q, i.e. every other tile, so every
+// SM sub-partition has two epilogue warps to interleave (a single warp per scheduler left the epilogue latency bound: 0.19 IPC,
+// tensor pipe 47 % busy -- profiles/r2b_ncu_big_lin_full.csv).  The two N tiles of a 512-wide row then belong to different groups:
+// group 0 hands its partial row sums to group 1 through shared memory (rowpart, triple buffered) and group 1 closes the row.
 template <class Epi, bool PAIR>
-__global__ void __launch_bounds__(kLinThreads, 1)
+__global__ void __launch_bounds__(PAIR ? kLinThreads + 128 : kLinThreads, 1)
 big_lin_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapAin,
                const typename Epi::Args ea, const LinShape sh) {
@@ -66,15 +72,19 @@ big_lin_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint64_t* empty = bars + 4;                  // [NST]
   uint64_t* tfull = bars + 8;                  // [2]
   uint64_t* tempty = bars + 10;                // [2]
-  uint64_t* ainfull = bars + 12;               // [kNS]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* ainfull = bars + 12;               // [2 groups][4]
+  uint64_t* rowbar = bars + 20;                // [3]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  float* rowpart = reinterpret_cast<float*>(smem + L.rowpart_off);
+  const int n_threads = PAIR ? kLinThreads + 128 : kLinThreads;
   const uint32_t tmem_cols = (2 * BN <= 32) ? 32u : (2 * BN <= 64 ? 64u : (2 * BN <= 128 ? 128u : (2 * BN <= 256 ? 256u : 512u)));
 
-  for (int i = tid; i < 2 * sh.N; i += kLinThreads) cv[i] = ea.colvec[i];
+  for (int i = tid; i < 2 * sh.N; i += n_threads) cv[i] = ea.colvec[i];
   if (tid == 0) {
     for (int i = 0; i < NST; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, PAIR ? 256 : 128); }
-    for (int i = 0; i < kNS; ++i) mbar_init(ainfull + i, 1);
+    for (int i = 0; i < 8; ++i) mbar_init(ainfull + i, 1);
+    for (int i = 0; i < 3; ++i) mbar_init(rowbar + i, 128);
     mbar_fence_init();
     tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapB);
     if (Epi::kStoresOut) tma_prefetch_desc(&mapOut);
@@ -144,87 +154,103 @@ big_lin_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
     }
   } else {
-    // ===================== epilogue (128 threads) =====================
-    const int et = tid - 64;                              // 0..127
+    // ===================== epilogue (one or two groups of 128 threads) =====================
+    constexpr int NG = PAIR ? 2 : 1;
+    constexpr int NSg = PAIR ? kNSPair : kNS;
+    const int grp = PAIR ? (warp - 2) >> 2 : 0;
+    const int et = (tid - 64) & 127;                      // 0..127 within the group
     const int r = (warp & 3) * 32 + lane;                 // TMEM lane = row of the tile (a warp may only touch lanes 32 (warp % 4)..)
     const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
-    uint8_t* slots = smem + L.slots_off;
-    const int CPR = sh.N / kChunk;                        // chunks per row block
+    uint8_t* slots = smem + L.slots_off + grp * NSg * 16384;
+    uint64_t* ainf = ainfull + grp * 4;
+    const int barid = 1 + grp;
+    const int CPT = BN / kChunk;                          // chunks per tile
     const int my_rbs = unit < n_ublocks ? (n_ublocks - unit + n_units - 1) / n_units : 0;
-    const long long total_chunks = (long long)my_rbs * CPR;
-    auto issue_ain = [&](long long g) {                   // thread et == 0 only
+    const int my_tiles = my_rbs * NT;                     // tiles of this CTA; group q takes tiles q, q + NG, ...
+    const int my_gtiles = my_tiles > grp ? (my_tiles - grp + NG - 1) / NG : 0;
+    const long long total_chunks = (long long)my_gtiles * CPT;
+    auto row_of = [&](int rbl) { const int ubl = unit + rbl * n_units; return (PAIR ? 2 * ubl + (int)rank : ubl) * 128; };
+    auto issue_ain = [&](long long g) {                   // thread et == 0 of the group only; g = chunk index within the group
       if (g >= total_chunks) return;
-      const int rbl = (int)(g / CPR), c = (int)(g % CPR);
-      const int slot = (int)(g % kNS);
-      mbar_expect_tx(ainfull + slot, 16384u);
-      const int ubl = unit + rbl * n_units;
-      tma_load_2d(slots + slot * 16384, &mapAin, c * kChunk, (PAIR ? 2 * ubl + (int)rank : ubl) * 128, ainfull + slot);
+      const int tile = (int)(g / CPT) * NG + grp, c = (int)(g % CPT);
+      const int slot = (int)(g % NSg);
+      mbar_expect_tx(ainf + slot, 16384u);
+      tma_load_2d(slots + slot * 16384, &mapAin, (tile % NT) * BN + c * kChunk, row_of(tile / NT), ainf + slot);
     };
     if (Epi::kHasAin && et == 0)
       for (int i = 0; i < kAinDepth; ++i) issue_ain(i);
-    int as = 0;
-    uint32_t aphase = 0;
-    long long g = 0;                                      // running chunk index of this CTA
-    for (int ub = unit; ub < n_ublocks; ub += n_units) {
-      const int rb = PAIR ? 2 * ub + (int)rank : ub;
-      const int grow = rb * 128 + r;
-      typename Epi::Row row;
-      Epi::begin_row(ea, row, grow);
-      for (int nt = 0; nt < NT; ++nt) {
-        mbar_wait(tfull + as, aphase);
-        tc_fence_after();
-        for (int c = 0; c < BN / kChunk; ++c, ++g) {
-          const int col0 = nt * BN + c * kChunk;
-          float acc[kChunk], ain[kChunk], out[kChunk];
-          tmem_ld32(tmem + lane_base + (uint32_t)(as * BN + c * kChunk), acc);
-          tmem_ld_wait();
-          if (c == BN / kChunk - 1) {                     // last read of this accumulator stage: hand it back to the MMA warp
-            tc_fence_before();
-            if (PAIR) mbar_arrive_leader(tempty + as); else mbar_arrive(tempty + as);
-          }
-          const int slot = (int)(g % kNS);
-          uint8_t* sl = slots + slot * 16384;
-          if (Epi::kHasAin) {
-            mbar_wait(ainfull + slot, (uint32_t)((g / kNS) & 1));
-#pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
-              const float4 v = *reinterpret_cast<const float4*>(sl + sw128_off(r, ch));
-              ain[4 * ch] = v.x; ain[4 * ch + 1] = v.y; ain[4 * ch + 2] = v.z; ain[4 * ch + 3] = v.w;
-            }
-          } else if (Epi::kStoresOut && sh.store_out) {
-            if (et == 0) tma_store_wait_read<kNS - 1>();  // the store that last used this slot has read it
-            named_bar_sync(1, 128);
-          }
-          Epi::chunk(ea, th, row, acc, ain, out, col0, cv, scratch, r, grow);
-          if (Epi::kStoresOut && sh.store_out) {
-#pragma unroll
-            for (int ch = 0; ch < 8; ++ch)
-              *reinterpret_cast<float4*>(sl + sw128_off(r, ch)) = make_float4(out[4 * ch], out[4 * ch + 1], out[4 * ch + 2], out[4 * ch + 3]);
-            fence_async_smem();
-            named_bar_sync(1, 128);
-            if (et == 0) {
-              tma_store_2d(&mapOut, col0, rb * 128, sl);
-              tma_store_commit();
-              if (Epi::kHasAin) {                          // refill: slot of chunk g + depth was last stored by chunk g + depth - kNS
-                tma_store_wait_read<kNS - kAinDepth>();
-                issue_ain(g + kAinDepth);
-              }
-            }
-          } else if (Epi::kHasAin) {
-            named_bar_sync(1, 128);
-            if (et == 0) issue_ain(g + kAinDepth);
-          }
-        }
-        as ^= 1;
-        if (as == 0) aphase ^= 1;
+    long long g = 0;                                      // running chunk index of this group
+    typename Epi::Row row;
+    int cur_rbl = -1, rb128 = 0, grow = 0;
+    for (int tile = grp; tile < my_tiles; tile += NG) {
+      const int rbl = tile / NT, nt = tile % NT;
+      const int as = tile & 1;
+      const uint32_t aphase = (uint32_t)((tile >> 1) & 1);
+      if (rbl != cur_rbl) {
+        cur_rbl = rbl;
+        rb128 = row_of(rbl);
+        grow = rb128 + r;
+        Epi::begin_row(ea, row, grow);
       }
-      Epi::end_row(ea, row, grow);
+      mbar_wait(tfull + as, aphase);
+      tc_fence_after();
+      for (int c = 0; c < CPT; ++c, ++g) {
+        const int col0 = nt * BN + c * kChunk;
+        float acc[kChunk], ain[kChunk], out[kChunk];
+        tmem_ld32(tmem + lane_base + (uint32_t)(as * BN + c * kChunk), acc);
+        tmem_ld_wait();
+        if (c == CPT - 1) {                               // last read of this accumulator stage: hand it back to the MMA warp
+          tc_fence_before();
+          if (PAIR) mbar_arrive_leader(tempty + as); else mbar_arrive(tempty + as);
+        }
+        const int slot = (int)(g % NSg);
+        uint8_t* sl = slots + slot * 16384;
+        if (Epi::kHasAin) {
+          mbar_wait(ainf + slot, (uint32_t)((g / NSg) & 1));
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            const float4 v = *reinterpret_cast<const float4*>(sl + sw128_off(r, ch));
+            ain[4 * ch] = v.x; ain[4 * ch + 1] = v.y; ain[4 * ch + 2] = v.z; ain[4 * ch + 3] = v.w;
+          }
+        } else if (Epi::kStoresOut && sh.store_out) {
+          if (et == 0) tma_store_wait_read<NSg - 1>();    // the store that last used this slot has read it
+          named_bar_sync(barid, 128);
+        }
+        Epi::chunk(ea, th, row, acc, ain, out, col0, cv, scratch, r, grow);
+        if (Epi::kStoresOut && sh.store_out) {
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch)
+            *reinterpret_cast<float4*>(sl + sw128_off(r, ch)) = make_float4(out[4 * ch], out[4 * ch + 1], out[4 * ch + 2], out[4 * ch + 3]);
+          fence_async_smem();
+          named_bar_sync(barid, 128);
+          if (et == 0) {
+            tma_store_2d(&mapOut, col0, rb128, sl);
+            tma_store_commit();
+            if (Epi::kHasAin) {                            // refill: the slot of chunk g + depth was last stored by chunk g + depth - NSg
+              tma_store_wait_read<NSg - kAinDepth>();
+              issue_ain(g + kAinDepth);
+            }
+          }
+        } else if (Epi::kHasAin) {
+          named_bar_sync(barid, 128);
+          if (et == 0) issue_ain(g + kAinDepth);
+        }
+      }
+      if (nt + NG >= NT) {                                 // this group's last tile of the row
+        if (NG == 2 && NT > 1) {                           // (NT even: group 0 owns the even tiles, group 1 the odd ones and the end of the row)
+          float* rp = rowpart + ((rbl % 3) * 128 + r) * 2;
+          if (grp == 0) { Epi::get_part(row, rp); mbar_arrive(rowbar + rbl % 3); }
+          else { mbar_wait(rowbar + rbl % 3, (uint32_t)((rbl / 3) & 1)); Epi::add_part(row, rp); Epi::end_row(ea, row, grow); }
+        } else {
+          Epi::end_row(ea, row, grow);
+        }
+      }
     }
     if (et == 0) tma_store_wait_all<0>();
   }
   tc_fence_before();
   if (PAIR) cluster_sync(); else __syncthreads();                // (pair: nobody leaves while the peer may still signal its barriers / read its tiles)
-  Epi::finish_thread(ea, th, sred, tid, kLinThreads);
+  Epi::finish_thread(ea, th, sred, tid, n_threads);
   if (warp == 1) { if (PAIR) tmem_dealloc_pair(tmem, tmem_cols); else tmem_dealloc(tmem, tmem_cols); }
 }
 
@@ -240,8 +266,8 @@ constexpr int kGradStages = 4;
 constexpr int kGradStageBytes = (4 + 10) * kGradGroupBytes;     // P: 4 groups, Q: up to 10 groups (320 columns)
 
 __global__ void __launch_bounds__(kLinThreads, 1)
-big_grad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapQ, float* __restrict__ partial,
-                const GradShape sh) {
+big_grad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapQ8, const __grid_constant__ CUtensorMap mapQr,
+                float* __restrict__ partial, const GradShape sh) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint64_t full[kGradStages], empty[kGradStages], done;
   __shared__ uint32_t tmem_slot;
@@ -257,7 +283,7 @@ big_grad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
     for (int i = 0; i < kGradStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
     mbar_init(&done, 1);
     mbar_fence_init();
-    tma_prefetch_desc(&mapP); tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapP); tma_prefetch_desc(&mapQ8); tma_prefetch_desc(&mapQr);
   }
   if (warp == 1) tmem_alloc(&tmem_slot, 512);
   tc_fence_before();
@@ -275,8 +301,11 @@ big_grad_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant_
       const int row = r0 + kb * kGradKR;
       // rows beyond r1 belong to the next split: they must not be counted twice -> the row coordinate is clamped by
       // rows_per_split being a multiple of kGradKR (host), only the LAST split can run past `rows` (TMA zero fill)
-      for (int i = 0; i < 4; ++i) tma_load_2d(sP + i * kGradGroupBytes, &mapP, mt * 128 + i * 32, row, full + stage);
-      for (int i = 0; i < qgroups; ++i) tma_load_2d(sQ + i * kGradGroupBytes, &mapQ, q0 + i * 32, row, full + stage);
+      // one 3-D box per operand part: [groups][32 rows][32 columns]
+      tma_load_3d(sP, &mapP, 0, row, mt * 4, full + stage);
+      const int g8 = qgroups < 8 ? 0 : 8;                 // a whole 256-column part through the 8-group map
+      if (g8) tma_load_3d(sQ, &mapQ8, 0, row, q0 / 32, full + stage);
+      if (qgroups - g8 > 0) tma_load_3d(sQ + g8 * kGradGroupBytes, &mapQr, 0, row, q0 / 32 + g8, full + stage);
       if (++stage == kGradStages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1 && lane == 0) {
@@ -363,6 +392,27 @@ int make_map(CUtensorMap* m, const float* base, long long width, long long rows,
   return MAPPO_OK;
 }
 
+// 3-D fp32 map over a row-major matrix [rows][width] (leading dimension ld) seen as [width / 32 column groups][rows][32]:
+// ONE box {32 columns, box_rows, box_groups} lands in shared memory as [group][row][32] -- the MN-major operand layout of the
+// weight-gradient GEMMs -- so a stage is filled by one TMA instruction per operand instead of one per 32-column group
+int make_map3(CUtensorMap* m, const float* base, long long width, long long rows, long long ld, int box_rows, int box_groups) {
+  int rc = ensure_encode();
+  if (rc) return rc;
+  cuuint64_t dims[3] = {32, (cuuint64_t)rows, (cuuint64_t)((width + 31) / 32)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(float), 128};
+  cuuint32_t box[3] = {32, (cuuint32_t)box_rows, (cuuint32_t)box_groups};
+  cuuint32_t es[3] = {1, 1, 1};
+  const CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (3-D) failed (%d): base %p width %lld rows %lld ld %lld box %d rows x %d groups", (int)r, (const void*)base,
+              width, rows, ld, box_rows, box_groups);
+    return MAPPO_ERR_CUDA;
+  }
+  return MAPPO_OK;
+}
+
 // pair mode (cta_group::2, 256-row tiles): halves the B-operand traffic per SM, which is what bounds the 128-row kernel
 // (48 KB of operands per 2.1 MFLOP k-step); used for every 256-wide N tile with at least two row blocks (the wave count is the
 // same as with single CTAs).  MAPPO_B200_PAIR=0 forces the single-CTA kernel.
@@ -375,7 +425,8 @@ static bool pair_enabled() {
 template <class Epi>
 static int lin_launch_t(const LinOperands& o, const typename Epi::Args& ea, LinShape sh, const char* name, cudaStream_t st) {
   sh.n_rowblocks = (sh.n_rows + 127) / 128;
-  const bool pair = pair_enabled() && sh.BN == 256 && sh.n_rowblocks >= 2 && o.sm_count >= 2;
+  const int NT = sh.N / sh.BN;
+  const bool pair = pair_enabled() && sh.BN == 256 && (NT == 1 || NT % 2 == 0) && sh.n_rowblocks >= 2 && o.sm_count >= 2;
   CUtensorMap mA, mB, mO, mI;
   int rc = make_map(&mA, o.A, sh.K, sh.n_rows, o.lda, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
@@ -384,7 +435,7 @@ static int lin_launch_t(const LinOperands& o, const typename Epi::Args& ea, LinS
   mO = mA; mI = mA;
   if (Epi::kStoresOut && sh.store_out) { rc = make_map(&mO, o.out, sh.N, sh.n_rows, o.ldo, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B); if (rc) return rc; }
   if (Epi::kHasAin) { rc = make_map(&mI, o.ain, sh.N, sh.n_rows, o.ldain, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B); if (rc) return rc; }
-  sh.n_stages = pair ? 4 : (sh.BN >= 256 ? 3 : 4);
+  sh.n_stages = pair ? 3 : (sh.BN >= 256 ? 3 : 4);     // pair: 3 x 32 KB of operands + 2 x 3 x 16 KB of staging slots
   const LinSmem L = make_lin_smem(sh.BN, sh.n_stages, sh.N, Epi::kNeedsScratch, pair);
   const size_t bytes = (size_t)L.total + 1024;
   if (bytes > 227 * 1024) { set_error("%s: %zu B shared memory > 227 KB (N = %d)", name, bytes, sh.N); return MAPPO_ERR_UNSUPPORTED; }
@@ -395,7 +446,7 @@ static int lin_launch_t(const LinOperands& o, const typename Epi::Args& ea, LinS
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(2 * (n_ublocks < max_pairs ? n_ublocks : max_pairs));
-    cfg.blockDim = dim3(kLinThreads);
+    cfg.blockDim = dim3(kLinThreads + 128);
     cfg.dynamicSmemBytes = bytes;
     cfg.stream = st;
     cudaLaunchAttribute attr;
@@ -418,15 +469,18 @@ int lin_head_launch(const LinOperands& o, const EpiHead::Args& ea, const LinShap
 int lin_sample_launch(const LinOperands& o, const EpiSample::Args& ea, const LinShape& sh, cudaStream_t st) { return lin_launch_t<EpiSample>(o, ea, sh, "big_lin_kernel<EpiSample>", st); }
 
 int grad_gemm_launch(const float* P, int ldp, const float* Q, int ldq_in, float* partial, GradShape sh, cudaStream_t st) {
-  CUtensorMap mP, mQ;
-  int rc = make_map(&mP, P, sh.Pw, sh.rows, ldp, 32, kGradKR, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  CUtensorMap mP, mQ8, mQr;
+  const int last = sh.qw[sh.n_tiles - 1] / 32, rem = last >= 8 ? last - 8 : last;       // groups the last tile loads through mapQr
+  int rc = make_map3(&mP, P, sh.Pw, sh.rows, ldp, kGradKR, 4);
   if (rc) return rc;
-  rc = make_map(&mQ, Q, sh.Qw, sh.rows, ldq_in, 32, kGradKR, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  rc = make_map3(&mQ8, Q, sh.Qw, sh.rows, ldq_in, kGradKR, 8);
+  if (rc) return rc;
+  rc = make_map3(&mQr, Q, sh.Qw, sh.rows, ldq_in, kGradKR, rem > 0 ? rem : 1);
   if (rc) return rc;
   const size_t bytes = (size_t)kGradStages * kGradStageBytes + 1024;
   if (cudaFuncSetAttribute(big_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
     return check_launch("big_grad_kernel: cudaFuncSetAttribute");
-  big_grad_kernel<<<sh.splits * sh.m_tiles * sh.n_tiles, kLinThreads, bytes, st>>>(mP, mQ, partial, sh);
+  big_grad_kernel<<<sh.splits * sh.m_tiles * sh.n_tiles, kLinThreads, bytes, st>>>(mP, mQ8, mQr, partial, sh);
   return check_launch("big_grad_kernel");
 }
 

@@ -21,8 +21,8 @@ constexpr int kGPStages = 6;
 constexpr int kGPStageBytes = (4 + 5) * kGPGroup;       // per CTA: 4 P groups + up to 5 Q groups (160 of 320 columns)
 
 __global__ void __launch_bounds__(kGPThreads, 1)
-big_grad_pair_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapQ, float* __restrict__ partial,
-                     const GradShape sh) {
+big_grad_pair_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapQ4, const __grid_constant__ CUtensorMap mapQa,
+                     const __grid_constant__ CUtensorMap mapQb, float* __restrict__ partial, const GradShape sh) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint64_t full[kGPStages], empty[kGPStages], done;
   __shared__ uint32_t tmem_slot;
@@ -41,7 +41,7 @@ big_grad_pair_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_cons
     for (int i = 0; i < kGPStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
     mbar_init(&done, 1);
     mbar_fence_init();
-    tma_prefetch_desc(&mapP); tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapP); tma_prefetch_desc(&mapQ4); tma_prefetch_desc(&mapQa); tma_prefetch_desc(&mapQb);
   }
   if (warp == 1) tmem_alloc_pair(&tmem_slot, 512);
   tc_fence_before();
@@ -59,9 +59,11 @@ big_grad_pair_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_cons
       if (rank == 0) mbar_expect_tx(full + stage, 2u * stage_tx);         // the pair's bytes land on the leader's barrier
       const uint32_t lb = leader_addr(full + stage);
       const int row = r0 + kb * kGPKR;
-      for (int i = 0; i < 4; ++i) tma_load_2d_pair(sP + i * kGPGroup, &mapP, mt * 256 + (int)rank * 128 + i * 32, row, lb);
-      for (int i = 0; i < g1; ++i) tma_load_2d_pair(sQ + i * kGPGroup, &mapQ, q0 + (int)rank * (n1 / 2) + i * 32, row, lb);
-      for (int i = 0; i < g2; ++i) tma_load_2d_pair(sQ + (g1 + i) * kGPGroup, &mapQ, q0 + n1 + (int)rank * (n2 / 2) + i * 32, row, lb);
+      // one 3-D box per operand part ([groups][32 rows][32 columns]): this CTA's 4 groups of P, its half of the N = n1 part of Q
+      // (4 groups through mapQ4, fewer through mapQa) and its half of the N = 64 part (mapQb, one group)
+      tma_load_3d_pair(sP, &mapP, 0, row, mt * 8 + (int)rank * 4, lb);
+      tma_load_3d_pair(sQ, g1 == 4 ? &mapQ4 : &mapQa, 0, row, q0 / 32 + (int)rank * g1, lb);
+      if (g2 > 0) tma_load_3d_pair(sQ + g1 * kGPGroup, &mapQb, 0, row, (q0 + n1) / 32 + (int)rank * g2, lb);
       if (++stage == kGPStages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1 && lane == 0 && rank == 0) {
@@ -108,16 +110,21 @@ big_grad_pair_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_cons
   if (warp == 1) tmem_dealloc_pair(tmem, 512);
 }
 
-int make_map(CUtensorMap* m, const float* base, long long width, long long rows, long long ld, int box_w, int box_h, int swizzle);
+int make_map3(CUtensorMap* m, const float* base, long long width, long long rows, long long ld, int box_rows, int box_groups);
 
-// sh: m_tiles counts 256-column tiles of P; every qw is a multiple of 64
+// sh: m_tiles counts 256-column tiles of P; every qw is a multiple of 64 (<= 320; only the last tile may differ from 256)
 int grad_gemm_pair_launch(const float* P, int ldp, const float* Q, int ldq_in, float* partial, GradShape sh, cudaStream_t st) {
   for (int i = 0; i < sh.n_tiles; ++i)
-    if (sh.qw[i] % 64 || sh.qw[i] > 320) { set_error("grad_gemm_pair: tile of %d columns", sh.qw[i]); return MAPPO_ERR_INVALID; }
-  CUtensorMap mP, mQ;
-  int rc = make_map(&mP, P, sh.Pw, sh.rows, ldp, 32, kGPKR, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (sh.qw[i] % 64 || sh.qw[i] > 320 || (i + 1 < sh.n_tiles && sh.qw[i] != 256)) { set_error("grad_gemm_pair: tile of %d columns", sh.qw[i]); return MAPPO_ERR_INVALID; }
+  const int lw = sh.qw[sh.n_tiles - 1], l1 = (lw > 256 ? 256 : lw) / 64;              // groups per CTA of the last tile's first part
+  CUtensorMap mP, mQ4, mQa, mQb;
+  int rc = make_map3(&mP, P, sh.Pw, sh.rows, ldp, kGPKR, 4);
   if (rc) return rc;
-  rc = make_map(&mQ, Q, sh.Qw, sh.rows, ldq_in, 32, kGPKR, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  rc = make_map3(&mQ4, Q, sh.Qw, sh.rows, ldq_in, kGPKR, 4);
+  if (rc) return rc;
+  rc = make_map3(&mQa, Q, sh.Qw, sh.rows, ldq_in, kGPKR, l1);
+  if (rc) return rc;
+  rc = make_map3(&mQb, Q, sh.Qw, sh.rows, ldq_in, kGPKR, 1);
   if (rc) return rc;
   const size_t bytes = (size_t)kGPStages * kGPStageBytes + 1024;
   if (cudaFuncSetAttribute(big_grad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
@@ -132,7 +139,7 @@ int grad_gemm_pair_launch(const float* P, int ldp, const float* Q, int ldq_in, f
   attr.id = cudaLaunchAttributeClusterDimension;
   attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
   cfg.attrs = &attr; cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, big_grad_pair_kernel, mP, mQ, partial, sh);
+  cudaLaunchKernelEx(&cfg, big_grad_pair_kernel, mP, mQ4, mQa, mQb, partial, sh);
   return check_launch("big_grad_pair_kernel");
 }
 
