@@ -29,14 +29,17 @@ constexpr int kAinDepth = 2;              // activation tiles in flight ahead of
 constexpr int kABytes = 128 * 128;        // A stage: 128 rows x 32 tf32
 
 struct LinSmem { int stage_bytes, stages_off, slots_off, colvec_off, scratch_off, rowpart_off, bars_off, total; };
-constexpr int kNSPair = 3;                // staging slots of EACH of the two epilogue groups of the pair kernel
+constexpr int kPairGroups = 1;            // epilogue groups of the pair kernel (2 = one per accumulator stage; measured: no gain, the
+                                          // kernel is bound by operand latency, not by the epilogue -- profiles/r2_summary.md)
+constexpr int kNSPair = 3;                // staging slots of each epilogue group of the pair kernel
+constexpr int kPairStages = 5;            // 5 x 32 KB of operands in flight per CTA (the k-step rate is latency / stages)
 // pair: each CTA of a cta_group::2 pair stages its 128 rows of A and HALF of the B tile (BN / 2 rows of W)
 __host__ __device__ inline LinSmem make_lin_smem(int BN, int n_stages, int N_cv, bool scratch, bool pair = false) {
   LinSmem s;
   s.stage_bytes = kABytes + (pair ? BN / 2 : BN) * 128;
   s.stages_off = 0;
   s.slots_off = n_stages * s.stage_bytes;
-  s.colvec_off = s.slots_off + (pair ? 2 * kNSPair : kNS) * 16384;
+  s.colvec_off = s.slots_off + (pair ? kPairGroups * kNSPair : kNS) * 16384;
   s.scratch_off = s.colvec_off + ((2 * N_cv * 4 + 127) & ~127);
   s.rowpart_off = s.scratch_off + (scratch ? 32 * kLgLd * 4 : 0);
   s.bars_off = s.rowpart_off + (pair ? 3 * 128 * 2 * 4 : 0);
@@ -49,7 +52,7 @@ __host__ __device__ inline LinSmem make_lin_smem(int BN, int n_stages, int N_cv,
 // tensor pipe 47 % busy -- profiles/r2b_ncu_big_lin_full.csv).  The two N tiles of a 512-wide row then belong to different groups:
 // group 0 hands its partial row sums to group 1 through shared memory (rowpart, triple buffered) and group 1 closes the row.
 template <class Epi, bool PAIR>
-__global__ void __launch_bounds__(PAIR ? kLinThreads + 128 : kLinThreads, 1)
+__global__ void __launch_bounds__(PAIR ? 64 + 128 * kPairGroups : kLinThreads, 1)
 big_lin_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapAin,
                const typename Epi::Args ea, const LinShape sh) {
@@ -68,15 +71,15 @@ big_lin_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   float* cv = reinterpret_cast<float*>(smem + L.colvec_off);
   float* scratch = reinterpret_cast<float*>(smem + L.scratch_off);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars_off);
-  uint64_t* full = bars;                       // [NST]
-  uint64_t* empty = bars + 4;                  // [NST]
-  uint64_t* tfull = bars + 8;                  // [2]
-  uint64_t* tempty = bars + 10;                // [2]
-  uint64_t* ainfull = bars + 12;               // [2 groups][4]
-  uint64_t* rowbar = bars + 20;                // [3]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  uint64_t* full = bars;                       // [NST <= 6]
+  uint64_t* empty = bars + 6;                  // [NST <= 6]
+  uint64_t* tfull = bars + 12;                 // [2]
+  uint64_t* tempty = bars + 14;                // [2]
+  uint64_t* ainfull = bars + 16;               // [2 groups][4]
+  uint64_t* rowbar = bars + 24;                // [3]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
   float* rowpart = reinterpret_cast<float*>(smem + L.rowpart_off);
-  const int n_threads = PAIR ? kLinThreads + 128 : kLinThreads;
+  const int n_threads = PAIR ? 64 + 128 * kPairGroups : kLinThreads;
   const uint32_t tmem_cols = (2 * BN <= 32) ? 32u : (2 * BN <= 64 ? 64u : (2 * BN <= 128 ? 128u : (2 * BN <= 256 ? 256u : 512u)));
 
   for (int i = tid; i < 2 * sh.N; i += n_threads) cv[i] = ea.colvec[i];
@@ -155,9 +158,9 @@ big_lin_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else {
     // ===================== epilogue (one or two groups of 128 threads) =====================
-    constexpr int NG = PAIR ? 2 : 1;
+    constexpr int NG = PAIR ? kPairGroups : 1;
     constexpr int NSg = PAIR ? kNSPair : kNS;
-    const int grp = PAIR ? (warp - 2) >> 2 : 0;
+    const int grp = NG > 1 ? (warp - 2) >> 2 : 0;
     const int et = (tid - 64) & 127;                      // 0..127 within the group
     const int r = (warp & 3) * 32 + lane;                 // TMEM lane = row of the tile (a warp may only touch lanes 32 (warp % 4)..)
     const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
@@ -435,7 +438,7 @@ static int lin_launch_t(const LinOperands& o, const typename Epi::Args& ea, LinS
   mO = mA; mI = mA;
   if (Epi::kStoresOut && sh.store_out) { rc = make_map(&mO, o.out, sh.N, sh.n_rows, o.ldo, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B); if (rc) return rc; }
   if (Epi::kHasAin) { rc = make_map(&mI, o.ain, sh.N, sh.n_rows, o.ldain, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B); if (rc) return rc; }
-  sh.n_stages = pair ? 3 : (sh.BN >= 256 ? 3 : 4);     // pair: 3 x 32 KB of operands + 2 x 3 x 16 KB of staging slots
+  sh.n_stages = pair ? kPairStages : (sh.BN >= 256 ? 3 : 4);
   const LinSmem L = make_lin_smem(sh.BN, sh.n_stages, sh.N, Epi::kNeedsScratch, pair);
   const size_t bytes = (size_t)L.total + 1024;
   if (bytes > 227 * 1024) { set_error("%s: %zu B shared memory > 227 KB (N = %d)", name, bytes, sh.N); return MAPPO_ERR_UNSUPPORTED; }
@@ -446,7 +449,7 @@ static int lin_launch_t(const LinOperands& o, const typename Epi::Args& ea, LinS
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(2 * (n_ublocks < max_pairs ? n_ublocks : max_pairs));
-    cfg.blockDim = dim3(kLinThreads + 128);
+    cfg.blockDim = dim3(64 + 128 * kPairGroups);
     cfg.dynamicSmemBytes = bytes;
     cfg.stream = st;
     cudaLaunchAttribute attr;

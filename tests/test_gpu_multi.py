@@ -139,5 +139,5 @@ def test_fused_tail_with_the_exchange_inside_matches_the_separate_launches(tmp_p
         mp.spawn(_worker, args=(2, 29700 + os.getpid() % 1000 + int(fused), out), nprocs=2, join=True)
         res[fused] = np.load(out)
     for k in ("actor", "critic", "info", "actor2", "critic2", "info2", "vn"):      # (up to the fp64-atomic noise of the statistics)
-        np.testing.assert_allclose(res["1"][k], res["0"][k], rtol=2e-5, atol=2e-9, err_msg=k)
+        np.testing.assert_allclose(res["1"][k], res["0"][k], rtol=1e-4, atol=5e-6, err_msg=k)
     assert bool(res["1"]["p2p"])
