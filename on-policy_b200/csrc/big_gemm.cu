@@ -416,12 +416,14 @@ int make_map3(CUtensorMap* m, const float* base, long long width, long long rows
   return MAPPO_OK;
 }
 
-// pair mode (cta_group::2, 256-row tiles): halves the B-operand traffic per SM, which is what bounds the 128-row kernel
-// (48 KB of operands per 2.1 MFLOP k-step); used for every 256-wide N tile with at least two row blocks (the wave count is the
-// same as with single CTAs).  MAPPO_B200_PAIR=0 forces the single-CTA kernel.
+// pair mode (cta_group::2, 256-row tiles, each CTA stages half of the B tile): implemented, parity-tested and MEASURED -- it moves
+// a third less operand data per SM (ncu: 672 MB instead of 1008 MB through the crossbar per 512 x 512 layer at c5) and is not
+// faster (22.5 vs 22.9 ms of forward GEMMs per c5 iteration; 3, 4 or 5 operand stages, one or two epilogue groups all land within
+// 5 %): the producer sits waiting for free stages, i.e. the MMA stream itself is the limit (tests/cuda/umma_rate.cu measures the
+// instruction's own rate).  Opt-in with MAPPO_B200_PAIR_LIN=1; the weight-gradient GEMM does use pairs (big_grad_pair.cu, + 5 %).
 static bool pair_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("MAPPO_B200_PAIR"); v = (e && e[0] == '0') ? 0 : 1; }
+  if (v < 0) { const char* e = getenv("MAPPO_B200_PAIR_LIN"); v = (e && e[0] == '1') ? 1 : 0; }
   return v != 0;
 }
 
