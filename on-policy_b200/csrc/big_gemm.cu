@@ -85,7 +85,7 @@ big_lin_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   for (int i = tid; i < 2 * sh.N; i += n_threads) cv[i] = ea.colvec[i];
   if (tid == 0) {
     for (int i = 0; i < NST; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, PAIR ? 256 : 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, PAIR ? 8 : 128); }     // pair: 4 warps x 2 CTAs
     for (int i = 0; i < 8; ++i) mbar_init(ainfull + i, 1);
     for (int i = 0; i < 3; ++i) mbar_init(rowbar + i, 128);
     mbar_fence_init();
@@ -204,7 +204,14 @@ big_lin_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         tmem_ld_wait();
         if (c == CPT - 1) {                               // last read of this accumulator stage: hand it back to the MMA warp
           tc_fence_before();
-          if (PAIR) mbar_arrive_leader(tempty + as); else mbar_arrive(tempty + as);
+          if (PAIR) {
+            // one remote arrive per WARP: a release at cluster scope costs a full memory barrier (ncu: MEMBAR.ALL.GPU + ERRBAR
+            // were the hottest epilogue instructions with one arrive per thread)
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(tempty + as);
+          } else {
+            mbar_arrive(tempty + as);
+          }
         }
         const int slot = (int)(g % NSg);
         uint8_t* sl = slots + slot * 16384;

@@ -889,8 +889,6 @@ __global__ void __cluster_dims__(kTailCtas, 1, 1) __launch_bounds__(kTailThreads
     for (int j = 0; j < kPer; ++j) {
       const int i = tid + j * kTailThreads;
       pr[j] = i < P ? a.p[i] : 0.f;
-      mr[j] = ((a.stages & 2) && i < P) ? a.m[i] : 0.f;
-      vr[j] = ((a.stages & 2) && i < P) ? a.v[i] : 0.f;
     }
     if (tid == 0 && (a.stages & 2)) {
       step_old = *a.step_dev; lr = a.lr_dev[0];
@@ -909,14 +907,33 @@ __global__ void __cluster_dims__(kTailCtas, 1, 1) __launch_bounds__(kTailThreads
         const int vb = unit + kTailUnits * (it * kTailUnroll + u), i = vb * 32 + pi;
         float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
         if (i < R) {
-          int s = sg;
-          for (; s + 24 < a.n_slots; s += 32) {
-            g0 += a.part[(size_t)s * R + i];
-            g1 += a.part[(size_t)(s + 8) * R + i];
-            g2 += a.part[(size_t)(s + 16) * R + i];
-            g3 += a.part[(size_t)(s + 24) * R + i];
+          if (a.n_slots <= 80) {
+            // every slot value of this (element, slot group) is requested before the first add: ONE memory round trip instead of
+            // one per loop iteration (the kernel is a chain of dependent loads: ncu showed 1.7 us of issue in 50 us).  The adds
+            // keep grad_reduce_kernel's order (x + 0.f == x for the padded tail).
+            float v[10];
+#pragma unroll
+            for (int q = 0; q < 10; ++q) {
+              const int s = sg + 8 * q;
+              v[q] = s < a.n_slots ? a.part[(size_t)s * R + i] : 0.f;
+            }
+            int qt = 0;                                    // first slot index of the sequential tail (indices stay compile time)
+#pragma unroll
+            for (int q0 = 0; q0 < 8; q0 += 4)
+              if (qt == q0 && sg + 8 * q0 + 24 < a.n_slots) { g0 += v[q0]; g1 += v[q0 + 1]; g2 += v[q0 + 2]; g3 += v[q0 + 3]; qt = q0 + 4; }
+#pragma unroll
+            for (int q = 0; q < 10; ++q)
+              if (q >= qt) g0 += v[q];
+          } else {
+            int s = sg;
+            for (; s + 24 < a.n_slots; s += 32) {
+              g0 += a.part[(size_t)s * R + i];
+              g1 += a.part[(size_t)(s + 8) * R + i];
+              g2 += a.part[(size_t)(s + 16) * R + i];
+              g3 += a.part[(size_t)(s + 24) * R + i];
+            }
+            for (; s < a.n_slots; s += 8) g0 += a.part[(size_t)s * R + i];
           }
-          for (; s < a.n_slots; s += 8) g0 += a.part[(size_t)s * R + i];
         }
         sacc[sub][u][sg][pi] = (g0 + g1) + (g2 + g3);
       }
@@ -940,6 +957,8 @@ __global__ void __cluster_dims__(kTailCtas, 1, 1) __launch_bounds__(kTailThreads
   for (int j = 0; j < kPer; ++j) {
     const int i = tid + j * kTailThreads;
     if (i < P) p_s[i] = pr[j];
+    mr[j] = ((a.stages & 2) && i < P) ? a.m[i] : 0.f;           // Adam moments: in flight underneath the unfold
+    vr[j] = ((a.stages & 2) && i < P) ? a.v[i] : 0.f;
   }
   __syncthreads();
 
