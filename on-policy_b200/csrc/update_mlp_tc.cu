@@ -1133,6 +1133,8 @@ int update_mlp_tc_tail_launch(const NetDev& n, const float* part, int n_slots, f
   if (bytes > configured) {
     if (cudaFuncSetAttribute(tc_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
       return check_launch("tc_tail_kernel: cudaFuncSetAttribute");
+    // same shared-memory carveout as the update kernel it alternates with on these SMs (no L1 / shared re-partitioning between them)
+    cudaFuncSetAttribute(tc_tail_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = bytes;
   }
   tc_tail_kernel<<<kTailCtas, kTailThreads, bytes, st>>>(a);
