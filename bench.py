@@ -434,6 +434,18 @@ def kernel_roofline(res, a, peaks, tf32_peak):
         for f, v in fl.items():
             table[f]["algorithmic_tflop"] = v / 1e12
             table[f]["tflops"] = v / 1e12 / (table[f]["ms_total"] * 1e-3) if table[f]["ms_total"] > 0 else None
+        # the same launches against the HBM roofline: every [B, 512] fp32 activation (168 MB at c5) is larger than L2, so each GEMM
+        # streams its operands from and its result to HBM once (algorithmic bytes per row)
+        Hx, pad = H + 64, lambda k: (k + 1 + 63) // 64 * 64
+        by = {"fwd_gemm": sum(4 * B * (pad(i) + Hx + L * (H + Hx)) for i in ins) * n_upd,
+              "bwd_gemm": sum(4 * B * (32 + 2 * H + L * 3 * H) for _ in ins) * n_upd,
+              "grad_gemm": sum(4 * B * ((H + pad(i)) + L * (H + Hx) + (Hx + 32)) for i in ins) * n_upd,
+              "head_loss": sum(4 * B * (H + 32) for _ in ins) * n_upd}
+        hbm_peak = float(peaks.get("hbm_gbs", 6580.0))
+        for f, v in by.items():
+            table[f]["algorithmic_gbyte"] = v / 1e9
+            table[f]["hbm_gbs"] = v / 1e9 / (table[f]["ms_total"] * 1e-3) if table[f]["ms_total"] > 0 else None
+            table[f]["hbm_frac"] = table[f]["hbm_gbs"] / hbm_peak if table[f]["hbm_gbs"] else None
         dom = max(("fwd_gemm", "bwd_gemm", "grad_gemm"), key=lambda f: table[f]["ms_total"])
         d = table[dom]
         avg_ms = d["ms_total"] / max(d["launches"], 1)
@@ -448,6 +460,9 @@ def kernel_roofline(res, a, peaks, tf32_peak):
                "avg_launch_ms": avg_ms, "launches_timed": d["launches"],
                "algorithmic_gflop_per_launch": d["algorithmic_tflop"] * 1e3 / max(d["launches"], 1),
                "kernel_share_of_step": d["ms_total"] / res["ms_per_step"],
+               "hbm": {"achieved": d.get("hbm_gbs"), "peak": hbm_peak, "unit": "GB/s", "frac": d.get("hbm_frac"),
+                       "note": "same launches against the HBM roofline (algorithmic operand + result bytes, MEASURED_PEAKS hbm_gbs): the "
+                               "GEMMs of this pipeline sit between both roofs"},
                "pipeline_families": table, "update_pipeline_ms_per_step": pipeline_ms,
                "update_pipeline_tflops": (fa + fc) * n_upd / 1e12 / (pipeline_ms * 1e-3) if pipeline_ms > 0 else None}
     else:
