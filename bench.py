@@ -357,6 +357,8 @@ def run_config(name, a, world, rank, dev, dist, sampler=None, light=False):
     launches = sum(j.eng.launches_per_iteration for j in jobs) * K
 
     # ---- end to end from host buffers (same flush discipline; its ~40 us of device time is inside the wall clock) ----
+    # double-buffered staging: the H2D of the next iteration's inputs overlaps this iteration's graph (engine.enable_input_prefetch)
+    prefetch = all([j.eng.enable_input_prefetch() for j in jobs]) if not getattr(a, "no_prefetch", False) else False
     for _ in range(3):
         step_e2e()
     e2e_blocks = max(1, min(blocks, int(round((0.3 if light else 1.0) / (K * est) + 0.5))))
@@ -389,7 +391,7 @@ def run_config(name, a, world, rank, dev, dist, sampler=None, light=False):
            "e2e_ms_per_step": e2e_ms_step, "e2e_value": steps_env / (e2e_ms_step * 1e-3), "blocks": blocks, "e2e_blocks": len(em),
            "block_ms_per_step": {"min": min(bm) / K, "median": sorted(bm)[len(bm) // 2] / K, "max": max(bm) / K},
            "launches": launches, "h2d": sum(j.eng.h2d_bytes() for j in jobs), "d2h": 48 * len(jobs), "clocks": clocks,
-           "wall_s_timed_region": t_wall, "info": info, "flush": flush, "steps_env": steps_env}
+           "wall_s_timed_region": t_wall, "info": info, "flush": flush, "steps_env": steps_env, "prefetch": bool(prefetch)}
     return res
 
 
@@ -534,7 +536,8 @@ def result_line(name, res, a, world, roof, cpu, clocks, extra_cfg):
             "timing": {"blocks_of_k_steps": res["blocks"], "block_ms_per_step": res["block_ms_per_step"], "e2e_blocks": res["e2e_blocks"],
                        "wall_s_timed_region": res["wall_s_timed_region"]},
             "e2e": {"value": res["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": res["h2d"], "d2h_bytes_per_step": res["d2h"],
-                    "ms_per_step": res["e2e_ms_per_step"]},
+                    "ms_per_step": res["e2e_ms_per_step"],
+                    "input_staging": "double buffered: the H2D of step i + 1 overlaps the graph of step i" if res.get("prefetch") else "synchronous"},
             "gpu_launches": res["launches"], "roofline": roof, "clocks": clocks, "train_info_last": res["info"]}
     if cpu is not None:
         line["cpu_baseline"] = cpu
@@ -678,6 +681,7 @@ def main():
     ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"], help="BASELINE.json workload (default c2 = configs[1])")
     ap.add_argument("--gemm", default=os.environ.get("MAPPO_B200_GEMM", "tf32"), choices=["tf32", "fp32"],
                     help="GEMM engine of the update kernels (tf32 = tcgen05 tensor cores)")
+    ap.add_argument("--no-prefetch", dest="no_prefetch", action="store_true", help="e2e: copy every step's inputs synchronously before its graph")
     ap.add_argument("--eager", action="store_true", help="no CUDA graph (for per-kernel profiling under ncu)")
     ap.add_argument("--env", default="staged", choices=["staged", "device"],
                     help="staged: synthetic env outputs uploaded per iteration (the BASELINE metric: the path only); "
