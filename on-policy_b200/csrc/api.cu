@@ -152,8 +152,14 @@ static int sm_count() {
 using namespace mappo;
 
 
+namespace mappo {
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MAPPO_B200_PDL"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v != 0;
+}
+}  // namespace mappo
 extern "C" {
-
 int32_t mappo_abi_version(void) { return MAPPO_ABI_VERSION; }
 const char* mappo_last_error(void) { return g_err; }
 

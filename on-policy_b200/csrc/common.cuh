@@ -461,6 +461,27 @@ struct SmemConfig {
   }
 };
 
+// ---- programmatic dependent launch (PDL) for the chains of small dependent kernels of an optimiser step -------------------------
+// A kernel launched with launch_pdl() may be SCHEDULED while its stream predecessor still runs: its CTAs take their SMs and park in
+// pdl_prologue() (griddepcontrol.wait) until the predecessor grid has completed and flushed, so the ~2 us of launch / scheduling
+// latency between two dependent kernels of a CUDA graph disappears.  Every kernel of such a chain calls pdl_prologue() first (it
+// also lets ITS successor start scheduling: griddepcontrol.launch_dependents); without the launch attribute both are no-ops.
+bool pdl_enabled();     // api.cu: env MAPPO_B200_PDL
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // error plumbing (api.cu)
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);

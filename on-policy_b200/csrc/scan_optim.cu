@@ -300,6 +300,7 @@ __global__ void __launch_bounds__(256)
 grad_reduce_kernel(const float* __restrict__ part, int n_slots, int P, float* __restrict__ grad,
                    float* __restrict__ sumsq_part) {
   __shared__ float sacc[8][33];
+  pdl_prologue();
   const int pi = threadIdx.x & 31, sg = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + pi;
   float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
@@ -331,7 +332,7 @@ int grad_reduce_launch(const float* part, int n_slots, int P, float* grad, float
                        cudaStream_t st) {
   const int blocks = (P + 31) / 32;
   if (n_blocks_out) *n_blocks_out = blocks;
-  grad_reduce_kernel<<<blocks, 256, 0, st>>>(part, n_slots, P, grad, sumsq_part);
+  launch_pdl(grad_reduce_kernel, dim3(blocks), dim3(256), 0, st, part, n_slots, P, grad, sumsq_part);
   return check_launch("grad_reduce_kernel");
 }
 
@@ -373,6 +374,7 @@ clip_adam_kernel(float* __restrict__ p, const float* __restrict__ grad, float* _
   __shared__ float s_total, s_coef, s_step_size, s_bc2_sqrt;
   __shared__ int s_step;
   __shared__ double s_p1, s_p2;
+  pdl_prologue();
   // this thread's operands first: their latency overlaps the scalar prologue below instead of following it
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   float g_in[VEC], m_in[VEC], v_in[VEC], p_in[VEC];
@@ -460,8 +462,8 @@ int clip_adam_launch(float* p, const float* grad, float* m, float* v, int P, con
     clip_adam_kernel<4><<<(P + 1023) / 1024, 256, 0, st>>>(p, grad, m, v, P, sumsq_part, n_part, lr_dev, step_dev, eps,
                                                            max_norm, use_clip, norm_out, beta_pow);
   else
-    clip_adam_kernel<1><<<(P + 255) / 256, 256, 0, st>>>(p, grad, m, v, P, sumsq_part, n_part, lr_dev, step_dev, eps,
-                                                         max_norm, use_clip, norm_out, beta_pow);
+    launch_pdl(clip_adam_kernel<1>, dim3((P + 255) / 256), dim3(256), 0, st, p, grad, m, v, P, sumsq_part, n_part, lr_dev, step_dev, eps,
+               max_norm, use_clip, norm_out, beta_pow);
   return check_launch("clip_adam_kernel");
 }
 

@@ -249,6 +249,7 @@ __global__ void __launch_bounds__(256)
 tc_unfold_kernel(const NetDev n, const float* __restrict__ p, const float* __restrict__ raw, float* __restrict__ g,
                  float* __restrict__ sumsq_part) {
   __shared__ UnfoldScratch S;
+  pdl_prologue();
   tc_unfold_unit(n, p, raw, g, sumsq_part, blockIdx.x, blockIdx.y, gridDim.x, threadIdx.x, true, S);
 }
 
@@ -297,6 +298,7 @@ __device__ __forceinline__ float pack_tc_element(const NetDev& n, const TcImage&
 }
 __global__ void __launch_bounds__(256) pack_tc_kernel(const NetDev n, const float* __restrict__ p, float* __restrict__ img) {
   const TcImage m = make_tc_image(n);
+  pdl_prologue();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m.total; i += gridDim.x * blockDim.x) img[i] = pack_tc_element(n, m, p, i);
 }
 
@@ -399,6 +401,7 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
                      int n_tiles, uint32_t tmem_cols) {
   extern __shared__ __align__(1024) float smem[];
   __shared__ double sred[2 * 32];
+  pdl_prologue();                                            // (PDL: scheduled under the weight-pack kernel, released when it has finished)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r = tid & (kTM - 1), wg = tid >> 7;              // my row of the tile, my half of the hidden columns
   const TcImage im = make_tc_image(n);
@@ -801,7 +804,7 @@ int update_mlp_tc_slot_floats(const NetDev& n) { return make_tc_raw(make_tc_imag
 // sum of the raw slots is in `raw_sum` -> flat gradient + sum(g^2) (one partial)
 int update_mlp_tc_unfold_launch(const NetDev& n, const float* params, const float* raw_sum, float* grad,
                                 float* sumsq_part, cudaStream_t st) {
-  tc_unfold_kernel<<<dim3(4, 3), 256, 0, st>>>(n, params, raw_sum, grad, sumsq_part);       // 12 partial sums of squares
+  launch_pdl(tc_unfold_kernel, dim3(4, 3), dim3(256), 0, st, n, params, raw_sum, grad, sumsq_part);       // 12 partial sums of squares
   return check_launch("tc_unfold_kernel");
 }
 
@@ -1157,7 +1160,7 @@ int update_mlp_tc_launch(const NetDev& n, const float* params, const BatchDev& b
   const size_t bytes = (size_t)sm.total * sizeof(float) + 1024;
   if (bytes > 227 * 1024) { set_error("update_mlp_tc: %zu B shared memory > 227 KB", bytes); return MAPPO_ERR_UNSUPPORTED; }
   if (!image_ready) {                  // (the fused optimiser tail of the previous step leaves the image of the current weights)
-    pack_tc_kernel<<<(im.total + 255) / 256, 256, 0, st>>>(n, params, image);      // one element per thread
+    launch_pdl(pack_tc_kernel, dim3((im.total + 255) / 256), dim3(256), 0, st, n, params, image);      // one element per thread
     const int rc = check_launch("pack_tc_kernel");
     if (rc) return rc;
   }
@@ -1170,8 +1173,8 @@ int update_mlp_tc_launch(const NetDev& n, const float* params, const BatchDev& b
   }
   const int n_tiles = (b.n_rows + kTM - 1) / kTM;
   const uint32_t cols = 512u;          // accumulators [0,272) + parked xhat0 [272,344): one CTA per SM owns all of TMEM
-  update_mlp_tc_kernel<<<n_slots, kTCThreads, bytes, st>>>(n, params, image, b, L, norm_stats, adv_stats, vn_state, grad_part,
-                                                           loss_out, n_tiles, cols);
+  launch_pdl(update_mlp_tc_kernel, dim3(n_slots), dim3(kTCThreads), bytes, st, n, params, image, b, L, norm_stats, adv_stats, vn_state, grad_part,
+             loss_out, n_tiles, cols);
   return check_launch("update_mlp_tc_kernel");
 }
 
