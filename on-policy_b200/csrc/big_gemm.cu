@@ -95,7 +95,8 @@ big_lin_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
   if (warp == 1) { if (PAIR) tmem_alloc_pair(tmem_slot, tmem_cols); else tmem_alloc(tmem_slot, tmem_cols); }
   tc_fence_before();
-  if (PAIR) cluster_sync(); else __syncthreads();                // (pair: the peer's barriers are initialised before anything signals them)
+  if (PAIR) cluster_sync();                                      // (pair: the peer's barriers are initialised before anything signals them)
+  __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   typename Epi::Thread th;

@@ -46,6 +46,7 @@ big_grad_pair_kernel(const __grid_constant__ CUtensorMap mapP, const __grid_cons
   if (warp == 1) tmem_alloc_pair(&tmem_slot, 512);
   tc_fence_before();
   cluster_sync();
+  __syncthreads();             // (the cluster barrier already orders the allocator's write of tmem_slot; racecheck only models bar.sync)
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   const uint32_t stage_tx = (uint32_t)((4 + g1 + g2) * kGPGroup);         // bytes ONE CTA loads per stage
