@@ -181,7 +181,8 @@ big_lin_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_expect_tx(ainf + slot, 16384u);
       tma_load_2d(slots + slot * 16384, &mapAin, (tile % NT) * BN + c * kChunk, row_of(tile / NT), ainf + slot);
     };
-    if (Epi::kHasAin && et == 0)
+    const bool direct = sh.direct != 0;
+    if (Epi::kHasAin && et == 0 && !direct)
       for (int i = 0; i < kAinDepth; ++i) issue_ain(i);
     long long g = 0;                                      // running chunk index of this group
     typename Epi::Row row;
@@ -216,6 +217,30 @@ big_lin_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         const int slot = (int)(g % NSg);
         uint8_t* sl = slots + slot * 16384;
+        if (direct) {
+          // the staging tile (16 KB written + 16 KB read per chunk, twice with the saved activation) shares the shared-memory port with
+          // the tensor core's operand reads and the TMA operand writes; here every thread moves its own 128-byte row segment instead
+          if (Epi::kHasAin) {
+            if (grow < sh.n_rows) {
+              const float4* ap = reinterpret_cast<const float4*>(sh.ain_ptr + (size_t)grow * sh.ain_ld + col0);
+#pragma unroll
+              for (int ch = 0; ch < 8; ++ch) {
+                const float4 v = __ldg(ap + ch);
+                ain[4 * ch] = v.x; ain[4 * ch + 1] = v.y; ain[4 * ch + 2] = v.z; ain[4 * ch + 3] = v.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < kChunk; ++j) ain[j] = 0.f;
+            }
+          }
+          Epi::chunk(ea, th, row, acc, ain, out, col0, cv, scratch, r, grow);
+          if (Epi::kStoresOut && sh.store_out && grow < sh.n_rows) {
+            float4* op = reinterpret_cast<float4*>(sh.out_ptr + (size_t)grow * sh.out_ld + col0);
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) op[ch] = make_float4(out[4 * ch], out[4 * ch + 1], out[4 * ch + 2], out[4 * ch + 3]);
+          }
+          continue;
+        }
         if (Epi::kHasAin) {
           mbar_wait(ainf + slot, (uint32_t)((g / NSg) & 1));
 #pragma unroll
@@ -438,6 +463,13 @@ static bool pair_enabled() {
 template <class Epi>
 static int lin_launch_t(const LinOperands& o, const typename Epi::Args& ea, LinShape sh, const char* name, cudaStream_t st) {
   sh.n_rowblocks = (sh.n_rows + 127) / 128;
+  {
+    static int direct = -1;
+    if (direct < 0) { const char* e = getenv("MAPPO_B200_DIRECT_EPI"); direct = (e && e[0] == '1') ? 1 : 0; }
+    sh.direct = (direct && sh.BN >= 128 && ((reinterpret_cast<uintptr_t>(o.out) | reinterpret_cast<uintptr_t>(o.ain)) & 15) == 0 &&
+                 o.ldo % 4 == 0 && o.ldain % 4 == 0) ? 1 : 0;
+    sh.out_ptr = o.out; sh.out_ld = o.ldo; sh.ain_ptr = o.ain; sh.ain_ld = o.ldain;
+  }
   const int NT = sh.N / sh.BN;
   const bool pair = pair_enabled() && sh.BN == 256 && (NT == 1 || NT % 2 == 0) && sh.n_rowblocks >= 2 && o.sm_count >= 2;
   CUtensorMap mA, mB, mO, mI;

@@ -6,7 +6,12 @@
 namespace mappo {
 namespace big {
 
-struct LinShape { int n_rows, K, N, BN, store_out, n_rowblocks, n_stages; };
+struct LinShape {
+  int n_rows, K, N, BN, store_out, n_rowblocks, n_stages;
+  int direct;                           // epilogue tiles bypass shared memory: result registers -> global, saved activation global -> registers
+  float* out_ptr; long long out_ld;     // (direct) result matrix
+  const float* ain_ptr; long long ain_ld;   // (direct) saved activation read by EpiBwd
+};
 struct LinOperands {
   const float* A; long long lda;        // [rows][K]   activations / gradients, K-major
   const float* W; long long ldw;        // [N][K]      packed weights, K-major
