@@ -493,10 +493,12 @@ def kernel_roofline(res, a, peaks, tf32_peak):
             j.eng.graph, j.trainer.overlap_nets = saved_graph, saved_overlap
         msl = [s.elapsed_time(e) for s, e in pairs]
         avg_ms = sum(msl) / max(len(msl), 1)
-        tc = a.gemm == "tf32" and not cfg.recurrent
+        tc = a.gemm == "tf32"
         peak = tf32_peak if tc else float(peaks.get("bf16_tflops", 1590.0))
         ach = (fa + fc) / 2 / (avg_ms * 1e-3) / 1e12
-        kname = ("update_mlp_tc_kernel (fused fwd+loss+bwd, tcgen05 kind::tf32 + TMEM; launch incl. its weight-pack kernel)" if tc else
+        kname = ("tcgen05 GRU pipeline (update_gru_tc.cu: base fwd -> sequence fwd -> heads + loss -> BPTT -> gate gradients -> base bwd, "
+                 "kind::tf32 + TMEM; the timed call includes weight packing, slot sums and unfold)" if (tc and cfg.recurrent) else
+                 "update_mlp_tc_kernel (fused fwd+loss+bwd, tcgen05 kind::tf32 + TMEM; launch incl. its weight-pack kernel)" if tc else
                  ("gru_seq_fwd/bwd kernels (4-launch fused GRU fwd+loss+BPTT pipeline, fp32 FFMA)" if cfg.recurrent else
                   "update_mlp_kernel (fused fwd+loss+bwd, fp32 FFMA tiles)"))
         out = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "kernel": kname,
@@ -514,13 +516,13 @@ def result_line(name, res, a, world, roof, cpu, clocks, extra_cfg):
     cfg, w, jobs = res["cfg"], res["workload"], res["jobs"]
     eng = jobs[0].eng
     tr = jobs[0].trainer
-    tc = a.gemm == "tf32" and not cfg.recurrent
+    tc = a.gemm == "tf32"
     line = {"metric": metric_name(name), "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": w["scaling"],
             "vs_baseline": None,
             "dtype": "tf32 tensor-core GEMMs (fp32 accumulate / fp32 elsewhere)" if tc else "f32",
             "data": "synthetic",
-            "config": {**workload_dict(w, world), "cuda_graph": res["graph_ok"], "gemm": a.gemm if not cfg.recurrent else "fp32 (GRU kernels)",
+            "config": {**workload_dict(w, world), "cuda_graph": res["graph_ok"], "gemm": a.gemm,
                        "collective": ("none (1 GPU)" if world == 1 else
                                       "one-shot peer-memory all-reduce kernel over NVLink, in-graph"
                                       if getattr(tr, "_p2p", None) is not None else

@@ -96,6 +96,10 @@ int update_mlp_tc_tail_launch(const NetDev&, const float*, int, float*, float*, 
                               long long, uint32_t*);
 int update_gru_slots(const NetDev& n, int n_rows, int seq_len, int sm_count);
 int64_t update_gru_workspace_floats(const NetDev& n, int n_rows);
+bool update_gru_tc_supported(const NetDev& n);
+int64_t update_gru_tc_workspace_floats(const NetDev& n, int n_rows, int sm_count);
+int update_gru_tc_launch(const NetDev&, const float*, const BatchDev&, const LossDev&, const double*, const double*, const float*,
+                         float* grad_out, double* loss_out, float* workspace, int sm_count, cudaStream_t);
 int update_gru_launch(const NetDev&, const float*, const BatchDev&, const LossDev&, const double*, const double*,
                       const float*, float*, int, double*, float*, cudaStream_t);
 int gae_launch(const float*, const float*, const float*, const float*, const float*, const float*, int, int, float,
@@ -545,13 +549,15 @@ int32_t mappo_debug_tc_timing(int64_t* out16) { return debug_tc_timing(reinterpr
 int32_t mappo_tf32_supported(const mappo_net_desc_t* desc) {
   if (validate_desc(desc)) return 0;
   const NetDev n = make_net_dev(desc);
-  return (update_mlp_tc_supported(n) || big::supported(n)) ? 1 : 0;
+  return (update_mlp_tc_supported(n) || update_gru_tc_supported(n) || big::supported(n)) ? 1 : 0;
 }
 
 int64_t mappo_update_workspace_floats(const mappo_net_desc_t* desc, int32_t n_rows, int32_t gemm_mode) {
   if (validate_desc(desc)) return -1;
   const NetDev n = make_net_dev(desc);
-  if (desc->recurrent) return update_gru_workspace_floats(n, n_rows);
+  if (desc->recurrent)
+    return (gemm_mode == MAPPO_GEMM_TF32 && update_gru_tc_supported(n)) ? update_gru_tc_workspace_floats(n, n_rows, sm_count())
+                                                                         : update_gru_workspace_floats(n, n_rows);
   if (big::supported(n)) return big::workspace_floats(n, n_rows, sm_count());
   // tf32: [folded weight image][slot-summed raw accumulators]
   return (gemm_mode == MAPPO_GEMM_TF32 && update_mlp_tc_supported(n))
@@ -605,7 +611,10 @@ int32_t mappo_update_tail(const mappo_net_desc_t* desc, float* params, const flo
 int32_t mappo_update_grad_slots(const mappo_net_desc_t* desc, int32_t n_rows, int32_t gemm_mode) {
   if (validate_desc(desc)) return -1;
   const NetDev n = make_net_dev(desc);
-  if (desc->recurrent) return update_gru_slots(n, n_rows, 1, sm_count());
+  if (desc->recurrent) {
+    if (gemm_mode == MAPPO_GEMM_TF32 && update_gru_tc_supported(n)) return 1;      // the tcgen05 GRU pipeline leaves the flat gradient in slot 0
+    return update_gru_slots(n, n_rows, 1, sm_count());
+  }
   if (big::supported(n)) return 1;                     // the GEMM pipeline leaves the complete flat gradient in slot 0
   if (gemm_mode == MAPPO_GEMM_TF32 && update_mlp_tc_supported(n)) return update_mlp_tc_slots(n, n_rows, sm_count());
   return update_mlp_slots(n, n_rows, sm_count());
@@ -632,6 +641,11 @@ int32_t mappo_update_fwd_bwd(const mappo_net_desc_t* desc, const float* params, 
   const NetDev n = make_net_dev(desc);
   if (desc->recurrent) {
     if (!workspace) { set_error("update_fwd_bwd: recurrent net needs a workspace"); return MAPPO_ERR_INVALID; }
+    if (loss->gemm_mode == MAPPO_GEMM_TF32 && !b.eval_only) {
+      if (!update_gru_tc_supported(n)) { set_error("update_fwd_bwd: MAPPO_GEMM_TF32 is not built for this recurrent net (hidden 64, layer_N 1, in_dim <= 63)"); return MAPPO_ERR_UNSUPPORTED; }
+      return update_gru_tc_launch(n, params, b, L, norm_stats, adv_stats, vn_state, grad_part, loss_out, workspace, sm_count(),
+                                  (cudaStream_t)stream);
+    }
     return update_gru_launch(n, params, b, L, norm_stats, adv_stats, vn_state, grad_part, n_slots, loss_out, workspace,
                              (cudaStream_t)stream);
   }

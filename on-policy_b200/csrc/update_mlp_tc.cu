@@ -20,159 +20,13 @@
 // constant-1 feature, the weight image holds W' = W diag(gamma) and b' = b + W beta in the column of the 1-feature.
 // dW' accumulates in TMEM across the tiles of a CTA; at the end dW = dW' diag(gamma) + db' beta^T, db = dW'[:, one],
 // dgamma = colsum(dW' .* W), dbeta = W^T db'  (chain rule of the folding), written to the CTA's gradient slot.
-#include "net_tiles.cuh"
+#include "tc64.cuh"
 #include "p2p.cuh"
 
 namespace mappo {
 
-constexpr int kTM = 128;                 // rows per tile, threads per CTA
-constexpr int kHF = 72;                  // hidden features incl. the constant-1 feature, padded to a multiple of 8
-constexpr int kHC = kHF / 4;             // 18 chunks
-constexpr int kOne = 64;                 // index of the constant-1 feature in hidden tiles
 
-// ------------------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t a = smem_u32(bar);
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-  }
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {     // one full warp
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {       // same warp
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], tf32 inputs, fp32 accumulate; issued by ONE thread
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-               ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-// 16 consecutive accumulator columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t* u = reinterpret_cast<uint32_t*>(v);
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
-                 "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
-               : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
-  uint32_t* u = reinterpret_cast<uint32_t*>(v);
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
-               : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
-  const uint32_t* u = reinterpret_cast<const uint32_t*>(v);
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-               ::"r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]) : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// tanh on the SFU (MUFU.TANH): max relative error 2^-11, the same class as the tf32 rounding of the GEMM inputs.
-__device__ __forceinline__ float act_fwd_tc(float z, int act) {
-  if (act == ACT_RELU) return fmaxf(z, 0.f);
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(z));
-  return y;
-}
-
-__device__ __forceinline__ float to_tf32(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
-}
-
-// shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (cute::UMMA::SmemDescriptor bit layout)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
-}
-// n MMAs over consecutive K-slices of two operands: the slice-to-slice advance only changes the 14-bit start-address
-// field (bits [0,14), in 16-byte units), so the descriptors are built once and bumped by a constant (shared memory ends
-// below 2^18 bytes: the field cannot overflow into the next one)
-__device__ __forceinline__ void umma_seq(uint32_t d_tmem, uint32_t a_addr, uint32_t a_step, uint32_t a_lbo, uint32_t b_addr,
-                                         uint32_t b_step, uint32_t b_lbo, uint32_t idesc, int n, bool accumulate_first) {
-  uint64_t ad = make_desc(a_addr, a_lbo, 128), bd = make_desc(b_addr, b_lbo, 128);
-  const uint64_t da = a_step >> 4, db = b_step >> 4;
-  for (int s = 0; s < n; ++s) {
-    umma_tf32(d_tmem, ad, bd, idesc, (accumulate_first || s > 0) ? 1u : 0u);
-    ad += da; bd += db;
-  }
-}
-
-// instruction descriptor: D fp32, A/B tf32 (cute::UMMA::InstrDescriptor bit layout)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// folded weight image (global), built once per optimiser step by pack_tc_kernel
-// ------------------------------------------------------------------------------------------------------------
-struct TcImage {
-  int inF;      // input features incl. constant-1, padded to a multiple of 8
-  int NH;       // head outputs padded to a multiple of 16
-  // float offsets.  forward (K = in-features):  w1 [inF/4][64][4], w2 [18][64][4], wh [18][NH][4]
-  //                 dX      (K = out-features): w2t [16][64][4] (rows = in-feature k), wht [NH/4][64][4]
-  int w1, w2, wh, w2t, wht, total;
-};
-__host__ __device__ inline TcImage make_tc_image(const NetDev& n) {
-  TcImage m;
-  m.inF = (n.in_dim + 1 + 7) & ~7;
-  m.NH = (n.head_total + 15) & ~15;
-  m.w1 = 0;
-  m.w2 = m.w1 + m.inF * 64;
-  m.wh = m.w2 + kHF * 64;
-  m.w2t = m.wh + kHF * m.NH;
-  m.wht = m.w2t + 64 * 64;
-  m.total = m.wht + m.NH * 64;
-  return m;
-}
-
-// Raw per-CTA gradient slot of the tcgen05 kernel: the folded accumulators exactly as they sit in TMEM.
-//   g2 [64][72] = dW2'  (column 64 = db2'),  g1 [64][inF] = dW1' (column in = db1'),  gh [64][NH] = dWh'^T (row = feature),
-//   dbh [NH].  mappo_update_finish sums the slots and unfolds ONCE (tc_unfold_kernel) instead of once per CTA.
-struct TcRaw { int g2, g1, gh, dbh, total; };
-__host__ __device__ inline TcRaw make_tc_raw(const TcImage& m) {
-  TcRaw r;
-  r.g2 = 0;
-  r.g1 = r.g2 + 64 * kHF;
-  r.gh = r.g1 + 64 * m.inF;
-  r.dbh = r.gh + 64 * m.NH;
-  r.total = (r.dbh + m.NH + 3) & ~3;
-  return r;
-}
 
 // dW = dW' diag(gamma_in) + db' beta_in^T, db = dW'[:, one], dgamma_in = colsum(dW' .* W), dbeta_in = W^T db'   (chain rule of the
 // folding) from the slot-summed raw accumulators.  Grid: blockIdx.y = layer (0 fc2, 1 fc1, 2 heads), blockIdx.x = block
@@ -192,8 +46,9 @@ __device__ __forceinline__ void tc_unfold_unit(const NetDev& n, const float* p, 
   auto put = [&](int off, float v) { g[off] = v; if (g_mirror) g_mirror[off] = v; sq = fmaf(v, v, sq); };
   const int K = sec == 0 ? 64 : (sec == 1 ? in : 64);
   const bool fold = sec == 1 ? (n.use_fn != 0) : true;
-  const int gam_off = sec == 0 ? n.g.ln1_w : (sec == 1 ? n.g.fn_w : n.g.ln2_w[0]);
-  const int bet_off = sec == 0 ? n.g.ln1_b : (sec == 1 ? n.g.fn_b : n.g.ln2_b[0]);
+  // the LayerNorm in front of the heads: base.mlp.fc2[0]'s for feed-forward nets, rnn.norm for recurrent ones
+  const int gam_off = sec == 0 ? n.g.ln1_w : (sec == 1 ? n.g.fn_w : (n.recurrent ? n.g.rnn_ln_w : n.g.ln2_w[0]));
+  const int bet_off = sec == 0 ? n.g.ln1_b : (sec == 1 ? n.g.fn_b : (n.recurrent ? n.g.rnn_ln_b : n.g.ln2_b[0]));
   float sg = 0.f, sb = 0.f;
   if (active && sec < 2) {
     const int ld = sec == 0 ? kHF : m.inF, one = sec == 0 ? kOne : in;
@@ -278,10 +133,11 @@ __device__ __forceinline__ float pack_tc_element(const NetDev& n, const TcImage&
       const int t = i - m.wh, kc = t / (4 * m.NH), a = (t >> 2) % m.NH, k = kc * 4 + (t & 3);
       if (a < n.head_total) {
         const float* W = p + n.g.head_w + a * H;
-        if (k < H) v = W[k] * p[n.g.ln2_w[0] + k];
+        const int gw = n.recurrent ? n.g.rnn_ln_w : n.g.ln2_w[0], gb = n.recurrent ? n.g.rnn_ln_b : n.g.ln2_b[0];
+        if (k < H) v = W[k] * p[gw + k];
         else if (k == kOne) {
           v = p[n.g.head_b + a];
-          for (int j0 = 0; j0 < H; ++j0) { const int j = (j0 + a) & 63; v = fmaf(W[j], p[n.g.ln2_b[0] + j], v); }
+          for (int j0 = 0; j0 < H; ++j0) { const int j = (j0 + a) & 63; v = fmaf(W[j], p[gb + j], v); }
         }
       }
     } else if (i < m.wht) {                               // fc2 transposed: element (row k, K-index o) = W2'[o][k]
@@ -289,7 +145,7 @@ __device__ __forceinline__ float pack_tc_element(const NetDev& n, const TcImage&
       v = p[n.g.fc2_w[0] + o * H + k] * p[n.g.ln1_w + k];
     } else {                                              // heads transposed: (row k, K-index a) = Wh'[a][k]
       const int t = i - m.wht, ac = t / 256, k = (t >> 2) & 63, a = ac * 4 + (t & 3);
-      if (a < n.head_total) v = p[n.g.head_w + a * H + k] * p[n.g.ln2_w[0] + k];
+      if (a < n.head_total) v = p[n.g.head_w + a * H + k] * p[(n.recurrent ? n.g.rnn_ln_w : n.g.ln2_w[0]) + k];
     }
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
@@ -305,8 +161,6 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const NetDev n, const floa
 // ------------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kS65 = 65, kS73 = 73;       // padded row strides of the transposed tiles (odd -> conflict-free scatter)
-constexpr int kTCThreads = 2 * kTM;       // two threads per row: warpgroup g owns hidden columns [32 g, 32 g + 32)
 struct TcSmem { int img, p, x1t, x2t, ta, lg, dbh, xch, misc, total; };   // float offsets
 __host__ __device__ inline TcSmem make_tc_smem(const TcImage& m) {
   TcSmem s;
@@ -331,49 +185,6 @@ __host__ __device__ inline TcSmem make_tc_smem(const TcImage& m) {
 __device__ long long g_tc_timing[16];
 #define TC_STAMP(i) do { if (blockIdx.x == 0 && tid == 0) g_tc_timing[i] = clock64(); } while (0)
 
-// The two threads of a row live in warps w and w + 4 (same TMEM lane window).  They meet on named barrier 1 + (w & 3)
-// (64 threads) and swap two partial sums through shared memory; both get bit-identical totals (a + b == b + a).
-// Two slots alternate so that a fast pair cannot overwrite values its partner has not read yet.
-struct PairXch {
-  float2* buf;       // [slot][warpgroup][128]
-  int wg, r, bar;
-  int slot;
-  __device__ __forceinline__ float2 sum(float a, float b) {
-    buf[(slot * 2 + wg) * kTM + r] = make_float2(a, b);
-    asm volatile("bar.sync %0, 64;" ::"r"(bar) : "memory");
-    const float2 o = buf[(slot * 2 + (wg ^ 1)) * kTM + r];
-    slot ^= 1;
-    return make_float2(a + o.x, b + o.y);
-  }
-};
-
-// LayerNorm statistics of a 64-wide row held as 2 x 32 register values (two-pass like torch)
-__device__ __forceinline__ void ln_stats_pair(const float* a, PairXch& px, float& mean, float& rstd) {
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) s += a[i];
-  mean = px.sum(s, 0.f).x * (1.f / 64.f);
-  float v = 0.f;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) { const float d = a[i] - mean; v = fmaf(d, d, v); }
-  rstd = 1.0f / sqrtf(px.sum(v, 0.f).x * (1.f / 64.f) + kLnEps);
-}
-
-// thread (row r, warpgroup g): write its 32 values as chunks [8 g, 8 g + 8) of row r of a K-major staging tile
-// [16 (+2 aug)][128][4] ...
-__device__ __forceinline__ void put_kmajor32(float* P, int r, int wg, const float* v, bool aug) {
-#pragma unroll
-  for (int kc = 0; kc < 8; ++kc)
-    reinterpret_cast<float4*>(P)[(wg * 8 + kc) * kTM + r] = make_float4(v[4 * kc], v[4 * kc + 1], v[4 * kc + 2], v[4 * kc + 3]);
-  if (aug) reinterpret_cast<float4*>(P)[(16 + wg) * kTM + r] = make_float4(wg == 0 ? 1.f : 0.f, 0.f, 0.f, 0.f);
-}
-// ... and as features [32 g, 32 g + 32) of column r of a transposed tile [32][S][4] (element (feature f, row r) at
-// ((r/4)*S + f)*4 + r%4)
-__device__ __forceinline__ void put_transposed32(float* T, int S, int r, int wg, const float* v) {
-  float* base = T + ((r >> 2) * S + wg * 32) * 4 + (r & 3);
-#pragma unroll
-  for (int f = 0; f < 32; ++f) base[f * 4] = v[f];
-}
 
 // LayerNorm + activation backward for one row: d = dL/dxhat (this thread's 32 columns) -> dZ in place.  xhat is re-read
 // from the transposed tile (conflict-free 4-byte loads).
@@ -394,11 +205,19 @@ __device__ __forceinline__ void ln_act_bwd32(float* d, const float* XT, int S, i
   }
 }
 
+// MODE (recurrent nets run the base MLP and the heads on either side of the GRU sequence kernels of update_gru_tc.cu; planes are
+// [position][64] fp32 workspaces indexed by the minibatch position p):
+//   TC_FULL      the whole MLP net (feed-forward policies)
+//   TC_BASE_FWD  S1..S5 only: xhat2 (pre-affine output of the last LayerNorm, tf32) -> plane_out                       no gradients
+//   TC_BASE_BWD  S1..S5 recomputed, dL/dxhat2 read from plane_in instead of the head path, S9..S11 -> G2 / G1
+//   TC_HEAD      row = plane_in[p] (GRU state h): LayerNorm -> heads -> loss -> dL/dh -> plane_out; Gh / dbh
+enum { TC_FULL = 0, TC_BASE_FWD = 1, TC_BASE_BWD = 2, TC_HEAD = 3 };
+template <int MODE>
 __global__ void __launch_bounds__(kTCThreads, 1)
 update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const float* __restrict__ image, const BatchDev b,
                      const LossDev L, const double* __restrict__ norm_stats, const double* __restrict__ adv_stats,
                      const float* __restrict__ vn_state, float* __restrict__ grad_part, double* __restrict__ loss_out,
-                     int n_tiles, uint32_t tmem_cols) {
+                     int n_tiles, uint32_t tmem_cols, const float* __restrict__ plane_in, float* __restrict__ plane_out) {
   extern __shared__ __align__(1024) float smem[];
   __shared__ double sred[2 * 32];
   pdl_prologue();                                            // (PDL: scheduled under the weight-pack kernel, released when it has finished)
@@ -473,9 +292,11 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
     const int gr = gr_next;
     gr_next = row_of(tile + gridDim.x);
     float mu0 = 0.f, rs0 = 1.f;
-    const RowIn rin = load_row_in(n, b, wg == 0 ? gr : -1);      // loss inputs (warpgroup 0 owns the loss): in flight
+    const RowIn rin = load_row_in(n, b, (wg == 0 && (MODE == TC_FULL || MODE == TC_HEAD)) ? gr : -1);      // loss inputs (warpgroup 0 owns the loss): in flight
                                                                  // during the whole forward pass
 
+    float mu1 = 0.f, rs1 = 1.f, mu2 = 0.f, rs2 = 1.f;
+    if (MODE != TC_HEAD) {
     // ---- S1: coalesced cooperative gather (a warp reads whole rows) -> shared staging -> my row in registers,
     //      feature LayerNorm, stage xhat0 (K-major in TA, + constant-1 feature), park it in TMEM ----
     {
@@ -553,7 +374,6 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
       umma_commit(bar_m);
     }
     // ---- S3: fc1 epilogue: activation, LayerNorm -> xhat1 (K-major staging + transposed copy) ----
-    float mu1, rs1, mu2, rs2;
     {
       float a[32];
       mbar_wait(bar_m, phase); phase ^= 1; TC_STAMP(3);
@@ -592,15 +412,44 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
       ln_stats_pair(a, px, mu2, rs2);
 #pragma unroll
       for (int i = 0; i < 32; ++i) a[i] = to_tf32((a[i] - mu2) * rs2);
+      if (MODE == TC_BASE_FWD) {                                  // the GRU's input rows; nothing else to do for this tile
+        if (p < b.n_rows) {
+          float4* dst = reinterpret_cast<float4*>(plane_out + (size_t)p * 64 + wg * 32);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) dst[q] = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+        }
+        tc_fence_before();
+        __syncthreads();
+        continue;
+      }
+      if (MODE == TC_FULL) put_kmajor32(P, r, wg, a, true);
+      put_transposed32(X2T, kS65, r, wg, a);
+    }
+    } else {
+      // ---- TC_HEAD: the GRU state of this position -> LayerNorm (rnn.norm, rnn.py:79) -> xhat (K-major staging + transposed) ----
+      float a[32];
+      if (gr >= 0) {
+        const float4* src = reinterpret_cast<const float4*>(plane_in + (size_t)p * 64 + wg * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { const float4 v = __ldg(src + q); a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w; }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) a[i] = 0.f;
+      }
+      ln_stats_pair(a, px, mu2, rs2);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) a[i] = to_tf32((a[i] - mu2) * rs2);
       put_kmajor32(P, r, wg, a, true);
       put_transposed32(X2T, kS65, r, wg, a);
     }
+    if (MODE != TC_BASE_BWD) {
     TC_STAMP(6);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
+      if (MODE == TC_HEAD && first_tile) mbar_wait(bar_w, 0);   // weight image has landed
       const uint32_t id = make_idesc(128, NH, 0, 0);
       umma_seq(tmem + cDh, aP, 2 * ROWB, ROWB, aWh, 2 * NH * 16, NH * 16, id, kHF / 8, false);
       umma_commit(bar_m);
@@ -652,18 +501,63 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
       umma_seq(tmem + cGh, aX2T, 2 * kS65 * 16, kS65 * 16, aTA, 2 * SH * 16, SH * 16, idg, kTM / 8, !first_tile);
       umma_commit(bar_g);
     }
-    // ---- S9: LayerNorm-2 + activation backward -> dZ2 (K-major staging + transposed) ----
-    {
+    }   // MODE != TC_BASE_BWD
+    if (MODE == TC_HEAD) {
+      // ---- S9 (heads only): LayerNorm backward without an activation -> dL/dh of the head path, fp32, to the workspace ----
       float d[32];
-      mbar_wait(bar_m, phase); phase ^= 1; TC_STAMP(9);
+      mbar_wait(bar_m, phase); phase ^= 1;
       tc_fence_after();
       tmem_ld16(tmem + lane_base + cMy, d);
       tmem_ld16(tmem + lane_base + cMy + 16, d + 16);
       tmem_ld_wait();
+      {
+        const float* base = X2T + ((r >> 2) * kS65 + wg * 32) * 4 + (r & 3);
+        float xh[32];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int f = 0; f < 32; ++f) { xh[f] = base[f * 4]; s1 += d[f]; s2 = fmaf(d[f], xh[f], s2); }
+        const float2 t = px.sum(s1, s2);
+        s1 = t.x * (1.f / 64.f); s2 = t.y * (1.f / 64.f);
+#pragma unroll
+        for (int f = 0; f < 32; ++f) d[f] = rs2 * (d[f] - s1 - xh[f] * s2);
+      }
+      if (p < b.n_rows) {
+        float4* dst = reinterpret_cast<float4*>(plane_out + (size_t)p * 64 + wg * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) dst[q] = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
+      }
+      mbar_wait(bar_g, phase_g); phase_g ^= 1;             // Gh has consumed dL^T (TA) and xhat^T (X2T)
+      tc_fence_after();
+      first_tile = false;
+      tc_fence_before();
+      __syncthreads();
+      continue;
+    }
+    // ---- S9: LayerNorm-2 + activation backward -> dZ2 (K-major staging + transposed) ----
+    {
+      float d[32];
+      if (MODE == TC_BASE_BWD) {                           // dL/dxhat2 from the GRU input projection (update_gru_tc.cu)
+        if (p < b.n_rows && gr >= 0) {
+          const float4* src = reinterpret_cast<const float4*>(plane_in + (size_t)p * 64 + wg * 32);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { const float4 v = __ldg(src + q); d[4 * q] = v.x; d[4 * q + 1] = v.y; d[4 * q + 2] = v.z; d[4 * q + 3] = v.w; }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) d[i] = 0.f;
+        }
+      } else {
+        mbar_wait(bar_m, phase); phase ^= 1; TC_STAMP(9);
+        tc_fence_after();
+        tmem_ld16(tmem + lane_base + cMy, d);
+        tmem_ld16(tmem + lane_base + cMy + 16, d + 16);
+        tmem_ld_wait();
+      }
       ln_act_bwd32(d, X2T, kS65, r, wg, px, mu2, rs2, act);
       put_kmajor32(P, r, wg, d, false);
-      mbar_wait(bar_g, phase_g); phase_g ^= 1;             // Gh has consumed dL^T (TA)
-      tc_fence_after();
+      if (MODE != TC_BASE_BWD) {
+        mbar_wait(bar_g, phase_g); phase_g ^= 1;           // Gh has consumed dL^T (TA)
+        tc_fence_after();
+      }
       put_transposed32(TA, kS65, r, wg, d);
     }
     TC_STAMP(10);
@@ -723,10 +617,11 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
   }
   // ---- dump the raw (still folded) accumulators into this CTA's slot; they are summed over slots and unfolded once
   //      by mappo_update_finish (tc_unfold_kernel).  Warpgroup 0 dumps G2, warpgroup 1 dumps G1 and Gh. ----
-  if (!b.eval_only) {
+  if (!b.eval_only && MODE != TC_BASE_FWD) {
     const TcRaw R = make_tc_raw(im);
     float* g = grad_part + (size_t)blockIdx.x * R.total;
-    const bool has_tile = !first_tile;
+    const bool has_tile = !first_tile && MODE != TC_HEAD;          // G2 / G1: not accumulated by the heads-only mode
+    const bool has_head = !first_tile && MODE != TC_BASE_BWD;      // Gh: not accumulated by the base-backward mode
     const int o = (warp & 3) * 16 + lane;                 // accumulator row of this thread in the M = 64 layout
     const bool own = lane < 16;
     float v[72];
@@ -761,7 +656,7 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
         for (int q = 0; q < 8; ++q)
           if (q * 4 < NH)
             reinterpret_cast<float4*>(g + R.gh + o * NH)[q] =
-                has_tile ? make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                has_head ? make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
     if (tid < NH) g[R.dbh + tid] = dbh[tid];
@@ -773,7 +668,9 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
   // ---- loss scalars + teardown ----
   tc_fence_before();
   __syncthreads();
-  if (n.is_critic) {
+  if (MODE == TC_BASE_FWD || MODE == TC_BASE_BWD) {
+    // no loss terms in these modes
+  } else if (n.is_critic) {
     double one[1] = {acc[0]};
     block_accumulate<1>(one, loss_out + 0, sred, tid, kTCThreads);
   } else {
@@ -1167,15 +1064,57 @@ int update_mlp_tc_launch(const NetDev& n, const float* params, const BatchDev& b
   static thread_local SmemConfig configured_dev = {};
   size_t& configured = configured_dev.slot();
   if (bytes > configured) {
-    if (cudaFuncSetAttribute(update_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+    if (cudaFuncSetAttribute(update_mlp_tc_kernel<TC_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
       return check_launch("update_mlp_tc: cudaFuncSetAttribute");
     configured = bytes;
   }
   const int n_tiles = (b.n_rows + kTM - 1) / kTM;
   const uint32_t cols = 512u;          // accumulators [0,272) + parked xhat0 [272,344): one CTA per SM owns all of TMEM
-  launch_pdl(update_mlp_tc_kernel, dim3(n_slots), dim3(kTCThreads), bytes, st, n, params, image, b, L, norm_stats, adv_stats, vn_state, grad_part,
-             loss_out, n_tiles, cols);
+  launch_pdl(update_mlp_tc_kernel<TC_FULL>, dim3(n_slots), dim3(kTCThreads), bytes, st, n, params, image, b, L, norm_stats, adv_stats, vn_state,
+             grad_part, loss_out, n_tiles, cols, (const float*)nullptr, (float*)nullptr);
   return check_launch("update_mlp_tc_kernel");
+}
+
+
+// ---- recurrent nets (update_gru_tc.cu): the same kernel around the GRU sequence kernels ----
+int update_mlp_tc_pack_launch(const NetDev& n, const float* params, float* image, cudaStream_t st) {
+  const TcImage im = make_tc_image(n);
+  launch_pdl(pack_tc_kernel, dim3((im.total + 255) / 256), dim3(256), 0, st, n, params, image);
+  return check_launch("pack_tc_kernel");
+}
+
+template <int MODE>
+static int mode_launch(const NetDev& n, const float* params, const float* image, const BatchDev& b, const LossDev& L,
+                       const double* norm_stats, const double* adv_stats, const float* vn_state, float* grad_part, int n_ctas,
+                       double* loss_out, const float* plane_in, float* plane_out, cudaStream_t st) {
+  const TcImage im = make_tc_image(n);
+  const TcSmem sm = make_tc_smem(im);
+  const size_t bytes = (size_t)sm.total * sizeof(float) + 1024;
+  if (bytes > 227 * 1024) { set_error("update_mlp_tc: %zu B shared memory > 227 KB", bytes); return MAPPO_ERR_UNSUPPORTED; }
+  static thread_local SmemConfig configured_dev = {};
+  size_t& configured = configured_dev.slot();
+  if (bytes > configured) {
+    if (cudaFuncSetAttribute(update_mlp_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+      return check_launch("update_mlp_tc: cudaFuncSetAttribute");
+    configured = bytes;
+  }
+  const int n_tiles = (b.n_rows + kTM - 1) / kTM;
+  launch_pdl(update_mlp_tc_kernel<MODE>, dim3(n_ctas), dim3(kTCThreads), bytes, st, n, params, image, b, L, norm_stats, adv_stats, vn_state,
+             grad_part, loss_out, n_tiles, 512u, plane_in, plane_out);
+  return check_launch("update_mlp_tc_kernel<mode>");
+}
+
+int update_mlp_tc_mode_launch(int mode, const NetDev& n, const float* params, const float* image, const BatchDev& b, const LossDev& L,
+                              const double* norm_stats, const double* adv_stats, const float* vn_state, float* grad_part, int n_ctas,
+                              double* loss_out, const float* plane_in, float* plane_out, cudaStream_t st) {
+  if (n.hid != 64 || n.layer_n != 1 || n.in_dim > 63 || n.head_total > 32) { set_error("update_mlp_tc: configuration not built"); return MAPPO_ERR_UNSUPPORTED; }
+  switch (mode) {
+    case TC_BASE_FWD: return mode_launch<TC_BASE_FWD>(n, params, image, b, L, norm_stats, adv_stats, vn_state, grad_part, n_ctas, loss_out, plane_in, plane_out, st);
+    case TC_BASE_BWD: return mode_launch<TC_BASE_BWD>(n, params, image, b, L, norm_stats, adv_stats, vn_state, grad_part, n_ctas, loss_out, plane_in, plane_out, st);
+    case TC_HEAD:     return mode_launch<TC_HEAD>(n, params, image, b, L, norm_stats, adv_stats, vn_state, grad_part, n_ctas, loss_out, plane_in, plane_out, st);
+  }
+  set_error("update_mlp_tc: bad mode %d", mode);
+  return MAPPO_ERR_INVALID;
 }
 
 }  // namespace mappo

@@ -377,7 +377,7 @@ class UpdateWorkspace:
         # hidden-64 tcgen05 path: the optimiser tail (slot sum, unfold, clip + Adam, next weight image) as one cluster launch
         # (mappo_update_tail).  image_ready: the workspace holds the image of the CURRENT weights -- callers clear it whenever
         # the parameters may have changed behind the tail's back (R_MAPPO.train() does at its start).
-        self.fused_tail = (self.gemm_mode == _lib.GEMM_TF32 and not lib.mappo_big_net(C.byref(net.desc))
+        self.fused_tail = (self.gemm_mode == _lib.GEMM_TF32 and not lib.mappo_big_net(C.byref(net.desc)) and not net.desc.recurrent
                            and os.environ.get("MAPPO_B200_FUSED_TAIL", "0") == "1")
         self.image_ready = 0
 

@@ -47,7 +47,7 @@ def test_tf32_path_is_active():
     assert ws_a.workspace.numel() > 1000          # folded tf32 weight image for the TMA bulk copy
 
 
-TF32_CASES = ["c1_mlp_discrete", "c2_mlp_n128", "c5_h512_hanabi"]
+TF32_CASES = ["c1_mlp_discrete", "c2_mlp_n128", "c5_h512_hanabi", "c3_gru_multidiscrete", "c4_gru_smac", "naive_rnn_ptl"]
 
 
 def _collect_fp32(monkeypatch, cfg, policy, trainer, buf, feed, noise):
@@ -147,6 +147,51 @@ def test_tf32_ctas_with_several_tiles_match_the_fp32_build(monkeypatch):
         _grad_check(res["tf32"][1][key], want, f"{key}")
     for k in ("value_loss", "dist_entropy", "ratio", "actor_grad_norm", "critic_grad_norm"):
         assert_close(res["tf32"][0][k], res["fp32"][0][k], 1e-2, 1e-6, k)
+
+
+def test_tf32_path_is_active_for_gru_nets():
+    g = Golden("c3_gru_multidiscrete")
+    args, policy, trainer, buf = TP.build(g.cfg, g)
+    from mappo_b200 import _lib
+    ws_a, ws_c = trainer._workspaces(200)
+    assert ws_a.gemm_mode == _lib.GEMM_TF32 and ws_c.gemm_mode == _lib.GEMM_TF32
+    assert ws_a.n_slots == 1 and ws_c.n_slots == 1          # the tcgen05 GRU pipeline leaves the flat gradient in slot 0
+
+
+@pytest.mark.parametrize("ctas", ["0", "5"])
+def test_tf32_gru_many_tiles_match_the_fp32_build(ctas, monkeypatch):
+    """GRU policy, 256 threads x 3 agents x 30 steps in chunks of 10: 2304 chunks = 18 sequence tiles, 23040 positions = 180
+    position tiles (> 148 SMs, so CTAs walk several tiles and keep their weight-gradient accumulators in TMEM across them; with
+    MAPPO_B200_GRU_CTAS=5 the sequence kernels walk several tiles per CTA as well).  First-update gradients and losses of the
+    tcgen05 build (update_gru_tc.cu) against the exact-fp32 build (update_gru.cu) on identical rollouts."""
+    from oracle import mappo_oracle as O
+    if ctas != "0":
+        monkeypatch.setenv("MAPPO_B200_GRU_CTAS", ctas)
+    cfg = O.PathConfig(episode_length=30, n_rollout_threads=256, num_agents=3, obs_dim=30, share_obs_dim=48,
+                       act_dims=(9,), use_ReLU=False, use_recurrent_policy=True, data_chunk_length=10, ppo_epoch=1,
+                       num_mini_batch=1, lr=5e-4, critic_lr=5e-4)
+    feed = O.make_feed(cfg, seed=3, kind="smac")
+    noise = np.random.RandomState(5).exponential(size=(cfg.episode_length, cfg.n_rollout_threads * cfg.num_agents, 9)) \
+        .astype(np.float32)
+    n_chunks = (cfg.episode_length // cfg.data_chunk_length) * cfg.n_rollout_threads * cfg.num_agents
+    perm = np.random.RandomState(6).permutation(n_chunks)
+    res = {}
+    for mode in ("fp32", "tf32"):
+        monkeypatch.setenv("MAPPO_B200_GEMM", mode)
+        torch.manual_seed(1)
+        args, policy, trainer, buf = TP.build(cfg)
+        TP.warm(buf, feed)
+        TP.collect_and_returns(cfg, policy, trainer, buf, feed, noise)
+        monkeypatch.setattr(torch, "randperm", TP.FakeRandperm([perm]))
+        info = trainer.train(buf)
+        res[mode] = (info, {("a", k): v.cpu().numpy().copy() for k, v in policy.actor.named_grads().items()} |
+                     {("c", k): v.cpu().numpy().copy() for k, v in policy.critic.named_grads().items()})
+    worst = 0.0
+    for key, want in res["fp32"][1].items():
+        worst = max(worst, _grad_check(res["tf32"][1][key], want, f"{key}"))
+    for k in ("value_loss", "dist_entropy", "ratio", "actor_grad_norm", "critic_grad_norm"):
+        assert_close(res["tf32"][0][k], res["fp32"][0][k], 1e-2, 1e-6, k)
+    print(f"\n[tf32 gru] worst gradient error relative to tensor scale: {worst:.3e}")
 
 
 @pytest.mark.parametrize("name", ["c1_mlp_discrete", "c2_mlp_n128"])
