@@ -187,9 +187,11 @@ __device__ long long g_tc_timing[16];
 
 
 // LayerNorm + activation backward for one row: d = dL/dxhat (this thread's 32 columns) -> dZ in place.  xhat is re-read
-// from the transposed tile (conflict-free 4-byte loads).
+// from the transposed tile (conflict-free 4-byte loads).  `pos`: bit f = the activation output of column f was > 0 in the forward
+// pass -- the ReLU derivative must not be taken from the value reconstructed out of the tf32-rounded xhat (an inactive unit's
+// exact 0 comes back as +-1e-4 |mu|, i.e. a coin flip).
 __device__ __forceinline__ void ln_act_bwd32(float* d, const float* XT, int S, int r, int wg, PairXch& px, float mu, float rs,
-                                             int act) {
+                                             int act, uint32_t pos) {
   const float* base = XT + ((r >> 2) * S + wg * 32) * 4 + (r & 3);
   float xh[32];
   float s1 = 0.f, s2 = 0.f;
@@ -201,7 +203,8 @@ __device__ __forceinline__ void ln_act_bwd32(float* d, const float* XT, int S, i
 #pragma unroll
   for (int f = 0; f < 32; ++f) {
     const float dA = rs * (d[f] - s1 - xh[f] * s2);
-    d[f] = to_tf32(dA * act_bwd(fmaf(xh[f], inv, mu), act));
+    const float da = act == ACT_RELU ? (((pos >> f) & 1u) ? 1.f : 0.f) : act_bwd(fmaf(xh[f], inv, mu), act);
+    d[f] = to_tf32(dA * da);
   }
 }
 
@@ -296,6 +299,7 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
                                                                  // during the whole forward pass
 
     float mu1 = 0.f, rs1 = 1.f, mu2 = 0.f, rs2 = 1.f;
+    uint32_t pos1 = 0u, pos2 = 0u;                              // activation output > 0, per column of this thread (ReLU backward)
     if (MODE != TC_HEAD) {
     // ---- S1: coalesced cooperative gather (a warp reads whole rows) -> shared staging -> my row in registers,
     //      feature LayerNorm, stage xhat0 (K-major in TA, + constant-1 feature), park it in TMEM ----
@@ -382,7 +386,7 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
       tmem_ld16(tmem + lane_base + cMy + 16, a + 16);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) a[i] = act_fwd_tc(a[i], act);
+      for (int i = 0; i < 32; ++i) { a[i] = act_fwd_tc(a[i], act); pos1 |= (a[i] > 0.f ? 1u : 0u) << i; }
       ln_stats_pair(a, px, mu1, rs1);
 #pragma unroll
       for (int i = 0; i < 32; ++i) a[i] = to_tf32((a[i] - mu1) * rs1);
@@ -408,7 +412,7 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
       tmem_ld16(tmem + lane_base + cMy + 16, a + 16);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) a[i] = act_fwd_tc(a[i], act);
+      for (int i = 0; i < 32; ++i) { a[i] = act_fwd_tc(a[i], act); pos2 |= (a[i] > 0.f ? 1u : 0u) << i; }
       ln_stats_pair(a, px, mu2, rs2);
 #pragma unroll
       for (int i = 0; i < 32; ++i) a[i] = to_tf32((a[i] - mu2) * rs2);
@@ -552,7 +556,7 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
         tmem_ld16(tmem + lane_base + cMy + 16, d + 16);
         tmem_ld_wait();
       }
-      ln_act_bwd32(d, X2T, kS65, r, wg, px, mu2, rs2, act);
+      ln_act_bwd32(d, X2T, kS65, r, wg, px, mu2, rs2, act, pos2);
       put_kmajor32(P, r, wg, d, false);
       if (MODE != TC_BASE_BWD) {
         mbar_wait(bar_g, phase_g); phase_g ^= 1;           // Gh has consumed dL^T (TA)
@@ -583,7 +587,7 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
       tmem_ld16(tmem + lane_base + cMy, d);
       tmem_ld16(tmem + lane_base + cMy + 16, d + 16);
       tmem_ld_wait();
-      ln_act_bwd32(d, X1T, kS73, r, wg, px, mu1, rs1, act);
+      ln_act_bwd32(d, X1T, kS73, r, wg, px, mu1, rs1, act, pos1);
       mbar_wait(bar_g, phase_g); phase_g ^= 1;             // G2 has consumed dZ2^T (TA)
       tc_fence_after();
       put_transposed32(TA, kS65, r, wg, d);
