@@ -210,4 +210,21 @@ __device__ __forceinline__ void put_transposed32(float* T, int S, int r, int wg,
   for (int f = 0; f < 32; ++f) base[f * 4] = v[f];
 }
 
+// ---- [position][64] fp32 workspace planes of the recurrent pipeline, tiled like the K-major operands (update_gru_tc.cu) ----
+__host__ __device__ inline int64_t plane_floats(int64_t n_rows) { return ((n_rows + kTM - 1) / kTM) * (int64_t)(16 * kTM * 4); }
+// float offset of the 4-column chunk `chunk` (0..15) of position p
+__device__ __forceinline__ size_t pl_off(size_t p, int chunk) { return ((p >> 7) * 16 + (size_t)chunk) * (kTM * 4) + (p & (kTM - 1)) * 4; }
+__device__ __forceinline__ void ld_pl16(const float* __restrict__ plane, size_t p, int chunk0, float* v) {      // 4 chunks = 16 columns
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(plane + pl_off(p, chunk0 + j)));
+    v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void st_pl16(float* __restrict__ plane, size_t p, int chunk0, const float* v) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<float4*>(plane + pl_off(p, chunk0 + j)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+
 }  // namespace mappo

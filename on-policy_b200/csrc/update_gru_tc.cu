@@ -52,6 +52,9 @@ __host__ __device__ inline GruImage make_gru_image() {
   return m;
 }
 
+// Workspace planes hold one 64-wide fp32 row per minibatch position p in the K-major tile layout of the UMMA operands:
+// [p / 128][16 chunks of 4 columns][128 rows][4] -- a warp (32 consecutive positions) then reads / writes 512 contiguous bytes per
+// 16-byte access instead of 32 rows 256 bytes apart (pl_off / ld_pl16 / st_pl16 in tc64.cuh).
 struct GruPlanes { float *X, *R, *Z, *N, *GHN, *H, *DHH, *DR, *DZ, *DN, *DFEAT; };
 
 __global__ void __launch_bounds__(256) gru_pack_kernel(const NetDev n, const float* __restrict__ p, float* __restrict__ img) {
@@ -87,8 +90,6 @@ __global__ void __launch_bounds__(256) gru_pack_kernel(const NetDev n, const flo
   }
 }
 
-__device__ __forceinline__ float sigm_tc(float x) { return 1.0f / (1.0f + expf(-x)); }
-
 __device__ __forceinline__ void ld_half16(const float* __restrict__ src, float* v) {      // 16 consecutive floats (64-byte aligned)
   const float4* s4 = reinterpret_cast<const float4*>(src);
 #pragma unroll
@@ -106,19 +107,44 @@ __device__ __forceinline__ void put_kmajor16(float* T, int c4, int r, const floa
 }
 
 // -------------------------------------------------------------------------------------------------------------------
-// 2. sequence forward.  Thread (row r = chunk of the tile, half wg) owns hidden columns [32 wg, 32 wg + 32) of every gate; the
-// state h stays in fp32 registers across the L steps (only the UMMA operand copy is rounded to tf32).
-// TMEM: [0,64) r, [64,128) z (x part + h part accumulated by two MMA batches), [128,192) W_in x + b_in, [192,256) W_hn hm.
+// 2. sequence forward.  512 threads = FOUR threads per chunk row: thread (row r, quarter q) owns hidden columns [16 q, 16 q + 16) of
+// every gate; warps w, w + 4, w + 8, w + 12 address the same 32 TMEM lanes.  The state h stays in fp32 registers across the L steps
+// (only the UMMA operand copy is rounded to tf32).
+// TMEM: two accumulator sets of 256 columns (step parity): [0,64) r, [64,128) z (x part, then the h part accumulated on top),
+// [128,192) W_hn hm + b_hn (b_hn preset with tcgen05.st, the h part accumulated on top), [192,256) W_in x + b_in.
+// The x part of step l + 1 does not depend on the state: it is issued right behind the h part of step l (into the other set, from
+// the other XA buffer) and runs under the cell math of step l, so the critical path of a step is the cell math, one barrier and
+// the 8 state MMAs (M 128, N 192, K 8 each).
 // -------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTCThreads, 1)
+constexpr int kSeqThreads = 512;
+
+__device__ __forceinline__ float tanh_ap(float x) {            // MUFU.TANH, relative error 2^-11
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigm_gate(float x) { return fmaf(0.5f, tanh_ap(0.5f * x), 0.5f); }      // absolute error <= 2.5e-4
+__device__ __forceinline__ float tanh_cell(float x) {          // 1 - 2 / (1 + e^(2x)): absolute error ~ 2e-7
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
+  return 1.f - __fdividef(2.f, 1.f + e);
+}
+// 16 values = features [c0, c0 + 16) of column r of a transposed tile [32][S][4]
+__device__ __forceinline__ void put_transposed16(float* T, int S, int r, int c0, const float* v) {
+  float* base = T + ((r >> 2) * S + c0) * 4 + (r & 3);
+#pragma unroll
+  for (int f = 0; f < 16; ++f) base[f * 4] = v[f];
+}
+
+__global__ void __launch_bounds__(kSeqThreads, 1)
 gru_tc_fwd_kernel(const NetDev n, const float* __restrict__ gimg, const BatchDev b, const GruPlanes ws, int n_seq_tiles) {
   extern __shared__ __align__(1024) float smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int r = tid & (kTM - 1), wg = tid >> 7;
+  const int r = tid & (kTM - 1), q = tid >> 7, c0 = q * 16;
   const GruImage im = make_gru_image();
   float* sImg = smem;
-  float* XA = sImg + im.fwd_floats;                 // [18][128][4]
-  float* HA = XA + kHC * kTM * 4;                   // [16][128][4]
+  float* XA0 = sImg + im.fwd_floats;                // 2 x [18][128][4]
+  float* HA = XA0 + 2 * kHC * kTM * 4;              // [16][128][4]
   uint64_t* bar_w = reinterpret_cast<uint64_t*>(HA + 16 * kTM * 4);
   uint64_t* bar_m = bar_w + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 2);
@@ -128,8 +154,10 @@ gru_tc_fwd_kernel(const NetDev n, const float* __restrict__ gimg, const BatchDev
     mbar_init(bar_m, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 256);
-  reinterpret_cast<float4*>(XA)[(16 + wg) * kTM + r] = make_float4(wg == 0 ? 1.f : 0.f, 0.f, 0.f, 0.f);     // constant-1 feature, pad
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  // constant-1 feature (chunk 16) and pad (chunk 17) of both XA buffers: 2 x 2 x 128 float4, one per thread
+  reinterpret_cast<float4*>(XA0 + (tid >> 8) * kHC * kTM * 4)[(16 + ((tid >> 7) & 1)) * kTM + r] =
+      make_float4(((tid >> 7) & 1) == 0 ? 1.f : 0.f, 0.f, 0.f, 0.f);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -141,108 +169,150 @@ gru_tc_fwd_kernel(const NetDev n, const float* __restrict__ gimg, const BatchDev
     tma_bulk_g2s(sImg + im.whh, gimg + im.whh, bytes - half, bar_w);
   }
   const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
-  const uint32_t aXA = smem_u32(XA), aHA = smem_u32(HA), aWih = smem_u32(sImg + im.wih), aWhh = smem_u32(sImg + im.whh);
-  const float* bhn = sImg + im.bhn;
+  const uint32_t aXA = smem_u32(XA0), aHA = smem_u32(HA), aWih = smem_u32(sImg + im.wih), aWhh = smem_u32(sImg + im.whh);
+  constexpr uint32_t kXAB = kHC * kTM * 16;         // bytes of one XA buffer
+  const float* bhn_g = gimg + im.bhn + c0;
   const float* h0 = n.is_critic ? b.h0_critic : b.h0_actor;
   uint32_t phase = 0;
   bool first = true;
+
+  // x part of a step: D[0,128) = xaug W_ih'[r, z]^T, D[192,256) = xaug W_ih'[n]^T
+  auto issue_x = [&](int step) {
+    const uint32_t d = tmem + 256u * (step & 1), a = aXA + (step & 1) * kXAB;
+    umma_seq(d, a, 2 * kRowB, kRowB, aWih, 2 * kG3 * 16, kG3 * 16, make_idesc(128, 128, 0, 0), kHF / 8, false);
+    umma_seq(d + 192, a, 2 * kRowB, kRowB, aWih + 128 * 16, 2 * kG3 * 16, kG3 * 16, make_idesc(128, 64, 0, 0), kHF / 8, false);
+  };
+  auto preset_bhn = [&](int step) {                 // D[128 + c0, +16) of this row <- b_hn
+    float v[16];
+    ld_half16(bhn_g, v);
+    tmem_st8(tmem + 256u * (step & 1) + lane_base + 128 + c0, v);
+    tmem_st8(tmem + 256u * (step & 1) + lane_base + 128 + c0 + 8, v + 8);
+  };
+
   for (int st = blockIdx.x; st < n_seq_tiles; st += gridDim.x) {
     const int c = st * kTM + r;
     const bool valid = c < Nc;
-    float h[32];
-    if (valid) {
-      const int src = b.seq_first ? b.seq_first[c] : c;
-      ld_half16(h0 + (size_t)src * 64 + wg * 32, h);
-      ld_half16(h0 + (size_t)src * 64 + wg * 32 + 16, h + 16);
-    } else {
+    float h[16], xq[16];
+    float mq = 0.f;
+    auto load_x = [&](int l) {                       // xq <- X row of step l (zeros past the end)
+      if (valid && l < Lsteps) ld_pl16(ws.X, (size_t)l * Nc + c, q * 4, xq);
+      else {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) h[i] = 0.f;
+        for (int i = 0; i < 16; ++i) xq[i] = 0.f;
+      }
+    };
+    auto load_m = [&](int l) {
+      mq = 0.f;
+      if (valid && l < Lsteps) { const size_t p = (size_t)l * Nc + c; mq = b.masks[b.rows ? b.rows[p] : (int)p]; }
+    };
+    if (valid) ld_half16(h0 + (size_t)(b.seq_first ? b.seq_first[c] : c) * 64 + c0, h);
+    else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) h[i] = 0.f;
     }
-    for (int l = 0; l < Lsteps; ++l) {
-      const size_t p = (size_t)l * Nc + c;
-      float m = 0.f;
-      {
-        float x[32];
-        if (valid) {
-          const int gr = b.rows ? b.rows[p] : (int)p;
-          m = b.masks[gr];
-          ld_half16(ws.X + p * 64 + wg * 32, x);
-          ld_half16(ws.X + p * 64 + wg * 32 + 16, x + 16);
-        } else {
+    load_x(0);
+    load_m(0);
+    put_kmajor16(XA0, q * 4, r, xq);
+    preset_bhn(0);
+    load_x(1);
+    fence_async_smem();
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      if (first) mbar_wait(bar_w, 0);
+      issue_x(0);
+    }
+    first = false;
+
+    // cell math of step l out of accumulator set l & 1: h (= hm_l, masked state of that step) -> h_l; planes of step l
+    auto cell = [&](int l) {
+      const uint32_t d = tmem + 256u * (l & 1) + lane_base + c0;
+      const size_t pp = (size_t)l * Nc + c;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) x[i] = 0.f;
+      for (int hh = 0; hh < 2; ++hh) {
+        float ar[8], az[8], ah[8], an[8];
+        tmem_ld8(d + hh * 8, ar);
+        tmem_ld8(d + 64 + hh * 8, az);
+        tmem_ld8(d + 128 + hh * 8, ah);
+        tmem_ld8(d + 192 + hh * 8, an);
+        tmem_ld_wait();
+        float hn[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {                // torch GRU cell, gate order (r, z, n)
+          const float rg = sigm_gate(ar[j]);
+          const float zg = sigm_gate(az[j]);
+          const float ng = tanh_cell(fmaf(rg, ah[j], an[j]));
+          hn[j] = fmaf(zg, h[hh * 8 + j] - ng, ng);  // (1 - z) n + z hm
+          ar[j] = rg; az[j] = zg; an[j] = ng;
         }
-        put_kmajor16(XA, wg * 8, r, x);
-        put_kmajor16(XA, wg * 8 + 4, r, x + 16);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h[hh * 8 + j] = hn[j];
+        if (valid) {
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const size_t o = pl_off(pp, q * 4 + hh * 2 + t);
+            *reinterpret_cast<float4*>(ws.R + o) = make_float4(ar[4 * t], ar[4 * t + 1], ar[4 * t + 2], ar[4 * t + 3]);
+            *reinterpret_cast<float4*>(ws.Z + o) = make_float4(az[4 * t], az[4 * t + 1], az[4 * t + 2], az[4 * t + 3]);
+            *reinterpret_cast<float4*>(ws.N + o) = make_float4(an[4 * t], an[4 * t + 1], an[4 * t + 2], an[4 * t + 3]);
+            *reinterpret_cast<float4*>(ws.GHN + o) = make_float4(ah[4 * t], ah[4 * t + 1], ah[4 * t + 2], ah[4 * t + 3]);
+            *reinterpret_cast<float4*>(ws.H + o) = make_float4(hn[4 * t], hn[4 * t + 1], hn[4 * t + 2], hn[4 * t + 3]);
+          }
+        }
+      }
+    };
+
+    for (int l = 0; l < Lsteps; ++l) {
+      if (l > 0) {
+        mbar_wait(bar_m, phase); phase ^= 1;         // state MMAs of step l - 1 done (and, in order before them, its x part)
+        tc_fence_after();
+        cell(l - 1);
       }
       {
-        float t[32];
+        float t[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { h[i] *= m; t[i] = to_tf32(h[i]); }        // h <- h * mask (rnn.py:27, :67)
-        put_kmajor16(HA, wg * 8, r, t);
-        put_kmajor16(HA, wg * 8 + 4, r, t + 16);
+        for (int i = 0; i < 16; ++i) { h[i] *= mq; t[i] = to_tf32(h[i]); }      // h <- h * mask_l (rnn.py:27, :67)
+        put_kmajor16(HA, q * 4, r, t);
+      }
+      if (l + 1 < Lsteps) {
+        put_kmajor16(XA0 + ((l + 1) & 1) * kHC * kTM * 4, q * 4, r, xq);
+        preset_bhn(l + 1);                           // (this thread has read its columns of that set in cell(l - 1) above)
       }
       fence_async_smem();
+      tmem_st_wait();
       tc_fence_before();
       __syncthreads();
       if (tid == 0) {
         tc_fence_after();
-        if (first) mbar_wait(bar_w, 0);
-        umma_seq(tmem, aXA, 2 * kRowB, kRowB, aWih, 2 * kG3 * 16, kG3 * 16, make_idesc(128, 192, 0, 0), kHF / 8, false);
-        umma_seq(tmem, aHA, 2 * kRowB, kRowB, aWhh, 2 * kG3 * 16, kG3 * 16, make_idesc(128, 128, 0, 0), 8, true);
-        umma_seq(tmem + 192, aHA, 2 * kRowB, kRowB, aWhh + 128 * 16, 2 * kG3 * 16, kG3 * 16, make_idesc(128, 64, 0, 0), 8, false);
+        umma_seq(tmem + 256u * (l & 1), aHA, 2 * kRowB, kRowB, aWhh, 2 * kG3 * 16, kG3 * 16, make_idesc(128, 192, 0, 0), 8, true);
         umma_commit(bar_m);
+        if (l + 1 < Lsteps) issue_x(l + 1);
       }
-      first = false;
-      mbar_wait(bar_m, phase); phase ^= 1;
-      tc_fence_after();
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int col0 = wg * 32 + cc * 16;
-        float ar[16], az[16], an[16], ah[16];
-        tmem_ld16(tmem + lane_base + col0, ar);
-        tmem_ld16(tmem + lane_base + 64 + col0, az);
-        tmem_ld16(tmem + lane_base + 128 + col0, an);
-        tmem_ld16(tmem + lane_base + 192 + col0, ah);
-        tmem_ld_wait();
-        float hn[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {                       // torch GRU cell, gate order (r, z, n)
-          const float rg = sigm_tc(ar[j]);
-          const float zg = sigm_tc(az[j]);
-          const float ghn = ah[j] + bhn[col0 + j];
-          const float ng = tanhf(fmaf(rg, ghn, an[j]));
-          hn[j] = fmaf(zg, h[cc * 16 + j] - ng, ng);         // (1 - z) n + z hm
-          ar[j] = rg; az[j] = zg; an[j] = ng; ah[j] = ghn;
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) h[cc * 16 + j] = hn[j];
-        if (valid) {
-          const size_t o = p * 64 + col0;
-          st_half16(ws.R + o, ar);
-          st_half16(ws.Z + o, az);
-          st_half16(ws.N + o, an);
-          st_half16(ws.GHN + o, ah);
-          st_half16(ws.H + o, hn);
-        }
-      }
-      tc_fence_before();
+      load_x(l + 2);                                 // in flight under the MMAs and the cell math
+      load_m(l + 1);
     }
+    mbar_wait(bar_m, phase); phase ^= 1;
+    tc_fence_after();
+    cell(Lsteps - 1);
+    tc_fence_before();
+    __syncthreads();                                 // every read of both accumulator sets is done before the next tile presets them
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 256);
+  if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 // -------------------------------------------------------------------------------------------------------------------
-// 4. sequence backward (BPTT).  dh carried in fp32 registers; per step the gate gradients go to the DR / DZ / DN planes (fp32) and,
-// tf32-rounded, into the K-major operand of dh_{l-1} += dgh W_hh (K = 192 gate outputs).
+// 4. sequence backward (BPTT), four threads per chunk row like the forward.  dh carried in fp32 registers; per step the gate
+// gradients go to the DR / DZ / DN planes (fp32) and, tf32-rounded, into the K-major operand of dh_{l-1} += dgh W_hh (K = 192 gate
+// outputs, 24 MMAs M 128 x N 64).
 // -------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTCThreads, 1)
+__global__ void __launch_bounds__(kSeqThreads, 1)
 gru_tc_bwd_kernel(const NetDev n, const float* __restrict__ gimg, const BatchDev b, const GruPlanes ws, int n_seq_tiles) {
   extern __shared__ __align__(1024) float smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int r = tid & (kTM - 1), wg = tid >> 7;
+  const int r = tid & (kTM - 1), q = tid >> 7, c0 = q * 16;
   const GruImage im = make_gru_image();
   float* sW = smem;                                 // whht [48][64][4]
   float* DG = sW + 48 * 64 * 4;                     // [48][128][4]: (dr, dz, dn * r)
@@ -274,55 +344,48 @@ gru_tc_bwd_kernel(const NetDev n, const float* __restrict__ gimg, const BatchDev
     const int c = st * kTM + r;
     const bool valid = c < Nc;
     const int src = valid ? (b.seq_first ? b.seq_first[c] : c) : 0;
-    float dh[32];
+    float dh[16];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) dh[i] = 0.f;
+    for (int i = 0; i < 16; ++i) dh[i] = 0.f;
     for (int l = Lsteps - 1; l >= 0; --l) {
       const size_t p = (size_t)l * Nc + c;
       float m = 0.f;
-      if (valid) m = b.masks[b.rows ? b.rows[p] : (int)p];
+      float rg[16], zg[16], ng[16], gh[16], dd[16], hp[16];
+      if (valid) {
+        m = b.masks[b.rows ? b.rows[p] : (int)p];
+        ld_pl16(ws.R, p, q * 4, rg);
+        ld_pl16(ws.Z, p, q * 4, zg);
+        ld_pl16(ws.N, p, q * 4, ng);
+        ld_pl16(ws.GHN, p, q * 4, gh);
+        ld_pl16(ws.DHH, p, q * 4, dd);
+        if (l > 0) ld_pl16(ws.H, p - (size_t)Nc, q * 4, hp);
+        else ld_half16(h0 + (size_t)src * 64 + c0, hp);
+      } else {
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int col0 = wg * 32 + cc * 16;
-        float rg[16], zg[16], ng[16], gh[16], dd[16], hp[16];
-        if (valid) {
-          const size_t o = p * 64 + col0;
-          ld_half16(ws.R + o, rg);
-          ld_half16(ws.Z + o, zg);
-          ld_half16(ws.N + o, ng);
-          ld_half16(ws.GHN + o, gh);
-          ld_half16(ws.DHH + o, dd);
-          ld_half16(l > 0 ? ws.H + (p - (size_t)Nc) * 64 + col0 : h0 + (size_t)src * 64 + col0, hp);
-        } else {
+        for (int j = 0; j < 16; ++j) { rg[j] = zg[j] = ng[j] = gh[j] = dd[j] = hp[j] = 0.f; }
+      }
 #pragma unroll
-          for (int j = 0; j < 16; ++j) { rg[j] = zg[j] = ng[j] = gh[j] = dd[j] = hp[j] = 0.f; }
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float d = dh[cc * 16 + j] + dd[j];                              // dL/dh_l: future steps + head path
-          const float hm = hp[j] * m;
-          const float dn_pre = d * (1.f - zg[j]) * (1.f - ng[j] * ng[j]);
-          const float dz_pre = d * (hm - ng[j]) * zg[j] * (1.f - zg[j]);
-          const float dr_pre = dn_pre * gh[j] * rg[j] * (1.f - rg[j]);
-          dh[cc * 16 + j] = d * zg[j];                                          // direct path h' = ... + z * hm
-          dd[j] = dr_pre; hp[j] = dz_pre; gh[j] = dn_pre;
-          ng[j] = to_tf32(dn_pre * rg[j]);
-        }
-        if (valid) {
-          const size_t o = p * 64 + col0;
-          st_half16(ws.DR + o, dd);
-          st_half16(ws.DZ + o, hp);
-          st_half16(ws.DN + o, gh);
-        }
-        if (l > 0) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) { dd[j] = to_tf32(dd[j]); hp[j] = to_tf32(hp[j]); }
-          put_kmajor16(DG, 0 + (col0 >> 2), r, dd);
-          put_kmajor16(DG, 16 + (col0 >> 2), r, hp);
-          put_kmajor16(DG, 32 + (col0 >> 2), r, ng);
-        }
+      for (int j = 0; j < 16; ++j) {
+        const float d = dh[j] + dd[j];                                          // dL/dh_l: future steps + head path
+        const float hm = hp[j] * m;
+        const float dn_pre = d * (1.f - zg[j]) * (1.f - ng[j] * ng[j]);
+        const float dz_pre = d * (hm - ng[j]) * zg[j] * (1.f - zg[j]);
+        const float dr_pre = dn_pre * gh[j] * rg[j] * (1.f - rg[j]);
+        dh[j] = d * zg[j];                                                      // direct path h' = ... + z * hm
+        dd[j] = dr_pre; hp[j] = dz_pre; gh[j] = dn_pre;
+        ng[j] = to_tf32(dn_pre * rg[j]);
+      }
+      if (valid) {
+        st_pl16(ws.DR, p, q * 4, dd);
+        st_pl16(ws.DZ, p, q * 4, hp);
+        st_pl16(ws.DN, p, q * 4, gh);
       }
       if (l == 0) break;                                                        // h0 is data: no gradient beyond the first step
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { dd[j] = to_tf32(dd[j]); hp[j] = to_tf32(hp[j]); }
+      put_kmajor16(DG, 0 + q * 4, r, dd);
+      put_kmajor16(DG, 16 + q * 4, r, hp);
+      put_kmajor16(DG, 32 + q * 4, r, ng);
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
@@ -336,12 +399,11 @@ gru_tc_bwd_kernel(const NetDev n, const float* __restrict__ gimg, const BatchDev
       mbar_wait(bar_m, phase); phase ^= 1;
       tc_fence_after();
       {
-        float t[32];
-        tmem_ld16(tmem + lane_base + wg * 32, t);
-        tmem_ld16(tmem + lane_base + wg * 32 + 16, t + 16);
+        float t[16];
+        tmem_ld16(tmem + lane_base + c0, t);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) dh[i] = (dh[i] + t[i]) * m;               // hm = h_{l-1} * mask_l
+        for (int i = 0; i < 16; ++i) dh[i] = (dh[i] + t[i]) * m;               // hm = h_{l-1} * mask_l
       }
       tc_fence_before();
     }
@@ -371,12 +433,12 @@ __host__ __device__ inline GradSmem make_grad_smem() {
   return s;
 }
 
-__global__ void __launch_bounds__(kTCThreads, 1)
+__global__ void __launch_bounds__(kSeqThreads, 1)
 gru_tc_grad_kernel(const NetDev n, const float* __restrict__ gimg, const BatchDev b, const GruPlanes ws, float* __restrict__ slots,
                    int n_tiles) {
   extern __shared__ __align__(1024) float smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int r = tid & (kTM - 1), wg = tid >> 7;
+  const int r = tid & (kTM - 1), q = tid >> 7, c0 = q * 16;     // four threads per row, 16 columns each
   const GruImage im = make_gru_image();
   const GradSmem sm = make_grad_smem();
   float* sW = smem + sm.w;
@@ -394,7 +456,7 @@ gru_tc_grad_kernel(const NetDev n, const float* __restrict__ gimg, const BatchDe
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
-  if (wg == 0) {                                     // constant-1 features 64 / 136 and the zero pads of both halves
+  if (q == 0) {                                      // constant-1 features 64 / 136 and the zero pads of both halves
     float* base = XHT + (r >> 2) * kXS * 4 + (r & 3);
 #pragma unroll
     for (int f = 64; f < 72; ++f) { base[f * 4] = (f == 64) ? 1.f : 0.f; base[(f + 72) * 4] = (f == 64) ? 1.f : 0.f; }
@@ -417,46 +479,38 @@ gru_tc_grad_kernel(const NetDev n, const float* __restrict__ gimg, const BatchDe
     const int p = tile * kTM + r;
     const bool valid = p < P;
     const int l = valid ? p / Nc : 0, c = valid ? p - l * Nc : 0;
-    float rg[32];
+    float rg[16], dg3[3][16];                       // every global load of the tile is issued up front: one exposed round trip
     {
-      float x[32], hm[32];
+      float x[16], hm[16];
       if (valid) {
         const float m = b.masks[b.rows ? b.rows[p] : p];
-        const float* hsrc = l > 0 ? ws.H + (size_t)(p - Nc) * 64 : h0 + (size_t)(b.seq_first ? b.seq_first[c] : c) * 64;
-        ld_half16(ws.X + (size_t)p * 64 + wg * 32, x);
-        ld_half16(ws.X + (size_t)p * 64 + wg * 32 + 16, x + 16);
-        ld_half16(hsrc + wg * 32, hm);
-        ld_half16(hsrc + wg * 32 + 16, hm + 16);
-        ld_half16(ws.R + (size_t)p * 64 + wg * 32, rg);
-        ld_half16(ws.R + (size_t)p * 64 + wg * 32 + 16, rg + 16);
+        ld_pl16(ws.X, (size_t)p, q * 4, x);
+        if (l > 0) ld_pl16(ws.H, (size_t)(p - Nc), q * 4, hm);
+        else ld_half16(h0 + (size_t)(b.seq_first ? b.seq_first[c] : c) * 64 + c0, hm);
+        ld_pl16(ws.R, (size_t)p, q * 4, rg);
+        ld_pl16(ws.DR, (size_t)p, q * 4, dg3[0]);
+        ld_pl16(ws.DZ, (size_t)p, q * 4, dg3[1]);
+        ld_pl16(ws.DN, (size_t)p, q * 4, dg3[2]);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) hm[i] = to_tf32(hm[i] * m);
+        for (int i = 0; i < 16; ++i) hm[i] = to_tf32(hm[i] * m);
       } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { x[i] = 0.f; hm[i] = 0.f; rg[i] = 0.f; }
+        for (int i = 0; i < 16; ++i) { x[i] = 0.f; hm[i] = 0.f; rg[i] = 0.f; dg3[0][i] = dg3[1][i] = dg3[2][i] = 0.f; }
       }
-      put_transposed32(XHT, kXS, r, wg, x);
-      put_transposed32(XHT + 72 * 4, kXS, r, wg, hm);
+      put_transposed16(XHT, kXS, r, c0, x);
+      put_transposed16(XHT, kXS, r, 72 + c0, hm);
     }
-#pragma unroll 1
+#pragma unroll
     for (int g = 0; g < 3; ++g) {
-      float dg[32];
-      if (valid) {
-        const float* pl = g == 0 ? ws.DR : (g == 1 ? ws.DZ : ws.DN);
-        ld_half16(pl + (size_t)p * 64 + wg * 32, dg);
-        ld_half16(pl + (size_t)p * 64 + wg * 32 + 16, dg + 16);
+      float dg[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) dg[i] = to_tf32(dg[i]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) dg[i] = 0.f;
-      }
-      put_kmajor32(DGk, r, wg, dg, false);
-      put_transposed32(DGT, kS65, r, wg, dg);
+      for (int i = 0; i < 16; ++i) dg[i] = to_tf32(dg3[g][i]);
+      put_kmajor16(DGk, q * 4, r, dg);
+      put_transposed16(DGT, kS65, r, c0, dg);
       if (g == 2) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) dg[i] = to_tf32(dg[i] * rg[i]);
-        put_transposed32(DHT, kS65, r, wg, dg);
+        for (int i = 0; i < 16; ++i) dg[i] = to_tf32(dg[i] * rg[i]);
+        put_transposed16(DHT, kS65, r, c0, dg);
       }
       fence_async_smem();
       tc_fence_before();
@@ -479,20 +533,17 @@ gru_tc_grad_kernel(const NetDev n, const float* __restrict__ gimg, const BatchDe
       tc_fence_after();
     }
     {
-      float d[32];
-      tmem_ld16(tmem + lane_base + wg * 32, d);
-      tmem_ld16(tmem + lane_base + wg * 32 + 16, d + 16);
+      float d[16];
+      tmem_ld16(tmem + lane_base + c0, d);
       tmem_ld_wait();
-      if (valid) {
-        st_half16(ws.DFEAT + (size_t)p * 64 + wg * 32, d);
-        st_half16(ws.DFEAT + (size_t)p * 64 + wg * 32 + 16, d + 16);
-      }
+      if (valid) st_pl16(ws.DFEAT, (size_t)p, q * 4, d);
     }
     first_tile = false;
     tc_fence_before();
   }
-  // raw accumulators -> this CTA's slot [3][64][144]; warpgroup w dumps columns [72 w, 72 w + 72) of every gate
-  {
+  // raw accumulators -> this CTA's slot [3][64][144]; warps 0..7: warpgroup w = q dumps columns [72 w, 72 w + 72) of every gate
+  if (q < 2) {
+    const int wg = q;
     float* gslot = slots + (size_t)blockIdx.x * kGcat;
     const bool has_tile = !first_tile;
     const int o = (warp & 3) * 16 + lane;              // accumulator row of this thread in the M = 64 layout
@@ -583,7 +634,7 @@ static GruTcWs make_gru_tc_ws(const NetDev& n, int n_rows, int sm_count) {
   w.scratch = o; o += 64;
   w.slots_tc = o; o += up((int64_t)2 * ctas * update_mlp_tc_slot_floats(n));
   w.slots_gru = o; o += up((int64_t)ctas * kGcat);
-  w.planes = o; o += (int64_t)10 * n_rows * 64;
+  w.planes = o; o += (int64_t)10 * plane_floats(n_rows);
   w.total = o;
   return w;
 }
@@ -618,7 +669,7 @@ int update_gru_tc_launch(const NetDev& n, const float* params, const BatchDev& b
   const GruImage im = make_gru_image();
   float* img_base = workspace + w.img_base;
   float* img_gru = workspace + w.img_gru;
-  const size_t plane = (size_t)b.n_rows * 64;
+  const size_t plane = (size_t)plane_floats(b.n_rows);
   float* pl = workspace + w.planes;
   GruPlanes ws;
   ws.X = pl; ws.R = pl + plane; ws.Z = pl + 2 * plane; ws.N = pl + 3 * plane; ws.GHN = pl + 4 * plane; ws.H = pl + 5 * plane;
@@ -642,9 +693,9 @@ int update_gru_tc_launch(const NetDev& n, const float* params, const BatchDev& b
   // 2. sequence forward
   {
     static thread_local SmemConfig cfg = {};
-    const size_t bytes = (size_t)(im.fwd_floats + kHC * kTM * 4 + 16 * kTM * 4 + 16) * sizeof(float) + 1024;
+    const size_t bytes = (size_t)(im.fwd_floats + 2 * kHC * kTM * 4 + 16 * kTM * 4 + 16) * sizeof(float) + 1024;
     if ((rc = set_smem(gru_tc_fwd_kernel, bytes, cfg, "gru_tc_fwd: cudaFuncSetAttribute"))) return rc;
-    gru_tc_fwd_kernel<<<seq_ctas, kTCThreads, bytes, st>>>(n, img_gru, b, ws, n_seq_tiles);
+    gru_tc_fwd_kernel<<<seq_ctas, kSeqThreads, bytes, st>>>(n, img_gru, b, ws, n_seq_tiles);
     if ((rc = check_launch("gru_tc_fwd_kernel"))) return rc;
   }
   // 3. heads + loss of every position
@@ -655,7 +706,7 @@ int update_gru_tc_launch(const NetDev& n, const float* params, const BatchDev& b
     static thread_local SmemConfig cfg = {};
     const size_t bytes = (size_t)(48 * 64 * 4 + 48 * kTM * 4 + 16) * sizeof(float) + 1024;
     if ((rc = set_smem(gru_tc_bwd_kernel, bytes, cfg, "gru_tc_bwd: cudaFuncSetAttribute"))) return rc;
-    gru_tc_bwd_kernel<<<seq_ctas, kTCThreads, bytes, st>>>(n, img_gru, b, ws, n_seq_tiles);
+    gru_tc_bwd_kernel<<<seq_ctas, kSeqThreads, bytes, st>>>(n, img_gru, b, ws, n_seq_tiles);
     if ((rc = check_launch("gru_tc_bwd_kernel"))) return rc;
   }
   // 5. gate gradients
@@ -663,7 +714,7 @@ int update_gru_tc_launch(const NetDev& n, const float* params, const BatchDev& b
     static thread_local SmemConfig cfg = {};
     const size_t bytes = (size_t)make_grad_smem().total * sizeof(float) + 1024;
     if ((rc = set_smem(gru_tc_grad_kernel, bytes, cfg, "gru_tc_grad: cudaFuncSetAttribute"))) return rc;
-    gru_tc_grad_kernel<<<ctas, kTCThreads, bytes, st>>>(n, img_gru, b, ws, slots_gru, n_tiles);
+    gru_tc_grad_kernel<<<ctas, kSeqThreads, bytes, st>>>(n, img_gru, b, ws, slots_gru, n_tiles);
     if ((rc = check_launch("gru_tc_grad_kernel"))) return rc;
   }
   // 6. base backward

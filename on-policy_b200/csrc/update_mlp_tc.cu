@@ -417,11 +417,7 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
 #pragma unroll
       for (int i = 0; i < 32; ++i) a[i] = to_tf32((a[i] - mu2) * rs2);
       if (MODE == TC_BASE_FWD) {                                  // the GRU's input rows; nothing else to do for this tile
-        if (p < b.n_rows) {
-          float4* dst = reinterpret_cast<float4*>(plane_out + (size_t)p * 64 + wg * 32);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) dst[q] = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
-        }
+        if (p < b.n_rows) { st_pl16(plane_out, (size_t)p, wg * 8, a); st_pl16(plane_out, (size_t)p, wg * 8 + 4, a + 16); }
         tc_fence_before();
         __syncthreads();
         continue;
@@ -432,11 +428,8 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
     } else {
       // ---- TC_HEAD: the GRU state of this position -> LayerNorm (rnn.norm, rnn.py:79) -> xhat (K-major staging + transposed) ----
       float a[32];
-      if (gr >= 0) {
-        const float4* src = reinterpret_cast<const float4*>(plane_in + (size_t)p * 64 + wg * 32);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) { const float4 v = __ldg(src + q); a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w; }
-      } else {
+      if (gr >= 0) { ld_pl16(plane_in, (size_t)p, wg * 8, a); ld_pl16(plane_in, (size_t)p, wg * 8 + 4, a + 16); }
+      else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) a[i] = 0.f;
       }
@@ -525,11 +518,7 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
 #pragma unroll
         for (int f = 0; f < 32; ++f) d[f] = rs2 * (d[f] - s1 - xh[f] * s2);
       }
-      if (p < b.n_rows) {
-        float4* dst = reinterpret_cast<float4*>(plane_out + (size_t)p * 64 + wg * 32);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) dst[q] = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
-      }
+      if (p < b.n_rows) { st_pl16(plane_out, (size_t)p, wg * 8, d); st_pl16(plane_out, (size_t)p, wg * 8 + 4, d + 16); }
       mbar_wait(bar_g, phase_g); phase_g ^= 1;             // Gh has consumed dL^T (TA) and xhat^T (X2T)
       tc_fence_after();
       first_tile = false;
@@ -541,11 +530,8 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
     {
       float d[32];
       if (MODE == TC_BASE_BWD) {                           // dL/dxhat2 from the GRU input projection (update_gru_tc.cu)
-        if (p < b.n_rows && gr >= 0) {
-          const float4* src = reinterpret_cast<const float4*>(plane_in + (size_t)p * 64 + wg * 32);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) { const float4 v = __ldg(src + q); d[4 * q] = v.x; d[4 * q + 1] = v.y; d[4 * q + 2] = v.z; d[4 * q + 3] = v.w; }
-        } else {
+        if (p < b.n_rows && gr >= 0) { ld_pl16(plane_in, (size_t)p, wg * 8, d); ld_pl16(plane_in, (size_t)p, wg * 8 + 4, d + 16); }
+        else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) d[i] = 0.f;
         }

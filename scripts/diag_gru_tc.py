@@ -44,7 +44,8 @@ for mode in ("fp32", "tf32"):
             pl = w[:8 * P * 64].reshape(8, P, 64)
             planes[nm] = dict(zip(["FEAT", "HM", "R", "Z", "N", "GHN", "DHH", "DFEAT"], pl))
         else:
-            pl = w[-10 * P * 64:].reshape(10, P, 64)
+            T = (P + 127) // 128                 # planes are tiled [p / 128][16 chunks][128 rows][4] (tc64.cuh: pl_off)
+            pl = w[-10 * T * 8192:].reshape(10, T, 16, 128, 4).transpose(0, 1, 3, 2, 4).reshape(10, T * 128, 64)[:, :P]
             planes[nm] = dict(zip(["X", "R", "Z", "N", "GHN", "H", "DFEAT", "DR", "DZ", "DN"], pl))
     grads = {("actor", k): v.cpu().numpy().copy() for k, v in policy.actor.named_grads().items()}
     grads.update({("critic", k): v.cpu().numpy().copy() for k, v in policy.critic.named_grads().items()})

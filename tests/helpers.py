@@ -89,7 +89,7 @@ def assert_close(a, b, rtol, atol, what=""):
                              f"(|err|={err[i]:.3e}, tol={tol[i]:.3e}); max|err|={err.max():.3e}")
 
 
-def grad_agreement(got, want, key, smooth, tf32, report=None):
+def grad_agreement(got, want, key, smooth, tf32, report=None, l2_tol=None):
     """Agreement of one gradient tensor with the reference, as (ok, relative L2 error).
 
     Smooth (tanh) nets: every element within a |ref| + b max|ref| (fp32 build a 2e-3, b 1e-4; tcgen05 / tf32 build a = b = 5e-3;
@@ -116,7 +116,7 @@ def grad_agreement(got, want, key, smooth, tf32, report=None):
     if smooth:
         ok = outside == 0.0
     else:
-        ok = l2 <= (5e-2 if tf32 else 2e-2)
+        ok = l2 <= (l2_tol if l2_tol is not None else (5e-2 if tf32 else 2e-2))
     if report is not None:
         report.append(f"{key}: max err / scale {err.max() / scale:.3e}, rel L2 {l2:.3e}, outside element tolerance {100 * outside:.2f} %"
                       + ("" if ok else "  <-- FAIL"))
