@@ -467,6 +467,60 @@ def kernel_roofline(res, a, peaks, tf32_peak):
                                "GEMMs of this pipeline sit between both roofs"},
                "pipeline_families": table, "update_pipeline_ms_per_step": pipeline_ms,
                "update_pipeline_tflops": (fa + fc) * n_upd / 1e12 / (pipeline_ms * 1e-3) if pipeline_ms > 0 else None}
+    elif cfg.recurrent and a.gemm == "tf32":
+        # tcgen05 GRU pipeline: the library times every kernel family with CUDA events on the launching stream (one eager train());
+        # the sequence kernels stream 64-float rows per position per plane: the honest bound of the dominant ones is HBM
+        lib.mappo_debug_gru_timing(1, None, None)
+        j = jobs[0]
+        saved_graph, saved_overlap = j.eng.graph, j.trainer.overlap_nets
+        j.eng.graph, j.trainer.overlap_nets = None, False
+        try:
+            res["flush"].zero_()
+            j.eng.step_resident()
+            torch.cuda.synchronize()
+        finally:
+            j.eng.graph, j.trainer.overlap_nets = saved_graph, saved_overlap
+        ms = (C.c_double * 8)()
+        cnt = (C.c_int64 * 8)()
+        lib.mappo_debug_gru_timing(0, ms, cnt)
+        fam = ["pack", "base_fwd", "seq_fwd", "heads_loss", "bptt", "gate_grad", "base_bwd", "reduce_unfold"]
+        table = {f: {"ms_total": ms[i], "launches": int(cnt[i])} for i, f in enumerate(fam)}
+        P = cfg.episode_length * cfg.n_rollout_threads * cfg.num_agents // cfg.data_chunk_length * cfg.data_chunk_length \
+            if cfg.use_recurrent_policy else cfg.episode_length * cfg.n_rollout_threads * cfg.num_agents
+        H = cfg.hidden_size
+        plane = 4 * P * H                                      # bytes of one [position][64] fp32 workspace plane
+        ins = (cfg.obs_dim, cfg.share_obs_dim)
+        heads = (sum(cfg.act_dims), 1)
+        n_upd = cfg.ppo_epoch * cfg.num_mini_batch             # per net kind; the table sums actor + critic launches
+        # algorithmic bytes per optimiser step, actor + critic (planes read + written by each kernel, gathered rows once)
+        by = {"base_fwd": sum(4 * P * i for i in ins) + 2 * plane, "seq_fwd": 2 * 6 * plane, "heads_loss": 2 * 2 * plane,
+              "bptt": 2 * 9 * plane, "gate_grad": 2 * 7 * plane, "base_bwd": sum(4 * P * i for i in ins) + 2 * plane}
+        fl = {"base_fwd": sum(2 * P * (i * H + H * H) for i in ins), "seq_fwd": 2 * 2 * P * 6 * H * H,
+              "heads_loss": sum(3 * 2 * P * H * h for h in heads), "bptt": 2 * 2 * P * 3 * H * H,
+              "gate_grad": 2 * 2 * P * (3 * H * H + 6 * H * H), "base_bwd": sum(2 * P * (3 * H * H + 2 * i * H) for i in ins)}
+        hbm_peak = float(peaks.get("hbm_gbs", 6580.0))
+        for f in by:
+            t = table[f]["ms_total"] * 1e-3
+            table[f]["algorithmic_gbyte"] = by[f] * n_upd / 1e9
+            table[f]["hbm_gbs"] = by[f] * n_upd / 1e9 / t if t > 0 else None
+            table[f]["hbm_frac"] = table[f]["hbm_gbs"] / hbm_peak if t > 0 else None
+            table[f]["tflops"] = fl[f] * n_upd / 1e12 / t if t > 0 else None
+        dom = max(by, key=lambda f: table[f]["ms_total"])
+        d = table[dom]
+        kern = {"base_fwd": "update_mlp_tc_kernel<TC_BASE_FWD>", "seq_fwd": "gru_tc_fwd_kernel", "heads_loss": "update_mlp_tc_kernel<TC_HEAD>",
+                "bptt": "gru_tc_bwd_kernel", "gate_grad": "gru_tc_grad_kernel", "base_bwd": "update_mlp_tc_kernel<TC_BASE_BWD>"}[dom]
+        pipeline_ms = sum(table[f]["ms_total"] for f in fam)
+        avg_ms = d["ms_total"] / max(d["launches"], 1)
+        out = {"bound": "hbm", "achieved": d["hbm_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": d["hbm_frac"],
+               "kernel": f"{kern} ({dom}: the slowest kernel family of the tcgen05 GRU pipeline, update_gru_tc.cu)",
+               "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6580 GB/s (B200_PROFILING.md)",
+               "avg_launch_ms": avg_ms, "launches_timed": d["launches"],
+               "algorithmic_mbyte_per_launch": d["algorithmic_gbyte"] * 1e3 / max(d["launches"], 1),
+               "kernel_share_of_step": d["ms_total"] / res["ms_per_step"],
+               "tensor": {"achieved": (fa + fc) * n_upd / 1e12 / (pipeline_ms * 1e-3) if pipeline_ms > 0 else None, "peak": tf32_peak,
+                          "unit": "TFLOP/s", "note": "whole pipeline (algorithmic GEMM FLOPs of one optimiser step / summed kernel time) "
+                                                      "against cuBLAS tf32 measured beside the run: the GEMMs are 64 wide, the planes set the pace"},
+               "pipeline_families": table, "update_pipeline_ms_per_step": pipeline_ms}
     else:
         orig = lib.mappo_update_fwd_bwd
         pairs = []
@@ -625,6 +679,8 @@ def run_gpu(a):
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
             key = ("big_lin_kernel" if eng0.big else ("update_mlp_tc_kernel" if a.gemm == "tf32" else "update_mlp_kernel"))
+            if cfg.recurrent and a.gemm == "tf32" and "kernel" in roof:
+                key = roof["kernel"].split(" ")[0] if a.config == "c4" else "-"      # per-kernel captures of the GRU pipeline at c4's size
             traffic = tj.get(key)
         roof["traffic"] = traffic
         roof["traffic_unit"] = "bytes/launch (ncu --set full, profiles/)"

@@ -26,7 +26,7 @@ extern "C" {
 
 #define MAPPO_MAX_HEADS 4      /* MultiDiscrete heads per actor */
 #define MAPPO_MAX_LAYERS 2     /* layer_N hidden (H->H) blocks per MLP base */
-#define MAPPO_ABI_VERSION 4
+#define MAPPO_ABI_VERSION 5
 
 typedef enum mappo_status {
   MAPPO_OK = 0,
@@ -193,6 +193,10 @@ int32_t mappo_big_net(const mappo_net_desc_t* desc);
  * GEMMs, [6] slot reduction + unfold -- accumulated over eager (non-captured) launches while `enable` was set; reading
  * synchronises on the recorded events.  Host pointers (7 entries each, nullable). */
 int32_t mappo_debug_big_timing(int32_t enable, double* ms_out7, int64_t* launches_out7);
+/* Same for the tcgen05 pipeline of recurrent (GRU) hidden-64 nets (MAPPO_GEMM_TF32; replaces the per-segment nn.GRU calls of
+ * algorithms/utils/rnn.py:43-77 and their autograd): [0] weight images, [1] base MLP forward, [2] sequence forward, [3] heads + loss,
+ * [4] BPTT, [5] gate gradients, [6] base MLP backward, [7] slot sums + unfold.  Host pointers (8 entries each, nullable). */
+int32_t mappo_debug_gru_timing(int32_t enable, double* ms_out8, int64_t* launches_out8);
 /* Kernel-level test entries: the two GEMM kernels of the pipeline in isolation (tests/test_gpu_bignet.py compares them with
  * torch.matmul).  mappo_debug_big_lin: out[rows, N] (leading dimension N + 32; columns N, N + 1 = row mean / sigma) =
  * relu(A[rows, K] W[N, K]^T + colvec[N + o]) and stats[rows] = (mean, 1 / sigma), K and N multiples of 32; scratch [rows, N]

@@ -193,6 +193,62 @@ __device__ __forceinline__ void tile_mm(const float* __restrict__ inT, int K, co
   }
 }
 
+// Two independent products of the same shape in ONE k loop (twice the independent FMA chains per thread: the rollout CTAs run one
+// warp per scheduler, so instruction-level parallelism is the only latency hiding there):
+//   sum == true :  out1T[n][r] = ((sum_k in2T[k][r] W2[n][k]) + ((sum_k in1T[k][r] W1[n][k]) + b1[n])) + b2[n]
+//                  -- bit-identical to tile_mm(in1, W1, b1 -> out1) followed by tile_mm(in2, W2, b2 -> out1, accumulate = true)
+//   sum == false:  out1T = in1 W1^T + b1,  out2T = in2 W2^T + b2
+// Forward orientation only (W row-major [N][K] with leading dimension ld), N == 16 * NJ.
+template <int TR, int NJ>
+__device__ __forceinline__ void tile_mm2(const float* __restrict__ in1T, const float* __restrict__ W1, const float* __restrict__ b1,
+                                         const float* __restrict__ in2T, const float* __restrict__ W2, const float* __restrict__ b2,
+                                         int K, int ld, float* __restrict__ out1T, float* __restrict__ out2T, bool sum, int tid) {
+  constexpr int LD = Tile<TR>::LD;
+  const int tx = tid & 15, r0 = (tid >> 4) * 4;
+  float acc1[4][NJ], acc2[4][NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    acc1[0][j] = acc1[1][j] = acc1[2][j] = acc1[3][j] = 0.f;
+    acc2[0][j] = acc2[1][j] = acc2[2][j] = acc2[3][j] = 0.f;
+  }
+  const float* ap1 = in1T + r0;
+  const float* ap2 = in2T + r0;
+  const float* w1 = W1 + tx * ld;
+  const float* w2 = W2 + tx * ld;
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    const float4 a1 = *reinterpret_cast<const float4*>(ap1 + k * LD);
+    const float4 a2 = *reinterpret_cast<const float4*>(ap2 + k * LD);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const float u = w1[16 * j * ld + k], v = w2[16 * j * ld + k];
+      acc1[0][j] = fmaf(a1.x, u, acc1[0][j]);
+      acc1[1][j] = fmaf(a1.y, u, acc1[1][j]);
+      acc1[2][j] = fmaf(a1.z, u, acc1[2][j]);
+      acc1[3][j] = fmaf(a1.w, u, acc1[3][j]);
+      acc2[0][j] = fmaf(a2.x, v, acc2[0][j]);
+      acc2[1][j] = fmaf(a2.y, v, acc2[1][j]);
+      acc2[2][j] = fmaf(a2.z, v, acc2[2][j]);
+      acc2[3][j] = fmaf(a2.w, v, acc2[3][j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int n = tx + 16 * j;
+    const float c1 = b1[n], c2 = b2[n];
+    float4 o1, o2;
+    o1.x = acc1[0][j] + c1; o1.y = acc1[1][j] + c1; o1.z = acc1[2][j] + c1; o1.w = acc1[3][j] + c1;
+    if (sum) {
+      o1.x = (acc2[0][j] + o1.x) + c2; o1.y = (acc2[1][j] + o1.y) + c2; o1.z = (acc2[2][j] + o1.z) + c2; o1.w = (acc2[3][j] + o1.w) + c2;
+      *reinterpret_cast<float4*>(out1T + n * LD + r0) = o1;
+    } else {
+      o2.x = acc2[0][j] + c2; o2.y = acc2[1][j] + c2; o2.z = acc2[2][j] + c2; o2.w = acc2[3][j] + c2;
+      *reinterpret_cast<float4*>(out1T + n * LD + r0) = o1;
+      *reinterpret_cast<float4*>(out2T + n * LD + r0) = o2;
+    }
+  }
+}
+
 // Fused layer: Y = LayerNorm(act(X W^T + b)) * gamma + beta for N == 16*NJ output features, the LayerNorm statistics
 // taken with warp shuffles across the 16 threads that share a row (no shared-memory pass, no extra barriers).
 // Optionally also leaves act(.) in AT and (mean, rstd) per row for a later backward pass.

@@ -170,16 +170,13 @@ __device__ __forceinline__ void pol_step(const NetDev& n, int which, const PolCt
       hT[cc * LD + r] = h * m;
     }
     __syncthreads();
-#pragma unroll 1
-    for (int gate = 0; gate < 3; ++gate)
-      tile_mm<TR, NJH>(feat, H, sW + s.wih + gate * H * s.ldh, s.ldh, 1, H, sW + s.bih + gate * H, ACT_NONE,
-                       gi + gate * H * LD, tid);
-    // each thread re-reads exactly the outputs it wrote, so no barrier is needed before accumulating
+    // r and z gates: x part and state part in one k loop (same summation order and rounding as two passes), then the n gate's two halves
 #pragma unroll 1
     for (int gate = 0; gate < 2; ++gate)
-      tile_mm<TR, NJH>(hT, H, sW + s.whh + gate * H * s.ldh, s.ldh, 1, H, sW + s.bhh + gate * H, ACT_NONE,
-                       gi + gate * H * LD, tid, true);
-    tile_mm<TR, NJH>(hT, H, sW + s.whh + 2 * H * s.ldh, s.ldh, 1, H, sW + s.bhh + 2 * H, ACT_NONE, gh, tid);
+      tile_mm2<TR, NJH>(feat, sW + s.wih + gate * H * s.ldh, sW + s.bih + gate * H, hT, sW + s.whh + gate * H * s.ldh,
+                        sW + s.bhh + gate * H, H, s.ldh, gi + gate * H * LD, nullptr, true, tid);
+    tile_mm2<TR, NJH>(feat, sW + s.wih + 2 * H * s.ldh, sW + s.bih + 2 * H, hT, sW + s.whh + 2 * H * s.ldh, sW + s.bhh + 2 * H, H, s.ldh,
+                      gi + 2 * H * LD, gh, false, tid);
     __syncthreads();
     float* hn = (feat == smem + u.s0) ? smem + u.s1 : smem + u.s0;      // new hidden state (pre-LN): the free tile
     for (int i = tid; i < TR * H; i += NT) {

@@ -14,6 +14,7 @@
 // affine in front of the GRU (base.mlp.fc2[0] LayerNorm) is folded into W_ih' = W_ih diag(gamma), b' = b_ih + W_ih beta
 // (+ b_hh for the r and z gates, whose pre-activations are plain sums), the rnn.norm affine into the heads.
 #include <cstdlib>
+#include <vector>
 #include "tc64.cuh"
 
 namespace mappo {
@@ -171,7 +172,8 @@ gru_tc_fwd_kernel(const NetDev n, const float* __restrict__ gimg, const BatchDev
   const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
   const uint32_t aXA = smem_u32(XA0), aHA = smem_u32(HA), aWih = smem_u32(sImg + im.wih), aWhh = smem_u32(sImg + im.whh);
   constexpr uint32_t kXAB = kHC * kTM * 16;         // bytes of one XA buffer
-  const float* bhn_g = gimg + im.bhn + c0;
+  float bhn[16];                                    // b_hh of the n gate for this thread's columns
+  ld_half16(gimg + im.bhn + c0, bhn);
   const float* h0 = n.is_critic ? b.h0_critic : b.h0_actor;
   uint32_t phase = 0;
   bool first = true;
@@ -183,10 +185,8 @@ gru_tc_fwd_kernel(const NetDev n, const float* __restrict__ gimg, const BatchDev
     umma_seq(d + 192, a, 2 * kRowB, kRowB, aWih + 128 * 16, 2 * kG3 * 16, kG3 * 16, make_idesc(128, 64, 0, 0), kHF / 8, false);
   };
   auto preset_bhn = [&](int step) {                 // D[128 + c0, +16) of this row <- b_hn
-    float v[16];
-    ld_half16(bhn_g, v);
-    tmem_st8(tmem + 256u * (step & 1) + lane_base + 128 + c0, v);
-    tmem_st8(tmem + 256u * (step & 1) + lane_base + 128 + c0 + 8, v + 8);
+    tmem_st8(tmem + 256u * (step & 1) + lane_base + 128 + c0, bhn);
+    tmem_st8(tmem + 256u * (step & 1) + lane_base + 128 + c0 + 8, bhn + 8);
   };
 
   for (int st = blockIdx.x; st < n_seq_tiles; st += gridDim.x) {
@@ -605,6 +605,41 @@ gru_unfold_kernel(const NetDev n, const float* __restrict__ p, const float* __re
 // -------------------------------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------------------------------
+// diagnostic (bench.py's roofline leg, eager passes only -- no events while a stream is capturing): CUDA-event time of each kernel
+// family of the pipeline
+enum { TG_PACK = 0, TG_BASE_FWD, TG_SEQ_FWD, TG_HEAD, TG_BPTT, TG_GATE_GRAD, TG_BASE_BWD, TG_FINISH, TG_N };
+struct GruTimedLaunch { cudaEvent_t a, b; int cat; };
+static bool g_gru_timing = false;
+static std::vector<GruTimedLaunch> g_gru_timed;
+struct GruTimed {
+  cudaStream_t st; cudaEvent_t a; int cat; bool on;
+  GruTimed(int c, cudaStream_t s) : st(s), a(nullptr), cat(c), on(false) {
+    if (!g_gru_timing) return;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
+    on = cudaEventCreate(&a) == cudaSuccess && cudaEventRecord(a, s) == cudaSuccess;
+  }
+  ~GruTimed() {
+    if (!on) return;
+    cudaEvent_t b;
+    if (cudaEventCreate(&b) == cudaSuccess && cudaEventRecord(b, st) == cudaSuccess) g_gru_timed.push_back({a, b, cat});
+  }
+};
+int debug_gru_timing(int enable, double* ms_out, long long* n_out) {
+  for (int i = 0; i < TG_N; ++i) { if (ms_out) ms_out[i] = 0.0; if (n_out) n_out[i] = 0; }
+  for (const GruTimedLaunch& t : g_gru_timed) {
+    cudaEventSynchronize(t.b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, t.a, t.b);
+    if (ms_out) ms_out[t.cat] += ms;
+    if (n_out) n_out[t.cat] += 1;
+    cudaEventDestroy(t.a); cudaEventDestroy(t.b);
+  }
+  g_gru_timed.clear();
+  g_gru_timing = enable != 0;
+  return MAPPO_OK;
+}
+
 bool update_gru_tc_supported(const NetDev& n) {
   return n.recurrent && n.hid == 64 && n.layer_n == 1 && n.in_dim <= 63 && n.head_total <= 32;
 }
@@ -684,14 +719,21 @@ int update_gru_tc_launch(const NetDev& n, const float* params, const BatchDev& b
   float* slots_gru = workspace + w.slots_gru;
   int rc;
   // weight images of the current parameters
-  if ((rc = update_mlp_tc_pack_launch(n, params, img_base, st))) return rc;
-  gru_pack_kernel<<<(im.total + 255) / 256, 256, 0, st>>>(n, params, img_gru);
-  if ((rc = check_launch("gru_pack_kernel"))) return rc;
+  {
+    GruTimed t(TG_PACK, st);
+    if ((rc = update_mlp_tc_pack_launch(n, params, img_base, st))) return rc;
+    gru_pack_kernel<<<(im.total + 255) / 256, 256, 0, st>>>(n, params, img_gru);
+    if ((rc = check_launch("gru_pack_kernel"))) return rc;
+  }
   // 1. base forward
-  if ((rc = update_mlp_tc_mode_launch(1, n, params, img_base, b, L, norm_stats, adv_stats, vn_state, nullptr, ctas, loss_out, nullptr, ws.X, st)))
-    return rc;
+  {
+    GruTimed t(TG_BASE_FWD, st);
+    if ((rc = update_mlp_tc_mode_launch(1, n, params, img_base, b, L, norm_stats, adv_stats, vn_state, nullptr, ctas, loss_out, nullptr, ws.X, st)))
+      return rc;
+  }
   // 2. sequence forward
   {
+    GruTimed t(TG_SEQ_FWD, st);
     static thread_local SmemConfig cfg = {};
     const size_t bytes = (size_t)(im.fwd_floats + 2 * kHC * kTM * 4 + 16 * kTM * 4 + 16) * sizeof(float) + 1024;
     if ((rc = set_smem(gru_tc_fwd_kernel, bytes, cfg, "gru_tc_fwd: cudaFuncSetAttribute"))) return rc;
@@ -699,10 +741,14 @@ int update_gru_tc_launch(const NetDev& n, const float* params, const BatchDev& b
     if ((rc = check_launch("gru_tc_fwd_kernel"))) return rc;
   }
   // 3. heads + loss of every position
-  if ((rc = update_mlp_tc_mode_launch(3, n, params, img_base, b, L, norm_stats, adv_stats, vn_state, slots_tc, ctas, loss_out, ws.H, ws.DHH, st)))
-    return rc;
+  {
+    GruTimed t(TG_HEAD, st);
+    if ((rc = update_mlp_tc_mode_launch(3, n, params, img_base, b, L, norm_stats, adv_stats, vn_state, slots_tc, ctas, loss_out, ws.H, ws.DHH, st)))
+      return rc;
+  }
   // 4. BPTT
   {
+    GruTimed t(TG_BPTT, st);
     static thread_local SmemConfig cfg = {};
     const size_t bytes = (size_t)(48 * 64 * 4 + 48 * kTM * 4 + 16) * sizeof(float) + 1024;
     if ((rc = set_smem(gru_tc_bwd_kernel, bytes, cfg, "gru_tc_bwd: cudaFuncSetAttribute"))) return rc;
@@ -711,6 +757,7 @@ int update_gru_tc_launch(const NetDev& n, const float* params, const BatchDev& b
   }
   // 5. gate gradients
   {
+    GruTimed t(TG_GATE_GRAD, st);
     static thread_local SmemConfig cfg = {};
     const size_t bytes = (size_t)make_grad_smem().total * sizeof(float) + 1024;
     if ((rc = set_smem(gru_tc_grad_kernel, bytes, cfg, "gru_tc_grad: cudaFuncSetAttribute"))) return rc;
@@ -718,10 +765,14 @@ int update_gru_tc_launch(const NetDev& n, const float* params, const BatchDev& b
     if ((rc = check_launch("gru_tc_grad_kernel"))) return rc;
   }
   // 6. base backward
-  if ((rc = update_mlp_tc_mode_launch(2, n, params, img_base, b, L, norm_stats, adv_stats, vn_state, slots_tc + (size_t)ctas * R, ctas, loss_out,
-                                      ws.DFEAT, nullptr, st)))
-    return rc;
+  {
+    GruTimed t(TG_BASE_BWD, st);
+    if ((rc = update_mlp_tc_mode_launch(2, n, params, img_base, b, L, norm_stats, adv_stats, vn_state, slots_tc + (size_t)ctas * R, ctas, loss_out,
+                                        ws.DFEAT, nullptr, st)))
+      return rc;
+  }
   // 7. slot sums + unfold
+  GruTimed t_fin(TG_FINISH, st);
   float* raw_base = workspace + w.raw_base;
   float* raw_gru = workspace + w.raw_gru;
   if ((rc = grad_reduce_launch(slots_tc, 2 * ctas, R, raw_base, nullptr, nullptr, st))) return rc;

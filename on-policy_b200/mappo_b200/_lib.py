@@ -59,6 +59,7 @@ _SIGS = {
     "mappo_rollout_image_floats": (_i32, [C.POINTER(NetDesc)]),
     "mappo_big_net": (_i32, [C.POINTER(NetDesc)]),
     "mappo_debug_big_timing": (_i32, [_i32, _P, _P]),
+    "mappo_debug_gru_timing": (_i32, [_i32, _P, _P]),
     "mappo_debug_big_lin": (_i32, [_P, _i32, _P, _i32, _P, _P, _P, _P, _i32, _i32, _i32, _i32, _P]),
     "mappo_debug_big_grad": (_i32, [_P, _i32, _i32, _i32, _P, _i32, _i32, _i32, _P, _P, _i32, _P]),
     "mappo_debug_big_grad_splits": (_i32, [_i32, _i32, _i32, _i32]),
@@ -124,7 +125,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError here = header / library out of sync
         fn.restype = res
         fn.argtypes = args
-    if lib.mappo_abi_version() != 4:
+    if lib.mappo_abi_version() != 5:
         raise RuntimeError("libmappo_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -78,6 +78,38 @@ def test_net_layout_matches_reference_param_count():
             assert lay.total == n_ref, (name, which)
 
 
+def test_tensor_core_build_selection_per_net_family():
+    """MAPPO_GEMM_TF32 is built for hidden-64 MLP nets (layer_N 1, in_dim <= 63), hidden-64 GRU nets (same base) and the hidden
+    >= 128 GEMM pipeline; the recurrent tcgen05 pipeline leaves the flat gradient in ONE slot and sizes its workspace (weight
+    images, raw gradient slots, ten [position][64] planes in 128-position tiles) from the row count alone -- host-side queries, no
+    GPU needed."""
+    from mappo_b200 import _lib
+    lib = _lib.load()
+
+    def desc(in_dim, hidden, layer_n, recurrent, heads=(5,)):
+        d = _lib.NetDesc()
+        d.in_dim, d.hidden, d.layer_n = in_dim, hidden, layer_n
+        d.use_feature_norm, d.use_relu, d.recurrent = 1, 0, recurrent
+        d.n_heads = len(heads)
+        for k, a in enumerate(heads):
+            d.head_dim[k] = a
+        d.is_critic = 0
+        return d
+
+    assert lib.mappo_tf32_supported(C.byref(desc(18, 64, 1, 0))) == 1
+    assert lib.mappo_tf32_supported(C.byref(desc(21, 64, 1, 1, (5, 10)))) == 1          # c3: GRU, MultiDiscrete
+    assert lib.mappo_tf32_supported(C.byref(desc(30, 64, 1, 1, (9,)))) == 1             # c4
+    assert lib.mappo_tf32_supported(C.byref(desc(100, 64, 1, 1))) == 0                  # in_dim > 63: fp32 kernels only
+    assert lib.mappo_tf32_supported(C.byref(desc(30, 64, 2, 1))) == 0                   # layer_N 2
+    assert lib.mappo_tf32_supported(C.byref(desc(40, 512, 2, 0, (20,)))) == 1           # c5 widths: GEMM pipeline
+    gru = desc(30, 64, 1, 1, (9,))
+    rows = 5120
+    ws_fp32 = lib.mappo_update_workspace_floats(C.byref(gru), rows, _lib.GEMM_FP32)
+    assert ws_fp32 == 8 * rows * 64
+    # (the grid-dependent part of the tcgen05 workspace needs the device's SM count: only checked where a GPU is present)
+    assert lib.mappo_update_slot_floats(C.byref(gru), _lib.GEMM_TF32) == lib.mappo_update_slot_floats(C.byref(gru), _lib.GEMM_FP32)
+
+
 def test_bad_descriptor_is_rejected_with_message():
     from mappo_b200 import _lib
     lib = _lib.load()
