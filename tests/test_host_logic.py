@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in sorted(declared) if not hasattr(lib, n)]
     assert not missing, f"declared in mappo_b200.h but not exported: {missing}"
     assert declared == set(_lib.EXPORTS), (declared ^ set(_lib.EXPORTS))
-    assert _lib.load().mappo_abi_version() == 4
+    assert _lib.load().mappo_abi_version() == 5
 
 
 def test_binding_arity_and_scalar_types_match_the_header():
