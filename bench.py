@@ -483,6 +483,8 @@ def kernel_roofline(res, a, peaks, tf32_peak):
         ms = (C.c_double * 8)()
         cnt = (C.c_int64 * 8)()
         lib.mappo_debug_gru_timing(0, ms, cnt)
+        cyc = (C.c_int64 * 16)()
+        lib.mappo_debug_gru_cycles(cyc)
         fam = ["pack", "base_fwd", "seq_fwd", "heads_loss", "bptt", "gate_grad", "base_bwd", "reduce_unfold"]
         table = {f: {"ms_total": ms[i], "launches": int(cnt[i])} for i, f in enumerate(fam)}
         P = cfg.episode_length * cfg.n_rollout_threads * cfg.num_agents // cfg.data_chunk_length * cfg.data_chunk_length \
@@ -520,7 +522,11 @@ def kernel_roofline(res, a, peaks, tf32_peak):
                "tensor": {"achieved": (fa + fc) * n_upd / 1e12 / (pipeline_ms * 1e-3) if pipeline_ms > 0 else None, "peak": tf32_peak,
                           "unit": "TFLOP/s", "note": "whole pipeline (algorithmic GEMM FLOPs of one optimiser step / summed kernel time) "
                                                       "against cuBLAS tf32 measured beside the run: the GEMMs are 64 wide, the planes set the pace"},
-               "pipeline_families": table, "update_pipeline_ms_per_step": pipeline_ms}
+               "pipeline_families": table, "update_pipeline_ms_per_step": pipeline_ms,
+               "seq_step_cycles": {"fwd": {nm: int(cyc[i + 1] - cyc[i]) for i, nm in enumerate(
+                                       ["wait_state_mma", "cell_math_stores", "operand_tiles", "barrier", "mma_issue", "prefetch_issue"])},
+                                   "bwd": {nm: int(cyc[9 + i] - cyc[8 + i]) for i, nm in enumerate(
+                                       ["loads_gate_math_stores", "operand_tile", "barrier", "mma_issue", "mma_wait", "dh_update"])}}}
     else:
         orig = lib.mappo_update_fwd_bwd
         pairs = []

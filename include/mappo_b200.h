@@ -197,6 +197,9 @@ int32_t mappo_debug_big_timing(int32_t enable, double* ms_out7, int64_t* launche
  * algorithms/utils/rnn.py:43-77 and their autograd): [0] weight images, [1] base MLP forward, [2] sequence forward, [3] heads + loss,
  * [4] BPTT, [5] gate gradients, [6] base MLP backward, [7] slot sums + unfold.  Host pointers (8 entries each, nullable). */
 int32_t mappo_debug_gru_timing(int32_t enable, double* ms_out8, int64_t* launches_out8);
+/* clock64 stamps inside one step of the two sequence kernels (CTA 0, thread 0; update_gru_tc.cu lists the points): where does a step's
+ * latency go.  Host pointer, 16 entries. */
+int32_t mappo_debug_gru_cycles(int64_t* out16);
 /* Kernel-level test entries: the two GEMM kernels of the pipeline in isolation (tests/test_gpu_bignet.py compares them with
  * torch.matmul).  mappo_debug_big_lin: out[rows, N] (leading dimension N + 32; columns N, N + 1 = row mean / sigma) =
  * relu(A[rows, K] W[N, K]^T + colvec[N + o]) and stats[rows] = (mean, 1 / sigma), K and N multiples of 32; scratch [rows, N]

@@ -98,6 +98,7 @@ int update_gru_slots(const NetDev& n, int n_rows, int seq_len, int sm_count);
 int64_t update_gru_workspace_floats(const NetDev& n, int n_rows);
 bool update_gru_tc_supported(const NetDev& n);
 int debug_gru_timing(int enable, double* ms_out, long long* n_out);
+int debug_gru_cycles(long long* out16);
 int64_t update_gru_tc_workspace_floats(const NetDev& n, int n_rows, int sm_count);
 int update_gru_tc_launch(const NetDev&, const float*, const BatchDev&, const LossDev&, const double*, const double*, const float*,
                          float* grad_out, double* loss_out, float* workspace, int sm_count, cudaStream_t);
@@ -335,6 +336,8 @@ int32_t mappo_rollout_image_floats(const mappo_net_desc_t* desc) {
   if (validate_desc(desc)) return -1;
   return rollout_image_floats(make_net_dev(desc));
 }
+
+int32_t mappo_debug_gru_cycles(int64_t* out16) { return debug_gru_cycles(reinterpret_cast<long long*>(out16)); }
 
 int32_t mappo_debug_gru_timing(int32_t enable, double* ms_out8, int64_t* launches_out8) {
   return debug_gru_timing(enable, ms_out8, reinterpret_cast<long long*>(launches_out8));

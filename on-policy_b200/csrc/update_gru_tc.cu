@@ -119,6 +119,13 @@ __device__ __forceinline__ void put_kmajor16(float* T, int c4, int r, const floa
 // -------------------------------------------------------------------------------------------------------------------
 constexpr int kSeqThreads = 512;
 
+// clock64 stamps of CTA 0 / thread 0 inside step 2 of its first tile (mappo_debug_gru_cycles): [0] top of the step, [1] state MMAs of
+// the previous step done, [2] cell math + plane stores issued, [3] operand tiles written, [4] barrier passed, [5] MMAs issued,
+// [6] prefetch loads issued; [8..] the same points of the BPTT kernel ([8] top, [9] loads landed + gate math + stores, [10] operand
+// written, [11] barrier, [12] MMAs issued, [13] MMAs done, [14] dh updated)
+__device__ long long g_gru_cycles[16];
+#define GRU_STAMP(i, cond) do { if (blockIdx.x == 0 && tid == 0 && (cond)) g_gru_cycles[i] = clock64(); } while (0)
+
 __device__ __forceinline__ float tanh_ap(float x) {            // MUFU.TANH, relative error 2^-11
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -194,6 +201,7 @@ gru_tc_fwd_kernel(const NetDev n, const float* __restrict__ gimg, const BatchDev
     const bool valid = c < Nc;
     float h[16], xq[16];
     float mq = 0.f;
+    int grq = -1;                                   // storage row of the step after the one mq belongs to
     auto load_x = [&](int l) {                       // xq <- X row of step l (zeros past the end)
       if (valid && l < Lsteps) ld_pl16(ws.X, (size_t)l * Nc + c, q * 4, xq);
       else {
@@ -201,9 +209,15 @@ gru_tc_fwd_kernel(const NetDev n, const float* __restrict__ gimg, const BatchDev
         for (int i = 0; i < 16; ++i) xq[i] = 0.f;
       }
     };
+    // mask of step l through the storage-row index fetched one step earlier, then the index of step l + 1: two independent loads
+    // (rows[p] -> masks[gr] back to back would park the warp on the first one: in-order issue)
+    auto load_gr = [&](int l) {
+      grq = -1;
+      if (valid && l < Lsteps) { const size_t p = (size_t)l * Nc + c; grq = b.rows ? b.rows[p] : (int)p; }
+    };
     auto load_m = [&](int l) {
-      mq = 0.f;
-      if (valid && l < Lsteps) { const size_t p = (size_t)l * Nc + c; mq = b.masks[b.rows ? b.rows[p] : (int)p]; }
+      mq = grq >= 0 ? b.masks[grq] : 0.f;
+      load_gr(l + 1);
     };
     if (valid) ld_half16(h0 + (size_t)(b.seq_first ? b.seq_first[c] : c) * 64 + c0, h);
     else {
@@ -211,6 +225,7 @@ gru_tc_fwd_kernel(const NetDev n, const float* __restrict__ gimg, const BatchDev
       for (int i = 0; i < 16; ++i) h[i] = 0.f;
     }
     load_x(0);
+    load_gr(0);
     load_m(0);
     put_kmajor16(XA0, q * 4, r, xq);
     preset_bhn(0);
@@ -264,11 +279,15 @@ gru_tc_fwd_kernel(const NetDev n, const float* __restrict__ gimg, const BatchDev
     };
 
     for (int l = 0; l < Lsteps; ++l) {
+      const bool stamp = l == 2 && st == (int)blockIdx.x;
+      GRU_STAMP(0, stamp);
       if (l > 0) {
         mbar_wait(bar_m, phase); phase ^= 1;         // state MMAs of step l - 1 done (and, in order before them, its x part)
         tc_fence_after();
+        GRU_STAMP(1, stamp);
         cell(l - 1);
       }
+      GRU_STAMP(2, stamp);
       {
         float t[16];
 #pragma unroll
@@ -282,15 +301,19 @@ gru_tc_fwd_kernel(const NetDev n, const float* __restrict__ gimg, const BatchDev
       fence_async_smem();
       tmem_st_wait();
       tc_fence_before();
+      GRU_STAMP(3, stamp);
       __syncthreads();
+      GRU_STAMP(4, stamp);
       if (tid == 0) {
         tc_fence_after();
         umma_seq(tmem + 256u * (l & 1), aHA, 2 * kRowB, kRowB, aWhh, 2 * kG3 * 16, kG3 * 16, make_idesc(128, 192, 0, 0), 8, true);
         umma_commit(bar_m);
         if (l + 1 < Lsteps) issue_x(l + 1);
       }
+      GRU_STAMP(5, stamp);
       load_x(l + 2);                                 // in flight under the MMAs and the cell math
       load_m(l + 1);
+      GRU_STAMP(6, stamp);
     }
     mbar_wait(bar_m, phase); phase ^= 1;
     tc_fence_after();
@@ -347,12 +370,18 @@ gru_tc_bwd_kernel(const NetDev n, const float* __restrict__ gimg, const BatchDev
     float dh[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) dh[i] = 0.f;
+    // mask of step l through the row index fetched one step earlier (no rows[p] -> masks[gr] chain inside a step)
+    auto row_of = [&](int l) { const size_t pp = (size_t)l * Nc + c; return (valid && l >= 0) ? (b.rows ? b.rows[pp] : (int)pp) : -1; };
+    int grq = row_of(Lsteps - 1);
+    float mq = grq >= 0 ? b.masks[grq] : 0.f;
+    grq = row_of(Lsteps - 2);
     for (int l = Lsteps - 1; l >= 0; --l) {
       const size_t p = (size_t)l * Nc + c;
-      float m = 0.f;
+      const float m = mq;
+      const bool stamp = l == Lsteps - 3 && st == (int)blockIdx.x;
+      GRU_STAMP(8, stamp);
       float rg[16], zg[16], ng[16], gh[16], dd[16], hp[16];
       if (valid) {
-        m = b.masks[b.rows ? b.rows[p] : (int)p];
         ld_pl16(ws.R, p, q * 4, rg);
         ld_pl16(ws.Z, p, q * 4, zg);
         ld_pl16(ws.N, p, q * 4, ng);
@@ -364,6 +393,8 @@ gru_tc_bwd_kernel(const NetDev n, const float* __restrict__ gimg, const BatchDev
 #pragma unroll
         for (int j = 0; j < 16; ++j) { rg[j] = zg[j] = ng[j] = gh[j] = dd[j] = hp[j] = 0.f; }
       }
+      mq = grq >= 0 ? b.masks[grq] : 0.f;          // step l - 1 (in flight under this step)
+      grq = row_of(l - 2);
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const float d = dh[j] + dd[j];                                          // dL/dh_l: future steps + head path
@@ -381,6 +412,7 @@ gru_tc_bwd_kernel(const NetDev n, const float* __restrict__ gimg, const BatchDev
         st_pl16(ws.DN, p, q * 4, gh);
       }
       if (l == 0) break;                                                        // h0 is data: no gradient beyond the first step
+      GRU_STAMP(9, stamp);
 #pragma unroll
       for (int j = 0; j < 16; ++j) { dd[j] = to_tf32(dd[j]); hp[j] = to_tf32(hp[j]); }
       put_kmajor16(DG, 0 + q * 4, r, dd);
@@ -388,7 +420,9 @@ gru_tc_bwd_kernel(const NetDev n, const float* __restrict__ gimg, const BatchDev
       put_kmajor16(DG, 32 + q * 4, r, ng);
       fence_async_smem();
       tc_fence_before();
+      GRU_STAMP(10, stamp);
       __syncthreads();
+      GRU_STAMP(11, stamp);
       if (tid == 0) {
         tc_fence_after();
         if (first) mbar_wait(bar_w, 0);
@@ -396,8 +430,10 @@ gru_tc_bwd_kernel(const NetDev n, const float* __restrict__ gimg, const BatchDev
         umma_commit(bar_m);
       }
       first = false;
+      GRU_STAMP(12, stamp);
       mbar_wait(bar_m, phase); phase ^= 1;
       tc_fence_after();
+      GRU_STAMP(13, stamp);
       {
         float t[16];
         tmem_ld16(tmem + lane_base + c0, t);
@@ -405,6 +441,7 @@ gru_tc_bwd_kernel(const NetDev n, const float* __restrict__ gimg, const BatchDev
 #pragma unroll
         for (int i = 0; i < 16; ++i) dh[i] = (dh[i] + t[i]) * m;               // hm = h_{l-1} * mask_l
       }
+      GRU_STAMP(14, stamp);
       tc_fence_before();
     }
   }
@@ -483,7 +520,7 @@ gru_tc_grad_kernel(const NetDev n, const float* __restrict__ gimg, const BatchDe
     {
       float x[16], hm[16];
       if (valid) {
-        const float m = b.masks[b.rows ? b.rows[p] : p];
+        const int gr = b.rows ? b.rows[p] : p;         // index first, mask (dependent) behind the plane loads
         ld_pl16(ws.X, (size_t)p, q * 4, x);
         if (l > 0) ld_pl16(ws.H, (size_t)(p - Nc), q * 4, hm);
         else ld_half16(h0 + (size_t)(b.seq_first ? b.seq_first[c] : c) * 64 + c0, hm);
@@ -491,6 +528,7 @@ gru_tc_grad_kernel(const NetDev n, const float* __restrict__ gimg, const BatchDe
         ld_pl16(ws.DR, (size_t)p, q * 4, dg3[0]);
         ld_pl16(ws.DZ, (size_t)p, q * 4, dg3[1]);
         ld_pl16(ws.DN, (size_t)p, q * 4, dg3[2]);
+        const float m = b.masks[gr];
 #pragma unroll
         for (int i = 0; i < 16; ++i) hm[i] = to_tf32(hm[i] * m);
       } else {
@@ -625,6 +663,9 @@ struct GruTimed {
     if (cudaEventCreate(&b) == cudaSuccess && cudaEventRecord(b, st) == cudaSuccess) g_gru_timed.push_back({a, b, cat});
   }
 };
+int debug_gru_cycles(long long* out16) {
+  return cudaMemcpyFromSymbol(out16, g_gru_cycles, sizeof(long long) * 16) == cudaSuccess ? 0 : MAPPO_ERR_CUDA;
+}
 int debug_gru_timing(int enable, double* ms_out, long long* n_out) {
   for (int i = 0; i < TG_N; ++i) { if (ms_out) ms_out[i] = 0.0; if (n_out) n_out[i] = 0; }
   for (const GruTimedLaunch& t : g_gru_timed) {

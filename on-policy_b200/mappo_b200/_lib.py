@@ -60,6 +60,7 @@ _SIGS = {
     "mappo_big_net": (_i32, [C.POINTER(NetDesc)]),
     "mappo_debug_big_timing": (_i32, [_i32, _P, _P]),
     "mappo_debug_gru_timing": (_i32, [_i32, _P, _P]),
+    "mappo_debug_gru_cycles": (_i32, [_P]),
     "mappo_debug_big_lin": (_i32, [_P, _i32, _P, _i32, _P, _P, _P, _P, _i32, _i32, _i32, _i32, _P]),
     "mappo_debug_big_grad": (_i32, [_P, _i32, _i32, _i32, _P, _i32, _i32, _i32, _P, _P, _i32, _P]),
     "mappo_debug_big_grad_splits": (_i32, [_i32, _i32, _i32, _i32]),

@@ -1,0 +1,15 @@
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -5 > gpurun_out/s34_alltests.log; tail -3 gpurun_out/s34_alltests.log
+for c in c3 c4; do
+timeout 600 python bench.py --config $c --steps 6 --warmup 3 --no-extras --cpu-iters 0 > gpurun_out/s34_$c.json 2> gpurun_out/s34_$c.err; python - $c <<'PY'
+import json, sys
+c = sys.argv[1]
+try:
+    l = json.loads(open(f'gpurun_out/s34_{c}.json').read().strip().splitlines()[-1])
+    pb = l['phase_breakdown_ms']; r = l['roofline']
+    print(c, l['ms_per_step'], l['value'], {k: round(v, 3) for k, v in pb.items() if k.endswith('_ms')}, r['kernel'][:30], r['frac'])
+    print('   ', {f: round(t['ms_total'] / max(t['launches'], 1) * 1000, 1) for f, t in r['pipeline_families'].items()})
+except Exception as e:
+    print(c, 'failed', e); print(open(f'gpurun_out/s34_{c}.err').read()[-1500:])
+PY
+done
