@@ -259,6 +259,7 @@ __device__ __forceinline__ void pol_step(const NetDev& n, int which, const PolCt
 
 }  // namespace mappo
 #include "rollout_mlp.cuh"
+#include "rollout_gru.cuh"       // warp-per-two-rows kernels of the recurrent policies
 #include "rollout_closed.cuh"
 namespace mappo {
 
@@ -427,6 +428,28 @@ int policy_step_launch(const NetDev* na, const NetDev* nc, const PolArgs& a, cud
       return check_launch("policy_step_fast_kernel");
     }
   }
+  {   // recurrent nets with a packed image: two rows per warp, state in registers (rollout_gru.cuh)
+    bool fast = true;
+    size_t fb = 0;
+    for (int w = 0; w < 2; ++w) {
+      const NetDev* n = w == 0 ? na : nc;
+      if (!n) continue;
+      if (!gru_fast_supported(*n) || !a.image[w] || !a.h_in[w]) fast = false;
+      else { const size_t b = gru_fast_smem_bytes(*n); fb = b > fb ? b : fb; }
+    }
+    if (fast && fb <= 227 * 1024) {
+      static thread_local SmemConfig configured_g_dev = {};
+      size_t& configured_g = configured_g_dev.slot();
+      if (fb > configured_g) {
+        if (cudaFuncSetAttribute(policy_step_gru_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fb) != cudaSuccess)
+          return check_launch("policy_step_gru_fast: cudaFuncSetAttribute");
+        configured_g = fb;
+      }
+      const dim3 grid((a.n_rows + kGRows - 1) / kGRows, (na && nc) ? 2 : 1);
+      policy_step_gru_fast_kernel<<<grid, kGT, fb, st>>>(na ? *na : ref, nc ? *nc : ref, a, na ? 0 : 1);
+      return check_launch("policy_step_gru_fast_kernel");
+    }
+  }
   size_t bytes = 0;
   for (const NetDev* n : {na, nc}) {
     if (!n) continue;
@@ -463,7 +486,21 @@ int rollout_persistent_launch(const NetDev& na, const NetDev& nc, const RolloutA
     rollout_fast_kernel<<<dim3((a.E + kFR - 1) / kFR, 2), kFT, fb, st>>>(na, nc, a);
     return check_launch("rollout_fast_kernel");
   }
-  if (a.share_agents > 0) { set_error("rollout: share_obs derived from obs is only built for the feed-forward path"); return MAPPO_ERR_UNSUPPORTED; }
+  if (gru_fast_supported(na) && gru_fast_supported(nc) && a.image[0] && a.image[1]) {
+    const size_t ba = gru_fast_smem_bytes(na), bc = gru_fast_smem_bytes(nc), fb = ba > bc ? ba : bc;
+    if (fb <= 227 * 1024) {
+      static thread_local SmemConfig configured_g_dev = {};
+      size_t& configured_g = configured_g_dev.slot();
+      if (fb > configured_g) {
+        if (cudaFuncSetAttribute(rollout_gru_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fb) != cudaSuccess)
+          return check_launch("rollout_gru_fast: cudaFuncSetAttribute");
+        configured_g = fb;
+      }
+      rollout_gru_fast_kernel<<<dim3((a.E + kGRows - 1) / kGRows, 2), kGT, fb, st>>>(na, nc, a);
+      return check_launch("rollout_gru_fast_kernel");
+    }
+  }
+  if (a.share_agents > 0) { set_error("rollout: share_obs derived from obs is only built for the feed-forward and the two-rows-per-warp recurrent path"); return MAPPO_ERR_UNSUPPORTED; }
   size_t bytes = 0;
   for (const NetDev* n : {&na, &nc}) {
     if (n->hid != 64) { set_error("rollout: hidden_size %d not built in the fused SIMT path (64 only)", n->hid); return MAPPO_ERR_UNSUPPORTED; }
@@ -512,10 +549,15 @@ int pack_rollout_launch(const NetDev& n, const float* params, float* image, cuda
     pack_fast_kernel<<<(make_fast_img(n).total + 255) / 256, 256, 0, st>>>(n, params, image);
     return check_launch("pack_fast_kernel");
   }
+  if (gru_fast_supported(n)) {            // recurrent nets: the feed-forward image + the gate matrices as [gate][k][lane][2]
+    pack_gru_fast_kernel<<<(make_gru_fast_img(n).total + 255) / 256, 256, 0, st>>>(n, params, image);
+    return check_launch("pack_gru_fast_kernel");
+  }
   pack_rollout_kernel<<<(n.g.total + 255) / 256, 256, 0, st>>>(n, params, image);
   return check_launch("pack_rollout_kernel");
 }
 int rollout_image_floats(const NetDev& n) {
+  if (gru_fast_supported(n)) return make_gru_fast_img(n).total;
   return fast_rollout_supported(n) ? make_fast_img(n).total : make_smem_w(n, true).total;
 }
 

@@ -53,11 +53,11 @@ __host__ __device__ inline bool fast_rollout_supported(const NetDev& n) {
   return !n.recurrent && n.hid == 64 && n.in_dim <= 64 && n.head_total <= 32;
 }
 
-__global__ void __launch_bounds__(256) pack_fast_kernel(const NetDev n, const float* __restrict__ p, float* __restrict__ img) {
-  const FastImg f = make_fast_img(n);
+// element i of the image (also the front part of the recurrent nets' image, rollout_gru.cuh)
+__device__ __forceinline__ float pack_fast_element(const NetDev& n, const FastImg& f, const float* __restrict__ p, int i) {
   const mappo_net_layout_t& g = n.g;
   const int in = n.in_dim;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < f.total; i += gridDim.x * blockDim.x) {
+  {
     float v = 0.f;
     if (i < f.w1) {                                       // feature-norm affine (only present when use_fn)
       const int t = i - f.fn_w;
@@ -85,8 +85,12 @@ __global__ void __launch_bounds__(256) pack_fast_kernel(const NetDev n, const fl
       const int a = i - f.bh;
       if (a < n.head_total) v = p[g.head_b + a];
     }
-    img[i] = v;
+    return v;
   }
+}
+__global__ void __launch_bounds__(256) pack_fast_kernel(const NetDev n, const float* __restrict__ p, float* __restrict__ img) {
+  const FastImg f = make_fast_img(n);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < f.total; i += gridDim.x * blockDim.x) img[i] = pack_fast_element(n, f, p, i);
 }
 
 __device__ __forceinline__ float warp_sum(float s) {

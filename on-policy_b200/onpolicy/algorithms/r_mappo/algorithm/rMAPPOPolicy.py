@@ -93,9 +93,10 @@ class R_MAPPOPolicy:
                     h_c_out = torch.empty(n_rows, self._recN, self._H, dtype=torch.float32, device=dev)
         img_a = img_c = None
         gemm = _lib.GEMM_TF32 if os.environ.get("MAPPO_B200_GEMM", "fp32") == "tf32" else _lib.GEMM_FP32
-        if not self._recurrent:
-            # feed-forward nets: hand the kernel the packed weight image (one TMA bulk copy per CTA, and the
-            # warp-per-two-rows rollout path).  Re-packed per call: the parameters may have been stepped in between.
+        if True:
+            # hand the kernel the packed weight image (one TMA bulk copy per CTA; feed-forward nets: the warp-per-row rollout path,
+            # recurrent hidden-64 nets: the two-rows-per-warp path of rollout_gru.cuh).  Re-packed per call: the parameters may
+            # have been stepped in between.
             # hidden >= 128 nets: the "image" is the workspace of the GEMM pipeline (packed weights + activations of n_rows)
             big = bool(lib.mappo_big_net(C.byref(self.actor.desc)))
             key = n_rows if big else 0
