@@ -404,6 +404,15 @@ int debug_pol_timing(long long* out16, int reset) {
 
 __global__ void counter_add_kernel(uint64_t* c, uint64_t inc) { *c += inc; }
 
+static int device_sm_count() {
+  static thread_local int sm[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& v = sm[dev & 63];
+  if (v == 0) { cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); if (v <= 0) v = 148; }
+  return v;
+}
+
 int policy_step_launch(const NetDev* na, const NetDev* nc, const PolArgs& a, cudaStream_t st) {
   const NetDev& ref = na ? *na : *nc;
   {   // feed-forward nets with a packed image: the warp-per-two-rows path (rollout_mlp.cuh)
@@ -435,7 +444,12 @@ int policy_step_launch(const NetDev* na, const NetDev* nc, const PolArgs& a, cud
       const NetDev* n = w == 0 ? na : nc;
       if (!n) continue;
       if (!gru_fast_supported(*n) || !a.image[w] || !a.h_in[w]) fast = false;
-      else { const size_t b = gru_fast_smem_bytes(*n); fb = b > fb ? b : fb; }
+    }
+    const int n_nets = (na && nc) ? 2 : 1;
+    const int warps = gru_fast_warps(a.n_rows, n_nets, device_sm_count());
+    for (int w = 0; w < 2 && fast; ++w) {
+      const NetDev* n = w == 0 ? na : nc;
+      if (n) { const size_t b = gru_fast_smem_bytes(*n, warps); fb = b > fb ? b : fb; }
     }
     if (fast && fb <= 227 * 1024) {
       static thread_local SmemConfig configured_g_dev = {};
@@ -445,8 +459,8 @@ int policy_step_launch(const NetDev* na, const NetDev* nc, const PolArgs& a, cud
           return check_launch("policy_step_gru_fast: cudaFuncSetAttribute");
         configured_g = fb;
       }
-      const dim3 grid((a.n_rows + kGRows - 1) / kGRows, (na && nc) ? 2 : 1);
-      policy_step_gru_fast_kernel<<<grid, kGT, fb, st>>>(na ? *na : ref, nc ? *nc : ref, a, na ? 0 : 1);
+      const dim3 grid((a.n_rows + 2 * warps - 1) / (2 * warps), n_nets);
+      policy_step_gru_fast_kernel<<<grid, 32 * warps, fb, st>>>(na ? *na : ref, nc ? *nc : ref, a, na ? 0 : 1);
       return check_launch("policy_step_gru_fast_kernel");
     }
   }
@@ -487,7 +501,8 @@ int rollout_persistent_launch(const NetDev& na, const NetDev& nc, const RolloutA
     return check_launch("rollout_fast_kernel");
   }
   if (gru_fast_supported(na) && gru_fast_supported(nc) && a.image[0] && a.image[1]) {
-    const size_t ba = gru_fast_smem_bytes(na), bc = gru_fast_smem_bytes(nc), fb = ba > bc ? ba : bc;
+    const int warps = gru_fast_warps(a.E, 2, device_sm_count());
+    const size_t ba = gru_fast_smem_bytes(na, warps), bc = gru_fast_smem_bytes(nc, warps), fb = ba > bc ? ba : bc;
     if (fb <= 227 * 1024) {
       static thread_local SmemConfig configured_g_dev = {};
       size_t& configured_g = configured_g_dev.slot();
@@ -496,7 +511,7 @@ int rollout_persistent_launch(const NetDev& na, const NetDev& nc, const RolloutA
           return check_launch("rollout_gru_fast: cudaFuncSetAttribute");
         configured_g = fb;
       }
-      rollout_gru_fast_kernel<<<dim3((a.E + kGRows - 1) / kGRows, 2), kGT, fb, st>>>(na, nc, a);
+      rollout_gru_fast_kernel<<<dim3((a.E + 2 * warps - 1) / (2 * warps), 2), 32 * warps, fb, st>>>(na, nc, a);
       return check_launch("rollout_gru_fast_kernel");
     }
   }

@@ -16,9 +16,8 @@
 
 namespace mappo {
 
-constexpr int kGW = 16;                  // warps per CTA
-constexpr int kGT = 32 * kGW;            // threads per CTA
-constexpr int kGRows = 2 * kGW;          // rows per CTA
+constexpr int kGW = 16;                  // warps per CTA at most (the launch picks 2..16 so that the CTAs of both nets cover the SMs)
+constexpr int kGT = 32 * kGW;            // threads per CTA at most
 constexpr int kGWarpScratch = 2 * 192;   // floats per warp: per row two 64-float activation buffers + the masked state
 
 struct GruFastImg {
@@ -103,6 +102,42 @@ __device__ __forceinline__ void fast_layer2(const float* __restrict__ X0, const 
     Y1[lane + 32] = fmaf(d1 * rs, gm[lane + 32], be[lane + 32]);
   }
   __syncwarp();
+}
+
+// r and z gates of both rows in ONE k loop (the activations are read once for two gates, 16 independent accumulators):
+// acc[gate][row][part (0 = x, 1 = h)][column half]; the gate matrices are 4096 floats apart in the image
+__device__ __forceinline__ void gru_gates_rz(const float* __restrict__ F0, const float* __restrict__ F1, const float* __restrict__ H0,
+                                             const float* __restrict__ H1, const float* __restrict__ Wi, const float* __restrict__ Wh,
+                                             int lane, float (&acc)[2][2][2][2]) {
+#pragma unroll
+  for (int gt = 0; gt < 2; ++gt)
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int s = 0; s < 2; ++s) acc[gt][r][s][0] = acc[gt][r][s][1] = 0.f;
+  const float2* wi = reinterpret_cast<const float2*>(Wi) + lane;
+  const float2* wh = reinterpret_cast<const float2*>(Wh) + lane;
+  const float4* f0 = reinterpret_cast<const float4*>(F0);
+  const float4* f1 = reinterpret_cast<const float4*>(F1);
+  const float4* h0 = reinterpret_cast<const float4*>(H0);
+  const float4* h1 = reinterpret_cast<const float4*>(H1);
+#pragma unroll 1
+  for (int q = 0; q < 16; ++q) {
+    const float4 x0 = f0[q], x1 = f1[q], y0 = h0[q], y1 = h1[q];
+    const float xs0[4] = {x0.x, x0.y, x0.z, x0.w}, xs1[4] = {x1.x, x1.y, x1.z, x1.w};
+    const float ys0[4] = {y0.x, y0.y, y0.z, y0.w}, ys1[4] = {y1.x, y1.y, y1.z, y1.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+#pragma unroll
+      for (int gt = 0; gt < 2; ++gt) {
+        const float2 u = wi[gt * 2048 + (4 * q + t) * 32], v = wh[gt * 2048 + (4 * q + t) * 32];
+        acc[gt][0][0][0] = fmaf(xs0[t], u.x, acc[gt][0][0][0]); acc[gt][0][0][1] = fmaf(xs0[t], u.y, acc[gt][0][0][1]);
+        acc[gt][1][0][0] = fmaf(xs1[t], u.x, acc[gt][1][0][0]); acc[gt][1][0][1] = fmaf(xs1[t], u.y, acc[gt][1][0][1]);
+        acc[gt][0][1][0] = fmaf(ys0[t], v.x, acc[gt][0][1][0]); acc[gt][0][1][1] = fmaf(ys0[t], v.y, acc[gt][0][1][1]);
+        acc[gt][1][1][0] = fmaf(ys1[t], v.x, acc[gt][1][1][0]); acc[gt][1][1][1] = fmaf(ys1[t], v.y, acc[gt][1][1][1]);
+      }
+    }
+  }
 }
 
 // x part and state part of one gate for both rows: acc[row][part (0 = x, 1 = h)][column half]
@@ -275,25 +310,21 @@ __device__ __forceinline__ void gru_fast_step(const NetDev& n, int which, const 
   const float* F1 = c.buf[1][xi];
   float rgate[2][2], zgate[2][2];
   {
+    float acc2[2][2][2][2];
+    gru_gates_rz(F0, F1, c.buf[0][2], c.buf[1][2], sW + c.m.wih, sW + c.m.whh, lane, acc2);
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int col = lane + 32 * j;
+        const float gir = acc2[0][r][0][j] + sW[c.m.bih + col];
+        rgate[r][j] = sigmoidf_((acc2[0][r][1][j] + gir) + sW[c.m.bhh + col]);
+        const float giz = acc2[1][r][0][j] + sW[c.m.bih + 64 + col];
+        zgate[r][j] = sigmoidf_((acc2[1][r][1][j] + giz) + sW[c.m.bhh + 64 + col]);
+      }
+  }
+  {
     float acc[2][2][2];
-    gru_gate2(F0, F1, c.buf[0][2], c.buf[1][2], sW + c.m.wih, sW + c.m.whh, lane, acc);
-#pragma unroll
-    for (int r = 0; r < 2; ++r)
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int col = lane + 32 * j;
-        const float gi = acc[r][0][j] + sW[c.m.bih + col];
-        rgate[r][j] = sigmoidf_((acc[r][1][j] + gi) + sW[c.m.bhh + col]);
-      }
-    gru_gate2(F0, F1, c.buf[0][2], c.buf[1][2], sW + c.m.wih + 4096, sW + c.m.whh + 4096, lane, acc);
-#pragma unroll
-    for (int r = 0; r < 2; ++r)
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int col = lane + 32 * j;
-        const float gi = acc[r][0][j] + sW[c.m.bih + 64 + col];
-        zgate[r][j] = sigmoidf_((acc[r][1][j] + gi) + sW[c.m.bhh + 64 + col]);
-      }
     gru_gate2(F0, F1, c.buf[0][2], c.buf[1][2], sW + c.m.wih + 8192, sW + c.m.whh + 8192, lane, acc);
 #pragma unroll
     for (int r = 0; r < 2; ++r)
@@ -363,8 +394,17 @@ __device__ __forceinline__ GruFastCtx gru_fast_setup(const NetDev& n, float* sme
   return c;
 }
 
-inline size_t gru_fast_smem_bytes(const NetDev& n) {
-  return (size_t)(make_gru_fast_img(n).total + kGW * kGWarpScratch) * sizeof(float);
+inline size_t gru_fast_smem_bytes(const NetDev& n, int warps) {
+  return (size_t)(make_gru_fast_img(n).total + warps * kGWarpScratch) * sizeof(float);
+}
+// warps per CTA (2 rows each): as few as cover the rows with one CTA per SM for both nets -- rows never interact and a warp's step is one
+// long dependent chain, so spreading the warps over the SMs beats stacking them on a scheduler
+inline int gru_fast_warps(int n_rows, int n_nets, int sm_count) {
+  const int ctas = sm_count / (n_nets > 0 ? n_nets : 1) > 0 ? sm_count / (n_nets > 0 ? n_nets : 1) : 1;
+  int w = (n_rows + 2 * ctas - 1) / (2 * ctas);
+  if (w < 2) w = 2;
+  if (w > kGW) w = kGW;
+  return w;
 }
 
 // one step (mappo_policy_step) of recurrent nets: state in from a.h_in, out to a.h_out (no done reset here: the caller's insert does it)
@@ -375,7 +415,7 @@ policy_step_gru_fast_kernel(const NetDev na, const NetDev nc, const PolArgs a, i
   const int tid = threadIdx.x, lane = tid & 31;
   const int which = first_net + blockIdx.y;
   const NetDev& n = which == 0 ? na : nc;
-  const int row0 = blockIdx.x * kGRows + 2 * (tid >> 5);
+  const int row0 = (blockIdx.x * (blockDim.x >> 5) + (tid >> 5)) * 2;
   int g[2];
   float x[2][2], h[2][2], mask[2];
 #pragma unroll
@@ -406,7 +446,7 @@ rollout_gru_fast_kernel(const NetDev na, const NetDev nc, const RolloutArgs a) {
   const int which = blockIdx.y;
   const NetDev& n = which == 0 ? na : nc;
   const int E = a.E, T = a.T, in = n.in_dim;
-  const int row0 = blockIdx.x * kGRows + 2 * (tid >> 5);
+  const int row0 = (blockIdx.x * (blockDim.x >> 5) + (tid >> 5)) * 2;
   float* store_in = which == 0 ? a.obs : a.share_obs;
   const float* feed_in = which == 0 ? a.f_obs : a.f_share;
   float* h_store = which == 0 ? a.h_actor : a.h_critic;
