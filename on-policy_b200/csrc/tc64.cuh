@@ -221,6 +221,13 @@ __device__ __forceinline__ void ld_pl16(const float* __restrict__ plane, size_t 
     v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
   }
 }
+// the same load, issued where it is written (asm volatile: the compiler may not sink it towards its first use -- a prefetch)
+__device__ __forceinline__ void ld_pl16_pinned(const float* __restrict__ plane, size_t p, int chunk0, float* v) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v[4 * j]), "=f"(v[4 * j + 1]), "=f"(v[4 * j + 2]), "=f"(v[4 * j + 3]) : "l"(plane + pl_off(p, chunk0 + j)));
+}
 __device__ __forceinline__ void st_pl16(float* __restrict__ plane, size_t p, int chunk0, const float* v) {
 #pragma unroll
   for (int j = 0; j < 4; ++j)

@@ -289,11 +289,24 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
   const uint32_t aW2T = smem_u32(sImg + im.w2t), aWhT = smem_u32(sImg + im.wht);
   constexpr uint32_t ROWB = kTM * 16;                  // chunk stride of a 128-row K-major staging tile
 
+  // TC_HEAD / TC_BASE_BWD: this thread's 32 plane values of a tile travel in registers, fetched one tile (heads) or half a tile (base
+  // backward) before their use, so the global-memory latency does not sit between two tiles
+  float pref[32];
+  auto fetch_plane_row = [&](int tile, bool ok) {
+    const size_t pp = (size_t)tile * kTM + r;
+    if (ok) { ld_pl16_pinned(plane_in, pp, wg * 8, pref); ld_pl16_pinned(plane_in, pp, wg * 8 + 4, pref + 16); }
+    else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) pref[i] = 0.f;
+    }
+  };
+  if (MODE == TC_HEAD) fetch_plane_row(blockIdx.x, gr_next >= 0);
   TC_STAMP(1);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int p = tile * kTM + r;
     const int gr = gr_next;
     gr_next = row_of(tile + gridDim.x);
+    if (MODE == TC_BASE_BWD) fetch_plane_row(tile, p < b.n_rows && gr >= 0);      // dL/dxhat2 of this tile, used in S9
     float mu0 = 0.f, rs0 = 1.f;
     const RowIn rin = load_row_in(n, b, (wg == 0 && (MODE == TC_FULL || MODE == TC_HEAD)) ? gr : -1);      // loss inputs (warpgroup 0 owns the loss): in flight
                                                                  // during the whole forward pass
@@ -428,11 +441,9 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
     } else {
       // ---- TC_HEAD: the GRU state of this position -> LayerNorm (rnn.norm, rnn.py:79) -> xhat (K-major staging + transposed) ----
       float a[32];
-      if (gr >= 0) { ld_pl16(plane_in, (size_t)p, wg * 8, a); ld_pl16(plane_in, (size_t)p, wg * 8 + 4, a + 16); }
-      else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) a[i] = 0.f;
-      }
+      for (int i = 0; i < 32; ++i) a[i] = pref[i];
+      fetch_plane_row(tile + gridDim.x, gr_next >= 0);           // next tile's rows: in flight under this tile
       ln_stats_pair(a, px, mu2, rs2);
 #pragma unroll
       for (int i = 0; i < 32; ++i) a[i] = to_tf32((a[i] - mu2) * rs2);
@@ -530,11 +541,8 @@ update_mlp_tc_kernel(const NetDev n, const float* __restrict__ params, const flo
     {
       float d[32];
       if (MODE == TC_BASE_BWD) {                           // dL/dxhat2 from the GRU input projection (update_gru_tc.cu)
-        if (p < b.n_rows && gr >= 0) { ld_pl16(plane_in, (size_t)p, wg * 8, d); ld_pl16(plane_in, (size_t)p, wg * 8 + 4, d + 16); }
-        else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) d[i] = 0.f;
-        }
+        for (int i = 0; i < 32; ++i) d[i] = pref[i];
       } else {
         mbar_wait(bar_m, phase); phase ^= 1; TC_STAMP(9);
         tc_fence_after();
