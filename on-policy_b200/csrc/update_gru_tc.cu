@@ -512,31 +512,40 @@ gru_tc_grad_kernel(const NetDev n, const float* __restrict__ gimg, const BatchDe
   const float* h0 = n.is_critic ? b.h0_critic : b.h0_actor;
   uint32_t phase = 0;
   bool first_tile = true;
+  // The six plane rows of a tile travel in registers (pinned loads): x, hm are consumed at the top of the tile, dg3 / rg by the three gate
+  // passes -- all dead once the last pass has written its operand tiles, so the NEXT tile's rows are fetched there and land under the
+  // last pass's MMAs and the result read-out (one exposed round trip per CTA instead of one per tile).
+  float x[16], hm[16], rg[16], dg3[3][16];
+  float mk = 0.f;
+  auto fetch_tile = [&](int tile) {
+    const int p = tile * kTM + r;
+    if (tile < n_tiles && p < P) {
+      const int l = p / Nc, c = p - l * Nc;
+      const int gr = b.rows ? b.rows[p] : p;           // index first, mask (dependent) behind the plane loads
+      ld_pl16_pinned(ws.X, (size_t)p, q * 4, x);
+      if (l > 0) ld_pl16_pinned(ws.H, (size_t)(p - Nc), q * 4, hm);
+      else ld_half16(h0 + (size_t)(b.seq_first ? b.seq_first[c] : c) * 64 + c0, hm);
+      ld_pl16_pinned(ws.R, (size_t)p, q * 4, rg);
+      ld_pl16_pinned(ws.DR, (size_t)p, q * 4, dg3[0]);
+      ld_pl16_pinned(ws.DZ, (size_t)p, q * 4, dg3[1]);
+      ld_pl16_pinned(ws.DN, (size_t)p, q * 4, dg3[2]);
+      mk = b.masks[gr];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { x[i] = 0.f; hm[i] = 0.f; rg[i] = 0.f; dg3[0][i] = dg3[1][i] = dg3[2][i] = 0.f; }
+      mk = 0.f;
+    }
+  };
+  fetch_tile(blockIdx.x);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int p = tile * kTM + r;
     const bool valid = p < P;
-    const int l = valid ? p / Nc : 0, c = valid ? p - l * Nc : 0;
-    float rg[16], dg3[3][16];                       // every global load of the tile is issued up front: one exposed round trip
     {
-      float x[16], hm[16];
-      if (valid) {
-        const int gr = b.rows ? b.rows[p] : p;         // index first, mask (dependent) behind the plane loads
-        ld_pl16(ws.X, (size_t)p, q * 4, x);
-        if (l > 0) ld_pl16(ws.H, (size_t)(p - Nc), q * 4, hm);
-        else ld_half16(h0 + (size_t)(b.seq_first ? b.seq_first[c] : c) * 64 + c0, hm);
-        ld_pl16(ws.R, (size_t)p, q * 4, rg);
-        ld_pl16(ws.DR, (size_t)p, q * 4, dg3[0]);
-        ld_pl16(ws.DZ, (size_t)p, q * 4, dg3[1]);
-        ld_pl16(ws.DN, (size_t)p, q * 4, dg3[2]);
-        const float m = b.masks[gr];
+      float t[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) hm[i] = to_tf32(hm[i] * m);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) { x[i] = 0.f; hm[i] = 0.f; rg[i] = 0.f; dg3[0][i] = dg3[1][i] = dg3[2][i] = 0.f; }
-      }
+      for (int i = 0; i < 16; ++i) t[i] = to_tf32(hm[i] * mk);
       put_transposed16(XHT, kXS, r, c0, x);
-      put_transposed16(XHT, kXS, r, 72 + c0, hm);
+      put_transposed16(XHT, kXS, r, 72 + c0, t);
     }
 #pragma unroll
     for (int g = 0; g < 3; ++g) {
@@ -549,6 +558,7 @@ gru_tc_grad_kernel(const NetDev n, const float* __restrict__ gimg, const BatchDe
 #pragma unroll
         for (int i = 0; i < 16; ++i) dg[i] = to_tf32(dg[i] * rg[i]);
         put_transposed16(DHT, kS65, r, c0, dg);
+        fetch_tile(tile + gridDim.x);                  // every register of this tile's rows is dead: next tile's rows in flight
       }
       fence_async_smem();
       tc_fence_before();
