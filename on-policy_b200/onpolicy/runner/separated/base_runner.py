@@ -60,8 +60,7 @@ class Runner(object):
             from onpolicy.algorithms.happo.policy import HAPPO_Policy as Policy_
         elif self.algorithm_name == "hatrpo":
             raise NotImplementedError("HATRPO (trust-region step with conjugate gradients) is outside the hot path (SURVEY 2.1)")
-        if self.use_render:
-            import imageio  # noqa: F401
+        if self.use_render:                                     # (imageio is imported where the gif is written: render())
             self.run_dir = config["run_dir"]
             self.gif_dir = str(self.run_dir / "gifs")
             os.makedirs(self.gif_dir, exist_ok=True)

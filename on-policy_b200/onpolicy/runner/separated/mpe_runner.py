@@ -130,3 +130,66 @@ class MPERunner(Runner):
             infos.append({"eval_average_episode_rewards": avg})
             print("eval average episode rewards of agent%i: " % agent_id + str(avg))
         self.log_train(infos, total_num_steps)
+
+    @torch.no_grad()
+    def render(self):
+        """reference :241-313: like the shared runner's render, every agent acting with its own policy."""
+        import time
+        envs, a = self.envs, self.all_args
+        n, M = self.n_rollout_threads, self.num_agents
+        dev = self.buffer[0].device
+        frames = []
+
+        def show():
+            if a.save_gifs:
+                frames.append(envs.render("rgb_array")[0][0])
+            else:
+                envs.render("human")
+
+        for _ in range(a.render_episodes):
+            obs = envs.reset()
+            show()
+            h = [torch.zeros(n, self.recurrent_N, self.hidden_size, device=dev) for _ in range(M)]
+            masks = torch.ones(n, M, 1, device=dev)
+            episode_rewards = []
+            for _step in range(self.episode_length):
+                t0 = time.time()
+                parts = []
+                for agent_id in range(M):
+                    self.trainer[agent_id].prep_rollout()
+                    mine = np.stack([np.asarray(o[agent_id], dtype=np.float32) for o in obs])
+                    act, h[agent_id] = self.trainer[agent_id].policy.act(mine, h[agent_id], masks[:, agent_id], deterministic=True)
+                    a_np = _t2n(act)
+                    space = envs.action_space[agent_id]
+                    if space.__class__.__name__ == "MultiDiscrete":
+                        parts.append(np.concatenate([np.eye(space.high[i] + 1)[a_np[:, i]] for i in range(space.shape)], 1))
+                    elif space.__class__.__name__ == "Discrete":
+                        parts.append(np.squeeze(np.eye(space.n)[a_np], 1))
+                    else:
+                        raise NotImplementedError
+                obs, rewards, dones, _ = envs.step([[parts[m][i] for m in range(M)] for i in range(n)])
+                episode_rewards.append(rewards)
+                done = torch.from_numpy(np.asarray(dones, dtype=bool)).to(dev)
+                masks = torch.ones(n, M, 1, device=dev)
+                masks[done] = 0.0
+                for agent_id in range(M):
+                    h[agent_id] = h[agent_id].clone()
+                    h[agent_id][done[:, agent_id]] = 0.0
+                show()
+                if a.save_gifs:
+                    elapsed = time.time() - t0
+                    if elapsed < a.ifi:
+                        time.sleep(a.ifi - elapsed)
+            rew = np.array(episode_rewards)
+            for agent_id in range(M):
+                print("eval average episode rewards of agent%i: " % agent_id + str(np.mean(np.sum(rew[:, :, agent_id], axis=0))))
+        if a.save_gifs:
+            import os
+            gif_dir = getattr(self, "gif_dir", None) or str(self.run_dir / "gifs")
+            os.makedirs(gif_dir, exist_ok=True)
+            try:
+                import imageio
+                imageio.mimsave(gif_dir + "/render.gif", frames, duration=a.ifi)
+            except ImportError:
+                np.savez_compressed(gif_dir + "/render.npz", frames=np.asarray(frames))
+

@@ -125,3 +125,56 @@ class MPERunner(Runner):
         avg = float(np.mean(np.sum(np.array(rewards_log), axis=0)))
         print("eval average episode rewards of agent: " + str(avg))
         self.log_env({"eval_average_episode_rewards": [avg]}, total_num_steps)
+
+    @torch.no_grad()
+    def render(self):
+        """reference :185-245: `render_episodes` deterministic episodes on self.envs; frames from envs.render('rgb_array') go to
+        <run_dir>/gifs/render.gif when --save_gifs (imageio, as in the reference; without it the frames are kept as render.npz),
+        otherwise envs.render('human') is called every step.  Prints the reference's average-episode-reward line."""
+        envs, a = self.envs, self.all_args
+        n, dev = self.n_rollout_threads, self.buffer.device
+        frames = []
+
+        def show():
+            if a.save_gifs:
+                frames.append(envs.render("rgb_array")[0][0])
+            else:
+                envs.render("human")
+
+        for _ in range(a.render_episodes):
+            obs = envs.reset()
+            show()
+            h = torch.zeros(n * self.num_agents, self.recurrent_N, self.hidden_size, device=dev)
+            masks = torch.ones(n * self.num_agents, 1, device=dev)
+            episode_rewards = []
+            for _step in range(self.episode_length):
+                t0 = time.time()
+                self.trainer.prep_rollout()
+                action, h = self.trainer.policy.act(np.asarray(obs).reshape(n * self.num_agents, -1), h, masks, deterministic=True)
+                actions = _t2n(action).reshape(n, self.num_agents, -1)
+                obs, rewards, dones, _ = envs.step(self._one_hot_actions(actions))
+                episode_rewards.append(rewards)
+                done = torch.from_numpy(np.asarray(dones, dtype=bool)).to(dev).reshape(-1)
+                h = h.clone()
+                h[done] = 0.0
+                masks = torch.ones(n * self.num_agents, 1, device=dev)
+                masks[done] = 0.0
+                show()
+                if a.save_gifs:
+                    elapsed = time.time() - t0
+                    if elapsed < a.ifi:
+                        time.sleep(a.ifi - elapsed)
+            print("average episode rewards is: " + str(np.mean(np.sum(np.array(episode_rewards), axis=0))))
+        if a.save_gifs:
+            self._save_frames(frames, a.ifi)
+
+    def _save_frames(self, frames, ifi):
+        import os
+        gif_dir = getattr(self, "gif_dir", None) or str(self.run_dir / "gifs")
+        os.makedirs(gif_dir, exist_ok=True)
+        try:
+            import imageio
+            imageio.mimsave(gif_dir + "/render.gif", frames, duration=ifi)
+        except ImportError:
+            np.savez_compressed(gif_dir + "/render.npz", frames=np.asarray(frames))
+

@@ -40,6 +40,12 @@ class FakeVecEnv:
         infos = [[{"individual_reward": float(rew[n, m, 0])} for m in range(M)] for n in range(N)]
         return self._obs(), rew, done, infos
 
+    def render(self, mode="human"):
+        self.render_calls = getattr(self, "render_calls", 0) + 1
+        if mode == "rgb_array":                                           # [thread][viewer] frames like the MPE wrappers
+            return [[np.full((4, 5, 3), self.t, dtype=np.uint8)] for _ in range(self.cfg.n_rollout_threads)]
+        return None
+
     def close(self):
         pass
 
@@ -223,6 +229,34 @@ def test_mpe_runners_evaluate(tmp_path, separated, capsys):
     if sc is not None:
         assert any("eval_average_episode_rewards" in k for k in sc)
     runner.writter.close()
+
+
+@pytest.mark.parametrize("separated", [False, True])
+def test_mpe_runners_render(tmp_path, separated, capsys):
+    """use_render (scripts/render/render_mpe.py): deterministic episodes, one frame per reset and per step, written under
+    <run_dir>/gifs with --save_gifs (shared :185-245, separated :241-313); 'human' mode just calls envs.render every step."""
+    if separated:
+        from onpolicy.runner.separated.mpe_runner import MPERunner
+    else:
+        from onpolicy.runner.shared.mpe_runner import MPERunner
+    cfg = O.PathConfig(episode_length=5, n_rollout_threads=1, num_agents=2, obs_dim=6, share_obs_dim=12, act_dims=(3,), ppo_epoch=1)
+    for save in (True, False):
+        env = FakeVecEnv(cfg, separated=separated)
+        c = _config(cfg, tmp_path / ("gif" if save else "human"), env, share_policy=not separated, use_render=True, save_gifs=save,
+                    render_episodes=2, ifi=0.0, n_render_rollout_threads=1)
+        (tmp_path / ("gif" if save else "human")).mkdir(exist_ok=True)
+        runner = MPERunner(c)
+        runner.render()
+        assert env.render_calls == 2 * (cfg.episode_length + 1)
+        assert env.last_actions is not None and env.last_actions.shape[:2] == (1, 2)
+        if save:
+            gdir = tmp_path / "gif" / "gifs"
+            files = sorted(f.name for f in gdir.iterdir())
+            assert files and files[0] in ("render.gif", "render.npz")
+            if files[0] == "render.npz":
+                assert np.load(gdir / "render.npz")["frames"].shape == (2 * (cfg.episode_length + 1), 4, 5, 3)
+    out = capsys.readouterr().out
+    assert ("average episode rewards" in out)
 
 
 def test_hanabi_forward_runner_matches_reference(tmp_path):
