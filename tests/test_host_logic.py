@@ -102,6 +102,10 @@ def test_tensor_core_build_selection_per_net_family():
     assert lib.mappo_tf32_supported(C.byref(desc(100, 64, 1, 1))) == 0                  # in_dim > 63: fp32 kernels only
     assert lib.mappo_tf32_supported(C.byref(desc(30, 64, 2, 1))) == 0                   # layer_N 2
     assert lib.mappo_tf32_supported(C.byref(desc(40, 512, 2, 0, (20,)))) == 1           # c5 widths: GEMM pipeline
+    # rollout weight image of recurrent hidden-64 nets (rollout_gru.cuh): the feed-forward image + 2 x 3 gate matrices [k][lane][2] +
+    # biases + rnn.norm; c3's actor: fn 2 x 24, fc1 24 x 64 + 3 x 64, fc2 64 x 64 + 3 x 64, heads 64 x 16 + 16 = 7104 floats
+    assert lib.mappo_rollout_image_floats(C.byref(desc(21, 64, 1, 1, (5, 10)))) == 7104 + 2 * 3 * 64 * 64 + 2 * 192 + 2 * 64
+    assert lib.mappo_rollout_image_floats(C.byref(desc(21, 64, 1, 0, (5, 10)))) == 7104
     gru = desc(30, 64, 1, 1, (9,))
     rows = 5120
     ws_fp32 = lib.mappo_update_workspace_floats(C.byref(gru), rows, _lib.GEMM_FP32)
